@@ -1,0 +1,202 @@
+"""Host-side mirror of ChameleonRT's ``RenderBackend`` for the CUDA wavefront path tracer.
+
+``RenderCUDA`` has the reference's backend surface (util/render_backend.h:12-32): ``name()``,
+``initialize(fb_width, fb_height)``, ``set_scene(scene)``,
+``render(pos, dir, up, fovy, camera_changed, readback_framebuffer) -> RenderStats`` and the
+public ``img`` / ``samples_per_pixel`` members — bound with ctypes to the C ABI of
+``include/crt_cuda.h`` (``libcrt_cuda_core.so``). The C++ twin that ChameleonRT itself loads is
+``backends/cuda/render_cuda.cpp``; both go through exactly the same entry points.
+
+There is no CPU fallback: if the CUDA extension is missing or no GPU is usable, construction
+raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from .scene import CRenderStats, CScene, RenderStats, Scene
+
+_CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+_LIB_PATH = os.path.join(_CSRC, "libcrt_cuda_core.so")
+_lib: Optional[C.CDLL] = None
+
+STAGE_NAMES = ("raygen", "traverse_closest", "shade", "traverse_any", "nee_resolve", "resolve", "frame")
+COUNTER_NAMES = ("closest_rays", "occlusion_rays", "kernel_launches", "nodes_visited", "tris_tested", "paths")
+SCENE_INFO_NAMES = ("triangles", "bvh8_nodes", "bvh8_depth", "bvh_build_ms", "node_bytes", "triangle_bytes")
+
+# Every symbol include/crt_cuda.h declares (tests check the library exports all of them).
+C_ABI_SYMBOLS = (
+    "crtc_last_error", "crtc_name", "crtc_create", "crtc_destroy", "crtc_set_option", "crtc_set_stream",
+    "crtc_initialize", "crtc_set_scene", "crtc_render", "crtc_read_accum", "crtc_get_stage_times",
+    "crtc_get_counters", "crtc_get_scene_info", "crtc_trace_closest", "crtc_trace_any", "crtc_bench_trace",
+    "crtc_local_buffers", "crtc_assemble_rank", "crtc_read_img",
+)
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load_lib() -> C.CDLL:
+    """Loads libcrt_cuda_core.so (built in-tree by ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(
+            f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). The CUDA backend has no CPU fallback.")
+    lib = C.CDLL(_LIB_PATH)
+    fp = C.POINTER(C.c_float)
+    vp = C.c_void_p
+    lib.crtc_last_error.restype = C.c_char_p
+    lib.crtc_name.restype = C.c_char_p
+    lib.crtc_create.argtypes = [C.POINTER(vp), C.c_int]
+    lib.crtc_destroy.argtypes = [vp]
+    lib.crtc_destroy.restype = None
+    lib.crtc_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    lib.crtc_set_stream.argtypes = [vp, vp]
+    lib.crtc_initialize.argtypes = [vp, C.c_int, C.c_int]
+    lib.crtc_set_scene.argtypes = [vp, C.POINTER(CScene)]
+    lib.crtc_render.argtypes = [vp, fp, fp, fp, C.c_float, C.c_int, C.c_int, vp, C.POINTER(CRenderStats)]
+    lib.crtc_read_accum.argtypes = [vp, vp]
+    lib.crtc_read_img.argtypes = [vp, vp]
+    lib.crtc_get_stage_times.argtypes = [vp, vp, C.c_int]
+    lib.crtc_get_counters.argtypes = [vp, vp, C.c_int]
+    lib.crtc_get_scene_info.argtypes = [vp, vp, C.c_int]
+    lib.crtc_trace_closest.argtypes = [vp, vp, C.c_uint64, vp]
+    lib.crtc_trace_any.argtypes = [vp, vp, C.c_uint64, vp]
+    lib.crtc_bench_trace.argtypes = [vp, vp, C.c_uint64, C.c_int, C.c_int, fp]
+    lib.crtc_local_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint32)]
+    lib.crtc_assemble_rank.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    _lib = lib
+    return lib
+
+
+def _vec3(v):
+    a = np.ascontiguousarray(v, dtype=np.float32).reshape(3)
+    return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class RenderCUDA:
+    """``RenderBackend`` implemented by the B200 wavefront path tracer."""
+
+    def __init__(self, device: int = 0, max_depth: int = 5, rank: int = 0, world_size: int = 1,
+                 count_traversal: bool = False, bvh_threads: int = 0, stream: Optional[int] = None):
+        self.lib = load_lib()
+        self.h = C.c_void_p()
+        self._check(self.lib.crtc_create(C.byref(self.h), device))
+        self.device = device
+        self.rank, self.world_size = rank, world_size
+        self.max_depth = max_depth
+        for key, val in (("max_depth", max_depth), ("world_size", world_size), ("rank", rank),
+                         ("count_traversal", int(count_traversal)), ("bvh_threads", bvh_threads)):
+            self._check(self.lib.crtc_set_option(self.h, key.encode(), val))
+        if stream is not None:
+            self._check(self.lib.crtc_set_stream(self.h, C.c_void_p(stream)))
+        self.width = self.height = 0
+        self.samples_per_pixel = 1
+        self.img: Optional[np.ndarray] = None
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise RuntimeError(self.lib.crtc_last_error().decode())
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.crtc_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- RenderBackend ----
+    def name(self) -> str:
+        return self.lib.crtc_name().decode()
+
+    def initialize(self, fb_width: int, fb_height: int) -> None:
+        self._check(self.lib.crtc_initialize(self.h, fb_width, fb_height))
+        self.width, self.height = fb_width, fb_height
+        self.img = np.zeros((fb_height, fb_width), dtype=np.uint32)
+
+    def set_scene(self, scene: Scene) -> None:
+        ms = scene.to_c()
+        self.samples_per_pixel = scene.samples_per_pixel
+        self._check(self.lib.crtc_set_scene(self.h, C.byref(ms.c)))
+
+    def render(self, pos, dir, up, fovy: float, camera_changed: bool, readback_framebuffer: bool = True) -> RenderStats:
+        _p, pp = _vec3(pos)
+        _d, dp = _vec3(dir)
+        _u, up_ = _vec3(up)
+        st = CRenderStats()
+        img_ptr = self.img.ctypes.data if (readback_framebuffer and self.img is not None) else None
+        self._check(self.lib.crtc_render(self.h, pp, dp, up_, C.c_float(fovy), 1 if camera_changed else 0,
+                                         1 if readback_framebuffer else 0, img_ptr, C.byref(st)))
+        return RenderStats(st.render_time, st.rays_per_second, st.num_rays)
+
+    # ---- extra exports ----
+    def read_accum(self) -> np.ndarray:
+        out = np.zeros((self.height, self.width, 3), dtype=np.float32)
+        self._check(self.lib.crtc_read_accum(self.h, out.ctypes.data))
+        return out
+
+    def read_img(self) -> np.ndarray:
+        out = np.zeros((self.height, self.width), dtype=np.uint32)
+        self._check(self.lib.crtc_read_img(self.h, out.ctypes.data))
+        return out
+
+    def stage_times(self) -> dict:
+        a = np.zeros(len(STAGE_NAMES), dtype=np.float32)
+        n = self.lib.crtc_get_stage_times(self.h, a.ctypes.data, len(a))
+        return {STAGE_NAMES[i]: float(a[i]) for i in range(n)}
+
+    def counters(self) -> dict:
+        a = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
+        n = self.lib.crtc_get_counters(self.h, a.ctypes.data, len(a))
+        return {COUNTER_NAMES[i]: int(a[i]) for i in range(n)}
+
+    def scene_info(self) -> dict:
+        a = np.zeros(len(SCENE_INFO_NAMES), dtype=np.float64)
+        n = self.lib.crtc_get_scene_info(self.h, a.ctypes.data, len(a))
+        return {SCENE_INFO_NAMES[i]: float(a[i]) for i in range(n)}
+
+    def trace_closest(self, rays: np.ndarray) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        hits = np.zeros((rays.shape[0], 4), dtype=np.float32)
+        self._check(self.lib.crtc_trace_closest(self.h, rays.ctypes.data, rays.shape[0], hits.ctypes.data))
+        return hits
+
+    def trace_any(self, rays: np.ndarray) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        occ = np.zeros(rays.shape[0], dtype=np.uint8)
+        self._check(self.lib.crtc_trace_any(self.h, rays.ctypes.data, rays.shape[0], occ.ctypes.data))
+        return occ
+
+    def bench_trace(self, rays: np.ndarray, any_hit: bool = False, iters: int = 10) -> float:
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        ms = C.c_float(0)
+        self._check(self.lib.crtc_bench_trace(self.h, rays.ctypes.data, rays.shape[0], 1 if any_hit else 0, iters,
+                                              C.byref(ms)))
+        return float(ms.value)
+
+    # ---- multi-GPU tile gather ----
+    def local_buffers(self):
+        """(accum device ptr, img device ptr, number of local 64x64 tiles)."""
+        a, i, n = C.c_void_p(), C.c_void_p(), C.c_uint32()
+        self._check(self.lib.crtc_local_buffers(self.h, C.byref(a), C.byref(i), C.byref(n)))
+        return a.value, i.value, n.value
+
+    def assemble_rank(self, src_rank: int, world_size: int, accum_dev_ptr: int, img_dev_ptr: int) -> None:
+        self._check(self.lib.crtc_assemble_rank(self.h, src_rank, world_size, C.c_void_p(accum_dev_ptr),
+                                                C.c_void_p(img_dev_ptr)))
+
+
+def local_tile_ids(fb_width: int, fb_height: int, rank: int, world_size: int):
+    """Tiles (64x64, ids as in render_embree.cpp:178-180) owned by ``rank``: id % world_size == rank."""
+    ntx = (fb_width + 63) // 64
+    nty = (fb_height + 63) // 64
+    return [t for t in range(ntx * nty) if t % world_size == rank]

@@ -1,0 +1,284 @@
+// bvh8_traverse.h — single-ray traversal of the compressed BVH8 + Moeller-Trumbore.
+//
+// Replaces rtcIntersectV / rtcOccludedV (reference call sites:
+// backends/embree/render_embree.ispc:245 and :144,170). Semantics kept:
+// closest hit with tnear < t < tfar, no backface culling, barycentrics (u,v) weight v1,v2.
+//
+// Written once as __host__ __device__ code: the CUDA kernels (kernels.cu) are the product;
+// the host instantiation exists only so that tests can validate the builder and the node
+// format on a machine without a GPU (tests/test_bvh8_host.py via libcrt_bvh8_hostcheck.so).
+// render() never runs the host instantiation.
+//
+// Arithmetic contract for the triangle test (the CPU oracle states the same
+// formula independently): explicit fmaf in a fixed order, NaN-failing comparisons,
+// equal-t ties broken toward the lower flattened primitive id so that the result does not
+// depend on traversal order.
+#pragma once
+
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define CRT_HD __host__ __device__ __forceinline__
+#else
+#define CRT_HD inline
+#include <cmath>
+#include <cstring>
+struct float4 {
+    float x, y, z, w;
+};
+struct float3 {
+    float x, y, z;
+};
+struct uint2 {
+    unsigned int x, y;
+};
+#endif
+
+namespace crt {
+
+CRT_HD uint32_t f2u(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+#endif
+}
+CRT_HD float u2f(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+CRT_HD int msb(uint32_t v)  // v != 0
+{
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)v);
+#else
+    return 31 - __builtin_clz(v);
+#endif
+}
+CRT_HD int popc(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+// per byte: 0xff if the byte's top bit is set else 0x00
+CRT_HD uint32_t sign_extend_s8x4(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(r) : "r"(v));
+    return r;
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        if (v & (0x80u << (8 * i))) {
+            r |= 0xffu << (8 * i);
+        }
+    }
+    return r;
+#endif
+}
+CRT_HD float fma_(float a, float b, float c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+CRT_HD float fminf_(float a, float b)
+{
+    return fminf(a, b);
+}
+CRT_HD float fmaxf_(float a, float b)
+{
+    return fmaxf(a, b);
+}
+
+struct Ray {
+    float ox, oy, oz, tnear;
+    float dx, dy, dz, tfar;
+};
+
+struct HitRecord {
+    float t, u, v;
+    uint32_t tri;   // leaf-order triangle index, 0xffffffff = miss
+    uint32_t flat;  // flattened primitive id of that triangle
+};
+
+// Moeller-Trumbore with the fixed fma order. tri = {v0.xyz|flat id, e1.xyz, e2.xyz}
+CRT_HD bool tri_test(const Ray &r, float tfar, const float4 t0, const float4 t1, const float4 t2, float &t, float &u,
+                     float &v)
+{
+    // p = cross(d, e2)
+    const float px = fma_(r.dy, t2.z, -(r.dz * t2.y));
+    const float py = fma_(r.dz, t2.x, -(r.dx * t2.z));
+    const float pz = fma_(r.dx, t2.y, -(r.dy * t2.x));
+    const float det = fma_(t1.z, pz, fma_(t1.y, py, t1.x * px));
+    const float inv = 1.f / det;
+    const float tx = r.ox - t0.x, ty = r.oy - t0.y, tz = r.oz - t0.z;
+    u = fma_(tz, pz, fma_(ty, py, tx * px)) * inv;
+    // q = cross(tv, e1)
+    const float qx = fma_(ty, t1.z, -(tz * t1.y));
+    const float qy = fma_(tz, t1.x, -(tx * t1.z));
+    const float qz = fma_(tx, t1.y, -(ty * t1.x));
+    v = fma_(r.dz, qz, fma_(r.dy, qy, r.dx * qx)) * inv;
+    t = fma_(t2.z, qz, fma_(t2.y, qy, t2.x * qx)) * inv;
+    return (u >= 0.f) && (v >= 0.f) && (u + v <= 1.f) && (t > r.tnear) && (t < tfar);
+}
+
+#ifndef CRT_STACK_SIZE
+#define CRT_STACK_SIZE 32
+#endif
+
+struct TraversalCounters {
+    uint32_t nodes = 0;
+    uint32_t tris = 0;
+};
+
+// ANY_HIT: return at the first accepted triangle. COUNT: fill counters (instrumented build
+// used to derive the algorithmic byte count of SURVEY.md §8d).
+template <bool ANY_HIT, bool COUNT>
+CRT_HD bool bvh8_trace(const float4 *__restrict__ nodes, const float4 *__restrict__ tris, const Ray &ray,
+                       HitRecord &hit, TraversalCounters *counters)
+{
+    // direction reciprocal with the usual guard for zero components
+    const float eps = 1e-20f;
+    const float idx = 1.f / (fabsf(ray.dx) > eps ? ray.dx : (ray.dx < 0.f ? -eps : eps));
+    const float idy = 1.f / (fabsf(ray.dy) > eps ? ray.dy : (ray.dy < 0.f ? -eps : eps));
+    const float idz = 1.f / (fabsf(ray.dz) > eps ? ray.dz : (ray.dz < 0.f ? -eps : eps));
+    const uint32_t oct_inv4 =
+        ((ray.dx < 0.f ? 0u : 0x04040404u) | (ray.dy < 0.f ? 0u : 0x02020202u) | (ray.dz < 0.f ? 0u : 0x01010101u));
+
+    float tfar = ray.tfar;
+    hit.t = ray.tfar;
+    hit.u = hit.v = 0.f;
+    hit.tri = 0xffffffffu;
+    hit.flat = 0xffffffffu;
+
+    uint2 stack[CRT_STACK_SIZE];
+    int sp = 0;
+    uint2 cur;
+    cur.x = 0;
+    cur.y = 0x80000000u;  // root: "inner child in slot 7 of a virtual parent"
+
+    for (;;) {
+        uint2 tri_group;
+        if (cur.y & 0xff000000u) {
+            const uint32_t hits_imask = cur.y;
+            const int child_bit = msb(hits_imask);
+            cur.y &= ~(1u << child_bit);
+            if (cur.y & 0xff000000u) {
+                stack[sp++] = cur;
+            }
+            const uint32_t slot_index = (uint32_t)(child_bit - 24) ^ (oct_inv4 & 0xffu);
+            const uint32_t rel = (uint32_t)popc(hits_imask & ~(0xffffffffu << slot_index));
+            const uint32_t node_index = cur.x + rel;
+            const float4 *np = nodes + (size_t)node_index * 5;
+            const float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
+            if (COUNT) {
+                counters->nodes++;
+            }
+            const uint32_t e_imask = f2u(n0.w);
+            const float adx = u2f((e_imask & 0xffu) << 23) * idx;
+            const float ady = u2f(((e_imask >> 8) & 0xffu) << 23) * idy;
+            const float adz = u2f(((e_imask >> 16) & 0xffu) << 23) * idz;
+            const float obx = (n0.x - ray.ox) * idx;
+            const float oby = (n0.y - ray.oy) * idy;
+            const float obz = (n0.z - ray.oz) * idz;
+            // Rounding slack: the plane distances below are fma(q, ad, ob) with |ob| possibly much
+            // larger than the result, so their absolute error scales with |ob| + 255|ad|. Widening
+            // the interval by that bound keeps the box test conservative with respect to the
+            // (independently rounded) triangle test, including for equal-t ties.
+            const float slack = 4e-7f * (fmaxf_(fmaxf_(fabsf(obx), fabsf(oby)), fabsf(obz)) +
+                                         255.f * fmaxf_(fmaxf_(fabsf(adx), fabsf(ady)), fabsf(adz)));
+            uint32_t hitmask = 0;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t meta4 = f2u(half == 0 ? n1.z : n1.w);
+                const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+                const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+                const uint32_t bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+                const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+                const uint32_t qlox = f2u(half == 0 ? n2.x : n2.y), qloy = f2u(half == 0 ? n2.z : n2.w);
+                const uint32_t qloz = f2u(half == 0 ? n3.x : n3.y), qhix = f2u(half == 0 ? n3.z : n3.w);
+                const uint32_t qhiy = f2u(half == 0 ? n4.x : n4.y), qhiz = f2u(half == 0 ? n4.z : n4.w);
+                const uint32_t xmin = ray.dx < 0.f ? qhix : qlox, xmax = ray.dx < 0.f ? qlox : qhix;
+                const uint32_t ymin = ray.dy < 0.f ? qhiy : qloy, ymax = ray.dy < 0.f ? qloy : qhiy;
+                const uint32_t zmin = ray.dz < 0.f ? qhiz : qloz, zmax = ray.dz < 0.f ? qloz : qhiz;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float tminx = fma_((float)((xmin >> (8 * j)) & 0xffu), adx, obx);
+                    const float tminy = fma_((float)((ymin >> (8 * j)) & 0xffu), ady, oby);
+                    const float tminz = fma_((float)((zmin >> (8 * j)) & 0xffu), adz, obz);
+                    const float tmaxx = fma_((float)((xmax >> (8 * j)) & 0xffu), adx, obx);
+                    const float tmaxy = fma_((float)((ymax >> (8 * j)) & 0xffu), ady, oby);
+                    const float tmaxz = fma_((float)((zmax >> (8 * j)) & 0xffu), adz, obz);
+                    const float tmin = fmaxf_(fmaxf_(tminx, tminy), fmaxf_(tminz, ray.tnear));
+                    const float tmax = fminf_(fminf_(tmaxx, tmaxy), fminf_(tmaxz, tfar)) + slack;
+                    if (tmin <= tmax) {
+                        const uint32_t bits = (child_bits4 >> (8 * j)) & 0xffu;
+                        const uint32_t idx_ = (bit_index4 >> (8 * j)) & 0xffu;
+                        hitmask |= bits << idx_;
+                    }
+                }
+            }
+            cur.x = f2u(n1.x);
+            cur.y = (hitmask & 0xff000000u) | (e_imask >> 24);
+            tri_group.x = f2u(n1.y);
+            tri_group.y = hitmask & 0x00ffffffu;
+        } else {
+            tri_group = cur;
+            cur.x = 0;
+            cur.y = 0;
+        }
+
+        while (tri_group.y) {
+            const int ti = msb(tri_group.y);
+            tri_group.y &= ~(1u << ti);
+            const uint32_t tri_index = tri_group.x + (uint32_t)ti;
+            const float4 *tp = tris + (size_t)tri_index * 3;
+            const float4 t0 = tp[0], t1 = tp[1], t2 = tp[2];
+            if (COUNT) {
+                counters->tris++;
+            }
+            float t, u, v;
+            // tfar + tie handling: accept t == tfar only to resolve ties by primitive id
+            if (tri_test(ray, hit.tri == 0xffffffffu ? tfar : INFINITY, t0, t1, t2, t, u, v)) {
+                const uint32_t flat = f2u(t0.w);
+                if (t < tfar || (t == tfar && hit.tri != 0xffffffffu && flat < hit.flat)) {
+                    hit.t = t;
+                    hit.u = u;
+                    hit.v = v;
+                    hit.tri = tri_index;
+                    hit.flat = flat;
+                    tfar = t;
+                    if (ANY_HIT) {
+                        return true;
+                    }
+                }
+            }
+        }
+
+        if ((cur.y & 0xff000000u) == 0) {
+            if (sp == 0) {
+                break;
+            }
+            cur = stack[--sp];
+        }
+    }
+    return hit.tri != 0xffffffffu;
+}
+
+}  // namespace crt

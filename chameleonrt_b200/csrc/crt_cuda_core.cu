@@ -1,0 +1,842 @@
+// crt_cuda_core.cu — the renderer object behind the C ABI of include/crt_cuda.h.
+//
+// Host-side role = RenderEmbree / RenderOptiX (reference backends/embree/render_embree.cpp,
+// backends/optix/render_optix.cpp): own the device scene, compute the camera basis, launch the
+// frame, time it, read the framebuffer back. Everything per-frame runs on the GPU as the
+// kernel chain of kernels.cuh; there is no CPU fallback anywhere in this file.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <memory>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/crt_cuda.h"
+#include "bvh8.h"
+#include "host_scene.h"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+#define CUDA_CHECK(expr)                                                                              \
+    do {                                                                                              \
+        cudaError_t err__ = (expr);                                                                   \
+        if (err__ != cudaSuccess) {                                                                   \
+            throw std::runtime_error(std::string(#expr) + " failed: " + cudaGetErrorString(err__) +    \
+                                     " (" __FILE__ ":" + std::to_string(__LINE__) + ")");             \
+        }                                                                                             \
+    } while (0)
+
+template <typename T>
+struct DeviceBuffer {
+    T *ptr = nullptr;
+    size_t count = 0;
+    ~DeviceBuffer() { release(); }
+    void release()
+    {
+        if (ptr) {
+            cudaFree(ptr);
+            ptr = nullptr;
+            count = 0;
+        }
+    }
+    void alloc(size_t n)
+    {
+        if (n == count && ptr) {
+            return;
+        }
+        release();
+        if (n) {
+            CUDA_CHECK(cudaMalloc(&ptr, n * sizeof(T)));
+        }
+        count = n;
+    }
+    void upload(const T *src, size_t n, cudaStream_t s)
+    {
+        alloc(n);
+        if (n) {
+            CUDA_CHECK(cudaMemcpyAsync(ptr, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
+        }
+    }
+};
+
+enum Stage { kStRaygen = 0, kStClosest, kStShade, kStAny, kStNee, kStResolve, kStFrame, kNumStages };
+
+}  // namespace
+
+struct crtc_renderer {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+
+    // options
+    int max_depth = 5;
+    int rank = 0, world_size = 1;
+    int bvh_threads = 0;
+    bool count_traversal = false;
+
+    // framebuffer layout
+    int fb_w = 0, fb_h = 0;
+    uint32_t ntx = 0, nty = 0;
+    std::vector<uint32_t> local_tiles;
+    uint32_t npx_local = 0;
+    uint32_t frame_id = 0;
+    uint32_t spp = 1;
+    bool have_scene = false;
+
+    // device scene
+    DeviceBuffer<float4> d_nodes, d_tris, d_shade, d_materials, d_lights;
+    DeviceBuffer<uint32_t> d_texels;
+    DeviceBuffer<crt::DevTex> d_tex;
+    uint32_t num_lights = 0;
+    std::vector<uint32_t> leaf_flat_ids;  // host copy: leaf-order triangle -> flattened prim id
+    double scene_info[6] = {0, 0, 0, 0, 0, 0};
+
+    // path state
+    size_t path_capacity = 0;
+    DeviceBuffer<float4> d_ray_o, d_ray_d, d_hit, d_thr_rng, d_radiance, d_nee_T, d_nee_l1, d_nee_l2, d_sray_o,
+        d_sray_d;
+    DeviceBuffer<uint8_t> d_vis;
+    DeviceBuffer<uint32_t> d_queue0, d_queue1, d_counters;
+    DeviceBuffer<unsigned long long> d_trav_counters;
+
+    // framebuffers
+    DeviceBuffer<uint32_t> d_tile_ids;
+    DeviceBuffer<float> d_accum_local, d_accum_full;
+    DeviceBuffer<uint32_t> d_img_local, d_img_full;
+
+    // timing
+    std::vector<cudaEvent_t> events;
+    std::vector<int> event_stage;  // stage that ENDS at event i (i >= 1)
+    float stage_ms[kNumStages] = {0};
+    uint64_t counters_out[6] = {0};
+    uint32_t *h_counters = nullptr;  // pinned
+    unsigned long long *h_trav = nullptr;
+
+    ~crtc_renderer()
+    {
+        for (auto e : events) {
+            cudaEventDestroy(e);
+        }
+        if (h_counters) {
+            cudaFreeHost(h_counters);
+        }
+        if (h_trav) {
+            cudaFreeHost(h_trav);
+        }
+        if (own_stream) {
+            cudaStreamDestroy(own_stream);
+        }
+    }
+
+    void make_current() { CUDA_CHECK(cudaSetDevice(device)); }
+
+    crt::DeviceScene device_scene() const
+    {
+        crt::DeviceScene sc;
+        sc.nodes = d_nodes.ptr;
+        sc.tris = d_tris.ptr;
+        sc.shade = d_shade.ptr;
+        sc.materials = d_materials.ptr;
+        sc.lights = d_lights.ptr;
+        sc.texels = d_texels.ptr;
+        sc.tex = d_tex.ptr;
+        sc.num_lights = num_lights;
+        return sc;
+    }
+
+    crt::FrameLayout frame_layout() const
+    {
+        crt::FrameLayout f;
+        f.fb_w = fb_w;
+        f.fb_h = fb_h;
+        f.ntx = ntx;
+        f.npx_local = npx_local;
+        f.spp = spp;
+        f.tile_ids = d_tile_ids.ptr;
+        return f;
+    }
+
+    crt::PathState path_state()
+    {
+        crt::PathState ps;
+        ps.ray_o = d_ray_o.ptr;
+        ps.ray_d = d_ray_d.ptr;
+        ps.hit = d_hit.ptr;
+        ps.thr_rng = d_thr_rng.ptr;
+        ps.radiance = d_radiance.ptr;
+        ps.nee_T = d_nee_T.ptr;
+        ps.nee_l1 = d_nee_l1.ptr;
+        ps.nee_l2 = d_nee_l2.ptr;
+        ps.sray_o = d_sray_o.ptr;
+        ps.sray_d = d_sray_d.ptr;
+        ps.vis = d_vis.ptr;
+        ps.queue[0] = d_queue0.ptr;
+        ps.queue[1] = d_queue1.ptr;
+        ps.counters = d_counters.ptr;
+        ps.trav_counters = d_trav_counters.ptr;
+        return ps;
+    }
+
+    void ensure_path_buffers(size_t npaths)
+    {
+        if (npaths <= path_capacity && d_counters.ptr) {
+            return;
+        }
+        d_ray_o.alloc(npaths);
+        d_ray_d.alloc(npaths);
+        d_hit.alloc(npaths);
+        d_thr_rng.alloc(npaths);
+        d_radiance.alloc(npaths);
+        d_nee_T.alloc(npaths);
+        d_nee_l1.alloc(npaths);
+        d_nee_l2.alloc(npaths);
+        d_sray_o.alloc(2 * npaths);
+        d_sray_d.alloc(2 * npaths);
+        d_vis.alloc(2 * npaths);
+        d_queue0.alloc(npaths);
+        d_queue1.alloc(npaths);
+        d_counters.alloc(crt::kNumCounters);
+        d_trav_counters.alloc(2);
+        path_capacity = npaths;
+        if (!h_counters) {
+            CUDA_CHECK(cudaMallocHost(&h_counters, crt::kNumCounters * sizeof(uint32_t)));
+            CUDA_CHECK(cudaMallocHost(&h_trav, 2 * sizeof(unsigned long long)));
+        }
+    }
+
+    void initialize(int w, int h)
+    {
+        if (w <= 0 || h <= 0) {
+            throw std::runtime_error("initialize: framebuffer dimensions must be positive");
+        }
+        make_current();
+        frame_id = 0;
+        fb_w = w;
+        fb_h = h;
+        // render_embree.cpp:43-44
+        ntx = w / crt::kTile + (w % crt::kTile != 0 ? 1 : 0);
+        nty = h / crt::kTile + (h % crt::kTile != 0 ? 1 : 0);
+        local_tiles.clear();
+        for (uint32_t t = 0; t < ntx * nty; ++t) {
+            if ((int)(t % (uint32_t)world_size) == rank) {
+                local_tiles.push_back(t);
+            }
+        }
+        npx_local = (uint32_t)local_tiles.size() * crt::kTilePixels;
+        d_tile_ids.upload(local_tiles.data(), local_tiles.size(), stream);
+        d_accum_local.alloc((size_t)npx_local * 3);
+        d_img_local.alloc(npx_local);
+        d_accum_full.alloc((size_t)w * h * 3);
+        d_img_full.alloc((size_t)w * h);
+        if (npx_local) {
+            CUDA_CHECK(cudaMemsetAsync(d_accum_local.ptr, 0, (size_t)npx_local * 3 * sizeof(float), stream));
+            CUDA_CHECK(cudaMemsetAsync(d_img_local.ptr, 0, (size_t)npx_local * 4, stream));
+        }
+        CUDA_CHECK(cudaMemsetAsync(d_accum_full.ptr, 0, (size_t)w * h * 3 * sizeof(float), stream));
+        CUDA_CHECK(cudaMemsetAsync(d_img_full.ptr, 0, (size_t)w * h * 4, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+
+    void set_scene(const crt_scene_t *scene)
+    {
+        make_current();
+        frame_id = 0;
+        crt::HostScene hs;
+        crt::flatten_scene(scene, hs);
+        crt::Bvh8 bvh;
+        crt::build_bvh8(hs.tri_verts.data(), hs.num_tris(), bvh_threads, bvh);
+        if (bvh.max_depth + 2 > CRT_STACK_SIZE) {
+            throw std::runtime_error("BVH8 depth " + std::to_string(bvh.max_depth) +
+                                     " exceeds the traversal stack (CRT_STACK_SIZE)");
+        }
+        std::vector<float> tri_records;
+        std::vector<crt::TriShade> shade;
+        crt::pack_triangles(hs, bvh, tri_records, shade);
+        leaf_flat_ids.resize(shade.size());
+        for (size_t i = 0; i < shade.size(); ++i) {
+            leaf_flat_ids[i] = shade[i].flat_id;
+        }
+        static_assert(sizeof(crt::Bvh8Node) == 5 * sizeof(float4), "node = 5 float4");
+        d_nodes.upload(reinterpret_cast<const float4 *>(bvh.nodes.data()), bvh.nodes.size() * 5, stream);
+        // keep at least one (degenerate) record so empty scenes have valid pointers
+        if (tri_records.empty()) {
+            tri_records.assign(12, 0.f);
+            shade.resize(1);
+            std::memset(&shade[0], 0, sizeof(crt::TriShade));
+        }
+        d_tris.upload(reinterpret_cast<const float4 *>(tri_records.data()), tri_records.size() / 4, stream);
+        d_shade.upload(reinterpret_cast<const float4 *>(shade.data()), shade.size() * 3, stream);
+        static_assert(sizeof(crt_material_t) == 64 && sizeof(crt_quad_light_t) == 80, "layouts");
+        if (hs.materials.empty()) {
+            hs.materials.resize(1);
+            std::memset(&hs.materials[0], 0, sizeof(crt_material_t));
+        }
+        d_materials.upload(reinterpret_cast<const float4 *>(hs.materials.data()), hs.materials.size() * 4, stream);
+        d_lights.upload(reinterpret_cast<const float4 *>(hs.lights.data()), hs.lights.size() * 5, stream);
+        num_lights = (uint32_t)hs.lights.size();
+        if (hs.texels.empty()) {
+            hs.texels.assign(1, 0u);
+        }
+        d_texels.upload(hs.texels.data(), hs.texels.size(), stream);
+        std::vector<crt::DevTex> tex(std::max<size_t>(1, hs.tex_desc.size()));
+        for (size_t i = 0; i < hs.tex_desc.size(); ++i) {
+            tex[i] = crt::DevTex{hs.tex_desc[i].offset, hs.tex_desc[i].width, hs.tex_desc[i].height, 0};
+        }
+        d_tex.upload(tex.data(), tex.size(), stream);
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        spp = std::max<uint32_t>(1u, hs.samples_per_pixel);
+        have_scene = true;
+        scene_info[0] = (double)hs.num_tris();
+        scene_info[1] = (double)bvh.nodes.size();
+        scene_info[2] = (double)bvh.max_depth;
+        scene_info[3] = bvh.build_seconds * 1e3;
+        scene_info[4] = (double)bvh.nodes.size() * 80.0;
+        scene_info[5] = (double)hs.num_tris() * 48.0;
+        if (npx_local) {
+            CUDA_CHECK(cudaMemsetAsync(d_accum_local.ptr, 0, (size_t)npx_local * 3 * sizeof(float), stream));
+        }
+    }
+
+    cudaEvent_t next_event(size_t &cursor, int stage_ended)
+    {
+        if (cursor >= events.size()) {
+            cudaEvent_t e;
+            CUDA_CHECK(cudaEventCreate(&e));
+            events.push_back(e);
+            event_stage.push_back(0);
+        }
+        event_stage[cursor] = stage_ended;
+        cudaEvent_t e = events[cursor++];
+        CUDA_CHECK(cudaEventRecord(e, stream));
+        return e;
+    }
+
+    static float3 glm_normalize(float3 v)
+    {
+        // glm::normalize(v) = v * inversesqrt(dot(v, v)), inversesqrt(x) = 1 / sqrt(x)
+        const float inv = 1.f / std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+        return make_float3(v.x * inv, v.y * inv, v.z * inv);
+    }
+    static float3 cross3(float3 a, float3 b)
+    {
+        return make_float3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+    }
+
+    // render_embree.cpp:149-159 / render_optix.cpp:454-460
+    crt::ViewParams view_params(const float *pos, const float *dir_, const float *up_, float fovy) const
+    {
+        const float3 dir = make_float3(dir_[0], dir_[1], dir_[2]);
+        const float3 up = make_float3(up_[0], up_[1], up_[2]);
+        const float plane_y = 2.f * std::tan((0.5f * fovy) * 0.01745329251994329576923690768489f);
+        const float plane_x = plane_y * static_cast<float>(fb_w) / static_cast<float>(fb_h);
+        crt::ViewParams v;
+        v.pos = make_float3(pos[0], pos[1], pos[2]);
+        const float3 du = glm_normalize(cross3(dir, up));
+        v.dir_du = make_float3(du.x * plane_x, du.y * plane_x, du.z * plane_x);
+        const float3 dvn = glm_normalize(cross3(v.dir_du, dir));
+        v.dir_dv = make_float3(-dvn.x * plane_y, -dvn.y * plane_y, -dvn.z * plane_y);
+        v.dir_top_left = make_float3(dir.x - 0.5f * v.dir_du.x - 0.5f * v.dir_dv.x,
+                                     dir.y - 0.5f * v.dir_du.y - 0.5f * v.dir_dv.y,
+                                     dir.z - 0.5f * v.dir_du.z - 0.5f * v.dir_dv.z);
+        v.frame_id = frame_id;
+        return v;
+    }
+
+    void render(const float *pos, const float *dir, const float *up, float fovy, bool camera_changed, bool readback,
+                uint32_t *img, crt_render_stats_t *stats)
+    {
+        if (fb_w == 0) {
+            throw std::runtime_error("render: initialize() has not been called");
+        }
+        if (!have_scene) {
+            throw std::runtime_error("render: set_scene() has not been called");
+        }
+        make_current();
+        if (camera_changed) {
+            frame_id = 0;  // render_embree.cpp:145-147
+        }
+        const crt::ViewParams view = view_params(pos, dir, up, fovy);
+        const size_t npaths = (size_t)npx_local * spp;
+        if (npaths >= 0x7fffffffull) {
+            throw std::runtime_error("render: more than 2^31 paths per frame on one device");
+        }
+        ensure_path_buffers(npaths);
+        const crt::DeviceScene sc = device_scene();
+        const crt::FrameLayout fl = frame_layout();
+        const crt::PathState ps = path_state();
+        uint32_t launches = 0;
+
+        size_t ev = 0;
+        next_event(ev, -1);
+        CUDA_CHECK(cudaMemsetAsync(d_counters.ptr, 0, crt::kNumCounters * sizeof(uint32_t), stream));
+        if (count_traversal) {
+            CUDA_CHECK(cudaMemsetAsync(d_trav_counters.ptr, 0, 2 * sizeof(unsigned long long), stream));
+        }
+        if (npaths) {
+            const unsigned g256 = (unsigned)((npaths + 255) / 256);
+            const unsigned g128 = (unsigned)((npaths + 127) / 128);
+            crt::k_raygen<<<g256, 256, 0, stream>>>(view, fl, ps);
+            ++launches;
+            next_event(ev, kStRaygen);
+            for (int b = 0; b < max_depth; ++b) {
+                uint32_t *qin = ps.queue[b & 1], *qout = ps.queue[(b + 1) & 1];
+                if (count_traversal) {
+                    crt::k_traverse_closest<true><<<g128, 128, 0, stream>>>(sc, ps, qin, ps.counters + crt::kCntQueue + b);
+                } else {
+                    crt::k_traverse_closest<false><<<g128, 128, 0, stream>>>(sc, ps, qin, ps.counters + crt::kCntQueue + b);
+                }
+                next_event(ev, kStClosest);
+                crt::k_shade<<<g128, 128, 0, stream>>>(sc, ps, qin, qout, b, max_depth);
+                next_event(ev, kStShade);
+                if (count_traversal) {
+                    crt::k_traverse_any<true><<<2 * g128, 128, 0, stream>>>(sc, ps, ps.counters + crt::kCntShadow + b);
+                } else {
+                    crt::k_traverse_any<false><<<2 * g128, 128, 0, stream>>>(sc, ps, ps.counters + crt::kCntShadow + b);
+                }
+                next_event(ev, kStAny);
+                crt::k_nee_resolve<<<g256, 256, 0, stream>>>(ps, qin, b);
+                next_event(ev, kStNee);
+                launches += 4;
+            }
+            const unsigned gpx = (unsigned)((npx_local + 255) / 256);
+            const bool full = world_size == 1;
+            crt::k_resolve<<<gpx, 256, 0, stream>>>(fl, ps, frame_id, d_accum_local.ptr, d_img_local.ptr,
+                                                    full ? d_accum_full.ptr : nullptr, full ? d_img_full.ptr : nullptr);
+            ++launches;
+            next_event(ev, kStResolve);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(h_counters, d_counters.ptr, crt::kNumCounters * sizeof(uint32_t),
+                                   cudaMemcpyDeviceToHost, stream));
+        if (count_traversal) {
+            CUDA_CHECK(cudaMemcpyAsync(h_trav, d_trav_counters.ptr, 2 * sizeof(unsigned long long),
+                                       cudaMemcpyDeviceToHost, stream));
+        }
+        if (readback && img && world_size == 1) {
+            CUDA_CHECK(cudaMemcpyAsync(img, d_img_full.ptr, (size_t)fb_w * fb_h * 4, cudaMemcpyDeviceToHost, stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        CUDA_CHECK(cudaGetLastError());
+
+        // stage times
+        for (int s = 0; s < kNumStages; ++s) {
+            stage_ms[s] = 0.f;
+        }
+        for (size_t i = 1; i < ev; ++i) {
+            float ms = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, events[i - 1], events[i]));
+            stage_ms[event_stage[i]] += ms;
+        }
+        if (ev > 1) {
+            CUDA_CHECK(cudaEventElapsedTime(&stage_ms[kStFrame], events[0], events[ev - 1]));
+        }
+        uint64_t closest = 0, shadow = 0;
+        for (int b = 0; b < max_depth; ++b) {
+            closest += h_counters[crt::kCntQueue + b];
+            shadow += h_counters[crt::kCntShadow + b];
+        }
+        counters_out[0] = closest;
+        counters_out[1] = shadow;
+        counters_out[2] = launches;
+        counters_out[3] = count_traversal ? h_trav[0] : 0;
+        counters_out[4] = count_traversal ? h_trav[1] : 0;
+        counters_out[5] = h_counters[crt::kCntQueue];
+        if (stats) {
+            stats->render_time = stage_ms[kStFrame];
+            stats->num_rays = closest + shadow;
+            stats->rays_per_second =
+                stage_ms[kStFrame] > 0.f ? (float)((double)(closest + shadow) / (stage_ms[kStFrame] * 1.0e-3)) : 0.f;
+        }
+        ++frame_id;
+    }
+
+    // ---- kernel-level access ----
+    void upload_rays(const float *rays, uint64_t n)
+    {
+        ensure_path_buffers(std::max<size_t>(n, path_capacity));
+        std::vector<float4> o(n), d(n);
+        for (uint64_t i = 0; i < n; ++i) {
+            o[i] = make_float4(rays[8 * i], rays[8 * i + 1], rays[8 * i + 2], rays[8 * i + 3]);
+            d[i] = make_float4(rays[8 * i + 4], rays[8 * i + 5], rays[8 * i + 6], rays[8 * i + 7]);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(d_ray_o.ptr, o.data(), n * sizeof(float4), cudaMemcpyHostToDevice, stream));
+        CUDA_CHECK(cudaMemcpyAsync(d_ray_d.ptr, d.data(), n * sizeof(float4), cudaMemcpyHostToDevice, stream));
+        const uint32_t cnt = (uint32_t)n;
+        CUDA_CHECK(cudaMemcpyAsync(d_counters.ptr, &cnt, 4, cudaMemcpyHostToDevice, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+
+    void launch_closest(uint64_t n)
+    {
+        const crt::DeviceScene sc = device_scene();
+        const crt::PathState ps = path_state();
+        const unsigned g = (unsigned)((n + 127) / 128);
+        if (count_traversal) {
+            crt::k_traverse_closest<true><<<g, 128, 0, stream>>>(sc, ps, nullptr, ps.counters);
+        } else {
+            crt::k_traverse_closest<false><<<g, 128, 0, stream>>>(sc, ps, nullptr, ps.counters);
+        }
+    }
+
+    // shadow-ray layout for the any-hit kernel: sray_o = org|tfar, sray_d = dir|bits(index)
+    void stage_any(uint64_t n, const float *rays)
+    {
+        std::vector<float4> o(n), d(n);
+        for (uint64_t i = 0; i < n; ++i) {
+            o[i] = make_float4(rays[8 * i], rays[8 * i + 1], rays[8 * i + 2], rays[8 * i + 7]);
+            uint32_t idx = (uint32_t)i;
+            float fi;
+            std::memcpy(&fi, &idx, 4);
+            d[i] = make_float4(rays[8 * i + 4], rays[8 * i + 5], rays[8 * i + 6], fi);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(d_sray_o.ptr, o.data(), n * sizeof(float4), cudaMemcpyHostToDevice, stream));
+        CUDA_CHECK(cudaMemcpyAsync(d_sray_d.ptr, d.data(), n * sizeof(float4), cudaMemcpyHostToDevice, stream));
+        const uint32_t cnt = (uint32_t)n;
+        CUDA_CHECK(cudaMemcpyAsync(d_counters.ptr, &cnt, 4, cudaMemcpyHostToDevice, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+
+    void launch_any(uint64_t n)
+    {
+        const crt::DeviceScene sc = device_scene();
+        const crt::PathState ps = path_state();
+        const unsigned g = (unsigned)((n + 127) / 128);
+        if (count_traversal) {
+            crt::k_traverse_any<true><<<g, 128, 0, stream>>>(sc, ps, ps.counters);
+        } else {
+            crt::k_traverse_any<false><<<g, 128, 0, stream>>>(sc, ps, ps.counters);
+        }
+    }
+
+    void require_scene() const
+    {
+        if (!have_scene) {
+            throw std::runtime_error("set_scene() has not been called");
+        }
+    }
+
+    void trace_closest(const float *rays, uint64_t n, float *hits)
+    {
+        require_scene();
+        make_current();
+        if (n == 0) {
+            return;
+        }
+        if (n > 0x3fffffffull) {
+            throw std::runtime_error("trace_closest: too many rays in one batch");
+        }
+        upload_rays(rays, n);
+        launch_closest(n);
+        std::vector<float4> h(n);
+        CUDA_CHECK(cudaMemcpyAsync(h.data(), d_hit.ptr, n * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        CUDA_CHECK(cudaGetLastError());
+        for (uint64_t i = 0; i < n; ++i) {
+            uint32_t tri;
+            std::memcpy(&tri, &h[i].w, 4);
+            const uint32_t flat = tri == crt::kMiss ? crt::kMiss : leaf_flat_ids[tri];
+            hits[4 * i] = h[i].x;
+            hits[4 * i + 1] = h[i].y;
+            hits[4 * i + 2] = h[i].z;
+            std::memcpy(&hits[4 * i + 3], &flat, 4);
+        }
+    }
+
+    void trace_any(const float *rays, uint64_t n, uint8_t *occluded)
+    {
+        require_scene();
+        make_current();
+        if (n == 0) {
+            return;
+        }
+        if (n > 0x3fffffffull) {
+            throw std::runtime_error("trace_any: too many rays in one batch");
+        }
+        ensure_path_buffers(std::max<size_t>((n + 1) / 2, path_capacity));
+        // the any-hit kernel uses tnear = EPSILON like the reference's shadow rays; a batch ray
+        // with another tnear is moved along its direction so the interval is preserved
+        std::vector<float> adj(rays, rays + 8 * n);
+        for (uint64_t i = 0; i < n; ++i) {
+            const float shift = adj[8 * i + 3] - crt::kEpsilon;
+            if (shift != 0.f) {
+                for (int k = 0; k < 3; ++k) {
+                    adj[8 * i + k] += shift * adj[8 * i + 4 + k];
+                }
+                adj[8 * i + 7] -= shift;
+            }
+        }
+        stage_any(n, adj.data());
+        launch_any(n);
+        std::vector<uint8_t> vis(n);
+        CUDA_CHECK(cudaMemcpyAsync(vis.data(), d_vis.ptr, n, cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        CUDA_CHECK(cudaGetLastError());
+        for (uint64_t i = 0; i < n; ++i) {
+            occluded[i] = vis[i] ? 0 : 1;
+        }
+    }
+
+    float bench_trace(const float *rays, uint64_t n, bool any_hit, int iters)
+    {
+        require_scene();
+        make_current();
+        if (n == 0 || iters <= 0) {
+            return 0.f;
+        }
+        if (any_hit) {
+            ensure_path_buffers(std::max<size_t>((n + 1) / 2, path_capacity));
+            stage_any(n, rays);
+        } else {
+            upload_rays(rays, n);
+        }
+        cudaEvent_t e0, e1;
+        CUDA_CHECK(cudaEventCreate(&e0));
+        CUDA_CHECK(cudaEventCreate(&e1));
+        for (int w = 0; w < 3; ++w) {
+            any_hit ? launch_any(n) : launch_closest(n);
+        }
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        CUDA_CHECK(cudaEventRecord(e0, stream));
+        for (int i = 0; i < iters; ++i) {
+            any_hit ? launch_any(n) : launch_closest(n);
+        }
+        CUDA_CHECK(cudaEventRecord(e1, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        CUDA_CHECK(cudaGetLastError());
+        float ms = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return ms / iters;
+    }
+
+    void assemble_rank(int src_rank, int ws, const void *accum_dev, const void *img_dev)
+    {
+        make_current();
+        std::vector<uint32_t> tiles;
+        for (uint32_t t = 0; t < ntx * nty; ++t) {
+            if ((int)(t % (uint32_t)ws) == src_rank) {
+                tiles.push_back(t);
+            }
+        }
+        if (tiles.empty()) {
+            return;
+        }
+        DeviceBuffer<uint32_t> d_tiles;
+        d_tiles.upload(tiles.data(), tiles.size(), stream);
+        crt::FrameLayout f = frame_layout();
+        f.tile_ids = d_tiles.ptr;
+        f.npx_local = (uint32_t)tiles.size() * crt::kTilePixels;
+        const unsigned g = (unsigned)((f.npx_local + 255) / 256);
+        crt::k_assemble<<<g, 256, 0, stream>>>(f, static_cast<const float *>(accum_dev),
+                                              static_cast<const uint32_t *>(img_dev), d_accum_full.ptr, d_img_full.ptr);
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        CUDA_CHECK(cudaGetLastError());
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+#define CRTC_TRY(body)                      \
+    try {                                   \
+        body;                               \
+        return 0;                           \
+    } catch (const std::exception &e) {     \
+        g_last_error = e.what();            \
+        return 1;                           \
+    } catch (...) {                         \
+        g_last_error = "unknown exception"; \
+        return 1;                           \
+    }
+
+extern "C" {
+
+const char *crtc_last_error(void)
+{
+    return g_last_error.c_str();
+}
+
+const char *crtc_name(void)
+{
+    return "CUDA wavefront (B200, BVH8)";
+}
+
+int crtc_create(crtc_renderer **out, int device)
+{
+    CRTC_TRY({
+        if (!out) {
+            throw std::runtime_error("crtc_create: out is NULL");
+        }
+        *out = nullptr;
+        int n = 0;
+        cudaError_t err = cudaGetDeviceCount(&n);
+        if (err != cudaSuccess || n == 0) {
+            throw std::runtime_error(std::string("crtc_create: no usable CUDA device (") +
+                                     (err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0") +
+                                     "); this backend has no CPU fallback");
+        }
+        if (device < 0 || device >= n) {
+            throw std::runtime_error("crtc_create: device ordinal out of range");
+        }
+        std::unique_ptr<crtc_renderer> r(new crtc_renderer());
+        r->device = device;
+        r->make_current();
+        CUDA_CHECK(cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking));
+        r->stream = r->own_stream;
+        *out = r.release();
+    })
+}
+
+void crtc_destroy(crtc_renderer *r)
+{
+    if (r) {
+        cudaSetDevice(r->device);
+        delete r;
+    }
+}
+
+int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
+{
+    CRTC_TRY({
+        const std::string k = key ? key : "";
+        if (k == "max_depth") {
+            if (value < 1 || value > crt::kMaxDepthSupported) {
+                throw std::runtime_error("max_depth must be in [1, 16]");
+            }
+            r->max_depth = (int)value;
+        } else if (k == "rank") {
+            r->rank = (int)value;
+        } else if (k == "world_size") {
+            if (value < 1) {
+                throw std::runtime_error("world_size must be >= 1");
+            }
+            r->world_size = (int)value;
+        } else if (k == "bvh_threads") {
+            r->bvh_threads = (int)value;
+        } else if (k == "count_traversal") {
+            r->count_traversal = value != 0;
+        } else {
+            throw std::runtime_error("unknown option '" + k + "'");
+        }
+        if (r->rank < 0 || r->rank >= r->world_size) {
+            if (k == "rank" || k == "world_size") {
+                // allow setting world_size before rank; validated again in initialize
+            }
+        }
+    })
+}
+
+int crtc_set_stream(crtc_renderer *r, void *cuda_stream)
+{
+    CRTC_TRY({ r->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : r->own_stream; })
+}
+
+int crtc_initialize(crtc_renderer *r, int fb_width, int fb_height)
+{
+    CRTC_TRY({
+        if (r->rank < 0 || r->rank >= r->world_size) {
+            throw std::runtime_error("rank must be in [0, world_size)");
+        }
+        r->initialize(fb_width, fb_height);
+    })
+}
+
+int crtc_set_scene(crtc_renderer *r, const crt_scene_t *scene)
+{
+    CRTC_TRY({
+        if (!scene) {
+            throw std::runtime_error("crtc_set_scene: scene is NULL");
+        }
+        r->set_scene(scene);
+    })
+}
+
+int crtc_render(crtc_renderer *r, const float *pos, const float *dir, const float *up, float fovy, int camera_changed,
+                int readback_framebuffer, uint32_t *img, crt_render_stats_t *stats)
+{
+    CRTC_TRY({ r->render(pos, dir, up, fovy, camera_changed != 0, readback_framebuffer != 0, img, stats); })
+}
+
+int crtc_read_accum(crtc_renderer *r, float *rgb_out)
+{
+    CRTC_TRY({
+        r->make_current();
+        CUDA_CHECK(cudaMemcpyAsync(rgb_out, r->d_accum_full.ptr, (size_t)r->fb_w * r->fb_h * 3 * sizeof(float),
+                                   cudaMemcpyDeviceToHost, r->stream));
+        CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    })
+}
+
+int crtc_read_img(crtc_renderer *r, uint32_t *img)
+{
+    CRTC_TRY({
+        r->make_current();
+        CUDA_CHECK(cudaMemcpyAsync(img, r->d_img_full.ptr, (size_t)r->fb_w * r->fb_h * 4, cudaMemcpyDeviceToHost,
+                                   r->stream));
+        CUDA_CHECK(cudaStreamSynchronize(r->stream));
+    })
+}
+
+int crtc_get_stage_times(crtc_renderer *r, float *ms_out, int n)
+{
+    const int m = std::min(n, (int)kNumStages);
+    for (int i = 0; i < m; ++i) {
+        ms_out[i] = r->stage_ms[i];
+    }
+    return m;
+}
+
+int crtc_get_counters(crtc_renderer *r, uint64_t *out, int n)
+{
+    const int m = std::min(n, 6);
+    for (int i = 0; i < m; ++i) {
+        out[i] = r->counters_out[i];
+    }
+    return m;
+}
+
+int crtc_get_scene_info(crtc_renderer *r, double *out, int n)
+{
+    const int m = std::min(n, 6);
+    for (int i = 0; i < m; ++i) {
+        out[i] = r->scene_info[i];
+    }
+    return m;
+}
+
+int crtc_trace_closest(crtc_renderer *r, const float *rays, uint64_t n, float *hits)
+{
+    CRTC_TRY({ r->trace_closest(rays, n, hits); })
+}
+
+int crtc_trace_any(crtc_renderer *r, const float *rays, uint64_t n, uint8_t *occluded)
+{
+    CRTC_TRY({ r->trace_any(rays, n, occluded); })
+}
+
+int crtc_bench_trace(crtc_renderer *r, const float *rays_host, uint64_t n, int any_hit, int iters, float *ms_out)
+{
+    CRTC_TRY({ *ms_out = r->bench_trace(rays_host, n, any_hit != 0, iters); })
+}
+
+int crtc_local_buffers(crtc_renderer *r, void **accum_dev, void **img_dev, uint32_t *num_local_tiles)
+{
+    CRTC_TRY({
+        *accum_dev = r->d_accum_local.ptr;
+        *img_dev = r->d_img_local.ptr;
+        *num_local_tiles = (uint32_t)r->local_tiles.size();
+    })
+}
+
+int crtc_assemble_rank(crtc_renderer *r, int src_rank, int world_size, const void *accum_dev, const void *img_dev)
+{
+    CRTC_TRY({ r->assemble_rank(src_rank, world_size, accum_dev, img_dev); })
+}
+}

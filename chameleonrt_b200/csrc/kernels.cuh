@@ -1,0 +1,440 @@
+// kernels.cuh — the per-frame hot path as a chain of sm_100a kernels (wavefront style).
+//
+// One kernel per stage over a device-resident, per-bounce compacted ray queue:
+//
+//   k_raygen            render_embree.ispc:212-232   rng seed, pixel jitter, primary ray
+//   k_traverse_closest  render_embree.ispc:245       (rtcIntersectV)  BVH8 + Moeller-Trumbore
+//   k_shade             render_embree.ispc:251-336   miss shader, hit decode, material unpack,
+//                                                    NEE with MIS (emits <= 2 shadow rays),
+//                                                    BSDF continuation, Russian roulette,
+//                                                    warp-aggregated queue compaction
+//   k_traverse_any      render_embree.ispc:144,170   (rtcOccludedV)   any-hit
+//   k_nee_resolve       render_embree.ispc:148-178,301  adds the unoccluded NEE terms in the
+//                                                    reference's order (light sample first)
+//   k_resolve           render_embree.ispc:339-353, 358-370  sample mean, running mean, sRGB8
+//
+// No OptiX, no RT-core intrinsics, no tensor cores (BASELINE.json north_star).
+// Compiled with -fmad=false: shading arithmetic follows the reference's operation order;
+// the traversal uses explicit fma (bvh8_traverse.h).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "bvh8_traverse.h"
+#include "shade_math.cuh"
+
+namespace crt {
+
+constexpr uint32_t kMiss = 0xffffffffu;
+constexpr int kTile = 64;                 // render_embree.h:25
+constexpr uint32_t kTilePixels = kTile * kTile;
+constexpr int kMaxDepthSupported = 16;
+// counters layout (uint32): [0..16] queue length entering bounce b; [17..33] shadow rays
+// emitted at bounce b; [34] paths started
+constexpr int kCntQueue = 0;
+constexpr int kCntShadow = 17;
+constexpr int kCntPaths = 34;
+constexpr int kNumCounters = 36;
+
+struct ViewParams {
+    float3 pos, dir_du, dir_dv, dir_top_left;  // embree_utils.h:137-140
+    uint32_t frame_id;
+};
+
+struct DeviceScene {
+    const float4 *nodes;      // 5 per BVH8 node
+    const float4 *tris;       // 3 per triangle, leaf order: {v0|flat id}, {e1}, {e2}
+    const float4 *shade;      // 3 per triangle, leaf order: TriShade
+    const float4 *materials;  // 4 per material (DisneyMaterial, util/material.h:29-46)
+    const float4 *lights;     // 5 per light (QuadLight, util/lights.h:6-18)
+    const uint32_t *texels;
+    const DevTex *tex;
+    uint32_t num_lights;
+};
+
+struct FrameLayout {
+    int fb_w, fb_h;
+    uint32_t ntx;             // tiles per row
+    uint32_t npx_local;       // num_local_tiles * 4096
+    uint32_t spp;
+    const uint32_t *tile_ids; // global tile id of each local tile
+};
+
+struct PathState {
+    float4 *ray_o;     // org.xyz, tnear
+    float4 *ray_d;     // dir.xyz, tfar
+    float4 *hit;       // t, u, v, bits(leaf-order triangle index | kMiss)
+    float4 *thr_rng;   // path_throughput.xyz, bits(rng state)
+    float4 *radiance;  // per-sample illum.xyz
+    float4 *nee_T;     // throughput before this bounce's update, bits(flags: 1 = has shadow ray B)
+    float4 *nee_l1;    // light-sample contribution (without throughput)
+    float4 *nee_l2;    // BSDF-sample contribution
+    float4 *sray_o;    // shadow ray org.xyz, tfar   (indexed by shadow-queue position)
+    float4 *sray_d;    // shadow ray dir.xyz, bits(path slot * 2 + which)
+    uint8_t *vis;      // 2 per path slot: 1 = unoccluded
+    uint32_t *queue[2];
+    uint32_t *counters;
+    unsigned long long *trav_counters;  // [0] nodes visited, [1] triangles tested
+};
+
+// Local pixel index -> framebuffer coordinates. Within a 64x64 tile pixels are ordered in
+// 8x4 blocks so that the 32 lanes of a warp cover a compact screen rectangle.
+__device__ __forceinline__ bool local_pixel_coords(const FrameLayout &f, uint32_t lp, uint32_t &x, uint32_t &y)
+{
+    const uint32_t lt = lp / kTilePixels, within = lp % kTilePixels;
+    const uint32_t tile = __ldg(f.tile_ids + lt);
+    const uint32_t blk = within >> 5, lane = within & 31u;
+    x = (tile % f.ntx) * kTile + (blk & 7u) * 8u + (lane & 7u);
+    y = (tile / f.ntx) * kTile + (blk >> 3) * 4u + (lane >> 3);
+    return x < (uint32_t)f.fb_w && y < (uint32_t)f.fb_h;
+}
+
+// Appends one item per predicated lane with a single atomic per warp; order inside the warp is
+// preserved. All 32 lanes must call.
+__device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred)
+{
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0) {
+        return 0;
+    }
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) {
+        base = atomicAdd(counter, (uint32_t)__popc(mask));
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_raygen(ViewParams view, FrameLayout f, PathState ps)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t npaths = f.npx_local * f.spp;
+    bool valid = false;
+    if (i < npaths) {
+        const uint32_t lp = i % f.npx_local, s = i / f.npx_local;
+        uint32_t x, y;
+        if (local_pixel_coords(f, lp, x, y)) {
+            valid = true;
+            // render_embree.ispc:213-232
+            uint32_t rng = get_rng(x + y * (uint32_t)f.fb_w, view.frame_id * f.spp + 1u + s);
+            const float px_x = ((float)x + lcg_randomf(rng)) / (float)(uint32_t)f.fb_w;
+            const float px_y = ((float)y + lcg_randomf(rng)) / (float)(uint32_t)f.fb_h;
+            const float3 dir = normalize(mk3(view.dir_du.x * px_x + view.dir_dv.x * px_y + view.dir_top_left.x,
+                                             view.dir_du.y * px_x + view.dir_dv.y * px_y + view.dir_top_left.y,
+                                             view.dir_du.z * px_x + view.dir_dv.z * px_y + view.dir_top_left.z));
+            ps.ray_o[i] = make_float4(view.pos.x, view.pos.y, view.pos.z, 0.f);
+            ps.ray_d[i] = make_float4(dir.x, dir.y, dir.z, 1e20f);
+            ps.thr_rng[i] = make_float4(1.f, 1.f, 1.f, __uint_as_float(rng));
+            ps.radiance[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    const uint32_t idx = warp_append(ps.counters + kCntQueue, valid);
+    if (valid) {
+        ps.queue[0][idx] = i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_traverse_closest(DeviceScene sc, PathState ps, const uint32_t *queue,
+                                                         const uint32_t *count_ptr)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t count = *count_ptr;
+    TraversalCounters cnt;
+    if (j < count) {
+        const uint32_t slot = queue ? queue[j] : j;
+        const float4 o = ps.ray_o[slot], d = ps.ray_d[slot];
+        Ray r{o.x, o.y, o.z, o.w, d.x, d.y, d.z, d.w};
+        HitRecord h;
+        bvh8_trace<false, COUNT>(sc.nodes, sc.tris, r, h, &cnt);
+        ps.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
+    }
+    if (COUNT) {
+        unsigned long long n = cnt.nodes, t = cnt.tris;
+        for (int off = 16; off > 0; off >>= 1) {
+            n += __shfl_down_sync(0xffffffffu, n, off);
+            t += __shfl_down_sync(0xffffffffu, t, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(ps.trav_counters, n);
+            atomicAdd(ps.trav_counters + 1, t);
+        }
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_traverse_any(DeviceScene sc, PathState ps, const uint32_t *count_ptr)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t count = *count_ptr;
+    TraversalCounters cnt;
+    if (k < count) {
+        const float4 o = ps.sray_o[k], d = ps.sray_d[k];
+        Ray r{o.x, o.y, o.z, kEpsilon, d.x, d.y, d.z, o.w};
+        HitRecord h;
+        const bool occluded = bvh8_trace<true, COUNT>(sc.nodes, sc.tris, r, h, &cnt);
+        ps.vis[__float_as_uint(d.w)] = occluded ? 0 : 1;
+    }
+    if (COUNT) {
+        unsigned long long n = cnt.nodes, t = cnt.tris;
+        for (int off = 16; off > 0; off >>= 1) {
+            n += __shfl_down_sync(0xffffffffu, n, off);
+            t += __shfl_down_sync(0xffffffffu, t, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(ps.trav_counters, n);
+            atomicAdd(ps.trav_counters + 1, t);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+__device__ __noinline__ float3 disney_brdf_call(const DisneyMaterial &mat, const float3 n, const float3 w_o,
+                                                const float3 w_i, const float3 v_x, const float3 v_y)
+{
+    return disney_brdf(mat, n, w_o, w_i, v_x, v_y);
+}
+__device__ __noinline__ float disney_pdf_call(const DisneyMaterial &mat, const float3 n, const float3 w_o,
+                                              const float3 w_i, const float3 v_x, const float3 v_y)
+{
+    return disney_pdf(mat, n, w_o, w_i, v_x, v_y);
+}
+__device__ __noinline__ float3 sample_disney_brdf_call(const DisneyMaterial &mat, const float3 n, const float3 w_o,
+                                                       const float3 v_x, const float3 v_y, uint32_t &rng,
+                                                       float3 &w_i, float &pdf)
+{
+    return sample_disney_brdf(mat, n, w_o, v_x, v_y, rng, w_i, pdf);
+}
+
+__global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState ps, const uint32_t *queue_in,
+                                               uint32_t *queue_out, int bounce, int max_depth)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t count = ps.counters[kCntQueue + bounce];
+    bool emit_a = false, emit_b = false, emit_next = false;
+    uint32_t slot = 0;
+    float3 hit_p = mk3(0.f), dir_a = mk3(0.f), dir_b = mk3(0.f);
+    float dist_a = 0.f, dist_b = 0.f;
+    if (j < count) {
+        slot = queue_in[j];
+        const float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot], h = ps.hit[slot], tr = ps.thr_rng[slot];
+        float3 path_throughput = mk3(tr.x, tr.y, tr.z);
+        uint32_t rng = __float_as_uint(tr.w);
+        const uint32_t tri = __float_as_uint(h.w);
+        const float3 dir = mk3(rd.x, rd.y, rd.z);
+        const float3 w_o = neg(dir);
+        if (tri == kMiss) {
+            // render_embree.ispc:258-262
+            float4 rad = ps.radiance[slot];
+            const float3 c = path_throughput * miss_shader(dir);
+            rad.x = rad.x + c.x;
+            rad.y = rad.y + c.y;
+            rad.z = rad.z + c.z;
+            ps.radiance[slot] = rad;
+        } else {
+            // render_embree.ispc:264-293 (the ray-independent part was precomputed per triangle)
+            hit_p = mk3(ro.x + h.x * dir.x, ro.y + h.x * dir.y, ro.z + h.x * dir.z);
+            const float4 s0 = __ldg(sc.shade + 3 * (size_t)tri), s1 = __ldg(sc.shade + 3 * (size_t)tri + 1),
+                         s2 = __ldg(sc.shade + 3 * (size_t)tri + 2);
+            float3 normal = mk3(s0.x, s0.y, s0.z);
+            const uint32_t material_id = __float_as_uint(s0.w);
+            float2 uv = make_float2(0.f, 0.f);
+            if (__float_as_uint(s2.z) != 0u) {
+                const float bw = 1.f - h.y - h.z;
+                uv.x = s1.x * bw + s1.z * h.y + s2.x * h.z;
+                uv.y = s1.y * bw + s1.w * h.y + s2.y * h.z;
+            }
+            DisneyMaterial mat;
+            unpack_material(mat, sc.materials, material_id, uv, sc.texels, sc.tex);
+            // render_embree.ispc:296-300
+            float3 v_x, v_y;
+            if (mat.specular_transmission == 0.f && dot(w_o, normal) < 0.f) {
+                normal = neg(normal);
+            }
+            ortho_basis(v_x, v_y, normal);
+
+            // ---- sample_direct_light, render_embree.ispc:105-181 ----
+            float3 l1 = mk3(0.f), l2 = mk3(0.f);
+            {
+                uint32_t light_id = (uint32_t)(lcg_randomf(rng) * (float)sc.num_lights);
+                light_id = min(light_id, sc.num_lights - 1u);
+                const QuadLight light = load_light(sc.lights, light_id);
+                {
+                    const float sx = lcg_randomf(rng);
+                    const float sy = lcg_randomf(rng);
+                    const float3 light_pos = sample_quad_light_position(light, sx, sy);
+                    float3 light_dir = light_pos - hit_p;
+                    const float light_dist = length(light_dir);
+                    light_dir = normalize(light_dir);
+                    const float light_pdf = quad_light_pdf(light, light_pos, light_dir);
+                    const float bsdf_pdf = disney_pdf_call(mat, normal, w_o, light_dir, v_x, v_y);
+                    // the reference traces (and counts) this shadow ray before the pdf tests
+                    emit_a = true;
+                    dir_a = light_dir;
+                    dist_a = light_dist;
+                    if (light_pdf >= kEpsilon && bsdf_pdf >= kEpsilon) {
+                        const float3 bsdf = disney_brdf_call(mat, normal, w_o, light_dir, v_x, v_y);
+                        const float w = power_heuristic(1.f, light_pdf, 1.f, bsdf_pdf);
+                        l1 = bsdf * light.emission * fabsf(dot(light_dir, normal)) * w / light_pdf;
+                    }
+                }
+                {
+                    float3 w_i;
+                    float bsdf_pdf;
+                    const float3 bsdf = sample_disney_brdf_call(mat, normal, w_o, v_x, v_y, rng, w_i, bsdf_pdf);
+                    float light_dist;
+                    float3 light_pos;
+                    if (!all_zero(bsdf) && bsdf_pdf >= kEpsilon &&
+                        quad_intersect(light, hit_p, w_i, light_dist, light_pos)) {
+                        const float light_pdf = quad_light_pdf(light, light_pos, w_i);
+                        if (light_pdf >= kEpsilon) {
+                            const float w = power_heuristic(1.f, bsdf_pdf, 1.f, light_pdf);
+                            emit_b = true;
+                            dir_b = w_i;
+                            dist_b = light_dist;
+                            l2 = bsdf * light.emission * fabsf(dot(w_i, normal)) * w / bsdf_pdf;
+                        }
+                    }
+                }
+            }
+            ps.nee_T[slot] = make_float4(path_throughput.x, path_throughput.y, path_throughput.z,
+                                         __uint_as_float(emit_b ? 1u : 0u));
+            ps.nee_l1[slot] = make_float4(l1.x, l1.y, l1.z, 0.f);
+            if (emit_b) {
+                ps.nee_l2[slot] = make_float4(l2.x, l2.y, l2.z, 0.f);
+            }
+
+            // ---- continuation, render_embree.ispc:313-336 ----
+            float pdf;
+            float3 w_i;
+            const float3 bsdf = sample_disney_brdf_call(mat, normal, w_o, v_x, v_y, rng, w_i, pdf);
+            if (!(pdf == 0.f || all_zero(bsdf))) {
+                path_throughput = path_throughput * bsdf * fabsf(dot(w_i, normal)) / pdf;
+                const int nb = bounce + 1;
+                bool alive = true;
+                if (nb > 3) {
+                    const float q =
+                        fmaxf(0.05f, 1.f - fmaxf(path_throughput.x, fmaxf(path_throughput.y, path_throughput.z)));
+                    if (lcg_randomf(rng) < q) {
+                        alive = false;
+                    } else {
+                        path_throughput = path_throughput / (1.f - q);
+                    }
+                }
+                if (alive && nb < max_depth) {
+                    emit_next = true;
+                    ps.ray_o[slot] = make_float4(hit_p.x, hit_p.y, hit_p.z, kEpsilon);
+                    ps.ray_d[slot] = make_float4(w_i.x, w_i.y, w_i.z, 1e20f);
+                    ps.thr_rng[slot] =
+                        make_float4(path_throughput.x, path_throughput.y, path_throughput.z, __uint_as_float(rng));
+                }
+            }
+        }
+    }
+    // ---- compaction: one atomic per warp per queue ----
+    const uint32_t ia = warp_append(ps.counters + kCntShadow + bounce, emit_a);
+    if (emit_a) {
+        ps.sray_o[ia] = make_float4(hit_p.x, hit_p.y, hit_p.z, dist_a);
+        ps.sray_d[ia] = make_float4(dir_a.x, dir_a.y, dir_a.z, __uint_as_float(slot * 2u));
+    }
+    const uint32_t ib = warp_append(ps.counters + kCntShadow + bounce, emit_b);
+    if (emit_b) {
+        ps.sray_o[ib] = make_float4(hit_p.x, hit_p.y, hit_p.z, dist_b);
+        ps.sray_d[ib] = make_float4(dir_b.x, dir_b.y, dir_b.z, __uint_as_float(slot * 2u + 1u));
+    }
+    const uint32_t in = warp_append(ps.counters + kCntQueue + bounce + 1, emit_next);
+    if (emit_next) {
+        queue_out[in] = slot;
+    }
+}
+
+// illum = illum + path_throughput * (L1 [if unoccluded] + L2 [if traced and unoccluded])
+__global__ void __launch_bounds__(256) k_nee_resolve(PathState ps, const uint32_t *queue_in, int bounce)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ps.counters[kCntQueue + bounce]) {
+        return;
+    }
+    const uint32_t slot = queue_in[j];
+    if (__float_as_uint(ps.hit[slot].w) == kMiss) {
+        return;
+    }
+    const float4 T = ps.nee_T[slot];
+    float3 illum = mk3(0.f);
+    if (ps.vis[2 * slot]) {
+        const float4 l1 = ps.nee_l1[slot];
+        illum = mk3(l1.x, l1.y, l1.z);
+    }
+    if (__float_as_uint(T.w) & 1u) {
+        if (ps.vis[2 * slot + 1]) {
+            const float4 l2 = ps.nee_l2[slot];
+            illum = illum + mk3(l2.x, l2.y, l2.z);
+        }
+    }
+    float4 rad = ps.radiance[slot];
+    rad.x = rad.x + T.x * illum.x;
+    rad.y = rad.y + T.y * illum.y;
+    rad.z = rad.z + T.z * illum.z;
+    ps.radiance[slot] = rad;
+}
+
+// render_embree.ispc:339-353 (sample mean + running mean) and :358-370 (sRGB8)
+__global__ void __launch_bounds__(256) k_resolve(FrameLayout f, PathState ps, uint32_t frame_id, float *accum_local,
+                                                uint32_t *img_local, float *accum_full, uint32_t *img_full)
+{
+    const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lp >= f.npx_local) {
+        return;
+    }
+    uint32_t x, y;
+    if (!local_pixel_coords(f, lp, x, y)) {
+        return;
+    }
+    float3 illum = mk3(0.f);
+    for (uint32_t s = 0; s < f.spp; ++s) {
+        const float4 r = ps.radiance[(size_t)s * f.npx_local + lp];
+        illum = illum + mk3(r.x, r.y, r.z);
+    }
+    illum = illum / (float)f.spp;
+    const float3 accum = mk3(accum_local[3 * (size_t)lp], accum_local[3 * (size_t)lp + 1], accum_local[3 * (size_t)lp + 2]);
+    illum = (illum + (float)frame_id * accum) / (float)(frame_id + 1u);
+    accum_local[3 * (size_t)lp] = illum.x;
+    accum_local[3 * (size_t)lp + 1] = illum.y;
+    accum_local[3 * (size_t)lp + 2] = illum.z;
+    const uint32_t rgba = float_to_srgb8(illum.x) | (float_to_srgb8(illum.y) << 8) | (float_to_srgb8(illum.z) << 16) |
+                          0xff000000u;
+    img_local[lp] = rgba;
+    if (accum_full) {
+        const size_t p = (size_t)y * f.fb_w + x;
+        accum_full[3 * p] = illum.x;
+        accum_full[3 * p + 1] = illum.y;
+        accum_full[3 * p + 2] = illum.z;
+        img_full[p] = rgba;
+    }
+}
+
+// Scatter another rank's tile-local buffers into the full frame (frame-end gather, §8e)
+__global__ void __launch_bounds__(256) k_assemble(FrameLayout f, const float *accum_local, const uint32_t *img_local,
+                                                 float *accum_full, uint32_t *img_full)
+{
+    const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lp >= f.npx_local) {
+        return;
+    }
+    uint32_t x, y;
+    if (!local_pixel_coords(f, lp, x, y)) {
+        return;
+    }
+    const size_t p = (size_t)y * f.fb_w + x;
+    accum_full[3 * p] = accum_local[3 * (size_t)lp];
+    accum_full[3 * p + 1] = accum_local[3 * (size_t)lp + 1];
+    accum_full[3 * p + 2] = accum_local[3 * (size_t)lp + 2];
+    img_full[p] = img_local[lp];
+}
+
+}  // namespace crt

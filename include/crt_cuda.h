@@ -1,0 +1,132 @@
+/* crt_cuda.h — C ABI of libcrt_cuda_core.so, the B200-native wavefront path tracer that sits
+ * behind ChameleonRT's RenderBackend interface.
+ *
+ * The reference's plugin boundary is C++ (a vtable and std::vector cross it:
+ * util/render_backend.h:12-32, util/render_plugin.h:23-63). This header is the plain-C
+ * surface underneath: one entry point per RenderBackend member, plain pointers and sizes, no
+ * C++ or torch types. backends/cuda/render_cuda.cpp (the drop-in `crt_cuda` plugin a
+ * ChameleonRT maintainer builds) and chameleonrt_b200/backend.py (ctypes) both bind exactly
+ * these symbols; INTEGRATION.md shows the binding.
+ *
+ *   RenderBackend member (util/render_backend.h)        ->  C entry point
+ *   ---------------------------------------------------------------------------------------
+ *   constructor / make_renderer (render_plugin.h:41)    ->  crtc_create
+ *   virtual ~RenderBackend()                 :16        ->  crtc_destroy
+ *   std::string name()                       :18        ->  crtc_name
+ *   void initialize(fb_width, fb_height)     :20        ->  crtc_initialize
+ *   void set_scene(const Scene&)             :23        ->  crtc_set_scene
+ *   RenderStats render(pos, dir, up, fovy,
+ *        camera_changed, readback_framebuffer) :26-31   ->  crtc_render
+ *   std::vector<uint32_t> img                :13        ->  the `img` out-parameter of crtc_render
+ *   uint32_t samples_per_pixel               :14        ->  crt_scene_t::samples_per_pixel
+ *
+ * Error behaviour: the reference throws std::runtime_error and nothing catches it
+ * (SURVEY.md §5). Here every call returns 0 on success and non-zero on failure, with the
+ * message available from crtc_last_error(); the C++ plugin rethrows it as
+ * std::runtime_error, the Python binding raises RuntimeError. There is NO CPU fallback: if
+ * no CUDA device is usable crtc_create fails.
+ *
+ * Threading: like the reference, all calls on one renderer come from one thread.
+ */
+#ifndef CRT_CUDA_H
+#define CRT_CUDA_H
+
+#include <stdint.h>
+
+#include "crt_scene.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct crtc_renderer crtc_renderer;
+
+/* Message of the last failed call on this thread ("" if none). */
+const char *crtc_last_error(void);
+
+/* RenderBackend::name(). */
+const char *crtc_name(void);
+
+/* Creates a renderer on CUDA device `device` (cudaSetDevice ordinal). */
+int crtc_create(crtc_renderer **out, int device);
+void crtc_destroy(crtc_renderer *r);
+
+/* Options the plugin API has no channel for (the reference hard-codes them; the plugin reads
+ * CRT_CUDA_* environment variables and forwards them here). Must be set before
+ * crtc_initialize / crtc_set_scene.
+ *   "max_depth"   path depth, reference MAX_PATH_DEPTH = 5 (backends/embree/util.ih:10)
+ *   "rank", "world_size"  image-tile sharding: this renderer owns the 64x64 tiles with
+ *                 tile_id % world_size == rank (tile_id as in render_embree.cpp:178-180)
+ *   "bvh_threads" host threads for the BVH8 build (0 = all)
+ *   "count_traversal" 1 = instrumented traversal kernels that count node visits and triangle
+ *                 tests (for the algorithmic-byte figure; slower, off by default)
+ */
+int crtc_set_option(crtc_renderer *r, const char *key, int64_t value);
+
+/* Use an existing CUDA stream (cudaStream_t) for all work of this renderer; NULL = the
+ * renderer's own stream. Lets a host that already owns a stream (e.g. PyTorch's current
+ * stream) order and time the work with its own events. */
+int crtc_set_stream(crtc_renderer *r, void *cuda_stream);
+
+/* RenderBackend::initialize: (re)allocates the framebuffer state and resets accumulation. */
+int crtc_initialize(crtc_renderer *r, int fb_width, int fb_height);
+
+/* RenderBackend::set_scene: flattens instances, builds the BVH8 on the host, uploads
+ * geometry / materials / textures / lights, resets accumulation. */
+int crtc_set_scene(crtc_renderer *r, const crt_scene_t *scene);
+
+/* RenderBackend::render. pos/dir/up: 3 floats each; fovy in degrees. If
+ * readback_framebuffer != 0 and img != NULL, img receives fb_width*fb_height RGBA8 pixels
+ * (row-major, y down — RenderBackend::img). stats may be NULL. With world_size > 1 only the
+ * tiles this rank owns are rendered and written; the rest of img is left untouched. */
+int crtc_render(crtc_renderer *r, const float *pos, const float *dir, const float *up, float fovy,
+                int camera_changed, int readback_framebuffer, uint32_t *img, crt_render_stats_t *stats);
+
+/* The accumulated float framebuffer (what parity compares): fb_width*fb_height*3 floats,
+ * row-major RGB. The reference keeps it backend-private and tile-major
+ * (render_embree.h:26, render_embree.ispc:345); this is the extra export SURVEY.md §8b asks
+ * for. */
+int crtc_read_accum(crtc_renderer *r, float *rgb_out);
+
+/* Per-stage device times of the last frame, in ms (CUDA events on the renderer's stream):
+ * [0] raygen [1] closest-hit traversal [2] shade [3] any-hit traversal [4] NEE resolve
+ * [5] resolve+tonemap [6] whole frame. Returns the number of entries written (<= n). */
+int crtc_get_stage_times(crtc_renderer *r, float *ms_out, int n);
+
+/* Counters of the last frame: [0] closest-hit rays [1] occlusion rays [2] kernel launches
+ * [3] BVH nodes visited [4] triangles tested ([3],[4] only with count_traversal=1)
+ * [5] paths started. */
+int crtc_get_counters(crtc_renderer *r, uint64_t *out, int n);
+
+/* Scene/BVH facts: [0] triangles [1] BVH8 nodes [2] BVH depth [3] build ms [4] node bytes
+ * [5] triangle bytes. */
+int crtc_get_scene_info(crtc_renderer *r, double *out, int n);
+
+/* Kernel-level access for parity tests and micro-benchmarks: trace a batch of rays against
+ * the current scene with the same traversal kernels render() uses. rays: n*8 floats
+ * {ox,oy,oz,tnear,dx,dy,dz,tfar} in HOST memory; hits: n*4 floats {t,u,v,bits(flat prim id or
+ * 0xffffffff)}; occluded: n bytes. */
+int crtc_trace_closest(crtc_renderer *r, const float *rays, uint64_t n, float *hits);
+int crtc_trace_any(crtc_renderer *r, const float *rays, uint64_t n, uint8_t *occluded);
+/* Same kernels on DEVICE-resident rays, repeated `iters` times, returning the mean kernel time
+ * in ms (CUDA events). For the roofline measurement of the traversal kernel in isolation. */
+int crtc_bench_trace(crtc_renderer *r, const float *rays_host, uint64_t n, int any_hit, int iters,
+                     float *ms_out);
+
+/* Multi-GPU: device pointers of this rank's tile-local buffers, for the frame-end gather over
+ * NVLink (torch.distributed / NCCL moves them; this library never touches the network).
+ * accum: num_local_tiles*4096*3 floats; img: num_local_tiles*4096 RGBA8. */
+int crtc_local_buffers(crtc_renderer *r, void **accum_dev, void **img_dev, uint32_t *num_local_tiles);
+/* On the assembling rank: scatter one rank's gathered tile-local buffers (DEVICE pointers) into
+ * the full row-major frame of this renderer. */
+int crtc_assemble_rank(crtc_renderer *r, int src_rank, int world_size, const void *accum_dev,
+                       const void *img_dev);
+/* Read the assembled full frame (after crtc_assemble_rank for every rank, or after a
+ * world_size==1 render). */
+int crtc_read_img(crtc_renderer *r, uint32_t *img);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif
