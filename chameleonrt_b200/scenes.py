@@ -97,6 +97,7 @@ def box(lo, hi, sub=(1, 1, 1), uv_scale=1.0):
 
 def cylinder(base, radius, height, nseg, nring, uv_scale=(1.0, 1.0), radius_fn=None):
     base = np.asarray(base, dtype=np.float64)
+    nseg = max(3, nseg)  # two segments would be two coincident sheets
     a = np.linspace(0, 2 * np.pi, nseg + 1)
     h = np.linspace(0, 1, nring + 1)
     A, H = np.meshgrid(a, h, indexing="ij")

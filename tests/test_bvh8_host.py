@@ -1,0 +1,108 @@
+"""The product's host-side scene flattening + BVH8 builder + node format, validated on CPU by
+running the host instantiation of the traversal (TEST-ONLY libcrt_bvh8_hostcheck.so) against
+the oracle. Bit-exact for identity-instanced (OBJ-class) scenes."""
+import numpy as np
+import pytest
+
+from chameleonrt_b200.scenes import cornell_box, san_miguel_like, sponza_like
+from helpers import HostCheck, bounce_rays, camera_for, synthetic_material_scene
+from oracle import OracleBackend
+from oracle.oracle import primary_rays
+
+
+def _rays(scene, cam, oracle, w=96, h=54):
+    c = camera_for(cam)
+    rays = primary_rays(w, h, c.eye(), c.dir(), c.up(), cam["fov_y"])
+    h0 = oracle.trace_closest(rays)
+    return np.concatenate([rays, bounce_rays(rays, h0), bounce_rays(rays, h0, seed=2)])
+
+
+@pytest.mark.parametrize("name", ["cornell", "sponza", "materials"])
+def test_bvh8_bit_exact_vs_oracle(built, name):
+    scene, cam = {"cornell": lambda: cornell_box(), "sponza": lambda: sponza_like(detail=0.35, tex_size=16),
+                  "materials": lambda: synthetic_material_scene()}[name]()
+    o = OracleBackend()
+    o.initialize(8, 8)
+    o.set_scene(scene)
+    hc = HostCheck(scene)
+    st = hc.stats()
+    assert st["tris"] == scene.total_tris()
+    rays = _rays(scene, cam, o)
+    ho, no = o.trace_closest(rays, True)
+    hb, nb, cnt = hc.trace(rays, normals=True, counters=True)
+    assert (ho.view(np.uint32) == hb.view(np.uint32)).all(), "closest hit (t,u,v,prim) differs from the oracle"
+    assert (no.view(np.uint32) == nb.view(np.uint32)).all(), "precomputed world normals differ from the oracle"
+    ha, _, _ = hc.trace(rays, any_hit=True)
+    assert ((ha[:, 3].view(np.uint32) != 0xFFFFFFFF) == o.trace_any(rays).astype(bool)).all()
+    assert cnt[:, 0].mean() < 64 and cnt[:, 1].mean() < 32  # a working hierarchy, not a linear scan
+
+
+def test_bvh8_instanced_scene_tolerance(built):
+    """glTF-class scene: the oracle intersects in object space (Embree instancing), the product
+    flattens to world space, so t/u/v agree to rounding and primitive ids agree except for
+    rays that graze an edge."""
+    scene, cam = san_miguel_like(scale=0.01, tex_size=16)
+    o = OracleBackend()
+    o.initialize(8, 8)
+    o.set_scene(scene)
+    hc = HostCheck(scene)
+    rays = _rays(scene, cam, o, 64, 36)
+    ho = o.trace_closest(rays)
+    hb, _, _ = hc.trace(rays)
+    same_prim = ho[:, 3].view(np.uint32) == hb[:, 3].view(np.uint32)
+    assert same_prim.mean() > 0.999
+    hit = same_prim & (ho[:, 3].view(np.uint32) != 0xFFFFFFFF)
+    np.testing.assert_allclose(hb[hit, 0], ho[hit, 0], rtol=2e-4, atol=1e-4)
+
+
+def test_bvh8_node_format(built):
+    """Structural invariants of the 80-byte node (bvh8.h)."""
+    scene, _ = sponza_like(detail=0.2, tex_size=16)
+    hc = HostCheck(scene)
+    st = hc.stats()
+    assert st["depth"] <= 30
+    assert st["nodes"] * 8 * 3 >= st["tris"]  # <= 3 triangles per leaf slot, 8 slots
+    assert st["nodes"] < st["tris"]
+
+
+def test_degenerate_and_tiny_scenes(built):
+    from chameleonrt_b200.scene import Geometry, Instance, Mesh, ParameterizedMesh, Scene, default_obj_light, DisneyMaterial
+
+    def mk(verts, idx):
+        return Scene(meshes=[Mesh([Geometry(np.array(verts, np.float32), np.array(idx, np.uint32))])],
+                     parameterized_meshes=[ParameterizedMesh(0, [0])], instances=[Instance(np.eye(4, dtype=np.float32), 0)],
+                     materials=[DisneyMaterial()], lights=[default_obj_light()])
+
+    # one triangle; two coincident triangles (tie -> lower primitive id); a zero-area triangle
+    ray = np.array([[0.25, 0.25, 1, 0, 0, 0, -1, 1e20]], np.float32)
+    for verts, idx, expect_prim in (
+        ([[0, 0, 0], [1, 0, 0], [0, 1, 0]], [[0, 1, 2]], 0),
+        ([[0, 0, 0], [1, 0, 0], [0, 1, 0]], [[0, 1, 2], [0, 1, 2]], 0),
+        ([[0, 0, 0], [1, 0, 0], [0, 1, 0], [5, 5, 5]], [[3, 3, 3], [0, 1, 2]], 1),
+    ):
+        scene = mk(verts, idx)
+        hc = HostCheck(scene)
+        h, _, _ = hc.trace(ray)
+        o = OracleBackend()
+        o.initialize(8, 8)
+        o.set_scene(scene)
+        ho = o.trace_closest(ray)
+        assert (h.view(np.uint32) == ho.view(np.uint32)).all()
+        assert h[0, 3].view(np.uint32) == expect_prim and h[0, 0] == 1.0
+
+
+def test_flatten_rejects_bad_input(built):
+    from chameleonrt_b200.scenes import cornell_box
+
+    scene, _ = cornell_box()
+    scene.parameterized_meshes[0].material_ids[0] = 99
+    with pytest.raises(RuntimeError, match="material"):
+        HostCheck(scene)
+    scene, _ = cornell_box()
+    scene.lights = []
+    with pytest.raises(RuntimeError, match="light"):
+        HostCheck(scene)
+    scene, _ = cornell_box()
+    scene.meshes[0].geometries[0].indices[0, 0] = 10_000
+    with pytest.raises(RuntimeError, match="index"):
+        HostCheck(scene)
