@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — MRays/s and ms/frame of the per-frame render path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W          # the CUDA wavefront backend
+  python bench.py --impl reference --gpus N ...           # the CPU path (oracle), rank 0 only
+
+A "step" is one frame: one pass of the hot path (raygen -> [closest-hit traversal -> shade ->
+any-hit traversal -> NEE resolve] x depth -> resolve/tonemap) over the whole image at the
+configured samples per pixel. Workload = BASELINE.json configs[1]: Sponza-class OBJ scene
+(seeded procedural stand-in, the asset is not on the box), 1280x720, 4 spp, max depth 8.
+
+N > 1 (torchrun, one process per GPU): the image's 64x64 tiles are sharded round-robin across
+ranks (scene + BVH replicated), every rank renders its tiles with no communication, and the
+accumulated tiles are gathered to rank 0 over NCCL/NVLink at frame end, inside the timed
+region. Total work is fixed, so scaling is "strong".
+
+One JSON line on stdout (rank 0). Keys follow the driver contract; `roofline` describes
+k_traverse_closest, `cpu_baseline` the CPU oracle timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = "C2 sponza_like OBJ-class scene (263,792 tris, 25 materials, 8 sRGB 1024^2 textures), 1280x720, 4 spp, max depth 8"
+WIDTH, HEIGHT, SPP, MAX_DEPTH = 1280, 720, 4, 8
+S_NODE, S_TRI, S_RAY, S_HIT = 80, 48, 32, 16  # algorithmic bytes, SURVEY.md §8d / DESIGN.md §5
+
+
+def make_workload():
+    from chameleonrt_b200 import ArcballCamera
+    from chameleonrt_b200.scenes import sponza_like
+
+    scene, cam = sponza_like(spp=SPP)
+    camera = ArcballCamera(cam["eye"], cam["center"], cam["up"])
+    return scene, (camera.eye(), camera.dir(), camera.up(), cam["fov_y"])
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons while the timed region runs."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thread.join(timeout=10)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def time_oracle(scene, view, budget_s: float, frames_cap: int, fast: bool = True):
+    """Times the CPU oracle (all host threads) on the workload; returns per-frame list."""
+    from oracle import OracleBackend
+
+    cpu = OracleBackend(max_depth=MAX_DEPTH, fast=fast)
+    cpu.initialize(WIDTH, HEIGHT)
+    cpu.set_scene(scene)
+    results = []
+    t0 = time.time()
+    f = 0
+    while True:
+        st = cpu.render(*view, f == 0, True)
+        results.append((st.render_time, st.num_rays))
+        f += 1
+        if f >= frames_cap or (time.time() - t0) > budget_s:
+            break
+    return results, cpu
+
+
+def run_reference_arm(args):
+    """--impl reference: the CPU implementation of the path on this box's host cores. The
+    reference's own Embree/ISPC backend cannot be built here (no Embree/TBB/ISPC/GLM/SDL, no
+    network: DESIGN.md §3), so this is the oracle port, with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene, view = make_workload()
+    from oracle import OracleBackend
+
+    cpu = OracleBackend(max_depth=MAX_DEPTH, fast=True)
+    cpu.initialize(WIDTH, HEIGHT)
+    cpu.set_scene(scene)
+    f = 0
+    for _ in range(args.warmup):
+        cpu.render(*view, f == 0, True)
+        f += 1
+    rays, ms = 0, 0.0
+    for _ in range(args.steps):
+        st = cpu.render(*view, f == 0, True)
+        f += 1
+        rays += st.num_rays
+        ms += st.render_time
+    value = rays / (ms * 1e3)
+    cores = cpu_cores()
+    line = {
+        "impl": "reference", "metric": "MRays/s", "value": value, "unit": "MRays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "spp": SPP, "max_depth": MAX_DEPTH},
+        "cpu_baseline": {"value": value, "unit": "MRays/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} full frames of the workload after {args.warmup} warm-up frames; "
+                                   "CPU oracle (Embree/ISPC backend restated, own BVH2), all host threads"},
+        "e2e": {"value": value, "unit": "MRays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cuda" else max(args.warmup, 1)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from chameleonrt_b200 import RenderCUDA
+    from chameleonrt_b200.distributed import gather_frame_cuda
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; the backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+
+    scene, view = make_workload()
+    stream = torch.cuda.current_stream(dev)
+    gpu = RenderCUDA(local_rank, max_depth=MAX_DEPTH, rank=rank, world_size=world, stream=stream.cuda_stream)
+    gpu.initialize(WIDTH, HEIGHT)
+    gpu.set_scene(scene)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def frame(f, readback):
+        st = gpu.render(*view, f == 0, readback and world == 1)
+        if world > 1:
+            gather_frame_cuda(gpu)
+            if readback and rank == 0:
+                gpu.img[...] = gpu.read_img()
+        return st
+
+    # ---- instrumented pass (not timed): exact node/triangle visit counts of the same frames ----
+    counts = None
+    if True:
+        inst = RenderCUDA(local_rank, max_depth=MAX_DEPTH, rank=rank, world_size=world, count_traversal=True,
+                          stream=stream.cuda_stream)
+        inst.initialize(WIDTH, HEIGHT)
+        inst.set_scene(scene)
+        acc = np.zeros(6, np.float64)
+        for f in range(args.warmup + args.steps):
+            inst.render(*view, f == 0, False)
+            if f >= args.warmup:
+                c = inst.counters()
+                acc += [c["closest_rays"], c["closest_nodes_visited"], c["closest_tris_tested"], c["occlusion_rays"],
+                        c["any_nodes_visited"], c["any_tris_tested"]]
+        counts = acc
+        del inst
+
+    # ---- device-timed region: inputs resident in HBM, no readback ----
+    f = 0
+    for _ in range(args.warmup):
+        frame(f, False)
+        f += 1
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rays = 0
+    launches = 0
+    stage_acc = {}
+    with ClockSampler(local_rank) as clocks:
+        e0.record(stream)
+        for _ in range(args.steps):
+            st = frame(f, False)
+            f += 1
+            rays += st.num_rays
+            launches += gpu.counters()["kernel_launches"] + (world if (world > 1 and rank == 0) else 0)
+            for k, v in gpu.stage_times().items():
+                stage_acc[k] = stage_acc.get(k, 0.0) + v
+        e1.record(stream)
+        barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    clock_summary = clocks.summary()
+
+    # ---- end-to-end region: the public call with host buffers (img readback every frame) ----
+    barrier()
+    t0 = time.perf_counter()
+    e2e_rays = 0
+    for _ in range(args.steps):
+        st = frame(f, True)
+        f += 1
+        e2e_rays += st.num_rays
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        t = torch.tensor([elapsed_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_ms = float(t[0]), float(t[1])
+        r = torch.tensor([float(rays), float(e2e_rays), float(launches)], dtype=torch.float64, device=dev)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+        rays, e2e_rays, launches = float(r[0]), float(r[1]), float(r[2])
+        c = torch.tensor(counts, dtype=torch.float64, device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        counts = c.cpu().numpy()
+        sa = torch.tensor([stage_acc[k] for k in sorted(stage_acc)], dtype=torch.float64, device=dev)
+        dist.all_reduce(sa, op=dist.ReduceOp.MAX)
+        stage_acc = {k: float(v) for k, v in zip(sorted(stage_acc), sa)}
+    else:
+        e2e_ms = e2e_s * 1e3
+
+    if rank == 0:
+        value = rays / (elapsed_ms * 1e3)  # MRays/s
+        peak, peak_src = hbm_peak()
+        n_launch = args.steps * MAX_DEPTH
+        closest_bytes = counts[1] * S_NODE + counts[2] * S_TRI + counts[0] * (S_RAY + S_HIT)
+        t_closest_ms = stage_acc["traverse_closest"]  # max over ranks of the per-rank sum
+        achieved = closest_bytes / world / (t_closest_ms * 1e-3) / 1e9  # per GPU GB/s
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_k_traverse_closest.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        any_bytes = counts[4] * S_NODE + counts[5] * S_TRI + counts[3] * (S_RAY + 1)
+        line = {
+            "metric": "MRays/s", "value": value, "unit": "MRays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "spp": SPP, "max_depth": MAX_DEPTH,
+                       "parallelism": f"image tiles 64x64 round-robin over {world} GPU(s), scene replicated, "
+                                      "frame-end NCCL gather to rank 0" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2: ~0.9 GB of per-frame path state streams through every bounce "
+                             "(L2 126 MB); the 15 MB BVH+triangles stay L2-resident by design"},
+            "roofline": {"kernel": "k_traverse_closest", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": closest_bytes / n_launch / world,
+                         "avg_launch_ms": t_closest_ms / n_launch,
+                         "nodes_per_ray": counts[1] / max(1.0, counts[0]), "tris_per_ray": counts[2] / max(1.0, counts[0])},
+            "roofline_any_hit": {"kernel": "k_traverse_any",
+                                 "achieved": any_bytes / world / (stage_acc["traverse_any"] * 1e-3) / 1e9,
+                                 "unit": "GB/s", "nodes_per_ray": counts[4] / max(1.0, counts[3]),
+                                 "tris_per_ray": counts[5] / max(1.0, counts[3])},
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()},
+            "e2e": {"value": e2e_rays / (e2e_ms * 1e3), "unit": "MRays/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": 52,  # ViewParams (camera basis + frame id) as kernel parameters
+                    "d2h_bytes_per_step": WIDTH * HEIGHT * 4 + 36 * 4},
+            "gpu_launches": int(launches),
+            "clocks": clock_summary,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            res, _ = time_oracle(scene, view, budget_s=20.0, frames_cap=6)
+            warm = res[1:] if len(res) > 1 else res
+            cms = sum(r[0] for r in warm)
+            crays = sum(r[1] for r in warm)
+            line["cpu_baseline"] = {
+                "value": crays / (cms * 1e3), "unit": "MRays/s", "cores": cpu_cores(), "kind": "port",
+                "ms_per_frame": cms / len(warm),
+                "sample": f"{len(warm)} full frame(s) of the same workload (1 warm-up frame discarded); CPU oracle "
+                          "= Embree/ISPC backend restated with an own BVH2, -O3 x86-64-v3, all host threads"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -25,7 +25,8 @@ _LIB_PATH = os.path.join(_CSRC, "libcrt_cuda_core.so")
 _lib: Optional[C.CDLL] = None
 
 STAGE_NAMES = ("raygen", "traverse_closest", "shade", "traverse_any", "nee_resolve", "resolve", "frame")
-COUNTER_NAMES = ("closest_rays", "occlusion_rays", "kernel_launches", "nodes_visited", "tris_tested", "paths")
+COUNTER_NAMES = ("closest_rays", "occlusion_rays", "kernel_launches", "closest_nodes_visited", "closest_tris_tested",
+                 "paths", "any_nodes_visited", "any_tris_tested")
 SCENE_INFO_NAMES = ("triangles", "bvh8_nodes", "bvh8_depth", "bvh_build_ms", "node_bytes", "triangle_bytes")
 
 # Every symbol include/crt_cuda.h declares (tests check the library exports all of them).

@@ -115,7 +115,7 @@ struct crtc_renderer {
     std::vector<cudaEvent_t> events;
     std::vector<int> event_stage;  // stage that ENDS at event i (i >= 1)
     float stage_ms[kNumStages] = {0};
-    uint64_t counters_out[6] = {0};
+    uint64_t counters_out[8] = {0};
     uint32_t *h_counters = nullptr;  // pinned
     unsigned long long *h_trav = nullptr;
 
@@ -203,11 +203,11 @@ struct crtc_renderer {
         d_queue0.alloc(npaths);
         d_queue1.alloc(npaths);
         d_counters.alloc(crt::kNumCounters);
-        d_trav_counters.alloc(2);
+        d_trav_counters.alloc(4);
         path_capacity = npaths;
         if (!h_counters) {
             CUDA_CHECK(cudaMallocHost(&h_counters, crt::kNumCounters * sizeof(uint32_t)));
-            CUDA_CHECK(cudaMallocHost(&h_trav, 2 * sizeof(unsigned long long)));
+            CUDA_CHECK(cudaMallocHost(&h_trav, 4 * sizeof(unsigned long long)));
         }
     }
 
@@ -377,7 +377,7 @@ struct crtc_renderer {
         next_event(ev, -1);
         CUDA_CHECK(cudaMemsetAsync(d_counters.ptr, 0, crt::kNumCounters * sizeof(uint32_t), stream));
         if (count_traversal) {
-            CUDA_CHECK(cudaMemsetAsync(d_trav_counters.ptr, 0, 2 * sizeof(unsigned long long), stream));
+            CUDA_CHECK(cudaMemsetAsync(d_trav_counters.ptr, 0, 4 * sizeof(unsigned long long), stream));
         }
         if (npaths) {
             const unsigned g256 = (unsigned)((npaths + 255) / 256);
@@ -415,7 +415,7 @@ struct crtc_renderer {
         CUDA_CHECK(cudaMemcpyAsync(h_counters, d_counters.ptr, crt::kNumCounters * sizeof(uint32_t),
                                    cudaMemcpyDeviceToHost, stream));
         if (count_traversal) {
-            CUDA_CHECK(cudaMemcpyAsync(h_trav, d_trav_counters.ptr, 2 * sizeof(unsigned long long),
+            CUDA_CHECK(cudaMemcpyAsync(h_trav, d_trav_counters.ptr, 4 * sizeof(unsigned long long),
                                        cudaMemcpyDeviceToHost, stream));
         }
         if (readback && img && world_size == 1) {
@@ -447,6 +447,8 @@ struct crtc_renderer {
         counters_out[3] = count_traversal ? h_trav[0] : 0;
         counters_out[4] = count_traversal ? h_trav[1] : 0;
         counters_out[5] = h_counters[crt::kCntQueue];
+        counters_out[6] = count_traversal ? h_trav[2] : 0;
+        counters_out[7] = count_traversal ? h_trav[3] : 0;
         if (stats) {
             stats->render_time = stage_ms[kStFrame];
             stats->num_rays = closest + shadow;
@@ -795,7 +797,7 @@ int crtc_get_stage_times(crtc_renderer *r, float *ms_out, int n)
 
 int crtc_get_counters(crtc_renderer *r, uint64_t *out, int n)
 {
-    const int m = std::min(n, 6);
+    const int m = std::min(n, 8);
     for (int i = 0; i < m; ++i) {
         out[i] = r->counters_out[i];
     }

@@ -75,7 +75,7 @@ struct PathState {
     uint8_t *vis;      // 2 per path slot: 1 = unoccluded
     uint32_t *queue[2];
     uint32_t *counters;
-    unsigned long long *trav_counters;  // [0] nodes visited, [1] triangles tested
+    unsigned long long *trav_counters;  // closest: [0] nodes visited [1] triangles tested; any-hit: [2], [3]
 };
 
 // Local pixel index -> framebuffer coordinates. Within a 64x64 tile pixels are ordered in
@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(128) k_traverse_any(DeviceScene sc, PathState 
             t += __shfl_down_sync(0xffffffffu, t, off);
         }
         if ((threadIdx.x & 31) == 0) {
-            atomicAdd(ps.trav_counters, n);
-            atomicAdd(ps.trav_counters + 1, t);
+            atomicAdd(ps.trav_counters + 2, n);
+            atomicAdd(ps.trav_counters + 3, t);
         }
     }
 }

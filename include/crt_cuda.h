@@ -94,8 +94,9 @@ int crtc_read_accum(crtc_renderer *r, float *rgb_out);
 int crtc_get_stage_times(crtc_renderer *r, float *ms_out, int n);
 
 /* Counters of the last frame: [0] closest-hit rays [1] occlusion rays [2] kernel launches
- * [3] BVH nodes visited [4] triangles tested ([3],[4] only with count_traversal=1)
- * [5] paths started. */
+ * [3] BVH nodes visited and [4] triangles tested by closest-hit traversal [5] paths started
+ * [6] nodes visited and [7] triangles tested by any-hit traversal ([3],[4],[6],[7] only with
+ * count_traversal=1). */
 int crtc_get_counters(crtc_renderer *r, uint64_t *out, int n);
 
 /* Scene/BVH facts: [0] triangles [1] BVH8 nodes [2] BVH depth [3] build ms [4] node bytes
