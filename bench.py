@@ -204,7 +204,10 @@ def main():
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
 
     scene, view = make_workload()
-    stream = torch.cuda.current_stream(dev)
+    # a dedicated (non-default) torch stream: the renderer launches on it, so torch.cuda.Event
+    # brackets exactly the kernels of the timed region
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     gpu = RenderCUDA(local_rank, max_depth=MAX_DEPTH, rank=rank, world_size=world, stream=stream.cuda_stream)
     gpu.initialize(WIDTH, HEIGHT)
     gpu.set_scene(scene)
