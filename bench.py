@@ -179,6 +179,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="for runs under ncu: skip the instrumented counting pass and the CPU baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else max(args.warmup, 1)
 
@@ -226,8 +228,8 @@ def main():
         return st
 
     # ---- instrumented pass (not timed): exact node/triangle visit counts of the same frames ----
-    counts = None
-    if True:
+    counts = np.zeros(6, np.float64)
+    if not args.profile_mode:
         inst = RenderCUDA(local_rank, max_depth=MAX_DEPTH, rank=rank, world_size=world, count_traversal=True,
                           stream=stream.cuda_stream)
         inst.initialize(WIDTH, HEIGHT)
@@ -333,7 +335,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clock_summary,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and not args.profile_mode and world == 1:
             res, _ = time_oracle(scene, view, budget_s=20.0, frames_cap=6)
             warm = res[1:] if len(res) > 1 else res
             cms = sum(r[0] for r in warm)

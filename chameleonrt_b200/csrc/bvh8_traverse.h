@@ -147,137 +147,175 @@ struct TraversalCounters {
     uint32_t tris = 0;
 };
 
-// ANY_HIT: return at the first accepted triangle. COUNT: fill counters (instrumented build
-// used to derive the algorithmic byte count of SURVEY.md §8d).
+// Plain per-thread array stack (host check; device fallback).
+struct ArrayStack {
+    uint2 e[CRT_STACK_SIZE];
+    int sp = 0;
+    CRT_HD void push(const uint2 v) { e[sp++] = v; }
+    CRT_HD uint2 pop() { return e[--sp]; }
+    CRT_HD bool empty() const { return sp == 0; }
+    CRT_HD void clear() { sp = 0; }
+};
+
+// Resumable traversal state of one ray: everything derived from the ray that the node step
+// needs, the current node group, and the best hit so far.
+struct TravState {
+    Ray ray;
+    float idx, idy, idz;
+    uint32_t oct_inv4;
+    float tfar;
+    uint2 cur;
+    HitRecord hit;
+};
+
+CRT_HD void trav_init(TravState &s, const Ray &ray)
+{
+    s.ray = ray;
+    // direction reciprocal with the usual guard for zero components
+    const float eps = 1e-20f;
+    s.idx = 1.f / (fabsf(ray.dx) > eps ? ray.dx : (ray.dx < 0.f ? -eps : eps));
+    s.idy = 1.f / (fabsf(ray.dy) > eps ? ray.dy : (ray.dy < 0.f ? -eps : eps));
+    s.idz = 1.f / (fabsf(ray.dz) > eps ? ray.dz : (ray.dz < 0.f ? -eps : eps));
+    s.oct_inv4 =
+        ((ray.dx < 0.f ? 0u : 0x04040404u) | (ray.dy < 0.f ? 0u : 0x02020202u) | (ray.dz < 0.f ? 0u : 0x01010101u));
+    s.tfar = ray.tfar;
+    s.hit.t = ray.tfar;
+    s.hit.u = s.hit.v = 0.f;
+    s.hit.tri = 0xffffffffu;
+    s.hit.flat = 0xffffffffu;
+    s.cur.x = 0;
+    s.cur.y = 0x80000000u;  // root: "inner child in slot 7 of a virtual parent"
+}
+
+// One traversal step: intersect one node (or take a popped triangle group), test the
+// triangles it yields, pop the next group. Returns true when the ray is finished.
+// ANY_HIT: finish at the first accepted triangle. COUNT: fill counters (instrumented build used
+// to derive the algorithmic byte count of SURVEY.md §8d).
+template <bool ANY_HIT, bool COUNT, typename Stack>
+CRT_HD bool trav_step(const float4 *__restrict__ nodes, const float4 *__restrict__ tris, TravState &s, Stack &stack,
+                      TraversalCounters *counters)
+{
+    const Ray &ray = s.ray;
+    uint2 tri_group;
+    if (s.cur.y & 0xff000000u) {
+        const uint32_t hits_imask = s.cur.y;
+        const int child_bit = msb(hits_imask);
+        s.cur.y &= ~(1u << child_bit);
+        if (s.cur.y & 0xff000000u) {
+            stack.push(s.cur);
+        }
+        const uint32_t slot_index = (uint32_t)(child_bit - 24) ^ (s.oct_inv4 & 0xffu);
+        const uint32_t rel = (uint32_t)popc(hits_imask & ~(0xffffffffu << slot_index));
+        const uint32_t node_index = s.cur.x + rel;
+        const float4 *np = nodes + (size_t)node_index * 5;
+        const float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
+        if (COUNT) {
+            counters->nodes++;
+        }
+        const uint32_t e_imask = f2u(n0.w);
+        const float adx = u2f((e_imask & 0xffu) << 23) * s.idx;
+        const float ady = u2f(((e_imask >> 8) & 0xffu) << 23) * s.idy;
+        const float adz = u2f(((e_imask >> 16) & 0xffu) << 23) * s.idz;
+        const float obx = (n0.x - ray.ox) * s.idx;
+        const float oby = (n0.y - ray.oy) * s.idy;
+        const float obz = (n0.z - ray.oz) * s.idz;
+        // Rounding slack: the plane distances below are fma(q, ad, ob) with |ob| possibly much
+        // larger than the result, so their absolute error scales with |ob| + 255|ad|. Widening
+        // the interval by that bound keeps the box test conservative with respect to the
+        // (independently rounded) triangle test, including for equal-t ties.
+        const float slack = 4e-7f * (fmaxf_(fmaxf_(fabsf(obx), fabsf(oby)), fabsf(obz)) +
+                                     255.f * fmaxf_(fmaxf_(fabsf(adx), fabsf(ady)), fabsf(adz)));
+        const float tmax_cap = s.tfar + slack;
+        const float tmin_cap = ray.tnear - slack;
+        uint32_t hitmask = 0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const uint32_t meta4 = f2u(half == 0 ? n1.z : n1.w);
+            const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+            const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+            const uint32_t bit_index4 = (meta4 ^ (s.oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+            const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+            const uint32_t qlox = f2u(half == 0 ? n2.x : n2.y), qloy = f2u(half == 0 ? n2.z : n2.w);
+            const uint32_t qloz = f2u(half == 0 ? n3.x : n3.y), qhix = f2u(half == 0 ? n3.z : n3.w);
+            const uint32_t qhiy = f2u(half == 0 ? n4.x : n4.y), qhiz = f2u(half == 0 ? n4.z : n4.w);
+            const uint32_t xmin = ray.dx < 0.f ? qhix : qlox, xmax = ray.dx < 0.f ? qlox : qhix;
+            const uint32_t ymin = ray.dy < 0.f ? qhiy : qloy, ymax = ray.dy < 0.f ? qloy : qhiy;
+            const uint32_t zmin = ray.dz < 0.f ? qhiz : qloz, zmax = ray.dz < 0.f ? qloz : qhiz;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float tminx = fma_((float)((xmin >> (8 * j)) & 0xffu), adx, obx);
+                const float tminy = fma_((float)((ymin >> (8 * j)) & 0xffu), ady, oby);
+                const float tminz = fma_((float)((zmin >> (8 * j)) & 0xffu), adz, obz);
+                const float tmaxx = fma_((float)((xmax >> (8 * j)) & 0xffu), adx, obx);
+                const float tmaxy = fma_((float)((ymax >> (8 * j)) & 0xffu), ady, oby);
+                const float tmaxz = fma_((float)((zmax >> (8 * j)) & 0xffu), adz, obz);
+                // (tmin - slack) <= (tmax + slack), with the caps carrying the slack
+                const float tmin = fmaxf_(fmaxf_(tminx, tminy), fmaxf_(tminz, tmin_cap));
+                const float tmax = fminf_(fminf_(tmaxx, tmaxy), fminf_(tmaxz, tmax_cap));
+                if (tmin <= tmax + slack) {
+                    const uint32_t bits = (child_bits4 >> (8 * j)) & 0xffu;
+                    const uint32_t idx_ = (bit_index4 >> (8 * j)) & 0xffu;
+                    hitmask |= bits << idx_;
+                }
+            }
+        }
+        s.cur.x = f2u(n1.x);
+        s.cur.y = (hitmask & 0xff000000u) | (e_imask >> 24);
+        tri_group.x = f2u(n1.y);
+        tri_group.y = hitmask & 0x00ffffffu;
+    } else {
+        tri_group = s.cur;
+        s.cur.x = 0;
+        s.cur.y = 0;
+    }
+
+    while (tri_group.y) {
+        const int ti = msb(tri_group.y);
+        tri_group.y &= ~(1u << ti);
+        const uint32_t tri_index = tri_group.x + (uint32_t)ti;
+        const float4 *tp = tris + (size_t)tri_index * 3;
+        const float4 t0 = tp[0], t1 = tp[1], t2 = tp[2];
+        if (COUNT) {
+            counters->tris++;
+        }
+        float t, u, v;
+        // once a hit exists, t == tfar is still let through so ties resolve by primitive id
+        if (tri_test(ray, s.hit.tri == 0xffffffffu ? s.tfar : INFINITY, t0, t1, t2, t, u, v)) {
+            const uint32_t flat = f2u(t0.w);
+            if (t < s.tfar || (t == s.tfar && s.hit.tri != 0xffffffffu && flat < s.hit.flat)) {
+                s.hit.t = t;
+                s.hit.u = u;
+                s.hit.v = v;
+                s.hit.tri = tri_index;
+                s.hit.flat = flat;
+                s.tfar = t;
+                if (ANY_HIT) {
+                    return true;
+                }
+            }
+        }
+    }
+
+    if ((s.cur.y & 0xff000000u) == 0) {
+        if (stack.empty()) {
+            return true;
+        }
+        s.cur = stack.pop();
+    }
+    return false;
+}
+
+// Whole-ray convenience wrapper (host check, simple device paths).
 template <bool ANY_HIT, bool COUNT>
 CRT_HD bool bvh8_trace(const float4 *__restrict__ nodes, const float4 *__restrict__ tris, const Ray &ray,
                        HitRecord &hit, TraversalCounters *counters)
 {
-    // direction reciprocal with the usual guard for zero components
-    const float eps = 1e-20f;
-    const float idx = 1.f / (fabsf(ray.dx) > eps ? ray.dx : (ray.dx < 0.f ? -eps : eps));
-    const float idy = 1.f / (fabsf(ray.dy) > eps ? ray.dy : (ray.dy < 0.f ? -eps : eps));
-    const float idz = 1.f / (fabsf(ray.dz) > eps ? ray.dz : (ray.dz < 0.f ? -eps : eps));
-    const uint32_t oct_inv4 =
-        ((ray.dx < 0.f ? 0u : 0x04040404u) | (ray.dy < 0.f ? 0u : 0x02020202u) | (ray.dz < 0.f ? 0u : 0x01010101u));
-
-    float tfar = ray.tfar;
-    hit.t = ray.tfar;
-    hit.u = hit.v = 0.f;
-    hit.tri = 0xffffffffu;
-    hit.flat = 0xffffffffu;
-
-    uint2 stack[CRT_STACK_SIZE];
-    int sp = 0;
-    uint2 cur;
-    cur.x = 0;
-    cur.y = 0x80000000u;  // root: "inner child in slot 7 of a virtual parent"
-
-    for (;;) {
-        uint2 tri_group;
-        if (cur.y & 0xff000000u) {
-            const uint32_t hits_imask = cur.y;
-            const int child_bit = msb(hits_imask);
-            cur.y &= ~(1u << child_bit);
-            if (cur.y & 0xff000000u) {
-                stack[sp++] = cur;
-            }
-            const uint32_t slot_index = (uint32_t)(child_bit - 24) ^ (oct_inv4 & 0xffu);
-            const uint32_t rel = (uint32_t)popc(hits_imask & ~(0xffffffffu << slot_index));
-            const uint32_t node_index = cur.x + rel;
-            const float4 *np = nodes + (size_t)node_index * 5;
-            const float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
-            if (COUNT) {
-                counters->nodes++;
-            }
-            const uint32_t e_imask = f2u(n0.w);
-            const float adx = u2f((e_imask & 0xffu) << 23) * idx;
-            const float ady = u2f(((e_imask >> 8) & 0xffu) << 23) * idy;
-            const float adz = u2f(((e_imask >> 16) & 0xffu) << 23) * idz;
-            const float obx = (n0.x - ray.ox) * idx;
-            const float oby = (n0.y - ray.oy) * idy;
-            const float obz = (n0.z - ray.oz) * idz;
-            // Rounding slack: the plane distances below are fma(q, ad, ob) with |ob| possibly much
-            // larger than the result, so their absolute error scales with |ob| + 255|ad|. Widening
-            // the interval by that bound keeps the box test conservative with respect to the
-            // (independently rounded) triangle test, including for equal-t ties.
-            const float slack = 4e-7f * (fmaxf_(fmaxf_(fabsf(obx), fabsf(oby)), fabsf(obz)) +
-                                         255.f * fmaxf_(fmaxf_(fabsf(adx), fabsf(ady)), fabsf(adz)));
-            uint32_t hitmask = 0;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const uint32_t meta4 = f2u(half == 0 ? n1.z : n1.w);
-                const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-                const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-                const uint32_t bit_index4 = (meta4 ^ (oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
-                const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-                const uint32_t qlox = f2u(half == 0 ? n2.x : n2.y), qloy = f2u(half == 0 ? n2.z : n2.w);
-                const uint32_t qloz = f2u(half == 0 ? n3.x : n3.y), qhix = f2u(half == 0 ? n3.z : n3.w);
-                const uint32_t qhiy = f2u(half == 0 ? n4.x : n4.y), qhiz = f2u(half == 0 ? n4.z : n4.w);
-                const uint32_t xmin = ray.dx < 0.f ? qhix : qlox, xmax = ray.dx < 0.f ? qlox : qhix;
-                const uint32_t ymin = ray.dy < 0.f ? qhiy : qloy, ymax = ray.dy < 0.f ? qloy : qhiy;
-                const uint32_t zmin = ray.dz < 0.f ? qhiz : qloz, zmax = ray.dz < 0.f ? qloz : qhiz;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float tminx = fma_((float)((xmin >> (8 * j)) & 0xffu), adx, obx);
-                    const float tminy = fma_((float)((ymin >> (8 * j)) & 0xffu), ady, oby);
-                    const float tminz = fma_((float)((zmin >> (8 * j)) & 0xffu), adz, obz);
-                    const float tmaxx = fma_((float)((xmax >> (8 * j)) & 0xffu), adx, obx);
-                    const float tmaxy = fma_((float)((ymax >> (8 * j)) & 0xffu), ady, oby);
-                    const float tmaxz = fma_((float)((zmax >> (8 * j)) & 0xffu), adz, obz);
-                    const float tmin = fmaxf_(fmaxf_(tminx, tminy), fmaxf_(tminz, ray.tnear));
-                    const float tmax = fminf_(fminf_(tmaxx, tmaxy), fminf_(tmaxz, tfar)) + slack;
-                    if (tmin <= tmax) {
-                        const uint32_t bits = (child_bits4 >> (8 * j)) & 0xffu;
-                        const uint32_t idx_ = (bit_index4 >> (8 * j)) & 0xffu;
-                        hitmask |= bits << idx_;
-                    }
-                }
-            }
-            cur.x = f2u(n1.x);
-            cur.y = (hitmask & 0xff000000u) | (e_imask >> 24);
-            tri_group.x = f2u(n1.y);
-            tri_group.y = hitmask & 0x00ffffffu;
-        } else {
-            tri_group = cur;
-            cur.x = 0;
-            cur.y = 0;
-        }
-
-        while (tri_group.y) {
-            const int ti = msb(tri_group.y);
-            tri_group.y &= ~(1u << ti);
-            const uint32_t tri_index = tri_group.x + (uint32_t)ti;
-            const float4 *tp = tris + (size_t)tri_index * 3;
-            const float4 t0 = tp[0], t1 = tp[1], t2 = tp[2];
-            if (COUNT) {
-                counters->tris++;
-            }
-            float t, u, v;
-            // tfar + tie handling: accept t == tfar only to resolve ties by primitive id
-            if (tri_test(ray, hit.tri == 0xffffffffu ? tfar : INFINITY, t0, t1, t2, t, u, v)) {
-                const uint32_t flat = f2u(t0.w);
-                if (t < tfar || (t == tfar && hit.tri != 0xffffffffu && flat < hit.flat)) {
-                    hit.t = t;
-                    hit.u = u;
-                    hit.v = v;
-                    hit.tri = tri_index;
-                    hit.flat = flat;
-                    tfar = t;
-                    if (ANY_HIT) {
-                        return true;
-                    }
-                }
-            }
-        }
-
-        if ((cur.y & 0xff000000u) == 0) {
-            if (sp == 0) {
-                break;
-            }
-            cur = stack[--sp];
-        }
+    TravState s;
+    trav_init(s, ray);
+    ArrayStack stack;
+    while (!trav_step<ANY_HIT, COUNT>(nodes, tris, s, stack, counters)) {
     }
+    hit = s.hit;
     return hit.tri != 0xffffffffu;
 }
 

@@ -137,6 +137,34 @@ struct crtc_renderer {
 
     void make_current() { CUDA_CHECK(cudaSetDevice(device)); }
 
+    // persistent traversal grid: every SM filled with as many blocks as fit
+    unsigned trav_grid = 0;
+    void launch_traverse(bool any_hit, const crt::DeviceScene &sc, const crt::PathState &ps, const uint32_t *queue,
+                         const uint32_t *count_ptr, uint32_t *work_counter)
+    {
+        if (trav_grid == 0) {
+            int sms = 0, per_sm = 0;
+            CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crt::k_traverse<false, false>,
+                                                                     crt::kTravBlock, 0));
+            trav_grid = (unsigned)(sms * std::max(1, per_sm));
+        }
+        const unsigned g = trav_grid;
+        if (any_hit) {
+            if (count_traversal) {
+                crt::k_traverse<true, true><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter);
+            } else {
+                crt::k_traverse<true, false><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter);
+            }
+        } else {
+            if (count_traversal) {
+                crt::k_traverse<false, true><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter);
+            } else {
+                crt::k_traverse<false, false><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter);
+            }
+        }
+    }
+
     crt::DeviceScene device_scene() const
     {
         crt::DeviceScene sc;
@@ -387,19 +415,11 @@ struct crtc_renderer {
             next_event(ev, kStRaygen);
             for (int b = 0; b < max_depth; ++b) {
                 uint32_t *qin = ps.queue[b & 1], *qout = ps.queue[(b + 1) & 1];
-                if (count_traversal) {
-                    crt::k_traverse_closest<true><<<g128, 128, 0, stream>>>(sc, ps, qin, ps.counters + crt::kCntQueue + b);
-                } else {
-                    crt::k_traverse_closest<false><<<g128, 128, 0, stream>>>(sc, ps, qin, ps.counters + crt::kCntQueue + b);
-                }
+                launch_traverse(false, sc, ps, qin, ps.counters + crt::kCntQueue + b, ps.counters + crt::kCntWorkClosest + b);
                 next_event(ev, kStClosest);
                 crt::k_shade<<<g128, 128, 0, stream>>>(sc, ps, qin, qout, b, max_depth);
                 next_event(ev, kStShade);
-                if (count_traversal) {
-                    crt::k_traverse_any<true><<<2 * g128, 128, 0, stream>>>(sc, ps, ps.counters + crt::kCntShadow + b);
-                } else {
-                    crt::k_traverse_any<false><<<2 * g128, 128, 0, stream>>>(sc, ps, ps.counters + crt::kCntShadow + b);
-                }
+                launch_traverse(true, sc, ps, nullptr, ps.counters + crt::kCntShadow + b, ps.counters + crt::kCntWorkAny + b);
                 next_event(ev, kStAny);
                 crt::k_nee_resolve<<<g256, 256, 0, stream>>>(ps, qin, b);
                 next_event(ev, kStNee);
@@ -474,16 +494,15 @@ struct crtc_renderer {
         CUDA_CHECK(cudaStreamSynchronize(stream));
     }
 
-    void launch_closest(uint64_t n)
+    void reset_work_counters()
     {
-        const crt::DeviceScene sc = device_scene();
-        const crt::PathState ps = path_state();
-        const unsigned g = (unsigned)((n + 127) / 128);
-        if (count_traversal) {
-            crt::k_traverse_closest<true><<<g, 128, 0, stream>>>(sc, ps, nullptr, ps.counters);
-        } else {
-            crt::k_traverse_closest<false><<<g, 128, 0, stream>>>(sc, ps, nullptr, ps.counters);
-        }
+        CUDA_CHECK(cudaMemsetAsync(d_counters.ptr + crt::kCntWorkClosest, 0, 2 * sizeof(uint32_t), stream));
+    }
+
+    void launch_closest(uint64_t)
+    {
+        CUDA_CHECK(cudaMemsetAsync(d_counters.ptr + crt::kCntWorkClosest, 0, sizeof(uint32_t), stream));
+        launch_traverse(false, device_scene(), path_state(), nullptr, d_counters.ptr, d_counters.ptr + crt::kCntWorkClosest);
     }
 
     // shadow-ray layout for the any-hit kernel: sray_o = org|tfar, sray_d = dir|bits(index)
@@ -504,16 +523,10 @@ struct crtc_renderer {
         CUDA_CHECK(cudaStreamSynchronize(stream));
     }
 
-    void launch_any(uint64_t n)
+    void launch_any(uint64_t)
     {
-        const crt::DeviceScene sc = device_scene();
-        const crt::PathState ps = path_state();
-        const unsigned g = (unsigned)((n + 127) / 128);
-        if (count_traversal) {
-            crt::k_traverse_any<true><<<g, 128, 0, stream>>>(sc, ps, ps.counters);
-        } else {
-            crt::k_traverse_any<false><<<g, 128, 0, stream>>>(sc, ps, ps.counters);
-        }
+        CUDA_CHECK(cudaMemsetAsync(d_counters.ptr + crt::kCntWorkAny, 0, sizeof(uint32_t), stream));
+        launch_traverse(true, device_scene(), path_state(), nullptr, d_counters.ptr, d_counters.ptr + crt::kCntWorkAny);
     }
 
     void require_scene() const

