@@ -1,0 +1,40 @@
+// render_cuda.h — RenderCUDA, the `crt_cuda` backend of ChameleonRT.
+//
+// Drop this directory into ChameleonRT as backends/cuda/ (see INTEGRATION.md): it is built as
+// the MODULE library libcrt_cuda.so that `./chameleonrt cuda <scene>` dlopen()s
+// (util/render_plugin.cpp:14-37). The class has the shape of the reference's other backends
+// (cf. backends/embree/render_embree.h:12-44, backends/optix/render_optix.h); all rendering is
+// delegated to the C ABI of include/crt_cuda.h (libcrt_cuda_core.so: host BVH8 build + the
+// sm_100a wavefront kernels).
+#pragma once
+
+#include <string>
+#include "render_backend.h"
+
+struct crtc_renderer;
+
+struct RenderCUDA : RenderBackend {
+    crtc_renderer *renderer = nullptr;
+    glm::ivec2 fb_dims = glm::ivec2(0);
+    bool native_display = false;
+
+    RenderCUDA();
+    ~RenderCUDA() override;
+
+    std::string name() override;
+    void initialize(const int fb_width, const int fb_height) override;
+    void set_scene(const Scene &scene) override;
+    RenderStats render(const glm::vec3 &pos,
+                       const glm::vec3 &dir,
+                       const glm::vec3 &up,
+                       const float fovy,
+                       const bool camera_changed,
+                       const bool readback_framebuffer) override;
+
+    // Extra export for parity harnesses: the accumulated float framebuffer,
+    // row-major RGB, fb_width * fb_height * 3 floats.
+    void read_accum(float *rgb_out);
+};
+
+// C entry point so a harness that only has the RenderBackend* can read the float framebuffer
+extern "C" int crt_cuda_read_accum(RenderBackend *backend, float *rgb_out);

@@ -1,0 +1,68 @@
+"""The drop-in boundary exercised the way ChameleonRT exercises it: the headless twin of the app
+(oracle/ref_build/crt_headless.cpp) loads `libcrt_<backend>.so` through the REFERENCE'S OWN
+RenderPlugin class, loads an .obj with the reference's own Scene loader, and drives
+initialize / set_scene / render. Binaries live in oracle/_ref/ (built by __graft_entry__.build()
+where /root/reference exists; they travel to the GPU box as built artefacts)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from chameleonrt_b200.obj_io import write_obj
+from chameleonrt_b200.scenes import cornell_box, sponza_like
+from helpers import ROOT, assert_parity
+
+REF = os.path.join(ROOT, "oracle", "_ref")
+HEADLESS = os.path.join(REF, "crt_headless")
+
+needs_ref = pytest.mark.skipif(not os.path.exists(HEADLESS), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def run_headless(backend, obj, cam, w, h, spp, frames, tmp_path, depth=5):
+    out = tmp_path / f"accum_{backend}.f32"
+    cmd = [HEADLESS, backend, obj, "-img", str(w), str(h), "-spp", str(spp), "-benchmark-frames", str(frames),
+           "-accum", str(out), "-eye", *map(str, cam["eye"]), "-center", *map(str, cam["center"]),
+           "-up", *map(str, cam["up"]), "-fov", str(cam["fov_y"])]
+    env = dict(os.environ, CRT_CUDA_MAX_DEPTH=str(depth))
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=str(tmp_path), env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    cam_line = [l for l in r.stdout.splitlines() if l.startswith("camera:")][0].split()[1:]
+    vec = [float.fromhex(x) for x in cam_line]
+    accum = np.fromfile(out, np.float32).reshape(h, w, 3)
+    assert os.path.exists(tmp_path / "chameleonrt.png")  # main.cpp:306-314 writes the final image
+    return accum, vec, r.stdout
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["cornell", "sponza"])
+def test_reference_loader_matches_python_scene_model(built, tmp_path, name):
+    """OBJ written by obj_io -> reference's load_obj (tinyobj, stb_image) -> oracle plugin must be
+    bit-identical to the oracle fed the in-memory Python Scene: pins chameleonrt_b200.scene /
+    scenes / obj_io against util/scene.cpp:94-228 (materials, generated light, texture flip)."""
+    from oracle import OracleBackend
+
+    scene, cam = cornell_box(spp=2) if name == "cornell" else sponza_like(spp=2, detail=0.2, tex_size=64)
+    obj = write_obj(scene, str(tmp_path / "scene.obj"))
+    accum, v, out = run_headless("oracle", obj, cam, 96, 64, 2, 2, tmp_path)
+    assert f"tris {scene.total_tris()}" in out and f"materials {len(scene.materials)}" in out
+    o = OracleBackend()
+    o.initialize(96, 64)
+    o.set_scene(scene)
+    for f in range(2):
+        o.render(v[0:3], v[3:6], v[6:9], v[9], f == 0)
+    assert (accum.view(np.uint32) == o.read_accum().view(np.uint32)).all()
+
+
+@needs_ref
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cornell", "sponza"])
+def test_cuda_plugin_drop_in(built, tmp_path, name):
+    """`crt_headless cuda scene.obj` vs `crt_headless oracle scene.obj`: the whole drop-in path
+    (dlopen + POPULATE_PLUGIN_FUNCTIONS + RenderCUDA : RenderBackend + C ABI + kernels)."""
+    scene, cam = cornell_box(spp=2) if name == "cornell" else sponza_like(spp=2, detail=0.3, tex_size=64)
+    obj = write_obj(scene, str(tmp_path / "scene.obj"))
+    a_gpu, v1, out = run_headless("cuda", obj, cam, 160, 96, 2, 2, tmp_path)
+    a_cpu, v2, _ = run_headless("oracle", obj, cam, 160, 96, 2, 2, tmp_path)
+    assert v1 == v2 and "CUDA wavefront" in out
+    assert_parity(a_gpu, a_cpu)
