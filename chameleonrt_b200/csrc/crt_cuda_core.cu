@@ -80,6 +80,7 @@ struct crtc_renderer {
     int rank = 0, world_size = 1;
     int bvh_threads = 0;
     bool count_traversal = false;
+    int tri_lanes = crt::kTriLanes, refill_idle = crt::kRefillIdle, trav_variant = 1;  // traversal scheduling knobs
 
     // framebuffer layout
     int fb_w = 0, fb_h = 0;
@@ -152,15 +153,15 @@ struct crtc_renderer {
         const unsigned g = trav_grid;
         if (any_hit) {
             if (count_traversal) {
-                crt::k_traverse<true, true><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter);
+                crt::k_traverse<true, true><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter, tri_lanes, refill_idle, trav_variant);
             } else {
-                crt::k_traverse<true, false><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter);
+                crt::k_traverse<true, false><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter, tri_lanes, refill_idle, trav_variant);
             }
         } else {
             if (count_traversal) {
-                crt::k_traverse<false, true><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter);
+                crt::k_traverse<false, true><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter, tri_lanes, refill_idle, trav_variant);
             } else {
-                crt::k_traverse<false, false><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter);
+                crt::k_traverse<false, false><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter, tri_lanes, refill_idle, trav_variant);
             }
         }
     }
@@ -737,6 +738,12 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
             r->bvh_threads = (int)value;
         } else if (k == "count_traversal") {
             r->count_traversal = value != 0;
+        } else if (k == "trav_variant") {
+            r->trav_variant = (int)value;
+        } else if (k == "tri_lanes") {
+            r->tri_lanes = (int)std::min<int64_t>(std::max<int64_t>(value, 1), 32);
+        } else if (k == "refill_idle") {
+            r->refill_idle = (int)std::min<int64_t>(std::max<int64_t>(value, 1), 32);
         } else {
             throw std::runtime_error("unknown option '" + k + "'");
         }

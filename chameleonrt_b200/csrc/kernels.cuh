@@ -154,6 +154,7 @@ constexpr int kTravBlock = 128;
 constexpr int kSmemStack = 8;
 constexpr int kRefillIdle = 4;
 constexpr uint32_t kFetchBatch = 64;
+constexpr int kTriLanes = 8;  // run the triangle phase when this many lanes have a triangle pending
 
 struct HybridStack {
     uint2 *sm;  // this thread's column of the block's shared stack: sm[i * kTravBlock]
@@ -173,6 +174,11 @@ struct HybridStack {
         --sp;
         return sp < kSmemStack ? sm[sp * kTravBlock] : local[sp - kSmemStack];
     }
+    __device__ __forceinline__ uint2 peek() const
+    {
+        return sp - 1 < kSmemStack ? sm[(sp - 1) * kTravBlock] : local[sp - 1 - kSmemStack];
+    }
+    __device__ __forceinline__ void drop() { --sp; }
     __device__ __forceinline__ bool empty() const { return sp == 0; }
 };
 
@@ -181,7 +187,8 @@ struct HybridStack {
 // ANY_HIT = true : rays from sray_o/sray_d, result to vis[]   (rtcOccludedV, :144,170)
 template <bool ANY_HIT, bool COUNT>
 __global__ void __launch_bounds__(kTravBlock)
-    k_traverse(DeviceScene sc, PathState ps, const uint32_t *queue, const uint32_t *count_ptr, uint32_t *work_counter)
+    k_traverse(DeviceScene sc, PathState ps, const uint32_t *queue, const uint32_t *count_ptr, uint32_t *work_counter,
+               int tri_lanes, int refill_idle, int variant)
 {
     __shared__ uint2 sm_stack[kSmemStack * kTravBlock];
     const uint32_t count = *count_ptr;
@@ -192,6 +199,7 @@ __global__ void __launch_bounds__(kTravBlock)
     stack.sm = sm_stack + threadIdx.x;
     stack.sp = 0;
     TravState st;
+    uint2 tri = make_uint2(0u, 0u);  // the pending (postponed) triangle group of this lane
     TraversalCounters cnt;
     bool alive = false;
     uint32_t out_index = 0;
@@ -231,6 +239,7 @@ __global__ void __launch_bounds__(kTravBlock)
                 }
                 trav_init(st, ray);
                 stack.sp = 0;
+                tri = make_uint2(0u, 0u);
                 alive = true;
             }
             batch_next += min((uint32_t)__popc(need), avail);
@@ -240,19 +249,89 @@ __global__ void __launch_bounds__(kTravBlock)
             break;
         }
         // ---- advance all live lanes until enough of them have finished ----
-        for (;;) {
-            if (alive) {
-                if (trav_step<ANY_HIT, COUNT>(sc.nodes, sc.tris, st, stack, &cnt)) {
-                    if (ANY_HIT) {
-                        ps.vis[out_index] = st.hit.tri != kMiss ? 0 : 1;
-                    } else {
-                        ps.hit[out_index] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.tri));
+        // Each iteration has a node phase and a triangle phase so that the lanes of a warp execute
+        // the same code together. Triangle tests are postponed (after Ylitie et al. 2017 §5.3): a
+        // lane keeps ONE pending triangle group in registers while it keeps descending, and the
+        // triangle phase — one test per lane — runs only when at least kTriLanes lanes have a
+        // triangle pending. A lane drains its pending group on its own only when a second group
+        // arrives or when it has nothing else left. The closest hit does not depend on the order
+        // of the tests (ties break on the primitive id), so results are unchanged.
+        if (variant == 0) {
+            // whole-step variant: one node + all its triangles per iteration
+            for (;;) {
+                if (alive) {
+                    if (trav_step<ANY_HIT, COUNT>(sc.nodes, sc.tris, st, stack, &cnt)) {
+                        if (ANY_HIT) {
+                            ps.vis[out_index] = st.hit.tri != kMiss ? 0 : 1;
+                        } else {
+                            ps.hit[out_index] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.tri));
+                        }
+                        alive = false;
                     }
-                    alive = false;
+                }
+                const int n_alive = __popc(__ballot_sync(0xffffffffu, alive));
+                if (n_alive == 0 || (!drained && 32 - n_alive >= refill_idle)) {
+                    break;
                 }
             }
+            continue;
+        }
+        for (;;) {
+            bool finished = false;
+            // node phase
+            if (alive && (st.cur.y & 0xff000000u)) {
+                const uint32_t node_index = next_child(st.cur, st.oct_inv4);
+                if (st.cur.y & 0xff000000u) {
+                    stack.push(st.cur);
+                }
+                if (COUNT) {
+                    cnt.nodes++;
+                }
+                uint2 new_tri;
+                node_intersect(sc.nodes, st, node_index, st.cur, new_tri);
+                if (new_tri.y) {
+                    while (tri.y && !finished) {  // a second group arrived: drain the older one now
+                        if (COUNT) {
+                            cnt.tris++;
+                        }
+                        finished = test_next_triangle(sc.tris, st, tri) && ANY_HIT;
+                    }
+                    tri = new_tri;
+                }
+            }
+            // triangle phase (warp-uniform decision)
+            if (__popc(__ballot_sync(0xffffffffu, alive && !finished && tri.y != 0u)) >= tri_lanes) {
+                if (alive && !finished && tri.y) {
+                    if (COUNT) {
+                        cnt.tris++;
+                    }
+                    finished = test_next_triangle(sc.tris, st, tri) && ANY_HIT;
+                }
+            }
+            // pop phase: a lane without node work takes the next node group from its stack
+            if (alive && !finished && (st.cur.y & 0xff000000u) == 0u) {
+                if (!stack.empty()) {
+                    st.cur = stack.pop();
+                } else {
+                    while (tri.y && !finished) {  // nothing else left: drain and finish
+                        if (COUNT) {
+                            cnt.tris++;
+                        }
+                        finished = test_next_triangle(sc.tris, st, tri) && ANY_HIT;
+                    }
+                    finished = true;
+                }
+            }
+            if (finished) {
+                if (ANY_HIT) {
+                    ps.vis[out_index] = st.hit.tri != kMiss ? 0 : 1;
+                } else {
+                    ps.hit[out_index] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.tri));
+                }
+                alive = false;
+            }
             const int n_alive = __popc(__ballot_sync(0xffffffffu, alive));
-            if (n_alive == 0 || (!drained && 32 - n_alive >= kRefillIdle)) {
+            if (n_alive == 0 || (!drained && 32 - n_alive >= refill_idle)) {
                 break;
             }
         }
