@@ -97,6 +97,10 @@ class RenderCUDA:
         for key, val in (("max_depth", max_depth), ("world_size", world_size), ("rank", rank),
                          ("count_traversal", int(count_traversal)), ("bvh_threads", bvh_threads)):
             self._check(self.lib.crtc_set_option(self.h, key.encode(), val))
+        # developer knobs of the traversal kernels (defaults are the tuned values)
+        for env, key in (("CRT_CUDA_REFILL_IDLE", "refill_idle"),):
+            if os.environ.get(env):
+                self._check(self.lib.crtc_set_option(self.h, key.encode(), int(os.environ[env])))
         if stream is not None:
             self._check(self.lib.crtc_set_stream(self.h, C.c_void_p(stream)))
         self.width = self.height = 0

@@ -187,15 +187,15 @@ CRT_HD void trav_init(TravState &s, const Ray &ray)
     s.cur.y = 0x80000000u;  // root: "inner child in slot 7 of a virtual parent"
 }
 
-// byte j of `packed` as the float 1 + b * 2^-15, built with one byte-permute and no
-// int->float conversion (I2F runs on the quarter-rate XU pipe, which the first profile showed at
-// 52 % utilisation with 48 conversions per node).
-CRT_HD float byte_unit(uint32_t packed, int j)
+// byte j of `packed` as an exact float, without an int->float conversion: I2F executes on the
+// quarter-rate XU pipe, which the first profile showed at 52 % utilisation (48 conversions per
+// node). One byte-permute builds the float 2^23 + b, one FADD removes the 2^23 — both exact.
+CRT_HD float byte_to_float(uint32_t packed, int j)
 {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(packed, 0x3F800000u, 0x7604u | ((uint32_t)j << 4)));
+    return __uint_as_float(__byte_perm(packed, 0x4B000000u, 0x7650u | (uint32_t)j)) - 8388608.f;
 #else
-    return u2f(0x3F800000u | (((packed >> (8 * j)) & 0xffu) << 8));
+    return (float)((packed >> (8 * j)) & 0xffu);
 #endif
 }
 
@@ -209,23 +209,25 @@ CRT_HD void node_intersect(const float4 *__restrict__ nodes, const TravState &s,
     const float4 *np = nodes + (size_t)node_index * 5;
     const float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
     const uint32_t e_imask = f2u(n0.w);
-    // plane distance = q * ad + ob with ad = 2^e / d, ob = (p - o) / d. q enters as
-    // qf = 1 + q * 2^-15, so t = qf * (ad * 2^15) + (ob - ad * 2^15).
-    const float adx = u2f((e_imask & 0xffu) << 23) * s.idx * 32768.f;
-    const float ady = u2f(((e_imask >> 8) & 0xffu) << 23) * s.idy * 32768.f;
-    const float adz = u2f(((e_imask >> 16) & 0xffu) << 23) * s.idz * 32768.f;
-    const float ob0x = (n0.x - ray.ox) * s.idx;
-    const float ob0y = (n0.y - ray.oy) * s.idy;
-    const float ob0z = (n0.z - ray.oz) * s.idz;
-    const float obx = ob0x - adx, oby = ob0y - ady, obz = ob0z - adz;
-    // Rounding slack: |ob| can be much larger than the plane distance (cancellation), and ob - ad'
-    // rounds at the scale of ad' = 2^15 ad, i.e. up to 2^-9 of a grid step. Widening the interval by
-    // that bound keeps the box test conservative with respect to the (independently rounded)
-    // triangle test, including for equal-t ties.
-    const float slack = 4e-7f * fmaxf_(fmaxf_(fabsf(ob0x), fabsf(ob0y)), fabsf(ob0z)) +
-                        1.5e-7f * fmaxf_(fmaxf_(fabsf(adx), fabsf(ady)), fabsf(adz));
-    const float tmax_cap = s.tfar + slack;
-    const float tmin_cap = ray.tnear - slack;
+    // plane distance = q * ad + ob with ad = 2^e / d, ob = (p - o) / d
+    const float adx = u2f((e_imask & 0xffu) << 23) * s.idx;
+    const float ady = u2f(((e_imask >> 8) & 0xffu) << 23) * s.idy;
+    const float adz = u2f(((e_imask >> 16) & 0xffu) << 23) * s.idz;
+    const float obx = (n0.x - ray.ox) * s.idx;
+    const float oby = (n0.y - ray.oy) * s.idy;
+    const float obz = (n0.z - ray.oz) * s.idz;
+    // Rounding slack, per axis: a plane distance is fma(q, ad, ob) with |ob| possibly much larger
+    // than the result (cancellation), so its absolute error scales with |ob| + 255 |ad| OF THAT AXIS
+    // (it grows like 1/d: huge for an axis the ray is nearly parallel to, tiny for the others).
+    // Each axis' interval is widened by its own bound — folded into ob, so it costs nothing per
+    // child — which keeps the box test conservative with respect to the (independently rounded)
+    // triangle test, including for equal-t ties, without loosening the other two axes.
+    const float sx = 4e-7f * (fabsf(obx) + 255.f * fabsf(adx));
+    const float sy = 4e-7f * (fabsf(oby) + 255.f * fabsf(ady));
+    const float sz = 4e-7f * (fabsf(obz) + 255.f * fabsf(adz));
+    const float obx_lo = obx - sx, obx_hi = obx + sx;
+    const float oby_lo = oby - sy, oby_hi = oby + sy;
+    const float obz_lo = obz - sz, obz_hi = obz + sz;
     uint32_t hitmask = 0;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -242,16 +244,15 @@ CRT_HD void node_intersect(const float4 *__restrict__ nodes, const TravState &s,
         const uint32_t zmin = ray.dz < 0.f ? qhiz : qloz, zmax = ray.dz < 0.f ? qloz : qhiz;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float tminx = fma_(byte_unit(xmin, j), adx, obx);
-            const float tminy = fma_(byte_unit(ymin, j), ady, oby);
-            const float tminz = fma_(byte_unit(zmin, j), adz, obz);
-            const float tmaxx = fma_(byte_unit(xmax, j), adx, obx);
-            const float tmaxy = fma_(byte_unit(ymax, j), ady, oby);
-            const float tmaxz = fma_(byte_unit(zmax, j), adz, obz);
-            // (tmin - slack) <= (tmax + slack), with the caps carrying the slack
-            const float tmin = fmaxf_(fmaxf_(tminx, tminy), fmaxf_(tminz, tmin_cap));
-            const float tmax = fminf_(fminf_(tmaxx, tmaxy), fminf_(tmaxz, tmax_cap));
-            if (tmin <= tmax + slack) {
+            const float tminx = fma_(byte_to_float(xmin, j), adx, obx_lo);
+            const float tminy = fma_(byte_to_float(ymin, j), ady, oby_lo);
+            const float tminz = fma_(byte_to_float(zmin, j), adz, obz_lo);
+            const float tmaxx = fma_(byte_to_float(xmax, j), adx, obx_hi);
+            const float tmaxy = fma_(byte_to_float(ymax, j), ady, oby_hi);
+            const float tmaxz = fma_(byte_to_float(zmax, j), adz, obz_hi);
+            const float tmin = fmaxf_(fmaxf_(tminx, tminy), fmaxf_(tminz, ray.tnear));
+            const float tmax = fminf_(fminf_(tmaxx, tmaxy), fminf_(tmaxz, s.tfar));
+            if (tmin <= tmax) {
                 const uint32_t bits = (child_bits4 >> (8 * j)) & 0xffu;
                 const uint32_t idx_ = (bit_index4 >> (8 * j)) & 0xffu;
                 hitmask |= bits << idx_;

@@ -80,7 +80,7 @@ struct crtc_renderer {
     int rank = 0, world_size = 1;
     int bvh_threads = 0;
     bool count_traversal = false;
-    int tri_lanes = crt::kTriLanes, refill_idle = crt::kRefillIdle, trav_variant = 1;  // traversal scheduling knobs
+    int refill_idle = crt::kRefillIdle;  // idle lanes that trigger a refill of the traversal warps
 
     // framebuffer layout
     int fb_w = 0, fb_h = 0;
@@ -153,15 +153,15 @@ struct crtc_renderer {
         const unsigned g = trav_grid;
         if (any_hit) {
             if (count_traversal) {
-                crt::k_traverse<true, true><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter, tri_lanes, refill_idle, trav_variant);
+                crt::k_traverse<true, true><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter, refill_idle);
             } else {
-                crt::k_traverse<true, false><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter, tri_lanes, refill_idle, trav_variant);
+                crt::k_traverse<true, false><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter, refill_idle);
             }
         } else {
             if (count_traversal) {
-                crt::k_traverse<false, true><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter, tri_lanes, refill_idle, trav_variant);
+                crt::k_traverse<false, true><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter, refill_idle);
             } else {
-                crt::k_traverse<false, false><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter, tri_lanes, refill_idle, trav_variant);
+                crt::k_traverse<false, false><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter, refill_idle);
             }
         }
     }
@@ -259,6 +259,7 @@ struct crtc_renderer {
             }
         }
         npx_local = (uint32_t)local_tiles.size() * crt::kTilePixels;
+        assemble_tiles.clear();
         d_tile_ids.upload(local_tiles.data(), local_tiles.size(), stream);
         d_accum_local.alloc((size_t)npx_local * 3);
         d_img_local.alloc(npx_local);
@@ -632,27 +633,41 @@ struct crtc_renderer {
         return ms / iters;
     }
 
+    // tile-id lists of the other ranks, cached on the device (keyed by world_size * 4096 + rank)
+    std::vector<std::pair<int, std::unique_ptr<DeviceBuffer<uint32_t>>>> assemble_tiles;
+
+    // Stream-ordered (no host synchronisation): the caller orders it after the gather.
     void assemble_rank(int src_rank, int ws, const void *accum_dev, const void *img_dev)
     {
         make_current();
-        std::vector<uint32_t> tiles;
-        for (uint32_t t = 0; t < ntx * nty; ++t) {
-            if ((int)(t % (uint32_t)ws) == src_rank) {
-                tiles.push_back(t);
+        const int key = ws * 4096 + src_rank;
+        DeviceBuffer<uint32_t> *d_tiles = nullptr;
+        for (auto &e : assemble_tiles) {
+            if (e.first == key) {
+                d_tiles = e.second.get();
             }
         }
-        if (tiles.empty()) {
+        if (!d_tiles) {
+            std::vector<uint32_t> tiles;
+            for (uint32_t t = 0; t < ntx * nty; ++t) {
+                if ((int)(t % (uint32_t)ws) == src_rank) {
+                    tiles.push_back(t);
+                }
+            }
+            assemble_tiles.emplace_back(key, std::make_unique<DeviceBuffer<uint32_t>>());
+            d_tiles = assemble_tiles.back().second.get();
+            d_tiles->upload(tiles.data(), tiles.size(), stream);
+            CUDA_CHECK(cudaStreamSynchronize(stream));  // `tiles` is a host temporary
+        }
+        if (d_tiles->count == 0) {
             return;
         }
-        DeviceBuffer<uint32_t> d_tiles;
-        d_tiles.upload(tiles.data(), tiles.size(), stream);
         crt::FrameLayout f = frame_layout();
-        f.tile_ids = d_tiles.ptr;
-        f.npx_local = (uint32_t)tiles.size() * crt::kTilePixels;
+        f.tile_ids = d_tiles->ptr;
+        f.npx_local = (uint32_t)d_tiles->count * crt::kTilePixels;
         const unsigned g = (unsigned)((f.npx_local + 255) / 256);
         crt::k_assemble<<<g, 256, 0, stream>>>(f, static_cast<const float *>(accum_dev),
                                               static_cast<const uint32_t *>(img_dev), d_accum_full.ptr, d_img_full.ptr);
-        CUDA_CHECK(cudaStreamSynchronize(stream));
         CUDA_CHECK(cudaGetLastError());
     }
 };
@@ -738,10 +753,6 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
             r->bvh_threads = (int)value;
         } else if (k == "count_traversal") {
             r->count_traversal = value != 0;
-        } else if (k == "trav_variant") {
-            r->trav_variant = (int)value;
-        } else if (k == "tri_lanes") {
-            r->tri_lanes = (int)std::min<int64_t>(std::max<int64_t>(value, 1), 32);
         } else if (k == "refill_idle") {
             r->refill_idle = (int)std::min<int64_t>(std::max<int64_t>(value, 1), 32);
         } else {

@@ -147,14 +147,14 @@ __global__ void __launch_bounds__(256) k_raygen(ViewParams view, FrameLayout f, 
 // lanes per instruction because a warp lived as long as its longest ray. Here every warp stays
 // resident, pulls rays from the queue in batches (one atomic per kFetchBatch rays), advances
 // all live lanes one traversal step at a time and refills idle lanes as soon as at least
-// kRefillIdle of them have finished (Aila & Laine 2009; Ylitie et al. 2017 §5). The first
-// kSmemStack entries of each lane's traversal stack live in shared memory, the rest spills to
-// local memory.
+// kRefillIdle of them have finished (Aila & Laine 2009; Ylitie et al. 2017 §5). Node tests stay
+// per lane; the triangles they yield are pooled across the warp and tested 32 pairs at a time
+// (see the loop body). The first kSmemStack entries of each lane's traversal stack live in shared
+// memory, the rest spills to local memory.
 constexpr int kTravBlock = 128;
 constexpr int kSmemStack = 8;
 constexpr int kRefillIdle = 4;
 constexpr uint32_t kFetchBatch = 64;
-constexpr int kTriLanes = 8;  // run the triangle phase when this many lanes have a triangle pending
 
 struct HybridStack {
     uint2 *sm;  // this thread's column of the block's shared stack: sm[i * kTravBlock]
@@ -186,11 +186,19 @@ struct HybridStack {
 //                  result to hit[slot]            (rtcIntersectV, render_embree.ispc:245)
 // ANY_HIT = true : rays from sray_o/sray_d, result to vis[]   (rtcOccludedV, :144,170)
 template <bool ANY_HIT, bool COUNT>
-__global__ void __launch_bounds__(kTravBlock)
+__global__ void __launch_bounds__(kTravBlock, 8)
     k_traverse(DeviceScene sc, PathState ps, const uint32_t *queue, const uint32_t *count_ptr, uint32_t *work_counter,
-               int tri_lanes, int refill_idle, int variant)
+               int refill_idle)
 {
     __shared__ uint2 sm_stack[kSmemStack * kTravBlock];
+    // warp-cooperative triangle testing: per warp, every lane's ray and best hit live in
+    // shared memory so that ANY lane can test a (ray, triangle) pair for its owner
+    __shared__ float sm_ray[kTravBlock / 32][8][32];            // ox oy oz tnear dx dy dz tfar0
+    __shared__ unsigned long long sm_key[kTravBlock / 32][32];  // bits(t) << 32 | flat id  (atomicMin)
+    __shared__ float sm_hit_u[kTravBlock / 32][32], sm_hit_v[kTravBlock / 32][32];
+    __shared__ uint32_t sm_hit_tri[kTravBlock / 32][32];
+    __shared__ uint32_t sm_slot[kTravBlock / 32][32];           // owner lane << 27 | triangle index
+    const int warp = threadIdx.x >> 5;
     const uint32_t count = *count_ptr;
     const int lane = threadIdx.x & 31;
     const unsigned lanemask_lt = (1u << lane) - 1u;
@@ -199,7 +207,7 @@ __global__ void __launch_bounds__(kTravBlock)
     stack.sm = sm_stack + threadIdx.x;
     stack.sp = 0;
     TravState st;
-    uint2 tri = make_uint2(0u, 0u);  // the pending (postponed) triangle group of this lane
+    uint2 tri = make_uint2(0u, 0u);  // triangle group yielded by this lane's last node step
     TraversalCounters cnt;
     bool alive = false;
     uint32_t out_index = 0;
@@ -241,6 +249,18 @@ __global__ void __launch_bounds__(kTravBlock)
                 stack.sp = 0;
                 tri = make_uint2(0u, 0u);
                 alive = true;
+                {
+                    sm_ray[warp][0][lane] = ray.ox;
+                    sm_ray[warp][1][lane] = ray.oy;
+                    sm_ray[warp][2][lane] = ray.oz;
+                    sm_ray[warp][3][lane] = ray.tnear;
+                    sm_ray[warp][4][lane] = ray.dx;
+                    sm_ray[warp][5][lane] = ray.dy;
+                    sm_ray[warp][6][lane] = ray.dz;
+                    sm_ray[warp][7][lane] = ray.tfar;
+                    sm_key[warp][lane] = ((unsigned long long)__float_as_uint(ray.tfar) << 32) | 0xffffffffull;
+                    sm_hit_tri[warp][lane] = kMiss;
+                }
             }
             batch_next += min((uint32_t)__popc(need), avail);
             need = __ballot_sync(0xffffffffu, !alive);
@@ -256,15 +276,108 @@ __global__ void __launch_bounds__(kTravBlock)
         // triangle pending. A lane drains its pending group on its own only when a second group
         // arrives or when it has nothing else left. The closest hit does not depend on the order
         // of the tests (ties break on the primitive id), so results are unchanged.
-        if (variant == 0) {
-            // whole-step variant: one node + all its triangles per iteration
+        {
+            // Warp-cooperative triangle tests. The first profiles showed the per-lane triangle loops issuing
+            // half of all instructions at 3-8 active lanes. Here the node phase stays per lane, but
+            // the triangles it yields are pooled across the warp: (owner lane, triangle) pairs are
+            // packed into 32 slots and EVERY lane tests one pair, reading the owner's ray from shared
+            // memory and merging hits with a 64-bit atomicMin on (t, flat primitive id) — the same
+            // closest-hit / tie rule as the sequential test, so results are unchanged.
+            __syncwarp();
             for (;;) {
+                // node phase
+                if (alive && (st.cur.y & 0xff000000u)) {
+                    const uint32_t node_index = next_child(st.cur, st.oct_inv4);
+                    if (st.cur.y & 0xff000000u) {
+                        stack.push(st.cur);
+                    }
+                    if (COUNT) {
+                        cnt.nodes++;
+                    }
+                    node_intersect(sc.nodes, st, node_index, st.cur, tri);
+                }
+                // triangle phase: pack pairs into slots, 32 at a time
+                for (;;) {
+                    const uint32_t k = alive ? (uint32_t)__popc(tri.y) : 0u;
+                    uint32_t pre = k;  // inclusive prefix sum over lanes
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const uint32_t o = __shfl_up_sync(0xffffffffu, pre, off);
+                        if (lane >= off) {
+                            pre += o;
+                        }
+                    }
+                    const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
+                    if (total == 0u) {
+                        break;
+                    }
+                    uint32_t pos = pre - k;
+                    while (tri.y && pos < 32u) {
+                        const int ti = msb(tri.y);
+                        tri.y &= ~(1u << ti);
+                        sm_slot[warp][pos++] = ((uint32_t)lane << 27) | (tri.x + (uint32_t)ti);
+                    }
+                    __syncwarp();
+                    const uint32_t npairs = min(total, 32u);
+                    bool won = false;
+                    unsigned long long cand = 0ull;
+                    uint32_t owner = 0u, tri_index = 0u;
+                    float hu = 0.f, hv = 0.f;
+                    if ((uint32_t)lane < npairs) {
+                        const uint32_t e = sm_slot[warp][lane];
+                        owner = e >> 27;
+                        tri_index = e & 0x07ffffffu;
+                        if (COUNT) {
+                            cnt.tris++;
+                        }
+                        Ray r;
+                        r.ox = sm_ray[warp][0][owner];
+                        r.oy = sm_ray[warp][1][owner];
+                        r.oz = sm_ray[warp][2][owner];
+                        r.tnear = sm_ray[warp][3][owner];
+                        r.dx = sm_ray[warp][4][owner];
+                        r.dy = sm_ray[warp][5][owner];
+                        r.dz = sm_ray[warp][6][owner];
+                        r.tfar = sm_ray[warp][7][owner];
+                        const float4 *tp = sc.tris + (size_t)tri_index * 3;
+                        const float4 t0 = tp[0], t1 = tp[1], t2 = tp[2];
+                        float t;
+                        if (tri_test(r, r.tfar, t0, t1, t2, t, hu, hv)) {
+                            cand = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)__float_as_uint(t0.w);
+                            won = atomicMin(&sm_key[warp][owner], cand) > cand;
+                        }
+                    }
+                    __syncwarp();
+                    if (won && sm_key[warp][owner] == cand) {  // the pair that holds the minimum records u, v
+                        sm_hit_u[warp][owner] = hu;
+                        sm_hit_v[warp][owner] = hv;
+                        sm_hit_tri[warp][owner] = tri_index;
+                    }
+                    __syncwarp();
+                    if (total <= 32u) {
+                        break;
+                    }
+                }
+                // refresh tfar, pop, finish
                 if (alive) {
-                    if (trav_step<ANY_HIT, COUNT>(sc.nodes, sc.tris, st, stack, &cnt)) {
-                        if (ANY_HIT) {
-                            ps.vis[out_index] = st.hit.tri != kMiss ? 0 : 1;
+                    st.tfar = __uint_as_float((uint32_t)(sm_key[warp][lane] >> 32));
+                    bool finished = ANY_HIT && sm_hit_tri[warp][lane] != kMiss;
+                    if (!finished && (st.cur.y & 0xff000000u) == 0u) {
+                        if (!stack.empty()) {
+                            st.cur = stack.pop();
                         } else {
-                            ps.hit[out_index] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.tri));
+                            finished = true;
+                        }
+                    }
+                    if (finished) {
+                        const uint32_t htri = sm_hit_tri[warp][lane];
+                        if (ANY_HIT) {
+                            ps.vis[out_index] = htri != kMiss ? 0 : 1;
+                        } else {
+                            ps.hit[out_index] = make_float4(__uint_as_float((uint32_t)(sm_key[warp][lane] >> 32)),
+                                                            htri != kMiss ? sm_hit_u[warp][lane] : 0.f,
+                                                            htri != kMiss ? sm_hit_v[warp][lane] : 0.f,
+                                                            __uint_as_float(htri));
                         }
                         alive = false;
                     }
@@ -273,66 +386,6 @@ __global__ void __launch_bounds__(kTravBlock)
                 if (n_alive == 0 || (!drained && 32 - n_alive >= refill_idle)) {
                     break;
                 }
-            }
-            continue;
-        }
-        for (;;) {
-            bool finished = false;
-            // node phase
-            if (alive && (st.cur.y & 0xff000000u)) {
-                const uint32_t node_index = next_child(st.cur, st.oct_inv4);
-                if (st.cur.y & 0xff000000u) {
-                    stack.push(st.cur);
-                }
-                if (COUNT) {
-                    cnt.nodes++;
-                }
-                uint2 new_tri;
-                node_intersect(sc.nodes, st, node_index, st.cur, new_tri);
-                if (new_tri.y) {
-                    while (tri.y && !finished) {  // a second group arrived: drain the older one now
-                        if (COUNT) {
-                            cnt.tris++;
-                        }
-                        finished = test_next_triangle(sc.tris, st, tri) && ANY_HIT;
-                    }
-                    tri = new_tri;
-                }
-            }
-            // triangle phase (warp-uniform decision)
-            if (__popc(__ballot_sync(0xffffffffu, alive && !finished && tri.y != 0u)) >= tri_lanes) {
-                if (alive && !finished && tri.y) {
-                    if (COUNT) {
-                        cnt.tris++;
-                    }
-                    finished = test_next_triangle(sc.tris, st, tri) && ANY_HIT;
-                }
-            }
-            // pop phase: a lane without node work takes the next node group from its stack
-            if (alive && !finished && (st.cur.y & 0xff000000u) == 0u) {
-                if (!stack.empty()) {
-                    st.cur = stack.pop();
-                } else {
-                    while (tri.y && !finished) {  // nothing else left: drain and finish
-                        if (COUNT) {
-                            cnt.tris++;
-                        }
-                        finished = test_next_triangle(sc.tris, st, tri) && ANY_HIT;
-                    }
-                    finished = true;
-                }
-            }
-            if (finished) {
-                if (ANY_HIT) {
-                    ps.vis[out_index] = st.hit.tri != kMiss ? 0 : 1;
-                } else {
-                    ps.hit[out_index] = make_float4(st.hit.t, st.hit.u, st.hit.v, __uint_as_float(st.hit.tri));
-                }
-                alive = false;
-            }
-            const int n_alive = __popc(__ballot_sync(0xffffffffu, alive));
-            if (n_alive == 0 || (!drained && 32 - n_alive >= refill_idle)) {
-                break;
             }
         }
     }

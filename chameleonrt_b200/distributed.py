@@ -33,11 +33,17 @@ def device_tensor(ptr: int, nbytes: int, device):
     return torch.as_tensor(_DevPtr(ptr, nbytes), device=device)
 
 
+_GATHER_CACHE = {}
+
+
 def gather_frame_cuda(renderer, group=None, dst: int = 0):
     """NCCL gather of this rank's tile-local accum + img buffers to ``dst`` and assembly there.
 
     Returns True on ``dst`` (full frame now readable with ``renderer.read_accum()/read_img()``).
-    All ranks must call. Pads to the largest per-rank tile count so chunks are uniform.
+    All ranks must call; everything is stream-ordered on the current torch stream (which must be
+    the renderer's stream), no host synchronisation. When every rank owns the same number of
+    tiles (e.g. 1280x720: 240 tiles over 1/2/4/8 ranks) the renderer's buffers are sent in place;
+    otherwise they are padded to the largest per-rank tile count.
     """
     import torch
     import torch.distributed as dist
@@ -47,19 +53,35 @@ def gather_frame_cuda(renderer, group=None, dst: int = 0):
     dev = torch.device("cuda", renderer.device)
     accum_ptr, img_ptr, nloc = renderer.local_buffers()
     max_tiles = tiles.max_local_tiles(renderer.width, renderer.height, world)
+    ntx, nty = tiles.num_tiles(renderer.width, renderer.height)
+    uniform = (ntx * nty) % world == 0
     a_bytes, i_bytes = tiles.TILE_PIXELS * 12, tiles.TILE_PIXELS * 4
-    send = torch.zeros(max_tiles * (a_bytes + i_bytes), dtype=torch.uint8, device=dev)
-    if nloc:
-        send[: nloc * a_bytes].copy_(device_tensor(accum_ptr, nloc * a_bytes, dev))
-        send[max_tiles * a_bytes: max_tiles * a_bytes + nloc * i_bytes].copy_(device_tensor(img_ptr, nloc * i_bytes, dev))
-    recv = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
-    dist.gather(send, recv, dst=dst, group=group)
+    key = (id(renderer), accum_ptr, img_ptr, world, max_tiles)
+    st = _GATHER_CACHE.get(key)
+    if st is None:
+        st = {}
+        if uniform:
+            st["send_a"] = device_tensor(accum_ptr, nloc * a_bytes, dev)
+            st["send_i"] = device_tensor(img_ptr, nloc * i_bytes, dev)
+        else:
+            st["send_a"] = torch.zeros(max_tiles * a_bytes, dtype=torch.uint8, device=dev)
+            st["send_i"] = torch.zeros(max_tiles * i_bytes, dtype=torch.uint8, device=dev)
+            st["src_a"] = device_tensor(accum_ptr, nloc * a_bytes, dev) if nloc else None
+            st["src_i"] = device_tensor(img_ptr, nloc * i_bytes, dev) if nloc else None
+        if rank == dst:
+            st["recv_a"] = [torch.empty(max_tiles * a_bytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+            st["recv_i"] = [torch.empty(max_tiles * i_bytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+        _GATHER_CACHE.clear()
+        _GATHER_CACHE[key] = st
+    if not uniform and nloc:
+        st["send_a"][: nloc * a_bytes].copy_(st["src_a"])
+        st["send_i"][: nloc * i_bytes].copy_(st["src_i"])
+    dist.gather(st["send_a"], st.get("recv_a"), dst=dst, group=group)
+    dist.gather(st["send_i"], st.get("recv_i"), dst=dst, group=group)
     if rank != dst:
         return False
-    torch.cuda.current_stream(dev).synchronize()
     for r in range(world):
-        base = recv[r].data_ptr()
-        renderer.assemble_rank(r, world, base, base + max_tiles * a_bytes)
+        renderer.assemble_rank(r, world, st["recv_a"][r].data_ptr(), st["recv_i"][r].data_ptr())
     return True
 
 

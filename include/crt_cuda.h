@@ -58,9 +58,8 @@ void crtc_destroy(crtc_renderer *r);
  *   "rank", "world_size"  image-tile sharding: this renderer owns the 64x64 tiles with
  *                 tile_id % world_size == rank (tile_id as in render_embree.cpp:178-180)
  *   "bvh_threads" host threads for the BVH8 build (0 = all)
- *   "tri_lanes", "refill_idle"  scheduling knobs of the persistent traversal kernels (how many
- *                 lanes must have a triangle pending before the warp runs a triangle phase; how
- *                 many idle lanes trigger a refill from the ray queue); defaults are tuned
+ *   "refill_idle" scheduling knob of the persistent traversal kernels (how many idle lanes
+ *                 trigger a refill from the ray queue); the default is tuned
  *   "count_traversal" 1 = instrumented traversal kernels that count node visits and triangle
  *                 tests (for the algorithmic-byte figure; slower, off by default)
  */

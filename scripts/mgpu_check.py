@@ -1,0 +1,45 @@
+"""Launched by torchrun (one process per GPU): renders a frame sharded by tiles over all ranks,
+gathers to rank 0 over NCCL and checks it is bit-identical to a single-GPU render of the same
+frame (SURVEY.md §8e determinism check)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from chameleonrt_b200 import ArcballCamera, RenderCUDA
+from chameleonrt_b200.distributed import gather_frame_cuda
+from chameleonrt_b200.scenes import sponza_like
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+stream = torch.cuda.Stream(dev)
+torch.cuda.set_stream(stream)
+w, h = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (640, 360)
+scene, cam = sponza_like(spp=2, detail=0.4, tex_size=128)
+c = ArcballCamera(cam["eye"], cam["center"], cam["up"])
+r = RenderCUDA(local, max_depth=5, rank=rank, world_size=world, stream=stream.cuda_stream)
+r.initialize(w, h)
+r.set_scene(scene)
+rays = 0
+for f in range(3):
+    st = r.render(c.eye(), c.dir(), c.up(), cam["fov_y"], f == 0, False)
+    gather_frame_cuda(r)
+t = torch.tensor([float(st.num_rays)], dtype=torch.float64, device=dev)
+dist.all_reduce(t)
+if rank == 0:
+    got_accum, got_img = r.read_accum(), r.read_img()
+    single = RenderCUDA(local, max_depth=5, stream=stream.cuda_stream)
+    single.initialize(w, h)
+    single.set_scene(scene)
+    for f in range(3):
+        s1 = single.render(c.eye(), c.dir(), c.up(), cam["fov_y"], f == 0, True)
+    ok = (got_accum.view(np.uint32) == single.read_accum().view(np.uint32)).all() and (got_img == single.read_img()).all()
+    ok = ok and int(t.item()) == s1.num_rays
+    print("MGPU_OK" if ok else "MGPU_MISMATCH", world, int(t.item()), s1.num_rays, flush=True)
+dist.barrier()
+dist.destroy_process_group()

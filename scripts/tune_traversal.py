@@ -5,7 +5,7 @@ import numpy as np
 from bench import make_workload, WIDTH, HEIGHT, MAX_DEPTH
 from chameleonrt_b200 import RenderCUDA
 scene, view = make_workload()
-for variant, tri_lanes, refill in [(0, 8, 4), (1, 8, 4), (1, 1, 4), (0, 8, 8)]:
+for variant, tri_lanes, refill in [(0, 8, 4), (1, 1, 4), (2, 1, 4), (2, 1, 2), (2, 1, 8), (2, 1, 1), (2, 1, 12)]:
     gpu = RenderCUDA(0, max_depth=MAX_DEPTH)
     gpu._check(gpu.lib.crtc_set_option(gpu.h, b"trav_variant", variant))
     gpu._check(gpu.lib.crtc_set_option(gpu.h, b"tri_lanes", tri_lanes))
