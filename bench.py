@@ -15,7 +15,7 @@ accumulated tiles are gathered to rank 0 over NCCL/NVLink at frame end, inside t
 region. Total work is fixed, so scaling is "strong".
 
 One JSON line on stdout (rank 0). Keys follow the driver contract; `roofline` describes
-k_traverse_closest, `cpu_baseline` the CPU oracle timed on this box's host cores.
+k_traverse, `cpu_baseline` the CPU oracle timed on this box's host cores.
 """
 from __future__ import annotations
 
@@ -169,10 +169,25 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "MRays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line: dict) -> None:
+    """The contract is ONE JSON line on stdout. Libraries (NCCL prints its version banner) write
+    to fd 1 too, so main() points fd 1 at stderr for the whole run and the result goes to the
+    saved real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
+_REAL_STDOUT = None
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -299,17 +314,21 @@ def main():
         value = rays / (elapsed_ms * 1e3)  # MRays/s
         peak, peak_src = hbm_peak()
         n_launch = args.steps * MAX_DEPTH
+        # dominant kernel: k_traverse (persistent BVH8 traversal; every launch but the first carries
+        # the shadow rays of bounce b and the continuation rays of bounce b+1)
         closest_bytes = counts[1] * S_NODE + counts[2] * S_TRI + counts[0] * (S_RAY + S_HIT)
-        t_closest_ms = stage_acc["traverse_closest"]  # max over ranks of the per-rank sum
-        achieved = closest_bytes / world / (t_closest_ms * 1e-3) / 1e9  # per GPU GB/s
+        any_bytes = counts[4] * S_NODE + counts[5] * S_TRI + counts[3] * (S_RAY + 1)
+        trav_bytes = closest_bytes + any_bytes
+        t_trav_ms = stage_acc["traverse_primary"] + stage_acc["traverse"]  # max over ranks of per-rank sums
+        n_launch = args.steps * (MAX_DEPTH + 1)
+        achieved = trav_bytes / world / (t_trav_ms * 1e-3) / 1e9  # per GPU GB/s
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_k_traverse_closest.json")
+        tpath = os.path.join(ROOT, "profiles", "traffic_k_traverse.json")
         if os.path.exists(tpath):
             try:
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        any_bytes = counts[4] * S_NODE + counts[5] * S_TRI + counts[3] * (S_RAY + 1)
         line = {
             "metric": "MRays/s", "value": value, "unit": "MRays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -319,15 +338,14 @@ def main():
                                       "frame-end NCCL gather to rank 0" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: ~0.9 GB of per-frame path state streams through every bounce "
                              "(L2 126 MB); the 15 MB BVH+triangles stay L2-resident by design"},
-            "roofline": {"kernel": "k_traverse_closest", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "k_traverse", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": closest_bytes / n_launch / world,
-                         "avg_launch_ms": t_closest_ms / n_launch,
-                         "nodes_per_ray": counts[1] / max(1.0, counts[0]), "tris_per_ray": counts[2] / max(1.0, counts[0])},
-            "roofline_any_hit": {"kernel": "k_traverse_any",
-                                 "achieved": any_bytes / world / (stage_acc["traverse_any"] * 1e-3) / 1e9,
-                                 "unit": "GB/s", "nodes_per_ray": counts[4] / max(1.0, counts[3]),
-                                 "tris_per_ray": counts[5] / max(1.0, counts[3])},
+                         "algorithmic_bytes_per_launch": trav_bytes / n_launch / world,
+                         "avg_launch_ms": t_trav_ms / n_launch,
+                         "closest": {"rays": counts[0], "nodes_per_ray": counts[1] / max(1.0, counts[0]),
+                                     "tris_per_ray": counts[2] / max(1.0, counts[0])},
+                         "any_hit": {"rays": counts[3], "nodes_per_ray": counts[4] / max(1.0, counts[3]),
+                                     "tris_per_ray": counts[5] / max(1.0, counts[3])}},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items()},
             "e2e": {"value": e2e_rays / (e2e_ms * 1e3), "unit": "MRays/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": 52,  # ViewParams (camera basis + frame id) as kernel parameters
@@ -345,7 +363,7 @@ def main():
                 "ms_per_frame": cms / len(warm),
                 "sample": f"{len(warm)} full frame(s) of the same workload (1 warm-up frame discarded); CPU oracle "
                           "= Embree/ISPC backend restated with an own BVH2, -O3 x86-64-v3, all host threads"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

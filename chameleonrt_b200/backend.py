@@ -24,7 +24,7 @@ _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 _LIB_PATH = os.path.join(_CSRC, "libcrt_cuda_core.so")
 _lib: Optional[C.CDLL] = None
 
-STAGE_NAMES = ("raygen", "traverse_closest", "shade", "traverse_any", "nee_resolve", "resolve", "frame")
+STAGE_NAMES = ("raygen", "traverse_primary", "shade", "traverse", "nee_resolve", "resolve", "frame")
 COUNTER_NAMES = ("closest_rays", "occlusion_rays", "kernel_launches", "closest_nodes_visited", "closest_tris_tested",
                  "paths", "any_nodes_visited", "any_tris_tested")
 SCENE_INFO_NAMES = ("triangles", "bvh8_nodes", "bvh8_depth", "bvh_build_ms", "node_bytes", "triangle_bytes")

@@ -66,7 +66,7 @@ struct DeviceBuffer {
     }
 };
 
-enum Stage { kStRaygen = 0, kStClosest, kStShade, kStAny, kStNee, kStResolve, kStFrame, kNumStages };
+enum Stage { kStRaygen = 0, kStPrimary, kStShade, kStTraverse, kStNee, kStResolve, kStFrame, kNumStages };
 
 }  // namespace
 
@@ -140,29 +140,21 @@ struct crtc_renderer {
 
     // persistent traversal grid: every SM filled with as many blocks as fit
     unsigned trav_grid = 0;
-    void launch_traverse(bool any_hit, const crt::DeviceScene &sc, const crt::PathState &ps, const uint32_t *queue,
-                         const uint32_t *count_ptr, uint32_t *work_counter)
+    void launch_traverse(const crt::DeviceScene &sc, const crt::PathState &ps, const uint32_t *queue,
+                         const uint32_t *count_closest, const uint32_t *count_any, uint32_t *work_counter)
     {
         if (trav_grid == 0) {
             int sms = 0, per_sm = 0;
             CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crt::k_traverse<false, false>,
-                                                                     crt::kTravBlock, 0));
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crt::k_traverse<false>, crt::kTravBlock, 0));
             trav_grid = (unsigned)(sms * std::max(1, per_sm));
         }
-        const unsigned g = trav_grid;
-        if (any_hit) {
-            if (count_traversal) {
-                crt::k_traverse<true, true><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter, refill_idle);
-            } else {
-                crt::k_traverse<true, false><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter, refill_idle);
-            }
+        if (count_traversal) {
+            crt::k_traverse<true><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any,
+                                                                             work_counter, refill_idle);
         } else {
-            if (count_traversal) {
-                crt::k_traverse<false, true><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter, refill_idle);
-            } else {
-                crt::k_traverse<false, false><<<g, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_ptr, work_counter, refill_idle);
-            }
+            crt::k_traverse<false><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any,
+                                                                              work_counter, refill_idle);
         }
     }
 
@@ -415,17 +407,22 @@ struct crtc_renderer {
             crt::k_raygen<<<g256, 256, 0, stream>>>(view, fl, ps);
             ++launches;
             next_event(ev, kStRaygen);
+            // closest hit of the primary rays, then per bounce: shade -> one traversal launch for this
+            // bounce's shadow rays AND the next bounce's continuation rays -> NEE resolve
+            launch_traverse(sc, ps, ps.queue[0], ps.counters + crt::kCntQueue, nullptr, ps.counters + crt::kCntWork);
+            ++launches;
+            next_event(ev, kStPrimary);
             for (int b = 0; b < max_depth; ++b) {
                 uint32_t *qin = ps.queue[b & 1], *qout = ps.queue[(b + 1) & 1];
-                launch_traverse(false, sc, ps, qin, ps.counters + crt::kCntQueue + b, ps.counters + crt::kCntWorkClosest + b);
-                next_event(ev, kStClosest);
                 crt::k_shade<<<g128, 128, 0, stream>>>(sc, ps, qin, qout, b, max_depth);
                 next_event(ev, kStShade);
-                launch_traverse(true, sc, ps, nullptr, ps.counters + crt::kCntShadow + b, ps.counters + crt::kCntWorkAny + b);
-                next_event(ev, kStAny);
+                const bool last = b + 1 == max_depth;
+                launch_traverse(sc, ps, qout, last ? nullptr : ps.counters + crt::kCntQueue + b + 1,
+                                ps.counters + crt::kCntShadow + b, ps.counters + crt::kCntWork + 1 + b);
+                next_event(ev, kStTraverse);
                 crt::k_nee_resolve<<<g256, 256, 0, stream>>>(ps, qin, b);
                 next_event(ev, kStNee);
-                launches += 4;
+                launches += 3;
             }
             const unsigned gpx = (unsigned)((npx_local + 255) / 256);
             const bool full = world_size == 1;
@@ -496,15 +493,10 @@ struct crtc_renderer {
         CUDA_CHECK(cudaStreamSynchronize(stream));
     }
 
-    void reset_work_counters()
-    {
-        CUDA_CHECK(cudaMemsetAsync(d_counters.ptr + crt::kCntWorkClosest, 0, 2 * sizeof(uint32_t), stream));
-    }
-
     void launch_closest(uint64_t)
     {
-        CUDA_CHECK(cudaMemsetAsync(d_counters.ptr + crt::kCntWorkClosest, 0, sizeof(uint32_t), stream));
-        launch_traverse(false, device_scene(), path_state(), nullptr, d_counters.ptr, d_counters.ptr + crt::kCntWorkClosest);
+        CUDA_CHECK(cudaMemsetAsync(d_counters.ptr + crt::kCntWork, 0, sizeof(uint32_t), stream));
+        launch_traverse(device_scene(), path_state(), nullptr, d_counters.ptr, nullptr, d_counters.ptr + crt::kCntWork);
     }
 
     // shadow-ray layout for the any-hit kernel: sray_o = org|tfar, sray_d = dir|bits(index)
@@ -527,8 +519,8 @@ struct crtc_renderer {
 
     void launch_any(uint64_t)
     {
-        CUDA_CHECK(cudaMemsetAsync(d_counters.ptr + crt::kCntWorkAny, 0, sizeof(uint32_t), stream));
-        launch_traverse(true, device_scene(), path_state(), nullptr, d_counters.ptr, d_counters.ptr + crt::kCntWorkAny);
+        CUDA_CHECK(cudaMemsetAsync(d_counters.ptr + crt::kCntWork, 0, sizeof(uint32_t), stream));
+        launch_traverse(device_scene(), path_state(), nullptr, nullptr, d_counters.ptr, d_counters.ptr + crt::kCntWork);
     }
 
     void require_scene() const

@@ -35,9 +35,8 @@ constexpr int kMaxDepthSupported = 16;
 constexpr int kCntQueue = 0;
 constexpr int kCntShadow = 17;
 constexpr int kCntPaths = 34;
-constexpr int kCntWorkClosest = 36;  // [36..52] work-distribution cursors of the closest-hit launches
-constexpr int kCntWorkAny = 53;      // [53..69] same for the any-hit launches
-constexpr int kNumCounters = 72;
+constexpr int kCntWork = 36;  // [36..53] work-distribution cursors of the traversal launches
+constexpr int kNumCounters = 56;
 
 struct ViewParams {
     float3 pos, dir_du, dir_dv, dir_top_left;  // embree_utils.h:137-140
@@ -69,7 +68,7 @@ struct PathState {
     float4 *hit;       // t, u, v, bits(leaf-order triangle index | kMiss)
     float4 *thr_rng;   // path_throughput.xyz, bits(rng state)
     float4 *radiance;  // per-sample illum.xyz
-    float4 *nee_T;     // throughput before this bounce's update, bits(flags: 1 = has shadow ray B)
+    float4 *nee_T;     // throughput before this bounce's update, bits(flags: 2 = hit (NEE valid), 1 = has shadow ray B)
     float4 *nee_l1;    // light-sample contribution (without throughput)
     float4 *nee_l2;    // BSDF-sample contribution
     float4 *sray_o;    // shadow ray org.xyz, tfar   (indexed by shadow-queue position)
@@ -182,13 +181,16 @@ struct HybridStack {
     __device__ __forceinline__ bool empty() const { return sp == 0; }
 };
 
-// ANY_HIT = false: rays from ray_o/ray_d (indexed through `queue`, or identity when null),
-//                  result to hit[slot]            (rtcIntersectV, render_embree.ispc:245)
-// ANY_HIT = true : rays from sray_o/sray_d, result to vis[]   (rtcOccludedV, :144,170)
-template <bool ANY_HIT, bool COUNT>
+// One launch serves both ray kinds so that the shadow rays of bounce b and the continuation rays
+// of bounce b+1 (both known once k_shade(b) has run) share a launch: half as many traversal
+// launches per frame and twice the rays per launch, which matters when a GPU only holds 1/8 of the
+// image. Work items [0, n_any) are shadow rays (sray_o/sray_d -> vis[], rtcOccludedV,
+// render_embree.ispc:144,170); items [n_any, n_any + n_closest) are closest-hit rays (ray_o/ray_d
+// through `queue`, or identity when null -> hit[], rtcIntersectV, render_embree.ispc:245).
+template <bool COUNT>
 __global__ void __launch_bounds__(kTravBlock, 8)
-    k_traverse(DeviceScene sc, PathState ps, const uint32_t *queue, const uint32_t *count_ptr, uint32_t *work_counter,
-               int refill_idle)
+    k_traverse(DeviceScene sc, PathState ps, const uint32_t *queue, const uint32_t *count_closest_ptr,
+               const uint32_t *count_any_ptr, uint32_t *work_counter, int refill_idle)
 {
     __shared__ uint2 sm_stack[kSmemStack * kTravBlock];
     // warp-cooperative triangle testing: per warp, every lane's ray and best hit live in
@@ -198,8 +200,10 @@ __global__ void __launch_bounds__(kTravBlock, 8)
     __shared__ float sm_hit_u[kTravBlock / 32][32], sm_hit_v[kTravBlock / 32][32];
     __shared__ uint32_t sm_hit_tri[kTravBlock / 32][32];
     __shared__ uint32_t sm_slot[kTravBlock / 32][32];           // owner lane << 27 | triangle index
+    __shared__ uint32_t sm_is_any[kTravBlock / 32][32];         // ray kind per lane (instrumented build only)
     const int warp = threadIdx.x >> 5;
-    const uint32_t count = *count_ptr;
+    const uint32_t n_any = count_any_ptr ? *count_any_ptr : 0u;
+    const uint32_t count = n_any + (count_closest_ptr ? *count_closest_ptr : 0u);
     const int lane = threadIdx.x & 31;
     const unsigned lanemask_lt = (1u << lane) - 1u;
     const uint32_t batch = count > 8u * gridDim.x * kTravBlock ? kFetchBatch : 32u;
@@ -208,8 +212,9 @@ __global__ void __launch_bounds__(kTravBlock, 8)
     stack.sp = 0;
     TravState st;
     uint2 tri = make_uint2(0u, 0u);  // triangle group yielded by this lane's last node step
-    TraversalCounters cnt;
+    TraversalCounters cnt, cnt_any;
     bool alive = false;
+    bool is_any = false;  // kind of the ray this lane currently holds
     uint32_t out_index = 0;
     uint32_t batch_next = 0, batch_end = 0;  // warp-uniform
     bool drained = false;                    // warp-uniform: the queue has no more rays
@@ -236,12 +241,13 @@ __global__ void __launch_bounds__(kTravBlock, 8)
             if (((need >> lane) & 1u) && r < avail) {
                 const uint32_t j = batch_next + r;
                 Ray ray;
-                if (ANY_HIT) {
+                is_any = j < n_any;
+                if (is_any) {
                     const float4 o = ps.sray_o[j], d = ps.sray_d[j];
                     ray = Ray{o.x, o.y, o.z, kEpsilon, d.x, d.y, d.z, o.w};
                     out_index = __float_as_uint(d.w);
                 } else {
-                    out_index = queue ? queue[j] : j;
+                    out_index = queue ? queue[j - n_any] : j - n_any;
                     const float4 o = ps.ray_o[out_index], d = ps.ray_d[out_index];
                     ray = Ray{o.x, o.y, o.z, o.w, d.x, d.y, d.z, d.w};
                 }
@@ -260,6 +266,9 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                     sm_ray[warp][7][lane] = ray.tfar;
                     sm_key[warp][lane] = ((unsigned long long)__float_as_uint(ray.tfar) << 32) | 0xffffffffull;
                     sm_hit_tri[warp][lane] = kMiss;
+                    if (COUNT) {
+                        sm_is_any[warp][lane] = is_any ? 1u : 0u;
+                    }
                 }
             }
             batch_next += min((uint32_t)__popc(need), avail);
@@ -292,7 +301,11 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                         stack.push(st.cur);
                     }
                     if (COUNT) {
-                        cnt.nodes++;
+                        if (is_any) {
+                            cnt_any.nodes++;
+                        } else {
+                            cnt.nodes++;
+                        }
                     }
                     node_intersect(sc.nodes, st, node_index, st.cur, tri);
                 }
@@ -327,8 +340,12 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                         const uint32_t e = sm_slot[warp][lane];
                         owner = e >> 27;
                         tri_index = e & 0x07ffffffu;
-                        if (COUNT) {
-                            cnt.tris++;
+                        if (COUNT) {  // attribute the test to the kind of the owner's ray
+                            if (sm_is_any[warp][owner]) {
+                                cnt_any.tris++;
+                            } else {
+                                cnt.tris++;
+                            }
                         }
                         Ray r;
                         r.ox = sm_ray[warp][0][owner];
@@ -361,7 +378,7 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                 // refresh tfar, pop, finish
                 if (alive) {
                     st.tfar = __uint_as_float((uint32_t)(sm_key[warp][lane] >> 32));
-                    bool finished = ANY_HIT && sm_hit_tri[warp][lane] != kMiss;
+                    bool finished = is_any && sm_hit_tri[warp][lane] != kMiss;
                     if (!finished && (st.cur.y & 0xff000000u) == 0u) {
                         if (!stack.empty()) {
                             st.cur = stack.pop();
@@ -371,7 +388,7 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                     }
                     if (finished) {
                         const uint32_t htri = sm_hit_tri[warp][lane];
-                        if (ANY_HIT) {
+                        if (is_any) {
                             ps.vis[out_index] = htri != kMiss ? 0 : 1;
                         } else {
                             ps.hit[out_index] = make_float4(__uint_as_float((uint32_t)(sm_key[warp][lane] >> 32)),
@@ -390,14 +407,18 @@ __global__ void __launch_bounds__(kTravBlock, 8)
         }
     }
     if (COUNT) {
-        unsigned long long n = cnt.nodes, t = cnt.tris;
+        unsigned long long n = cnt.nodes, t = cnt.tris, na = cnt_any.nodes, ta = cnt_any.tris;
         for (int off = 16; off > 0; off >>= 1) {
             n += __shfl_down_sync(0xffffffffu, n, off);
             t += __shfl_down_sync(0xffffffffu, t, off);
+            na += __shfl_down_sync(0xffffffffu, na, off);
+            ta += __shfl_down_sync(0xffffffffu, ta, off);
         }
         if (lane == 0) {
-            atomicAdd(ps.trav_counters + (ANY_HIT ? 2 : 0), n);
-            atomicAdd(ps.trav_counters + (ANY_HIT ? 3 : 1), t);
+            atomicAdd(ps.trav_counters, n);
+            atomicAdd(ps.trav_counters + 1, t);
+            atomicAdd(ps.trav_counters + 2, na);
+            atomicAdd(ps.trav_counters + 3, ta);
         }
     }
 }
@@ -445,6 +466,9 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState ps, con
             rad.y = rad.y + c.y;
             rad.z = rad.z + c.z;
             ps.radiance[slot] = rad;
+            // no NEE at a miss: flags = 0 (k_nee_resolve must not look at hit[], which the merged
+            // traversal launch overwrites with the NEXT bounce's hit before it runs)
+            ps.nee_T[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
         } else {
             // render_embree.ispc:264-293 (the ray-independent part was precomputed per triangle)
             hit_p = mk3(ro.x + h.x * dir.x, ro.y + h.x * dir.y, ro.z + h.x * dir.z);
@@ -512,7 +536,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState ps, con
                 }
             }
             ps.nee_T[slot] = make_float4(path_throughput.x, path_throughput.y, path_throughput.z,
-                                         __uint_as_float(emit_b ? 1u : 0u));
+                                         __uint_as_float(emit_b ? 3u : 2u));  // bit 1: valid, bit 0: has ray B
             ps.nee_l1[slot] = make_float4(l1.x, l1.y, l1.z, 0.f);
             if (emit_b) {
                 ps.nee_l2[slot] = make_float4(l2.x, l2.y, l2.z, 0.f);
@@ -570,10 +594,10 @@ __global__ void __launch_bounds__(256) k_nee_resolve(PathState ps, const uint32_
         return;
     }
     const uint32_t slot = queue_in[j];
-    if (__float_as_uint(ps.hit[slot].w) == kMiss) {
-        return;
-    }
     const float4 T = ps.nee_T[slot];
+    if ((__float_as_uint(T.w) & 2u) == 0u) {
+        return;  // the path missed at this bounce
+    }
     float3 illum = mk3(0.f);
     if (ps.vis[2 * slot]) {
         const float4 l1 = ps.nee_l1[slot];

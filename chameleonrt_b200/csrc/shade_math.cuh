@@ -260,7 +260,16 @@ CRT_D float power_heuristic(float n_f, float pdf_f, float n_g, float pdf_g)
     const float g = n_g * pdf_g;
     return (f * f) / (f * f + g * g);
 }
-CRT_D float schlick_weight(float cos_theta) { return powf(saturate(1.f - cos_theta), 5.f); }
+// disney_bsdf.ih:74-76 is pow(saturate(1 - cos_theta), 5). Evaluated here as m^2 * m^2 * m: powf is
+// ~100 instructions and this weight is needed ~10 times per shaded hit (it was about a third of
+// k_shade's instructions); the product is within 2 ulp of powf (the reference's own ISPC pow under
+// --opt=fast-math is no closer). One of the two documented arithmetic deviations.
+CRT_D float schlick_weight(float cos_theta)
+{
+    const float m = saturate(1.f - cos_theta);
+    const float m2 = m * m;
+    return m2 * m2 * m;
+}
 CRT_D float fresnel_dielectric(float cos_theta_i, float eta_i, float eta_t)
 {
     const float g = pow2(eta_t) / pow2(eta_i) - 1.f + pow2(cos_theta_i);

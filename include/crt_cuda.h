@@ -91,7 +91,8 @@ int crtc_render(crtc_renderer *r, const float *pos, const float *dir, const floa
 int crtc_read_accum(crtc_renderer *r, float *rgb_out);
 
 /* Per-stage device times of the last frame, in ms (CUDA events on the renderer's stream):
- * [0] raygen [1] closest-hit traversal [2] shade [3] any-hit traversal [4] NEE resolve
+ * [0] raygen [1] traversal of the primary rays [2] shade [3] traversal of bounce b's shadow rays
+ * together with bounce b+1's continuation rays (one launch per bounce) [4] NEE resolve
  * [5] resolve+tonemap [6] whole frame. Returns the number of entries written (<= n). */
 int crtc_get_stage_times(crtc_renderer *r, float *ms_out, int n);
 
