@@ -33,16 +33,36 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-WORKLOAD = "C2 sponza_like OBJ-class scene (263,792 tris, 25 materials, 8 sRGB 1024^2 textures), 1280x720, 4 spp, max depth 8"
+# BASELINE.json configs. The default (what the driver runs) is configs[1] = "c2"; c3 / c4 are the
+# HBM-resident stress cases and are run by hand (results under profiles/).
+WORKLOADS = {
+    "c2": dict(name="C2 sponza_like OBJ-class scene (263,792 tris, 25 materials, 8 sRGB 1024^2 textures), "
+                    "1280x720, 4 spp, max depth 8", gen="sponza_like", kw={}, w=1280, h=720, spp=4, depth=8),
+    "c3": dict(name="C3 san_miguel_like glTF-class scene (10.5 M instanced tris, 961 instances, 100 materials, "
+                    "11 textures), 1920x1080, 8 spp, max depth 8", gen="san_miguel_like", kw={}, w=1920, h=1080, spp=8, depth=8),
+    "c4": dict(name="C4 rungholt_like OBJ-class voxel city (6.7 M tris, 80 untextured materials), "
+                    "1920x1080, 4 spp, max depth 8", gen="rungholt_like", kw={"scale": 1.24}, w=1920, h=1080, spp=4, depth=8),
+}
+WORKLOAD = WORKLOADS["c2"]["name"]
 WIDTH, HEIGHT, SPP, MAX_DEPTH = 1280, 720, 4, 8
 S_NODE, S_TRI, S_RAY, S_HIT = 80, 48, 32, 16  # algorithmic bytes, SURVEY.md §8d / DESIGN.md §5
 
 
+def select_workload(key: str) -> None:
+    global WORKLOAD, WIDTH, HEIGHT, SPP, MAX_DEPTH, _GEN
+    w = WORKLOADS[key]
+    WORKLOAD, WIDTH, HEIGHT, SPP, MAX_DEPTH = w["name"], w["w"], w["h"], w["spp"], w["depth"]
+    _GEN = (w["gen"], w["kw"])
+
+
+_GEN = ("sponza_like", {})
+
+
 def make_workload():
     from chameleonrt_b200 import ArcballCamera
-    from chameleonrt_b200.scenes import sponza_like
+    from chameleonrt_b200 import scenes
 
-    scene, cam = sponza_like(spp=SPP)
+    scene, cam = getattr(scenes, _GEN[0])(spp=SPP, **_GEN[1])
     camera = ArcballCamera(cam["eye"], cam["center"], cam["up"])
     return scene, (camera.eye(), camera.dir(), camera.up(), cam["fov_y"])
 
@@ -193,11 +213,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-mode", action="store_true",
                     help="for runs under ncu: skip the instrumented counting pass and the CPU baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else max(args.warmup, 1)
+    select_workload(args.workload)
 
     if args.impl == "reference":
         run_reference_arm(args)
@@ -207,7 +229,7 @@ def main():
     import torch.distributed as dist
 
     from chameleonrt_b200 import RenderCUDA
-    from chameleonrt_b200.distributed import gather_frame_cuda
+    from chameleonrt_b200.distributed import FrameGatherer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -234,13 +256,24 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    gatherer = FrameGatherer(gpu) if world > 1 else None
+
     def frame(f, readback):
+        """One step. N > 1: the frame-end gather of frame f is started here and overlaps the
+        rendering of frame f+1 (it is completed by the next submit or by flush()); with
+        readback the assembled frame is needed now, so the gather is finished immediately."""
         st = gpu.render(*view, f == 0, readback and world == 1)
         if world > 1:
-            gather_frame_cuda(gpu)
-            if readback and rank == 0:
-                gpu.img[...] = gpu.read_img()
+            gatherer.submit()
+            if readback:
+                gatherer.finish()
+                if rank == 0:
+                    gpu.img[...] = gpu.read_img()
         return st
+
+    def flush():
+        if world > 1:
+            gatherer.finish()
 
     # ---- instrumented pass (not timed): exact node/triangle visit counts of the same frames ----
     counts = np.zeros(6, np.float64)
@@ -264,6 +297,7 @@ def main():
     for _ in range(args.warmup):
         frame(f, False)
         f += 1
+    flush()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rays = 0
@@ -278,6 +312,7 @@ def main():
             launches += gpu.counters()["kernel_launches"] + (world if (world > 1 and rank == 0) else 0)
             for k, v in gpu.stage_times().items():
                 stage_acc[k] = stage_acc.get(k, 0.0) + v
+        flush()  # the last frame's gather + assembly belong to the timed region
         e1.record(stream)
         barrier()
     elapsed_ms = e0.elapsed_time(e1)
@@ -336,8 +371,9 @@ def main():
             "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "spp": SPP, "max_depth": MAX_DEPTH,
                        "parallelism": f"image tiles 64x64 round-robin over {world} GPU(s), scene replicated, "
                                       "frame-end NCCL gather to rank 0" if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2: ~0.9 GB of per-frame path state streams through every bounce "
-                             "(L2 126 MB); the 15 MB BVH+triangles stay L2-resident by design"},
+                       "l2": f"inputs larger than L2: ~{WIDTH * HEIGHT * SPP * 250 / 1e9:.1f} GB of per-frame path state "
+                             f"streams through every bounce (L2 126 MB); scene = {gpu.scene_info()['node_bytes'] / 1e6:.0f} MB "
+                             f"nodes + {2 * gpu.scene_info()['triangle_bytes'] / 1e6:.0f} MB triangle/shading records"},
             "roofline": {"kernel": "k_traverse", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": trav_bytes / n_launch / world,

@@ -33,56 +33,76 @@ def device_tensor(ptr: int, nbytes: int, device):
     return torch.as_tensor(_DevPtr(ptr, nbytes), device=device)
 
 
-_GATHER_CACHE = {}
+class FrameGatherer:
+    """Frame-end gather of one renderer's tiles to rank ``dst`` (NCCL) and assembly there.
 
-
-def gather_frame_cuda(renderer, group=None, dst: int = 0):
-    """NCCL gather of this rank's tile-local accum + img buffers to ``dst`` and assembly there.
-
-    Returns True on ``dst`` (full frame now readable with ``renderer.read_accum()/read_img()``).
-    All ranks must call; everything is stream-ordered on the current torch stream (which must be
-    the renderer's stream), no host synchronisation. When every rank owns the same number of
-    tiles (e.g. 1280x720: 240 tiles over 1/2/4/8 ranks) the renderer's buffers are sent in place;
-    otherwise they are padded to the largest per-rank tile count.
+    ``submit()`` stages this rank's tile-local accum + img buffers (a device-to-device copy, so the
+    next frame may overwrite them) and starts the gather asynchronously on NCCL's stream;
+    ``finish()`` makes the renderer's stream wait for it and, on ``dst``, scatters every rank's
+    chunk into the full frame (``k_assemble``). ``submit()`` of the next frame finishes the previous
+    one first, so in a frame loop the transfer of frame f overlaps the rendering of frame f+1;
+    call ``finish()`` right after ``submit()`` when the assembled frame is needed immediately.
+    Everything is stream-ordered on the current torch stream (= the renderer's stream).
     """
-    import torch
-    import torch.distributed as dist
 
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    dev = torch.device("cuda", renderer.device)
-    accum_ptr, img_ptr, nloc = renderer.local_buffers()
-    max_tiles = tiles.max_local_tiles(renderer.width, renderer.height, world)
-    ntx, nty = tiles.num_tiles(renderer.width, renderer.height)
-    uniform = (ntx * nty) % world == 0
-    a_bytes, i_bytes = tiles.TILE_PIXELS * 12, tiles.TILE_PIXELS * 4
-    key = (id(renderer), accum_ptr, img_ptr, world, max_tiles)
-    st = _GATHER_CACHE.get(key)
-    if st is None:
-        st = {}
-        if uniform:
-            st["send_a"] = device_tensor(accum_ptr, nloc * a_bytes, dev)
-            st["send_i"] = device_tensor(img_ptr, nloc * i_bytes, dev)
-        else:
-            st["send_a"] = torch.zeros(max_tiles * a_bytes, dtype=torch.uint8, device=dev)
-            st["send_i"] = torch.zeros(max_tiles * i_bytes, dtype=torch.uint8, device=dev)
-            st["src_a"] = device_tensor(accum_ptr, nloc * a_bytes, dev) if nloc else None
-            st["src_i"] = device_tensor(img_ptr, nloc * i_bytes, dev) if nloc else None
-        if rank == dst:
-            st["recv_a"] = [torch.empty(max_tiles * a_bytes, dtype=torch.uint8, device=dev) for _ in range(world)]
-            st["recv_i"] = [torch.empty(max_tiles * i_bytes, dtype=torch.uint8, device=dev) for _ in range(world)]
-        _GATHER_CACHE.clear()
-        _GATHER_CACHE[key] = st
-    if not uniform and nloc:
-        st["send_a"][: nloc * a_bytes].copy_(st["src_a"])
-        st["send_i"][: nloc * i_bytes].copy_(st["src_i"])
-    dist.gather(st["send_a"], st.get("recv_a"), dst=dst, group=group)
-    dist.gather(st["send_i"], st.get("recv_i"), dst=dst, group=group)
-    if rank != dst:
-        return False
-    for r in range(world):
-        renderer.assemble_rank(r, world, st["recv_a"][r].data_ptr(), st["recv_i"][r].data_ptr())
-    return True
+    def __init__(self, renderer, group=None, dst: int = 0):
+        import torch
+        import torch.distributed as dist
+
+        self.r, self.group, self.dst = renderer, group, dst
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.dev = torch.device("cuda", renderer.device)
+        accum_ptr, img_ptr, nloc = renderer.local_buffers()
+        self.nloc = nloc
+        max_tiles = tiles.max_local_tiles(renderer.width, renderer.height, self.world)
+        a_bytes, i_bytes = tiles.TILE_PIXELS * 12, tiles.TILE_PIXELS * 4
+        self.src_a = device_tensor(accum_ptr, nloc * a_bytes, self.dev) if nloc else None
+        self.src_i = device_tensor(img_ptr, nloc * i_bytes, self.dev) if nloc else None
+        self.send_a = torch.zeros(max_tiles * a_bytes, dtype=torch.uint8, device=self.dev)
+        self.send_i = torch.zeros(max_tiles * i_bytes, dtype=torch.uint8, device=self.dev)
+        self.recv_a = self.recv_i = None
+        if self.rank == dst:
+            self.recv_a = [torch.empty_like(self.send_a) for _ in range(self.world)]
+            self.recv_i = [torch.empty_like(self.send_i) for _ in range(self.world)]
+        self.work = None
+
+    def submit(self):
+        import torch.distributed as dist
+
+        self.finish()
+        if self.nloc:
+            self.send_a[: self.src_a.numel()].copy_(self.src_a)
+            self.send_i[: self.src_i.numel()].copy_(self.src_i)
+        self.work = [dist.gather(self.send_a, self.recv_a, dst=self.dst, group=self.group, async_op=True),
+                     dist.gather(self.send_i, self.recv_i, dst=self.dst, group=self.group, async_op=True)]
+
+    def finish(self) -> bool:
+        """Returns True on ``dst`` when a frame was assembled."""
+        if self.work is None:
+            return False
+        for w in self.work:
+            w.wait()  # the current stream waits for NCCL; no host synchronisation
+        self.work = None
+        if self.rank != self.dst:
+            return False
+        for r in range(self.world):
+            self.r.assemble_rank(r, self.world, self.recv_a[r].data_ptr(), self.recv_i[r].data_ptr())
+        return True
+
+
+_GATHERERS = {}
+
+
+def gather_frame_cuda(renderer, group=None, dst: int = 0) -> bool:
+    """Blocking convenience form: gather this frame now and assemble it on ``dst`` (True there)."""
+    key = (id(renderer), renderer.width, renderer.height)
+    g = _GATHERERS.get(key)
+    if g is None:
+        _GATHERERS.clear()
+        g = _GATHERERS[key] = FrameGatherer(renderer, group, dst)
+    g.submit()
+    return g.finish()
 
 
 def gather_frame_numpy(local_accum: np.ndarray, local_img: np.ndarray, fb_width: int, fb_height: int,

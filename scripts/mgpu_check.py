@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 
 from chameleonrt_b200 import ArcballCamera, RenderCUDA
-from chameleonrt_b200.distributed import gather_frame_cuda
+from chameleonrt_b200.distributed import FrameGatherer
 from chameleonrt_b200.scenes import sponza_like
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -25,10 +25,11 @@ c = ArcballCamera(cam["eye"], cam["center"], cam["up"])
 r = RenderCUDA(local, max_depth=5, rank=rank, world_size=world, stream=stream.cuda_stream)
 r.initialize(w, h)
 r.set_scene(scene)
-rays = 0
+gatherer = FrameGatherer(r)
 for f in range(3):
     st = r.render(c.eye(), c.dir(), c.up(), cam["fov_y"], f == 0, False)
-    gather_frame_cuda(r)
+    gatherer.submit()  # pipelined: frame f's transfer overlaps frame f+1's rendering
+gatherer.finish()
 t = torch.tensor([float(st.num_rays)], dtype=torch.float64, device=dev)
 dist.all_reduce(t)
 if rank == 0:
