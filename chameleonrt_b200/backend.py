@@ -32,7 +32,7 @@ SCENE_INFO_NAMES = ("triangles", "bvh8_nodes", "bvh8_depth", "bvh_build_ms", "no
 # Every symbol include/crt_cuda.h declares (tests check the library exports all of them).
 C_ABI_SYMBOLS = (
     "crtc_last_error", "crtc_name", "crtc_create", "crtc_destroy", "crtc_set_option", "crtc_set_stream",
-    "crtc_initialize", "crtc_set_scene", "crtc_render", "crtc_read_accum", "crtc_get_stage_times",
+    "crtc_initialize", "crtc_set_scene", "crtc_render", "crtc_render_async", "crtc_sync", "crtc_read_accum", "crtc_get_stage_times",
     "crtc_get_counters", "crtc_get_scene_info", "crtc_trace_closest", "crtc_trace_any", "crtc_bench_trace",
     "crtc_local_buffers", "crtc_assemble_rank", "crtc_read_img",
 )
@@ -64,6 +64,8 @@ def load_lib() -> C.CDLL:
     lib.crtc_initialize.argtypes = [vp, C.c_int, C.c_int]
     lib.crtc_set_scene.argtypes = [vp, C.POINTER(CScene)]
     lib.crtc_render.argtypes = [vp, fp, fp, fp, C.c_float, C.c_int, C.c_int, vp, C.POINTER(CRenderStats)]
+    lib.crtc_render_async.argtypes = [vp, fp, fp, fp, C.c_float, C.c_int]
+    lib.crtc_sync.argtypes = [vp, C.POINTER(CRenderStats), vp, vp, C.POINTER(C.c_uint32)]
     lib.crtc_read_accum.argtypes = [vp, vp]
     lib.crtc_read_img.argtypes = [vp, vp]
     lib.crtc_get_stage_times.argtypes = [vp, vp, C.c_int]
@@ -142,6 +144,25 @@ class RenderCUDA:
         self._check(self.lib.crtc_render(self.h, pp, dp, up_, C.c_float(fovy), 1 if camera_changed else 0,
                                          1 if readback_framebuffer else 0, img_ptr, C.byref(st)))
         return RenderStats(st.render_time, st.rays_per_second, st.num_rays)
+
+    # ---- throughput variant: frames in flight (see include/crt_cuda.h) ----
+    def render_async(self, pos, dir, up, fovy: float, camera_changed: bool) -> None:
+        _p, pp = _vec3(pos)
+        _d, dp = _vec3(dir)
+        _u, up_ = _vec3(up)
+        self._check(self.lib.crtc_render_async(self.h, pp, dp, up_, C.c_float(fovy), 1 if camera_changed else 0))
+
+    def sync(self):
+        """Waits for all frames queued with render_async; returns (RenderStats totals, stage ms sums,
+        counter sums, number of frames)."""
+        st = CRenderStats()
+        stages = np.zeros(len(STAGE_NAMES), dtype=np.float32)
+        counters = np.zeros(len(COUNTER_NAMES), dtype=np.uint64)
+        n = C.c_uint32(0)
+        self._check(self.lib.crtc_sync(self.h, C.byref(st), stages.ctypes.data, counters.ctypes.data, C.byref(n)))
+        return (RenderStats(st.render_time, st.rays_per_second, st.num_rays),
+                {STAGE_NAMES[i]: float(stages[i]) for i in range(len(STAGE_NAMES))},
+                {COUNTER_NAMES[i]: int(counters[i]) for i in range(len(COUNTER_NAMES))}, int(n.value))
 
     # ---- extra exports (SURVEY.md §8b) ----
     def read_accum(self) -> np.ndarray:

@@ -68,6 +68,43 @@ struct DeviceBuffer {
 
 enum Stage { kStRaygen = 0, kStPrimary, kStShade, kStTraverse, kStNee, kStResolve, kStFrame, kNumStages };
 
+// What one enqueued frame leaves behind for later collection: its stage events and a pinned copy
+// of its device counters. Several frames may be in flight (crtc_render_async), so every frame has
+// its own record.
+struct FrameRecord {
+    std::vector<cudaEvent_t> events;
+    std::vector<int> event_stage;  // stage that ENDS at event i (i >= 1)
+    size_t num_events = 0;
+    uint32_t *h_counters = nullptr;  // pinned
+    unsigned long long *h_trav = nullptr;
+    uint32_t launches = 0;
+
+    FrameRecord()
+    {
+        CUDA_CHECK(cudaMallocHost(&h_counters, crt::kNumCounters * sizeof(uint32_t)));
+        CUDA_CHECK(cudaMallocHost(&h_trav, 4 * sizeof(unsigned long long)));
+    }
+    ~FrameRecord()
+    {
+        for (auto e : events) {
+            cudaEventDestroy(e);
+        }
+        cudaFreeHost(h_counters);
+        cudaFreeHost(h_trav);
+    }
+    void mark(cudaStream_t s, int stage_ended)
+    {
+        if (num_events >= events.size()) {
+            cudaEvent_t e;
+            CUDA_CHECK(cudaEventCreate(&e));
+            events.push_back(e);
+            event_stage.push_back(0);
+        }
+        event_stage[num_events] = stage_ended;
+        CUDA_CHECK(cudaEventRecord(events[num_events++], s));
+    }
+};
+
 }  // namespace
 
 struct crtc_renderer {
@@ -112,25 +149,15 @@ struct crtc_renderer {
     DeviceBuffer<float> d_accum_local, d_accum_full;
     DeviceBuffer<uint32_t> d_img_local, d_img_full;
 
-    // timing
-    std::vector<cudaEvent_t> events;
-    std::vector<int> event_stage;  // stage that ENDS at event i (i >= 1)
-    float stage_ms[kNumStages] = {0};
-    uint64_t counters_out[8] = {0};
-    uint32_t *h_counters = nullptr;  // pinned
-    unsigned long long *h_trav = nullptr;
+    // frames: records of enqueued-but-not-collected frames, and a pool of reusable ones
+    std::vector<std::unique_ptr<FrameRecord>> in_flight, record_pool;
+    float stage_ms[kNumStages] = {0};   // last collected frame
+    uint64_t counters_out[8] = {0};     // last collected frame
 
     ~crtc_renderer()
     {
-        for (auto e : events) {
-            cudaEventDestroy(e);
-        }
-        if (h_counters) {
-            cudaFreeHost(h_counters);
-        }
-        if (h_trav) {
-            cudaFreeHost(h_trav);
-        }
+        in_flight.clear();
+        record_pool.clear();
         if (own_stream) {
             cudaStreamDestroy(own_stream);
         }
@@ -226,10 +253,6 @@ struct crtc_renderer {
         d_counters.alloc(crt::kNumCounters);
         d_trav_counters.alloc(4);
         path_capacity = npaths;
-        if (!h_counters) {
-            CUDA_CHECK(cudaMallocHost(&h_counters, crt::kNumCounters * sizeof(uint32_t)));
-            CUDA_CHECK(cudaMallocHost(&h_trav, 4 * sizeof(unsigned long long)));
-        }
     }
 
     void initialize(int w, int h)
@@ -326,20 +349,6 @@ struct crtc_renderer {
         }
     }
 
-    cudaEvent_t next_event(size_t &cursor, int stage_ended)
-    {
-        if (cursor >= events.size()) {
-            cudaEvent_t e;
-            CUDA_CHECK(cudaEventCreate(&e));
-            events.push_back(e);
-            event_stage.push_back(0);
-        }
-        event_stage[cursor] = stage_ended;
-        cudaEvent_t e = events[cursor++];
-        CUDA_CHECK(cudaEventRecord(e, stream));
-        return e;
-    }
-
     static float3 glm_normalize(float3 v)
     {
         // glm::normalize(v) = v * inversesqrt(dot(v, v)), inversesqrt(x) = 1 / sqrt(x)
@@ -371,8 +380,8 @@ struct crtc_renderer {
         return v;
     }
 
-    void render(const float *pos, const float *dir, const float *up, float fovy, bool camera_changed, bool readback,
-                uint32_t *img, crt_render_stats_t *stats)
+    // Enqueues one frame on the stream (no host synchronisation) and returns its record.
+    FrameRecord &enqueue_frame(const float *pos, const float *dir, const float *up, float fovy, bool camera_changed)
     {
         if (fb_w == 0) {
             throw std::runtime_error("render: initialize() has not been called");
@@ -393,10 +402,16 @@ struct crtc_renderer {
         const crt::DeviceScene sc = device_scene();
         const crt::FrameLayout fl = frame_layout();
         const crt::PathState ps = path_state();
-        uint32_t launches = 0;
+        if (record_pool.empty()) {
+            record_pool.emplace_back(new FrameRecord());
+        }
+        in_flight.push_back(std::move(record_pool.back()));
+        record_pool.pop_back();
+        FrameRecord &rec = *in_flight.back();
+        rec.num_events = 0;
+        rec.launches = 0;
 
-        size_t ev = 0;
-        next_event(ev, -1);
+        rec.mark(stream, -1);
         CUDA_CHECK(cudaMemsetAsync(d_counters.ptr, 0, crt::kNumCounters * sizeof(uint32_t), stream));
         if (count_traversal) {
             CUDA_CHECK(cudaMemsetAsync(d_trav_counters.ptr, 0, 4 * sizeof(unsigned long long), stream));
@@ -405,76 +420,130 @@ struct crtc_renderer {
             const unsigned g256 = (unsigned)((npaths + 255) / 256);
             const unsigned g128 = (unsigned)((npaths + 127) / 128);
             crt::k_raygen<<<g256, 256, 0, stream>>>(view, fl, ps);
-            ++launches;
-            next_event(ev, kStRaygen);
+            rec.mark(stream, kStRaygen);
             // closest hit of the primary rays, then per bounce: shade -> one traversal launch for this
             // bounce's shadow rays AND the next bounce's continuation rays -> NEE resolve
             launch_traverse(sc, ps, ps.queue[0], ps.counters + crt::kCntQueue, nullptr, ps.counters + crt::kCntWork);
-            ++launches;
-            next_event(ev, kStPrimary);
+            rec.mark(stream, kStPrimary);
+            rec.launches += 2;
             for (int b = 0; b < max_depth; ++b) {
                 uint32_t *qin = ps.queue[b & 1], *qout = ps.queue[(b + 1) & 1];
                 crt::k_shade<<<g128, 128, 0, stream>>>(sc, ps, qin, qout, b, max_depth);
-                next_event(ev, kStShade);
+                rec.mark(stream, kStShade);
                 const bool last = b + 1 == max_depth;
                 launch_traverse(sc, ps, qout, last ? nullptr : ps.counters + crt::kCntQueue + b + 1,
                                 ps.counters + crt::kCntShadow + b, ps.counters + crt::kCntWork + 1 + b);
-                next_event(ev, kStTraverse);
+                rec.mark(stream, kStTraverse);
                 crt::k_nee_resolve<<<g256, 256, 0, stream>>>(ps, qin, b);
-                next_event(ev, kStNee);
-                launches += 3;
+                rec.mark(stream, kStNee);
+                rec.launches += 3;
             }
             const unsigned gpx = (unsigned)((npx_local + 255) / 256);
             const bool full = world_size == 1;
             crt::k_resolve<<<gpx, 256, 0, stream>>>(fl, ps, frame_id, d_accum_local.ptr, d_img_local.ptr,
                                                     full ? d_accum_full.ptr : nullptr, full ? d_img_full.ptr : nullptr);
-            ++launches;
-            next_event(ev, kStResolve);
+            rec.launches += 1;
+            rec.mark(stream, kStResolve);
         }
-        CUDA_CHECK(cudaMemcpyAsync(h_counters, d_counters.ptr, crt::kNumCounters * sizeof(uint32_t),
+        CUDA_CHECK(cudaMemcpyAsync(rec.h_counters, d_counters.ptr, crt::kNumCounters * sizeof(uint32_t),
                                    cudaMemcpyDeviceToHost, stream));
         if (count_traversal) {
-            CUDA_CHECK(cudaMemcpyAsync(h_trav, d_trav_counters.ptr, 4 * sizeof(unsigned long long),
+            CUDA_CHECK(cudaMemcpyAsync(rec.h_trav, d_trav_counters.ptr, 4 * sizeof(unsigned long long),
                                        cudaMemcpyDeviceToHost, stream));
         }
+        CUDA_CHECK(cudaGetLastError());
+        ++frame_id;
+        return rec;
+    }
+
+    // After a stream synchronisation: folds every in-flight frame's events and counters into
+    // `stage_sum` / `counter_sum` (both optional) and leaves the last frame's values in
+    // stage_ms / counters_out. Returns the number of frames collected.
+    uint32_t collect(float *stage_sum, uint64_t *counter_sum)
+    {
+        uint32_t n = 0;
+        for (auto &recp : in_flight) {
+            FrameRecord &rec = *recp;
+            for (int s = 0; s < kNumStages; ++s) {
+                stage_ms[s] = 0.f;
+            }
+            for (size_t i = 1; i < rec.num_events; ++i) {
+                float ms = 0.f;
+                CUDA_CHECK(cudaEventElapsedTime(&ms, rec.events[i - 1], rec.events[i]));
+                stage_ms[rec.event_stage[i]] += ms;
+            }
+            if (rec.num_events > 1) {
+                CUDA_CHECK(cudaEventElapsedTime(&stage_ms[kStFrame], rec.events[0], rec.events[rec.num_events - 1]));
+            }
+            uint64_t closest = 0, shadow = 0;
+            for (int b = 0; b < max_depth; ++b) {
+                closest += rec.h_counters[crt::kCntQueue + b];
+                shadow += rec.h_counters[crt::kCntShadow + b];
+            }
+            counters_out[0] = closest;
+            counters_out[1] = shadow;
+            counters_out[2] = rec.launches;
+            counters_out[3] = count_traversal ? rec.h_trav[0] : 0;
+            counters_out[4] = count_traversal ? rec.h_trav[1] : 0;
+            counters_out[5] = rec.h_counters[crt::kCntQueue];
+            counters_out[6] = count_traversal ? rec.h_trav[2] : 0;
+            counters_out[7] = count_traversal ? rec.h_trav[3] : 0;
+            for (int s = 0; stage_sum && s < kNumStages; ++s) {
+                stage_sum[s] += stage_ms[s];
+            }
+            for (int k = 0; counter_sum && k < 8; ++k) {
+                counter_sum[k] += counters_out[k];
+            }
+            ++n;
+        }
+        for (auto &recp : in_flight) {
+            record_pool.push_back(std::move(recp));
+        }
+        in_flight.clear();
+        return n;
+    }
+
+    // RenderBackend::render: enqueue, wait, collect (+ optional readback of img).
+    void render(const float *pos, const float *dir, const float *up, float fovy, bool camera_changed, bool readback,
+                uint32_t *img, crt_render_stats_t *stats)
+    {
+        enqueue_frame(pos, dir, up, fovy, camera_changed);
         if (readback && img && world_size == 1) {
             CUDA_CHECK(cudaMemcpyAsync(img, d_img_full.ptr, (size_t)fb_w * fb_h * 4, cudaMemcpyDeviceToHost, stream));
         }
         CUDA_CHECK(cudaStreamSynchronize(stream));
         CUDA_CHECK(cudaGetLastError());
-
-        // stage times
-        for (int s = 0; s < kNumStages; ++s) {
-            stage_ms[s] = 0.f;
-        }
-        for (size_t i = 1; i < ev; ++i) {
-            float ms = 0.f;
-            CUDA_CHECK(cudaEventElapsedTime(&ms, events[i - 1], events[i]));
-            stage_ms[event_stage[i]] += ms;
-        }
-        if (ev > 1) {
-            CUDA_CHECK(cudaEventElapsedTime(&stage_ms[kStFrame], events[0], events[ev - 1]));
-        }
-        uint64_t closest = 0, shadow = 0;
-        for (int b = 0; b < max_depth; ++b) {
-            closest += h_counters[crt::kCntQueue + b];
-            shadow += h_counters[crt::kCntShadow + b];
-        }
-        counters_out[0] = closest;
-        counters_out[1] = shadow;
-        counters_out[2] = launches;
-        counters_out[3] = count_traversal ? h_trav[0] : 0;
-        counters_out[4] = count_traversal ? h_trav[1] : 0;
-        counters_out[5] = h_counters[crt::kCntQueue];
-        counters_out[6] = count_traversal ? h_trav[2] : 0;
-        counters_out[7] = count_traversal ? h_trav[3] : 0;
+        collect(nullptr, nullptr);
         if (stats) {
+            const uint64_t rays = counters_out[0] + counters_out[1];
             stats->render_time = stage_ms[kStFrame];
-            stats->num_rays = closest + shadow;
+            stats->num_rays = rays;
             stats->rays_per_second =
-                stage_ms[kStFrame] > 0.f ? (float)((double)(closest + shadow) / (stage_ms[kStFrame] * 1.0e-3)) : 0.f;
+                stage_ms[kStFrame] > 0.f ? (float)((double)rays / (stage_ms[kStFrame] * 1.0e-3)) : 0.f;
         }
-        ++frame_id;
+    }
+
+    // crtc_sync: waits for every frame enqueued with crtc_render_async and returns their totals.
+    uint32_t sync_frames(crt_render_stats_t *total, float *stage_sum, uint64_t *counter_sum)
+    {
+        make_current();
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        CUDA_CHECK(cudaGetLastError());
+        float ssum[kNumStages] = {0};
+        uint64_t csum[8] = {0};
+        const uint32_t n = collect(ssum, csum);
+        if (total) {
+            total->render_time = ssum[kStFrame];
+            total->num_rays = csum[0] + csum[1];
+            total->rays_per_second = ssum[kStFrame] > 0.f ? (float)((double)total->num_rays / (ssum[kStFrame] * 1.0e-3)) : 0.f;
+        }
+        for (int s = 0; stage_sum && s < kNumStages; ++s) {
+            stage_sum[s] = ssum[s];
+        }
+        for (int k = 0; counter_sum && k < 8; ++k) {
+            counter_sum[k] = csum[k];
+        }
+        return n;
     }
 
     // ---- kernel-level access ----
@@ -787,6 +856,23 @@ int crtc_render(crtc_renderer *r, const float *pos, const float *dir, const floa
                 int readback_framebuffer, uint32_t *img, crt_render_stats_t *stats)
 {
     CRTC_TRY({ r->render(pos, dir, up, fovy, camera_changed != 0, readback_framebuffer != 0, img, stats); })
+}
+
+int crtc_render_async(crtc_renderer *r, const float *pos, const float *dir, const float *up, float fovy,
+                      int camera_changed)
+{
+    CRTC_TRY({ r->enqueue_frame(pos, dir, up, fovy, camera_changed != 0); })
+}
+
+int crtc_sync(crtc_renderer *r, crt_render_stats_t *total, float *stage_ms_sum, uint64_t *counters_sum,
+              uint32_t *num_frames)
+{
+    CRTC_TRY({
+        const uint32_t n = r->sync_frames(total, stage_ms_sum, counters_sum);
+        if (num_frames) {
+            *num_frames = n;
+        }
+    })
 }
 
 int crtc_read_accum(crtc_renderer *r, float *rgb_out)

@@ -84,6 +84,17 @@ int crtc_set_scene(crtc_renderer *r, const crt_scene_t *scene);
 int crtc_render(crtc_renderer *r, const float *pos, const float *dir, const float *up, float fovy,
                 int camera_changed, int readback_framebuffer, uint32_t *img, crt_render_stats_t *stats);
 
+/* Throughput variant of render for frame loops that do not need each frame's result on the host:
+ * enqueues the frame on the renderer's stream and returns immediately, so the host can queue the
+ * next frame (or a gather) while this one runs. crtc_sync waits for all such frames and returns
+ * their totals: `total` (render_time = sum of per-frame device times, num_rays = sum),
+ * `stage_ms_sum` (7 floats, as crtc_get_stage_times), `counters_sum` (8, as crtc_get_counters),
+ * `num_frames`; any of them may be NULL. The accumulation semantics are those of crtc_render. */
+int crtc_render_async(crtc_renderer *r, const float *pos, const float *dir, const float *up, float fovy,
+                      int camera_changed);
+int crtc_sync(crtc_renderer *r, crt_render_stats_t *total, float *stage_ms_sum, uint64_t *counters_sum,
+              uint32_t *num_frames);
+
 /* The accumulated float framebuffer (what parity compares): fb_width*fb_height*3 floats,
  * row-major RGB. The reference keeps it backend-private and tile-major
  * (render_embree.h:26, render_embree.ispc:345); this is the extra export SURVEY.md §8b asks
