@@ -424,24 +424,10 @@ __global__ void __launch_bounds__(kTravBlock, 8)
 }
 
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ float3 disney_brdf_call(const DisneyMaterial &mat, const float3 n, const float3 w_o,
-                                                const float3 w_i, const float3 v_x, const float3 v_y)
-{
-    return disney_brdf(mat, n, w_o, w_i, v_x, v_y);
-}
-__device__ __noinline__ float disney_pdf_call(const DisneyMaterial &mat, const float3 n, const float3 w_o,
-                                              const float3 w_i, const float3 v_x, const float3 v_y)
-{
-    return disney_pdf(mat, n, w_o, w_i, v_x, v_y);
-}
-__device__ __noinline__ float3 sample_disney_brdf_call(const DisneyMaterial &mat, const float3 n, const float3 w_o,
-                                                       const float3 v_x, const float3 v_y, uint32_t &rng,
-                                                       float3 &w_i, float &pdf)
-{
-    return sample_disney_brdf(mat, n, w_o, v_x, v_y, rng, w_i, pdf);
-}
-
-__global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState ps, const uint32_t *queue_in,
+// 80 registers (6 blocks of 128 per SM) with the three BSDF evaluations inlined measured fastest:
+// 3.19 ms/frame -> 2.67 ms on C2 against 4 blocks x 106 registers with out-of-line BSDF calls
+// (inlining lets the compiler share sub-expressions between disney_pdf and disney_brdf).
+__global__ void __launch_bounds__(128, 6) k_shade(DeviceScene sc, PathState ps, const uint32_t *queue_in,
                                                uint32_t *queue_out, int bounce, int max_depth)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -505,13 +491,13 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState ps, con
                     const float light_dist = length(light_dir);
                     light_dir = normalize(light_dir);
                     const float light_pdf = quad_light_pdf(light, light_pos, light_dir);
-                    const float bsdf_pdf = disney_pdf_call(mat, normal, w_o, light_dir, v_x, v_y);
+                    const float bsdf_pdf = disney_pdf(mat, normal, w_o, light_dir, v_x, v_y);
                     // the reference traces (and counts) this shadow ray before the pdf tests
                     emit_a = true;
                     dir_a = light_dir;
                     dist_a = light_dist;
                     if (light_pdf >= kEpsilon && bsdf_pdf >= kEpsilon) {
-                        const float3 bsdf = disney_brdf_call(mat, normal, w_o, light_dir, v_x, v_y);
+                        const float3 bsdf = disney_brdf(mat, normal, w_o, light_dir, v_x, v_y);
                         const float w = power_heuristic(1.f, light_pdf, 1.f, bsdf_pdf);
                         l1 = bsdf * light.emission * fabsf(dot(light_dir, normal)) * w / light_pdf;
                     }
@@ -519,7 +505,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState ps, con
                 {
                     float3 w_i;
                     float bsdf_pdf;
-                    const float3 bsdf = sample_disney_brdf_call(mat, normal, w_o, v_x, v_y, rng, w_i, bsdf_pdf);
+                    const float3 bsdf = sample_disney_brdf(mat, normal, w_o, v_x, v_y, rng, w_i, bsdf_pdf);
                     float light_dist;
                     float3 light_pos;
                     if (!all_zero(bsdf) && bsdf_pdf >= kEpsilon &&
@@ -545,7 +531,7 @@ __global__ void __launch_bounds__(128) k_shade(DeviceScene sc, PathState ps, con
             // ---- continuation, render_embree.ispc:313-336 ----
             float pdf;
             float3 w_i;
-            const float3 bsdf = sample_disney_brdf_call(mat, normal, w_o, v_x, v_y, rng, w_i, pdf);
+            const float3 bsdf = sample_disney_brdf(mat, normal, w_o, v_x, v_y, rng, w_i, pdf);
             if (!(pdf == 0.f || all_zero(bsdf))) {
                 path_throughput = path_throughput * bsdf * fabsf(dot(w_i, normal)) / pdf;
                 const int nb = bounce + 1;
