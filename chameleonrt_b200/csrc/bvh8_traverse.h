@@ -163,14 +163,16 @@ struct TravState {
     Ray ray;
     float idx, idy, idz;
     uint32_t oct_inv4;
+    uint32_t one;  // 0x3F800000, deliberately opaque to the compiler (see byte_unit)
     float tfar;
     uint2 cur;
     HitRecord hit;
 };
 
-CRT_HD void trav_init(TravState &s, const Ray &ray)
+CRT_HD void trav_init(TravState &s, const Ray &ray, uint32_t one = 0x3F800000u)
 {
     s.ray = ray;
+    s.one = one;
     // direction reciprocal with the usual guard for zero components
     const float eps = 1e-20f;
     s.idx = 1.f / (fabsf(ray.dx) > eps ? ray.dx : (ray.dx < 0.f ? -eps : eps));
@@ -187,15 +189,25 @@ CRT_HD void trav_init(TravState &s, const Ray &ray)
     s.cur.y = 0x80000000u;  // root: "inner child in slot 7 of a virtual parent"
 }
 
-// byte j of `packed` as an exact float, without an int->float conversion: I2F executes on the
-// quarter-rate XU pipe, which the first profile showed at 52 % utilisation (48 conversions per
-// node). One byte-permute builds the float 2^23 + b, one FADD removes the 2^23 — both exact.
-CRT_HD float byte_to_float(uint32_t packed, int j)
+// byte j of `packed` as the float 1 + b * 2^-15, built by ONE byte-permute (no int->float
+// conversion: I2F executes on the quarter-rate XU pipe, which the first profile showed at 52 %
+// utilisation with 48 conversions per node). `one` must hold 0x3F800000 in a REGISTER the compiler
+// cannot see through (TravState::one comes from a kernel argument): SASS PRMT takes a single
+// immediate, and with the constant in a register the selector becomes the immediate instead of
+// being re-materialised into a register before every PRMT.
+CRT_HD float byte_unit(uint32_t packed, int j, uint32_t one)
 {
 #if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(packed, 0x4B000000u, 0x7650u | (uint32_t)j)) - 8388608.f;
+    uint32_t r;
+    switch (j) {  // j is a compile-time constant after unrolling; the selector must be an immediate
+    case 0: asm("prmt.b32 %0, %1, %2, 0x7604;" : "=r"(r) : "r"(packed), "r"(one)); break;
+    case 1: asm("prmt.b32 %0, %1, %2, 0x7614;" : "=r"(r) : "r"(packed), "r"(one)); break;
+    case 2: asm("prmt.b32 %0, %1, %2, 0x7624;" : "=r"(r) : "r"(packed), "r"(one)); break;
+    default: asm("prmt.b32 %0, %1, %2, 0x7634;" : "=r"(r) : "r"(packed), "r"(one)); break;
+    }
+    return __uint_as_float(r);
 #else
-    return (float)((packed >> (8 * j)) & 0xffu);
+    return u2f(one | (((packed >> (8 * j)) & 0xffu) << 8));
 #endif
 }
 
@@ -209,22 +221,26 @@ CRT_HD void node_intersect(const float4 *__restrict__ nodes, const TravState &s,
     const float4 *np = nodes + (size_t)node_index * 5;
     const float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
     const uint32_t e_imask = f2u(n0.w);
-    // plane distance = q * ad + ob with ad = 2^e / d, ob = (p - o) / d
-    const float adx = u2f((e_imask & 0xffu) << 23) * s.idx;
-    const float ady = u2f(((e_imask >> 8) & 0xffu) << 23) * s.idy;
-    const float adz = u2f(((e_imask >> 16) & 0xffu) << 23) * s.idz;
-    const float obx = (n0.x - ray.ox) * s.idx;
-    const float oby = (n0.y - ray.oy) * s.idy;
-    const float obz = (n0.z - ray.oz) * s.idz;
-    // Rounding slack, per axis: a plane distance is fma(q, ad, ob) with |ob| possibly much larger
-    // than the result (cancellation), so its absolute error scales with |ob| + 255 |ad| OF THAT AXIS
-    // (it grows like 1/d: huge for an axis the ray is nearly parallel to, tiny for the others).
-    // Each axis' interval is widened by its own bound — folded into ob, so it costs nothing per
-    // child — which keeps the box test conservative with respect to the (independently rounded)
-    // triangle test, including for equal-t ties, without loosening the other two axes.
-    const float sx = 4e-7f * (fabsf(obx) + 255.f * fabsf(adx));
-    const float sy = 4e-7f * (fabsf(oby) + 255.f * fabsf(ady));
-    const float sz = 4e-7f * (fabsf(obz) + 255.f * fabsf(adz));
+    // plane distance = q * ad0 + ob0 with ad0 = 2^e / d, ob0 = (p - o) / d. q enters as
+    // qf = 1 + q * 2^-15 (byte_unit), so t = qf * ad + ob with ad = 2^15 ad0 and ob = ob0 - ad.
+    const float adx = u2f((e_imask & 0xffu) << 23) * s.idx * 32768.f;
+    const float ady = u2f(((e_imask >> 8) & 0xffu) << 23) * s.idy * 32768.f;
+    const float adz = u2f(((e_imask >> 16) & 0xffu) << 23) * s.idz * 32768.f;
+    const float ob0x = (n0.x - ray.ox) * s.idx;
+    const float ob0y = (n0.y - ray.oy) * s.idy;
+    const float ob0z = (n0.z - ray.oz) * s.idz;
+    const float obx = ob0x - adx, oby = ob0y - ady, obz = ob0z - adz;
+    // Rounding slack, per axis: |ob0| can be much larger than a plane distance (cancellation), and
+    // ob0 - ad rounds at the scale of ad = 2^15 ad0 (up to 2^-9 of a grid step), so the absolute
+    // error of a plane distance is bounded by ~2e-7 |ob0| + 1.2e-7 |ad| OF THAT AXIS (it grows like
+    // 1/d: huge for an axis the ray is nearly parallel to, tiny for the others). Each axis'
+    // interval is widened by its own bound — folded into ob, so it costs nothing per child — which
+    // keeps the box test conservative with respect to the (independently rounded) triangle test,
+    // including for equal-t ties, without loosening the other two axes. (A first version widened all
+    // axes by the worst axis' bound: near-axis rays then visited the whole tree.)
+    const float sx = 4e-7f * fabsf(ob0x) + 2.4e-7f * fabsf(adx);
+    const float sy = 4e-7f * fabsf(ob0y) + 2.4e-7f * fabsf(ady);
+    const float sz = 4e-7f * fabsf(ob0z) + 2.4e-7f * fabsf(adz);
     const float obx_lo = obx - sx, obx_hi = obx + sx;
     const float oby_lo = oby - sy, oby_hi = oby + sy;
     const float obz_lo = obz - sz, obz_hi = obz + sz;
@@ -244,12 +260,12 @@ CRT_HD void node_intersect(const float4 *__restrict__ nodes, const TravState &s,
         const uint32_t zmin = ray.dz < 0.f ? qhiz : qloz, zmax = ray.dz < 0.f ? qloz : qhiz;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float tminx = fma_(byte_to_float(xmin, j), adx, obx_lo);
-            const float tminy = fma_(byte_to_float(ymin, j), ady, oby_lo);
-            const float tminz = fma_(byte_to_float(zmin, j), adz, obz_lo);
-            const float tmaxx = fma_(byte_to_float(xmax, j), adx, obx_hi);
-            const float tmaxy = fma_(byte_to_float(ymax, j), ady, oby_hi);
-            const float tmaxz = fma_(byte_to_float(zmax, j), adz, obz_hi);
+            const float tminx = fma_(byte_unit(xmin, j, s.one), adx, obx_lo);
+            const float tminy = fma_(byte_unit(ymin, j, s.one), ady, oby_lo);
+            const float tminz = fma_(byte_unit(zmin, j, s.one), adz, obz_lo);
+            const float tmaxx = fma_(byte_unit(xmax, j, s.one), adx, obx_hi);
+            const float tmaxy = fma_(byte_unit(ymax, j, s.one), ady, oby_hi);
+            const float tmaxz = fma_(byte_unit(zmax, j, s.one), adz, obz_hi);
             const float tmin = fmaxf_(fmaxf_(tminx, tminy), fmaxf_(tminz, ray.tnear));
             const float tmax = fminf_(fminf_(tmaxx, tmaxy), fminf_(tmaxz, s.tfar));
             if (tmin <= tmax) {

@@ -196,6 +196,7 @@ struct crtc_renderer {
         sc.texels = d_texels.ptr;
         sc.tex = d_tex.ptr;
         sc.num_lights = num_lights;
+        sc.float_one = 0x3F800000u;
         return sc;
     }
 

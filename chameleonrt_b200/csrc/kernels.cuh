@@ -52,6 +52,7 @@ struct DeviceScene {
     const uint32_t *texels;
     const DevTex *tex;
     uint32_t num_lights;
+    uint32_t float_one;  // 0x3F800000 as a run-time value (bvh8_traverse.h: byte_unit)
 };
 
 struct FrameLayout {
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                     const float4 o = ps.ray_o[out_index], d = ps.ray_d[out_index];
                     ray = Ray{o.x, o.y, o.z, o.w, d.x, d.y, d.z, d.w};
                 }
-                trav_init(st, ray);
+                trav_init(st, ray, sc.float_one);
                 stack.sp = 0;
                 tri = make_uint2(0u, 0u);
                 alive = true;
