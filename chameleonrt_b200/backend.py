@@ -64,7 +64,7 @@ def load_lib() -> C.CDLL:
     lib.crtc_initialize.argtypes = [vp, C.c_int, C.c_int]
     lib.crtc_set_scene.argtypes = [vp, C.POINTER(CScene)]
     lib.crtc_render.argtypes = [vp, fp, fp, fp, C.c_float, C.c_int, C.c_int, vp, C.POINTER(CRenderStats)]
-    lib.crtc_render_async.argtypes = [vp, fp, fp, fp, C.c_float, C.c_int]
+    lib.crtc_render_async.argtypes = [vp, fp, fp, fp, C.c_float, C.c_int, C.c_uint32]
     lib.crtc_sync.argtypes = [vp, C.POINTER(CRenderStats), vp, vp, C.POINTER(C.c_uint32)]
     lib.crtc_read_accum.argtypes = [vp, vp]
     lib.crtc_read_img.argtypes = [vp, vp]
@@ -146,11 +146,14 @@ class RenderCUDA:
         return RenderStats(st.render_time, st.rays_per_second, st.num_rays)
 
     # ---- throughput variant: frames in flight (see include/crt_cuda.h) ----
-    def render_async(self, pos, dir, up, fovy: float, camera_changed: bool) -> None:
+    def render_async(self, pos, dir, up, fovy: float, camera_changed: bool, num_frames: int = 1) -> None:
+        """Enqueues ``num_frames`` consecutive frames as one wavefront (bit-identical to that many
+        ``render`` calls); returns immediately."""
         _p, pp = _vec3(pos)
         _d, dp = _vec3(dir)
         _u, up_ = _vec3(up)
-        self._check(self.lib.crtc_render_async(self.h, pp, dp, up_, C.c_float(fovy), 1 if camera_changed else 0))
+        self._check(self.lib.crtc_render_async(self.h, pp, dp, up_, C.c_float(fovy), 1 if camera_changed else 0,
+                                               num_frames))
 
     def sync(self):
         """Waits for all frames queued with render_async; returns (RenderStats totals, stage ms sums,

@@ -78,6 +78,7 @@ struct FrameRecord {
     uint32_t *h_counters = nullptr;  // pinned
     unsigned long long *h_trav = nullptr;
     uint32_t launches = 0;
+    uint32_t frames = 1;  // frames rendered by this record's launch sequence
 
     FrameRecord()
     {
@@ -208,6 +209,7 @@ struct crtc_renderer {
         f.ntx = ntx;
         f.npx_local = npx_local;
         f.spp = spp;
+        f.frames = 1;
         f.tile_ids = d_tile_ids.ptr;
         return f;
     }
@@ -382,8 +384,14 @@ struct crtc_renderer {
     }
 
     // Enqueues one frame on the stream (no host synchronisation) and returns its record.
-    FrameRecord &enqueue_frame(const float *pos, const float *dir, const float *up, float fovy, bool camera_changed)
+    // `num_frames` consecutive frames are rendered as ONE wavefront (their samples are in flight
+    // together) and folded into the running mean in order — bit-identical to num_frames calls.
+    FrameRecord &enqueue_frame(const float *pos, const float *dir, const float *up, float fovy, bool camera_changed,
+                               uint32_t num_frames = 1)
     {
+        if (num_frames < 1 || num_frames > 64) {
+            throw std::runtime_error("render: num_frames must be in [1, 64]");
+        }
         if (fb_w == 0) {
             throw std::runtime_error("render: initialize() has not been called");
         }
@@ -395,13 +403,14 @@ struct crtc_renderer {
             frame_id = 0;  // render_embree.cpp:145-147
         }
         const crt::ViewParams view = view_params(pos, dir, up, fovy);
-        const size_t npaths = (size_t)npx_local * spp;
+        const size_t npaths = (size_t)npx_local * spp * num_frames;
         if (npaths >= 0x7fffffffull) {
-            throw std::runtime_error("render: more than 2^31 paths per frame on one device");
+            throw std::runtime_error("render: more than 2^31 paths in flight on one device");
         }
         ensure_path_buffers(npaths);
         const crt::DeviceScene sc = device_scene();
-        const crt::FrameLayout fl = frame_layout();
+        crt::FrameLayout fl = frame_layout();
+        fl.frames = num_frames;
         const crt::PathState ps = path_state();
         if (record_pool.empty()) {
             record_pool.emplace_back(new FrameRecord());
@@ -453,7 +462,8 @@ struct crtc_renderer {
                                        cudaMemcpyDeviceToHost, stream));
         }
         CUDA_CHECK(cudaGetLastError());
-        ++frame_id;
+        frame_id += num_frames;
+        rec.frames = num_frames;
         return rec;
     }
 
@@ -495,7 +505,7 @@ struct crtc_renderer {
             for (int k = 0; counter_sum && k < 8; ++k) {
                 counter_sum[k] += counters_out[k];
             }
-            ++n;
+            n += rec.frames;
         }
         for (auto &recp : in_flight) {
             record_pool.push_back(std::move(recp));
@@ -860,9 +870,9 @@ int crtc_render(crtc_renderer *r, const float *pos, const float *dir, const floa
 }
 
 int crtc_render_async(crtc_renderer *r, const float *pos, const float *dir, const float *up, float fovy,
-                      int camera_changed)
+                      int camera_changed, uint32_t num_frames)
 {
-    CRTC_TRY({ r->enqueue_frame(pos, dir, up, fovy, camera_changed != 0); })
+    CRTC_TRY({ r->enqueue_frame(pos, dir, up, fovy, camera_changed != 0, num_frames); })
 }
 
 int crtc_sync(crtc_renderer *r, crt_render_stats_t *total, float *stage_ms_sum, uint64_t *counters_sum,

@@ -60,6 +60,8 @@ struct FrameLayout {
     uint32_t ntx;             // tiles per row
     uint32_t npx_local;       // num_local_tiles * 4096
     uint32_t spp;
+    uint32_t frames;          // consecutive frames rendered by this launch sequence (>= 1): their
+                              // frames * spp samples per pixel are in flight together
     const uint32_t *tile_ids; // global tile id of each local tile
 };
 
@@ -114,14 +116,15 @@ __device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred)
 __global__ void __launch_bounds__(256) k_raygen(ViewParams view, FrameLayout f, PathState ps)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t npaths = f.npx_local * f.spp;
+    const uint32_t npaths = f.npx_local * f.spp * f.frames;
     bool valid = false;
     if (i < npaths) {
+        // sample index over the batch: frame (view.frame_id + s / spp), sample s % spp of it
         const uint32_t lp = i % f.npx_local, s = i / f.npx_local;
         uint32_t x, y;
         if (local_pixel_coords(f, lp, x, y)) {
             valid = true;
-            // render_embree.ispc:213-232
+            // render_embree.ispc:213-232; (frame_id + k) * spp + 1 + (s - k * spp) == frame_id * spp + 1 + s
             uint32_t rng = get_rng(x + y * (uint32_t)f.fb_w, view.frame_id * f.spp + 1u + s);
             const float px_x = ((float)x + lcg_randomf(rng)) / (float)(uint32_t)f.fb_w;
             const float px_y = ((float)y + lcg_randomf(rng)) / (float)(uint32_t)f.fb_h;
@@ -615,14 +618,19 @@ __global__ void __launch_bounds__(256) k_resolve(FrameLayout f, PathState ps, ui
     if (!local_pixel_coords(f, lp, x, y)) {
         return;
     }
-    float3 illum = mk3(0.f);
-    for (uint32_t s = 0; s < f.spp; ++s) {
-        const float4 r = ps.radiance[(size_t)s * f.npx_local + lp];
-        illum = illum + mk3(r.x, r.y, r.z);
+    // the frames of the batch are folded into the running mean one after the other, exactly as if
+    // they had been rendered by separate calls
+    float3 illum = mk3(accum_local[3 * (size_t)lp], accum_local[3 * (size_t)lp + 1], accum_local[3 * (size_t)lp + 2]);
+    for (uint32_t k = 0; k < f.frames; ++k) {
+        const float3 accum = illum;
+        illum = mk3(0.f);
+        for (uint32_t s = 0; s < f.spp; ++s) {
+            const float4 r = ps.radiance[(size_t)(k * f.spp + s) * f.npx_local + lp];
+            illum = illum + mk3(r.x, r.y, r.z);
+        }
+        illum = illum / (float)f.spp;
+        illum = (illum + (float)(frame_id + k) * accum) / (float)(frame_id + k + 1u);
     }
-    illum = illum / (float)f.spp;
-    const float3 accum = mk3(accum_local[3 * (size_t)lp], accum_local[3 * (size_t)lp + 1], accum_local[3 * (size_t)lp + 2]);
-    illum = (illum + (float)frame_id * accum) / (float)(frame_id + 1u);
     accum_local[3 * (size_t)lp] = illum.x;
     accum_local[3 * (size_t)lp + 1] = illum.y;
     accum_local[3 * (size_t)lp + 2] = illum.z;

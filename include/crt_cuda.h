@@ -85,13 +85,16 @@ int crtc_render(crtc_renderer *r, const float *pos, const float *dir, const floa
                 int camera_changed, int readback_framebuffer, uint32_t *img, crt_render_stats_t *stats);
 
 /* Throughput variant of render for frame loops that do not need each frame's result on the host:
- * enqueues the frame on the renderer's stream and returns immediately, so the host can queue the
- * next frame (or a gather) while this one runs. crtc_sync waits for all such frames and returns
+ * enqueues `num_frames` (>= 1) consecutive frames on the renderer's stream and returns immediately,
+ * so the host can queue more work (or a gather) while they run. The frames of one call are
+ * rendered as a single wavefront — num_frames * spp samples per pixel in flight together, seeded
+ * and folded into the running mean exactly as num_frames separate calls would be (bit-identical
+ * result) — which keeps a GPU that owns only part of the image busy. crtc_sync waits for all such frames and returns
  * their totals: `total` (render_time = sum of per-frame device times, num_rays = sum),
  * `stage_ms_sum` (7 floats, as crtc_get_stage_times), `counters_sum` (8, as crtc_get_counters),
  * `num_frames`; any of them may be NULL. The accumulation semantics are those of crtc_render. */
 int crtc_render_async(crtc_renderer *r, const float *pos, const float *dir, const float *up, float fovy,
-                      int camera_changed);
+                      int camera_changed, uint32_t num_frames);
 int crtc_sync(crtc_renderer *r, crt_render_stats_t *total, float *stage_ms_sum, uint64_t *counters_sum,
               uint32_t *num_frames);
 

@@ -262,6 +262,16 @@ def test_async_frames_match_blocking_frames(mods):
     assert stages["frame"] > 0 and stages["traverse"] > 0
     assert (a.read_accum().view(np.uint32) == b.read_accum().view(np.uint32)).all()
     assert (a.read_img() == b.read_img()).all()
+    # a batch of frames rendered as one wavefront: 1 + 3 frames == 4 separate frames, bit for bit
+    d = mods[0](0)
+    d.initialize(96, 64)
+    d.set_scene(scene)
+    d.render_async(c.eye(), c.dir(), c.up(), cam["fov_y"], True, 1)
+    d.render_async(c.eye(), c.dir(), c.up(), cam["fov_y"], False, 3)
+    totals_d, _, counters_d, n_d = d.sync()
+    assert n_d == 4 and totals_d.num_rays == rays and counters_d["kernel_launches"] == 2 * (2 + 3 * 5 + 1)
+    assert (a.read_accum().view(np.uint32) == d.read_accum().view(np.uint32)).all()
+    assert (a.read_img() == d.read_img()).all()
 
 
 def test_rungholt_like_frame(mods):
