@@ -205,6 +205,11 @@ _REAL_STDOUT = None
 
 def main():
     global _REAL_STDOUT
+    # watchdog: a run that does not finish is killed with a traceback instead of hanging its caller
+    import faulthandler
+
+    faulthandler.dump_traceback_later(int(os.environ.get("CRT_BENCH_WATCHDOG", "900")), repeat=False, file=sys.stderr,
+                                      exit=True)
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
@@ -310,13 +315,19 @@ def main():
         # region, so the GPU queue stays full; N > 1: each frame's gather overlaps the next frame
         e0.record(stream)
         done = 0
+        batch_done = []  # the host stays at most 2 batches ahead of the GPU (bounded launch queues)
         while done < args.steps:
+            if len(batch_done) >= 2:
+                batch_done[-2].synchronize()
             nb = min(frames_in_flight, args.steps - done)
             gpu.render_async(*view, f == 0, nb)
             f += nb
             done += nb
             if world > 1:
                 gatherer.submit()
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            batch_done.append(ev)
         flush()  # the last frame's gather + assembly belong to the timed region
         e1.record(stream)
         barrier()
