@@ -134,11 +134,27 @@ def cpu_cores():
         return os.cpu_count() or 1
 
 
-def time_oracle(scene, view, budget_s: float, frames_cap: int, fast: bool = True):
-    """Times the CPU oracle (all host threads) on the workload; returns per-frame list."""
+def cpu_reference_backend():
+    """The CPU implementation of the path that is timed beside the GPU. Where the reference's own Embree
+    backend was compiled (oracle/_ref/libcrt_embree_fast.so: /root/reference/backends/embree sources, ISPC
+    kernels as scalar C++, Embree/TBB replaced by stand-ins; oracle/ref_build/Makefile) that is used and the
+    kind is "reference"; otherwise the oracle port. Both render bit-identical frames in their strict builds
+    (tests/test_reference_embree.py); these are the -O3 builds of each."""
+    from oracle import ref_embree
+
+    if ref_embree.available(fast=True) and os.environ.get("CRT_BENCH_CPU", "reference") != "port":
+        return (ref_embree.RefEmbreeBackend(max_depth=MAX_DEPTH, fast=True), "reference",
+                "the reference's backends/embree sources (render_embree.cpp + render_embree.ispc/.ih compiled as "
+                "scalar C++, -O3 x86-64-v3; Embree replaced by an own BVH2, TBB by std::thread), all host threads")
     from oracle import OracleBackend
 
-    cpu = OracleBackend(max_depth=MAX_DEPTH, fast=fast)
+    return (OracleBackend(max_depth=MAX_DEPTH, fast=True), "port",
+            "CPU oracle = Embree/ISPC backend restated with an own BVH2, -O3 x86-64-v3, all host threads")
+
+
+def time_oracle(scene, view, budget_s: float, frames_cap: int):
+    """Times the CPU implementation (all host threads) on the workload; returns per-frame list."""
+    cpu, kind, desc = cpu_reference_backend()
     cpu.initialize(WIDTH, HEIGHT)
     cpu.set_scene(scene)
     results = []
@@ -150,21 +166,19 @@ def time_oracle(scene, view, budget_s: float, frames_cap: int, fast: bool = True
         f += 1
         if f >= frames_cap or (time.time() - t0) > budget_s:
             break
-    return results, cpu
+    return results, kind, desc
 
 
 def run_reference_arm(args):
-    """--impl reference: the CPU implementation of the path on this box's host cores. The
-    reference's own Embree/ISPC backend cannot be built here (no Embree/TBB/ISPC/GLM/SDL, no
-    network: DESIGN.md §3), so this is the oracle port, with every host thread."""
+    """--impl reference: the CPU implementation of the path on this box's host cores, with every host
+    thread: the reference's own Embree backend sources where they were compiled (oracle/_ref, prebuilt for
+    the GPU box), else the oracle port (cpu_reference_backend)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     scene, view = make_workload()
-    from oracle import OracleBackend
-
     budget_s = float(os.environ.get("CRT_BENCH_REF_BUDGET", "240"))
-    cpu = OracleBackend(max_depth=MAX_DEPTH, fast=True)
+    cpu, kind, desc = cpu_reference_backend()
     cpu.initialize(WIDTH, HEIGHT)
     cpu.set_scene(scene)
     # probe: one full frame. Each step is a full frame of the workload when K + W of them fit the
@@ -178,6 +192,10 @@ def run_reference_arm(args):
     if est > budget_s and SPP > 1:
         spp_step = max(1, int(SPP * budget_s / est))
         scene.samples_per_pixel = spp_step
+        # a fresh backend: the reference's set_scene appends to its material/texture tables
+        # (render_embree.cpp:106-131), it is meant to be called once per renderer
+        cpu, kind, desc = cpu_reference_backend()
+        cpu.initialize(WIDTH, HEIGHT)
         cpu.set_scene(scene)
     f = 0
     for _ in range(args.warmup):
@@ -196,10 +214,9 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "spp": SPP, "max_depth": MAX_DEPTH},
-        "cpu_baseline": {"value": value, "unit": "MRays/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "MRays/s", "cores": cores, "kind": kind,
                          "sample": f"{args.steps} frames of the workload at {spp_step} of {SPP} spp per step after 1 "
-                                   f"probe + {args.warmup} warm-up frames; CPU oracle (Embree/ISPC backend "
-                                   "restated, own BVH2), all host threads"},
+                                   f"probe + {args.warmup} warm-up frames; {desc}"},
         "e2e": {"value": value, "unit": "MRays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -440,15 +457,14 @@ def main():
             "clocks": clock_summary,
         }
         if not args.no_cpu_baseline and not args.profile_mode and world == 1:
-            res, _ = time_oracle(scene, view, budget_s=20.0, frames_cap=6)
+            res, cpu_kind, cpu_desc = time_oracle(scene, view, budget_s=20.0, frames_cap=6)
             warm = res[1:] if len(res) > 1 else res
             cms = sum(r[0] for r in warm)
             crays = sum(r[1] for r in warm)
             line["cpu_baseline"] = {
-                "value": crays / (cms * 1e3), "unit": "MRays/s", "cores": cpu_cores(), "kind": "port",
+                "value": crays / (cms * 1e3), "unit": "MRays/s", "cores": cpu_cores(), "kind": cpu_kind,
                 "ms_per_frame": cms / len(warm),
-                "sample": f"{len(warm)} full frame(s) of the same workload (1 warm-up frame discarded); CPU oracle "
-                          "= Embree/ISPC backend restated with an own BVH2, -O3 x86-64-v3, all host threads"}
+                "sample": f"{len(warm)} full frame(s) of the same workload (1 warm-up frame discarded); {cpu_desc}"}
         emit(line)
     if world > 1:
         dist.barrier()

@@ -20,6 +20,7 @@ tests read like the reference:
 from __future__ import annotations
 
 import ctypes as C
+import math
 import struct
 from dataclasses import dataclass, field
 from typing import List, Optional
@@ -35,7 +36,24 @@ TEXTURED_PARAM_MASK = 0x80000000
 def textured_param(tex_id: int, channel: int = 0) -> float:
     """Encode a texture handle into a material float (util/texture_channel_mask.h:16-23)."""
     mask = TEXTURED_PARAM_MASK | ((channel & 0x3) << 29) | (tex_id & 0x1FFFFFFF)
+    if (mask >> 23) & 0xFF == 0:
+        # a float32 denormal: build the value by integer arithmetic, a float->double load would read
+        # it as zero on a thread in denormals-are-zero mode (see f32_bits)
+        return -math.ldexp(mask & 0x7FFFFF, -149)
     return struct.unpack("<f", struct.pack("<I", mask))[0]
+
+
+def f32_bits(v: float) -> int:
+    """IEEE-754 binary32 bit pattern of ``v`` (a Python float holding a float32 value), computed so that
+    it does not depend on the thread's flush-to-zero / denormals-are-zero mode: texture handles with a
+    small id are float32 DENORMALS (0x80000000 | id), and a double->float conversion under FTZ (the
+    reference's Embree backend switches it on, render_embree.cpp:21-24) would flush them to -0."""
+    v = float(v)
+    a = abs(v)
+    if a != 0.0 and a < 2.0 ** -126:  # float32 denormal: integer multiple of 2^-149, exact in double
+        sign = 0x80000000 if math.copysign(1.0, v) < 0 else 0
+        return sign | int(round(a * 2.0 ** 149))
+    return int(np.float32(v).view(np.uint32))
 
 
 @dataclass
@@ -365,8 +383,8 @@ class Scene:
             cinst[i].parameterized_mesh_id = inst.parameterized_mesh_id
         cmats = (CMaterial * max(1, len(self.materials)))()
         for i, mat in enumerate(self.materials):
-            raw = np.array(mat.as_floats(), dtype=np.float32)
-            # texture handles are NaN-patterned floats: copy bitwise
+            # texture handles are bit patterns (negative denormals / NaNs as floats): copy bitwise
+            raw = np.array([f32_bits(x) for x in mat.as_floats()], dtype=np.uint32)
             C.memmove(C.addressof(cmats[i]), raw.ctypes.data, 64)
         ctex = (CImage * max(1, len(self.textures)))()
         for i, t in enumerate(self.textures):

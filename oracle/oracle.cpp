@@ -4,11 +4,20 @@
  * and bench.py's cpu_baseline / --impl reference legs may load it. The CUDA backend under
  * chameleonrt_b200/ never links, imports or calls anything in this directory.
  *
- * PARITY STATUS: "parity unpinned". The reference ships no tests, golden images or
- * known-answer vectors, and its Embree backend cannot be built here
- * (no Embree/TBB/ISPC/GLM/SDL), so this restatement is pinned only by
- * (a) line-by-line citation of the reference sources below, (b) a brute-force
- * cross-check of its own BVH, and (c) self-generated golden vectors (tests/golden/).
+ * PARITY STATUS: PINNED against the reference's own code run in this sandbox. The reference ships
+ * no tests, golden images or known-answer vectors, and its build system cannot run
+ * here (no Embree/TBB/ISPC/GLM/SDL), but its Embree backend's OWN SOURCES compile from where they
+ * lie: oracle/ref_build/Makefile builds backends/embree/{render_embree.cpp,embree_utils.cpp} and
+ * render_embree.ispc + *.ih (the ISPC kernels as scalar C++, ref_build/ispc_cpp/prologue.h) into
+ * oracle/_ref/libcrt_embree.so. This restatement reproduces that library's float framebuffers,
+ * per-pixel ray counts, sRGB8 images and pure-function tables BIT FOR BIT on every scene class
+ * (tests/test_reference_embree.py: frozen in tests/golden/ref_embree_frames.npz, and live where
+ * the library exists, up to full 1280x720x4spp depth-8 frames). What that pin cannot cover, because the
+ * third-party pieces are absent: Embree's own triangle intersector and BVH (replaced on BOTH sides
+ * by this repository's intersection contract, below), the ISPC built-in math library (libm on both
+ * sides: last-ulp differences in sin/cos/pow/log/atan2/acos) and ISPC's table-driven
+ * float_to_srgb8. Also pinned by (a) line-by-line citation of the reference sources below, (b) a
+ * brute-force cross-check of its own BVH, (c) independent numpy restatements (tests/).
  *
  * What it restates (all paths relative to /root/reference):
  *   backends/embree/render_embree.ispc:66-370   trace_rays, sample_direct_light,
@@ -1052,7 +1061,8 @@ struct Hit {
     float3 ng;  // unnormalised, object space
 };
 
-// glm::inverse restated (cofactor expansion, column-major), float arithmetic
+// glm::inverse (embree_utils.cpp:97) as a general cofactor-expansion inverse, column-major, float arithmetic;
+// real GLM is absent here, third_party/miniglm and third_party/embree_stub use this same operation order
 void mat4_inverse(const float *m, float *out)
 {
     float inv[16];

@@ -34,6 +34,44 @@ def _render(r, cam, frames):
     return st
 
 
+# ---------------------------------------------------------------- against the reference's own output
+@pytest.fixture(scope="module")
+def ref_golden():
+    import os
+
+    from helpers import ROOT
+
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_embree_frames.npz"))
+
+
+def _ref_case_names():
+    from ref_cases import FRAME_CASES
+
+    return list(FRAME_CASES)
+
+
+@pytest.mark.parametrize("name", _ref_case_names())
+def test_cuda_matches_reference_embree_frames(mods, ref_golden, name):
+    """The CUDA backend against float framebuffers rendered by the REFERENCE'S OWN Embree/ISPC backend
+    (tests/golden/ref_embree_frames.npz, made by tests/golden/make_ref_embree_golden.py from
+    /root/reference/backends/embree compiled as described in oracle/ref_build/Makefile): same scene, camera,
+    seed, spp, depth and frame count. The frames are small (3.5-9 K pixels), so the matching-pixel threshold is
+    0.99 rather than the 0.999 used on the larger oracle comparisons; the per-pixel tolerance is the same."""
+    from ref_cases import make_case
+
+    RenderCUDA = mods[0]
+    scene, view, w, h, frames, depth = make_case(name)
+    gpu = RenderCUDA(0, max_depth=depth)
+    gpu.initialize(w, h)
+    gpu.set_scene(scene)
+    st = None
+    for f in range(frames):
+        st = gpu.render(*view, f == 0, True)
+    assert_parity(gpu.read_accum(), ref_golden[f"{name}.accum"], min_frac=0.99, max_rel_l1=1e-2)
+    ref_rays = int(ref_golden[f"{name}.rays"][-1])
+    assert abs(int(st.num_rays) - ref_rays) <= max(16, ref_rays // 500)  # REPORT_RAY_STATS count of the last frame
+
+
 # ---------------------------------------------------------------- kernel level: traversal
 @pytest.mark.parametrize("name", ["cornell", "sponza", "materials"])
 def test_traversal_kernels_bit_exact(mods, name):

@@ -1,6 +1,7 @@
 """The CPU oracle against the frozen golden vectors and against independent numpy/Python
-restatements of the reference's pure functions (parity is unpinned by the
-reference, so the oracle is pinned here twice)."""
+restatements of the reference's pure functions (the reference ships no vectors of its own, SURVEY.md
+§8c; the pin against the reference's own code is tests/test_reference_embree.py, these are the older,
+independent ones)."""
 import ctypes as C
 import math
 
