@@ -15,6 +15,8 @@
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <limits>
@@ -60,19 +62,170 @@ struct B2Node {
     uint32_t count;  // 0 = inner, 1 = leaf
 };
 
+// 4-wide float / int vectors (GCC/Clang vector extensions: SSE on x86-64, NEON on aarch64). Lane 3 is
+// padding everywhere below. vmin/vmax pick their operand exactly like std::min/std::max.
+typedef float f4 __attribute__((vector_size(16)));
+typedef int i4 __attribute__((vector_size(16)));
+inline f4 vmin(f4 a, f4 b) { return b < a ? b : a; }
+inline f4 vmax(f4 a, f4 b) { return a < b ? b : a; }
+inline f4 splat(float x) { return f4{x, x, x, x}; }
+constexpr float kFltMax = std::numeric_limits<float>::max();
+
+struct VBox {
+    f4 lo, hi;
+    void reset()
+    {
+        lo = splat(kFltMax);
+        hi = splat(-kFltMax);
+    }
+    void grow(const VBox &o)
+    {
+        lo = vmin(lo, o.lo);
+        hi = vmax(hi, o.hi);
+    }
+    void grow_pt(f4 p)
+    {
+        lo = vmin(lo, p);
+        hi = vmax(hi, p);
+    }
+    Box box() const
+    {
+        Box b;
+        for (int a = 0; a < 3; ++a) {
+            b.lo[a] = lo[a];
+            b.hi[a] = hi[a];
+        }
+        return b;
+    }
+    float half_area() const
+    {
+        const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+};
+
+// One primitive of the BVH2 build: 32 bytes, kept physically in tree order (partitioned in place, or
+// through a scratch buffer for big ranges), so every pass over a node's range is a sequential stream.
+struct Prim {
+    // box; the padding lanes carry the triangle index as the mantissas of two floats in [1, 2)
+    // (low 23 bits in lo[3], the rest in hi[3]): the lanes ride through the vector arithmetic below,
+    // and a raw index there would be a denormal operand (a microcode assist per operation)
+    f4 lo, hi;
+    static float pack23(uint32_t m)
+    {
+        const uint32_t u = 0x3F800000u | (m & 0x7FFFFFu);
+        float f;
+        std::memcpy(&f, &u, 4);
+        return f;
+    }
+    static uint32_t unpack23(float f)
+    {
+        uint32_t u;
+        std::memcpy(&u, &f, 4);
+        return u & 0x7FFFFFu;
+    }
+    void set_id(uint32_t i)
+    {
+        lo[3] = pack23(i);
+        hi[3] = pack23(i >> 23);
+    }
+    uint32_t id() const { return unpack23(lo[3]) | (unpack23(hi[3]) << 23); }
+    f4 centroid() const { return splat(0.5f) * (lo + hi); }
+};
+
 struct Task {
     uint32_t node, first, count;
+    VBox box, cbox;  // bounds of the range's boxes and of its centroids (known from the parent's split)
 };
 
 constexpr int kBins = 16;
-constexpr uint32_t kParallelThreshold = 1u << 15;
+constexpr uint32_t kParallelThreshold = 1u << 15;  // both halves at least this big: share the right half
+constexpr uint32_t kBigTask = 1u << 19;            // ranges this big are binned / partitioned by several threads
+constexpr uint32_t kBlock = 1u << 14;              // block of a big range (fixed: results do not depend on threads)
+
+struct Bins {
+    VBox box[3][kBins];
+    uint32_t cnt[3][kBins];
+    void reset()
+    {
+        for (int a = 0; a < 3; ++a) {
+            for (int b = 0; b < kBins; ++b) {
+                box[a][b].reset();
+                cnt[a][b] = 0;
+            }
+        }
+    }
+    void merge(const Bins &o)
+    {
+        for (int a = 0; a < 3; ++a) {
+            for (int b = 0; b < kBins; ++b) {
+                box[a][b].grow(o.box[a][b]);
+                cnt[a][b] += o.cnt[a][b];
+            }
+        }
+    }
+};
+
+struct BinFrame {
+    f4 cmin, scale;
+    bool valid[3];
+    explicit BinFrame(const VBox &cbox)
+    {
+        cmin = cbox.lo;
+        scale = splat(0.f);
+        for (int a = 0; a < 3; ++a) {
+            const float ext = cbox.hi[a] - cbox.lo[a];
+            valid[a] = ext > 0.f;
+            scale[a] = valid[a] ? kBins / ext : 0.f;
+        }
+        cmin[3] = 0.f;
+    }
+    // bin of the centroid on every axis: clamp((int)((c - cmin) * scale), 0, kBins - 1)
+    i4 bins(const Prim &p) const
+    {
+        f4 x = (p.centroid() - cmin) * scale;
+        x = vmin(vmax(x, splat(0.f)), splat((float)(kBins - 1)));
+        return __builtin_convertvector(x, i4);
+    }
+};
+
+// Runs f(block) for block in [0, nblocks) on `nthreads` threads (the caller is one of them).
+template <typename F>
+void parallel_blocks(uint32_t nblocks, int nthreads, const F &f)
+{
+    nthreads = (int)std::min<uint32_t>((uint32_t)std::max(1, nthreads), nblocks);
+    if (nthreads <= 1) {
+        for (uint32_t b = 0; b < nblocks; ++b) {
+            f(b);
+        }
+        return;
+    }
+    std::atomic<uint32_t> next(0);
+    auto run = [&] {
+        for (;;) {
+            const uint32_t b = next.fetch_add(1);
+            if (b >= nblocks) {
+                return;
+            }
+            f(b);
+        }
+    };
+    std::vector<std::thread> helpers;
+    for (int t = 1; t < nthreads; ++t) {
+        helpers.emplace_back(run);
+    }
+    run();
+    for (auto &h : helpers) {
+        h.join();
+    }
+}
 
 struct Bvh2Builder {
-    const Box *prim_box;
-    const float *prim_cent;  // 3 per prim
-    std::vector<uint32_t> prim_ids;
+    std::vector<Prim> prims, scratch;
     std::vector<B2Node> nodes;
     std::atomic<uint32_t> next_node{1};
+    int threads = 1;
+    std::atomic<int> big_running{0};  // big ranges being split right now: they share the helper threads
 
     std::mutex mtx;
     std::condition_variable cv;
@@ -89,59 +242,47 @@ struct Bvh2Builder {
         cv.notify_one();
     }
 
-    // Splits [first, first+count) of prim_ids; returns the split position.
-    uint32_t split(const Task &t, const Box &cbox)
+    void bin_range(uint32_t first, uint32_t count, const BinFrame &fr, Bins &bins) const
     {
-        const uint32_t first = t.first, count = t.count;
-        Box bin_box[3][kBins];
-        uint32_t bin_cnt[3][kBins];
-        float scale[3], cmin[3];
-        bool valid[3];
-        for (int a = 0; a < 3; ++a) {
-            cmin[a] = cbox.lo[a];
-            const float ext = cbox.hi[a] - cbox.lo[a];
-            valid[a] = ext > 0.f;
-            scale[a] = valid[a] ? kBins / ext : 0.f;
-            for (int b = 0; b < kBins; ++b) {
-                bin_box[a][b].reset();
-                bin_cnt[a][b] = 0;
-            }
-        }
-        for (uint32_t i = first; i < first + count; ++i) {
-            const uint32_t p = prim_ids[i];
-            const float *c = prim_cent + 3 * (size_t)p;
+        bins.reset();
+        const Prim *p = prims.data() + first;
+        for (uint32_t i = 0; i < count; ++i) {
+            const i4 b = fr.bins(p[i]);
             for (int a = 0; a < 3; ++a) {
-                if (!valid[a]) {
-                    continue;
-                }
-                int b = (int)((c[a] - cmin[a]) * scale[a]);
-                b = std::min(std::max(b, 0), kBins - 1);
-                bin_box[a][b].grow(prim_box[p]);
-                bin_cnt[a][b]++;
+                VBox &bb = bins.box[a][b[a]];
+                bb.lo = vmin(bb.lo, p[i].lo);
+                bb.hi = vmax(bb.hi, p[i].hi);
+                bins.cnt[a][b[a]]++;
             }
         }
+    }
+
+    // Binned SAH over the three axes; returns false if no split separates the primitives.
+    static bool choose_split(const Bins &bins, const BinFrame &fr, int &best_axis, int &best_bin)
+    {
         float best_cost = std::numeric_limits<float>::max();
-        int best_axis = -1, best_bin = 0;
+        best_axis = -1;
+        best_bin = 0;
         for (int a = 0; a < 3; ++a) {
-            if (!valid[a]) {
+            if (!fr.valid[a]) {
                 continue;
             }
             float right_area[kBins];
             uint32_t right_cnt[kBins];
-            Box acc;
+            VBox acc;
             acc.reset();
             uint32_t cnt = 0;
             for (int b = kBins - 1; b > 0; --b) {
-                acc.grow(bin_box[a][b]);
-                cnt += bin_cnt[a][b];
+                acc.grow(bins.box[a][b]);
+                cnt += bins.cnt[a][b];
                 right_area[b] = cnt ? acc.half_area() : 0.f;
                 right_cnt[b] = cnt;
             }
             acc.reset();
             cnt = 0;
             for (int b = 0; b < kBins - 1; ++b) {
-                acc.grow(bin_box[a][b]);
-                cnt += bin_cnt[a][b];
+                acc.grow(bins.box[a][b]);
+                cnt += bins.cnt[a][b];
                 if (cnt == 0 || right_cnt[b + 1] == 0) {
                     continue;
                 }
@@ -153,51 +294,164 @@ struct Bvh2Builder {
                 }
             }
         }
-        uint32_t mid = first + count / 2;
-        if (best_axis >= 0) {
-            const int a = best_axis;
-            auto it = std::partition(prim_ids.begin() + first, prim_ids.begin() + first + count,
-                                     [&](uint32_t p) {
-                                         int b = (int)((prim_cent[3 * (size_t)p + a] - cmin[a]) * scale[a]);
-                                         b = std::min(std::max(b, 0), kBins - 1);
-                                         return b <= best_bin;
-                                     });
-            const uint32_t m = (uint32_t)(it - prim_ids.begin());
-            if (m > first && m < first + count) {
-                mid = m;
-            }
-        }
-        return mid;
+        return best_axis >= 0;
     }
 
-    void process(Task root_task)
+    void range_bounds(uint32_t first, uint32_t count, VBox &box, VBox &cbox) const
+    {
+        box.reset();
+        cbox.reset();
+        for (uint32_t i = first; i < first + count; ++i) {
+            box.lo = vmin(box.lo, prims[i].lo);
+            box.hi = vmax(box.hi, prims[i].hi);
+            cbox.grow_pt(prims[i].centroid());
+        }
+    }
+
+    // Splits the task's range; fills the two child tasks (ranges and bounds).
+    void split(const Task &t, Task &tl, Task &tr)
+    {
+        const uint32_t first = t.first, count = t.count;
+        const BinFrame fr(t.cbox);
+        Bins bins;
+        const bool big = count >= kBigTask;
+        const uint32_t nblocks = big ? (count + kBlock - 1) / kBlock : 0;
+        std::vector<Bins> block_bins;
+        int nthreads = 1;
+        if (big) {
+            const int running = big_running.fetch_add(1) + 1;
+            nthreads = std::max(1, threads / running);
+            block_bins.resize(nblocks);
+            parallel_blocks(nblocks, nthreads, [&](uint32_t b) {
+                const uint32_t bf = first + b * kBlock;
+                bin_range(bf, std::min(kBlock, first + count - bf), fr, block_bins[b]);
+            });
+            bins.reset();
+            for (uint32_t b = 0; b < nblocks; ++b) {
+                bins.merge(block_bins[b]);
+            }
+        } else {
+            bin_range(first, count, fr, bins);
+        }
+        int axis, bin;
+        uint32_t mid = first + count / 2;
+        bool have_bounds = false;
+        if (choose_split(bins, fr, axis, bin)) {
+            uint32_t nleft = 0;
+            for (int b = 0; b <= bin; ++b) {
+                nleft += bins.cnt[axis][b];
+            }
+            tl.cbox.reset();
+            tr.cbox.reset();
+            if (big) {
+                // stable partition through the scratch buffer, block by block: the left / right
+                // offsets of a block follow from its own bin counts
+                std::vector<uint32_t> loff(nblocks), roff(nblocks);
+                std::vector<VBox> lcb(nblocks), rcb(nblocks);
+                uint32_t l = 0, r = 0;
+                for (uint32_t b = 0; b < nblocks; ++b) {
+                    loff[b] = l;
+                    roff[b] = r;
+                    uint32_t bl = 0, bc = 0;
+                    for (int k = 0; k < kBins; ++k) {
+                        bc += block_bins[b].cnt[axis][k];
+                        bl += k <= bin ? block_bins[b].cnt[axis][k] : 0;
+                    }
+                    l += bl;
+                    r += bc - bl;
+                }
+                parallel_blocks(nblocks, nthreads, [&](uint32_t b) {
+                    const uint32_t bf = first + b * kBlock, be = std::min(bf + kBlock, first + count);
+                    Prim *dl = scratch.data() + first + loff[b], *dr = scratch.data() + first + nleft + roff[b];
+                    VBox cl, cr;
+                    cl.reset();
+                    cr.reset();
+                    for (uint32_t i = bf; i < be; ++i) {
+                        const Prim &p = prims[i];
+                        if (fr.bins(p)[axis] <= bin) {
+                            *dl++ = p;
+                            cl.grow_pt(p.centroid());
+                        } else {
+                            *dr++ = p;
+                            cr.grow_pt(p.centroid());
+                        }
+                    }
+                    lcb[b] = cl;
+                    rcb[b] = cr;
+                });
+                parallel_blocks(nblocks, nthreads, [&](uint32_t b) {
+                    const uint32_t bf = first + b * kBlock, be = std::min(bf + kBlock, first + count);
+                    std::memcpy(prims.data() + bf, scratch.data() + bf, (size_t)(be - bf) * sizeof(Prim));
+                });
+                for (uint32_t b = 0; b < nblocks; ++b) {
+                    tl.cbox.grow(lcb[b]);
+                    tr.cbox.grow(rcb[b]);
+                }
+                mid = first + nleft;
+            } else {
+                // in-place two-pointer partition (the order std::partition produces), collecting the
+                // centroid bounds of both sides on the way
+                Prim *lo = prims.data() + first, *hi = prims.data() + first + count;
+                for (;;) {
+                    while (lo < hi && fr.bins(*lo)[axis] <= bin) {
+                        tl.cbox.grow_pt(lo->centroid());
+                        ++lo;
+                    }
+                    while (lo < hi && !(fr.bins(hi[-1])[axis] <= bin)) {
+                        tr.cbox.grow_pt(hi[-1].centroid());
+                        --hi;
+                    }
+                    if (lo >= hi) {
+                        break;
+                    }
+                    std::swap(*lo, hi[-1]);
+                }
+                mid = (uint32_t)(lo - prims.data());
+            }
+            // box bounds of the halves are the unions of their bins
+            tl.box.reset();
+            tr.box.reset();
+            for (int b = 0; b < kBins; ++b) {
+                if (bins.cnt[axis][b]) {
+                    (b <= bin ? tl : tr).box.grow(bins.box[axis][b]);
+                }
+            }
+            have_bounds = true;
+        }
+        if (big) {
+            big_running.fetch_sub(1);
+        }
+        tl.first = first;
+        tl.count = mid - first;
+        tr.first = mid;
+        tr.count = first + count - mid;
+        if (!have_bounds) {  // coincident centroids: split the range in the middle
+            range_bounds(tl.first, tl.count, tl.box, tl.cbox);
+            range_bounds(tr.first, tr.count, tr.box, tr.cbox);
+        }
+    }
+
+    void process(const Task &root_task)
     {
         std::vector<Task> local;
         local.push_back(root_task);
         while (!local.empty()) {
             const Task t = local.back();
             local.pop_back();
-            Box box, cbox;
-            box.reset();
-            cbox.reset();
-            for (uint32_t i = t.first; i < t.first + t.count; ++i) {
-                const uint32_t p = prim_ids[i];
-                box.grow(prim_box[p]);
-                cbox.grow_pt(prim_cent + 3 * (size_t)p);
-            }
             B2Node &n = nodes[t.node];
-            n.box = box;
+            n.box = t.box.box();
             if (t.count == 1) {
-                n.left = prim_ids[t.first];
+                n.left = prims[t.first].id();
                 n.count = 1;
                 continue;
             }
-            const uint32_t mid = split(t, cbox);
+            Task tl, tr;
+            split(t, tl, tr);
             const uint32_t left = next_node.fetch_add(2);
             n.left = left;
             n.count = 0;
-            const Task tl{left, t.first, mid - t.first};
-            const Task tr{left + 1, mid, t.first + t.count - mid};
+            tl.node = left;
+            tr.node = left + 1;
             if (tl.count >= kParallelThreshold && tr.count >= kParallelThreshold) {
                 push_shared(tr);
                 local.push_back(tl);
@@ -234,14 +488,47 @@ struct Bvh2Builder {
         }
     }
 
-    void build(uint32_t n, int threads)
+    // verts: 9 floats per triangle
+    void build(const float *verts, uint32_t n, int nthreads)
     {
-        prim_ids.resize(n);
-        for (uint32_t i = 0; i < n; ++i) {
-            prim_ids[i] = i;
+        threads = std::max(1, nthreads);
+        prims.resize(n);
+        if (n >= kBigTask) {
+            scratch.resize(n);
+        }
+        const uint32_t nblocks = (n + kBlock - 1) / kBlock;
+        std::vector<VBox> bb(nblocks), bc(nblocks);
+        parallel_blocks(nblocks, threads, [&](uint32_t b) {
+            bb[b].reset();
+            bc[b].reset();
+            const uint32_t e = std::min(n, (b + 1) * kBlock);
+            for (uint32_t i = b * kBlock; i < e; ++i) {
+                const float *v = verts + 9 * (size_t)i;
+                VBox x;
+                x.reset();
+                for (int k = 0; k < 3; ++k) {
+                    x.grow_pt(f4{v[3 * k], v[3 * k + 1], v[3 * k + 2], 0.f});
+                }
+                Prim &p = prims[i];
+                p.lo = x.lo;
+                p.hi = x.hi;
+                bb[b].grow(x);
+                bc[b].grow_pt(p.centroid());
+                p.set_id(i);
+            }
+        });
+        Task root;
+        root.node = 0;
+        root.first = 0;
+        root.count = n;
+        root.box.reset();
+        root.cbox.reset();
+        for (uint32_t b = 0; b < nblocks; ++b) {
+            root.box.grow(bb[b]);
+            root.cbox.grow(bc[b]);
         }
         nodes.resize(2 * (size_t)n - 1);
-        push_shared(Task{0, 0, n});
+        push_shared(root);
         std::vector<std::thread> pool;
         for (int i = 1; i < threads; ++i) {
             pool.emplace_back([this] { worker(); });
@@ -251,6 +538,8 @@ struct Bvh2Builder {
             th.join();
         }
         nodes.resize(next_node.load());
+        std::vector<Prim>().swap(prims);
+        std::vector<Prim>().swap(scratch);
     }
 };
 
@@ -280,14 +569,59 @@ struct Collapser {
         tri_count.resize(nodes.size());
     }
 
-    // post-order over an explicit stack (SAH trees can be deep)
-    void run(uint32_t root)
+    // The dynamic programme only looks at a node's two children, so disjoint subtrees are independent:
+    // the tree is cut at a frontier of subtree roots, the subtrees are solved in parallel, then the few
+    // nodes above the frontier are solved from the finished subtree roots.
+    void run_parallel(uint32_t root, int threads)
     {
+        std::vector<uint32_t> frontier{root};
+        const size_t want = (size_t)std::max(1, threads) * 8;
+        std::vector<uint8_t> is_frontier;
+        if (threads > 1 && n2.size() > (1u << 16)) {
+            // level-wise expansion; leaves stay in the frontier (they are trivial subtrees)
+            while (frontier.size() < want) {
+                std::vector<uint32_t> next;
+                bool expanded = false;
+                for (uint32_t n : frontier) {
+                    if (n2[n].count) {
+                        next.push_back(n);
+                    } else {
+                        next.push_back(n2[n].left);
+                        next.push_back(n2[n].left + 1);
+                        expanded = true;
+                    }
+                }
+                frontier.swap(next);
+                if (!expanded) {
+                    break;
+                }
+            }
+            is_frontier.assign(n2.size(), 0);
+            for (uint32_t n : frontier) {
+                is_frontier[n] = 1;
+            }
+            parallel_blocks((uint32_t)frontier.size(), threads, [&](uint32_t i) { run(frontier[i], nullptr); });
+            run(root, is_frontier.data());
+        } else {
+            run(root, nullptr);
+        }
+    }
+
+    // post-order over an explicit stack (SAH trees can be deep); nodes flagged in `solved` are taken as
+    // already computed and not descended into
+    void run(uint32_t root, const uint8_t *solved)
+    {
+        if (solved && solved[root]) {
+            return;
+        }
         std::vector<std::pair<uint32_t, bool>> stack;
         stack.emplace_back(root, false);
         while (!stack.empty()) {
             auto [n, expanded] = stack.back();
             stack.pop_back();
+            if (solved && solved[n]) {
+                continue;
+            }
             const B2Node &node = n2[n];
             if (node.count) {
                 tri_count[n] = 1;
@@ -372,19 +706,23 @@ struct Collapser {
     }
 };
 
-void collect_tris(const std::vector<B2Node> &n2, uint32_t n, std::vector<uint32_t> &out)
+// Triangle indices under BVH2 node n (a collapsed leaf: <= 3 triangles), left to right; returns the count.
+uint32_t collect_tris(const std::vector<B2Node> &n2, uint32_t n, uint32_t *out)
 {
-    std::vector<uint32_t> stack{n};
-    while (!stack.empty()) {
-        const uint32_t c = stack.back();
-        stack.pop_back();
+    uint32_t stack[8];
+    int sp = 0;
+    uint32_t k = 0;
+    stack[sp++] = n;
+    while (sp) {
+        const uint32_t c = stack[--sp];
         if (n2[c].count) {
-            out.push_back(n2[c].left);
+            out[k++] = n2[c].left;
         } else {
-            stack.push_back(n2[c].left + 1);
-            stack.push_back(n2[c].left);
+            stack[sp++] = n2[c].left + 1;
+            stack[sp++] = n2[c].left;
         }
     }
+    return k;
 }
 
 inline float pow2_from_biased(uint8_t e)
@@ -395,17 +733,30 @@ inline float pow2_from_biased(uint8_t e)
     return f;
 }
 
-// Writes one BVH8 node from its (<= 8) children.
-void emit_node(const std::vector<B2Node> &n2, const Collapser &col, const Box &box, const uint32_t *children,
-               int num_children, Bvh8Node &out, uint32_t child_base, uint32_t tri_base,
-               std::vector<uint32_t> &tri_order, uint32_t *inner_children, int &num_inner)
+// What the serial layout pass decides for one BVH8 node; the parallel pass fills the node from it.
+struct NodePlan {
+    uint32_t b2node;
+    uint32_t children[8];  // BVH2 node ids
+    int8_t slot_child[8];  // slot -> index into children, -1 = empty
+    uint8_t num_children;
+    uint32_t child_base, tri_base;
+};
+
+inline bool is_leaf_child(const std::vector<B2Node> &n2, const Collapser &col, uint32_t cn)
 {
-    // --- slot assignment: slot s should hold the child met first by rays of octant s
-    // (bit 2/1/0 set = negative x/y/z direction); greedy minimum of dot(centroid offset, d_s)
+    return n2[cn].count || col.decision[7 * (size_t)cn].type == kLeaf;
+}
+
+// Slot assignment: slot s should hold the child met first by rays of octant s (bit 2/1/0 set =
+// negative x/y/z direction); greedy minimum of dot(centroid offset, d_s).
+void assign_slots(const std::vector<B2Node> &n2, NodePlan &pl)
+{
+    const Box &box = n2[pl.b2node].box;
+    const int num_children = pl.num_children;
     float cx = 0.5f * (box.lo[0] + box.hi[0]), cy = 0.5f * (box.lo[1] + box.hi[1]), cz = 0.5f * (box.lo[2] + box.hi[2]);
     float cst[8][8];
     for (int c = 0; c < num_children; ++c) {
-        const Box &b = n2[children[c]].box;
+        const Box &b = n2[pl.children[c]].box;
         const float ox = 0.5f * (b.lo[0] + b.hi[0]) - cx, oy = 0.5f * (b.lo[1] + b.hi[1]) - cy,
                     oz = 0.5f * (b.lo[2] + b.hi[2]) - cz;
         for (int s = 0; s < 8; ++s) {
@@ -413,9 +764,8 @@ void emit_node(const std::vector<B2Node> &n2, const Collapser &col, const Box &b
             cst[c][s] = ox * dx + oy * dy + oz * dz;
         }
     }
-    int slot_child[8];
     for (int s = 0; s < 8; ++s) {
-        slot_child[s] = -1;
+        pl.slot_child[s] = -1;
     }
     bool child_done[8] = {false};
     for (int it = 0; it < num_children; ++it) {
@@ -426,7 +776,7 @@ void emit_node(const std::vector<B2Node> &n2, const Collapser &col, const Box &b
                 continue;
             }
             for (int s = 0; s < 8; ++s) {
-                if (slot_child[s] >= 0) {
+                if (pl.slot_child[s] >= 0) {
                     continue;
                 }
                 if (cst[c][s] < best) {
@@ -437,10 +787,14 @@ void emit_node(const std::vector<B2Node> &n2, const Collapser &col, const Box &b
             }
         }
         child_done[bc] = true;
-        slot_child[bs] = bc;
+        pl.slot_child[bs] = (int8_t)bc;
     }
+}
 
-    // --- quantisation frame
+// Writes one BVH8 node (quantisation frame, child boxes, meta bytes) and its leaves' triangle order.
+void fill_node(const std::vector<B2Node> &n2, const Collapser &col, const NodePlan &pl, Bvh8Node &out, uint32_t *tri_order)
+{
+    const Box &box = n2[pl.b2node].box;
     std::memset(&out, 0, sizeof(out));
     float max_ext = 0.f;
     for (int a = 0; a < 3; ++a) {
@@ -461,20 +815,19 @@ void emit_node(const std::vector<B2Node> &n2, const Collapser &col, const Box &b
         out.e[a] = (uint8_t)(e + 127);
         step[a] = pow2_from_biased(out.e[a]);
     }
-    out.child_base = child_base;
-    out.tri_base = tri_base;
+    out.child_base = pl.child_base;
+    out.tri_base = pl.tri_base;
 
     uint8_t *qlo[3] = {out.qlo_x, out.qlo_y, out.qlo_z};
     uint8_t *qhi[3] = {out.qhi_x, out.qhi_y, out.qhi_z};
     uint32_t tri_off = 0;
-    num_inner = 0;
     for (int s = 0; s < 8; ++s) {
-        const int c = slot_child[s];
+        const int c = pl.slot_child[s];
         if (c < 0) {
             out.meta[s] = 0;
             continue;
         }
-        const uint32_t cn = children[c];
+        const uint32_t cn = pl.children[c];
         const Box &b = n2[cn].box;
         for (int a = 0; a < 3; ++a) {
             const double p = out.p[a], st = step[a];
@@ -499,18 +852,14 @@ void emit_node(const std::vector<B2Node> &n2, const Collapser &col, const Box &b
             qlo[a][s] = (uint8_t)lo;
             qhi[a][s] = (uint8_t)hi;
         }
-        const bool is_leaf = n2[cn].count || col.decision[7 * (size_t)cn].type == kLeaf;
-        if (is_leaf) {
-            const size_t before = tri_order.size();
-            collect_tris(n2, cn, tri_order);
-            const uint32_t k = (uint32_t)(tri_order.size() - before);
+        if (is_leaf_child(n2, col, cn)) {
+            const uint32_t k = collect_tris(n2, cn, tri_order + pl.tri_base + tri_off);
             const uint8_t unary = k == 1 ? 0b001 : (k == 2 ? 0b011 : 0b111);
             out.meta[s] = (uint8_t)((unary << 5) | tri_off);
             tri_off += k;
         } else {
             out.meta[s] = (uint8_t)((0b001 << 5) | (24 + s));
             out.imask |= (uint8_t)(1u << s);
-            inner_children[num_inner++] = cn;
         }
     }
 }
@@ -522,6 +871,7 @@ void build_bvh8(const float *verts, size_t num_tris, int threads, Bvh8 &out)
     const auto t0 = std::chrono::steady_clock::now();
     out.nodes.clear();
     out.tri_order.clear();
+    out.max_depth = 0;
     if (threads <= 0) {
         threads = std::max(1u, std::thread::hardware_concurrency());
     }
@@ -536,86 +886,95 @@ void build_bvh8(const float *verts, size_t num_tris, int threads, Bvh8 &out)
         out.nodes.push_back(root);
         return;
     }
-    std::vector<Box> boxes(num_tris);
-    std::vector<float> cent(3 * num_tris);
-    {
-        auto fill = [&](size_t b, size_t e) {
-            for (size_t i = b; i < e; ++i) {
-                Box bx;
-                bx.reset();
-                bx.grow_pt(verts + 9 * i);
-                bx.grow_pt(verts + 9 * i + 3);
-                bx.grow_pt(verts + 9 * i + 6);
-                boxes[i] = bx;
-                for (int a = 0; a < 3; ++a) {
-                    cent[3 * i + a] = 0.5f * (bx.lo[a] + bx.hi[a]);
-                }
-            }
-        };
-        std::vector<std::thread> pool;
-        const size_t chunk = (num_tris + threads - 1) / threads;
-        for (int t = 0; t < threads; ++t) {
-            const size_t b = std::min(num_tris, t * chunk), e = std::min(num_tris, (t + 1) * chunk);
-            if (b < e) {
-                pool.emplace_back(fill, b, e);
-            }
+    const bool timing = std::getenv("CRT_BVH8_TIMING") != nullptr;
+    auto lap = [&, last = t0](const char *what) mutable {
+        const auto now = std::chrono::steady_clock::now();
+        if (timing) {
+            std::fprintf(stderr, "[bvh8] %-10s %.3f s\n", what, std::chrono::duration<double>(now - last).count());
         }
-        for (auto &th : pool) {
-            th.join();
-        }
-    }
+        last = now;
+    };
     Bvh2Builder b2;
-    b2.prim_box = boxes.data();
-    b2.prim_cent = cent.data();
-    b2.build((uint32_t)num_tris, threads);
+    b2.build(verts, (uint32_t)num_tris, threads);
     const std::vector<B2Node> &n2 = b2.nodes;
     for (int a = 0; a < 3; ++a) {
         out.scene_lo[a] = n2[0].box.lo[a];
         out.scene_hi[a] = n2[0].box.hi[a];
     }
 
+    lap("bvh2");
     Collapser col(n2);
-    col.run(0);
+    col.run_parallel(0, threads);
+    lap("collapse");
 
-    out.tri_order.reserve(num_tris);
-    out.nodes.reserve(num_tris / 2 + 16);
-    struct Pending {
-        uint32_t b2node;
-        uint32_t out_index;
-        uint32_t depth;
-    };
-    std::deque<Pending> queue;
-    out.nodes.emplace_back();
-    queue.push_back(Pending{0, 0, 1});
+    // Layout pass, breadth-first, one level at a time: in parallel over the level's nodes, which BVH2
+    // nodes become the children of each BVH8 node and which slot each takes; then serially, where the
+    // node's children and triangles start. Siblings are contiguous (child_base + rank among the inner
+    // children in slot order), triangles of a node likewise; the order is plain BFS.
+    std::vector<NodePlan> plans;
+    plans.reserve(num_tris / 2 + 16);
+    plans.emplace_back();
+    plans[0].b2node = 0;
+    uint32_t tri_total = 0;
     out.sah_cost = 0.0;
     const double root_area = std::max(1e-30f, n2[0].box.half_area());
-    while (!queue.empty()) {
-        const Pending cur = queue.front();
-        queue.pop_front();
-        out.max_depth = std::max(out.max_depth, cur.depth);
-        uint32_t children[8];
-        int num = 0;
-        const bool root_is_leaf = n2[cur.b2node].count || col.decision[7 * (size_t)cur.b2node].type == kLeaf;
-        if (root_is_leaf) {
-            // only possible for the scene root (<= 3 triangles): one leaf child
-            children[num++] = cur.b2node;
-        } else {
-            col.get_children(cur.b2node, 0, children, num);
+    size_t level_begin = 0, level_end = 1;
+    while (level_begin < level_end) {
+        ++out.max_depth;
+        const uint32_t kPlanBlock = 256;
+        const uint32_t nb = (uint32_t)((level_end - level_begin + kPlanBlock - 1) / kPlanBlock);
+        parallel_blocks(nb, threads, [&](uint32_t b) {
+            const size_t e = std::min(level_end, level_begin + (size_t)(b + 1) * kPlanBlock);
+            for (size_t i = level_begin + (size_t)b * kPlanBlock; i < e; ++i) {
+                NodePlan &pl = plans[i];
+                int num = 0;
+                if (is_leaf_child(n2, col, pl.b2node)) {
+                    // only possible for the scene root (<= 3 triangles): one leaf child
+                    pl.children[num++] = pl.b2node;
+                } else {
+                    col.get_children(pl.b2node, 0, pl.children, num);
+                }
+                pl.num_children = (uint8_t)num;
+                assign_slots(n2, pl);
+            }
+        });
+        for (size_t cur = level_begin; cur < level_end; ++cur) {
+            // (plans may reallocate below: index, do not hold references across emplace_back)
+            plans[cur].child_base = (uint32_t)plans.size();
+            plans[cur].tri_base = tri_total;
+            out.sah_cost += n2[plans[cur].b2node].box.half_area() / root_area * kNodeCost;
+            for (int s = 0; s < 8; ++s) {
+                const int c = plans[cur].slot_child[s];
+                if (c < 0) {
+                    continue;
+                }
+                const uint32_t cn = plans[cur].children[c];
+                if (is_leaf_child(n2, col, cn)) {
+                    tri_total += col.tri_count[cn];
+                } else {
+                    plans.emplace_back();
+                    plans.back().b2node = cn;
+                }
+            }
         }
-        uint32_t inner[8];
-        int num_inner = 0;
-        const uint32_t child_base = (uint32_t)out.nodes.size();
-        const uint32_t tri_base = (uint32_t)out.tri_order.size();
-        Bvh8Node node;
-        emit_node(n2, col, n2[cur.b2node].box, children, num, node, child_base, tri_base, out.tri_order, inner,
-                  num_inner);
-        out.nodes[cur.out_index] = node;
-        out.sah_cost += n2[cur.b2node].box.half_area() / root_area * kNodeCost;
-        for (int i = 0; i < num_inner; ++i) {
-            out.nodes.emplace_back();
-            queue.push_back(Pending{inner[i], child_base + (uint32_t)i, cur.depth + 1});
-        }
+        level_begin = level_end;
+        level_end = plans.size();
     }
+    lap("layout");
+    // Fill pass (parallel): quantised child boxes, meta bytes and triangle order of every node.
+    out.nodes.resize(plans.size());
+    out.tri_order.resize(tri_total);
+    {
+        const uint32_t kFillBlock = 1024;
+        const uint32_t nb = ((uint32_t)plans.size() + kFillBlock - 1) / kFillBlock;
+        parallel_blocks(nb, threads, [&](uint32_t b) {
+            const size_t e = std::min(plans.size(), (size_t)(b + 1) * kFillBlock);
+            for (size_t i = (size_t)b * kFillBlock; i < e; ++i) {
+                fill_node(n2, col, plans[i], out.nodes[i], out.tri_order.data());
+            }
+        });
+    }
+    lap("emit");
     out.build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 

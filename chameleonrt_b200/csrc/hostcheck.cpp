@@ -63,6 +63,23 @@ void crt_hostcheck_stats(void *p, double *out5)
     out5[4] = h->bvh.build_seconds * 1e3;
 }
 
+// FNV-1a over the node array and the triangle order: lets tests assert that builder changes
+// (threading, memory layout) leave the emitted BVH8 byte-identical
+uint64_t crt_hostcheck_digest(void *p)
+{
+    HostCheck *h = static_cast<HostCheck *>(p);
+    uint64_t d = 1469598103934665603ull;
+    auto mix = [&](const void *data, size_t n) {
+        const unsigned char *b = static_cast<const unsigned char *>(data);
+        for (size_t i = 0; i < n; ++i) {
+            d = (d ^ b[i]) * 1099511628211ull;
+        }
+    };
+    mix(h->bvh.nodes.data(), h->bvh.nodes.size() * sizeof(crt::Bvh8Node));
+    mix(h->bvh.tri_order.data(), h->bvh.tri_order.size() * sizeof(uint32_t));
+    return d;
+}
+
 // rays: n*8 floats; hits: n*4 floats {t,u,v,bits(flat id)}; normals (optional) n*3;
 // counters (optional) n*2 uint32 {nodes visited, triangles tested}
 void crt_hostcheck_trace(void *p, const float *rays, uint64_t n, int any_hit, float *hits, float *normals,

@@ -54,6 +54,8 @@ class HostCheck:
         lib.crt_hostcheck_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.crt_hostcheck_stats.argtypes = [C.c_void_p, C.c_void_p]
         lib.crt_hostcheck_last_error.restype = C.c_char_p
+        lib.crt_hostcheck_digest.restype = C.c_uint64
+        lib.crt_hostcheck_digest.argtypes = [C.c_void_p]
         self.lib = lib
         ms = scene.to_c()
         self.h = lib.crt_hostcheck_create(C.byref(ms.c), threads)
@@ -69,6 +71,9 @@ class HostCheck:
         a = (C.c_double * 5)()
         self.lib.crt_hostcheck_stats(self.h, a)
         return dict(nodes=int(a[0]), tris=int(a[1]), depth=int(a[2]), sah=a[3], build_ms=a[4])
+
+    def digest(self) -> int:
+        return int(self.lib.crt_hostcheck_digest(self.h))
 
     def trace(self, rays, any_hit=False, normals=False, counters=False):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)

@@ -106,3 +106,29 @@ def test_flatten_rejects_bad_input(built):
     scene.meshes[0].geometries[0].indices[0, 0] = 10_000
     with pytest.raises(RuntimeError, match="index"):
         HostCheck(scene)
+
+
+def test_big_scene_parallel_build_is_deterministic_and_exact(built):
+    """A scene above the builder's big-range threshold (2^19 triangles): the top of the tree is binned and
+    partitioned by several threads, the collapse and the node emission run in parallel. The emitted BVH8
+    must not depend on the thread count, and traversal must still be bit-exact against the oracle."""
+    from chameleonrt_b200.scenes import rungholt_like
+
+    scene, cam = rungholt_like(spp=1, scale=0.12)
+    assert scene.total_tris() > (1 << 19)
+    digests, stats = [], []
+    for threads in (1, 3, 0):
+        hc = HostCheck(scene, threads)
+        digests.append(hc.digest())
+        stats.append(hc.stats())
+    assert digests[0] == digests[1] == digests[2]
+    assert stats[0]["tris"] == scene.total_tris() and stats[0]["nodes"] == stats[2]["nodes"]
+    o = OracleBackend()
+    o.initialize(8, 8)
+    o.set_scene(scene)
+    rays = _rays(scene, cam, o, 64, 36)
+    ho = o.trace_closest(rays)
+    hb, _, _ = hc.trace(rays)
+    assert (ho.view(np.uint32) == hb.view(np.uint32)).all()
+    ha, _, _ = hc.trace(rays, any_hit=True)
+    assert ((ha[:, 3].view(np.uint32) != 0xFFFFFFFF) == o.trace_any(rays).astype(bool)).all()
