@@ -9,6 +9,7 @@
 // The reference has no builder (Embree / OptiX do it); nothing here is
 // derived from reference code.
 #include "bvh8.h"
+#include "host_parallel.h"
 
 #include <algorithm>
 #include <atomic>
@@ -188,37 +189,6 @@ struct BinFrame {
         return __builtin_convertvector(x, i4);
     }
 };
-
-// Runs f(block) for block in [0, nblocks) on `nthreads` threads (the caller is one of them).
-template <typename F>
-void parallel_blocks(uint32_t nblocks, int nthreads, const F &f)
-{
-    nthreads = (int)std::min<uint32_t>((uint32_t)std::max(1, nthreads), nblocks);
-    if (nthreads <= 1) {
-        for (uint32_t b = 0; b < nblocks; ++b) {
-            f(b);
-        }
-        return;
-    }
-    std::atomic<uint32_t> next(0);
-    auto run = [&] {
-        for (;;) {
-            const uint32_t b = next.fetch_add(1);
-            if (b >= nblocks) {
-                return;
-            }
-            f(b);
-        }
-    };
-    std::vector<std::thread> helpers;
-    for (int t = 1; t < nthreads; ++t) {
-        helpers.emplace_back(run);
-    }
-    run();
-    for (auto &h : helpers) {
-        h.join();
-    }
-}
 
 struct Bvh2Builder {
     std::vector<Prim> prims, scratch;

@@ -297,7 +297,7 @@ struct crtc_renderer {
         make_current();
         frame_id = 0;
         crt::HostScene hs;
-        crt::flatten_scene(scene, hs);
+        crt::flatten_scene(scene, hs, bvh_threads);
         crt::Bvh8 bvh;
         crt::build_bvh8(hs.tri_verts.data(), hs.num_tris(), bvh_threads, bvh);
         if (bvh.max_depth + 2 > CRT_STACK_SIZE) {
@@ -306,7 +306,7 @@ struct crtc_renderer {
         }
         std::vector<float> tri_records;
         std::vector<crt::TriShade> shade;
-        crt::pack_triangles(hs, bvh, tri_records, shade);
+        crt::pack_triangles(hs, bvh, tri_records, shade, bvh_threads);
         leaf_flat_ids.resize(shade.size());
         for (size_t i = 0; i < shade.size(); ++i) {
             leaf_flat_ids[i] = shade[i].flat_id;

@@ -4,8 +4,10 @@
 #include "host_scene.h"
 
 #include "bvh8.h"
+#include "host_parallel.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
@@ -84,7 +86,7 @@ void check_param(float x, uint32_t num_textures, const char *what, uint32_t mat)
 
 }  // namespace
 
-void flatten_scene(const crt_scene_t *s, HostScene &out)
+void flatten_scene(const crt_scene_t *s, HostScene &out, int threads)
 {
     out = HostScene();
     out.samples_per_pixel = s->samples_per_pixel;
@@ -116,14 +118,24 @@ void flatten_scene(const crt_scene_t *s, HostScene &out)
     out.tri_verts.resize(total * 9);
     out.tri_shade.resize(total);
 
+    // one segment per (instance, geometry); its triangles are processed in fixed blocks on several threads
+    struct Segment {
+        uint32_t instance, geometry, mat_id;
+        size_t flat_base;
+    };
+    struct Block {
+        uint32_t segment, p_begin, p_end;
+    };
+    std::vector<Segment> segments;
+    std::vector<Block> blocks;
+    std::vector<float> w2o_all((size_t)s->num_instances * 16);
+    const uint32_t kBlockTris = 1u << 15;
     size_t flat = 0;
     for (uint32_t i = 0; i < s->num_instances; ++i) {
         const crt_instance_t &inst = s->instances[i];
         const crt_parameterized_mesh_t &pm = s->parameterized_meshes[inst.parameterized_mesh_id];
         const crt_mesh_t &mesh = s->meshes[pm.mesh_id];
-        const float *m = inst.transform;
-        float w2o[16];
-        mat4_inverse(m, w2o);
+        mat4_inverse(inst.transform, &w2o_all[(size_t)i * 16]);
         for (uint32_t g = 0; g < mesh.num_geometries; ++g) {
             const crt_geometry_t &geom = mesh.geometries[g];
             const uint32_t mat_id = pm.material_ids[g];
@@ -132,54 +144,72 @@ void flatten_scene(const crt_scene_t *s, HostScene &out)
                                          " but the scene has " + std::to_string(s->num_materials) +
                                          " (run validate_materials, util/scene.cpp:935-958)");
             }
-            for (uint32_t p = 0; p < geom.num_tris; ++p, ++flat) {
-                const uint32_t idx[3] = {geom.indices[3 * p], geom.indices[3 * p + 1], geom.indices[3 * p + 2]};
-                float vo[3][3];
+            segments.push_back(Segment{i, g, mat_id, flat});
+            for (uint32_t p = 0; p < geom.num_tris; p += kBlockTris) {
+                blocks.push_back(Block{(uint32_t)segments.size() - 1, p, std::min(geom.num_tris, p + kBlockTris)});
+            }
+            flat += geom.num_tris;
+        }
+    }
+    std::atomic<bool> bad_index(false);
+    parallel_blocks((uint32_t)blocks.size(), host_threads(threads), [&](uint32_t bi) {
+        const Block &blk = blocks[bi];
+        const Segment &seg = segments[blk.segment];
+        const crt_instance_t &inst = s->instances[seg.instance];
+        const crt_geometry_t &geom = s->meshes[s->parameterized_meshes[inst.parameterized_mesh_id].mesh_id].geometries[seg.geometry];
+        const float *m = inst.transform;
+        const float *w2o = &w2o_all[(size_t)seg.instance * 16];
+        for (uint32_t p = blk.p_begin; p < blk.p_end; ++p) {
+            const size_t f = seg.flat_base + p;
+            const uint32_t idx[3] = {geom.indices[3 * p], geom.indices[3 * p + 1], geom.indices[3 * p + 2]};
+            if (idx[0] >= geom.num_vertices || idx[1] >= geom.num_vertices || idx[2] >= geom.num_vertices) {
+                bad_index = true;
+                return;
+            }
+            float vo[3][3];
+            for (int k = 0; k < 3; ++k) {
+                const float *v = geom.vertices + 3 * (size_t)idx[k];
+                vo[k][0] = v[0];
+                vo[k][1] = v[1];
+                vo[k][2] = v[2];
+                float *w = &out.tri_verts[f * 9 + 3 * k];
+                w[0] = m[0] * v[0] + m[4] * v[1] + m[8] * v[2] + m[12];
+                w[1] = m[1] * v[0] + m[5] * v[1] + m[9] * v[2] + m[13];
+                w[2] = m[2] * v[0] + m[6] * v[1] + m[10] * v[2] + m[14];
+            }
+            TriShade &ts = out.tri_shade[f];
+            // Ng = cross(v1 - v0, v2 - v0) in object space, normalised
+            const float e1[3] = {vo[1][0] - vo[0][0], vo[1][1] - vo[0][1], vo[1][2] - vo[0][2]};
+            const float e2[3] = {vo[2][0] - vo[0][0], vo[2][1] - vo[0][1], vo[2][2] - vo[0][2]};
+            float n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+            normalize3(n);
+            // normal = normalize(transpose(world_to_object) * n), mat4.ih:11-33
+            float r[3];
+            r[0] = w2o[0] * n[0] + w2o[1] * n[1] + w2o[2] * n[2];
+            r[1] = w2o[4] * n[0] + w2o[5] * n[1] + w2o[6] * n[2];
+            r[2] = w2o[8] * n[0] + w2o[9] * n[1] + w2o[10] * n[2];
+            normalize3(r);
+            ts.n[0] = r[0];
+            ts.n[1] = r[1];
+            ts.n[2] = r[2];
+            ts.material_id = seg.mat_id;
+            ts.flat_id = (uint32_t)f;
+            if (geom.uvs) {
+                ts.has_uv = 1;
                 for (int k = 0; k < 3; ++k) {
-                    if (idx[k] >= geom.num_vertices) {
-                        throw std::runtime_error("triangle index out of range");
-                    }
-                    const float *v = geom.vertices + 3 * (size_t)idx[k];
-                    vo[k][0] = v[0];
-                    vo[k][1] = v[1];
-                    vo[k][2] = v[2];
-                    float *w = &out.tri_verts[flat * 9 + 3 * k];
-                    w[0] = m[0] * v[0] + m[4] * v[1] + m[8] * v[2] + m[12];
-                    w[1] = m[1] * v[0] + m[5] * v[1] + m[9] * v[2] + m[13];
-                    w[2] = m[2] * v[0] + m[6] * v[1] + m[10] * v[2] + m[14];
+                    ts.uv[2 * k] = geom.uvs[2 * (size_t)idx[k]];
+                    ts.uv[2 * k + 1] = geom.uvs[2 * (size_t)idx[k] + 1];
                 }
-                TriShade &ts = out.tri_shade[flat];
-                // Ng = cross(v1 - v0, v2 - v0) in object space, normalised
-                const float e1[3] = {vo[1][0] - vo[0][0], vo[1][1] - vo[0][1], vo[1][2] - vo[0][2]};
-                const float e2[3] = {vo[2][0] - vo[0][0], vo[2][1] - vo[0][1], vo[2][2] - vo[0][2]};
-                float n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2],
-                              e1[0] * e2[1] - e1[1] * e2[0]};
-                normalize3(n);
-                // normal = normalize(transpose(world_to_object) * n), mat4.ih:11-33
-                float r[3];
-                r[0] = w2o[0] * n[0] + w2o[1] * n[1] + w2o[2] * n[2];
-                r[1] = w2o[4] * n[0] + w2o[5] * n[1] + w2o[6] * n[2];
-                r[2] = w2o[8] * n[0] + w2o[9] * n[1] + w2o[10] * n[2];
-                normalize3(r);
-                ts.n[0] = r[0];
-                ts.n[1] = r[1];
-                ts.n[2] = r[2];
-                ts.material_id = mat_id;
-                ts.flat_id = (uint32_t)flat;
-                if (geom.uvs) {
-                    ts.has_uv = 1;
-                    for (int k = 0; k < 3; ++k) {
-                        ts.uv[2 * k] = geom.uvs[2 * (size_t)idx[k]];
-                        ts.uv[2 * k + 1] = geom.uvs[2 * (size_t)idx[k] + 1];
-                    }
-                } else {
-                    ts.has_uv = 0;
-                    for (int k = 0; k < 6; ++k) {
-                        ts.uv[k] = 0.f;
-                    }
+            } else {
+                ts.has_uv = 0;
+                for (int k = 0; k < 6; ++k) {
+                    ts.uv[k] = 0.f;
                 }
             }
         }
+    });
+    if (bad_index) {
+        throw std::runtime_error("triangle index out of range");
     }
 
     // materials
@@ -251,12 +281,15 @@ void flatten_scene(const crt_scene_t *s, HostScene &out)
 }
 
 void pack_triangles(const HostScene &scene, const Bvh8 &bvh, std::vector<float> &tri_records,
-                    std::vector<TriShade> &shade_leaf_order)
+                    std::vector<TriShade> &shade_leaf_order, int threads)
 {
     const size_t n = bvh.tri_order.size();
     tri_records.resize(n * 12);
     shade_leaf_order.resize(n);
-    for (size_t i = 0; i < n; ++i) {
+    const size_t kBlockTris = 1u << 15;
+    parallel_blocks((uint32_t)((n + kBlockTris - 1) / kBlockTris), host_threads(threads), [&](uint32_t blk) {
+    const size_t end = std::min(n, (size_t)(blk + 1) * kBlockTris);
+    for (size_t i = (size_t)blk * kBlockTris; i < end; ++i) {
         const uint32_t src = bvh.tri_order[i];
         const float *v = &scene.tri_verts[(size_t)src * 9];
         float *r = &tri_records[i * 12];
@@ -275,6 +308,7 @@ void pack_triangles(const HostScene &scene, const Bvh8 &bvh, std::vector<float> 
         r[11] = 0.f;
         shade_leaf_order[i] = scene.tri_shade[src];
     }
+    });
 }
 
 }  // namespace crt

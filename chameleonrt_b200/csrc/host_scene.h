@@ -52,10 +52,11 @@ struct Bvh8;
 // {v0.xyz, bits(flat id)}, {e1.xyz, 0}, {e2.xyz, 0} with e1 = v1 - v0, e2 = v2 - v0
 // (the subtraction the intersector would otherwise do per test), and the shading records
 // permuted into the same order.
+// threads <= 0: hardware concurrency.
 void pack_triangles(const HostScene &scene, const Bvh8 &bvh, std::vector<float> &tri_records,
-                    std::vector<TriShade> &shade_leaf_order);
+                    std::vector<TriShade> &shade_leaf_order, int threads = 0);
 
 // Throws std::runtime_error on malformed input (bad material / texture / mesh ids).
-void flatten_scene(const crt_scene_t *scene, HostScene &out);
+void flatten_scene(const crt_scene_t *scene, HostScene &out, int threads = 0);
 
 }  // namespace crt

@@ -35,9 +35,9 @@ void *crt_hostcheck_create(const crt_scene_t *scene, int threads)
 {
     try {
         auto *h = new HostCheck();
-        crt::flatten_scene(scene, h->scene);
+        crt::flatten_scene(scene, h->scene, threads);
         crt::build_bvh8(h->scene.tri_verts.data(), h->scene.num_tris(), threads, h->bvh);
-        crt::pack_triangles(h->scene, h->bvh, h->tri_records, h->shade);
+        crt::pack_triangles(h->scene, h->bvh, h->tri_records, h->shade, threads);
         h->node_f4.resize(h->bvh.nodes.size() * 20);
         std::memcpy(h->node_f4.data(), h->bvh.nodes.data(), h->bvh.nodes.size() * 80);
         return h;
