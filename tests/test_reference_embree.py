@@ -166,3 +166,22 @@ def test_headless_embree_plugin_equals_oracle_plugin(built, tmp_path, name):
     a_cpu, v2, _ = run_headless("oracle", obj, cam, 100, 76, 2, 2, tmp_path)
     assert v1 == v2 and "Embree (w/ TBB & ISPC)" in out
     assert _same(a_ref, a_cpu)
+
+
+def test_headless_embree_plugin_on_gltf_instances(built, tmp_path):
+    """The reference's glTF loader + the reference's Embree backend (instanced scene: rtcSetGeometryTransform,
+    world_to_object normals) against the oracle plugin on the same .gltf: bit for bit."""
+    _ref_mod()
+    from test_reference_plugin import HEADLESS, run_headless
+
+    if not os.path.exists(HEADLESS):
+        pytest.skip("oracle/_ref/crt_headless not built")
+    from chameleonrt_b200.gltf_io import write_gltf
+    from chameleonrt_b200.scenes import san_miguel_like
+
+    scene, cam = san_miguel_like(spp=2, scale=0.02, tex_size=64)
+    gltf = write_gltf(scene, str(tmp_path / "scene.gltf"))
+    a_ref, v1, out = run_headless("embree", gltf, cam, 96, 54, 2, 2, tmp_path)
+    a_cpu, v2, _ = run_headless("oracle", gltf, cam, 96, 54, 2, 2, tmp_path)
+    assert v1 == v2 and "Embree (w/ TBB & ISPC)" in out
+    assert _same(a_ref, a_cpu)

@@ -66,3 +66,44 @@ def test_cuda_plugin_drop_in(built, tmp_path, name):
     a_cpu, v2, _ = run_headless("oracle", obj, cam, 160, 96, 2, 2, tmp_path)
     assert v1 == v2 and "CUDA wavefront" in out
     assert_parity(a_gpu, a_cpu)
+
+
+@needs_ref
+def test_gltf_through_reference_loader_matches_python_scene_model(built, tmp_path):
+    """The instanced, textured glTF-class scene written by gltf_io -> the reference's load_gltf (tinygltf,
+    flatten_gltf, generated light; util/scene.cpp:230-415) -> oracle plugin is bit-identical to the oracle fed the
+    in-memory Python Scene: pins scene.py / scenes.san_miguel_like / gltf_io against the reference's glTF import
+    (parameterized meshes, instance matrices, sRGB base colour + linear metallic-roughness texture handles)."""
+    from chameleonrt_b200.gltf_io import write_gltf
+    from chameleonrt_b200.scenes import san_miguel_like
+    from oracle import OracleBackend
+
+    scene, cam = san_miguel_like(spp=2, scale=0.02, tex_size=64)
+    gltf = write_gltf(scene, str(tmp_path / "scene.gltf"))
+    accum, v, out = run_headless("oracle", gltf, cam, 96, 54, 2, 2, tmp_path)
+    assert f"tris {scene.total_tris()}" in out and f"instances {len(scene.instances)}" in out
+    assert f"materials {len(scene.materials)}" in out and f"textures {len(scene.textures)}" in out
+    o = OracleBackend()
+    o.initialize(96, 54)
+    o.set_scene(scene)
+    for f in range(2):
+        o.render(v[0:3], v[3:6], v[6:9], v[9], f == 0)
+    assert (accum.view(np.uint32) == o.read_accum().view(np.uint32)).all()
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_cuda_plugin_drop_in_gltf_instances(built, tmp_path):
+    """`crt_headless cuda scene.gltf`: BASELINE config 3's scene class (glTF, instances with non-identity
+    transforms, textures) through the reference's loader into the CUDA plugin. The CUDA path flattens instances
+    to world space, the oracle intersects in object space like Embree: parity is statistical, as in
+    tests/test_gpu_parity.py::test_instanced_textured_gltf_class_scene."""
+    from chameleonrt_b200.gltf_io import write_gltf
+    from chameleonrt_b200.scenes import san_miguel_like
+
+    scene, cam = san_miguel_like(spp=2, scale=0.02, tex_size=64)
+    gltf = write_gltf(scene, str(tmp_path / "scene.gltf"))
+    a_gpu, v1, out = run_headless("cuda", gltf, cam, 192, 108, 2, 2, tmp_path)
+    a_cpu, v2, _ = run_headless("oracle", gltf, cam, 192, 108, 2, 2, tmp_path)
+    assert v1 == v2 and "CUDA wavefront" in out
+    assert_parity(a_gpu, a_cpu, min_frac=0.99, max_rel_l1=1e-2)
