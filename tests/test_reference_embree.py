@@ -185,3 +185,18 @@ def test_headless_embree_plugin_on_gltf_instances(built, tmp_path):
     a_cpu, v2, _ = run_headless("oracle", gltf, cam, 96, 54, 2, 2, tmp_path)
     assert v1 == v2 and "Embree (w/ TBB & ISPC)" in out
     assert _same(a_ref, a_cpu)
+
+
+def test_headless_embree_plugin_on_crts_all_lobes(built, tmp_path):
+    """Every BSDF lobe, textured scalar parameters and an explicit light, loaded by the reference's .crts
+    importer and rendered by the reference's Embree backend, against the oracle plugin: bit for bit."""
+    _ref_mod()
+    from test_reference_plugin import HEADLESS, _crts_case, run_headless
+
+    if not os.path.exists(HEADLESS):
+        pytest.skip("oracle/_ref/crt_headless not built")
+    scene, cam, crts = _crts_case(tmp_path)
+    a_ref, v1, out = run_headless("embree", crts, cam, 96, 72, 2, 2, tmp_path)
+    a_cpu, v2, _ = run_headless("oracle", crts, cam, 96, 72, 2, 2, tmp_path)
+    assert v1 == v2 and "Embree (w/ TBB & ISPC)" in out
+    assert _same(a_ref, a_cpu)

@@ -107,3 +107,47 @@ def test_cuda_plugin_drop_in_gltf_instances(built, tmp_path):
     a_cpu, v2, _ = run_headless("oracle", gltf, cam, 192, 108, 2, 2, tmp_path)
     assert v1 == v2 and "CUDA wavefront" in out
     assert_parity(a_gpu, a_cpu, min_frac=0.99, max_rel_l1=1e-2)
+
+
+def _crts_case(tmp_path):
+    """All BSDF lobes + textured scalar parameters + an explicit (axis-aligned) quad light, as a .crts file."""
+    from chameleonrt_b200.crts_io import write_crts
+    from chameleonrt_b200.scene import QuadLight
+    from helpers import synthetic_material_scene
+
+    scene, cam = synthetic_material_scene(spp=2)
+    scene.lights = [QuadLight(emission=(12.0, 11.0, 9.0, 1.0), position=(0.5, 4.5, 0.5, 1.0), normal=(0.0, -1.0, 0.0),
+                              v_x=(1.0, 0.0, 0.0), width=1.5, v_y=(0.0, 0.0, 1.0), height=1.0)]
+    return scene, cam, write_crts(scene, str(tmp_path / "materials.crts"))
+
+
+@needs_ref
+def test_crts_through_reference_loader_matches_python_scene_model(built, tmp_path):
+    """.crts is the one format whose importer reads every Disney parameter, per-parameter texture handles
+    (texture id + channel) and explicit quad lights (util/scene.cpp:417-620). File -> reference loader -> oracle
+    plugin is bit-identical to the oracle fed the in-memory Scene, and to crts_io.crts_scene_view()."""
+    from chameleonrt_b200.crts_io import crts_scene_view
+    from oracle import OracleBackend
+
+    scene, cam, crts = _crts_case(tmp_path)
+    accum, v, out = run_headless("oracle", crts, cam, 96, 72, 2, 2, tmp_path)
+    assert f"tris {scene.total_tris()}" in out and "lights 1" in out and f"textures {len(scene.textures)}" in out
+    for sc in (scene, crts_scene_view(scene)):
+        o = OracleBackend()
+        o.initialize(96, 72)
+        o.set_scene(sc)
+        for f in range(2):
+            o.render(v[0:3], v[3:6], v[6:9], v[9], f == 0)
+        assert (accum.view(np.uint32) == o.read_accum().view(np.uint32)).all()
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_cuda_plugin_drop_in_crts_all_lobes(built, tmp_path):
+    """`crt_headless cuda materials.crts`: transmission, anisotropy, clearcoat, sheen and textured metallic /
+    roughness through the reference's loader into the CUDA plugin."""
+    scene, cam, crts = _crts_case(tmp_path)
+    a_gpu, v1, out = run_headless("cuda", crts, cam, 192, 128, 2, 2, tmp_path, depth=6)
+    a_cpu, v2, _ = run_headless("oracle", crts, cam, 192, 128, 2, 2, tmp_path, depth=6)
+    assert v1 == v2 and "CUDA wavefront" in out
+    assert_parity(a_gpu, a_cpu, min_frac=0.99, max_rel_l1=1e-2)
