@@ -1004,6 +1004,17 @@ static std::atomic<uint64_t> g_box_tests(0), g_tri_tests(0);
 #define COUNT_BOX()
 #define COUNT_TRI()
 #endif
+// Reciprocal direction for the slab test. A zero component would give 0 * inf = NaN for a ray that lies
+// exactly in a box plane (it happens: one primary ray in ~7 M on the bench scene has dir.z == 0 and travels in
+// the plane of an edge) and the NaN would cull the box; clamping |d| to 1e-20 keeps every product finite
+// and the test conservative. The CUDA traversal clamps the same way (bvh8_traverse.h trav_init).
+inline float3 safe_inv_dir(const float3 d)
+{
+    const float eps = 1e-20f;
+    return make_float3(1.f / (std::fabs(d.x) > eps ? d.x : (d.x < 0.f ? -eps : eps)),
+                       1.f / (std::fabs(d.y) > eps ? d.y : (d.y < 0.f ? -eps : eps)),
+                       1.f / (std::fabs(d.z) > eps ? d.z : (d.z < 0.f ? -eps : eps)));
+}
 inline bool box_hit(const AABB &b, const float3 org, const float3 inv_dir, float tnear,
                     float tfar, float &tentry)
 {
@@ -1137,6 +1148,7 @@ struct Oracle {
     int max_depth = 5;
     int num_threads = 0;
     bool brute_force = false;
+    uint32_t win_x0 = 0, win_y0 = 0, win_x1 = 0xffffffffu, win_y1 = 0xffffffffu;  // debug pixel window
     // tile storage, render_embree.cpp:38-56
     static const int TILE = 64;
     std::vector<std::vector<float>> tiles;
@@ -1310,7 +1322,7 @@ struct Oracle {
         if (mesh.tris.empty()) {
             return false;
         }
-        const float3 inv_dir = make_float3(1.f / dir.x, 1.f / dir.y, 1.f / dir.z);
+        const float3 inv_dir = safe_inv_dir(dir);
         uint32_t stack[128];
         int sp = 0;
         stack[sp++] = 0;
@@ -1383,7 +1395,7 @@ struct Oracle {
             }
             return best;
         }
-        const float3 inv_dir = make_float3(1.f / dir.x, 1.f / dir.y, 1.f / dir.z);
+        const float3 inv_dir = safe_inv_dir(dir);
         uint32_t stack[128];
         int sp = 0;
         stack[sp++] = 0;
@@ -1528,6 +1540,9 @@ struct Oracle {
         for (uint32_t ray = 0; ray < tile_w * tile_h; ++ray) {
             const uint32_t i = ray % tile_w;
             const uint32_t j = ray / tile_w;
+            if (tile_x + i < win_x0 || tile_x + i >= win_x1 || tile_y + j < win_y0 || tile_y + j >= win_y1) {
+                continue;  // debugging aid: only the pixels of the window are rendered (oracle_set_pixel_window)
+            }
             uint32_t ray_count = 0;
             float3 illum = make_float3(0.f);
             for (uint32_t s = 0; s < spp; ++s) {
@@ -1740,6 +1755,17 @@ void oracle_set_options(void *o, int max_depth, int num_threads, int brute_force
     orc->max_depth = max_depth;
     orc->num_threads = num_threads;
     orc->brute_force = brute_force != 0;
+}
+// Debugging aid: restrict rendering to the pixels [x0, x1) x [y0, y1) of the framebuffer (all others keep
+// their previous value). Lets a single pixel of a full-size frame be re-rendered, e.g. with brute-force
+// intersection, to arbitrate between two traversals.
+void oracle_set_pixel_window(void *o, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1)
+{
+    Oracle *orc = static_cast<Oracle *>(o);
+    orc->win_x0 = x0;
+    orc->win_y0 = y0;
+    orc->win_x1 = x1;
+    orc->win_y1 = y1;
 }
 void oracle_initialize(void *o, int w, int h)
 {

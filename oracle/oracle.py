@@ -30,6 +30,7 @@ def load_oracle_lib(fast: bool = False) -> C.CDLL:
     lib.oracle_destroy.argtypes = [C.c_void_p]
     lib.oracle_set_options.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.oracle_initialize.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.oracle_set_pixel_window.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     lib.oracle_set_scene.argtypes = [C.c_void_p, C.POINTER(CScene)]
     lib.oracle_render.argtypes = [C.c_void_p, fp, fp, fp, C.c_float, C.c_int, C.POINTER(CRenderStats)]
     lib.oracle_read_img.argtypes = [C.c_void_p, C.c_void_p]
@@ -90,6 +91,10 @@ class OracleBackend:
         ms = scene.to_c()
         self.samples_per_pixel = scene.samples_per_pixel
         self.lib.oracle_set_scene(self.h, C.byref(ms.c))
+
+    def set_pixel_window(self, x0: int, y0: int, x1: int, y1: int) -> None:
+        """Debugging aid: render only the pixels [x0, x1) x [y0, y1) from now on."""
+        self.lib.oracle_set_pixel_window(self.h, x0, y0, x1, y1)
 
     def render(self, pos, dir, up, fovy, camera_changed, readback_framebuffer=True) -> RenderStats:
         _p, pp = _vec3(pos)

@@ -132,3 +132,35 @@ def test_big_scene_parallel_build_is_deterministic_and_exact(built):
     assert (ho.view(np.uint32) == hb.view(np.uint32)).all()
     ha, _, _ = hc.trace(rays, any_hit=True)
     assert ((ha[:, 3].view(np.uint32) != 0xFFFFFFFF) == o.trace_any(rays).astype(bool)).all()
+
+
+def test_axis_parallel_ray_in_a_box_plane(built):
+    """A ray with an exactly zero direction component that travels IN the plane of triangle edges (and so of
+    BVH box faces): (lo - o) * (1 / 0) = 0 * inf = NaN used to cull those boxes in the oracle's slab test, so
+    the oracle's BVH missed a triangle brute force hits (found on the bench scene: one primary ray in ~7 M has
+    dir.z == 0). Oracle BVH, oracle brute force and the product's traversal must agree bit for bit."""
+    from chameleonrt_b200.scene import DisneyMaterial, Instance, Mesh, ParameterizedMesh, Scene, default_obj_light
+    from chameleonrt_b200.scenes import MeshBuilder, grid
+
+    b = MeshBuilder()
+    b.add(*grid((4.0, -4.0, -4.0), (0.0, 8.0, 0.0), (0.0, 0.0, 8.0), 32, 32))   # wall x = 4, grid lines every 0.25
+    b.add(*grid((8.0, -4.0, -4.0), (0.0, 8.0, 0.0), (0.0, 0.0, 8.0), 16, 16))   # a second wall behind it
+    scene = Scene(meshes=[Mesh([b.geometry()])], parameterized_meshes=[ParameterizedMesh(0, [0])],
+                  instances=[Instance(np.eye(4, dtype=np.float32), 0)], materials=[DisneyMaterial()], textures=[],
+                  lights=[default_obj_light()], samples_per_pixel=1)
+    rays = []
+    for z in (0.25, -1.5, 0.0, 3.75):            # on grid lines of the first wall
+        for dy in (0.28, -0.28, 0.0):
+            rays.append([0.0, 0.1, z, 0.0, 0.96, dy, 0.0, 1e20])
+    for y in (0.5, -2.25):                        # zero y component, travelling in a horizontal grid line
+        rays.append([0.0, y, 0.3, 0.0, 0.96, 0.0, 0.28, 1e20])
+    rays = np.array(rays, np.float32)
+    bvh, brute = OracleBackend(), OracleBackend(brute_force=True)
+    for o in (bvh, brute):
+        o.initialize(8, 8)
+        o.set_scene(scene)
+    h_brute = brute.trace_closest(rays)
+    assert (h_brute[:, 3].view(np.uint32) != 0xFFFFFFFF).all() and (h_brute[:, 0] < 5.0).all()  # all hit the first wall
+    assert (bvh.trace_closest(rays).view(np.uint32) == h_brute.view(np.uint32)).all()
+    hb, _, _ = HostCheck(scene).trace(rays)
+    assert (hb.view(np.uint32) == h_brute.view(np.uint32)).all()
