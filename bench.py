@@ -349,13 +349,14 @@ def main():
     f += frames_in_flight
     if world > 1:
         gatherer.submit()
+        gatherer.finish()
     flush()
     barrier()
     gpu.sync()  # drop the warm-up batch's record
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         # frames are enqueued back to back (crtc_render_async): the host never waits inside the timed
-        # region, so the GPU queue stays full; N > 1: each frame's gather overlaps the next frame
+        # region, so the GPU queue stays full (the host is kept at most two batches ahead)
         e0.record(stream)
         done = 0
         batch_done = []  # the host stays at most 2 batches ahead of the GPU (bounded launch queues)
@@ -367,11 +368,15 @@ def main():
             f += nb
             done += nb
             if world > 1:
+                # One gather per batch of N frames, completed right away (stream-ordered, no host wait):
+                # ~15 MB over NVLink against >= 10 ms of rendering per batch, so overlapping it with the
+                # next batch would buy < 1 % and is not worth keeping collectives in flight across launches.
                 gatherer.submit()
+                gatherer.finish()
             ev = torch.cuda.Event()
             ev.record(stream)
             batch_done.append(ev)
-        flush()  # the last frame's gather + assembly belong to the timed region
+        flush()  # (no-op unless a gather is still pending)
         e1.record(stream)
         barrier()
     totals, stage_acc, csum, nframes = gpu.sync()
@@ -435,8 +440,8 @@ def main():
             "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "spp": SPP, "max_depth": MAX_DEPTH,
                        "parallelism": (f"image tiles 64x64 round-robin over {world} GPUs, scene replicated; {frames_in_flight} "
                                        "consecutive frames per wavefront (bit-identical to frame-by-frame), NCCL gather "
-                                       "of the accumulated tiles to rank 0 once per batch, overlapped with the next "
-                                       "batch; e2e: frame by frame, gather + readback every frame") if world > 1 else "single GPU",
+                                       "of the accumulated tiles to rank 0 once per batch (stream-ordered, not "
+                                       "overlapped); e2e: frame by frame, gather + readback every frame") if world > 1 else "single GPU",
                        "frames_in_flight": frames_in_flight,
                        "l2": f"inputs larger than L2: ~{WIDTH * HEIGHT * SPP * 250 / 1e9:.1f} GB of per-frame path state "
                              f"streams through every bounce (L2 126 MB); scene = {gpu.scene_info()['node_bytes'] / 1e6:.0f} MB "
