@@ -239,7 +239,7 @@ def main():
     # watchdog: a run that does not finish is killed with a traceback instead of hanging its caller
     import faulthandler
 
-    faulthandler.dump_traceback_later(int(os.environ.get("CRT_BENCH_WATCHDOG", "900")), repeat=False, file=sys.stderr,
+    faulthandler.dump_traceback_later(int(os.environ.get("CRT_BENCH_WATCHDOG", "600")), repeat=False, file=sys.stderr,
                                       exit=True)
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
