@@ -46,12 +46,12 @@ def exp(r, any_hit, mode):
     lib.crt_hostcheck_trace_exp(hc.h, r.ctypes.data, len(r), any_hit, mode, hits.ctypes.data, cnt.ctypes.data); return hits, cnt
 hb,_,cb = hc.trace(allr, counters=True)
 print("product closest: %.2f nodes %.2f tris" % (cb[:,0].mean(), cb[:,1].mean()))
-for mode in (1,0,2):
+for mode in (1,3,0,2):
     h, c_ = exp(allr, 0, mode)
     print("mode", mode, "closest: %.2f nodes %.2f tris maxstack %d  identical hits: %s" % (c_[:,0].mean(), c_[:,1].mean(), c_[:,2].max(), np.array_equal(h.view(np.uint32), hb.view(np.uint32))))
 ha,_,ca = hc.trace(sh, any_hit=True, counters=True)
 print("product any: %.2f nodes %.2f tris" % (ca[:,0].mean(), ca[:,1].mean()))
-for mode in (1,0,2):
+for mode in (1,3,0,2):
     h, c_ = exp(sh, 1, mode)
     occ = (h[:,3].view(np.uint32)!=0xFFFFFFFF); occp = (ha[:,3].view(np.uint32)!=0xFFFFFFFF)
     print("mode", mode, "any: %.2f nodes %.2f tris  same occlusion: %s" % (c_[:,0].mean(), c_[:,1].mean(), np.array_equal(occ, occp)))

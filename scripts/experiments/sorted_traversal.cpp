@@ -8,6 +8,7 @@
 //           entry distance exceeds the current hit; leaf slots beyond the current hit are skipped
 //   mode 0: children pushed far-to-near (true distance order), culled at pop
 //   mode 2: mode 0 with the leaf triangle groups deferred as distance-keyed entries too
+//   mode 3: mode 1 with the truly nearest hit child moved to the top of the stack (one min-selection, no sort)
 #include "../../chameleonrt_b200/csrc/hostcheck.cpp"
 
 // ---------------- experiment: distance-sorted traversal with per-child entry distances on the stack
@@ -169,6 +170,20 @@ extern "C" void crt_hostcheck_trace_exp(void *p, const float *rays, uint64_t n, 
                             int ts = slots[a]; slots[a] = slots[b]; slots[b] = ts;
                         }
                     }
+                }
+                if (mode == 3 && ni > 1) {
+                    // octant order, except that the truly nearest child is moved to the top of the stack
+                    int best_a = 0;
+                    for (int a = 1; a < ni; ++a) {
+                        if (inner[a].tmin < inner[best_a].tmin) {
+                            best_a = a;
+                        }
+                    }
+                    const Ent t = inner[best_a];
+                    for (int a = best_a; a + 1 < ni; ++a) {
+                        inner[a] = inner[a + 1];
+                    }
+                    inner[ni - 1] = t;
                 }
                 for (int a = 0; a < ni; ++a) {
                     stack[sp++] = inner[a];  // lowest key pushed first -> highest key popped first
