@@ -882,7 +882,7 @@ void build_bvh8(const float *verts, size_t num_tris, int threads, Bvh8 &out)
     // node's children and triangles start. Siblings are contiguous (child_base + rank among the inner
     // children in slot order), triangles of a node likewise; the order is plain BFS.
     std::vector<NodePlan> plans;
-    plans.reserve(num_tris / 2 + 16);
+    plans.reserve(num_tris / 6 + 16);  // ~1 node per 10 triangles in practice; grows if needed
     plans.emplace_back();
     plans[0].b2node = 0;
     uint32_t tri_total = 0;
