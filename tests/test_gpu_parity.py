@@ -312,6 +312,45 @@ def test_async_frames_match_blocking_frames(mods):
     assert (a.read_img() == d.read_img()).all()
 
 
+def test_sharded_ranks_with_frames_in_flight(mods):
+    """What bench.py does at N > 1: every rank renders its tiles of N consecutive frames as ONE wavefront
+    (render_async(num_frames=N)); the assembled result equals N frames rendered one by one on a single GPU, bit for
+    bit. Ranks are emulated on this GPU, as in test_full_size_properties."""
+    from chameleonrt_b200.scenes import cornell_box
+
+    RenderCUDA = mods[0]
+    scene, cam = cornell_box(spp=2)
+    c = camera_for(cam)
+    args = (c.eye(), c.dir(), c.up(), cam["fov_y"])
+    w, h = 200, 136  # 4 x 3 tiles, ragged on both axes
+    single = RenderCUDA(0)
+    single.initialize(w, h)
+    single.set_scene(scene)
+    rays = 0
+    for f in range(6):
+        rays += single.render(*args, f == 0, True).num_rays
+    for world in (2, 3):
+        ranks = []
+        got_rays = 0
+        for rank in range(world):
+            r = RenderCUDA(0, rank=rank, world_size=world)
+            r.initialize(w, h)
+            r.set_scene(scene)
+            r.render_async(*args, True, world)            # frames 0 .. world-1 in one wavefront
+            r.render_async(*args, False, 6 - world)       # the remaining frames in a second one
+            totals, _, _, n = r.sync()
+            assert n == 6
+            got_rays += totals.num_rays
+            ranks.append(r)
+        dst = ranks[0]
+        for src, r in enumerate(ranks):
+            acc, img, ntiles = r.local_buffers()
+            dst.assemble_rank(src, world, acc, img)
+        assert got_rays == rays
+        assert (dst.read_accum().view(np.uint32) == single.read_accum().view(np.uint32)).all()
+        assert (dst.read_img() == single.read_img()).all()
+
+
 def test_rungholt_like_frame(mods):
     """OBJ-class voxel city (untextured, no uvs, axis-aligned faces: the flat-box / tie cases)."""
     from chameleonrt_b200.scenes import rungholt_like
