@@ -417,14 +417,13 @@ def main():
     if rank == 0:
         value = rays / (elapsed_ms * 1e3)  # MRays/s
         peak, peak_src = hbm_peak()
-        n_launch = args.steps * MAX_DEPTH
         # dominant kernel: k_traverse (persistent BVH8 traversal; every launch but the first carries
         # the shadow rays of bounce b and the continuation rays of bounce b+1)
         closest_bytes = counts[1] * S_NODE + counts[2] * S_TRI + counts[0] * (S_RAY + S_HIT)
         any_bytes = counts[4] * S_NODE + counts[5] * S_TRI + counts[3] * (S_RAY + 1)
         trav_bytes = closest_bytes + any_bytes
         t_trav_ms = stage_acc["traverse_primary"] + stage_acc["traverse"]  # max over ranks of per-rank sums
-        n_launch = args.steps * (MAX_DEPTH + 1)
+        n_launch = n_batches * (MAX_DEPTH + 1)  # k_traverse launches per rank in the timed region
         achieved = trav_bytes / world / (t_trav_ms * 1e-3) / 1e9  # per GPU GB/s
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic_k_traverse.json")
