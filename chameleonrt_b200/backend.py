@@ -89,7 +89,8 @@ class RenderCUDA:
     """``RenderBackend`` implemented by the B200 wavefront path tracer."""
 
     def __init__(self, device: int = 0, max_depth: int = 5, rank: int = 0, world_size: int = 1,
-                 count_traversal: bool = False, bvh_threads: int = 0, stream: Optional[int] = None):
+                 count_traversal: bool = False, bvh_threads: int = 0, stream: Optional[int] = None,
+                 any_far_first: Optional[bool] = None):
         self.lib = load_lib()
         self.h = C.c_void_p()
         self._check(self.lib.crtc_create(C.byref(self.h), device))
@@ -100,9 +101,11 @@ class RenderCUDA:
                          ("count_traversal", int(count_traversal)), ("bvh_threads", bvh_threads)):
             self._check(self.lib.crtc_set_option(self.h, key.encode(), val))
         # developer knobs of the traversal kernels (defaults are the tuned values)
-        for env, key in (("CRT_CUDA_REFILL_IDLE", "refill_idle"),):
+        for env, key in (("CRT_CUDA_REFILL_IDLE", "refill_idle"), ("CRT_CUDA_ANY_FAR_FIRST", "any_far_first")):
             if os.environ.get(env):
                 self._check(self.lib.crtc_set_option(self.h, key.encode(), int(os.environ[env])))
+        if any_far_first is not None:  # traversal order of shadow rays; never changes a result (crt_cuda.h)
+            self._check(self.lib.crtc_set_option(self.h, b"any_far_first", int(any_far_first)))
         if stream is not None:
             self._check(self.lib.crtc_set_stream(self.h, C.c_void_p(stream)))
         self.width = self.height = 0

@@ -189,6 +189,15 @@ CRT_HD void trav_init(TravState &s, const Ray &ray, uint32_t one = 0x3F800000u)
     s.cur.y = 0x80000000u;  // root: "inner child in slot 7 of a virtual parent"
 }
 
+// Visit the children of every node in the REVERSE of the ray's octant order (farthest first). For an
+// any-hit query the answer does not depend on the order, only the work does: on the bench scene 92 % of the
+// light-sample shadow rays are occluded, mostly by geometry near the light's end of the segment, and far-first
+// finds an occluder after 14 % fewer node steps and 27 % fewer triangle tests (scripts/bvh_quality.py).
+CRT_HD void trav_reverse_order(TravState &s)
+{
+    s.oct_inv4 ^= 0x07070707u;
+}
+
 // byte j of `packed` as the float 1 + b * 2^-15, built by ONE byte-permute (no int->float
 // conversion: I2F executes on the quarter-rate XU pipe, which the first profile showed at 52 %
 // utilisation with 48 conversions per node). `one` must hold 0x3F800000 in a REGISTER the compiler
@@ -362,10 +371,13 @@ CRT_HD bool trav_step(const float4 *__restrict__ nodes, const float4 *__restrict
 // Whole-ray convenience wrapper (host check, simple device paths).
 template <bool ANY_HIT, bool COUNT>
 CRT_HD bool bvh8_trace(const float4 *__restrict__ nodes, const float4 *__restrict__ tris, const Ray &ray,
-                       HitRecord &hit, TraversalCounters *counters)
+                       HitRecord &hit, TraversalCounters *counters, bool far_first = false)
 {
     TravState s;
     trav_init(s, ray);
+    if (far_first) {
+        trav_reverse_order(s);
+    }
     ArrayStack stack;
     while (!trav_step<ANY_HIT, COUNT>(nodes, tris, s, stack, counters)) {
     }

@@ -119,6 +119,7 @@ struct crtc_renderer {
     int bvh_threads = 0;
     bool count_traversal = false;
     int refill_idle = crt::kRefillIdle;  // idle lanes that trigger a refill of the traversal warps
+    bool any_far_first = false;          // shadow rays visit the children of a node farthest-first
 
     // framebuffer layout
     int fb_w = 0, fb_h = 0;
@@ -177,12 +178,13 @@ struct crtc_renderer {
             CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crt::k_traverse<false>, crt::kTravBlock, 0));
             trav_grid = (unsigned)(sms * std::max(1, per_sm));
         }
+        const int sched = (refill_idle & 0xff) | (any_far_first ? 0x100 : 0);
         if (count_traversal) {
             crt::k_traverse<true><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any,
-                                                                             work_counter, refill_idle);
+                                                                             work_counter, sched);
         } else {
             crt::k_traverse<false><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any,
-                                                                              work_counter, refill_idle);
+                                                                              work_counter, sched);
         }
     }
 
@@ -827,6 +829,8 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
             r->count_traversal = value != 0;
         } else if (k == "refill_idle") {
             r->refill_idle = (int)std::min<int64_t>(std::max<int64_t>(value, 1), 32);
+        } else if (k == "any_far_first") {
+            r->any_far_first = value != 0;
         } else {
             throw std::runtime_error("unknown option '" + k + "'");
         }

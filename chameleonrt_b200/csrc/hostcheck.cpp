@@ -94,7 +94,8 @@ void crt_hostcheck_trace(void *p, const float *rays, uint64_t n, int any_hit, fl
         crt::HitRecord hit;
         crt::TraversalCounters cnt;
         if (any_hit) {
-            crt::bvh8_trace<true, true>(nodes, tris, r, hit, &cnt);
+            // any_hit == 2: children in reverse octant order (what the kernels do for shadow rays)
+            crt::bvh8_trace<true, true>(nodes, tris, r, hit, &cnt, any_hit == 2);
         } else {
             crt::bvh8_trace<false, true>(nodes, tris, r, hit, &cnt);
         }

@@ -194,8 +194,11 @@ struct HybridStack {
 template <bool COUNT>
 __global__ void __launch_bounds__(kTravBlock, 8)
     k_traverse(DeviceScene sc, PathState ps, const uint32_t *queue, const uint32_t *count_closest_ptr,
-               const uint32_t *count_any_ptr, uint32_t *work_counter, int refill_idle)
+               const uint32_t *count_any_ptr, uint32_t *work_counter, int sched)
 {
+    // sched: bits 0-7 = idle lanes that trigger a refill; bit 8 = shadow rays visit children far-first
+    const int refill_idle = sched & 0xff;
+    const bool any_far_first = (sched & 0x100) != 0;
     __shared__ uint2 sm_stack[kSmemStack * kTravBlock];
     // warp-cooperative triangle testing: per warp, every lane's ray and best hit live in
     // shared memory so that ANY lane can test a (ray, triangle) pair for its owner
@@ -256,6 +259,9 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                     ray = Ray{o.x, o.y, o.z, o.w, d.x, d.y, d.z, d.w};
                 }
                 trav_init(st, ray, sc.float_one);
+                if (is_any && any_far_first) {
+                    trav_reverse_order(st);  // same answer, different order (bvh8_traverse.h)
+                }
                 stack.sp = 0;
                 tri = make_uint2(0u, 0u);
                 alive = true;

@@ -60,6 +60,10 @@ void crtc_destroy(crtc_renderer *r);
  *   "bvh_threads" host threads for the BVH8 build (0 = all)
  *   "refill_idle" scheduling knob of the persistent traversal kernels (how many idle lanes
  *                 trigger a refill from the ray queue); the default is tuned
+ *   "any_far_first" 1 = shadow (any-hit) rays visit the children of a BVH node farthest-first instead of
+ *                 nearest-first. The result of an occlusion query does not depend on the order; the work does
+ *                 (fewer node steps when occluders sit near the light's end of the segment, more when they sit
+ *                 near the surface). Off by default.
  *   "count_traversal" 1 = instrumented traversal kernels that count node visits and triangle
  *                 tests (for the algorithmic-byte figure; slower, off by default)
  */

@@ -60,7 +60,14 @@ def main():
     if args.lib:
         real_cdll = C.CDLL
         helpers.C.CDLL = lambda path, *a, **k: real_cdll(args.lib if "hostcheck" in path else path, *a, **k)
-    scene, cam = getattr(scenes, args.scene)(spp=1)
+    if args.scene == "materials":
+        scene, cam = helpers.synthetic_material_scene()
+    elif args.scene == "san_miguel_like":
+        scene, cam = scenes.san_miguel_like(spp=1, scale=0.1, tex_size=64)
+    elif args.scene == "cornell":
+        scene, cam = scenes.cornell_box(spp=1)
+    else:
+        scene, cam = getattr(scenes, args.scene)(spp=1)
     c = helpers.camera_for(cam)
     hc = helpers.HostCheck(scene)
     st = hc.stats()
@@ -85,8 +92,12 @@ def main():
         print(f"  closest {name:8s} {len(r):7d} rays: {cnt[:, 0].mean():6.2f} nodes  {cnt[:, 1].mean():6.2f} tris")
         tot_n += cnt[:, 0].sum(); tot_t += cnt[:, 1].sum(); tot_r += len(r)
     print(f"  closest all      {tot_r:7d} rays: {tot_n / tot_r:6.2f} nodes  {tot_t / tot_r:6.2f} tris")
-    _, _, cnt = hc.trace(sh, any_hit=True, counters=True)
-    print(f"  any-hit shadow   {len(sh):7d} rays: {cnt[:, 0].mean():6.2f} nodes  {cnt[:, 1].mean():6.2f} tris")
+    h_near, _, cnt = hc.trace(sh, any_hit=True, counters=True)
+    print(f"  any-hit shadow   {len(sh):7d} rays: {cnt[:, 0].mean():6.2f} nodes  {cnt[:, 1].mean():6.2f} tris  (near-first)")
+    h_far, _, cnt = hc.trace(sh, any_hit=True, counters=True, far_first=True)
+    occ_near, occ_far = (h[:, 3].view(np.uint32) != 0xFFFFFFFF for h in (h_near, h_far))
+    print(f"  any-hit shadow   {len(sh):7d} rays: {cnt[:, 0].mean():6.2f} nodes  {cnt[:, 1].mean():6.2f} tris  (far-first; "
+          f"{100 * occ_far.mean():.1f} % occluded, same answers: {np.array_equal(occ_near, occ_far)})")
 
 
 if __name__ == "__main__":

@@ -28,7 +28,9 @@ from chameleonrt_b200 import scenes
 from oracle import OracleBackend
 from oracle.oracle import primary_rays
 from bvh_quality import cosine_bounce, shadow_rays
-scene, cam = scenes.sponza_like(spp=1)
+import os
+_sc = os.environ.get("EXP_SCENE", "sponza_like")
+scene, cam = scenes.san_miguel_like(spp=1, scale=0.1, tex_size=64) if _sc == "san_miguel_like" else getattr(scenes, _sc)(spp=1)
 c = helpers.camera_for(cam)
 hc = helpers.HostCheck(scene)
 lib = hc.lib
@@ -49,6 +51,8 @@ print("product closest: %.2f nodes %.2f tris" % (cb[:,0].mean(), cb[:,1].mean())
 for mode in (1,3,0,2):
     h, c_ = exp(allr, 0, mode)
     print("mode", mode, "closest: %.2f nodes %.2f tris maxstack %d  identical hits: %s" % (c_[:,0].mean(), c_[:,1].mean(), c_[:,2].max(), np.array_equal(h.view(np.uint32), hb.view(np.uint32))))
+h4, c4 = exp(allr, 0, 4)
+print("sorted traversal: %.2f of %.2f node visits per ray find no child at all (box of the node hit, all 8 children missed)" % (c4[:,2].mean(), c4[:,0].mean()))
 ha,_,ca = hc.trace(sh, any_hit=True, counters=True)
 print("product any: %.2f nodes %.2f tris" % (ca[:,0].mean(), ca[:,1].mean()))
 for mode in (1,3,0,2):
@@ -78,3 +82,10 @@ used = front & lfacing
 print("light-sample shadow rays: %d; surface faces light %.3f; light faces surface %.3f; visibility used %.3f" % (len(sh), front.mean(), lfacing.mean(), used.mean()))
 ha,_,ca = hc.trace(sh, any_hit=True, counters=True)
 print("node visits in unused rays: %.3f of all any-hit node visits" % (ca[~used,0].sum()/ca[:,0].sum()))
+occ = ha[:, 3].view(np.uint32) != 0xFFFFFFFF
+print("any-hit: %.1f %% of shadow rays occluded; nodes per occluded ray %.2f, per unoccluded ray %.2f; share of any-hit node visits spent on occluded rays %.2f"
+      % (100 * occ.mean(), ca[occ, 0].mean(), ca[~occ, 0].mean(), ca[occ, 0].sum() / ca[:, 0].sum()))
+for mode, name in ((10, "farthest child first"), (11, "largest child first"), (12, "longest segment first"), (13, "segment x area first")):
+    h, c_ = exp(sh, 1, mode)
+    o2 = (h[:, 3].view(np.uint32) != 0xFFFFFFFF)
+    print("any-hit order: %-24s %.2f nodes %.2f tris  same occlusion: %s" % (name, c_[:, 0].mean(), c_[:, 1].mean(), np.array_equal(o2, occ)))

@@ -15,7 +15,8 @@
 namespace {
 struct Ent { uint32_t node; float tmin; };
 inline void child_boxes(const float4 *nodes, const crt::TravState &s, uint32_t node_index, float *tmin8, bool *hit8,
-                        uint32_t &imask, uint32_t &child_base, uint32_t &tri_base, uint8_t *meta8)
+                        uint32_t &imask, uint32_t &child_base, uint32_t &tri_base, uint8_t *meta8, float *area8 = nullptr,
+                        float *tmax8 = nullptr)
 {
     using namespace crt;
     const Ray &ray = s.ray;
@@ -54,6 +55,17 @@ inline void child_boxes(const float4 *nodes, const crt::TravState &s, uint32_t n
             const float tmax = fminf_(fminf_(tmaxx, tmaxy), fminf_(tmaxz, s.tfar));
             tmin8[slot] = tmin;
             hit8[slot] = meta8[slot] != 0 && tmin <= tmax;
+            if (tmax8) {
+                tmax8[slot] = tmax;
+            }
+            if (area8) {
+                const float ex = u2f((e_imask & 0xffu) << 23), ey = u2f(((e_imask >> 8) & 0xffu) << 23),
+                            ez = u2f(((e_imask >> 16) & 0xffu) << 23);
+                const float dx = ex * (float)(((qhix >> (8 * j)) & 0xff) - ((qlox >> (8 * j)) & 0xff));
+                const float dy = ey * (float)(((qhiy >> (8 * j)) & 0xff) - ((qloy >> (8 * j)) & 0xff));
+                const float dz = ez * (float)(((qhiz >> (8 * j)) & 0xff) - ((qloz >> (8 * j)) & 0xff));
+                area8[slot] = dx * dy + dy * dz + dz * dx;
+            }
         }
     }
 }
@@ -75,11 +87,11 @@ extern "C" void crt_hostcheck_trace_exp(void *p, const float *rays, uint64_t n, 
         Ent stack[256];
         int sp = 0;
         stack[sp++] = Ent{0, r.tnear};
-        uint32_t nvis = 0, ntri = 0, maxsp = 0;
+        uint32_t nvis = 0, ntri = 0, maxsp = 0, nempty = 0;
         bool done = false;
         while (sp && !done) {
             const Ent e = stack[--sp];
-            if (e.tmin > s.tfar) {
+            if (mode < 10 && e.tmin > s.tfar) {
                 continue;
             }
             if (e.node & 0x80000000u) {
@@ -97,11 +109,31 @@ extern "C" void crt_hostcheck_trace_exp(void *p, const float *rays, uint64_t n, 
                 continue;
             }
             ++nvis;
-            float tmin8[8];
+            float tmin8[8], area8[8], tmax8[8];
             bool hit8[8];
             uint8_t meta8[8];
             uint32_t imask, child_base, tri_base;
-            child_boxes(nodes, s, e.node, tmin8, hit8, imask, child_base, tri_base, meta8);
+            child_boxes(nodes, s, e.node, tmin8, hit8, imask, child_base, tri_base, meta8, area8, tmax8);
+            if (mode >= 10) {
+                // any-hit ordering experiments: the stack key is a priority, not a distance (nothing is culled:
+                // an any-hit ray's interval never shrinks). Highest key is visited first.
+                for (int slot = 0; slot < 8; ++slot) {
+                    if (hit8[slot] && (imask & (1u << slot))) {
+                        const float key = mode == 10 ? tmin8[slot]                          // farthest entry first
+                                          : mode == 11 ? area8[slot]                          // largest child first
+                                          : mode == 12 ? (tmax8[slot] - tmin8[slot])          // longest ray segment inside first
+                                                       : (tmax8[slot] - tmin8[slot]) * area8[slot];
+                        tmin8[slot] = -key;  // reuse the sort below: entries sorted far-to-near by "tmin"
+                    }
+                }
+            }
+            {
+                bool any_child = false;
+                for (int slot = 0; slot < 8; ++slot) {
+                    any_child = any_child || hit8[slot];
+                }
+                nempty += any_child ? 0u : 1u;
+            }
             // leaves first (as the product does: triangles of a node are tested when the node is visited)
             Ent inner[16];
             int ni = 0;
@@ -119,7 +151,7 @@ extern "C" void crt_hostcheck_trace_exp(void *p, const float *rays, uint64_t n, 
                         inner[ni++] = Ent{0x80000000u | (k << 29) | (tri_base + off), tmin8[slot]};
                         continue;
                     }
-                    if (tmin8[slot] > s.tfar) {
+                    if (mode < 10 && tmin8[slot] > s.tfar) {
                         continue;
                     }
                     uint2 tg;
@@ -137,7 +169,7 @@ extern "C" void crt_hostcheck_trace_exp(void *p, const float *rays, uint64_t n, 
                     }
                 }
             }
-            if (mode == 0 || mode == 2) {
+            if (mode == 0 || mode == 2 || mode == 4 || mode >= 10) {
                 // far first onto the stack
                 for (int a = 0; a < ni; ++a) {
                     for (int b = a + 1; b < ni; ++b) {
@@ -200,6 +232,6 @@ extern "C" void crt_hostcheck_trace_exp(void *p, const float *rays, uint64_t n, 
         std::memcpy(&o[3], &s.hit.flat, 4);
         counters[3 * i] = nvis;
         counters[3 * i + 1] = ntri;
-        counters[3 * i + 2] = maxsp;
+        counters[3 * i + 2] = mode == 4 ? nempty : maxsp;
     }
 }

@@ -75,13 +75,13 @@ class HostCheck:
     def digest(self) -> int:
         return int(self.lib.crt_hostcheck_digest(self.h))
 
-    def trace(self, rays, any_hit=False, normals=False, counters=False):
+    def trace(self, rays, any_hit=False, normals=False, counters=False, far_first=False):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         n = len(rays)
         hits = np.zeros((n, 4), np.float32)
         nrm = np.zeros((n, 3), np.float32) if normals else None
         cnt = np.zeros((n, 2), np.uint32) if counters else None
-        self.lib.crt_hostcheck_trace(self.h, rays.ctypes.data, n, 1 if any_hit else 0, hits.ctypes.data,
+        self.lib.crt_hostcheck_trace(self.h, rays.ctypes.data, n, (2 if far_first else 1) if any_hit else 0, hits.ctypes.data,
                                      nrm.ctypes.data if normals else None, cnt.ctypes.data if counters else None)
         return hits, nrm, cnt
 

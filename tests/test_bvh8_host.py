@@ -34,6 +34,9 @@ def test_bvh8_bit_exact_vs_oracle(built, name):
     assert (no.view(np.uint32) == nb.view(np.uint32)).all(), "precomputed world normals differ from the oracle"
     ha, _, _ = hc.trace(rays, any_hit=True)
     assert ((ha[:, 3].view(np.uint32) != 0xFFFFFFFF) == o.trace_any(rays).astype(bool)).all()
+    # children visited farthest-first (option any_far_first): an occlusion query has the same answer
+    hf, _, _ = hc.trace(rays, any_hit=True, far_first=True)
+    assert ((hf[:, 3].view(np.uint32) != 0xFFFFFFFF) == o.trace_any(rays).astype(bool)).all()
     assert cnt[:, 0].mean() < 64 and cnt[:, 1].mean() < 32  # a working hierarchy, not a linear scan
 
 
