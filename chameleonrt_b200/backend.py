@@ -90,7 +90,7 @@ class RenderCUDA:
 
     def __init__(self, device: int = 0, max_depth: int = 5, rank: int = 0, world_size: int = 1,
                  count_traversal: bool = False, bvh_threads: int = 0, stream: Optional[int] = None,
-                 any_far_first: Optional[bool] = None):
+                 any_far_first: Optional[int] = None):
         self.lib = load_lib()
         self.h = C.c_void_p()
         self._check(self.lib.crtc_create(C.byref(self.h), device))
@@ -104,7 +104,7 @@ class RenderCUDA:
         for env, key in (("CRT_CUDA_REFILL_IDLE", "refill_idle"), ("CRT_CUDA_ANY_FAR_FIRST", "any_far_first")):
             if os.environ.get(env):
                 self._check(self.lib.crtc_set_option(self.h, key.encode(), int(os.environ[env])))
-        if any_far_first is not None:  # traversal order of shadow rays; never changes a result (crt_cuda.h)
+        if any_far_first is not None:  # 0 / 1 / 2 = auto: traversal order of shadow rays; never changes a result (crt_cuda.h)
             self._check(self.lib.crtc_set_option(self.h, b"any_far_first", int(any_far_first)))
         if stream is not None:
             self._check(self.lib.crtc_set_stream(self.h, C.c_void_p(stream)))

@@ -119,7 +119,37 @@ struct crtc_renderer {
     int bvh_threads = 0;
     bool count_traversal = false;
     int refill_idle = crt::kRefillIdle;  // idle lanes that trigger a refill of the traversal warps
-    bool any_far_first = false;          // shadow rays visit the children of a node farthest-first
+    // Shadow rays visit the children of a node farthest-first: 0 = no (default), 1 = yes, 2 = auto — frame 1
+    // after set_scene is rendered near-first, frame 2 far-first, and from frame 3 on the order whose traversal
+    // stage was faster is kept (blocking render() calls only; the image is the same either way).
+    int any_far_first = 0;
+    int auto_frames = 0;            // blocking frames rendered since set_scene (auto mode)
+    float auto_trav_ms[2] = {0.f, 0.f};
+    bool auto_decided = false, auto_choice = false;
+    bool frame_far_first = false;   // the order used by the frame being enqueued
+
+    bool pick_far_first() const
+    {
+        if (any_far_first != 2) {
+            return any_far_first == 1;
+        }
+        return auto_decided ? auto_choice : auto_frames == 2;
+    }
+    // after a blocking frame's stage times are known
+    void auto_tune_step()
+    {
+        if (any_far_first != 2 || auto_decided) {
+            return;
+        }
+        if (auto_frames == 1 || auto_frames == 2) {
+            auto_trav_ms[auto_frames - 1] = stage_ms[kStTraverse];
+        }
+        if (auto_frames == 2) {
+            auto_decided = true;
+            auto_choice = auto_trav_ms[1] < 0.97f * auto_trav_ms[0];  // switch only for a clear gain
+        }
+        ++auto_frames;
+    }
 
     // framebuffer layout
     int fb_w = 0, fb_h = 0;
@@ -178,7 +208,7 @@ struct crtc_renderer {
             CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crt::k_traverse<false>, crt::kTravBlock, 0));
             trav_grid = (unsigned)(sms * std::max(1, per_sm));
         }
-        const int sched = (refill_idle & 0xff) | (any_far_first ? 0x100 : 0);
+        const int sched = (refill_idle & 0xff) | (frame_far_first ? 0x100 : 0);
         if (count_traversal) {
             crt::k_traverse<true><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any,
                                                                              work_counter, sched);
@@ -298,6 +328,8 @@ struct crtc_renderer {
     {
         make_current();
         frame_id = 0;
+        auto_frames = 0;
+        auto_decided = false;
         crt::HostScene hs;
         crt::flatten_scene(scene, hs, bvh_threads);
         crt::Bvh8 bvh;
@@ -410,6 +442,7 @@ struct crtc_renderer {
             throw std::runtime_error("render: more than 2^31 paths in flight on one device");
         }
         ensure_path_buffers(npaths);
+        frame_far_first = pick_far_first();
         const crt::DeviceScene sc = device_scene();
         crt::FrameLayout fl = frame_layout();
         fl.frames = num_frames;
@@ -527,6 +560,7 @@ struct crtc_renderer {
         CUDA_CHECK(cudaStreamSynchronize(stream));
         CUDA_CHECK(cudaGetLastError());
         collect(nullptr, nullptr);
+        auto_tune_step();
         if (stats) {
             const uint64_t rays = counters_out[0] + counters_out[1];
             stats->render_time = stage_ms[kStFrame];
@@ -830,7 +864,10 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
         } else if (k == "refill_idle") {
             r->refill_idle = (int)std::min<int64_t>(std::max<int64_t>(value, 1), 32);
         } else if (k == "any_far_first") {
-            r->any_far_first = value != 0;
+            if (value < 0 || value > 2) {
+                throw std::runtime_error("any_far_first must be 0 (off), 1 (on) or 2 (auto)");
+            }
+            r->any_far_first = (int)value;
         } else {
             throw std::runtime_error("unknown option '" + k + "'");
         }

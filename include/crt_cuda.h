@@ -63,7 +63,8 @@ void crtc_destroy(crtc_renderer *r);
  *   "any_far_first" 1 = shadow (any-hit) rays visit the children of a BVH node farthest-first instead of
  *                 nearest-first. The result of an occlusion query does not depend on the order; the work does
  *                 (fewer node steps when occluders sit near the light's end of the segment, more when they sit
- *                 near the surface). Off by default.
+ *                 near the surface). 2 = decide per scene: of the second and third crtc_render frame after
+ *                 crtc_set_scene one runs each order, the faster traversal stage wins. 0 (default) = off.
  *   "count_traversal" 1 = instrumented traversal kernels that count node visits and triangle
  *                 tests (for the algorithmic-byte figure; slower, off by default)
  */
