@@ -193,13 +193,29 @@ inline float luminance(const float3 &c)
 {
     return 0.2126f * c.x + 0.7152f * c.y + 0.0722f * c.z;
 }
+// ISPC's min / max on floats lower to minps / maxps: "a < b ? a : b" and "a > b ? a : b", i.e. the SECOND
+// operand comes back when either one is NaN (std::min / std::max return the FIRST). Only NaN-carrying paths can
+// tell (the reference's transmission lobe produces some, util/scene.cpp:196), but their ray counts then follow
+// the reference's; clamp(v, lo, hi) is min(max(v, lo), hi) in the ISPC standard library.
+inline float ispc_max(float a, float b)
+{
+    return a > b ? a : b;
+}
+inline float ispc_min(float a, float b)
+{
+    return a < b ? a : b;
+}
+inline float clampf_ispc(float x, float lo, float hi)
+{
+    return ispc_min(ispc_max(x, lo), hi);
+}
 inline float clampf(float x, float lo, float hi)
 {
     return x < lo ? lo : (x > hi ? hi : x);
 }
 inline float saturate(float x)
 {
-    return clampf(x, 0.f, 1.f);
+    return clampf_ispc(x, 0.f, 1.f);
 }
 inline float lerp(float x, float y, float s)
 {
@@ -459,7 +475,7 @@ inline float3 cos_sample_hemisphere(float2 u)
         }
     }
     d = radius * make_float2(std::cos(theta), std::sin(theta));
-    return make_float3(d.x, d.y, std::sqrt(std::max(0.f, 1.f - d.x * d.x - d.y * d.y)));
+    return make_float3(d.x, d.y, std::sqrt(ispc_max(0.f, 1.f - d.x * d.x - d.y * d.y)));
 }
 inline float3 spherical_dir(float sin_theta, float cos_theta, float phi)
 {
@@ -628,7 +644,7 @@ inline float3 disney_microfacet_isotropic(const DisneyMaterial &mat, const float
     float3 tint = lum > 0.f ? mat.base_color / lum : make_float3(1.f);
     float3 spec = lerp(mat.specular * 0.08f * lerp(make_float3(1.f), tint, mat.specular_tint),
                        mat.base_color, mat.metallic);
-    float alpha = std::max(0.001f, mat.roughness * mat.roughness);
+    float alpha = ispc_max(0.001f, mat.roughness * mat.roughness);
     float d = gtr_2(dot(n, w_h), alpha);
     float3 f = lerp(spec, make_float3(1.f), schlick_weight(dot(w_i, w_h)));
     float g = smith_shadowing_ggx(dot(n, w_i), alpha) * smith_shadowing_ggx(dot(n, w_o), alpha);
@@ -646,7 +662,7 @@ inline float3 disney_microfacet_transmission_isotropic(const DisneyMaterial &mat
     float eta_o = entering ? 1.f : mat.ior;
     float eta_i = entering ? mat.ior : 1.f;
     float3 w_h = normalize(w_o + w_i * eta_i / eta_o);
-    float alpha = std::max(0.001f, mat.roughness * mat.roughness);
+    float alpha = ispc_max(0.001f, mat.roughness * mat.roughness);
     float d = gtr_2(std::fabs(dot(n, w_h)), alpha);
     float f = fresnel_dielectric(std::fabs(dot(w_i, n)), eta_o, eta_i);
     float g = smith_shadowing_ggx(std::fabs(dot(n, w_i)), alpha) *
@@ -668,7 +684,7 @@ inline float3 disney_microfacet_anisotropic(const DisneyMaterial &mat, const flo
                        mat.base_color, mat.metallic);
     float aspect = std::sqrt(1.f - mat.anisotropy * 0.9f);
     float a = mat.roughness * mat.roughness;
-    float2 alpha = make_float2(std::max(0.001f, a / aspect), std::max(0.001f, a * aspect));
+    float2 alpha = make_float2(ispc_max(0.001f, a / aspect), ispc_max(0.001f, a * aspect));
     float d = gtr_2_aniso(dot(n, w_h), std::fabs(dot(w_h, v_x)), std::fabs(dot(w_h, v_y)), alpha);
     float3 f = lerp(spec, make_float3(1.f), schlick_weight(dot(w_i, w_h)));
     float g = smith_shadowing_ggx_aniso(dot(n, w_i), std::fabs(dot(w_i, v_x)),
@@ -723,10 +739,10 @@ float3 disney_brdf(const DisneyMaterial &mat, const float3 &n, const float3 &w_o
 float disney_pdf(const DisneyMaterial &mat, const float3 &n, const float3 &w_o,
                  const float3 &w_i, const float3 &v_x, const float3 &v_y)
 {
-    float alpha = std::max(0.001f, mat.roughness * mat.roughness);
+    float alpha = ispc_max(0.001f, mat.roughness * mat.roughness);
     float aspect = std::sqrt(1.f - mat.anisotropy * 0.9f);
     float2 alpha_aniso =
-        make_float2(std::max(0.001f, alpha / aspect), std::max(0.001f, alpha * aspect));
+        make_float2(ispc_max(0.001f, alpha / aspect), ispc_max(0.001f, alpha * aspect));
     float clearcoat_alpha = lerp(0.1f, 0.001f, mat.clearcoat_gloss);
     float diffuse = lambertian_pdf(w_i, n);
     float clear_coat = gtr_1_pdf(w_o, w_i, n, clearcoat_alpha);
@@ -764,13 +780,13 @@ float3 sample_disney_brdf(const DisneyMaterial &mat, const float3 &n, const floa
         w_i = sample_lambertian_dir(n, v_x, v_y, samples);
     } else if (component == 1) {
         float3 w_h;
-        float alpha = std::max(0.001f, mat.roughness * mat.roughness);
+        float alpha = ispc_max(0.001f, mat.roughness * mat.roughness);
         if (mat.anisotropy == 0.f) {
             w_h = sample_gtr_2_h(n, v_x, v_y, alpha, samples);
         } else {
             float aspect = std::sqrt(1.f - mat.anisotropy * 0.9f);
             float2 alpha_aniso =
-                make_float2(std::max(0.001f, alpha / aspect), std::max(0.001f, alpha * aspect));
+                make_float2(ispc_max(0.001f, alpha / aspect), ispc_max(0.001f, alpha * aspect));
             w_h = sample_gtr_2_aniso_h(n, v_x, v_y, alpha_aniso, samples);
         }
         w_i = reflect(neg(w_o), w_h);
@@ -789,7 +805,7 @@ float3 sample_disney_brdf(const DisneyMaterial &mat, const float3 &n, const floa
             return make_float3(0.f);
         }
     } else {
-        float alpha = std::max(0.001f, mat.roughness * mat.roughness);
+        float alpha = ispc_max(0.001f, mat.roughness * mat.roughness);
         float3 w_h = sample_gtr_2_h(n, v_x, v_y, alpha, samples);
         if (dot(w_o, w_h) < 0.f) {
             w_h = neg(w_h);
@@ -1601,8 +1617,8 @@ struct Oracle {
                     ++bounce;
                     if (bounce > 3) {
                         const float q =
-                            std::max(0.05f, 1.f - std::max(path_throughput.x,
-                                                           std::max(path_throughput.y, path_throughput.z)));
+                            ispc_max(0.05f, 1.f - ispc_max(path_throughput.x,
+                                                           ispc_max(path_throughput.y, path_throughput.z)));
                         if (lcg_randomf(rng) < q) {
                             break;
                         }
