@@ -9,6 +9,8 @@
 //   mode 0: children pushed far-to-near (true distance order), culled at pop
 //   mode 2: mode 0 with the leaf triangle groups deferred as distance-keyed entries too
 //   mode 3: mode 1 with the truly nearest hit child moved to the top of the stack (one min-selection, no sort)
+#include <cstdio>
+#include <functional>
 #include "../../chameleonrt_b200/csrc/hostcheck.cpp"
 
 // ---------------- experiment: distance-sorted traversal with per-child entry distances on the stack
@@ -234,4 +236,54 @@ extern "C" void crt_hostcheck_trace_exp(void *p, const float *rays, uint64_t n, 
         counters[3 * i + 1] = ntri;
         counters[3 * i + 2] = mode == 4 ? nempty : maxsp;
     }
+}
+
+// ---------------- debugging aid: follow the path from the root to the leaf that holds a given triangle (by
+// flattened primitive id) and report, level by level, whether the ray's box test accepts the child on that path
+extern "C" void crt_hostcheck_explain(void *p, const float *ray8, uint32_t flat_id)
+{
+    using namespace crt;
+    HostCheck *h = static_cast<HostCheck *>(p);
+    const float4 *nodes = reinterpret_cast<const float4 *>(h->node_f4.data());
+    uint32_t leaf_index = 0xffffffffu;
+    for (size_t i = 0; i < h->shade.size(); ++i) {
+        if (h->shade[i].flat_id == flat_id) {
+            leaf_index = (uint32_t)i;
+        }
+    }
+    std::printf("triangle flat %u is leaf-order index %u\n", flat_id, leaf_index);
+    Ray r;
+    std::memcpy(&r, ray8, 32);
+    TravState s;
+    trav_init(s, r);
+    // depth-first search for the node path
+    struct Frame { uint32_t node; int slot; };
+    std::vector<uint32_t> path;
+    std::vector<int> slots;
+    std::function<bool(uint32_t)> find = [&](uint32_t node) -> bool {
+        float tmin8[8], tmax8[8], area8[8];
+        bool hit8[8];
+        uint8_t meta8[8];
+        uint32_t imask, child_base, tri_base;
+        child_boxes(nodes, s, node, tmin8, hit8, imask, child_base, tri_base, meta8, area8, tmax8);
+        for (int slot = 0; slot < 8; ++slot) {
+            if (meta8[slot] == 0) continue;
+            bool contains = false;
+            if (imask & (1u << slot)) {
+                const uint32_t rel = (uint32_t)popc(imask & ((1u << slot) - 1u));
+                contains = find(child_base + rel);
+            } else {
+                const uint32_t off = meta8[slot] & 0x1f, un = meta8[slot] >> 5;
+                const uint32_t k = un == 1 ? 1 : (un == 3 ? 2 : 3);
+                contains = leaf_index >= tri_base + off && leaf_index < tri_base + off + k;
+            }
+            if (contains) {
+                std::printf("  node %u slot %d (%s): box test %s  tmin %.9g tmax %.9g\n", node, slot, (imask & (1u << slot)) ? "inner" : "leaf",
+                            hit8[slot] ? "HIT" : "MISS", tmin8[slot], tmax8[slot]);
+                return true;
+            }
+        }
+        return false;
+    };
+    find(0);
 }

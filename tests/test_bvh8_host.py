@@ -167,3 +167,19 @@ def test_axis_parallel_ray_in_a_box_plane(built):
     assert (bvh.trace_closest(rays).view(np.uint32) == h_brute.view(np.uint32)).all()
     hb, _, _ = HostCheck(scene).trace(rays)
     assert (hb.view(np.uint32) == h_brute.view(np.uint32)).all()
+
+
+def test_fuzz_bvh8_against_brute_force(built):
+    """scripts/fuzz_bvh8_vs_bruteforce.py on fixed seeds: adversarial random scenes (soups, slivers, duplicated
+    sheets, huge + tiny triangles, power-of-two grids) and rays (from / towards vertices, axis-parallel with exact
+    zeros along grid lines, short segments): the product's builder + traversal equals brute force bit for bit,
+    for closest hits and for occlusion in both descent orders. 1,900 seeds were clean when this was written."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import fuzz_bvh8_vs_bruteforce as fuzz
+
+    for seed in (0, 7, 22, 53, 98, 106, 1234, 2222):
+        ok, info = fuzz.one(seed)
+        assert ok, (seed, info)
