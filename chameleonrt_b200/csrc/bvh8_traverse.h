@@ -23,6 +23,7 @@
 #define CRT_HD inline
 #include <cmath>
 #include <cstring>
+#if !defined(__VECTOR_TYPES_H__)  // a host translation unit that included <cuda_runtime.h> has these already
 struct float4 {
     float x, y, z, w;
 };
@@ -32,6 +33,7 @@ struct float3 {
 struct uint2 {
     unsigned int x, y;
 };
+#endif
 #endif
 
 namespace crt {

