@@ -354,6 +354,26 @@ uint64_t crt_wavecheck_render(void *p, const float *pos, const float *dir, const
     return r->last_rays;
 }
 
+// crtc_renderer::assemble_rank: scatter rank `src`'s tile-local buffers into `dst`'s full frame (k_assemble)
+void crt_wavecheck_assemble(void *dst_, void *src_)
+{
+    HostWavefront *dst = static_cast<HostWavefront *>(dst_), *src = static_cast<HostWavefront *>(src_);
+    if (src->npx_local == 0) {
+        return;
+    }
+    crt::FrameLayout f;
+    f.fb_w = dst->fb_w;
+    f.fb_h = dst->fb_h;
+    f.ntx = dst->ntx;
+    f.npx_local = src->npx_local;
+    f.spp = dst->spp;
+    f.frames = 1;
+    f.tile_ids = src->tile_ids.data();
+    HostWavefront::launch(f.npx_local, [&] {
+        crt::k_assemble(f, src->accum_local.data(), src->img_local.data(), dst->accum_full.data(), dst->img_full.data());
+    });
+}
+
 void crt_wavecheck_read(void *p, float *accum_full, uint32_t *img_full)
 {
     HostWavefront *r = static_cast<HostWavefront *>(p);

@@ -31,6 +31,7 @@ def _load(name):
     lib.crt_wavecheck_render.restype = C.c_uint64
     lib.crt_wavecheck_render.argtypes = [C.c_void_p, fp, fp, fp, C.c_float, C.c_int, C.c_uint32, C.c_int]
     lib.crt_wavecheck_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.crt_wavecheck_assemble.argtypes = [C.c_void_p, C.c_void_p]
     lib.crt_wavecheck_last_error.restype = C.c_char_p
     return lib
 
@@ -106,6 +107,17 @@ def test_frames_in_flight_and_tile_sharding_on_the_kernel_source(libs):
     rays_b = batched.render(view, True, 1) + batched.render(view, False, 3)   # 1 + 3 frames as two wavefronts
     a2, i2 = batched.read()
     assert rays == rays_b and np.array_equal(a1.view(np.uint32), a2.view(np.uint32)) and np.array_equal(i1, i2)
+    # tile sharding with frames in flight (what bench.py does at N > 1): every rank renders its tiles of the 4
+    # frames as wavefronts of `world` and 4 - `world` frames; k_assemble puts the ranks' tiles together
+    for world in (2, 3):
+        ranks = [HostWavefront(libs[0], scene, w, h, 5, rank, world) for rank in range(world)]
+        rays_s = 0
+        for r in ranks:
+            rays_s += r.render(view, True, world) + r.render(view, False, 4 - world)
+        for r in ranks:
+            libs[0].crt_wavecheck_assemble(ranks[0].h_, r.h_)
+        a4, i4 = ranks[0].read()
+        assert rays_s == rays and np.array_equal(a1.view(np.uint32), a4.view(np.uint32)) and np.array_equal(i1, i4)
     # shadow rays farthest-first: same frame
     far = HostWavefront(libs[0], scene, w, h, 5)
     for f in range(4):
