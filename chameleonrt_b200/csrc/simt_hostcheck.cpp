@@ -1,0 +1,259 @@
+// simt_hostcheck.cpp — TEST-ONLY shared library (libcrt_simt_hostcheck.so).
+//
+// Executes the product's k_traverse kernel (kernels.cuh) on the host with REAL warp semantics: every CUDA thread
+// of a block is an OS thread, the 32 threads of a warp rendezvous at each warp collective (__ballot_sync,
+// __shfl_*_sync, __syncwarp are barrier-backed exchanges), __shared__ arrays are shared by the block's threads and
+// atomics are real atomics. That is the part of the backend the other host checks cannot reach — the persistent
+// warps' dynamic ray fetch and refill, the shared-memory short stack, the warp-pooled triangle tests merged by a
+// 64-bit atomicMin, the merged shadow + closest launch — so that tests/test_simt_host.py can compare the
+// kernel's results, ray by ray and bit by bit, with the single-ray host instantiation of bvh8_traverse.h (itself
+// checked against brute force), on a machine without a GPU. One block runs at a time (the kernel is persistent:
+// a single block drains the whole queue). It is not linked into libcrt_cuda_core.so and render() cannot reach it.
+#include <pthread.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>  // vector types only
+
+// ---- SIMT execution environment ----
+namespace simt {
+struct Idx3 {
+    unsigned x = 0, y = 0, z = 0;
+};
+struct Warp {
+    pthread_barrier_t barrier;
+    unsigned long long slots[32];
+    Warp() { pthread_barrier_init(&barrier, nullptr, 32); }
+    ~Warp() { pthread_barrier_destroy(&barrier); }
+    void sync() { pthread_barrier_wait(&barrier); }
+};
+static thread_local Warp *warp = nullptr;
+static thread_local int lane = 0;
+
+template <typename T>
+inline unsigned long long to_bits(T v)
+{
+    unsigned long long b = 0;
+    static_assert(sizeof(T) <= 8, "exchange of at most 8 bytes");
+    std::memcpy(&b, &v, sizeof(T));
+    return b;
+}
+template <typename T>
+inline T from_bits(unsigned long long b)
+{
+    T v;
+    std::memcpy(&v, &b, sizeof(T));
+    return v;
+}
+// every lane deposits a value, then reads the lane `src`'s (two rendezvous: publish, consume)
+template <typename T>
+inline T exchange(T v, int src)
+{
+    warp->slots[lane] = to_bits(v);
+    warp->sync();
+    const T r = (src >= 0 && src < 32) ? from_bits<T>(warp->slots[src]) : v;
+    warp->sync();
+    return r;
+}
+}  // namespace simt
+
+static thread_local simt::Idx3 threadIdx, blockIdx, blockDim, gridDim;
+
+template <typename T>
+static inline T __ldg(const T *p)
+{
+    return *p;
+}
+static inline uint32_t __float_as_uint(float f)
+{
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
+static inline float __uint_as_float(uint32_t u)
+{
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+static inline float __uint2float_rn(uint32_t u) { return (float)u; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline unsigned __ballot_sync(unsigned, bool pred)
+{
+    simt::warp->slots[simt::lane] = pred ? 1ull : 0ull;
+    simt::warp->sync();
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) {
+        m |= simt::warp->slots[l] ? (1u << l) : 0u;
+    }
+    simt::warp->sync();
+    return m;
+}
+template <typename T>
+static inline T __shfl_sync(unsigned, T v, int src)
+{
+    return simt::exchange(v, src & 31);
+}
+template <typename T>
+static inline T __shfl_up_sync(unsigned, T v, int delta)
+{
+    return simt::exchange(v, simt::lane - delta);  // lanes below `delta` keep their own value
+}
+template <typename T>
+static inline T __shfl_down_sync(unsigned, T v, int delta)
+{
+    return simt::exchange(v, simt::lane + delta > 31 ? -1 : simt::lane + delta);
+}
+static inline void __syncwarp() { simt::warp->sync(); }
+static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v)
+{
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+    }
+    return old;
+}
+using std::max;
+using std::min;
+#ifndef __launch_bounds__
+#define __launch_bounds__(...)
+#endif
+#undef __shared__
+#define __shared__ static  // one block at a time: a function-local static is the block's shared memory
+
+#include "bvh8.h"
+#include "host_scene.h"
+#include "kernels.cuh"
+
+namespace {
+
+std::string g_err;
+
+struct SimtCheck {
+    std::vector<float4> nodes, tris;
+    std::vector<uint32_t> leaf_flat_ids;  // leaf-order triangle index -> flattened primitive id
+};
+
+}  // namespace
+
+extern "C" {
+
+const char *crt_simt_last_error() { return g_err.c_str(); }
+
+void *crt_simt_create(const crt_scene_t *scene)
+{
+    try {
+        auto *h = new SimtCheck();
+        crt::HostScene hs;
+        crt::flatten_scene(scene, hs, 0);
+        crt::Bvh8 bvh;
+        crt::build_bvh8(hs.tri_verts.data(), hs.num_tris(), 0, bvh);
+        std::vector<float> rec;
+        std::vector<crt::TriShade> sh;
+        crt::pack_triangles(hs, bvh, rec, sh, 0);
+        h->nodes.resize(bvh.nodes.size() * 5);
+        std::memcpy(h->nodes.data(), bvh.nodes.data(), bvh.nodes.size() * 80);
+        if (rec.empty()) {
+            rec.assign(12, 0.f);
+        }
+        h->tris.resize(rec.size() / 4);
+        std::memcpy(h->tris.data(), rec.data(), rec.size() * 4);
+        for (const crt::TriShade &t : sh) {
+            h->leaf_flat_ids.push_back(t.flat_id);
+        }
+        return h;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+void crt_simt_destroy(void *p) { delete static_cast<SimtCheck *>(p); }
+
+// One k_traverse launch (the production instantiation, COUNT = false) of `blocks` blocks of kTravBlock threads:
+// closest rays: n x 8 floats (through an identity or a permuted queue), hits out: n x 4 {t, u, v, bits(flattened
+// primitive id | 0xffffffff)} — the kernel stores the leaf-order triangle index, translated here like crtc_trace_closest
+// any rays: m x 8 floats {o, tnear ignored (the kernel uses kEpsilon), d, tfar}, vis out: m bytes (1 = unoccluded)
+// sched: bits 0-7 refill_idle, bit 8 far-first shadow rays. Single-ray results for comparison come from
+// libcrt_bvh8_hostcheck.so.
+void crt_simt_traverse(void *p, const float *closest, uint32_t n_closest, const uint32_t *queue_perm, const float *any,
+                       uint32_t n_any, int blocks, int sched, float *hits_out, uint8_t *vis_out)
+{
+    SimtCheck *h = static_cast<SimtCheck *>(p);
+    const uint32_t slots = std::max(1u, n_closest);
+    std::vector<float4> ray_o(slots), ray_d(slots), hit(slots), sray_o(std::max(1u, n_any)), sray_d(std::max(1u, n_any));
+    std::vector<uint8_t> vis(std::max(1u, n_any), 7);
+    std::vector<uint32_t> queue(slots), counters(crt::kNumCounters, 0u);
+    for (uint32_t i = 0; i < n_closest; ++i) {
+        const float *r = closest + 8 * (size_t)i;
+        ray_o[i] = make_float4(r[0], r[1], r[2], r[3]);
+        ray_d[i] = make_float4(r[4], r[5], r[6], r[7]);
+        hit[i] = make_float4(-1.f, -1.f, -1.f, 0.f);
+        queue[i] = queue_perm ? queue_perm[i] : i;
+    }
+    for (uint32_t j = 0; j < n_any; ++j) {
+        const float *r = any + 8 * (size_t)j;
+        sray_o[j] = make_float4(r[0], r[1], r[2], r[7]);
+        sray_d[j] = make_float4(r[4], r[5], r[6], __uint_as_float(j));
+    }
+    counters[crt::kCntQueue] = n_closest;
+    counters[crt::kCntShadow] = n_any;
+    crt::DeviceScene sc{};
+    sc.nodes = h->nodes.data();
+    sc.tris = h->tris.data();
+    sc.float_one = 0x3F800000u;
+    crt::PathState ps{};
+    ps.ray_o = ray_o.data();
+    ps.ray_d = ray_d.data();
+    ps.hit = hit.data();
+    ps.sray_o = sray_o.data();
+    ps.sray_d = sray_d.data();
+    ps.vis = vis.data();
+    ps.queue[0] = queue.data();
+    ps.queue[1] = queue.data();
+    ps.counters = counters.data();
+    unsigned long long trav[4] = {0, 0, 0, 0};
+    ps.trav_counters = trav;
+    uint32_t *work_counter = counters.data() + crt::kCntWork;
+
+    for (int b = 0; b < blocks; ++b) {
+        simt::Warp warps[crt::kTravBlock / 32];
+        std::vector<std::thread> threads;
+        for (int t = 0; t < crt::kTravBlock; ++t) {
+            threads.emplace_back([&, t, b] {
+                threadIdx.x = (unsigned)t;
+                blockIdx.x = (unsigned)b;
+                blockDim.x = crt::kTravBlock;
+                gridDim.x = (unsigned)blocks;
+                simt::warp = &warps[t / 32];
+                simt::lane = t % 32;
+                crt::k_traverse<false>(sc, ps, ps.queue[0], counters.data() + crt::kCntQueue, n_any ? counters.data() + crt::kCntShadow : nullptr,
+                                       work_counter, sched);
+            });
+        }
+        for (auto &th : threads) {
+            th.join();
+        }
+    }
+    for (uint32_t i = 0; i < n_closest; ++i) {
+        hits_out[4 * i] = hit[i].x;
+        hits_out[4 * i + 1] = hit[i].y;
+        hits_out[4 * i + 2] = hit[i].z;
+        const uint32_t leaf = __float_as_uint(hit[i].w);
+        hits_out[4 * i + 3] = __uint_as_float(leaf == crt::kMiss || leaf >= h->leaf_flat_ids.size() ? crt::kMiss : h->leaf_flat_ids[leaf]);
+    }
+    if (n_any) {
+        std::memcpy(vis_out, vis.data(), n_any);
+    }
+}
+}

@@ -1,0 +1,87 @@
+"""k_traverse — the persistent, warp-cooperative traversal kernel — executed on the host under a SIMT emulation
+(TEST-ONLY libcrt_simt_hostcheck.so: one OS thread per CUDA thread, the 32 threads of a warp rendezvous at every
+__ballot_sync / __shfl_*_sync / __syncwarp, block-shared memory and atomics are real). Its results must equal, ray by
+ray and bit by bit, the single-ray host instantiation of bvh8_traverse.h (which the other tests pin against brute
+force and the oracle): dynamic ray fetch and refill, the shared-memory short stack with local-memory spill, the
+warp-pooled triangle tests merged by a 64-bit atomicMin, the merged shadow + closest launch, queue indirection,
+partially filled warps, the far-first shadow order."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from chameleonrt_b200.scene import CScene
+from helpers import HostCheck, camera_for
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+
+
+@pytest.fixture(scope="module")
+def lib(built):
+    lib = C.CDLL(os.path.join(ROOT, "chameleonrt_b200", "csrc", "libcrt_simt_hostcheck.so"))
+    lib.crt_simt_create.restype = C.c_void_p
+    lib.crt_simt_create.argtypes = [C.POINTER(CScene)]
+    lib.crt_simt_destroy.argtypes = [C.c_void_p]
+    lib.crt_simt_traverse.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p]
+    return lib
+
+
+def _rays(scene, cam, w, h, seed):
+    from bvh_quality import cosine_bounce, shadow_rays
+    from oracle import OracleBackend
+    from oracle.oracle import primary_rays
+
+    c = camera_for(cam)
+    o = OracleBackend(fast=True)
+    o.initialize(8, 8)
+    o.set_scene(scene)
+    rng = np.random.default_rng(seed)
+    rays = primary_rays(w, h, c.eye(), c.dir(), c.up(), cam["fov_y"])
+    hits, normals = o.trace_closest(rays, True)
+    b1, p = cosine_bounce(rays, hits, normals, rng)
+    return np.ascontiguousarray(np.concatenate([rays, b1]), np.float32), shadow_rays(p, scene.lights[0], rng)
+
+
+def _run(lib, h, closest, shadow, sched, perm=None, blocks=1):
+    out, vis = np.zeros((len(closest), 4), np.float32), np.zeros(max(1, len(shadow)), np.uint8)
+    q = None if perm is None else np.ascontiguousarray(perm, np.uint32)
+    lib.crt_simt_traverse(h, closest.ctypes.data, len(closest), None if q is None else q.ctypes.data, shadow.ctypes.data, len(shadow),
+                          blocks, sched, out.ctypes.data, vis.ctypes.data)
+    return out, vis[: len(shadow)]
+
+
+@pytest.mark.parametrize("name", ["sponza", "cornell"])
+def test_k_traverse_under_simt_emulation_equals_single_ray_traversal(lib, name):
+    from chameleonrt_b200.scenes import cornell_box, sponza_like
+
+    scene, cam = sponza_like(spp=1, detail=0.3, tex_size=16) if name == "sponza" else cornell_box()
+    ms = scene.to_c()
+    h = lib.crt_simt_create(C.byref(ms.c))
+    assert h
+    closest, shadow = _rays(scene, cam, 40, 24, 5)
+    shadow[:, 3] = 1e-4  # the kernel starts shadow rays at kEpsilon
+    hc = HostCheck(scene)
+    want, _, _ = hc.trace(closest)
+    occluded = hc.trace(shadow, any_hit=True)[0][:, 3].view(np.uint32) != 0xFFFFFFFF
+    # default scheduling, far-first shadow rays, refill as soon as one lane idles, refill only when the warp is empty
+    for sched in (4, 4 | 0x100, 1, 32):
+        got, vis = _run(lib, h, closest, shadow, sched)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), hex(sched)
+        assert np.array_equal(vis == 0, occluded) and set(np.unique(vis)) <= {0, 1}
+    # closest rays only / shadow rays only / a ragged handful (partially filled warp) / nothing at all
+    got, _ = _run(lib, h, closest, shadow[:0], 4)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    _, vis = _run(lib, h, closest[:0], shadow, 4)
+    assert np.array_equal(vis == 0, occluded)
+    got, vis = _run(lib, h, closest[:37], shadow[:5], 4)
+    assert np.array_equal(got.view(np.uint32), want[:37].view(np.uint32)) and np.array_equal(vis == 0, occluded[:5])
+    _run(lib, h, closest[:0], shadow[:0], 4)
+    # queue indirection (the compacted queue of a later bounce): slots visited in a permuted order, two blocks
+    perm = np.random.default_rng(1).permutation(len(closest)).astype(np.uint32)
+    got, vis = _run(lib, h, closest, shadow, 4, perm, blocks=2)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)) and np.array_equal(vis == 0, occluded)
+    lib.crt_simt_destroy(h)
