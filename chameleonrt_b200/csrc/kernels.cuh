@@ -154,6 +154,13 @@ __global__ void __launch_bounds__(256) k_raygen(ViewParams view, FrameLayout f, 
 // per lane; the triangles they yield are pooled across the warp and tested 32 pairs at a time
 // (see the loop body). The first kSmemStack entries of each lane's traversal stack live in shared
 // memory, the rest spills to local memory.
+// Profiling hooks of the SIMT emulation (simt_hostcheck.cpp defines them before including this file); they
+// expand to nothing everywhere else, the CUDA build included.
+#ifndef CRT_PROF_NODE_PHASE
+#define CRT_PROF_NODE_PHASE(lane_has_node)
+#define CRT_PROF_TRI_PASS(lane_has_pair)
+#endif
+
 constexpr int kTravBlock = 128;
 constexpr int kSmemStack = 8;
 constexpr int kRefillIdle = 4;
@@ -289,12 +296,9 @@ __global__ void __launch_bounds__(kTravBlock, 8)
         }
         // ---- advance all live lanes until enough of them have finished ----
         // Each iteration has a node phase and a triangle phase so that the lanes of a warp execute
-        // the same code together. Triangle tests are postponed (after Ylitie et al. 2017 §5.3): a
-        // lane keeps ONE pending triangle group in registers while it keeps descending, and the
-        // triangle phase — one test per lane — runs only when at least kTriLanes lanes have a
-        // triangle pending. A lane drains its pending group on its own only when a second group
-        // arrives or when it has nothing else left. The closest hit does not depend on the order
-        // of the tests (ties break on the primitive id), so results are unchanged.
+        // the same code together; the triangles a node step yields are tested in the same iteration
+        // (a per-lane postponement after Ylitie et al. 2017 §5.3 was measured and dropped).
+        // The closest hit does not depend on the order of the tests (ties break on the primitive id).
         {
             // Warp-cooperative triangle tests. The first profiles showed the per-lane triangle loops issuing
             // half of all instructions at 3-8 active lanes. Here the node phase stays per lane, but
@@ -305,6 +309,7 @@ __global__ void __launch_bounds__(kTravBlock, 8)
             __syncwarp();
             for (;;) {
                 // node phase
+                CRT_PROF_NODE_PHASE(alive && (st.cur.y & 0xff000000u));
                 if (alive && (st.cur.y & 0xff000000u)) {
                     const uint32_t node_index = next_child(st.cur, st.oct_inv4);
                     if (st.cur.y & 0xff000000u) {
@@ -342,6 +347,7 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                     }
                     __syncwarp();
                     const uint32_t npairs = min(total, 32u);
+                    CRT_PROF_TRI_PASS((uint32_t)lane < npairs);
                     bool won = false;
                     unsigned long long cand = 0ull;
                     uint32_t owner = 0u, tri_index = 0u;

@@ -131,6 +131,28 @@ using std::min;
 #undef __shared__
 #define __shared__ static  // one block at a time: a function-local static is the block's shared memory
 
+// ---- warp-level work profile: what the kernel's instruction stream costs, counted per warp ----
+// A warp executes the node phase once per loop iteration if ANY of its lanes has a node to intersect, and one
+// triangle pass per 32 pooled (ray, triangle) pairs; lanes without work in a phase are idle issue slots. The
+// counters give node-phase executions and triangle passes (~ the warp instructions the hardware issues, the limiter
+// ncu shows for this kernel) and the lanes that did useful work in them (~ warp execution efficiency).
+namespace simt {
+struct Profile {
+    std::atomic<unsigned long long> node_phases{0}, node_lanes{0}, tri_passes{0}, tri_lanes{0};
+};
+static Profile profile;
+inline void prof_phase(bool lane_active, std::atomic<unsigned long long> &phases, std::atomic<unsigned long long> &lanes)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, lane_active);
+    if (lane == 0 && m) {
+        phases.fetch_add(1, std::memory_order_relaxed);
+        lanes.fetch_add((unsigned long long)__builtin_popcount(m), std::memory_order_relaxed);
+    }
+}
+}  // namespace simt
+#define CRT_PROF_NODE_PHASE(x) simt::prof_phase((x), simt::profile.node_phases, simt::profile.node_lanes)
+#define CRT_PROF_TRI_PASS(x) simt::prof_phase((x), simt::profile.tri_passes, simt::profile.tri_lanes)
+
 #include "bvh8.h"
 #include "host_scene.h"
 #include "kernels.cuh"
@@ -179,6 +201,21 @@ void *crt_simt_create(const crt_scene_t *scene)
 }
 
 void crt_simt_destroy(void *p) { delete static_cast<SimtCheck *>(p); }
+
+// out4: node-phase executions, lanes active in them, triangle passes, lanes active in them (since the last reset)
+void crt_simt_profile(unsigned long long *out4, int reset)
+{
+    out4[0] = simt::profile.node_phases.load();
+    out4[1] = simt::profile.node_lanes.load();
+    out4[2] = simt::profile.tri_passes.load();
+    out4[3] = simt::profile.tri_lanes.load();
+    if (reset) {
+        simt::profile.node_phases = 0;
+        simt::profile.node_lanes = 0;
+        simt::profile.tri_passes = 0;
+        simt::profile.tri_lanes = 0;
+    }
+}
 
 // One k_traverse launch (the production instantiation, COUNT = false) of `blocks` blocks of kTravBlock threads:
 // closest rays: n x 8 floats (through an identity or a permuted queue), hits out: n x 4 {t, u, v, bits(flattened
