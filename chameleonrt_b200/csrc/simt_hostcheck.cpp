@@ -9,8 +9,6 @@
 // kernel's results, ray by ray and bit by bit, with the single-ray host instantiation of bvh8_traverse.h (itself
 // checked against brute force), on a machine without a GPU. One block runs at a time (the kernel is persistent:
 // a single block drains the whole queue). It is not linked into libcrt_cuda_core.so and render() cannot reach it.
-#include <pthread.h>
-
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -21,137 +19,7 @@
 #include <thread>
 #include <vector>
 
-#include <cuda_runtime.h>  // vector types only
-
-// ---- SIMT execution environment ----
-namespace simt {
-struct Idx3 {
-    unsigned x = 0, y = 0, z = 0;
-};
-struct Warp {
-    pthread_barrier_t barrier;
-    unsigned long long slots[32];
-    Warp() { pthread_barrier_init(&barrier, nullptr, 32); }
-    ~Warp() { pthread_barrier_destroy(&barrier); }
-    void sync() { pthread_barrier_wait(&barrier); }
-};
-static thread_local Warp *warp = nullptr;
-static thread_local int lane = 0;
-
-template <typename T>
-inline unsigned long long to_bits(T v)
-{
-    unsigned long long b = 0;
-    static_assert(sizeof(T) <= 8, "exchange of at most 8 bytes");
-    std::memcpy(&b, &v, sizeof(T));
-    return b;
-}
-template <typename T>
-inline T from_bits(unsigned long long b)
-{
-    T v;
-    std::memcpy(&v, &b, sizeof(T));
-    return v;
-}
-// every lane deposits a value, then reads the lane `src`'s (two rendezvous: publish, consume)
-template <typename T>
-inline T exchange(T v, int src)
-{
-    warp->slots[lane] = to_bits(v);
-    warp->sync();
-    const T r = (src >= 0 && src < 32) ? from_bits<T>(warp->slots[src]) : v;
-    warp->sync();
-    return r;
-}
-}  // namespace simt
-
-static thread_local simt::Idx3 threadIdx, blockIdx, blockDim, gridDim;
-
-template <typename T>
-static inline T __ldg(const T *p)
-{
-    return *p;
-}
-static inline uint32_t __float_as_uint(float f)
-{
-    uint32_t u;
-    std::memcpy(&u, &f, 4);
-    return u;
-}
-static inline float __uint_as_float(uint32_t u)
-{
-    float f;
-    std::memcpy(&f, &u, 4);
-    return f;
-}
-static inline float __uint2float_rn(uint32_t u) { return (float)u; }
-static inline int __popc(unsigned v) { return __builtin_popcount(v); }
-static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
-static inline unsigned __ballot_sync(unsigned, bool pred)
-{
-    simt::warp->slots[simt::lane] = pred ? 1ull : 0ull;
-    simt::warp->sync();
-    unsigned m = 0;
-    for (int l = 0; l < 32; ++l) {
-        m |= simt::warp->slots[l] ? (1u << l) : 0u;
-    }
-    simt::warp->sync();
-    return m;
-}
-template <typename T>
-static inline T __shfl_sync(unsigned, T v, int src)
-{
-    return simt::exchange(v, src & 31);
-}
-template <typename T>
-static inline T __shfl_up_sync(unsigned, T v, int delta)
-{
-    return simt::exchange(v, simt::lane - delta);  // lanes below `delta` keep their own value
-}
-template <typename T>
-static inline T __shfl_down_sync(unsigned, T v, int delta)
-{
-    return simt::exchange(v, simt::lane + delta > 31 ? -1 : simt::lane + delta);
-}
-static inline void __syncwarp() { simt::warp->sync(); }
-static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v)
-{
-    unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
-    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
-    }
-    return old;
-}
-using std::max;
-using std::min;
-#ifndef __launch_bounds__
-#define __launch_bounds__(...)
-#endif
-#undef __shared__
-#define __shared__ static  // one block at a time: a function-local static is the block's shared memory
-
-// ---- warp-level work profile: what the kernel's instruction stream costs, counted per warp ----
-// A warp executes the node phase once per loop iteration if ANY of its lanes has a node to intersect, and one
-// triangle pass per 32 pooled (ray, triangle) pairs; lanes without work in a phase are idle issue slots. The
-// counters give node-phase executions and triangle passes (~ the warp instructions the hardware issues, the limiter
-// ncu shows for this kernel) and the lanes that did useful work in them (~ warp execution efficiency).
-namespace simt {
-struct Profile {
-    std::atomic<unsigned long long> node_phases{0}, node_lanes{0}, tri_passes{0}, tri_lanes{0};
-};
-static Profile profile;
-inline void prof_phase(bool lane_active, std::atomic<unsigned long long> &phases, std::atomic<unsigned long long> &lanes)
-{
-    const unsigned m = __ballot_sync(0xffffffffu, lane_active);
-    if (lane == 0 && m) {
-        phases.fetch_add(1, std::memory_order_relaxed);
-        lanes.fetch_add((unsigned long long)__builtin_popcount(m), std::memory_order_relaxed);
-    }
-}
-}  // namespace simt
-#define CRT_PROF_NODE_PHASE(x) simt::prof_phase((x), simt::profile.node_phases, simt::profile.node_lanes)
-#define CRT_PROF_TRI_PASS(x) simt::prof_phase((x), simt::profile.tri_passes, simt::profile.tri_lanes)
+#include "simt_env.h"
 
 #include "bvh8.h"
 #include "host_scene.h"

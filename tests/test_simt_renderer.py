@@ -1,0 +1,117 @@
+"""The PRODUCT's renderer object and C ABI (chameleonrt_b200/csrc/crt_cuda_core.cu + kernels.cuh) running end to end
+on a machine without a GPU: tests/simt_emu builds the same sources for the host, executes every kernel launch under
+the SIMT environment of chameleonrt_b200/csrc/simt_env.h (an OS thread per CUDA thread, barrier-backed warp
+collectives, real shared memory and atomics) and replaces the CUDA runtime by two dozen host stubs. A RenderCUDA is
+pointed at that library (here only — nothing in chameleonrt_b200/ can load it) and put through the SAME test functions
+the B200 runs (tests/test_gpu_parity.py), at the sizes the emulation can afford, plus
+small versions of the frames-in-flight, tile-sharding and shadow-ray-order tests (under a second per 48x48x2spp frame). This checks the launch sequence,
+queue hand-offs, counters, frame records, options and error paths of the real orchestration code, and dry-runs the
+GPU tests' own code; what stays GPU-only is timing and CUDA's floating-point library.
+Set CRT_SIMT_FULL=1 for the longer cases."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import assert_parity, camera_for, parity
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FULL = os.environ.get("CRT_SIMT_FULL") == "1"
+
+
+@pytest.fixture(scope="module")
+def mods(built):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt_emu"))
+    import build as simt_build
+
+    lib_path = simt_build.build()
+    import chameleonrt_b200.backend as backend
+    from oracle import OracleBackend
+    from oracle.oracle import primary_rays
+
+    saved = (backend._LIB_PATH, backend._lib)
+    backend._LIB_PATH, backend._lib = lib_path, None
+    yield backend.RenderCUDA, OracleBackend, primary_rays
+    backend._LIB_PATH, backend._lib = saved
+
+
+@pytest.fixture(scope="module")
+def gpu_tests():
+    import test_gpu_parity
+
+    return test_gpu_parity
+
+
+def test_the_gpu_suites_own_tests_on_the_emulated_renderer(mods, gpu_tests, golden):
+    gpu_tests.test_error_behaviour(mods)
+    gpu_tests.test_traversal_empty_batch_and_misses(mods)
+    gpu_tests.test_traversal_golden_cornell(mods, golden)
+    gpu_tests.test_cornell_frame_matches_golden_and_oracle(mods, golden)
+    gpu_tests.test_camera_changed_resets_accumulation(mods)
+    gpu_tests.test_ragged_framebuffer_and_resize(mods)
+    gpu_tests.test_async_frames_match_blocking_frames(mods)
+
+
+def test_reference_frames_on_the_emulated_renderer(mods, gpu_tests):
+    ref_golden = np.load(os.path.join(ROOT, "tests", "golden", "ref_embree_frames.npz"))
+    for name in ("cornell_d8", "ragged_70x50", "cornell", "materials", "rungholt_like") + (("sponza_like", "sponza_like_d8", "san_miguel_like_instances") if FULL else ()):
+        gpu_tests.test_cuda_matches_reference_embree_frames(mods, ref_golden, name)
+
+
+def test_frames_in_flight_sharding_and_shadow_order_on_the_emulated_renderer(mods):
+    from chameleonrt_b200.scenes import cornell_box
+
+    RenderCUDA = mods[0]
+    scene, cam = cornell_box(spp=1)
+    c = camera_for(cam)
+    args = (c.eye(), c.dir(), c.up(), cam["fov_y"])
+    w, h = 70, 40  # two tiles, ragged
+    single = RenderCUDA(0)
+    single.initialize(w, h)
+    single.set_scene(scene)
+    rays = sum(single.render(*args, f == 0, True).num_rays for f in range(3))
+    want, want_img = single.read_accum(), single.read_img()
+    # render_async + sync, one frame at a time and as a 1 + 2 batch
+    for batches in ((1, 1, 1), (1, 2)):
+        r = RenderCUDA(0)
+        r.initialize(w, h)
+        r.set_scene(scene)
+        for i, nb in enumerate(batches):
+            r.render_async(*args, i == 0, nb)
+        totals, stages, counters, n = r.sync()
+        assert n == 3 and totals.num_rays == rays and counters["kernel_launches"] == len(batches) * (2 + 3 * 5 + 1)
+        assert (r.read_accum().view(np.uint32) == want.view(np.uint32)).all() and (r.read_img() == want_img).all()
+    # two ranks, each rendering its tile of the three frames as wavefronts of 2 + 1, assembled on rank 0
+    ranks, got = [], 0
+    for rank in range(2):
+        r = RenderCUDA(0, rank=rank, world_size=2)
+        r.initialize(w, h)
+        r.set_scene(scene)
+        r.render_async(*args, True, 2)
+        r.render_async(*args, False, 1)
+        got += r.sync()[0].num_rays
+        ranks.append(r)
+    for src, r in enumerate(ranks):
+        acc, img, ntiles = r.local_buffers()
+        assert ntiles == 1
+        ranks[0].assemble_rank(src, 2, acc, img)
+    assert got == rays and (ranks[0].read_accum().view(np.uint32) == want.view(np.uint32)).all()
+    assert (ranks[0].read_img() == want_img).all()
+    # shadow rays far-first: on, and decided per scene from frames 1 and 2 — same image
+    for mode in (1, 2):
+        r = RenderCUDA(0, any_far_first=mode)
+        r.initialize(w, h)
+        r.set_scene(scene)
+        assert sum(r.render(*args, f == 0, True).num_rays for f in range(3)) == rays
+        assert (r.read_accum().view(np.uint32) == want.view(np.uint32)).all()
+
+
+@pytest.mark.skipif(not FULL, reason="set CRT_SIMT_FULL=1 (several minutes under the emulation)")
+def test_longer_gpu_tests_on_the_emulated_renderer(mods, gpu_tests):
+    gpu_tests.test_sharded_ranks_with_frames_in_flight(mods)
+    gpu_tests.test_shadow_ray_order_option_does_not_change_the_image(mods)
+    gpu_tests.test_all_bsdf_lobes_and_textured_params(mods)
+    gpu_tests.test_instanced_textured_gltf_class_scene(mods)
+    for spp, frames, depth in [(1, 1, 5), (1, 3, 5), (4, 2, 5), (2, 2, 8), (1, 1, 1)]:
+        gpu_tests.test_cornell_frames(mods, spp, frames, depth)
