@@ -58,5 +58,30 @@ def build(force: bool = False) -> str:
     return LIB
 
 
+def build_plugin(force: bool = False):
+    """oracle/_ref/libcrt_cuda_simt.so: the drop-in C++ plugin (backends/cuda/*.cpp, unchanged) linked against the
+    emulated core, so that `crt_headless cuda_simt <scene>` runs the whole drop-in path — the reference's loaders,
+    RenderPlugin, RenderCUDA : RenderBackend, the C ABI, the kernels — without a GPU. Needs the reference headers and
+    the objects oracle/ref_build compiled from the reference's util/ + imgui/ (so: only where /root/reference is);
+    returns None elsewhere."""
+    ref = os.environ.get("REF", "/root/reference")
+    obj = os.path.join(ROOT, "oracle", "_ref", "obj")
+    if not os.path.isdir(os.path.join(ref, "util")) or not os.path.isdir(obj):
+        return None
+    core = build(force)
+    out = os.path.join(ROOT, "oracle", "_ref", "libcrt_cuda_simt.so")
+    srcs = [os.path.join(ROOT, "backends", "cuda", f) for f in ("render_cuda.cpp", "render_cuda_plugin.cpp", "render_cuda.h")]
+    srcs += [os.path.join(HERE, "plugin_alias.cpp"), core]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
+        return out
+    objs = sorted(os.path.join(obj, f) for f in os.listdir(obj) if f.startswith(("util_", "imgui_")) and f.endswith(".o"))
+    inc = [f"-I{ROOT}/third_party/miniglm", f"-I{ROOT}/third_party/sdl_stub", f"-I{ref}/util", f"-I{ref}/util/parallel_hashmap",
+           f"-I{ref}/imgui", f"-I{ROOT}/include"]
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-fPIC", "-w", "-pthread", *inc, "-DCRT_CUDA_HEADLESS", "-shared", "-o", out,
+                           srcs[0], srcs[1], srcs[3], *objs, "-L" + OUT, "-lcrt_cuda_core_simt", "-Wl,-rpath," + OUT])
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True))
+    print(build_plugin(force=True))

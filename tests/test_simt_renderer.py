@@ -115,3 +115,39 @@ def test_longer_gpu_tests_on_the_emulated_renderer(mods, gpu_tests):
     gpu_tests.test_instanced_textured_gltf_class_scene(mods)
     for spp, frames, depth in [(1, 1, 5), (1, 3, 5), (4, 2, 5), (2, 2, 8), (1, 1, 1)]:
         gpu_tests.test_cornell_frames(mods, spp, frames, depth)
+
+
+def test_drop_in_plugin_on_the_emulated_core(built, tmp_path):
+    """`crt_headless cuda_simt <scene>`: the C++ plugin of backends/cuda (unchanged sources) linked against the
+    emulated core — the reference's own loaders (OBJ, glTF with instances, .crts with every Disney parameter and an
+    explicit light), RenderPlugin, RenderCUDA : RenderBackend, the C ABI and the kernels, without a GPU. Same checks
+    as the B200's test_cuda_plugin_drop_in* tests."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt_emu"))
+    import build as simt_build
+    from test_reference_plugin import HEADLESS, _crts_case, run_headless
+
+    if not os.path.exists(HEADLESS) or simt_build.build_plugin() is None:
+        pytest.skip("needs oracle/_ref (built where /root/reference is)")
+    from chameleonrt_b200.gltf_io import write_gltf
+    from chameleonrt_b200.obj_io import write_obj
+    from chameleonrt_b200.scenes import cornell_box, san_miguel_like
+
+    scene, cam = cornell_box(spp=2)
+    obj = write_obj(scene, str(tmp_path / "scene.obj"))
+    a_gpu, v1, out = run_headless("cuda_simt", obj, cam, 96, 64, 2, 2, tmp_path)
+    a_cpu, v2, _ = run_headless("oracle", obj, cam, 96, 64, 2, 2, tmp_path)
+    assert v1 == v2 and "CUDA wavefront" in out
+    assert_parity(a_gpu, a_cpu)
+    if not FULL:
+        return
+    scene, cam = san_miguel_like(spp=2, scale=0.02, tex_size=64)
+    gltf = write_gltf(scene, str(tmp_path / "scene.gltf"))
+    a_gpu, v1, out = run_headless("cuda_simt", gltf, cam, 192, 108, 2, 2, tmp_path)
+    a_cpu, v2, _ = run_headless("oracle", gltf, cam, 192, 108, 2, 2, tmp_path)
+    assert v1 == v2 and "CUDA wavefront" in out
+    assert_parity(a_gpu, a_cpu, min_frac=0.99, max_rel_l1=1e-2)
+    scene, cam, crts = _crts_case(tmp_path)
+    a_gpu, v1, out = run_headless("cuda_simt", crts, cam, 192, 128, 2, 2, tmp_path, depth=6)
+    a_cpu, v2, _ = run_headless("oracle", crts, cam, 192, 128, 2, 2, tmp_path, depth=6)
+    assert v1 == v2 and "CUDA wavefront" in out
+    assert_parity(a_gpu, a_cpu, min_frac=0.99, max_rel_l1=1e-2)
