@@ -53,7 +53,10 @@ def build(force: bool = False) -> str:
     cuda_inc = os.path.join(os.path.dirname(os.path.dirname(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"))), "include")
     subprocess.check_call(["make", "-s", "-C", CSRC, "host_scene.o", "bvh8_build.o"])
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-pthread", "-march=x86-64-v3", "-ffp-contract=off", "-Wno-attributes",
-                           "-I" + CSRC, "-I" + cuda_inc, "-shared", "-o", LIB, gen, os.path.join(HERE, "cuda_emu.cpp"),
+                           "-I" + CSRC, "-I" + cuda_inc, "-shared",
+                           # -Bsymbolic: the library's calls to cudaMalloc & co. must bind to ITS stubs even when a real
+                           # libcudart is already in the process (torch loads one globally)
+                           "-Wl,-Bsymbolic", "-o", LIB, gen, os.path.join(HERE, "cuda_emu.cpp"),
                            os.path.join(CSRC, "host_scene.o"), os.path.join(CSRC, "bvh8_build.o")])
     return LIB
 
