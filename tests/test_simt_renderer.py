@@ -151,3 +151,11 @@ def test_drop_in_plugin_on_the_emulated_core(built, tmp_path):
     a_cpu, v2, _ = run_headless("oracle", crts, cam, 192, 128, 2, 2, tmp_path, depth=6)
     assert v1 == v2 and "CUDA wavefront" in out
     assert_parity(a_gpu, a_cpu, min_frac=0.99, max_rel_l1=1e-2)
+
+
+def test_graft_entry_smoke_on_the_emulated_renderer(mods, capsys):
+    """__graft_entry__.smoke() — what the driver runs on the B200 before the bench — dry-run on the emulation."""
+    import __graft_entry__ as g
+
+    g.smoke()
+    assert "pixels within tol=1.00000" in capsys.readouterr().out
