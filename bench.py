@@ -321,29 +321,33 @@ def main():
     # buffers already have their batch size when the clock starts)
     n_warm = args.warmup + frames_in_flight
 
-    # ---- instrumented pass (not timed): exact node/triangle visit counts of the same frames ----
-    counts = np.zeros(6, np.float64)
-    if not args.profile_mode:
-        inst = RenderCUDA(local_rank, max_depth=MAX_DEPTH, rank=rank, world_size=world, count_traversal=True,
-                          stream=stream.cuda_stream)
-        inst.initialize(WIDTH, HEIGHT)
-        inst.set_scene(scene)
-        acc = np.zeros(6, np.float64)
-        for f in range(n_warm + args.steps):
-            inst.render(*view, f == 0, False)
-            if f >= n_warm:
-                c = inst.counters()
-                acc += [c["closest_rays"], c["closest_nodes_visited"], c["closest_tris_tested"], c["occlusion_rays"],
-                        c["any_nodes_visited"], c["any_tris_tested"]]
-        counts = acc
-        del inst
-
     # ---- device-timed region: inputs resident in HBM, no readback ----
     f = 0
     for _ in range(args.warmup):
         frame(f, False)
         f += 1
     flush()  # no collective in flight while the batch-sized path state is (re)allocated
+    # The renderer has by now settled the descent order of its shadow rays for this scene (option any_far_first =
+    # 2: frames 1 and 2 try one order each; the image does not depend on it). The counting pass must use the same.
+    shadow_far_first = gpu.get_option("any_far_first_decision")
+
+    # ---- instrumented pass (not timed): exact node/triangle visit counts of the same frames ----
+    counts = np.zeros(6, np.float64)
+    if not args.profile_mode:
+        inst = RenderCUDA(local_rank, max_depth=MAX_DEPTH, rank=rank, world_size=world, count_traversal=True,
+                          stream=stream.cuda_stream, any_far_first=1 if shadow_far_first == 1 else 0)
+        inst.initialize(WIDTH, HEIGHT)
+        inst.set_scene(scene)
+        acc = np.zeros(6, np.float64)
+        for fi in range(n_warm + args.steps):
+            inst.render(*view, fi == 0, False)
+            if fi >= n_warm:
+                c = inst.counters()
+                acc += [c["closest_rays"], c["closest_nodes_visited"], c["closest_tris_tested"], c["occlusion_rays"],
+                        c["any_nodes_visited"], c["any_tris_tested"]]
+        counts = acc
+        del inst
+
     barrier()
     gpu.render_async(*view, False, frames_in_flight)  # warm-up batch
     f += frames_in_flight
@@ -442,6 +446,8 @@ def main():
                                        "of the accumulated tiles to rank 0 once per batch (stream-ordered, not "
                                        "overlapped); e2e: frame by frame, gather + readback every frame") if world > 1 else "single GPU",
                        "frames_in_flight": frames_in_flight,
+                       "shadow_ray_order": {1: "far-first", 0: "near-first"}.get(shadow_far_first, "undecided (near-first)") +
+                                           " (chosen per scene from the traversal times of warm-up frames 1 and 2; same image either way)",
                        "l2": f"inputs larger than L2: ~{WIDTH * HEIGHT * SPP * 250 / 1e9:.1f} GB of per-frame path state "
                              f"streams through every bounce (L2 126 MB); scene = {gpu.scene_info()['node_bytes'] / 1e6:.0f} MB "
                              f"nodes + {2 * gpu.scene_info()['triangle_bytes'] / 1e6:.0f} MB triangle/shading records"},

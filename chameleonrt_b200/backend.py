@@ -31,7 +31,7 @@ SCENE_INFO_NAMES = ("triangles", "bvh8_nodes", "bvh8_depth", "bvh_build_ms", "no
 
 # Every symbol include/crt_cuda.h declares (tests check the library exports all of them).
 C_ABI_SYMBOLS = (
-    "crtc_last_error", "crtc_name", "crtc_create", "crtc_destroy", "crtc_set_option", "crtc_set_stream",
+    "crtc_last_error", "crtc_name", "crtc_create", "crtc_destroy", "crtc_set_option", "crtc_get_option", "crtc_set_stream",
     "crtc_initialize", "crtc_set_scene", "crtc_render", "crtc_render_async", "crtc_sync", "crtc_read_accum", "crtc_get_stage_times",
     "crtc_get_counters", "crtc_get_scene_info", "crtc_trace_closest", "crtc_trace_any", "crtc_bench_trace",
     "crtc_local_buffers", "crtc_assemble_rank", "crtc_read_img",
@@ -60,6 +60,7 @@ def load_lib() -> C.CDLL:
     lib.crtc_destroy.argtypes = [vp]
     lib.crtc_destroy.restype = None
     lib.crtc_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    lib.crtc_get_option.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
     lib.crtc_set_stream.argtypes = [vp, vp]
     lib.crtc_initialize.argtypes = [vp, C.c_int, C.c_int]
     lib.crtc_set_scene.argtypes = [vp, C.POINTER(CScene)]
@@ -157,6 +158,11 @@ class RenderCUDA:
         _u, up_ = _vec3(up)
         self._check(self.lib.crtc_render_async(self.h, pp, dp, up_, C.c_float(fovy), 1 if camera_changed else 0,
                                                num_frames))
+
+    def get_option(self, key: str) -> int:
+        v = C.c_int64(0)
+        self._check(self.lib.crtc_get_option(self.h, key.encode(), C.byref(v)))
+        return int(v.value)
 
     def sync(self):
         """Waits for all frames queued with render_async; returns (RenderStats totals, stage ms sums,

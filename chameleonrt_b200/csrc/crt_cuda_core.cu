@@ -119,10 +119,10 @@ struct crtc_renderer {
     int bvh_threads = 0;
     bool count_traversal = false;
     int refill_idle = crt::kRefillIdle;  // idle lanes that trigger a refill of the traversal warps
-    // Shadow rays visit the children of a node farthest-first: 0 = no (default), 1 = yes, 2 = auto — frame 1
+    // Shadow rays visit the children of a node farthest-first: 0 = no, 1 = yes, 2 = auto (default) — frame 1
     // after set_scene is rendered near-first, frame 2 far-first, and from frame 3 on the order whose traversal
     // stage was faster is kept (blocking render() calls only; the image is the same either way).
-    int any_far_first = 0;
+    int any_far_first = 2;
     int auto_frames = 0;            // blocking frames rendered since set_scene (auto mode)
     float auto_trav_ms[2] = {0.f, 0.f};
     bool auto_decided = false, auto_choice = false;
@@ -868,6 +868,8 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
                 throw std::runtime_error("any_far_first must be 0 (off), 1 (on) or 2 (auto)");
             }
             r->any_far_first = (int)value;
+            r->auto_frames = 0;
+            r->auto_decided = false;
         } else {
             throw std::runtime_error("unknown option '" + k + "'");
         }
@@ -875,6 +877,36 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
             if (k == "rank" || k == "world_size") {
                 // allow setting world_size before rank; validated again in initialize
             }
+        }
+    })
+}
+
+int crtc_get_option(crtc_renderer *r, const char *key, int64_t *value)
+{
+    CRTC_TRY({
+        const std::string k = key ? key : "";
+        if (!value) {
+            throw std::runtime_error("crtc_get_option: value is null");
+        }
+        if (k == "max_depth") {
+            *value = r->max_depth;
+        } else if (k == "rank") {
+            *value = r->rank;
+        } else if (k == "world_size") {
+            *value = r->world_size;
+        } else if (k == "bvh_threads") {
+            *value = r->bvh_threads;
+        } else if (k == "count_traversal") {
+            *value = r->count_traversal ? 1 : 0;
+        } else if (k == "refill_idle") {
+            *value = r->refill_idle;
+        } else if (k == "any_far_first") {
+            *value = r->any_far_first;
+        } else if (k == "any_far_first_decision") {
+            // the order frames are rendered with from now on: 0 near-first, 1 far-first, -1 auto mode still undecided
+            *value = r->any_far_first != 2 ? (r->any_far_first == 1 ? 1 : 0) : (r->auto_decided ? (r->auto_choice ? 1 : 0) : -1);
+        } else {
+            throw std::runtime_error("unknown option '" + k + "'");
         }
     })
 }

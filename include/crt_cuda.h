@@ -64,11 +64,15 @@ void crtc_destroy(crtc_renderer *r);
  *                 nearest-first. The result of an occlusion query does not depend on the order; the work does
  *                 (fewer node steps when occluders sit near the light's end of the segment, more when they sit
  *                 near the surface). 2 = decide per scene: of the second and third crtc_render frame after
- *                 crtc_set_scene one runs each order, the faster traversal stage wins. 0 (default) = off.
+ *                 crtc_set_scene one runs each order, the faster traversal stage wins (the default). 0 = off.
  *   "count_traversal" 1 = instrumented traversal kernels that count node visits and triangle
  *                 tests (for the algorithmic-byte figure; slower, off by default)
  */
 int crtc_set_option(crtc_renderer *r, const char *key, int64_t value);
+
+/* Reads an option back. Besides the keys above: "any_far_first_decision" = the shadow-ray order frames are
+ * rendered with from now on (0 near-first, 1 far-first, -1 = mode 2 has not decided yet). */
+int crtc_get_option(crtc_renderer *r, const char *key, int64_t *value);
 
 /* Use an existing CUDA stream (cudaStream_t) for all work of this renderer; NULL = the
  * renderer's own stream. Lets a host that already owns a stream (e.g. PyTorch's current
