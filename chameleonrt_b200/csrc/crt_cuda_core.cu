@@ -120,8 +120,10 @@ struct crtc_renderer {
     bool count_traversal = false;
     int refill_idle = crt::kRefillIdle;  // idle lanes that trigger a refill of the traversal warps
     // Shadow rays visit the children of a node farthest-first: 0 = no, 1 = yes, 2 = auto (default) — frame 1
-    // after set_scene is rendered near-first, frame 2 far-first, and from frame 3 on the order whose traversal
-    // stage was faster is kept (blocking render() calls only; the image is the same either way).
+    // after set_scene is rendered far-first, frame 2 near-first, and far-first is kept from frame 3 on only if its
+    // traversal stage was at least 3 % faster (blocking render() calls only; the image is the same either way).
+    // Far-first is tried on the EARLIER, possibly colder frame on purpose: whatever warm-up effect is left works
+    // against the switch, so a wrong decision can only mean staying with near-first.
     int any_far_first = 2;
     int auto_frames = 0;            // blocking frames rendered since set_scene (auto mode)
     float auto_trav_ms[2] = {0.f, 0.f};
@@ -133,7 +135,7 @@ struct crtc_renderer {
         if (any_far_first != 2) {
             return any_far_first == 1;
         }
-        return auto_decided ? auto_choice : auto_frames == 2;
+        return auto_decided ? auto_choice : auto_frames == 1;
     }
     // after a blocking frame's stage times are known
     void auto_tune_step()
@@ -142,11 +144,11 @@ struct crtc_renderer {
             return;
         }
         if (auto_frames == 1 || auto_frames == 2) {
-            auto_trav_ms[auto_frames - 1] = stage_ms[kStTraverse];
+            auto_trav_ms[auto_frames - 1] = stage_ms[kStTraverse];  // [0] far-first (frame 1), [1] near-first (frame 2)
         }
         if (auto_frames == 2) {
             auto_decided = true;
-            auto_choice = auto_trav_ms[1] < 0.97f * auto_trav_ms[0];  // switch only for a clear gain
+            auto_choice = auto_trav_ms[0] < 0.97f * auto_trav_ms[1];  // switch only for a clear gain
         }
         ++auto_frames;
     }

@@ -63,8 +63,9 @@ void crtc_destroy(crtc_renderer *r);
  *   "any_far_first" 1 = shadow (any-hit) rays visit the children of a BVH node farthest-first instead of
  *                 nearest-first. The result of an occlusion query does not depend on the order; the work does
  *                 (fewer node steps when occluders sit near the light's end of the segment, more when they sit
- *                 near the surface). 2 = decide per scene: of the second and third crtc_render frame after
- *                 crtc_set_scene one runs each order, the faster traversal stage wins (the default). 0 = off.
+ *                 near the surface). 2 = decide per scene (the default): the second crtc_render frame after
+ *                 crtc_set_scene runs far-first, the third near-first, and far-first is kept only if its traversal
+ *                 stage was at least 3 % faster. 0 = off.
  *   "count_traversal" 1 = instrumented traversal kernels that count node visits and triangle
  *                 tests (for the algorithmic-byte figure; slower, off by default)
  */
