@@ -42,6 +42,10 @@ WORKLOADS = {
                     "11 textures), 1920x1080, 8 spp, max depth 8", gen="san_miguel_like", kw={}, w=1920, h=1080, spp=8, depth=8),
     "c4": dict(name="C4 rungholt_like OBJ-class voxel city (6.7 M tris, 80 untextured materials), "
                     "1920x1080, 4 spp, max depth 8", gen="rungholt_like", kw={"scale": 1.24}, w=1920, h=1080, spp=4, depth=8),
+    # not a benchmark: a frame small enough for the CPU emulation of the renderer, used by tests/test_bench_contract.py
+    # to dry-run this file's GPU arm where no GPU exists
+    "dev": dict(name="DEV cornell_box, 64x48, 1 spp, max depth 5 (dry run, not a benchmark)", gen="cornell_box", kw={}, w=64, h=48,
+                spp=1, depth=5),
 }
 WORKLOAD = WORKLOADS["c2"]["name"]
 WIDTH, HEIGHT, SPP, MAX_DEPTH = 1280, 720, 4, 8
@@ -145,7 +149,7 @@ def cpu_reference_backend():
     if ref_embree.available(fast=True) and os.environ.get("CRT_BENCH_CPU", "reference") != "port":
         return (ref_embree.RefEmbreeBackend(max_depth=MAX_DEPTH, fast=True), "reference",
                 "the reference's backends/embree sources (render_embree.cpp + render_embree.ispc/.ih compiled as "
-                "scalar C++, -O3 x86-64-v3; Embree replaced by an own BVH2, TBB by std::thread), all host threads")
+                "scalar C++, -O3 x86-64-v3; Embree replaced by an own 4-wide BVH, TBB by std::thread), all host threads")
     from oracle import OracleBackend
 
     return (OracleBackend(max_depth=MAX_DEPTH, fast=True), "port",

@@ -49,3 +49,56 @@ def test_gpu_arm_fails_loudly_without_a_gpu(built):
     r = _run(["--steps", "1", "--warmup", "0"])
     assert r.returncode != 0 and r.stdout.strip() == ""
     assert "CUDA device" in r.stderr
+
+
+def test_gpu_arm_dry_run_on_the_emulated_renderer(built, tmp_path):
+    """bench.py's GPU arm, every line of it — warm-up, the renderer's shadow-order decision, the counting pass, the
+    untimed batch, the device-timed loop with frames in flight, the end-to-end loop, the CPU baseline, the JSON — run
+    in a subprocess where `torch.cuda` is a thin fake over wall-clock time and RenderCUDA loads the CPU emulation of
+    the renderer (tests/simt_emu), on the tiny `dev` workload. Numbers are meaningless; the point is that the code
+    path the driver runs on the B200 executes and prints one well-formed line."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt_emu"))
+    import build as simt_build
+
+    lib = simt_build.build()
+    driver = tmp_path / "dry_run.py"
+    driver.write_text(f'''
+import sys, time, types
+sys.path.insert(0, {ROOT!r})
+import torch
+class _Stream:
+    cuda_stream = 0
+    def __init__(self, *a, **k): pass
+class _Event:
+    def __init__(self, enable_timing=False): self.t = None
+    def record(self, stream=None): self.t = time.perf_counter()
+    def synchronize(self): pass
+    def elapsed_time(self, other): return (other.t - self.t) * 1e3
+torch.cuda.is_available = lambda: True
+torch.cuda.set_device = lambda d: None
+torch.cuda.Stream = _Stream
+torch.cuda.set_stream = lambda s: None
+torch.cuda.Event = _Event
+torch.cuda.synchronize = lambda d=None: None
+import chameleonrt_b200.backend as backend
+backend._LIB_PATH, backend._lib = {lib!r}, None
+import bench
+sys.argv = ["bench.py", "--workload", "dev", "--steps", "2", "--warmup", "3"]
+bench.main()
+''')
+    r = subprocess.run([sys.executable, str(driver)], capture_output=True, text=True, cwd=ROOT, timeout=900,
+                       env=dict(os.environ, CRT_BENCH_REF_BUDGET="2"))
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "stage_ms_per_step"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["value"] > 0 and d["gpu_launches"] == 2 * (2 + 3 * 5 + 1)
+    assert d["config"]["workload"].startswith("DEV") and d["config"]["frames_in_flight"] == 1
+    assert d["config"]["shadow_ray_order"].split()[0] in ("far-first", "near-first")
+    rf = d["roofline"]
+    assert rf["kernel"] == "k_traverse" and rf["bound"] == "hbm" and rf["achieved"] > 0 and 0 < rf["frac"] and rf["closest"]["nodes_per_ray"] > 0
+    assert d["e2e"]["value"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 64 * 48 * 4 + 36 * 4
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] > 0
