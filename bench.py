@@ -44,7 +44,7 @@ WORKLOADS = {
                     "1920x1080, 4 spp, max depth 8", gen="rungholt_like", kw={"scale": 1.24}, w=1920, h=1080, spp=4, depth=8),
     # not a benchmark: a frame small enough for the CPU emulation of the renderer, used by tests/test_bench_contract.py
     # to dry-run this file's GPU arm where no GPU exists
-    "dev": dict(name="DEV cornell_box, 64x48, 1 spp, max depth 5 (dry run, not a benchmark)", gen="cornell_box", kw={}, w=64, h=48,
+    "dev": dict(name="DEV cornell_box, 128x48, 1 spp, max depth 5 (dry run, not a benchmark)", gen="cornell_box", kw={}, w=128, h=48,
                 spp=1, depth=5),
 }
 WORKLOAD = WORKLOADS["c2"]["name"]

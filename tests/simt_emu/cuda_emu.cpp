@@ -1,8 +1,8 @@
 // cuda_emu.cpp — TEST-ONLY: host definitions of the two dozen CUDA runtime entry points crt_cuda_core.cu calls, so
 // that the renderer object and its C ABI can run on a machine without a GPU on top of the SIMT environment of
 // chameleonrt_b200/csrc/simt_env.h (tests/simt_emu/build.py turns the <<<...>>> launches into simt::launch calls).
-// "Device" memory is host memory, streams are synchronous, events are wall-clock timestamps. One "device" with
-// two "SMs" (so that the persistent traversal kernel is launched with more than one block).
+// "Device" memory is host memory, streams are synchronous, events are wall-clock timestamps. Eight "devices" (all the same host) with
+// two "SMs" each (so that the persistent traversal kernel is launched with more than one block).
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -19,10 +19,10 @@ extern "C" {
 
 cudaError_t cudaGetDeviceCount(int *count)
 {
-    *count = 1;
+    *count = 8;
     return cudaSuccess;
 }
-cudaError_t cudaSetDevice(int device) { return device == 0 ? cudaSuccess : cudaErrorInvalidDevice; }
+cudaError_t cudaSetDevice(int device) { return device >= 0 && device < 8 ? cudaSuccess : cudaErrorInvalidDevice; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulated CUDA error"; }
 cudaError_t cudaDeviceGetAttribute(int *value, enum cudaDeviceAttr attr, int)

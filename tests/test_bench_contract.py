@@ -100,5 +100,67 @@ bench.main()
     assert d["config"]["shadow_ray_order"].split()[0] in ("far-first", "near-first")
     rf = d["roofline"]
     assert rf["kernel"] == "k_traverse" and rf["bound"] == "hbm" and rf["achieved"] > 0 and 0 < rf["frac"] and rf["closest"]["nodes_per_ray"] > 0
-    assert d["e2e"]["value"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 64 * 48 * 4 + 36 * 4
+    assert d["e2e"]["value"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 128 * 48 * 4 + 36 * 4
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] > 0
+
+
+def test_gpu_arm_dry_run_two_ranks(built, tmp_path):
+    """The N = 2 path of bench.py — tile sharding, two frames in flight per wavefront, the per-batch gather and
+    assembly on rank 0, the reductions over ranks — dry-run as two processes: gloo instead of NCCL, host tensors
+    aliasing the emulated renderer's "device" buffers instead of CUDA tensors. Rank 0 prints the one line."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "simt_emu"))
+    import build as simt_build
+    import socket
+
+    lib = simt_build.build()
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    driver = tmp_path / "dry_run2.py"
+    driver.write_text(f'''
+import ctypes, sys, time
+sys.path.insert(0, {ROOT!r})
+import numpy as np
+import torch
+import torch.distributed as dist
+class _Stream:
+    cuda_stream = 0
+    def __init__(self, *a, **k): pass
+class _Event:
+    def __init__(self, enable_timing=False): self.t = None
+    def record(self, stream=None): self.t = time.perf_counter()
+    def synchronize(self): pass
+    def elapsed_time(self, other): return (other.t - self.t) * 1e3
+torch.cuda.is_available = lambda: True
+torch.cuda.set_device = lambda d: None
+torch.cuda.Stream = _Stream
+torch.cuda.set_stream = lambda s: None
+torch.cuda.Event = _Event
+torch.cuda.synchronize = lambda d=None: None
+_real_device = torch.device
+torch.device = lambda *a, **k: _real_device("cpu")
+_real_init = dist.init_process_group
+dist.init_process_group = lambda backend=None, **k: _real_init("gloo")
+import chameleonrt_b200.backend as backend
+backend._LIB_PATH, backend._lib = {lib!r}, None
+import chameleonrt_b200.distributed as cd
+cd.device_tensor = lambda ptr, nbytes, device: torch.from_numpy(np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(ptr)))
+import bench
+sys.argv = ["bench.py", "--gpus", "2", "--workload", "dev", "--steps", "4", "--warmup", "3"]
+bench.main()
+''')
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   CRT_BENCH_REF_BUDGET="2")
+        procs.append(subprocess.Popen([sys.executable, str(driver)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT, env=env))
+    outs = [p.communicate(timeout=900) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se[-3000:]
+    assert outs[1][0].strip() == ""
+    lines = [l for l in outs[0][0].splitlines() if l.strip()]
+    assert len(lines) == 1, outs[0][0]
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["steps"] == 4 and d["config"]["frames_in_flight"] == 2 and d["value"] > 0 and d["e2e"]["value"] > 0
+    assert d["gpu_launches"] == 2 * 2 * (2 + 3 * 5 + 1) + 2 * 2  # 2 ranks x 2 batches x launches per wavefront + k_assemble on rank 0
+    assert "cpu_baseline" not in d and d["roofline"]["closest"]["rays"] > 0 and "image tiles 64x64" in d["config"]["parallelism"]
