@@ -42,6 +42,8 @@ WORKLOADS = {
                     "11 textures), 1920x1080, 8 spp, max depth 8", gen="san_miguel_like", kw={}, w=1920, h=1080, spp=8, depth=8),
     "c4": dict(name="C4 rungholt_like OBJ-class voxel city (6.7 M tris, 80 untextured materials), "
                     "1920x1080, 4 spp, max depth 8", gen="rungholt_like", kw={"scale": 1.24}, w=1920, h=1080, spp=4, depth=8),
+    "c5": dict(name="C5 san_miguel_like glTF-class scene (10.5 M instanced tris), 3840x2160, 8 spp per step (64 spp accumulated "
+                    "after 8 steps), max depth 8; meant for --gpus 8", gen="san_miguel_like", kw={}, w=3840, h=2160, spp=8, depth=8),
     # not a benchmark: a frame small enough for the CPU emulation of the renderer, used by tests/test_bench_contract.py
     # to dry-run this file's GPU arm where no GPU exists
     "dev": dict(name="DEV cornell_box, 128x48, 1 spp, max depth 5 (dry run, not a benchmark)", gen="cornell_box", kw={}, w=128, h=48,
