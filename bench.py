@@ -229,6 +229,57 @@ def run_reference_arm(args):
     emit(line)
 
 
+def run_set_scene_probe() -> None:
+    """Sub-process of the N=1 run (`--probe-set-scene`): crtc_set_scene of the bench scene with the BVH8 built on the
+    host (binned SAH, the default and what the timed region renders over) and on the device (bvh8_device.cuh, SURVEY.md
+    §8(f) rank 1), wall-clock around the call, then two frames over each tree: they must be bit-identical, and the
+    instrumented counters tell what the faster build costs in traversal work. Its own process, so that a fault in
+    the newer device builder cannot take the bench line with it."""
+    import time
+
+    import numpy as np
+
+    from chameleonrt_b200 import RenderCUDA
+
+    scene, view = make_workload()
+    out, frames = {}, {}
+    for builder in ("host", "device"):
+        r = RenderCUDA(0, max_depth=MAX_DEPTH, bvh_builder=builder, count_traversal=True, any_far_first=0)
+        r.initialize(WIDTH, HEIGHT)
+        t0 = time.perf_counter()
+        r.set_scene(scene)
+        wall = (time.perf_counter() - t0) * 1e3
+        for f in range(2):
+            r.render(*view, f == 0, False)
+        info, c, st = r.scene_info(), r.counters(), r.stage_times()
+        out[builder] = {"set_scene_ms": wall, "bvh_build_ms": info["bvh_build_ms"], "bvh8_nodes": int(info["bvh8_nodes"]),
+                        "bvh8_depth": int(info["bvh8_depth"]),
+                        "closest_nodes_per_ray": c["closest_nodes_visited"] / max(1, c["closest_rays"]),
+                        "any_hit_nodes_per_ray": c["any_nodes_visited"] / max(1, c["occlusion_rays"]),
+                        "traverse_ms_instrumented": st["traverse"] + st["traverse_primary"]}
+        frames[builder] = r.read_accum()
+        del r
+    out["triangles"] = int(info["triangles"])
+    out["frames_bit_identical"] = bool(np.array_equal(frames["host"].view(np.uint32), frames["device"].view(np.uint32)))
+    emit(out)
+
+
+def set_scene_probe(workload_key: str):
+    """Runs run_set_scene_probe() in a child process; returns its dict, or {"error": ...}."""
+    import subprocess
+
+    try:
+        # (CRT_BENCH_PROBE_SCRIPT: tests/test_bench_contract.py dry-runs this through its own launcher)
+        script = os.environ.get("CRT_BENCH_PROBE_SCRIPT", os.path.abspath(__file__))
+        p = subprocess.run([sys.executable, script, "--probe-set-scene", "--workload", workload_key],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=int(os.environ.get("CRT_BENCH_PROBE_TIMEOUT", "240")))
+        if p.returncode != 0:
+            return {"error": f"exit code {p.returncode}: " + p.stderr.decode(errors="replace").strip().splitlines()[-1][:300]}
+        return json.loads(p.stdout.decode().strip().splitlines()[-1])
+    except Exception as e:  # timeout, unparsable output
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def emit(line: dict) -> None:
     """The contract is ONE JSON line on stdout. Libraries (NCCL prints its version banner) write
     to fd 1 too, so main() points fd 1 at stderr for the whole run and the result goes to the
@@ -259,9 +310,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-mode", action="store_true",
                     help="for runs under ncu: skip the instrumented counting pass and the CPU baseline")
+    ap.add_argument("--probe-set-scene", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else max(args.warmup, 1)
     select_workload(args.workload)
+    if args.probe_set_scene:
+        run_set_scene_probe()
+        return
 
     if args.impl == "reference":
         run_reference_arm(args)
@@ -481,6 +536,9 @@ def main():
                 "value": crays / (cms * 1e3), "unit": "MRays/s", "cores": cpu_cores(), "kind": cpu_kind,
                 "ms_per_frame": cms / len(warm),
                 "sample": f"{len(warm)} full frame(s) of the same workload (1 warm-up frame discarded); {cpu_desc}"}
+        if world == 1 and not args.profile_mode and os.environ.get("CRT_BENCH_SET_SCENE_PROBE", "1") != "0":
+            # outside the timed region, in a child process: set_scene with the host and with the device BVH builder
+            line["set_scene"] = set_scene_probe(args.workload)
         emit(line)
     if world > 1:
         dist.barrier()

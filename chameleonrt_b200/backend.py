@@ -91,7 +91,7 @@ class RenderCUDA:
 
     def __init__(self, device: int = 0, max_depth: int = 5, rank: int = 0, world_size: int = 1,
                  count_traversal: bool = False, bvh_threads: int = 0, stream: Optional[int] = None,
-                 any_far_first: Optional[int] = None):
+                 any_far_first: Optional[int] = None, bvh_builder: Optional[str] = None):
         self.lib = load_lib()
         self.h = C.c_void_p()
         self._check(self.lib.crtc_create(C.byref(self.h), device))
@@ -107,6 +107,14 @@ class RenderCUDA:
                 self._check(self.lib.crtc_set_option(self.h, key.encode(), int(os.environ[env])))
         if any_far_first is not None:  # 0 / 1 / 2 = auto: traversal order of shadow rays; never changes a result (crt_cuda.h)
             self._check(self.lib.crtc_set_option(self.h, b"any_far_first", int(any_far_first)))
+        # where set_scene builds the BVH8: "host" (binned SAH, the default) or "device" (LBVH on the GPU: faster
+        # set_scene, a somewhat slower tree); the rendered image is the same either way (crt_cuda.h)
+        bvh_builder = bvh_builder or os.environ.get("CRT_CUDA_BVH_BUILDER")
+        if bvh_builder is not None:
+            bvh_builder = {"0": "host", "1": "device"}.get(str(bvh_builder), bvh_builder)  # the plugin's env var is numeric
+            if bvh_builder not in ("host", "device"):
+                raise ValueError("bvh_builder must be 'host' or 'device'")
+            self._check(self.lib.crtc_set_option(self.h, b"bvh_builder", 1 if bvh_builder == "device" else 0))
         if stream is not None:
             self._check(self.lib.crtc_set_stream(self.h, C.c_void_p(stream)))
         self.width = self.height = 0

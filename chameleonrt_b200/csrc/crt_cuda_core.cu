@@ -17,6 +17,7 @@
 
 #include "../../include/crt_cuda.h"
 #include "bvh8.h"
+#include "bvh8_device.cuh"
 #include "host_scene.h"
 #include "kernels.cuh"
 
@@ -117,6 +118,7 @@ struct crtc_renderer {
     int max_depth = 5;
     int rank = 0, world_size = 1;
     int bvh_threads = 0;
+    int bvh_builder = 0;  // 0 = host (binned SAH, bvh8_build.cpp), 1 = device (LBVH, bvh8_device.cuh)
     bool count_traversal = false;
     int refill_idle = crt::kRefillIdle;  // idle lanes that trigger a refill of the traversal warps
     // Shadow rays visit the children of a node farthest-first: 0 = no, 1 = yes, 2 = auto (default) — frame 1
@@ -326,6 +328,194 @@ struct crtc_renderer {
         CUDA_CHECK(cudaStreamSynchronize(stream));
     }
 
+    static void check_depth(uint32_t depth)
+    {
+        if (depth + 2 > CRT_STACK_SIZE) {
+            throw std::runtime_error("BVH8 depth " + std::to_string(depth) + " exceeds the traversal stack (CRT_STACK_SIZE)");
+        }
+    }
+
+    // exclusive scan of n items (in place allowed); `scratch` holds the tile sums of every recursion level
+    template <typename T>
+    void device_scan(const T *in, T *out, uint32_t n, T *scratch)
+    {
+        const unsigned tiles = (n + crt::kBuildTile - 1) / crt::kBuildTile;
+        T *sums = tiles > 1 ? scratch : nullptr;
+        crt::k_scan_tile<T><<<tiles, crt::kBuildBlock, 0, stream>>>(in, out, n, sums);
+        if (tiles > 1) {
+            device_scan<T>(scratch, scratch, tiles, scratch + tiles);
+            crt::k_scan_add<T><<<tiles, crt::kBuildBlock, 0, stream>>>(out, n, scratch);
+        }
+    }
+    static size_t scan_scratch_items(size_t n)
+    {
+        size_t total = 0;
+        while (n > (size_t)crt::kBuildTile) {
+            n = (n + crt::kBuildTile - 1) / crt::kBuildTile;
+            total += n;
+        }
+        return total + 1;
+    }
+
+    // set_scene with option bvh_builder = 1: everything after the flattening happens on the device
+    // (bvh8_device.cuh); fills d_nodes, d_tris, d_shade and leaf_flat_ids like the host path.
+    void build_on_device(const crt::HostScene &hs, uint32_t &num_nodes, uint32_t &depth, double &ms)
+    {
+        const uint32_t n = (uint32_t)hs.num_tris();
+        if (hs.num_tris() >= (1u << 30)) {
+            throw std::runtime_error("device BVH build: at most 2^30 - 1 triangles");
+        }
+        int sms = 0;
+        CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        auto grid_for = [&](uint32_t items) {
+            return std::max(1u, std::min((items + crt::kBuildBlock - 1) / crt::kBuildBlock, (uint32_t)sms * 8u));
+        };
+        cudaEvent_t ev0, ev1;
+        CUDA_CHECK(cudaEventCreate(&ev0));
+        CUDA_CHECK(cudaEventCreate(&ev1));
+        const uint32_t num_b2 = 2 * n - 1, max_nodes = std::max(1u, n - 1);
+        DeviceBuffer<float> d_verts;
+        DeviceBuffer<float4> d_shade_in, tri_lo, tri_hi, box_lo, box_hi, nodes_tmp;
+        DeviceBuffer<uint32_t> cbounds, vals0, vals1, hist, d_parent, arrivals, slots, work0, work1, tri_order;
+        DeviceBuffer<crt::u64> keys0, keys1, counts, offsets, scan_scratch;
+        DeviceBuffer<uint2> d_children;
+        DeviceBuffer<float> cost;
+        DeviceBuffer<uint8_t> decision;
+        d_verts.upload(hs.tri_verts.data(), (size_t)n * 9, stream);
+        static_assert(sizeof(crt::TriShade) == 3 * sizeof(float4), "TriShade = 3 float4");
+        d_shade_in.upload(reinterpret_cast<const float4 *>(hs.tri_shade.data()), (size_t)n * 3, stream);
+        CUDA_CHECK(cudaEventRecord(ev0, stream));
+        tri_lo.alloc(n);
+        tri_hi.alloc(n);
+        const uint32_t cb_init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+        cbounds.upload(cb_init, 6, stream);
+        keys0.alloc(n);
+        keys1.alloc(n);
+        vals0.alloc(n);
+        vals1.alloc(n);
+        const uint32_t tiles = (n + crt::kBuildTile - 1) / crt::kBuildTile;
+        hist.alloc((size_t)tiles * 256);
+        d_children.alloc(std::max(1u, n - 1));
+        d_parent.alloc(num_b2);
+        box_lo.alloc(num_b2);
+        box_hi.alloc(num_b2);
+        arrivals.alloc(std::max(1u, n - 1));
+        cost.alloc((size_t)num_b2 * 7);
+        decision.alloc((size_t)num_b2 * 7);
+        slots.alloc((size_t)max_nodes * 8);
+        work0.alloc(max_nodes);
+        work1.alloc(max_nodes);
+        counts.alloc(max_nodes);
+        offsets.alloc(max_nodes);
+        scan_scratch.alloc(std::max(scan_scratch_items(max_nodes), (scan_scratch_items((size_t)tiles * 256) + 1) / 2 + 1));
+        nodes_tmp.alloc((size_t)max_nodes * 5);
+        tri_order.alloc(n);
+
+        crt::Lbvh b;
+        b.n = n;
+        b.verts = d_verts.ptr;
+        b.tri_lo = tri_lo.ptr;
+        b.tri_hi = tri_hi.ptr;
+        b.cbounds = cbounds.ptr;
+        b.children = d_children.ptr;
+        b.parent = d_parent.ptr;
+        b.box_lo = box_lo.ptr;
+        b.box_hi = box_hi.ptr;
+        b.arrivals = arrivals.ptr;
+        b.cost = cost.ptr;
+        b.decision = decision.ptr;
+        const unsigned g = grid_for(n);
+        crt::k_lbvh_bounds<<<g, crt::kBuildBlock, 0, stream>>>(b);
+        crt::k_lbvh_keys<<<g, crt::kBuildBlock, 0, stream>>>(b, keys0.ptr, vals0.ptr);
+        crt::u64 *kin = keys0.ptr, *kout = keys1.ptr;
+        uint32_t *vin = vals0.ptr, *vout = vals1.ptr;
+        for (int shift = 0; shift < 64; shift += 8) {  // 63 key bits
+            crt::k_radix_hist<<<tiles, crt::kBuildBlock, 0, stream>>>(kin, n, shift, hist.ptr, tiles);
+            device_scan<uint32_t>(hist.ptr, hist.ptr, tiles * 256u, reinterpret_cast<uint32_t *>(scan_scratch.ptr));
+            crt::k_radix_scatter<<<tiles, crt::kBuildBlock, 0, stream>>>(kin, vin, kout, vout, n, shift, hist.ptr, tiles);
+            std::swap(kin, kout);
+            std::swap(vin, vout);
+        }
+        if (n > 1) {
+            crt::k_lbvh_hierarchy<<<grid_for(n - 1), crt::kBuildBlock, 0, stream>>>(b, kin);
+        }
+        crt::k_lbvh_refit<<<g, crt::kBuildBlock, 0, stream>>>(b, vin);
+
+        // BVH8 levels: the host only learns each level's size
+        const uint32_t root = 0u;
+        CUDA_CHECK(cudaMemcpyAsync(work0.ptr, &root, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        uint32_t *work = work0.ptr, *next_work = work1.ptr;
+        uint32_t node_begin = 0, count = 1, tri_total = 0;
+        depth = 0;
+        crt::u64 *h_tail = nullptr;  // pinned: last offset, last count of the level
+        CUDA_CHECK(cudaMallocHost(&h_tail, 2 * sizeof(crt::u64)));
+        try {
+            while (count) {
+                ++depth;
+                if ((size_t)node_begin + count > max_nodes) {
+                    throw std::runtime_error("device BVH build: node count exceeds its bound");
+                }
+                crt::LevelArgs lv;
+                lv.work = work;
+                lv.count = count;
+                lv.node_begin = node_begin;
+                lv.next_begin = node_begin + count;
+                lv.tri_begin = tri_total;
+                lv.slots = slots.ptr;
+                lv.counts = counts.ptr;
+                lv.offsets = offsets.ptr;
+                lv.next_work = next_work;
+                lv.nodes = reinterpret_cast<crt::Bvh8Node *>(nodes_tmp.ptr);
+                lv.tri_order = tri_order.ptr;
+                const unsigned gl = grid_for(count);
+                crt::k_plan_level<<<gl, crt::kBuildBlock, 0, stream>>>(b, lv);
+                device_scan<crt::u64>(counts.ptr, offsets.ptr, count, scan_scratch.ptr);
+                CUDA_CHECK(cudaMemcpyAsync(h_tail, offsets.ptr + (count - 1), sizeof(crt::u64), cudaMemcpyDeviceToHost, stream));
+                CUDA_CHECK(cudaMemcpyAsync(h_tail + 1, counts.ptr + (count - 1), sizeof(crt::u64), cudaMemcpyDeviceToHost, stream));
+                crt::k_emit_level<<<gl, crt::kBuildBlock, 0, stream>>>(b, lv, vin);
+                CUDA_CHECK(cudaStreamSynchronize(stream));
+                const crt::u64 total = h_tail[0] + h_tail[1];
+                node_begin += count;
+                count = (uint32_t)(total >> 32);
+                tri_total += (uint32_t)total;
+                std::swap(work, next_work);
+            }
+        } catch (...) {
+            cudaFreeHost(h_tail);
+            throw;
+        }
+        cudaFreeHost(h_tail);
+        if (tri_total != n) {
+            throw std::runtime_error("device BVH build: emitted " + std::to_string(tri_total) + " of " + std::to_string(n) +
+                                     " triangles");
+        }
+        check_depth(depth);
+        num_nodes = node_begin;
+        d_nodes.alloc((size_t)num_nodes * 5);
+        CUDA_CHECK(cudaMemcpyAsync(d_nodes.ptr, nodes_tmp.ptr, (size_t)num_nodes * 80, cudaMemcpyDeviceToDevice, stream));
+        d_tris.alloc((size_t)n * 3);
+        d_shade.alloc((size_t)n * 3);
+        crt::k_pack_leaf_order<<<g, crt::kBuildBlock, 0, stream>>>(d_verts.ptr, d_shade_in.ptr, tri_order.ptr, n, d_tris.ptr,
+                                                                  d_shade.ptr);
+        CUDA_CHECK(cudaEventRecord(ev1, stream));
+        CUDA_CHECK(cudaGetLastError());
+        std::vector<uint32_t> order(n);
+        CUDA_CHECK(cudaMemcpyAsync(order.data(), tri_order.ptr, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        float t = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&t, ev0, ev1));
+        ms = t;
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+        leaf_flat_ids.resize(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            if (order[i] >= n) {
+                throw std::runtime_error("device BVH build: triangle order out of range");
+            }
+            leaf_flat_ids[i] = hs.tri_shade[order[i]].flat_id;
+        }
+    }
+
     void set_scene(const crt_scene_t *scene)
     {
         make_current();
@@ -334,29 +524,36 @@ struct crtc_renderer {
         auto_decided = false;
         crt::HostScene hs;
         crt::flatten_scene(scene, hs, bvh_threads);
-        crt::Bvh8 bvh;
-        crt::build_bvh8(hs.tri_verts.data(), hs.num_tris(), bvh_threads, bvh);
-        if (bvh.max_depth + 2 > CRT_STACK_SIZE) {
-            throw std::runtime_error("BVH8 depth " + std::to_string(bvh.max_depth) +
-                                     " exceeds the traversal stack (CRT_STACK_SIZE)");
+        uint32_t bvh_nodes = 0, bvh_depth = 0;
+        double bvh_ms = 0.0;
+        if (bvh_builder == 1 && hs.num_tris() > 0) {
+            build_on_device(hs, bvh_nodes, bvh_depth, bvh_ms);
+        } else {
+            crt::Bvh8 bvh;
+            crt::build_bvh8(hs.tri_verts.data(), hs.num_tris(), bvh_threads, bvh);
+            check_depth(bvh.max_depth);
+            std::vector<float> tri_records;
+            std::vector<crt::TriShade> shade;
+            crt::pack_triangles(hs, bvh, tri_records, shade, bvh_threads);
+            leaf_flat_ids.resize(shade.size());
+            for (size_t i = 0; i < shade.size(); ++i) {
+                leaf_flat_ids[i] = shade[i].flat_id;
+            }
+            static_assert(sizeof(crt::Bvh8Node) == 5 * sizeof(float4), "node = 5 float4");
+            d_nodes.upload(reinterpret_cast<const float4 *>(bvh.nodes.data()), bvh.nodes.size() * 5, stream);
+            // keep at least one (degenerate) record so empty scenes have valid pointers
+            if (tri_records.empty()) {
+                tri_records.assign(12, 0.f);
+                shade.resize(1);
+                std::memset(&shade[0], 0, sizeof(crt::TriShade));
+            }
+            d_tris.upload(reinterpret_cast<const float4 *>(tri_records.data()), tri_records.size() / 4, stream);
+            d_shade.upload(reinterpret_cast<const float4 *>(shade.data()), shade.size() * 3, stream);
+            CUDA_CHECK(cudaStreamSynchronize(stream));  // the staging vectors go out of scope
+            bvh_nodes = (uint32_t)bvh.nodes.size();
+            bvh_depth = bvh.max_depth;
+            bvh_ms = bvh.build_seconds * 1e3;
         }
-        std::vector<float> tri_records;
-        std::vector<crt::TriShade> shade;
-        crt::pack_triangles(hs, bvh, tri_records, shade, bvh_threads);
-        leaf_flat_ids.resize(shade.size());
-        for (size_t i = 0; i < shade.size(); ++i) {
-            leaf_flat_ids[i] = shade[i].flat_id;
-        }
-        static_assert(sizeof(crt::Bvh8Node) == 5 * sizeof(float4), "node = 5 float4");
-        d_nodes.upload(reinterpret_cast<const float4 *>(bvh.nodes.data()), bvh.nodes.size() * 5, stream);
-        // keep at least one (degenerate) record so empty scenes have valid pointers
-        if (tri_records.empty()) {
-            tri_records.assign(12, 0.f);
-            shade.resize(1);
-            std::memset(&shade[0], 0, sizeof(crt::TriShade));
-        }
-        d_tris.upload(reinterpret_cast<const float4 *>(tri_records.data()), tri_records.size() / 4, stream);
-        d_shade.upload(reinterpret_cast<const float4 *>(shade.data()), shade.size() * 3, stream);
         static_assert(sizeof(crt_material_t) == 64 && sizeof(crt_quad_light_t) == 80, "layouts");
         if (hs.materials.empty()) {
             hs.materials.resize(1);
@@ -378,10 +575,10 @@ struct crtc_renderer {
         spp = std::max<uint32_t>(1u, hs.samples_per_pixel);
         have_scene = true;
         scene_info[0] = (double)hs.num_tris();
-        scene_info[1] = (double)bvh.nodes.size();
-        scene_info[2] = (double)bvh.max_depth;
-        scene_info[3] = bvh.build_seconds * 1e3;
-        scene_info[4] = (double)bvh.nodes.size() * 80.0;
+        scene_info[1] = (double)bvh_nodes;
+        scene_info[2] = (double)bvh_depth;
+        scene_info[3] = bvh_ms;
+        scene_info[4] = (double)bvh_nodes * 80.0;
         scene_info[5] = (double)hs.num_tris() * 48.0;
         if (npx_local) {
             CUDA_CHECK(cudaMemsetAsync(d_accum_local.ptr, 0, (size_t)npx_local * 3 * sizeof(float), stream));
@@ -861,6 +1058,11 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
             r->world_size = (int)value;
         } else if (k == "bvh_threads") {
             r->bvh_threads = (int)value;
+        } else if (k == "bvh_builder") {
+            if (value != 0 && value != 1) {
+                throw std::runtime_error("bvh_builder must be 0 (host) or 1 (device)");
+            }
+            r->bvh_builder = (int)value;
         } else if (k == "count_traversal") {
             r->count_traversal = value != 0;
         } else if (k == "refill_idle") {
@@ -898,6 +1100,8 @@ int crtc_get_option(crtc_renderer *r, const char *key, int64_t *value)
             *value = r->world_size;
         } else if (k == "bvh_threads") {
             *value = r->bvh_threads;
+        } else if (k == "bvh_builder") {
+            *value = r->bvh_builder;
         } else if (k == "count_traversal") {
             *value = r->count_traversal ? 1 : 0;
         } else if (k == "refill_idle") {

@@ -1,6 +1,7 @@
 // simt_env.h — TEST-ONLY: a SIMT execution environment for running the CUDA kernels of kernels.cuh on the host.
 // Every CUDA thread of a block is an OS thread; the 32 threads of a warp rendezvous at each warp collective
-// (__ballot_sync, __shfl_*_sync, __syncwarp are barrier-backed exchanges), __shared__ variables become
+// (__ballot_sync, __shfl_*_sync, __match_any_sync, __syncwarp are barrier-backed exchanges; __syncthreads is a
+// barrier over the block's threads), __shared__ variables become
 // function-local statics (blocks run one at a time) and atomics are real atomics. Included BEFORE kernels.cuh by
 // simt_hostcheck.cpp (k_traverse alone) and by tests/simt_emu (the whole renderer). Never part of the product.
 #pragma once
@@ -61,6 +62,7 @@ struct Warp {
 };
 static thread_local Warp *warp = nullptr;
 static thread_local int lane = 0;
+static thread_local YieldBarrier *block_barrier = nullptr;  // all threads of the running block (__syncthreads)
 
 template <typename T>
 inline unsigned long long to_bits(T v)
@@ -138,6 +140,37 @@ static inline T __shfl_down_sync(unsigned, T v, int delta)
     return simt::exchange(v, simt::lane + delta > 31 ? -1 : simt::lane + delta);
 }
 static inline void __syncwarp() { simt::warp->sync(); }
+static inline void __syncthreads() { simt::block_barrier->wait(); }
+static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+// lanes holding the same value
+template <typename T>
+static inline unsigned __match_any_sync(unsigned, T v)
+{
+    simt::warp->slots[simt::lane] = simt::to_bits(v);
+    simt::warp->sync();
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) {
+        m |= simt::warp->slots[l] == simt::to_bits(v) ? (1u << l) : 0u;
+    }
+    simt::warp->sync();
+    return m;
+}
+static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
+static inline uint32_t atomicMin(uint32_t *p, uint32_t v)
+{
+    uint32_t old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+    }
+    return old;
+}
+static inline uint32_t atomicMax(uint32_t *p, uint32_t v)
+{
+    uint32_t old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+    }
+    return old;
+}
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v)
@@ -185,6 +218,7 @@ struct Pool {
     YieldBarrier start{kMaxBlock + 1}, finish{kMaxBlock + 1};  // kMaxBlock workers + the launching thread
     std::vector<std::thread> workers;
     Warp warps[kMaxBlock / 32];
+    YieldBarrier block_bar{kMaxBlock};  // parties = the launch's block size
     const std::function<void()> *kernel = nullptr;
     unsigned block = 0, grid = 0, block_index = 0;
     bool quit = false;
@@ -205,6 +239,7 @@ struct Pool {
                         gridDim.x = grid;
                         warp = &warps[t / 32];
                         lane = (int)(t % 32);
+                        block_barrier = &block_bar;
                         (*kernel)();
                     }
                     finish.wait();
@@ -245,6 +280,7 @@ inline void launch(unsigned grid, unsigned block, const Kernel &kernel)
     p.kernel = &fn;
     p.block = block;
     p.grid = grid;
+    p.block_bar.parties = block;
     for (unsigned b = 0; b < grid; ++b) {
         p.block_index = b;
         p.start.wait();

@@ -36,12 +36,12 @@ def translate(src: str) -> str:
         pos = i + 1
         n += 1
     out.append(src[pos:])
-    assert n == 7, f"expected 7 kernel launches in crt_cuda_core.cu, found {n}"
+    assert n == 18, f"expected 18 kernel launches in crt_cuda_core.cu, found {n}"
     return '#include "simt_env.h"\n' + "".join(out)
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(CSRC, f) for f in ("crt_cuda_core.cu", "kernels.cuh", "shade_math.cuh", "bvh8_traverse.h", "simt_env.h",
+    srcs = [os.path.join(CSRC, f) for f in ("crt_cuda_core.cu", "bvh8_device.cuh", "kernels.cuh", "shade_math.cuh", "bvh8_traverse.h", "simt_env.h",
                                             "host_scene.cpp", "bvh8_build.cpp")] + [os.path.join(HERE, "cuda_emu.cpp"), __file__]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB

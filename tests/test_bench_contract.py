@@ -83,11 +83,11 @@ torch.cuda.synchronize = lambda d=None: None
 import chameleonrt_b200.backend as backend
 backend._LIB_PATH, backend._lib = {lib!r}, None
 import bench
-sys.argv = ["bench.py", "--workload", "dev", "--steps", "2", "--warmup", "3"]
+sys.argv = ["bench.py"] + (sys.argv[1:] or ["--workload", "dev", "--steps", "2", "--warmup", "3"])
 bench.main()
 ''')
     r = subprocess.run([sys.executable, str(driver)], capture_output=True, text=True, cwd=ROOT, timeout=900,
-                       env=dict(os.environ, CRT_BENCH_REF_BUDGET="2"))
+                       env=dict(os.environ, CRT_BENCH_REF_BUDGET="2", CRT_BENCH_PROBE_SCRIPT=str(driver)))
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, r.stdout
@@ -102,6 +102,11 @@ bench.main()
     assert rf["kernel"] == "k_traverse" and rf["bound"] == "hbm" and rf["achieved"] > 0 and 0 < rf["frac"] and rf["closest"]["nodes_per_ray"] > 0
     assert d["e2e"]["value"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 128 * 48 * 4 + 36 * 4
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] > 0
+    # the set_scene probe (child process): host-built and device-built BVH8, same frames
+    ss = d["set_scene"]
+    assert "error" not in ss, ss
+    assert ss["frames_bit_identical"] is True and ss["triangles"] == 34
+    assert ss["host"]["set_scene_ms"] > 0 and ss["device"]["bvh8_nodes"] >= 1 and ss["device"]["closest_nodes_per_ray"] > 0
 
 
 def test_gpu_arm_dry_run_two_ranks(built, tmp_path):

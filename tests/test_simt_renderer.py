@@ -159,3 +159,18 @@ def test_graft_entry_smoke_on_the_emulated_renderer(mods, capsys):
 
     g.smoke()
     assert "pixels within tol=1.00000" in capsys.readouterr().out
+
+
+def test_device_bvh_builder_on_the_emulated_renderer(mods, gpu_tests):
+    """set_scene with bvh_builder="device" (bvh8_device.cuh: Morton keys, the hand-written radix sort and scans, Karras
+    hierarchy, refit + collapse DP with inter-block atomics, level-wise BVH8 emission) executed under the SIMT
+    emulation: frames bit-identical to the host-built tree's, and the edge cases of the GPU test."""
+    from chameleonrt_b200.scenes import cornell_box, rungholt_like, san_miguel_like, sponza_like
+
+    cases = [("cornell", lambda: cornell_box(spp=2), 40, 40, 2, 5),
+             ("sponza", lambda: sponza_like(spp=1, detail=0.2, tex_size=32), 48, 32, 1, 8),
+             ("instances", lambda: san_miguel_like(spp=1, scale=0.02, tex_size=32), 48, 32, 1, 5)]
+    if FULL:
+        cases.append(("voxels", lambda: rungholt_like(spp=1, scale=0.1), 48, 32, 1, 5))
+    gpu_tests.test_device_built_bvh_renders_the_same_image(mods, cases)
+    gpu_tests.test_device_built_bvh_edge_cases(mods, big=4099 if FULL else 2500)
