@@ -41,7 +41,7 @@ RenderCUDA::RenderCUDA()
     check(crtc_create(&renderer, static_cast<int>(env_or("CRT_CUDA_DEVICE", 0))));
     check(crtc_set_option(renderer, "max_depth", env_or("CRT_CUDA_MAX_DEPTH", 5)));
     check(crtc_set_option(renderer, "bvh_threads", env_or("CRT_CUDA_BVH_THREADS", 0)));
-    check(crtc_set_option(renderer, "bvh_builder", env_or("CRT_CUDA_BVH_BUILDER", 0)));  // 1 = build on the device
+    check(crtc_set_option(renderer, "bvh_builder", env_or("CRT_CUDA_BVH_BUILDER", 0)));  // 1 / 2 = build on the device (crt_cuda.h)
     check(crtc_set_option(renderer, "any_far_first", env_or("CRT_CUDA_ANY_FAR_FIRST", 2)));  // crt_cuda.h; 2 = per scene
 }
 

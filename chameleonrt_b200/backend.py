@@ -102,19 +102,22 @@ class RenderCUDA:
                          ("count_traversal", int(count_traversal)), ("bvh_threads", bvh_threads)):
             self._check(self.lib.crtc_set_option(self.h, key.encode(), val))
         # developer knobs of the traversal kernels (defaults are the tuned values)
-        for env, key in (("CRT_CUDA_REFILL_IDLE", "refill_idle"), ("CRT_CUDA_ANY_FAR_FIRST", "any_far_first")):
+        for env, key in (("CRT_CUDA_REFILL_IDLE", "refill_idle"), ("CRT_CUDA_ANY_FAR_FIRST", "any_far_first"),
+                         ("CRT_CUDA_PLOC_RADIUS", "bvh_ploc_radius")):
             if os.environ.get(env):
                 self._check(self.lib.crtc_set_option(self.h, key.encode(), int(os.environ[env])))
         if any_far_first is not None:  # 0 / 1 / 2 = auto: traversal order of shadow rays; never changes a result (crt_cuda.h)
             self._check(self.lib.crtc_set_option(self.h, b"any_far_first", int(any_far_first)))
-        # where set_scene builds the BVH8: "host" (binned SAH, the default) or "device" (LBVH on the GPU: faster
-        # set_scene, a somewhat slower tree); the rendered image is the same either way (crt_cuda.h)
+        # where set_scene builds the BVH8: "host" (binned SAH, the default), "device" (PLOC on the GPU: much faster
+        # set_scene, a somewhat slower tree) or "device_lbvh" (plain Morton-order LBVH: faster still, slower tree);
+        # the rendered image is the same in every case (crt_cuda.h)
         bvh_builder = bvh_builder or os.environ.get("CRT_CUDA_BVH_BUILDER")
         if bvh_builder is not None:
-            bvh_builder = {"0": "host", "1": "device"}.get(str(bvh_builder), bvh_builder)  # the plugin's env var is numeric
-            if bvh_builder not in ("host", "device"):
-                raise ValueError("bvh_builder must be 'host' or 'device'")
-            self._check(self.lib.crtc_set_option(self.h, b"bvh_builder", 1 if bvh_builder == "device" else 0))
+            names = ("host", "device", "device_lbvh")
+            bvh_builder = {"0": names[0], "1": names[1], "2": names[2]}.get(str(bvh_builder), bvh_builder)  # the plugin's env var is numeric
+            if bvh_builder not in names:
+                raise ValueError(f"bvh_builder must be one of {names}")
+            self._check(self.lib.crtc_set_option(self.h, b"bvh_builder", names.index(bvh_builder)))
         if stream is not None:
             self._check(self.lib.crtc_set_stream(self.h, C.c_void_p(stream)))
         self.width = self.height = 0

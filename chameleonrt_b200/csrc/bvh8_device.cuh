@@ -2,15 +2,20 @@
 //
 // Replaces, like bvh8_build.cpp, what the reference delegates to Embree / OptiX (rtcCommitScene,
 // backends/embree/embree_utils.cpp:75,128; optixAccelBuild + compaction, backends/optix/optix_utils.cpp:183-245).
-// The host builder (binned SAH) stays the default: it makes the better tree; this one makes set_scene fast —
-// a handful of streaming passes over the triangles instead of seconds of host work on C3 / C4 / C5.
+// The host builder (binned SAH) stays the default: it makes the better tree; these make set_scene fast —
+// streaming passes over the triangles instead of seconds of host work on C3 / C4 / C5.
 //
 //   1. k_lbvh_bounds     triangle boxes + bounds of the centroids (ordered-int atomics)
 //   2. k_lbvh_keys       63-bit Morton code of each centroid (21 bits per axis)
 //   3. radix sort        8 passes of 8 bits over (key, triangle): k_radix_hist -> scan -> k_radix_scatter (stable)
-//   4. k_lbvh_hierarchy  Karras 2012: every internal node finds its key range and split independently
-//   5. k_lbvh_refit      bottom-up (second arrival at a node proceeds): boxes AND the 8-wide collapse's dynamic
-//                        programme (Ylitie et al. 2017 §4.1, the same recurrences as Collapser::run in bvh8_build.cpp)
+//   4. the binary tree over the sorted triangles, one of
+//      PLOC (bvh_builder = 1; Meister & Bittner 2018): repeat { k_ploc_nn: every cluster finds its nearest neighbour
+//        (smallest merged surface area) among the 2 x 16 clusters around it in Morton order; k_ploc_mark -> scan ->
+//        k_ploc_merge: mutual nearest neighbours become a node, the cluster array is compacted } until one is left
+//      LBVH (bvh_builder = 2; Karras 2012): k_lbvh_hierarchy, every internal node finds its key range and split
+//        independently, then k_lbvh_refit bottom-up (the second arrival at a node proceeds)
+//   5. with every node, as it is made: its box AND the 8-wide collapse's dynamic programme (collapse_dp: Ylitie et al.
+//      2017 §4.1, the same recurrences as Collapser::run in bvh8_build.cpp)
 //   6. per BVH8 level    k_plan_level (children of each node from the DP decisions, octant slot assignment, counts)
 //                        -> scan -> k_emit_level (quantised node, next level's work list, leaf triangle order)
 //   7. k_pack_leaf_order triangle + shading records in leaf order (= pack_triangles of host_scene.cpp)
@@ -34,18 +39,19 @@ constexpr uint32_t kB2Invalid = 0xffffffffu;
 constexpr float kDevPrimCost = 0.3f, kDevNodeCost = 1.0f;  // = kPrimCost, kNodeCost of bvh8_build.cpp
 typedef unsigned long long u64;
 
-// BVH2 node ids: internal nodes 0 .. n-2 (0 = root), leaf j (j-th triangle in Morton order) = n-1+j.
+// BVH2 node ids: leaf j (the j-th triangle in Morton order) = j, internal node k = n + k, k in [0, n-1).
+// LBVH: internal node 0 is the root; PLOC: nodes are numbered as they are made, the last one (n-2) is the root.
 struct Lbvh {
     uint32_t n;
     const float *verts;        // 9 floats per triangle, input order
     float4 *tri_lo, *tri_hi;   // per input triangle
     uint32_t *cbounds;         // 6 ordered uints: centroid min xyz, max xyz
-    uint2 *children;           // per internal node
-    uint32_t *parent;          // per node (2n-1)
-    float4 *box_lo, *box_hi;   // per node; box_lo.w = bits(triangle count)
-    uint32_t *arrivals;        // per internal node
-    float *cost;               // 7 per node
-    uint8_t *decision;         // 7 per node: type | dist_left << 2 | dist_right << 5
+    uint2 *children;           // per internal node (index k)
+    uint32_t *parent;          // per node id (2n-1); LBVH only
+    float4 *box_lo, *box_hi;   // per node id; box_lo.w = bits(triangle count)
+    uint32_t *arrivals;        // per internal node (index k); LBVH only
+    float *cost;               // 7 per node id
+    uint8_t *decision;         // 7 per node id: type | dist_left << 2 | dist_right << 5
 };
 
 __device__ __forceinline__ uint32_t ordered_from_float(float f)
@@ -294,19 +300,19 @@ __global__ void __launch_bounds__(kBuildBlock) k_lbvh_hierarchy(Lbvh b, const u6
         } while (t > 1);
         const int gamma = i + s * d + min(d, 0);
         const int first = min(i, j), last = max(i, j);
-        const uint32_t left = first == gamma ? (uint32_t)(n - 1 + gamma) : (uint32_t)gamma;
-        const uint32_t right = last == gamma + 1 ? (uint32_t)(n - 1 + gamma + 1) : (uint32_t)(gamma + 1);
+        const uint32_t left = first == gamma ? (uint32_t)gamma : (uint32_t)(n + gamma);
+        const uint32_t right = last == gamma + 1 ? (uint32_t)(gamma + 1) : (uint32_t)(n + gamma + 1);
         b.children[i] = make_uint2(left, right);
-        b.parent[left] = (uint32_t)i;
-        b.parent[right] = (uint32_t)i;
+        b.parent[left] = (uint32_t)(n + i);
+        b.parent[right] = (uint32_t)(n + i);
         b.arrivals[i] = 0u;
         if (i == 0) {
-            b.parent[0] = kB2Invalid;
+            b.parent[n] = kB2Invalid;
         }
     }
 }
 
-// ---- 5. refit + collapse DP, bottom-up ----
+// ---- 5. boxes + collapse DP ----
 __device__ __forceinline__ float box_half_area(const float4 lo, const float4 hi)
 {
     const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
@@ -318,89 +324,180 @@ __device__ __forceinline__ uint8_t make_decision(uint8_t type, int dl, int dr)
     return (uint8_t)(type | (dl << 2) | (dr << 5));
 }
 
-__global__ void __launch_bounds__(kBuildBlock) k_lbvh_refit(Lbvh b, const uint32_t *vals)
+// leaf j = the j-th triangle in Morton order; also the initial cluster list of PLOC
+__global__ void __launch_bounds__(kBuildBlock) k_bvh2_leaves(Lbvh b, const uint32_t *vals, uint32_t *clusters)
+{
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < b.n; j += gridDim.x * blockDim.x) {
+        const uint32_t t = vals[j];
+        float4 lo = b.tri_lo[t];
+        const float4 hi = b.tri_hi[t];
+        lo.w = __uint_as_float(1u);
+        b.box_lo[j] = lo;
+        b.box_hi[j] = hi;
+        const float c = box_half_area(lo, hi) * kDevPrimCost;
+        for (int i = 0; i < 7; ++i) {
+            b.cost[7 * (size_t)j + i] = c;
+            b.decision[7 * (size_t)j + i] = make_decision(kDecLeaf, 0, 0);
+        }
+        if (clusters) {
+            clusters[j] = j;
+        }
+    }
+}
+
+// Node p over the finished subtrees l and r: box, triangle count, and cost[i] = the cheapest way to represent the
+// subtree as a forest of at most i+1 BVH8 children, with the decision that achieves it.
+__device__ __forceinline__ void collapse_dp(const Lbvh &b, uint32_t p, uint32_t l, uint32_t r)
+{
+    const float4 llo = b.box_lo[l], lhi = b.box_hi[l], rlo = b.box_lo[r], rhi = b.box_hi[r];
+    const uint32_t cnt = __float_as_uint(llo.w) + __float_as_uint(rlo.w);
+    const float4 lo = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), __uint_as_float(cnt));
+    const float4 hi = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
+    b.box_lo[p] = lo;
+    b.box_hi[p] = hi;
+    const float area = box_half_area(lo, hi);
+    float cl[7], cr[7], cn[7];
+    uint8_t dn[7];
+    for (int i = 0; i < 7; ++i) {
+        cl[i] = b.cost[7 * (size_t)l + i];
+        cr[i] = b.cost[7 * (size_t)r + i];
+    }
+    {
+        // i = 0: a single root — a leaf (<= 3 triangles) or an internal node whose 8 slots go to the two subtrees
+        const float inf = __uint_as_float(0x7f800000u);
+        const float cost_leaf = cnt <= 3u ? area * (float)cnt * kDevPrimCost : inf;
+        float best = inf;
+        int bl = 0, br = 0;
+        for (int k = 0; k < 7; ++k) {
+            const float c = cl[k] + cr[6 - k];
+            if (c < best) {
+                best = c;
+                bl = k;
+                br = 6 - k;
+            }
+        }
+        const float cost_internal = best + area * kDevNodeCost;
+        if (cost_leaf < cost_internal) {
+            cn[0] = cost_leaf;
+            dn[0] = make_decision(kDecLeaf, 0, 0);
+        } else {
+            cn[0] = cost_internal;
+            dn[0] = make_decision(kDecInternal, bl, br);
+        }
+    }
+    for (int i = 1; i < 7; ++i) {  // a forest of up to i+1 roots
+        cn[i] = cn[i - 1];
+        dn[i] = dn[i - 1];
+        for (int k = 0; k < i; ++k) {
+            const float c = cl[k] + cr[i - k - 1];
+            if (c < cn[i]) {
+                cn[i] = c;
+                dn[i] = make_decision(kDecDistribute, k, i - k - 1);
+            }
+        }
+    }
+    for (int i = 0; i < 7; ++i) {
+        b.cost[7 * (size_t)p + i] = cn[i];
+        b.decision[7 * (size_t)p + i] = dn[i];
+    }
+}
+
+// LBVH: bottom-up from every leaf; the second thread to arrive at a node finds both subtrees finished
+__global__ void __launch_bounds__(kBuildBlock) k_lbvh_refit(Lbvh b)
 {
     const uint32_t n = b.n;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        uint32_t id = n - 1 + j;
-        {
-            const uint32_t t = vals[j];
-            float4 lo = b.tri_lo[t];
-            const float4 hi = b.tri_hi[t];
-            lo.w = __uint_as_float(1u);
-            b.box_lo[id] = lo;
-            b.box_hi[id] = hi;
-            const float c = box_half_area(lo, hi) * kDevPrimCost;
-            for (int i = 0; i < 7; ++i) {
-                b.cost[7 * (size_t)id + i] = c;
-                b.decision[7 * (size_t)id + i] = make_decision(kDecLeaf, 0, 0);
-            }
-        }
-        if (n == 1) {
-            b.parent[0] = kB2Invalid;
-            break;
-        }
-        uint32_t p = b.parent[id];
+        uint32_t p = b.parent[j];
         while (p != kB2Invalid) {
             __threadfence();  // publish this subtree before announcing it
-            if (atomicAdd(&b.arrivals[p], 1u) == 0u) {
+            if (atomicAdd(&b.arrivals[p - n], 1u) == 0u) {
                 break;  // the sibling subtree is not finished: its thread will continue from here
             }
             __threadfence();
-            const uint2 ch = b.children[p];
-            const float4 llo = b.box_lo[ch.x], lhi = b.box_hi[ch.x], rlo = b.box_lo[ch.y], rhi = b.box_hi[ch.y];
-            const uint32_t cnt = __float_as_uint(llo.w) + __float_as_uint(rlo.w);
-            float4 lo = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), __uint_as_float(cnt));
-            const float4 hi = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
-            b.box_lo[p] = lo;
-            b.box_hi[p] = hi;
-            // cost[i] = cheapest way to represent this subtree as a forest of at most i+1 BVH8 children
-            const float area = box_half_area(lo, hi);
-            float cl[7], cr[7], cn[7];
-            uint8_t dn[7];
-            for (int i = 0; i < 7; ++i) {
-                cl[i] = b.cost[7 * (size_t)ch.x + i];
-                cr[i] = b.cost[7 * (size_t)ch.y + i];
-            }
-            {
-                const float inf = __uint_as_float(0x7f800000u);
-                const float cost_leaf = cnt <= 3u ? area * (float)cnt * kDevPrimCost : inf;
-                float best = inf;
-                int bl = 0, br = 0;
-                for (int k = 0; k < 7; ++k) {
-                    const float c = cl[k] + cr[6 - k];
-                    if (c < best) {
-                        best = c;
-                        bl = k;
-                        br = 6 - k;
-                    }
-                }
-                const float cost_internal = best + area * kDevNodeCost;
-                if (cost_leaf < cost_internal) {
-                    cn[0] = cost_leaf;
-                    dn[0] = make_decision(kDecLeaf, 0, 0);
-                } else {
-                    cn[0] = cost_internal;
-                    dn[0] = make_decision(kDecInternal, bl, br);
-                }
-            }
-            for (int i = 1; i < 7; ++i) {
-                cn[i] = cn[i - 1];
-                dn[i] = dn[i - 1];
-                for (int k = 0; k < i; ++k) {
-                    const float c = cl[k] + cr[i - k - 1];
-                    if (c < cn[i]) {
-                        cn[i] = c;
-                        dn[i] = make_decision(kDecDistribute, k, i - k - 1);
-                    }
-                }
-            }
-            for (int i = 0; i < 7; ++i) {
-                b.cost[7 * (size_t)p + i] = cn[i];
-                b.decision[7 * (size_t)p + i] = dn[i];
-            }
+            const uint2 ch = b.children[p - n];
+            collapse_dp(b, p, ch.x, ch.y);
             p = b.parent[p];
         }
+    }
+}
+
+// ---- PLOC ----
+constexpr int kPlocRadius = 16, kPlocMaxRadius = 32;
+
+// nn[i] = the cluster within `radius` (<= kPlocMaxRadius) positions of i whose union with i has the smallest surface area (ties: the
+// lower position, so that the relation is symmetric and some pair is always mutual). forced: pair up neighbours
+// (i ^ 1) regardless of distance — the way out if an adversarial input makes the mutual pairs too few.
+__global__ void __launch_bounds__(kBuildBlock) k_ploc_nn(Lbvh b, const uint32_t *clusters, uint32_t m, uint32_t *nn, int radius,
+                                                         int forced)
+{
+    __shared__ float4 slo[kBuildBlock + 2 * kPlocMaxRadius], shi[kBuildBlock + 2 * kPlocMaxRadius];
+    const int block_first = (int)(blockIdx.x * blockDim.x) - radius;
+    for (int k = threadIdx.x; k < kBuildBlock + 2 * radius; k += blockDim.x) {
+        const int pos = block_first + k;
+        if (pos >= 0 && pos < (int)m) {
+            const uint32_t c = clusters[pos];
+            slo[k] = b.box_lo[c];
+            shi[k] = b.box_hi[c];
+        }
+    }
+    __syncthreads();
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i < (int)m) {
+        uint32_t best_j = (uint32_t)i;
+        if (forced) {
+            best_j = (uint32_t)(i ^ 1) < m ? (uint32_t)(i ^ 1) : (uint32_t)i;
+        } else {
+            const float4 lo = slo[threadIdx.x + radius], hi = shi[threadIdx.x + radius];
+            float best = __uint_as_float(0x7f800000u);
+            const int j0 = max(i - radius, 0), j1 = min(i + radius, (int)m - 1);
+            for (int j = j0; j <= j1; ++j) {
+                if (j == i) {
+                    continue;
+                }
+                const float4 ol = slo[j - block_first], oh = shi[j - block_first];
+                const float4 ul = make_float4(fminf(lo.x, ol.x), fminf(lo.y, ol.y), fminf(lo.z, ol.z), 0.f);
+                const float4 uh = make_float4(fmaxf(hi.x, oh.x), fmaxf(hi.y, oh.y), fmaxf(hi.z, oh.z), 0.f);
+                const float a = box_half_area(ul, uh);
+                if (a < best || best_j == (uint32_t)i) {  // (the second test also takes a NaN / inf area)
+                    best = a;
+                    best_j = (uint32_t)j;
+                }
+            }
+        }
+        nn[i] = best_j;
+    }
+    __syncthreads();
+}
+
+// counts[i] = (cluster i survives this round) << 32 | (cluster i is the lower half of a merging pair)
+__global__ void __launch_bounds__(kBuildBlock) k_ploc_mark(const uint32_t *nn, uint32_t m, u64 *counts)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const uint32_t j = nn[i];
+        const bool mutual = j != i && nn[j] == i;
+        counts[i] = ((u64)(mutual && j < i ? 0u : 1u) << 32) | (mutual && i < j ? 1u : 0u);
+    }
+}
+
+__global__ void __launch_bounds__(kBuildBlock) k_ploc_merge(Lbvh b, const uint32_t *clusters, const uint32_t *nn, uint32_t m,
+                                                            const u64 *offsets, uint32_t nodes_made, uint32_t *clusters_out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const uint32_t j = nn[i];
+        const bool mutual = j != i && nn[j] == i;
+        if (mutual && j < i) {
+            continue;  // merged into position j
+        }
+        const u64 off = offsets[i];
+        uint32_t c = clusters[i];
+        if (mutual) {
+            const uint32_t k = nodes_made + (uint32_t)off;  // internal node index
+            const uint32_t other = clusters[j];
+            b.children[k] = make_uint2(c, other);
+            collapse_dp(b, b.n + k, c, other);
+            c = b.n + k;
+        }
+        clusters_out[(uint32_t)(off >> 32)] = c;
     }
 }
 
@@ -419,7 +516,7 @@ struct LevelArgs {
     uint32_t *tri_order;    // leaf order -> input triangle
 };
 
-__device__ __forceinline__ bool lbvh_is_leaf(const Lbvh &b, uint32_t node) { return node >= b.n - 1u; }
+__device__ __forceinline__ bool lbvh_is_leaf(const Lbvh &b, uint32_t node) { return node < b.n; }
 __device__ __forceinline__ bool lbvh_leaf_child(const Lbvh &b, uint32_t node)
 {
     return lbvh_is_leaf(b, node) || (b.decision[7 * (size_t)node] & 3u) == kDecLeaf;
@@ -449,7 +546,7 @@ __global__ void __launch_bounds__(kBuildBlock) k_plan_level(Lbvh b, LevelArgs lv
                     continue;
                 }
                 const uint8_t d = b.decision[7 * (size_t)nd + st_i[sp]];
-                const uint2 ch = b.children[nd];
+                const uint2 ch = b.children[nd - b.n];
                 const uint8_t dl = (d >> 2) & 7u, dr = (d >> 5) & 7u;
                 const bool expand_l = (b.decision[7 * (size_t)ch.x + dl] & 3u) == kDecDistribute;
                 const bool expand_r = (b.decision[7 * (size_t)ch.y + dr] & 3u) == kDecDistribute;
@@ -577,14 +674,19 @@ __global__ void __launch_bounds__(kBuildBlock) k_emit_level(Lbvh b, LevelArgs lv
                     qhi[a] = (uint8_t)hi;
                 }
                 if (lbvh_leaf_child(b, cn)) {
-                    // the <= 3 triangles under cn, left to right (they are consecutive in Morton order)
-                    uint32_t first = cn;
-                    while (!lbvh_is_leaf(b, first)) {
-                        first = b.children[first].x;
-                    }
-                    const uint32_t k = __float_as_uint(clo.w);
-                    for (uint32_t t = 0; t < k; ++t) {
-                        lv.tri_order[tri_base + tri_off + t] = vals[first - (b.n - 1u) + t];
+                    // the <= 3 triangles under cn, left to right
+                    uint32_t st[4], k = 0u;
+                    int sp = 0;
+                    st[sp++] = cn;
+                    while (sp) {
+                        const uint32_t c = st[--sp];
+                        if (lbvh_is_leaf(b, c)) {
+                            lv.tri_order[tri_base + tri_off + k++] = vals[c];
+                        } else {
+                            const uint2 ch = b.children[c - b.n];
+                            st[sp++] = ch.y;
+                            st[sp++] = ch.x;
+                        }
                     }
                     meta = (uint8_t)(((k == 1u ? 0b001u : (k == 2u ? 0b011u : 0b111u)) << 5) | tri_off);
                     tri_off += k;

@@ -118,7 +118,9 @@ struct crtc_renderer {
     int max_depth = 5;
     int rank = 0, world_size = 1;
     int bvh_threads = 0;
-    int bvh_builder = 0;  // 0 = host (binned SAH, bvh8_build.cpp), 1 = device (LBVH, bvh8_device.cuh)
+    int bvh_builder = 0;  // 0 = host (binned SAH, bvh8_build.cpp); on the device (bvh8_device.cuh): 1 = PLOC, 2 = LBVH
+    int build_rounds = 0;
+    int ploc_radius = crt::kPlocRadius;
     bool count_traversal = false;
     int refill_idle = crt::kRefillIdle;  // idle lanes that trigger a refill of the traversal warps
     // Shadow rays visit the children of a node farthest-first: 0 = no, 1 = yes, 2 = auto (default) — frame 1
@@ -376,7 +378,8 @@ struct crtc_renderer {
         const uint32_t num_b2 = 2 * n - 1, max_nodes = std::max(1u, n - 1);
         DeviceBuffer<float> d_verts;
         DeviceBuffer<float4> d_shade_in, tri_lo, tri_hi, box_lo, box_hi, nodes_tmp;
-        DeviceBuffer<uint32_t> cbounds, vals0, vals1, hist, d_parent, arrivals, slots, work0, work1, tri_order;
+        DeviceBuffer<uint32_t> cbounds, vals0, vals1, hist, d_parent, arrivals, slots, work0, work1, tri_order, clusters0,
+            clusters1, nn;
         DeviceBuffer<crt::u64> keys0, keys1, counts, offsets, scan_scratch;
         DeviceBuffer<uint2> d_children;
         DeviceBuffer<float> cost;
@@ -405,9 +408,9 @@ struct crtc_renderer {
         slots.alloc((size_t)max_nodes * 8);
         work0.alloc(max_nodes);
         work1.alloc(max_nodes);
-        counts.alloc(max_nodes);
-        offsets.alloc(max_nodes);
-        scan_scratch.alloc(std::max(scan_scratch_items(max_nodes), (scan_scratch_items((size_t)tiles * 256) + 1) / 2 + 1));
+        counts.alloc(n);
+        offsets.alloc(n);
+        scan_scratch.alloc(std::max(scan_scratch_items(n), (scan_scratch_items((size_t)tiles * 256) + 1) / 2 + 1));
         nodes_tmp.alloc((size_t)max_nodes * 5);
         tri_order.alloc(n);
 
@@ -436,55 +439,95 @@ struct crtc_renderer {
             std::swap(kin, kout);
             std::swap(vin, vout);
         }
-        if (n > 1) {
-            crt::k_lbvh_hierarchy<<<grid_for(n - 1), crt::kBuildBlock, 0, stream>>>(b, kin);
+        crt::u64 *h_tail = nullptr;  // pinned: last offset + last count of a scan = its total
+        CUDA_CHECK(cudaMallocHost(&h_tail, 2 * sizeof(crt::u64)));
+        struct FreeHost {
+            void *p;
+            ~FreeHost() { cudaFreeHost(p); }
+        } free_tail{h_tail};
+        auto scan_total = [&](uint32_t items) {  // enqueue after device_scan(counts -> offsets); valid after a sync
+            CUDA_CHECK(cudaMemcpyAsync(h_tail, offsets.ptr + (items - 1), sizeof(crt::u64), cudaMemcpyDeviceToHost, stream));
+            CUDA_CHECK(cudaMemcpyAsync(h_tail + 1, counts.ptr + (items - 1), sizeof(crt::u64), cudaMemcpyDeviceToHost, stream));
+        };
+        uint32_t root = 0u;  // a single triangle: the leaf is the root
+        if (bvh_builder == 2) {
+            crt::k_bvh2_leaves<<<g, crt::kBuildBlock, 0, stream>>>(b, vin, nullptr);
+            if (n > 1) {
+                crt::k_lbvh_hierarchy<<<grid_for(n - 1), crt::kBuildBlock, 0, stream>>>(b, kin);
+                crt::k_lbvh_refit<<<g, crt::kBuildBlock, 0, stream>>>(b);
+                root = n;
+            }
+        } else {
+            clusters0.alloc(n);
+            clusters1.alloc(n);
+            nn.alloc(n);
+            uint32_t *cl = clusters0.ptr, *cl_next = clusters1.ptr;
+            crt::k_bvh2_leaves<<<g, crt::kBuildBlock, 0, stream>>>(b, vin, cl);
+            uint32_t m = n, nodes_made = 0;
+            build_rounds = 0;
+            while (m > 1) {
+                // (an adversarial input can leave one mutual pair per round; after 256 rounds neighbours are paired up)
+                const int forced = build_rounds >= 256 ? 1 : 0;
+                const unsigned gm = (m + crt::kBuildBlock - 1) / crt::kBuildBlock;
+                crt::k_ploc_nn<<<gm, crt::kBuildBlock, 0, stream>>>(b, cl, m, nn.ptr, ploc_radius, forced);
+                crt::k_ploc_mark<<<grid_for(m), crt::kBuildBlock, 0, stream>>>(nn.ptr, m, counts.ptr);
+                device_scan<crt::u64>(counts.ptr, offsets.ptr, m, scan_scratch.ptr);
+                scan_total(m);
+                crt::k_ploc_merge<<<grid_for(m), crt::kBuildBlock, 0, stream>>>(b, cl, nn.ptr, m, offsets.ptr, nodes_made, cl_next);
+                CUDA_CHECK(cudaStreamSynchronize(stream));
+                const crt::u64 total = h_tail[0] + h_tail[1];
+                const uint32_t merged = (uint32_t)total, left = (uint32_t)(total >> 32);
+                if (merged == 0 || left + merged != m) {
+                    throw std::runtime_error("device BVH build: a PLOC round made no progress");
+                }
+                nodes_made += merged;
+                m = left;
+                std::swap(cl, cl_next);
+                ++build_rounds;
+            }
+            if (n > 1) {
+                if (nodes_made != n - 1) {
+                    throw std::runtime_error("device BVH build: PLOC made " + std::to_string(nodes_made) + " of " +
+                                             std::to_string(n - 1) + " nodes");
+                }
+                root = n + (n - 2);
+            }
         }
-        crt::k_lbvh_refit<<<g, crt::kBuildBlock, 0, stream>>>(b, vin);
 
         // BVH8 levels: the host only learns each level's size
-        const uint32_t root = 0u;
         CUDA_CHECK(cudaMemcpyAsync(work0.ptr, &root, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
         uint32_t *work = work0.ptr, *next_work = work1.ptr;
         uint32_t node_begin = 0, count = 1, tri_total = 0;
         depth = 0;
-        crt::u64 *h_tail = nullptr;  // pinned: last offset, last count of the level
-        CUDA_CHECK(cudaMallocHost(&h_tail, 2 * sizeof(crt::u64)));
-        try {
-            while (count) {
-                ++depth;
-                if ((size_t)node_begin + count > max_nodes) {
-                    throw std::runtime_error("device BVH build: node count exceeds its bound");
-                }
-                crt::LevelArgs lv;
-                lv.work = work;
-                lv.count = count;
-                lv.node_begin = node_begin;
-                lv.next_begin = node_begin + count;
-                lv.tri_begin = tri_total;
-                lv.slots = slots.ptr;
-                lv.counts = counts.ptr;
-                lv.offsets = offsets.ptr;
-                lv.next_work = next_work;
-                lv.nodes = reinterpret_cast<crt::Bvh8Node *>(nodes_tmp.ptr);
-                lv.tri_order = tri_order.ptr;
-                const unsigned gl = grid_for(count);
-                crt::k_plan_level<<<gl, crt::kBuildBlock, 0, stream>>>(b, lv);
-                device_scan<crt::u64>(counts.ptr, offsets.ptr, count, scan_scratch.ptr);
-                CUDA_CHECK(cudaMemcpyAsync(h_tail, offsets.ptr + (count - 1), sizeof(crt::u64), cudaMemcpyDeviceToHost, stream));
-                CUDA_CHECK(cudaMemcpyAsync(h_tail + 1, counts.ptr + (count - 1), sizeof(crt::u64), cudaMemcpyDeviceToHost, stream));
-                crt::k_emit_level<<<gl, crt::kBuildBlock, 0, stream>>>(b, lv, vin);
-                CUDA_CHECK(cudaStreamSynchronize(stream));
-                const crt::u64 total = h_tail[0] + h_tail[1];
-                node_begin += count;
-                count = (uint32_t)(total >> 32);
-                tri_total += (uint32_t)total;
-                std::swap(work, next_work);
+        while (count) {
+            ++depth;
+            if ((size_t)node_begin + count > max_nodes) {
+                throw std::runtime_error("device BVH build: node count exceeds its bound");
             }
-        } catch (...) {
-            cudaFreeHost(h_tail);
-            throw;
+            crt::LevelArgs lv;
+            lv.work = work;
+            lv.count = count;
+            lv.node_begin = node_begin;
+            lv.next_begin = node_begin + count;
+            lv.tri_begin = tri_total;
+            lv.slots = slots.ptr;
+            lv.counts = counts.ptr;
+            lv.offsets = offsets.ptr;
+            lv.next_work = next_work;
+            lv.nodes = reinterpret_cast<crt::Bvh8Node *>(nodes_tmp.ptr);
+            lv.tri_order = tri_order.ptr;
+            const unsigned gl = grid_for(count);
+            crt::k_plan_level<<<gl, crt::kBuildBlock, 0, stream>>>(b, lv);
+            device_scan<crt::u64>(counts.ptr, offsets.ptr, count, scan_scratch.ptr);
+            scan_total(count);
+            crt::k_emit_level<<<gl, crt::kBuildBlock, 0, stream>>>(b, lv, vin);
+            CUDA_CHECK(cudaStreamSynchronize(stream));
+            const crt::u64 total = h_tail[0] + h_tail[1];
+            node_begin += count;
+            count = (uint32_t)(total >> 32);
+            tri_total += (uint32_t)total;
+            std::swap(work, next_work);
         }
-        cudaFreeHost(h_tail);
         if (tri_total != n) {
             throw std::runtime_error("device BVH build: emitted " + std::to_string(tri_total) + " of " + std::to_string(n) +
                                      " triangles");
@@ -526,7 +569,7 @@ struct crtc_renderer {
         crt::flatten_scene(scene, hs, bvh_threads);
         uint32_t bvh_nodes = 0, bvh_depth = 0;
         double bvh_ms = 0.0;
-        if (bvh_builder == 1 && hs.num_tris() > 0) {
+        if (bvh_builder != 0 && hs.num_tris() > 0) {
             build_on_device(hs, bvh_nodes, bvh_depth, bvh_ms);
         } else {
             crt::Bvh8 bvh;
@@ -1058,9 +1101,14 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
             r->world_size = (int)value;
         } else if (k == "bvh_threads") {
             r->bvh_threads = (int)value;
+        } else if (k == "bvh_ploc_radius") {
+            if (value < 1 || value > crt::kPlocMaxRadius) {
+                throw std::runtime_error("bvh_ploc_radius must be in [1, 32]");
+            }
+            r->ploc_radius = (int)value;
         } else if (k == "bvh_builder") {
-            if (value != 0 && value != 1) {
-                throw std::runtime_error("bvh_builder must be 0 (host) or 1 (device)");
+            if (value < 0 || value > 2) {
+                throw std::runtime_error("bvh_builder must be 0 (host), 1 (device, PLOC) or 2 (device, LBVH)");
             }
             r->bvh_builder = (int)value;
         } else if (k == "count_traversal") {
@@ -1102,6 +1150,8 @@ int crtc_get_option(crtc_renderer *r, const char *key, int64_t *value)
             *value = r->bvh_threads;
         } else if (k == "bvh_builder") {
             *value = r->bvh_builder;
+        } else if (k == "bvh_build_rounds") {
+            *value = r->build_rounds;  // PLOC rounds of the last device build
         } else if (k == "count_traversal") {
             *value = r->count_traversal ? 1 : 0;
         } else if (k == "refill_idle") {

@@ -58,10 +58,11 @@ void crtc_destroy(crtc_renderer *r);
  *   "rank", "world_size"  image-tile sharding: this renderer owns the 64x64 tiles with
  *                 tile_id % world_size == rank (tile_id as in render_embree.cpp:178-180)
  *   "bvh_threads" host threads for the BVH8 build (0 = all)
- *   "bvh_builder" where crtc_set_scene builds the BVH8: 0 = on the host (binned SAH, the default), 1 = on the device
- *                 (Morton-code LBVH + the same 8-wide collapse; chameleonrt_b200/csrc/bvh8_device.cuh) — a much
- *                 shorter set_scene on scenes of millions of triangles for a somewhat slower tree. Rendered frames
- *                 are bit-identical either way (closest hits break ties on the primitive id).
+ *   "bvh_builder" where crtc_set_scene builds the BVH8: 0 = on the host (binned SAH, the default); on the device
+ *                 (chameleonrt_b200/csrc/bvh8_device.cuh): 1 = PLOC (mutual nearest neighbours in Morton order),
+ *                 2 = LBVH (Karras), both followed by the host builder's 8-wide collapse — a much shorter set_scene
+ *                 on scenes of millions of triangles for a somewhat slower tree. Rendered frames are bit-identical
+ *                 in every case (closest hits break ties on the primitive id).
  *   "refill_idle" scheduling knob of the persistent traversal kernels (how many idle lanes
  *                 trigger a refill from the ray queue); the default is tuned
  *   "any_far_first" 1 = shadow (any-hit) rays visit the children of a BVH node farthest-first instead of

@@ -1,8 +1,9 @@
 """Randomised end-to-end check of the PRODUCT's renderer (crt_cuda_core.cu + kernels, through the C ABI) running on
 the CPU SIMT emulation (tests/simt_emu) against the oracle: random scenes as in fuzz_oracle_vs_reference.py (identity
 instance transforms; sheared ones only statistically), random spp / depth / frame counts / ragged sizes, frames
-rendered blocking, asynchronously and as batches, random shadow-order mode. All pixels within the parity tolerance,
-ray counts equal (NaN paths aside).   python scripts/fuzz_renderer_emulated.py [n] [first_seed]"""
+rendered blocking, asynchronously and as batches, random shadow-order mode, random BVH builder (host / device PLOC /
+device LBVH). All pixels within the parity tolerance, ray counts equal (NaN paths aside); frames over a device-built
+tree bit-identical to frames over the host-built one.   python scripts/fuzz_renderer_emulated.py [n] [first_seed]"""
 import os
 import sys
 import warnings
@@ -36,7 +37,8 @@ def one(seed):
     cpu.initialize(w, h)
     cpu.set_scene(scene)
     rays_cpu = sum(cpu.render(*view, f == 0, True).num_rays for f in range(frames))
-    gpu = backend.RenderCUDA(0, max_depth=depth, any_far_first=int(rng.integers(0, 3)))
+    builder = ("host", "device", "device_lbvh")[int(rng.integers(0, 3))]
+    gpu = backend.RenderCUDA(0, max_depth=depth, any_far_first=int(rng.integers(0, 3)), bvh_builder=builder)
     gpu.initialize(w, h)
     gpu.set_scene(scene)
     how = int(rng.integers(0, 3))
@@ -57,7 +59,13 @@ def one(seed):
     frac, rel_l1 = parity(got, want)
     ok = frac >= (0.98 if sheared else 0.999) and rel_l1 <= (5e-2 if sheared else 1e-4)
     ok = ok and (has_nan or sheared or rays == rays_cpu)
-    return ok, (frac, rel_l1, rays, rays_cpu, has_nan, sheared, how, scene.total_tris(), w, h, depth, frames, scene.samples_per_pixel)
+    if builder != "host":  # the tree must not matter, bit for bit
+        ref = backend.RenderCUDA(0, max_depth=depth, any_far_first=0, bvh_builder="host")
+        ref.initialize(w, h)
+        ref.set_scene(scene)
+        rays_ref = sum(ref.render(*view, f == 0, True).num_rays for f in range(frames))
+        ok = ok and rays_ref == rays and np.array_equal(ref.read_accum().view(np.uint32), got.view(np.uint32))
+    return ok, (frac, rel_l1, rays, rays_cpu, has_nan, sheared, how, builder, scene.total_tris(), w, h, depth, frames, scene.samples_per_pixel)
 
 
 if __name__ == "__main__":

@@ -401,24 +401,29 @@ def test_shadow_ray_order_option_does_not_change_the_image(mods):
     assert c2["any_nodes_visited"] in (c0["any_nodes_visited"], c1["any_nodes_visited"])  # auto settled on one of them
 
 
-# ---------------------------------------------------------------- set_scene on the device (bvh_builder="device")
-def _device_and_host_builders(mods, scene, w, h, frames, cam, depth=5):
+# ---------------------------------------------------------------- set_scene on the device (bvh_builder="device" / "device_lbvh")
+BUILDERS = ("host", "device", "device_lbvh")
+
+
+def _render_over_each_builder(mods, scene, w, h, frames, cam, depth=5):
     RenderCUDA = mods[0]
     out = {}
-    for b in ("host", "device"):
+    for b in BUILDERS:
         r = RenderCUDA(0, max_depth=depth, count_traversal=True, bvh_builder=b, any_far_first=0)
         r.initialize(w, h)
         r.set_scene(scene)
         st = _render(r, cam, frames)
-        out[b] = dict(r=r, accum=r.read_accum(), img=r.read_img(), rays=st.num_rays, counters=r.counters(), info=r.scene_info())
-    return out["host"], out["device"]
+        out[b] = dict(accum=r.read_accum(), img=r.read_img(), rays=st.num_rays, counters=r.counters(), info=r.scene_info(),
+                      rounds=r.get_option("bvh_build_rounds"))
+    return out
 
 
 def test_device_built_bvh_renders_the_same_image(mods, cases=None):
-    """Option bvh_builder = "device": Morton codes, radix sort, Karras hierarchy, bottom-up refit + collapse DP and
-    the level-wise BVH8 emission all run as kernels (bvh8_device.cuh). A closest hit (ties: lower flattened primitive
-    id) and an occlusion answer do not depend on the tree, so the frames must be bit-identical to the ones rendered
-    over the host-built tree — only the instrumented node / triangle counts and the set_scene time differ."""
+    """Options bvh_builder = "device" (PLOC) and "device_lbvh" (Karras): Morton codes, radix sort, the binary tree,
+    boxes + the collapse DP and the level-wise BVH8 emission all run as kernels (bvh8_device.cuh). A closest hit
+    (ties: lower flattened primitive id) and an occlusion answer do not depend on the tree, so the frames must be
+    bit-identical to the ones rendered over the host-built tree — only the instrumented node / triangle counts and
+    the set_scene time differ."""
     from chameleonrt_b200.scenes import cornell_box, rungholt_like, san_miguel_like, sponza_like
 
     cases = cases or [("cornell", lambda: cornell_box(spp=2), 128, 128, 2, 5),
@@ -427,15 +432,19 @@ def test_device_built_bvh_renders_the_same_image(mods, cases=None):
                       ("voxels", lambda: rungholt_like(spp=1, scale=0.25), 192, 108, 1, 5)]
     for name, make, w, h, frames, depth in cases:
         scene, cam = make()
-        host, dev = _device_and_host_builders(mods, scene, w, h, frames, cam, depth)
-        assert (host["accum"].view(np.uint32) == dev["accum"].view(np.uint32)).all(), name
-        assert (host["img"] == dev["img"]).all() and host["rays"] == dev["rays"], name
-        for k in ("closest_rays", "occlusion_rays", "paths"):
-            assert host["counters"][k] == dev["counters"][k], (name, k)
-        assert dev["info"]["triangles"] == host["info"]["triangles"]
-        assert 0 < dev["info"]["bvh8_nodes"] < max(2, dev["info"]["triangles"]) and dev["info"]["bvh8_depth"] <= 30
-        # an LBVH is a worse tree than binned SAH, but not arbitrarily worse
-        assert dev["counters"]["closest_nodes_visited"] < 2.0 * host["counters"]["closest_nodes_visited"], name
+        out = _render_over_each_builder(mods, scene, w, h, frames, cam, depth)
+        host = out["host"]
+        for b, worse in (("device", 1.3), ("device_lbvh", 2.0)):
+            dev = out[b]
+            assert (host["accum"].view(np.uint32) == dev["accum"].view(np.uint32)).all(), (name, b)
+            assert (host["img"] == dev["img"]).all() and host["rays"] == dev["rays"], (name, b)
+            for k in ("closest_rays", "occlusion_rays", "paths"):
+                assert host["counters"][k] == dev["counters"][k], (name, b, k)
+            assert dev["info"]["triangles"] == host["info"]["triangles"]
+            assert 0 < dev["info"]["bvh8_nodes"] < max(2, dev["info"]["triangles"]) and dev["info"]["bvh8_depth"] <= 30
+            # PLOC comes close to the binned-SAH tree, the LBVH is clearly worse — but neither arbitrarily so
+            assert dev["counters"]["closest_nodes_visited"] < worse * host["counters"]["closest_nodes_visited"] + 64, (name, b)
+        assert 0 < out["device"]["rounds"] <= 256 + 32 or host["info"]["triangles"] < 2
 
 
 def _soup_scene(verts, idx):
@@ -475,7 +484,7 @@ def test_device_built_bvh_edge_cases(mods, big=4099):
         scene = _soup_scene(verts, idx)
         rays = primary_rays(48, 48, eye, d.astype(np.float32), up, 50.0)
         res = []
-        for b in ("host", "device"):
+        for b in BUILDERS:
             r = RenderCUDA(0, bvh_builder=b)
             r.initialize(16, 16)
             r.set_scene(scene)
@@ -485,10 +494,23 @@ def test_device_built_bvh_edge_cases(mods, big=4099):
             sh[:, 3] = 1e-4
             sh[:, 7] = np.where(np.arange(len(sh)) % 2 == 0, 2.5, 1e20)
             res.append((r.trace_closest(more), r.trace_any(sh), r.scene_info()))
-        (hh, ah, ih), (hd, ad, idv) = res
-        assert (hh.view(np.uint32) == hd.view(np.uint32)).all(), len(idx)
-        assert (ah == ad).all(), len(idx)
-        assert idv["triangles"] == len(idx) and idv["bvh8_nodes"] >= 1
+        hh, ah, _ = res[0]
+        for (hd, ad, idv), b in zip(res[1:], BUILDERS[1:]):
+            assert (hh.view(np.uint32) == hd.view(np.uint32)).all(), (len(idx), b)
+            assert (ah == ad).all(), (len(idx), b)
+            assert idv["triangles"] == len(idx) and idv["bvh8_nodes"] >= 1
+    # a chain of triangles whose gaps halve: every cluster's nearest neighbour is the next one, one mutual pair per round
+    # (PLOC's worst case; after 256 rounds the builder pairs neighbours up instead)
+    k = 900
+    x = np.cumsum(0.995 ** np.arange(k)).astype(np.float32)
+    tri = np.array([[0, 0, 0], [1e-4, 0, 0], [0, 1e-4, 0]], np.float32)
+    verts = (tri[None] + np.stack([x, np.zeros(k, np.float32), np.zeros(k, np.float32)], 1)[:, None]).reshape(-1, 3)
+    r = RenderCUDA(0, bvh_builder="device")
+    r.initialize(16, 16)
+    r.set_scene(_soup_scene(verts, np.arange(3 * k, dtype=np.uint32).reshape(-1, 3)))
+    down = np.array([[x[7] + 2e-5, 2e-5, 1, 0, 0, 0, -1, 1e20], [x[k - 1] + 2e-5, 2e-5, 1, 0, 0, 0, -1, 1e20]], np.float32)
+    assert r.trace_closest(down)[:, 3].view(np.uint32).tolist() == [7, k - 1]
+    assert r.get_option("bvh_build_rounds") > 256, "the chain was meant to exhaust the mutual-pair rounds"
     # an empty scene takes the host path (nothing to sort) and renders the background
     r = RenderCUDA(0, bvh_builder="device")
     r.initialize(16, 16)
