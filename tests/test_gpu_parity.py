@@ -400,119 +400,3 @@ def test_shadow_ray_order_option_does_not_change_the_image(mods):
     assert c0["any_nodes_visited"] != c1["any_nodes_visited"]
     assert c2["any_nodes_visited"] in (c0["any_nodes_visited"], c1["any_nodes_visited"])  # auto settled on one of them
 
-
-# ---------------------------------------------------------------- set_scene on the device (bvh_builder="device" / "device_lbvh")
-BUILDERS = ("host", "device", "device_lbvh")
-
-
-def _render_over_each_builder(mods, scene, w, h, frames, cam, depth=5):
-    RenderCUDA = mods[0]
-    out = {}
-    for b in BUILDERS:
-        r = RenderCUDA(0, max_depth=depth, count_traversal=True, bvh_builder=b, any_far_first=0)
-        r.initialize(w, h)
-        r.set_scene(scene)
-        st = _render(r, cam, frames)
-        out[b] = dict(accum=r.read_accum(), img=r.read_img(), rays=st.num_rays, counters=r.counters(), info=r.scene_info(),
-                      rounds=r.get_option("bvh_build_rounds"))
-    return out
-
-
-def test_device_built_bvh_renders_the_same_image(mods, cases=None):
-    """Options bvh_builder = "device" (PLOC) and "device_lbvh" (Karras): Morton codes, radix sort, the binary tree,
-    boxes + the collapse DP and the level-wise BVH8 emission all run as kernels (bvh8_device.cuh). A closest hit
-    (ties: lower flattened primitive id) and an occlusion answer do not depend on the tree, so the frames must be
-    bit-identical to the ones rendered over the host-built tree — only the instrumented node / triangle counts and
-    the set_scene time differ."""
-    from chameleonrt_b200.scenes import cornell_box, rungholt_like, san_miguel_like, sponza_like
-
-    cases = cases or [("cornell", lambda: cornell_box(spp=2), 128, 128, 2, 5),
-                      ("sponza", lambda: sponza_like(spp=2, detail=0.5, tex_size=64), 320, 180, 2, 8),
-                      ("instances", lambda: san_miguel_like(spp=1, scale=0.05, tex_size=64), 192, 108, 1, 5),
-                      ("voxels", lambda: rungholt_like(spp=1, scale=0.25), 192, 108, 1, 5)]
-    for name, make, w, h, frames, depth in cases:
-        scene, cam = make()
-        out = _render_over_each_builder(mods, scene, w, h, frames, cam, depth)
-        host = out["host"]
-        for b, worse in (("device", 1.3), ("device_lbvh", 2.0)):
-            dev = out[b]
-            assert (host["accum"].view(np.uint32) == dev["accum"].view(np.uint32)).all(), (name, b)
-            assert (host["img"] == dev["img"]).all() and host["rays"] == dev["rays"], (name, b)
-            for k in ("closest_rays", "occlusion_rays", "paths"):
-                assert host["counters"][k] == dev["counters"][k], (name, b, k)
-            assert dev["info"]["triangles"] == host["info"]["triangles"]
-            assert 0 < dev["info"]["bvh8_nodes"] < max(2, dev["info"]["triangles"]) and dev["info"]["bvh8_depth"] <= 30
-            # PLOC comes close to the binned-SAH tree, the LBVH is clearly worse — but neither arbitrarily so
-            assert dev["counters"]["closest_nodes_visited"] < worse * host["counters"]["closest_nodes_visited"] + 64, (name, b)
-        assert 0 < out["device"]["rounds"] <= 256 + 32 or host["info"]["triangles"] < 2
-
-
-def _soup_scene(verts, idx):
-    from chameleonrt_b200.scene import DisneyMaterial, Geometry, Instance, Mesh, ParameterizedMesh, Scene, default_obj_light
-
-    return Scene(meshes=[Mesh([Geometry(np.ascontiguousarray(verts, np.float32), np.ascontiguousarray(idx, np.uint32))])],
-                 parameterized_meshes=[ParameterizedMesh(0, [0])], instances=[Instance(np.eye(4, dtype=np.float32), 0)],
-                 materials=[DisneyMaterial()], lights=[default_obj_light()])
-
-
-def test_device_built_bvh_edge_cases(mods, big=4099):
-    """1, 2, 3, 4 triangles; coincident triangles (equal Morton codes: the sorted position breaks the tie, the lower
-    primitive id wins the hit); zero-area triangles; a flat scene (two axes of the centroid bounds degenerate); counts
-    around the sort tile (2048 keys) — closest hits and occlusion against the host-built tree, ray by ray."""
-    RenderCUDA, _, primary_rays = mods
-    rng = np.random.default_rng(5)
-
-    def soup(n, flat=False, dup=False):
-        c = rng.uniform(-1, 1, (n, 1, 3)).astype(np.float32)
-        if flat:
-            c[:, :, 1] = 0.0
-        v = c + rng.normal(scale=0.15, size=(n, 3, 3)).astype(np.float32)
-        if flat:
-            v[:, :, 1] = 0.0
-        if dup:
-            v[:] = v[0]
-        if n > 5:
-            v[3, 2] = v[3, 1]  # a zero-area triangle
-        return v.reshape(-1, 3), np.arange(3 * n, dtype=np.uint32).reshape(-1, 3)
-
-    cases = [soup(1), soup(2), soup(3), soup(4), soup(9, dup=True), soup(300, flat=True), soup(2047), soup(2048), soup(2049),
-             soup(big)]
-    eye = np.array([0.1, 3.0, 0.2], np.float32)
-    d = -eye / np.linalg.norm(eye)
-    up = np.array([0, 0, 1], np.float32)
-    for verts, idx in cases:
-        scene = _soup_scene(verts, idx)
-        rays = primary_rays(48, 48, eye, d.astype(np.float32), up, 50.0)
-        res = []
-        for b in BUILDERS:
-            r = RenderCUDA(0, bvh_builder=b)
-            r.initialize(16, 16)
-            r.set_scene(scene)
-            h0 = r.trace_closest(rays)
-            more = np.concatenate([rays, bounce_rays(rays, h0, 3)])
-            sh = more.copy()
-            sh[:, 3] = 1e-4
-            sh[:, 7] = np.where(np.arange(len(sh)) % 2 == 0, 2.5, 1e20)
-            res.append((r.trace_closest(more), r.trace_any(sh), r.scene_info()))
-        hh, ah, _ = res[0]
-        for (hd, ad, idv), b in zip(res[1:], BUILDERS[1:]):
-            assert (hh.view(np.uint32) == hd.view(np.uint32)).all(), (len(idx), b)
-            assert (ah == ad).all(), (len(idx), b)
-            assert idv["triangles"] == len(idx) and idv["bvh8_nodes"] >= 1
-    # a chain of triangles whose gaps halve: every cluster's nearest neighbour is the next one, one mutual pair per round
-    # (PLOC's worst case; after 256 rounds the builder pairs neighbours up instead)
-    k = 900
-    x = np.cumsum(0.995 ** np.arange(k)).astype(np.float32)
-    tri = np.array([[0, 0, 0], [1e-4, 0, 0], [0, 1e-4, 0]], np.float32)
-    verts = (tri[None] + np.stack([x, np.zeros(k, np.float32), np.zeros(k, np.float32)], 1)[:, None]).reshape(-1, 3)
-    r = RenderCUDA(0, bvh_builder="device")
-    r.initialize(16, 16)
-    r.set_scene(_soup_scene(verts, np.arange(3 * k, dtype=np.uint32).reshape(-1, 3)))
-    down = np.array([[x[7] + 2e-5, 2e-5, 1, 0, 0, 0, -1, 1e20], [x[k - 1] + 2e-5, 2e-5, 1, 0, 0, 0, -1, 1e20]], np.float32)
-    assert r.trace_closest(down)[:, 3].view(np.uint32).tolist() == [7, k - 1]
-    assert r.get_option("bvh_build_rounds") > 256, "the chain was meant to exhaust the mutual-pair rounds"
-    # an empty scene takes the host path (nothing to sort) and renders the background
-    r = RenderCUDA(0, bvh_builder="device")
-    r.initialize(16, 16)
-    r.set_scene(_soup_scene(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32)))
-    assert r.trace_closest(rays[:4])[:, 3].view(np.uint32).tolist() == [0xFFFFFFFF] * 4

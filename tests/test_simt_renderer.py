@@ -161,7 +161,7 @@ def test_graft_entry_smoke_on_the_emulated_renderer(mods, capsys):
     assert "pixels within tol=1.00000" in capsys.readouterr().out
 
 
-def test_device_bvh_builder_on_the_emulated_renderer(mods, gpu_tests):
+def test_device_bvh_builder_on_the_emulated_renderer(mods):
     """set_scene with bvh_builder="device" (bvh8_device.cuh: Morton keys, the hand-written radix sort and scans, Karras
     hierarchy, refit + collapse DP with inter-block atomics, level-wise BVH8 emission) executed under the SIMT
     emulation: frames bit-identical to the host-built tree's, and the edge cases of the GPU test."""
@@ -172,5 +172,7 @@ def test_device_bvh_builder_on_the_emulated_renderer(mods, gpu_tests):
              ("instances", lambda: san_miguel_like(spp=1, scale=0.02, tex_size=32), 48, 32, 1, 5)]
     if FULL:
         cases.append(("voxels", lambda: rungholt_like(spp=1, scale=0.1), 48, 32, 1, 5))
-    gpu_tests.test_device_built_bvh_renders_the_same_image(mods, cases)
-    gpu_tests.test_device_built_bvh_edge_cases(mods, big=4099 if FULL else 2500)
+    import test_z_device_bvh_build as dev_tests
+
+    dev_tests.test_device_built_bvh_renders_the_same_image(mods, cases)
+    dev_tests.test_device_built_bvh_edge_cases(mods, big=4099 if FULL else 2500)
