@@ -5,6 +5,8 @@
 // The host builder (binned SAH) stays the default: it makes the better tree; these make set_scene fast —
 // streaming passes over the triangles instead of seconds of host work on C3 / C4 / C5.
 //
+//   0. k_flatten         instances -> one world-space triangle soup + per-triangle shading records (= the triangle half
+//                        of flatten_scene, host_scene.cpp; the unique meshes are uploaded once, not once per instance)
 //   1. k_lbvh_bounds     triangle boxes + bounds of the centroids (ordered-int atomics)
 //   2. k_lbvh_keys       63-bit Morton code of each centroid (21 bits per axis)
 //   3. radix sort        8 passes of 8 bits over (key, triangle): k_radix_hist -> scan -> k_radix_scatter (stable)
@@ -53,6 +55,93 @@ struct Lbvh {
     float *cost;               // 7 per node id
     uint8_t *decision;         // 7 per node id: type | dist_left << 2 | dist_right << 5
 };
+
+// ---- 0. flatten: thread per flattened triangle ----
+struct DevSegment {  // one (instance, geometry) pair with at least one triangle
+    uint32_t flat_base, num_tris;
+    uint32_t vert_off, num_verts;  // first vertex / vertex count in the vertex arena (3 floats per vertex)
+    uint32_t tri_off;              // first triangle in the index arena (3 indices per triangle)
+    uint32_t uv_off;               // first vertex in the uv arena (2 floats per vertex), kB2Invalid = the geometry has no uvs
+    uint32_t mat_id, instance;
+};
+
+__device__ __forceinline__ void dev_normalize3(float *v)
+{
+    // float3.ih:63-70: c = 1/length, then multiply (as normalize3 of host_scene.cpp)
+    const float l = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    const float c = 1.f / l;
+    v[0] *= c;
+    v[1] *= c;
+    v[2] *= c;
+}
+
+// xforms: 32 floats per instance = object_to_world, world_to_object (column-major). Arithmetic and its order are
+// those of flatten_scene (compiled with -fmad=false here, -ffp-contract=off there), so that the records are the same
+// bits: world-space vertices, normalize(transpose(world_to_object) * normalize(cross(v1 - v0, v2 - v0)))
+// (render_embree.ispc:269,288-290), material id, the three uvs, the flattened primitive id.
+__global__ void __launch_bounds__(kBuildBlock) k_flatten(const DevSegment *segs, uint32_t num_segs, const float *xforms,
+                                                         const float *vert_arena, const uint32_t *index_arena,
+                                                         const float *uv_arena, uint32_t total, float *verts_out,
+                                                         float4 *shade_out, uint32_t *bad_index)
+{
+    for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
+        uint32_t lo = 0u, hi = num_segs - 1u;  // the last segment with flat_base <= f
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1u) >> 1;
+            if (segs[mid].flat_base <= f) {
+                lo = mid;
+            } else {
+                hi = mid - 1u;
+            }
+        }
+        const DevSegment seg = segs[lo];
+        const uint32_t p = f - seg.flat_base;
+        const uint32_t *ip = index_arena + 3 * (size_t)(seg.tri_off + p);
+        const uint32_t idx[3] = {ip[0], ip[1], ip[2]};
+        float *w = verts_out + (size_t)f * 9;
+        if (idx[0] >= seg.num_verts || idx[1] >= seg.num_verts || idx[2] >= seg.num_verts) {
+            *bad_index = 1u;  // reported by the host after the launch
+            for (int k = 0; k < 9; ++k) {
+                w[k] = 0.f;
+            }
+            shade_out[(size_t)f * 3] = shade_out[(size_t)f * 3 + 1] = shade_out[(size_t)f * 3 + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        const float *m = xforms + (size_t)seg.instance * 32, *w2o = m + 16;
+        float vo[3][3];
+        for (int k = 0; k < 3; ++k) {
+            const float *v = vert_arena + 3 * (size_t)(seg.vert_off + idx[k]);
+            vo[k][0] = v[0];
+            vo[k][1] = v[1];
+            vo[k][2] = v[2];
+            w[3 * k] = m[0] * v[0] + m[4] * v[1] + m[8] * v[2] + m[12];
+            w[3 * k + 1] = m[1] * v[0] + m[5] * v[1] + m[9] * v[2] + m[13];
+            w[3 * k + 2] = m[2] * v[0] + m[6] * v[1] + m[10] * v[2] + m[14];
+        }
+        const float e1[3] = {vo[1][0] - vo[0][0], vo[1][1] - vo[0][1], vo[1][2] - vo[0][2]};
+        const float e2[3] = {vo[2][0] - vo[0][0], vo[2][1] - vo[0][1], vo[2][2] - vo[0][2]};
+        float n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+        dev_normalize3(n);
+        float r[3];
+        r[0] = w2o[0] * n[0] + w2o[1] * n[1] + w2o[2] * n[2];
+        r[1] = w2o[4] * n[0] + w2o[5] * n[1] + w2o[6] * n[2];
+        r[2] = w2o[8] * n[0] + w2o[9] * n[1] + w2o[10] * n[2];
+        dev_normalize3(r);
+        float uv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const bool has_uv = seg.uv_off != kB2Invalid;
+        if (has_uv) {
+            for (int k = 0; k < 3; ++k) {
+                const float *t = uv_arena + 2 * (size_t)(seg.uv_off + idx[k]);
+                uv[2 * k] = t[0];
+                uv[2 * k + 1] = t[1];
+            }
+        }
+        // TriShade (host_scene.h): {n.xyz, material}, {uv0, uv1}, {uv2, has_uv, flat id}
+        shade_out[(size_t)f * 3] = make_float4(r[0], r[1], r[2], __uint_as_float(seg.mat_id));
+        shade_out[(size_t)f * 3 + 1] = make_float4(uv[0], uv[1], uv[2], uv[3]);
+        shade_out[(size_t)f * 3 + 2] = make_float4(uv[4], uv[5], __uint_as_float(has_uv ? 1u : 0u), __uint_as_float(f));
+    }
+}
 
 __device__ __forceinline__ uint32_t ordered_from_float(float f)
 {

@@ -361,10 +361,104 @@ struct crtc_renderer {
 
     // set_scene with option bvh_builder = 1: everything after the flattening happens on the device
     // (bvh8_device.cuh); fills d_nodes, d_tris, d_shade and leaf_flat_ids like the host path.
-    void build_on_device(const crt::HostScene &hs, uint32_t &num_nodes, uint32_t &depth, double &ms)
+    // The triangle half of flatten_scene on the device: the unique geometries are uploaded once (not once per
+    // instance) and k_flatten writes the world-space soup and the shading records in flattened order.
+    void flatten_on_device(const crt_scene_t *scene, const crt::FlattenPlan &plan, DeviceBuffer<float> &d_verts,
+                           DeviceBuffer<float4> &d_shade_in)
     {
-        const uint32_t n = (uint32_t)hs.num_tris();
-        if (hs.num_tris() >= (1u << 30)) {
+        const uint32_t total = (uint32_t)plan.total_tris;
+        struct Placed {
+            uint32_t vert_off, tri_off, uv_off;
+        };
+        std::vector<std::vector<Placed>> placed(scene->num_meshes);  // [mesh][geometry], filled on first use
+        std::vector<crt::DevSegment> segs;
+        size_t nv = 0, nt = 0, nuv = 0;
+        struct Copy {
+            const crt_geometry_t *geom;
+            Placed at;
+        };
+        std::vector<Copy> copies;
+        for (const crt::FlattenSegment &fs : plan.segments) {
+            const crt_mesh_t &mesh = scene->meshes[fs.mesh];
+            const crt_geometry_t &geom = mesh.geometries[fs.geometry];
+            if (geom.num_tris == 0) {
+                continue;
+            }
+            std::vector<Placed> &pm = placed[fs.mesh];
+            if (pm.empty()) {
+                pm.assign(mesh.num_geometries, Placed{crt::kB2Invalid, crt::kB2Invalid, crt::kB2Invalid});
+            }
+            Placed &pl = pm[fs.geometry];
+            if (pl.tri_off == crt::kB2Invalid) {
+                if (nv + geom.num_vertices >= 0xffffffffull || nt + geom.num_tris >= 0xffffffffull) {
+                    throw std::runtime_error("device set_scene: geometry arenas exceed 2^32 - 1 elements");
+                }
+                pl.vert_off = (uint32_t)nv;
+                pl.tri_off = (uint32_t)nt;
+                nv += geom.num_vertices;
+                nt += geom.num_tris;
+                if (geom.uvs) {
+                    pl.uv_off = (uint32_t)nuv;
+                    nuv += geom.num_vertices;
+                }
+                copies.push_back(Copy{&geom, pl});
+            }
+            crt::DevSegment ds;
+            ds.flat_base = (uint32_t)fs.flat_base;
+            ds.num_tris = geom.num_tris;
+            ds.vert_off = pl.vert_off;
+            ds.num_verts = geom.num_vertices;
+            ds.tri_off = pl.tri_off;
+            ds.uv_off = pl.uv_off;
+            ds.mat_id = fs.mat_id;
+            ds.instance = fs.instance;
+            segs.push_back(ds);
+        }
+        DeviceBuffer<float> vert_arena, uv_arena, xforms;
+        DeviceBuffer<uint32_t> index_arena, bad;
+        DeviceBuffer<crt::DevSegment> d_segs;
+        vert_arena.alloc(std::max<size_t>(1, nv * 3));
+        index_arena.alloc(std::max<size_t>(1, nt * 3));
+        uv_arena.alloc(std::max<size_t>(1, nuv * 2));
+        for (const Copy &c : copies) {
+            CUDA_CHECK(cudaMemcpyAsync(vert_arena.ptr + (size_t)c.at.vert_off * 3, c.geom->vertices,
+                                       (size_t)c.geom->num_vertices * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+            CUDA_CHECK(cudaMemcpyAsync(index_arena.ptr + (size_t)c.at.tri_off * 3, c.geom->indices,
+                                       (size_t)c.geom->num_tris * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+            if (c.geom->uvs) {
+                CUDA_CHECK(cudaMemcpyAsync(uv_arena.ptr + (size_t)c.at.uv_off * 2, c.geom->uvs,
+                                           (size_t)c.geom->num_vertices * 2 * sizeof(float), cudaMemcpyHostToDevice, stream));
+            }
+        }
+        std::vector<float> xf((size_t)scene->num_instances * 32);
+        for (uint32_t i = 0; i < scene->num_instances; ++i) {
+            std::memcpy(&xf[(size_t)i * 32], scene->instances[i].transform, 16 * sizeof(float));
+            std::memcpy(&xf[(size_t)i * 32 + 16], &plan.w2o_all[(size_t)i * 16], 16 * sizeof(float));
+        }
+        xforms.upload(xf.data(), xf.size(), stream);
+        d_segs.upload(segs.data(), segs.size(), stream);
+        const uint32_t zero = 0u;
+        bad.upload(&zero, 1, stream);
+        d_verts.alloc((size_t)total * 9);
+        d_shade_in.alloc((size_t)total * 3);
+        int sms = 0;
+        CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        const unsigned g = std::max(1u, std::min((total + crt::kBuildBlock - 1) / crt::kBuildBlock, (uint32_t)sms * 8u));
+        crt::k_flatten<<<g, crt::kBuildBlock, 0, stream>>>(d_segs.ptr, (uint32_t)segs.size(), xforms.ptr, vert_arena.ptr,
+                                                          index_arena.ptr, uv_arena.ptr, total, d_verts.ptr, d_shade_in.ptr,
+                                                          bad.ptr);
+        uint32_t bad_host = 0u;
+        CUDA_CHECK(cudaMemcpyAsync(&bad_host, bad.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CUDA_CHECK(cudaStreamSynchronize(stream));  // also: the staging vectors and arenas go out of scope
+        if (bad_host) {
+            throw std::runtime_error("triangle index out of range");
+        }
+    }
+
+    void build_on_device(uint32_t n, DeviceBuffer<float> &d_verts, DeviceBuffer<float4> &d_shade_in, uint32_t &num_nodes,
+                         uint32_t &depth, double &ms)
+    {
+        if (n >= (1u << 30)) {
             throw std::runtime_error("device BVH build: at most 2^30 - 1 triangles");
         }
         int sms = 0;
@@ -376,17 +470,14 @@ struct crtc_renderer {
         CUDA_CHECK(cudaEventCreate(&ev0));
         CUDA_CHECK(cudaEventCreate(&ev1));
         const uint32_t num_b2 = 2 * n - 1, max_nodes = std::max(1u, n - 1);
-        DeviceBuffer<float> d_verts;
-        DeviceBuffer<float4> d_shade_in, tri_lo, tri_hi, box_lo, box_hi, nodes_tmp;
+        DeviceBuffer<float4> tri_lo, tri_hi, box_lo, box_hi, nodes_tmp;
         DeviceBuffer<uint32_t> cbounds, vals0, vals1, hist, d_parent, arrivals, slots, work0, work1, tri_order, clusters0,
             clusters1, nn;
         DeviceBuffer<crt::u64> keys0, keys1, counts, offsets, scan_scratch;
         DeviceBuffer<uint2> d_children;
         DeviceBuffer<float> cost;
         DeviceBuffer<uint8_t> decision;
-        d_verts.upload(hs.tri_verts.data(), (size_t)n * 9, stream);
         static_assert(sizeof(crt::TriShade) == 3 * sizeof(float4), "TriShade = 3 float4");
-        d_shade_in.upload(reinterpret_cast<const float4 *>(hs.tri_shade.data()), (size_t)n * 3, stream);
         CUDA_CHECK(cudaEventRecord(ev0, stream));
         tri_lo.alloc(n);
         tri_hi.alloc(n);
@@ -555,7 +646,7 @@ struct crtc_renderer {
             if (order[i] >= n) {
                 throw std::runtime_error("device BVH build: triangle order out of range");
             }
-            leaf_flat_ids[i] = hs.tri_shade[order[i]].flat_id;
+            leaf_flat_ids[i] = order[i];  // the flattened primitive id IS the index in flattened order
         }
     }
 
@@ -566,12 +657,24 @@ struct crtc_renderer {
         auto_frames = 0;
         auto_decided = false;
         crt::HostScene hs;
-        crt::flatten_scene(scene, hs, bvh_threads);
         uint32_t bvh_nodes = 0, bvh_depth = 0;
         double bvh_ms = 0.0;
-        if (bvh_builder != 0 && hs.num_tris() > 0) {
-            build_on_device(hs, bvh_nodes, bvh_depth, bvh_ms);
+        size_t num_tris = 0;
+        crt::FlattenPlan plan;
+        if (bvh_builder != 0) {
+            crt::plan_flatten(scene, plan);
+        }
+        if (bvh_builder != 0 && plan.total_tris > 0) {
+            // set_scene on the device: only the references are checked and the materials / textures converted on the host
+            crt::convert_shading_inputs(scene, hs);
+            DeviceBuffer<float> d_verts;
+            DeviceBuffer<float4> d_shade_in;
+            flatten_on_device(scene, plan, d_verts, d_shade_in);
+            num_tris = plan.total_tris;
+            build_on_device((uint32_t)num_tris, d_verts, d_shade_in, bvh_nodes, bvh_depth, bvh_ms);
         } else {
+            crt::flatten_scene(scene, hs, bvh_threads);
+            num_tris = hs.num_tris();
             crt::Bvh8 bvh;
             crt::build_bvh8(hs.tri_verts.data(), hs.num_tris(), bvh_threads, bvh);
             check_depth(bvh.max_depth);
@@ -617,12 +720,12 @@ struct crtc_renderer {
         CUDA_CHECK(cudaStreamSynchronize(stream));
         spp = std::max<uint32_t>(1u, hs.samples_per_pixel);
         have_scene = true;
-        scene_info[0] = (double)hs.num_tris();
+        scene_info[0] = (double)num_tris;
         scene_info[1] = (double)bvh_nodes;
         scene_info[2] = (double)bvh_depth;
         scene_info[3] = bvh_ms;
         scene_info[4] = (double)bvh_nodes * 80.0;
-        scene_info[5] = (double)hs.num_tris() * 48.0;
+        scene_info[5] = (double)num_tris * 48.0;
         if (npx_local) {
             CUDA_CHECK(cudaMemsetAsync(d_accum_local.ptr, 0, (size_t)npx_local * 3 * sizeof(float), stream));
         }

@@ -86,10 +86,9 @@ void check_param(float x, uint32_t num_textures, const char *what, uint32_t mat)
 
 }  // namespace
 
-void flatten_scene(const crt_scene_t *s, HostScene &out, int threads)
+void plan_flatten(const crt_scene_t *s, FlattenPlan &plan)
 {
-    out = HostScene();
-    out.samples_per_pixel = s->samples_per_pixel;
+    plan = FlattenPlan();
     if (s->num_lights == 0) {
         throw std::runtime_error("scene has no lights (the path tracer samples exactly one quad light per bounce)");
     }
@@ -115,27 +114,14 @@ void flatten_scene(const crt_scene_t *s, HostScene &out, int threads)
     if (total >= 0xffffffffull) {
         throw std::runtime_error("scene exceeds 2^32-1 flattened triangles");
     }
-    out.tri_verts.resize(total * 9);
-    out.tri_shade.resize(total);
-
-    // one segment per (instance, geometry); its triangles are processed in fixed blocks on several threads
-    struct Segment {
-        uint32_t instance, geometry, mat_id;
-        size_t flat_base;
-    };
-    struct Block {
-        uint32_t segment, p_begin, p_end;
-    };
-    std::vector<Segment> segments;
-    std::vector<Block> blocks;
-    std::vector<float> w2o_all((size_t)s->num_instances * 16);
-    const uint32_t kBlockTris = 1u << 15;
+    plan.total_tris = total;
+    plan.w2o_all.resize((size_t)s->num_instances * 16);
     size_t flat = 0;
     for (uint32_t i = 0; i < s->num_instances; ++i) {
         const crt_instance_t &inst = s->instances[i];
         const crt_parameterized_mesh_t &pm = s->parameterized_meshes[inst.parameterized_mesh_id];
         const crt_mesh_t &mesh = s->meshes[pm.mesh_id];
-        mat4_inverse(inst.transform, &w2o_all[(size_t)i * 16]);
+        mat4_inverse(inst.transform, &plan.w2o_all[(size_t)i * 16]);
         for (uint32_t g = 0; g < mesh.num_geometries; ++g) {
             const crt_geometry_t &geom = mesh.geometries[g];
             const uint32_t mat_id = pm.material_ids[g];
@@ -144,17 +130,39 @@ void flatten_scene(const crt_scene_t *s, HostScene &out, int threads)
                                          " but the scene has " + std::to_string(s->num_materials) +
                                          " (run validate_materials, util/scene.cpp:935-958)");
             }
-            segments.push_back(Segment{i, g, mat_id, flat});
-            for (uint32_t p = 0; p < geom.num_tris; p += kBlockTris) {
-                blocks.push_back(Block{(uint32_t)segments.size() - 1, p, std::min(geom.num_tris, p + kBlockTris)});
-            }
+            plan.segments.push_back(FlattenSegment{i, pm.mesh_id, g, mat_id, flat});
             flat += geom.num_tris;
+        }
+    }
+}
+
+void flatten_scene(const crt_scene_t *s, HostScene &out, int threads)
+{
+    out = HostScene();
+    FlattenPlan plan;
+    plan_flatten(s, plan);
+    const size_t total = plan.total_tris;
+    out.tri_verts.resize(total * 9);
+    out.tri_shade.resize(total);
+
+    // one segment per (instance, geometry); its triangles are processed in fixed blocks on several threads
+    struct Block {
+        uint32_t segment, p_begin, p_end;
+    };
+    const std::vector<FlattenSegment> &segments = plan.segments;
+    const std::vector<float> &w2o_all = plan.w2o_all;
+    std::vector<Block> blocks;
+    const uint32_t kBlockTris = 1u << 15;
+    for (size_t si = 0; si < segments.size(); ++si) {
+        const uint32_t nt = s->meshes[segments[si].mesh].geometries[segments[si].geometry].num_tris;
+        for (uint32_t p = 0; p < nt; p += kBlockTris) {
+            blocks.push_back(Block{(uint32_t)si, p, std::min(nt, p + kBlockTris)});
         }
     }
     std::atomic<bool> bad_index(false);
     parallel_blocks((uint32_t)blocks.size(), host_threads(threads), [&](uint32_t bi) {
         const Block &blk = blocks[bi];
-        const Segment &seg = segments[blk.segment];
+        const FlattenSegment &seg = segments[blk.segment];
         const crt_instance_t &inst = s->instances[seg.instance];
         const crt_geometry_t &geom = s->meshes[s->parameterized_meshes[inst.parameterized_mesh_id].mesh_id].geometries[seg.geometry];
         const float *m = inst.transform;
@@ -211,7 +219,12 @@ void flatten_scene(const crt_scene_t *s, HostScene &out, int threads)
     if (bad_index) {
         throw std::runtime_error("triangle index out of range");
     }
+    convert_shading_inputs(s, out);
+}
 
+void convert_shading_inputs(const crt_scene_t *s, HostScene &out)
+{
+    out.samples_per_pixel = s->samples_per_pixel;
     // materials
     out.materials.assign(s->materials, s->materials + s->num_materials);
     for (uint32_t i = 0; i < s->num_materials; ++i) {

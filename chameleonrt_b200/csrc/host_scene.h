@@ -59,4 +59,20 @@ void pack_triangles(const HostScene &scene, const Bvh8 &bvh, std::vector<float> 
 // Throws std::runtime_error on malformed input (bad material / texture / mesh ids).
 void flatten_scene(const crt_scene_t *scene, HostScene &out, int threads = 0);
 
+// The two halves of flatten_scene, for the device set_scene path (bvh8_device.cuh: k_flatten does the per-triangle
+// work from the plan): (1) validation of the instance / mesh / material references, one segment per (instance,
+// geometry) with the index of its first flattened triangle, and every instance's world_to_object matrix
+// (embree_utils.cpp:97); (2) materials, lights and the texture arena (no triangles).
+struct FlattenSegment {
+    uint32_t instance, mesh, geometry, mat_id;
+    size_t flat_base;
+};
+struct FlattenPlan {
+    std::vector<FlattenSegment> segments;
+    std::vector<float> w2o_all;  // 16 floats per instance, column-major
+    size_t total_tris = 0;
+};
+void plan_flatten(const crt_scene_t *scene, FlattenPlan &plan);
+void convert_shading_inputs(const crt_scene_t *scene, HostScene &out);
+
 }  // namespace crt

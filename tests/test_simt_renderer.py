@@ -176,3 +176,4 @@ def test_device_bvh_builder_on_the_emulated_renderer(mods):
 
     dev_tests.test_device_built_bvh_renders_the_same_image(mods, cases)
     dev_tests.test_device_built_bvh_edge_cases(mods, big=4099 if FULL else 2500)
+    dev_tests.test_device_set_scene_rejects_bad_input(mods)

@@ -125,3 +125,30 @@ def test_device_built_bvh_edge_cases(mods, big=4099):
     r.initialize(16, 16)
     r.set_scene(_soup_scene(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32)))
     assert r.trace_closest(rays[:4])[:, 3].view(np.uint32).tolist() == [0xFFFFFFFF] * 4
+
+
+def test_device_set_scene_rejects_bad_input(mods):
+    """The device path checks what flatten_scene checks (the references on the host, the vertex indices in k_flatten)
+    and raises the same errors; the renderer stays usable afterwards."""
+    from chameleonrt_b200.scenes import cornell_box
+
+    RenderCUDA = mods[0]
+    r = RenderCUDA(0, bvh_builder="device")
+    r.initialize(16, 16)
+    scene, _ = cornell_box()
+    scene.parameterized_meshes[0].material_ids[0] = 99
+    with pytest.raises(RuntimeError, match="material"):
+        r.set_scene(scene)
+    scene, _ = cornell_box()
+    scene.lights = []
+    with pytest.raises(RuntimeError, match="light"):
+        r.set_scene(scene)
+    scene, _ = cornell_box()
+    scene.meshes[0].geometries[0].indices[0, 0] = 10_000
+    with pytest.raises(RuntimeError, match="index out of range"):
+        r.set_scene(scene)
+    scene, cam = cornell_box()
+    r.set_scene(scene)
+    assert _render(r, cam, 1).num_rays > 0
+    with pytest.raises(ValueError):
+        RenderCUDA(0, bvh_builder="gpu")
