@@ -666,7 +666,7 @@ struct crtc_renderer {
         }
         if (bvh_builder != 0 && plan.total_tris > 0) {
             // set_scene on the device: only the references are checked and the materials / textures converted on the host
-            crt::convert_shading_inputs(scene, hs);
+            crt::convert_shading_inputs(scene, hs, bvh_threads);
             DeviceBuffer<float> d_verts;
             DeviceBuffer<float4> d_shade_in;
             flatten_on_device(scene, plan, d_verts, d_shade_in);

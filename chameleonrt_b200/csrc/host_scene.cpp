@@ -219,10 +219,10 @@ void flatten_scene(const crt_scene_t *s, HostScene &out, int threads)
     if (bad_index) {
         throw std::runtime_error("triangle index out of range");
     }
-    convert_shading_inputs(s, out);
+    convert_shading_inputs(s, out, threads);
 }
 
-void convert_shading_inputs(const crt_scene_t *s, HostScene &out)
+void convert_shading_inputs(const crt_scene_t *s, HostScene &out, int threads)
 {
     out.samples_per_pixel = s->samples_per_pixel;
     // materials
@@ -270,14 +270,31 @@ void convert_shading_inputs(const crt_scene_t *s, HostScene &out)
     }
     out.texels.resize(texels);
     out.tex_desc.resize(s->num_textures);
+    // (rows of every texture in fixed blocks on several threads: C3's 11 M texels are the largest host cost of
+    // set_scene once the BVH is built on the device)
+    struct TexBlock {
+        uint32_t tex;
+        size_t px_begin, px_end;
+    };
+    std::vector<TexBlock> tex_blocks;
+    const size_t kBlockTexels = (size_t)1 << 18;
     size_t off = 0;
     for (uint32_t i = 0; i < s->num_textures; ++i) {
         const crt_image_t &im = s->textures[i];
         out.tex_desc[i] = TexDesc{(uint32_t)off, im.width, im.height, 0};
+        const size_t n = (size_t)im.width * im.height;
+        for (size_t b = 0; b < n; b += kBlockTexels) {
+            tex_blocks.push_back(TexBlock{i, b, std::min(n, b + kBlockTexels)});
+        }
+        off += n;
+    }
+    parallel_blocks((uint32_t)tex_blocks.size(), host_threads(threads), [&](uint32_t bi) {
+        const TexBlock &tb = tex_blocks[bi];
+        const crt_image_t &im = s->textures[tb.tex];
+        const size_t base = out.tex_desc[tb.tex].offset;
         const bool srgb = im.color_space == CRT_COLOR_SPACE_SRGB;
         const int convert_channels = std::min(3, im.channels);
-        const size_t n = (size_t)im.width * im.height;
-        for (size_t px = 0; px < n; ++px) {
+        for (size_t px = tb.px_begin; px < tb.px_end; ++px) {
             uint8_t c[4] = {0, 0, 0, 0};  // channels the image lacks read as 0 (texture2d.ih:13-27)
             for (int k = 0; k < im.channels; ++k) {
                 uint8_t v = im.data[px * im.channels + k];
@@ -286,11 +303,9 @@ void convert_shading_inputs(const crt_scene_t *s, HostScene &out)
                 }
                 c[k] = v;
             }
-            out.texels[off + px] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) |
-                                   ((uint32_t)c[3] << 24);
+            out.texels[base + px] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24);
         }
-        off += n;
-    }
+    });
 }
 
 void pack_triangles(const HostScene &scene, const Bvh8 &bvh, std::vector<float> &tri_records,

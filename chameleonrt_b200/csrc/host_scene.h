@@ -73,6 +73,6 @@ struct FlattenPlan {
     size_t total_tris = 0;
 };
 void plan_flatten(const crt_scene_t *scene, FlattenPlan &plan);
-void convert_shading_inputs(const crt_scene_t *scene, HostScene &out);
+void convert_shading_inputs(const crt_scene_t *scene, HostScene &out, int threads = 0);
 
 }  // namespace crt
