@@ -1,46 +1,56 @@
-// render_cuda_plugin.cpp — the four plugin callbacks + POPULATE_PLUGIN_FUNCTIONS
-// (util/render_plugin.h:55-63), mirroring backends/embree/render_embree_plugin.cpp:7-27.
-#include <SDL.h>
-#include "imgui.h"
-#include "render_cuda.h"
+// render_cuda_plugin.cpp — what ChameleonRT dlopens as libcrt_cuda.so: the function table of
+// util/render_plugin.h:23-41, filled through POPULATE_PLUGIN_FUNCTIONS (util/render_plugin.h:55-63). The role of
+// backends/embree/render_embree_plugin.cpp for the Embree backend.
 #include "render_plugin.h"
 
+#include <SDL.h>
+
+#include "imgui.h"
+#include "render_cuda.h"
+
+#ifndef CRT_CUDA_HEADLESS
+#include "display/gldisplay.h"
+#endif
+
+namespace crt_cuda_plugin {
+
 #ifdef CRT_CUDA_HEADLESS
-// Headless builds (no SDL2 / OpenGL on the machine): a display that shows nothing.
-struct NullDisplay : Display {
+// Machines without SDL2 / OpenGL (the build sandbox, the GPU box): a display that shows nothing, so that the
+// headless twin of main.cpp (oracle/ref_build) can drive the plugin exactly like the application does.
+struct NullDisplay final : Display {
     std::string gpu_brand() override { return "NVIDIA B200 (headless)"; }
     std::string name() override { return "null"; }
     void resize(const int, const int) override {}
     void new_frame() override {}
     void display(RenderBackend *) override {}
 };
+using PluginDisplay = NullDisplay;
 #else
-#include "display/gldisplay.h"
+using PluginDisplay = GLDisplay;
 #endif
 
-uint32_t get_sdl_window_flags()
-{
-    return SDL_WINDOW_OPENGL;
-}
+struct Hooks {
+    // the window the application creates must be able to host this plugin's display
+    static uint32_t window_flags() { return SDL_WINDOW_OPENGL; }
 
-void set_imgui_context(ImGuiContext *context)
-{
-    ImGui::SetCurrentContext(context);
-}
+    // the application owns the ImGui context; the plugin's own copy of imgui is pointed at it (main.cpp:98)
+    static void adopt_imgui(ImGuiContext *ctx) { ImGui::SetCurrentContext(ctx); }
 
-std::unique_ptr<Display> make_display(SDL_Window *window)
-{
+    static std::unique_ptr<Display> display_for(SDL_Window *window)
+    {
 #ifdef CRT_CUDA_HEADLESS
-    (void)window;
-    return std::make_unique<NullDisplay>();
+        (void)window;
+        return std::unique_ptr<Display>(new PluginDisplay());
 #else
-    return std::make_unique<GLDisplay>(window);
+        return std::unique_ptr<Display>(new PluginDisplay(window));
 #endif
-}
+    }
 
-std::unique_ptr<RenderBackend> make_renderer(Display *)
-{
-    return std::make_unique<RenderCUDA>();
-}
+    // img is read back to the host every frame (render_cuda.cpp), so any display works: the Display is not needed
+    static std::unique_ptr<RenderBackend> renderer_for(Display *) { return std::unique_ptr<RenderBackend>(new RenderCUDA()); }
+};
 
-POPULATE_PLUGIN_FUNCTIONS(get_sdl_window_flags, set_imgui_context, make_display, make_renderer)
+}  // namespace crt_cuda_plugin
+
+POPULATE_PLUGIN_FUNCTIONS(crt_cuda_plugin::Hooks::window_flags, crt_cuda_plugin::Hooks::adopt_imgui,
+                          crt_cuda_plugin::Hooks::display_for, crt_cuda_plugin::Hooks::renderer_for)
