@@ -19,12 +19,12 @@ HEADLESS = os.path.join(REF, "crt_headless")
 needs_ref = pytest.mark.skipif(not os.path.exists(HEADLESS), reason="oracle/_ref not built (needs /root/reference)")
 
 
-def run_headless(backend, obj, cam, w, h, spp, frames, tmp_path, depth=5):
+def run_headless(backend, obj, cam, w, h, spp, frames, tmp_path, depth=5, extra_env=None):
     out = tmp_path / f"accum_{backend}.f32"
     cmd = [HEADLESS, backend, obj, "-img", str(w), str(h), "-spp", str(spp), "-benchmark-frames", str(frames),
            "-accum", str(out), "-eye", *map(str, cam["eye"]), "-center", *map(str, cam["center"]),
            "-up", *map(str, cam["up"]), "-fov", str(cam["fov_y"])]
-    env = dict(os.environ, CRT_CUDA_MAX_DEPTH=str(depth))
+    env = dict(os.environ, CRT_CUDA_MAX_DEPTH=str(depth), **(extra_env or {}))
     r = subprocess.run(cmd, capture_output=True, text=True, cwd=str(tmp_path), env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     cam_line = [l for l in r.stdout.splitlines() if l.startswith("camera:")][0].split()[1:]

@@ -138,6 +138,12 @@ def test_drop_in_plugin_on_the_emulated_core(built, tmp_path):
     a_cpu, v2, _ = run_headless("oracle", obj, cam, 96, 64, 2, 2, tmp_path)
     assert v1 == v2 and "CUDA wavefront" in out
     assert_parity(a_gpu, a_cpu)
+    # the plugin's environment knob for the device BVH builders: same frame, bit for bit
+    for builder in ("1", "2"):
+        a_dev, _, _ = run_headless("cuda_simt", obj, cam, 96, 64, 2, 2, tmp_path, extra_env={"CRT_CUDA_BVH_BUILDER": builder})
+        assert np.array_equal(a_dev.view(np.uint32), a_gpu.view(np.uint32))
+    with pytest.raises(AssertionError, match="bvh_builder must be"):  # the knob does reach the core
+        run_headless("cuda_simt", obj, cam, 96, 64, 2, 2, tmp_path, extra_env={"CRT_CUDA_BVH_BUILDER": "7"})
     if not FULL:
         return
     scene, cam = san_miguel_like(spp=2, scale=0.02, tex_size=64)
