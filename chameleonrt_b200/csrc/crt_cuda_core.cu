@@ -123,6 +123,7 @@ struct crtc_renderer {
     int ploc_radius = crt::kPlocRadius;
     bool count_traversal = false;
     int refill_idle = crt::kRefillIdle;  // idle lanes that trigger a refill of the traversal warps
+    int tri_pass_defer = 0;              // 0 (default) / 16 / 24: pooled pairs a triangle pass waits for (kernels.cuh)
     // Shadow rays visit the children of a node farthest-first: 0 = no, 1 = yes, 2 = auto (default) — frame 1
     // after set_scene is rendered far-first, frame 2 near-first, and far-first is kept from frame 3 on only if its
     // traversal stage was at least 3 % faster (blocking render() calls only; the image is the same either way).
@@ -215,12 +216,27 @@ struct crtc_renderer {
             trav_grid = (unsigned)(sms * std::max(1, per_sm));
         }
         const int sched = (refill_idle & 0xff) | (frame_far_first ? 0x100 : 0);
-        if (count_traversal) {
-            crt::k_traverse<true><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any,
-                                                                             work_counter, sched);
-        } else {
-            crt::k_traverse<false><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any,
-                                                                              work_counter, sched);
+        // (one instantiation per variant, so that the default kernel's code does not change with the options)
+        const int variant = (count_traversal ? 1 : 0) | (tri_pass_defer == 16 ? 2 : (tri_pass_defer == 24 ? 4 : 0));
+        switch (variant) {
+        case 0:
+            crt::k_traverse<false><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any, work_counter, sched);
+            break;
+        case 1:
+            crt::k_traverse<true><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any, work_counter, sched);
+            break;
+        case 2:
+            crt::k_traverse<false, 16><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any, work_counter, sched);
+            break;
+        case 3:
+            crt::k_traverse<true, 16><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any, work_counter, sched);
+            break;
+        case 4:
+            crt::k_traverse<false, 24><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any, work_counter, sched);
+            break;
+        default:
+            crt::k_traverse<true, 24><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any, work_counter, sched);
+            break;
         }
     }
 
@@ -1204,6 +1220,11 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
             r->world_size = (int)value;
         } else if (k == "bvh_threads") {
             r->bvh_threads = (int)value;
+        } else if (k == "tri_pass_defer") {
+            if (value != 0 && value != 16 && value != 24) {
+                throw std::runtime_error("tri_pass_defer must be 0, 16 or 24");
+            }
+            r->tri_pass_defer = (int)value;
         } else if (k == "bvh_ploc_radius") {
             if (value < 1 || value > crt::kPlocMaxRadius) {
                 throw std::runtime_error("bvh_ploc_radius must be in [1, 32]");
@@ -1251,6 +1272,8 @@ int crtc_get_option(crtc_renderer *r, const char *key, int64_t *value)
             *value = r->world_size;
         } else if (k == "bvh_threads") {
             *value = r->bvh_threads;
+        } else if (k == "tri_pass_defer") {
+            *value = r->tri_pass_defer;
         } else if (k == "bvh_builder") {
             *value = r->bvh_builder;
         } else if (k == "bvh_build_rounds") {

@@ -198,7 +198,11 @@ struct HybridStack {
 // image. Work items [0, n_any) are shadow rays (sray_o/sray_d -> vis[], rtcOccludedV,
 // render_embree.ispc:144,170); items [n_any, n_any + n_closest) are closest-hit rays (ray_o/ray_d
 // through `queue`, or identity when null -> hit[], rtcIntersectV, render_embree.ispc:245).
-template <bool COUNT>
+// DEFER > 0 (option "tri_pass_defer", off by default): a triangle pass runs only once DEFER (lane, triangle) pairs
+// are pooled or no lane can descend any further; a lane whose triangle group is still untested waits. Fewer,
+// fuller passes for emptier node phases (DESIGN.md §2 "Warp-level work": 0.571 -> 0.523 in the emulation's cost
+// model at DEFER = 16); same results, since the closest hit does not depend on the order of the tests.
+template <bool COUNT, int DEFER = 0>
 __global__ void __launch_bounds__(kTravBlock, 8)
     k_traverse(DeviceScene sc, PathState ps, const uint32_t *queue, const uint32_t *count_closest_ptr,
                const uint32_t *count_any_ptr, uint32_t *work_counter, int sched)
@@ -309,8 +313,9 @@ __global__ void __launch_bounds__(kTravBlock, 8)
             __syncwarp();
             for (;;) {
                 // node phase
-                CRT_PROF_NODE_PHASE(alive && (st.cur.y & 0xff000000u));
-                if (alive && (st.cur.y & 0xff000000u)) {
+                const bool can_step = alive && (st.cur.y & 0xff000000u) && (DEFER == 0 || tri.y == 0u);
+                CRT_PROF_NODE_PHASE(can_step);
+                if (can_step) {
                     const uint32_t node_index = next_child(st.cur, st.oct_inv4);
                     if (st.cur.y & 0xff000000u) {
                         stack.push(st.cur);
@@ -338,6 +343,13 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                     const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
                     if (total == 0u) {
                         break;
+                    }
+                    if (DEFER > 0) {
+                        // wait for a fuller pool while some lane without a pending group can still descend
+                        const bool free_lane = alive && tri.y == 0u && ((st.cur.y & 0xff000000u) || !stack.empty());
+                        if (total < (uint32_t)DEFER && __ballot_sync(0xffffffffu, free_lane) != 0u) {
+                            break;
+                        }
                     }
                     uint32_t pos = pre - k;
                     while (tri.y && pos < 32u) {
@@ -395,7 +407,10 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                 if (alive) {
                     st.tfar = __uint_as_float((uint32_t)(sm_key[warp][lane] >> 32));
                     bool finished = is_any && sm_hit_tri[warp][lane] != kMiss;
-                    if (!finished && (st.cur.y & 0xff000000u) == 0u) {
+                    if (DEFER > 0 && finished) {
+                        tri.y = 0u;  // an occluded shadow ray needs no further tests
+                    }
+                    if (!finished && (DEFER == 0 || tri.y == 0u) && (st.cur.y & 0xff000000u) == 0u) {
                         if (!stack.empty()) {
                             st.cur = stack.pop();
                         } else {

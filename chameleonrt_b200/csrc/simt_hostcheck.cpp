@@ -89,7 +89,8 @@ void crt_simt_profile(unsigned long long *out4, int reset)
 // closest rays: n x 8 floats (through an identity or a permuted queue), hits out: n x 4 {t, u, v, bits(flattened
 // primitive id | 0xffffffff)} — the kernel stores the leaf-order triangle index, translated here like crtc_trace_closest
 // any rays: m x 8 floats {o, tnear ignored (the kernel uses kEpsilon), d, tfar}, vis out: m bytes (1 = unoccluded)
-// sched: bits 0-7 refill_idle, bit 8 far-first shadow rays. Single-ray results for comparison come from
+// sched: bits 0-7 refill_idle, bit 8 far-first shadow rays, bits 16-23 (here only) the DEFER instantiation: 0 / 16 / 24.
+// Single-ray results for comparison come from
 // libcrt_bvh8_hostcheck.so.
 void crt_simt_traverse(void *p, const float *closest, uint32_t n_closest, const uint32_t *queue_perm, const float *any,
                        uint32_t n_any, int blocks, int sched, float *hits_out, uint8_t *vis_out)
@@ -142,8 +143,18 @@ void crt_simt_traverse(void *p, const float *closest, uint32_t n_closest, const 
                 gridDim.x = (unsigned)blocks;
                 simt::warp = &warps[t / 32];
                 simt::lane = t % 32;
-                crt::k_traverse<false>(sc, ps, ps.queue[0], counters.data() + crt::kCntQueue, n_any ? counters.data() + crt::kCntShadow : nullptr,
-                                       work_counter, sched);
+                const uint32_t *any_count = n_any ? counters.data() + crt::kCntShadow : nullptr;
+                switch ((sched >> 16) & 0xff) {  // test-only selector of the instantiation (option "tri_pass_defer")
+                case 16:
+                    crt::k_traverse<false, 16>(sc, ps, ps.queue[0], counters.data() + crt::kCntQueue, any_count, work_counter, sched & 0xffff);
+                    break;
+                case 24:
+                    crt::k_traverse<false, 24>(sc, ps, ps.queue[0], counters.data() + crt::kCntQueue, any_count, work_counter, sched & 0xffff);
+                    break;
+                default:
+                    crt::k_traverse<false>(sc, ps, ps.queue[0], counters.data() + crt::kCntQueue, any_count, work_counter, sched & 0xffff);
+                    break;
+                }
             });
         }
         for (auto &th : threads) {

@@ -58,6 +58,9 @@ void crtc_destroy(crtc_renderer *r);
  *   "rank", "world_size"  image-tile sharding: this renderer owns the 64x64 tiles with
  *                 tile_id % world_size == rank (tile_id as in render_embree.cpp:178-180)
  *   "bvh_threads" host threads for the BVH8 build (0 = all)
+ *   "tri_pass_defer" 0 (default), 16 or 24: experimental scheduling variant of the traversal kernel — a warp's pooled
+ *                 triangle pass waits until that many (ray, triangle) pairs are pending or no lane can descend.
+ *                 Never changes a result; not yet timed on a GPU.
  *   "bvh_builder" where crtc_set_scene builds the BVH8: 0 = on the host (binned SAH, the default); on the device
  *                 (chameleonrt_b200/csrc/bvh8_device.cuh): 1 = PLOC (mutual nearest neighbours in Morton order),
  *                 2 = LBVH (Karras), both followed by the host builder's 8-wide collapse — a much shorter set_scene

@@ -1,17 +1,38 @@
-"""Sweep the traversal scheduling knobs on the C2 workload (run on the GPU box)."""
-import sys, os, ctypes as C
+"""Sweep the scheduling variants of k_traverse on a bench workload (run on the GPU box): the refill threshold, the
+shadow-ray order, the deferred triangle pass, and — through the tree they traverse — the BVH builder. Every variant
+renders the same image (tested); only the stage times differ.
+    python scripts/tune_traversal.py [c2|c3|c4] [quick]"""
+import itertools
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
-from bench import make_workload, WIDTH, HEIGHT, MAX_DEPTH
-from chameleonrt_b200 import RenderCUDA
-scene, view = make_workload()
-for refill in (1, 2, 4, 8, 12):
-    gpu = RenderCUDA(0, max_depth=MAX_DEPTH)
+import bench  # noqa: E402
+from chameleonrt_b200 import RenderCUDA  # noqa: E402
+
+args = [a for a in sys.argv[1:] if a != "quick"]
+quick = "quick" in sys.argv
+bench.select_workload(args[0] if args else "c2")
+scene, view = bench.make_workload()
+refills = (4,) if quick else (1, 2, 4, 8)
+grid = itertools.product(("host", "device"), refills, (0, 1), (0, 16, 24))
+print(f"# {bench.WORKLOAD}; mean of frames 3..7, ms", flush=True)
+base = None
+for builder, refill, far, defer in grid:
+    if builder == "device" and (refill != 4 or quick and (far or defer)):
+        continue  # the tree matters through its quality; one line per ordering is enough
+    gpu = RenderCUDA(0, max_depth=bench.MAX_DEPTH, bvh_builder=builder, any_far_first=far, tri_pass_defer=defer)
     gpu._check(gpu.lib.crtc_set_option(gpu.h, b"refill_idle", refill))
-    gpu.initialize(WIDTH, HEIGHT); gpu.set_scene(scene)
+    gpu.initialize(bench.WIDTH, bench.HEIGHT)
+    gpu.set_scene(scene)
     acc = {}
     for f in range(8):
-        st = gpu.render(*view, f == 0, False)
+        gpu.render(*view, f == 0, False)
         if f >= 3:
-            for k, v in gpu.stage_times().items(): acc[k] = acc.get(k, 0) + v / 5
-    print(f"refill_idle={refill:2d} " + ' '.join(f"{k}={v:.3f}" for k, v in acc.items()), flush=True)
+            for k, v in gpu.stage_times().items():
+                acc[k] = acc.get(k, 0) + v / 5
+    trav = acc["traverse"] + acc["traverse_primary"]
+    base = base or trav
+    print(f"builder={builder:6s} refill_idle={refill:2d} far_first={far} tri_pass_defer={defer:2d}  traverse {trav:7.3f} "
+          f"({trav / base - 1:+.1%})  frame {acc['frame']:7.3f}  " + " ".join(f"{k}={v:.3f}" for k, v in acc.items()
+                                                                                if k not in ("frame",)), flush=True)

@@ -20,7 +20,7 @@ LIB = os.path.join(OUT, "libcrt_cuda_core_simt.so")
 
 def translate(src: str) -> str:
     out, pos = [], 0
-    pat = re.compile(r"(crt::k_\w+(?:<\w+>)?)<<<([^,]+),\s*([^,]+),\s*0,\s*stream>>>\(")
+    pat = re.compile(r"(crt::k_\w+(?:<[\w, ]+>)?)<<<([^,]+),\s*([^,]+),\s*0,\s*stream>>>\(")
     n = 0
     while True:
         m = pat.search(src, pos)
@@ -36,7 +36,7 @@ def translate(src: str) -> str:
         pos = i + 1
         n += 1
     out.append(src[pos:])
-    assert n == 24, f"expected 24 kernel launches in crt_cuda_core.cu, found {n}"
+    assert n == 28, f"expected 28 kernel launches in crt_cuda_core.cu, found {n}"
     return '#include "simt_env.h"\n' + "".join(out)
 
 

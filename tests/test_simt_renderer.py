@@ -183,3 +183,10 @@ def test_device_bvh_builder_on_the_emulated_renderer(mods):
     dev_tests.test_device_built_bvh_renders_the_same_image(mods, cases)
     dev_tests.test_device_built_bvh_edge_cases(mods, big=4099 if FULL else 2500)
     dev_tests.test_device_set_scene_rejects_bad_input(mods)
+
+
+def test_triangle_pass_deferral_on_the_emulated_renderer(mods):
+    """k_traverse<COUNT, DEFER> (option tri_pass_defer) in the whole renderer: same frames, same ray counts."""
+    import test_z_device_bvh_build as dev_tests
+
+    dev_tests.test_triangle_pass_deferral_does_not_change_the_image(mods, size=(48, 32), detail=0.2)

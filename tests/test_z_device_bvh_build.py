@@ -1,7 +1,8 @@
-"""set_scene with the BVH8 built ON THE DEVICE (options bvh_builder = "device" / "device_lbvh", bvh8_device.cuh;
+"""(1) set_scene with the BVH8 built ON THE DEVICE (options bvh_builder = "device" / "device_lbvh", bvh8_device.cuh;
 SURVEY.md §8(f) rank 1) against the host-built tree, through the C ABI. Run on the B200 box: python -m pytest tests -m gpu.
 (The file sorts last on purpose: these kernels were written after the round's GPU budget was spent and have so far
-only run under the CPU SIMT emulation — tests/test_simt_renderer.py calls the same functions there.)"""
+only run under the CPU SIMT emulation — tests/test_simt_renderer.py calls the same functions there.)
+(2) The deferred-triangle-pass instantiations of k_traverse (option tri_pass_defer), likewise new and opt-in."""
 import numpy as np
 import pytest
 
@@ -152,3 +153,31 @@ def test_device_set_scene_rejects_bad_input(mods):
     assert _render(r, cam, 1).num_rays > 0
     with pytest.raises(ValueError):
         RenderCUDA(0, bvh_builder="gpu")
+
+
+def test_triangle_pass_deferral_does_not_change_the_image(mods, size=(256, 144), detail=0.3):
+    """Option tri_pass_defer = 16 / 24 selects k_traverse<COUNT, DEFER>: a warp's triangle pass waits until that many
+    (lane, triangle) pairs are pooled or no lane can descend. Scheduling only: frames, ray counts and — for closest-hit
+    rays, whose node visits do change with later tfar updates — nothing but the instrumented work counters move."""
+    from chameleonrt_b200.scenes import sponza_like
+    from helpers import camera_for
+
+    RenderCUDA = mods[0]
+    scene, cam = sponza_like(spp=2, detail=detail, tex_size=64)
+    c = camera_for(cam)
+    out = []
+    for defer, far in ((0, 0), (16, 0), (24, 1)):
+        r = RenderCUDA(0, max_depth=5, count_traversal=True, any_far_first=far, tri_pass_defer=defer)
+        r.initialize(*size)
+        r.set_scene(scene)
+        for f in range(2):
+            st = r.render(c.eye(), c.dir(), c.up(), cam["fov_y"], f == 0, True)
+        out.append((r.read_accum(), r.read_img(), st.num_rays, r.counters()))
+        assert r.get_option("tri_pass_defer") == defer
+    a0, i0, n0, c0 = out[0]
+    for a, i, n, cn in out[1:]:
+        assert (a0.view(np.uint32) == a.view(np.uint32)).all() and (i0 == i).all() and n0 == n
+        assert c0["closest_rays"] == cn["closest_rays"] and c0["occlusion_rays"] == cn["occlusion_rays"]
+        assert cn["closest_tris_tested"] > 0 and cn["closest_nodes_visited"] >= c0["closest_nodes_visited"]
+    with pytest.raises(RuntimeError, match="tri_pass_defer"):
+        RenderCUDA(0, tri_pass_defer=8)
