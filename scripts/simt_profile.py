@@ -75,11 +75,17 @@ def main():
     print(f"scene {args.scene}, {len(prim)} primary rays, {len(b1)} bounce rays, {len(sh0)} shadow rays (one block of 4 warps drains each launch)")
     print("primary rays (coherent):")
     run(prim, empty, 4, "refill at 4 idle lanes (default)")
+    run(prim, empty, 4 | (16 << 16), "triangle pass deferred until 16 pairs are pooled")
     print("the merged launch of bounce 0: its shadow rays + the continuation rays of bounce 1:")
     base = run(b1, sh0, 4, "default: refill at 4 idle lanes, near-first")
     for ri in (1, 8, 16, 32):
         run(b1, sh0, ri, f"refill at {ri} idle lanes")
     run(b1, sh0, 4 | 0x100, "shadow rays far-first")
+    # bits 16-23: the instantiation (test-only selector of simt_hostcheck.cpp) = option tri_pass_defer
+    run(b1, sh0, 4 | (16 << 16), "triangle pass deferred until 16 pairs are pooled")
+    run(b1, sh0, 4 | (24 << 16), "triangle pass deferred until 24 pairs are pooled")
+    run(b1, sh0, 4 | 0x100 | (16 << 16), "deferred (16) + shadow rays far-first")
+    run(b1, sh0, 1 | 0x100 | (16 << 16), "deferred (16) + far-first + refill at 1 idle lane")
     run(np.ascontiguousarray(b1[sort_key(b1)]), np.ascontiguousarray(sh0[sort_key(sh0)]), 4, "rays sorted by octant, then position")
     run(np.ascontiguousarray(b1[sort_key(b1)]), np.ascontiguousarray(sh0[sort_key(sh0)]), 4 | 0x100, "sorted + shadow rays far-first")
     print("the same rays as two launches (shadow rays alone, continuation rays alone):")
