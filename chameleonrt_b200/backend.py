@@ -173,6 +173,10 @@ class RenderCUDA:
         self._check(self.lib.crtc_render_async(self.h, pp, dp, up_, C.c_float(fovy), 1 if camera_changed else 0,
                                                num_frames))
 
+    def set_option(self, key: str, value: int) -> None:
+        """crtc_set_option (include/crt_cuda.h lists the keys); options apply to the next set_scene / frame."""
+        self._check(self.lib.crtc_set_option(self.h, key.encode(), int(value)))
+
     def get_option(self, key: str) -> int:
         v = C.c_int64(0)
         self._check(self.lib.crtc_get_option(self.h, key.encode(), C.byref(v)))

@@ -13,7 +13,8 @@
 //   4. the binary tree over the sorted triangles, one of
 //      PLOC (bvh_builder = 1; Meister & Bittner 2018): repeat { k_ploc_nn: every cluster finds its nearest neighbour
 //        (smallest merged surface area) among the 2 x 16 clusters around it in Morton order; k_ploc_mark -> scan ->
-//        k_ploc_merge: mutual nearest neighbours become a node, the cluster array is compacted } until one is left
+//        k_ploc_merge: mutual nearest neighbours become a node, the cluster array is compacted } until <= 1024 are left;
+//        k_ploc_tail runs the remaining rounds (two thirds of them) in one block, out of shared memory
 //      LBVH (bvh_builder = 2; Karras 2012): k_lbvh_hierarchy, every internal node finds its key range and split
 //        independently, then k_lbvh_refit bottom-up (the second arrival at a node proceeds)
 //   5. with every node, as it is made: its box AND the 8-wide collapse's dynamic programme (collapse_dp: Ylitie et al.
@@ -587,6 +588,118 @@ __global__ void __launch_bounds__(kBuildBlock) k_ploc_merge(Lbvh b, const uint32
             c = b.n + k;
         }
         clusters_out[(uint32_t)(off >> 32)] = c;
+    }
+}
+
+// The last rounds of PLOC in ONE block. The cluster count shrinks by about a fifth per round, so two thirds of a
+// build's rounds run on fewer than kPlocTailMax clusters — from the host each of them is six tiny launches and a round
+// trip for the count. Here the cluster list, the nearest-neighbour table and the boxes live in shared memory and a
+// round is four block barriers. Same algorithm, same ties, same node numbering as the launches it replaces: the tree
+// is identical (tested). rounds_io: rounds done so far in, total rounds out (the 256-round cut-off carries over).
+constexpr int kPlocTailMax = 1024;
+constexpr int kPlocTailItems = kPlocTailMax / kBuildBlock;  // consecutive clusters per thread in the scan / merge
+
+__global__ void __launch_bounds__(kBuildBlock) k_ploc_tail(Lbvh b, const uint32_t *clusters, uint32_t m, uint32_t nodes_made,
+                                                           int radius, uint32_t *rounds_io)
+{
+    __shared__ uint32_t cl[2][kPlocTailMax];
+    __shared__ uint32_t nn[kPlocTailMax];
+    __shared__ float4 slo[kPlocTailMax], shi[kPlocTailMax];
+    __shared__ uint32_t warp_total[kBuildBlock / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+        cl[0][i] = clusters[i];
+    }
+    uint32_t rounds = *rounds_io;
+    int cur = 0;
+    __syncthreads();
+    while (m > 1u) {
+        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+            const uint32_t c = cl[cur][i];
+            slo[i] = b.box_lo[c];
+            shi[i] = b.box_hi[c];
+        }
+        __syncthreads();
+        const bool forced = rounds >= 256u;
+        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {  // = k_ploc_nn
+            uint32_t best_j = i;
+            if (forced) {
+                best_j = (i ^ 1u) < m ? (i ^ 1u) : i;
+            } else {
+                const float4 lo = slo[i], hi = shi[i];
+                float best = __uint_as_float(0x7f800000u);
+                const int j0 = max((int)i - radius, 0), j1 = min((int)i + radius, (int)m - 1);
+                for (int j = j0; j <= j1; ++j) {
+                    if (j == (int)i) {
+                        continue;
+                    }
+                    const float4 ol = slo[j], oh = shi[j];
+                    const float4 ul = make_float4(fminf(lo.x, ol.x), fminf(lo.y, ol.y), fminf(lo.z, ol.z), 0.f);
+                    const float4 uh = make_float4(fmaxf(hi.x, oh.x), fmaxf(hi.y, oh.y), fmaxf(hi.z, oh.z), 0.f);
+                    const float a = box_half_area(ul, uh);
+                    if (a < best || best_j == i) {
+                        best = a;
+                        best_j = (uint32_t)j;
+                    }
+                }
+            }
+            nn[i] = best_j;
+        }
+        __syncthreads();
+        // = k_ploc_mark + scan: thread t owns clusters [t * 4, t * 4 + 4); keep << 16 | leader fits 32 bits (m <= 1024)
+        uint32_t flags[kPlocTailItems], sum = 0u;
+        for (int k = 0; k < kPlocTailItems; ++k) {
+            const uint32_t i = threadIdx.x * (uint32_t)kPlocTailItems + (uint32_t)k;
+            flags[k] = 0u;
+            if (i < m) {
+                const uint32_t j = nn[i];
+                const bool mutual = j != i && nn[j] == i;
+                flags[k] = ((mutual && j < i ? 0u : 1u) << 16) | (mutual && i < j ? 1u : 0u);
+            }
+            sum += flags[k];
+        }
+        uint32_t inc = sum;
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) {
+                inc += o;
+            }
+        }
+        if (lane == 31) {
+            warp_total[warp] = inc;
+        }
+        __syncthreads();
+        uint32_t run = inc - sum, total = 0u;
+        for (int w = 0; w < kBuildBlock / 32; ++w) {
+            if (w < warp) {
+                run += warp_total[w];
+            }
+            total += warp_total[w];
+        }
+        // = k_ploc_merge
+        for (int k = 0; k < kPlocTailItems; ++k) {
+            const uint32_t i = threadIdx.x * (uint32_t)kPlocTailItems + (uint32_t)k;
+            if (i < m && (flags[k] >> 16)) {
+                uint32_t c = cl[cur][i];
+                if (flags[k] & 1u) {
+                    const uint32_t node = nodes_made + (run & 0xffffu);
+                    const uint32_t other = cl[cur][nn[i]];
+                    b.children[node] = make_uint2(c, other);
+                    collapse_dp(b, b.n + node, c, other);
+                    c = b.n + node;
+                }
+                cl[cur ^ 1][run >> 16] = c;
+            }
+            run += flags[k];
+        }
+        __syncthreads();  // also makes this round's nodes (global memory) visible to the whole block
+        m = total >> 16;
+        nodes_made += total & 0xffffu;
+        cur ^= 1;
+        ++rounds;
+    }
+    if (threadIdx.x == 0) {
+        *rounds_io = rounds;
     }
 }
 

@@ -121,6 +121,7 @@ struct crtc_renderer {
     int bvh_builder = 0;  // 0 = host (binned SAH, bvh8_build.cpp); on the device (bvh8_device.cuh): 1 = PLOC, 2 = LBVH
     int build_rounds = 0;
     int ploc_radius = crt::kPlocRadius;
+    bool ploc_tail = true;  // the last rounds of PLOC in one block (k_ploc_tail); off only to test that the tree is the same
     bool count_traversal = false;
     int refill_idle = crt::kRefillIdle;  // idle lanes that trigger a refill of the traversal warps
     int tri_pass_defer = 0;              // 0 (default) / 16 / 24: pooled pairs a triangle pass waits for (kernels.cuh)
@@ -573,6 +574,19 @@ struct crtc_renderer {
             uint32_t m = n, nodes_made = 0;
             build_rounds = 0;
             while (m > 1) {
+                if (ploc_tail && m <= (uint32_t)crt::kPlocTailMax) {
+                    // the remaining rounds in one block (k_ploc_tail): no more round trips
+                    uint32_t *rounds_dev = nn.ptr;  // free from here on
+                    uint32_t rounds_host = (uint32_t)build_rounds;
+                    CUDA_CHECK(cudaMemcpyAsync(rounds_dev, &rounds_host, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+                    crt::k_ploc_tail<<<1, crt::kBuildBlock, 0, stream>>>(b, cl, m, nodes_made, ploc_radius, rounds_dev);
+                    CUDA_CHECK(cudaMemcpyAsync(&rounds_host, rounds_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+                    CUDA_CHECK(cudaStreamSynchronize(stream));
+                    build_rounds = (int)rounds_host;
+                    nodes_made += m - 1;
+                    m = 1;
+                    break;
+                }
                 // (an adversarial input can leave one mutual pair per round; after 256 rounds neighbours are paired up)
                 const int forced = build_rounds >= 256 ? 1 : 0;
                 const unsigned gm = (m + crt::kBuildBlock - 1) / crt::kBuildBlock;
@@ -1225,6 +1239,8 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
                 throw std::runtime_error("tri_pass_defer must be 0, 16 or 24");
             }
             r->tri_pass_defer = (int)value;
+        } else if (k == "bvh_ploc_tail") {
+            r->ploc_tail = value != 0;
         } else if (k == "bvh_ploc_radius") {
             if (value < 1 || value > crt::kPlocMaxRadius) {
                 throw std::runtime_error("bvh_ploc_radius must be in [1, 32]");

@@ -36,7 +36,7 @@ def translate(src: str) -> str:
         pos = i + 1
         n += 1
     out.append(src[pos:])
-    assert n == 28, f"expected 28 kernel launches in crt_cuda_core.cu, found {n}"
+    assert n == 29, f"expected 29 kernel launches in crt_cuda_core.cu, found {n}"
     return '#include "simt_env.h"\n' + "".join(out)
 
 

@@ -183,6 +183,7 @@ def test_device_bvh_builder_on_the_emulated_renderer(mods):
     dev_tests.test_device_built_bvh_renders_the_same_image(mods, cases)
     dev_tests.test_device_built_bvh_edge_cases(mods, big=4099 if FULL else 2500)
     dev_tests.test_device_set_scene_rejects_bad_input(mods)
+    dev_tests.test_ploc_tail_kernel_builds_the_same_tree(mods, detail=0.2, size=(48, 32))
 
 
 def test_triangle_pass_deferral_on_the_emulated_renderer(mods):

@@ -57,6 +57,28 @@ def test_device_built_bvh_renders_the_same_image(mods, cases=None):
         assert 0 < out["device"]["rounds"] <= 256 + 32 or host["info"]["triangles"] < 2
 
 
+def test_ploc_tail_kernel_builds_the_same_tree(mods, detail=0.5, size=(160, 90)):
+    """k_ploc_tail runs the last PLOC rounds (<= 1024 clusters) in one block out of shared memory instead of six
+    launches and a host round trip per round. Same algorithm, ties and node numbering: the tree — hence every
+    instrumented traversal counter — and the number of rounds must equal the launch-per-round build's."""
+    from chameleonrt_b200.scenes import cornell_box, sponza_like
+
+    RenderCUDA = mods[0]
+    for scene, cam in (cornell_box(spp=1), sponza_like(spp=1, detail=detail, tex_size=32)):
+        res = []
+        for tail in (1, 0):
+            r = RenderCUDA(0, bvh_builder="device", count_traversal=True, any_far_first=0)
+            r.set_option("bvh_ploc_tail", tail)
+            r.initialize(*size)
+            r.set_scene(scene)
+            _render(r, cam, 1)
+            res.append((r.scene_info()["bvh8_nodes"], r.scene_info()["bvh8_depth"], r.get_option("bvh_build_rounds"), r.counters(),
+                        r.read_accum()))
+        assert res[0][:3] == res[1][:3], (res[0][:3], res[1][:3])
+        assert res[0][3] == res[1][3]
+        assert (res[0][4].view(np.uint32) == res[1][4].view(np.uint32)).all()
+
+
 def _soup_scene(verts, idx):
     from chameleonrt_b200.scene import DisneyMaterial, Geometry, Instance, Mesh, ParameterizedMesh, Scene, default_obj_light
 
