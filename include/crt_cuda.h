@@ -66,6 +66,8 @@ void crtc_destroy(crtc_renderer *r);
  *                 2 = LBVH (Karras), both followed by the host builder's 8-wide collapse — a much shorter set_scene
  *                 on scenes of millions of triangles for a somewhat slower tree. Rendered frames are bit-identical
  *                 in every case (closest hits break ties on the primitive id).
+ *                 Developer knobs of the PLOC builder: "bvh_ploc_radius" (1..32, default 16: clusters searched on
+ *                 either side) and "bvh_ploc_tail" (default 1: the last rounds run in a single block).
  *   "refill_idle" scheduling knob of the persistent traversal kernels (how many idle lanes
  *                 trigger a refill from the ray queue); the default is tuned
  *   "any_far_first" 1 = shadow (any-hit) rays visit the children of a BVH node farthest-first instead of
@@ -80,7 +82,8 @@ void crtc_destroy(crtc_renderer *r);
 int crtc_set_option(crtc_renderer *r, const char *key, int64_t value);
 
 /* Reads an option back. Besides the keys above: "any_far_first_decision" = the shadow-ray order frames are
- * rendered with from now on (0 near-first, 1 far-first, -1 = mode 2 has not decided yet). */
+ * rendered with from now on (0 near-first, 1 far-first, -1 = mode 2 has not decided yet); "bvh_build_rounds" = the
+ * number of PLOC rounds of the last device build. */
 int crtc_get_option(crtc_renderer *r, const char *key, int64_t *value);
 
 /* Use an existing CUDA stream (cudaStream_t) for all work of this renderer; NULL = the
