@@ -67,6 +67,43 @@ struct DeviceBuffer {
     }
 };
 
+// One cudaMalloc / cudaFree for a group of temporaries (the device set_scene needs ~25 of them, and cudaMalloc /
+// cudaFree cost more than most of its kernels). Used in two passes: the ArenaBuf::alloc calls run once to add up the
+// sizes, commit() allocates, and the same calls run again to hand out the pointers.
+struct DeviceArena {
+    char *base = nullptr;
+    size_t used = 0, capacity = 0;
+    ~DeviceArena()
+    {
+        if (base) {
+            cudaFree(base);
+        }
+    }
+    void commit()
+    {
+        capacity = used;
+        used = 0;
+        CUDA_CHECK(cudaMalloc(&base, std::max<size_t>(capacity, 256)));
+    }
+    void *take(size_t bytes)
+    {
+        used = (used + 255) & ~(size_t)255;
+        void *p = base ? base + used : nullptr;
+        used += bytes;
+        if (base && used > capacity) {
+            throw std::runtime_error("DeviceArena: the second pass asked for more than the first");
+        }
+        return p;
+    }
+};
+template <typename T>
+struct ArenaBuf {
+    DeviceArena *arena;
+    T *ptr = nullptr;
+    explicit ArenaBuf(DeviceArena &a) : arena(&a) {}
+    void alloc(size_t n) { ptr = static_cast<T *>(arena->take(std::max<size_t>(n, 1) * sizeof(T))); }
+};
+
 enum Stage { kStRaygen = 0, kStPrimary, kStShade, kStTraverse, kStNee, kStResolve, kStFrame, kNumStages };
 
 // What one enqueued frame leaves behind for later collection: its stage events and a pinned copy
@@ -431,12 +468,21 @@ struct crtc_renderer {
             ds.instance = fs.instance;
             segs.push_back(ds);
         }
-        DeviceBuffer<float> vert_arena, uv_arena, xforms;
-        DeviceBuffer<uint32_t> index_arena, bad;
-        DeviceBuffer<crt::DevSegment> d_segs;
-        vert_arena.alloc(std::max<size_t>(1, nv * 3));
-        index_arena.alloc(std::max<size_t>(1, nt * 3));
-        uv_arena.alloc(std::max<size_t>(1, nuv * 2));
+        DeviceArena arena;
+        ArenaBuf<float> vert_arena(arena), uv_arena(arena), xforms(arena);
+        ArenaBuf<uint32_t> index_arena(arena), bad(arena);
+        ArenaBuf<crt::DevSegment> d_segs(arena);
+        auto carve = [&] {
+            vert_arena.alloc(nv * 3);
+            index_arena.alloc(nt * 3);
+            uv_arena.alloc(nuv * 2);
+            xforms.alloc((size_t)scene->num_instances * 32);
+            d_segs.alloc(segs.size());
+            bad.alloc(1);
+        };
+        carve();
+        arena.commit();
+        carve();
         for (const Copy &c : copies) {
             CUDA_CHECK(cudaMemcpyAsync(vert_arena.ptr + (size_t)c.at.vert_off * 3, c.geom->vertices,
                                        (size_t)c.geom->num_vertices * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
@@ -452,10 +498,9 @@ struct crtc_renderer {
             std::memcpy(&xf[(size_t)i * 32], scene->instances[i].transform, 16 * sizeof(float));
             std::memcpy(&xf[(size_t)i * 32 + 16], &plan.w2o_all[(size_t)i * 16], 16 * sizeof(float));
         }
-        xforms.upload(xf.data(), xf.size(), stream);
-        d_segs.upload(segs.data(), segs.size(), stream);
-        const uint32_t zero = 0u;
-        bad.upload(&zero, 1, stream);
+        CUDA_CHECK(cudaMemcpyAsync(xforms.ptr, xf.data(), xf.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+        CUDA_CHECK(cudaMemcpyAsync(d_segs.ptr, segs.data(), segs.size() * sizeof(crt::DevSegment), cudaMemcpyHostToDevice, stream));
+        CUDA_CHECK(cudaMemsetAsync(bad.ptr, 0, sizeof(uint32_t), stream));
         d_verts.alloc((size_t)total * 9);
         d_shade_in.alloc((size_t)total * 3);
         int sms = 0;
@@ -487,40 +532,53 @@ struct crtc_renderer {
         CUDA_CHECK(cudaEventCreate(&ev0));
         CUDA_CHECK(cudaEventCreate(&ev1));
         const uint32_t num_b2 = 2 * n - 1, max_nodes = std::max(1u, n - 1);
-        DeviceBuffer<float4> tri_lo, tri_hi, box_lo, box_hi, nodes_tmp;
-        DeviceBuffer<uint32_t> cbounds, vals0, vals1, hist, d_parent, arrivals, slots, work0, work1, tri_order, clusters0,
-            clusters1, nn;
-        DeviceBuffer<crt::u64> keys0, keys1, counts, offsets, scan_scratch;
-        DeviceBuffer<uint2> d_children;
-        DeviceBuffer<float> cost;
-        DeviceBuffer<uint8_t> decision;
+        DeviceArena arena;
+        ArenaBuf<float4> tri_lo(arena), tri_hi(arena), box_lo(arena), box_hi(arena), nodes_tmp(arena);
+        ArenaBuf<uint32_t> cbounds(arena), vals0(arena), vals1(arena), hist(arena), d_parent(arena), arrivals(arena), slots(arena),
+            work0(arena), work1(arena), tri_order(arena), clusters0(arena), clusters1(arena), nn(arena);
+        ArenaBuf<crt::u64> keys0(arena), keys1(arena), counts(arena), offsets(arena), scan_scratch(arena);
+        ArenaBuf<uint2> d_children(arena);
+        ArenaBuf<float> cost(arena);
+        ArenaBuf<uint8_t> decision(arena);
         static_assert(sizeof(crt::TriShade) == 3 * sizeof(float4), "TriShade = 3 float4");
         CUDA_CHECK(cudaEventRecord(ev0, stream));
-        tri_lo.alloc(n);
-        tri_hi.alloc(n);
-        const uint32_t cb_init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
-        cbounds.upload(cb_init, 6, stream);
-        keys0.alloc(n);
-        keys1.alloc(n);
-        vals0.alloc(n);
-        vals1.alloc(n);
         const uint32_t tiles = (n + crt::kBuildTile - 1) / crt::kBuildTile;
-        hist.alloc((size_t)tiles * 256);
-        d_children.alloc(std::max(1u, n - 1));
-        d_parent.alloc(num_b2);
-        box_lo.alloc(num_b2);
-        box_hi.alloc(num_b2);
-        arrivals.alloc(std::max(1u, n - 1));
-        cost.alloc((size_t)num_b2 * 7);
-        decision.alloc((size_t)num_b2 * 7);
-        slots.alloc((size_t)max_nodes * 8);
-        work0.alloc(max_nodes);
-        work1.alloc(max_nodes);
-        counts.alloc(n);
-        offsets.alloc(n);
-        scan_scratch.alloc(std::max(scan_scratch_items(n), (scan_scratch_items((size_t)tiles * 256) + 1) / 2 + 1));
-        nodes_tmp.alloc((size_t)max_nodes * 5);
-        tri_order.alloc(n);
+        auto carve = [&] {
+            tri_lo.alloc(n);
+            tri_hi.alloc(n);
+            cbounds.alloc(6);
+            keys0.alloc(n);
+            keys1.alloc(n);
+            vals0.alloc(n);
+            vals1.alloc(n);
+            hist.alloc((size_t)tiles * 256);
+            d_children.alloc(n);
+            box_lo.alloc(num_b2);
+            box_hi.alloc(num_b2);
+            cost.alloc((size_t)num_b2 * 7);
+            decision.alloc((size_t)num_b2 * 7);
+            slots.alloc((size_t)max_nodes * 8);
+            work0.alloc(max_nodes);
+            work1.alloc(max_nodes);
+            counts.alloc(n);
+            offsets.alloc(n);
+            scan_scratch.alloc(std::max(scan_scratch_items(n), (scan_scratch_items((size_t)tiles * 256) + 1) / 2 + 1));
+            nodes_tmp.alloc((size_t)max_nodes * 5);
+            tri_order.alloc(n);
+            if (bvh_builder == 2) {
+                d_parent.alloc(num_b2);
+                arrivals.alloc(n);
+            } else {
+                clusters0.alloc(n);
+                clusters1.alloc(n);
+                nn.alloc(n);
+            }
+        };
+        carve();
+        arena.commit();
+        carve();
+        const uint32_t cb_init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+        CUDA_CHECK(cudaMemcpyAsync(cbounds.ptr, cb_init, sizeof(cb_init), cudaMemcpyHostToDevice, stream));
 
         crt::Lbvh b;
         b.n = n;
@@ -566,9 +624,6 @@ struct crtc_renderer {
                 root = n;
             }
         } else {
-            clusters0.alloc(n);
-            clusters1.alloc(n);
-            nn.alloc(n);
             uint32_t *cl = clusters0.ptr, *cl_next = clusters1.ptr;
             crt::k_bvh2_leaves<<<g, crt::kBuildBlock, 0, stream>>>(b, vin, cl);
             uint32_t m = n, nodes_made = 0;
