@@ -326,7 +326,7 @@ def main():
     import torch.distributed as dist
 
     from chameleonrt_b200 import RenderCUDA
-    from chameleonrt_b200.distributed import FrameGatherer
+    from chameleonrt_b200.distributed import FrameGatherer, PeerFrame
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -354,7 +354,10 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    gatherer = FrameGatherer(gpu) if world > 1 else None
+    # CRT_BENCH_FRAME=peer: no gather, every rank's resolve kernel writes into rank 0's frame over NVLink (PeerFrame;
+    # opt-in until it has been timed: the gather is the path the committed multi-GPU numbers were measured with)
+    peer_frame = os.environ.get("CRT_BENCH_FRAME", "gather") == "peer"
+    gatherer = (PeerFrame(gpu) if peer_frame else FrameGatherer(gpu)) if world > 1 else None
 
     def frame(f, readback):
         """One step. N > 1: the frame-end gather of frame f is started here and overlaps the
@@ -448,7 +451,7 @@ def main():
     assert nframes == args.steps
     rays = totals.num_rays
     n_batches = -(-args.steps // frames_in_flight)
-    launches = csum["kernel_launches"] + (n_batches * world if (world > 1 and rank == 0) else 0)  # + k_assemble
+    launches = csum["kernel_launches"] + (n_batches * world if (world > 1 and rank == 0 and not peer_frame) else 0)  # + k_assemble
     elapsed_ms = e0.elapsed_time(e1)
     clock_summary = clocks.summary()
 
@@ -503,9 +506,11 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "spp": SPP, "max_depth": MAX_DEPTH,
                        "parallelism": (f"image tiles 64x64 round-robin over {world} GPUs, scene replicated; {frames_in_flight} "
-                                       "consecutive frames per wavefront (bit-identical to frame-by-frame), NCCL gather "
-                                       "of the accumulated tiles to rank 0 once per batch (stream-ordered, not "
-                                       "overlapped); e2e: frame by frame, gather + readback every frame") if world > 1 else "single GPU",
+                                       "consecutive frames per wavefront (bit-identical to frame-by-frame), " +
+                                       ("tiles written into rank 0's frame by every rank's resolve kernel through peer-mapped "
+                                        "memory (no gather; a one-element all-reduce per batch as the barrier)" if peer_frame else
+                                        "NCCL gather of the accumulated tiles to rank 0 once per batch (stream-ordered, not overlapped)") +
+                                       "; e2e: frame by frame, assembly + readback every frame") if world > 1 else "single GPU",
                        "frames_in_flight": frames_in_flight,
                        "shadow_ray_order": {1: "far-first", 0: "near-first"}.get(shadow_far_first, "undecided (near-first)") +
                                            " (chosen per scene from the traversal times of warm-up frames 1 and 2; same image either way)",

@@ -34,7 +34,7 @@ C_ABI_SYMBOLS = (
     "crtc_last_error", "crtc_name", "crtc_create", "crtc_destroy", "crtc_set_option", "crtc_get_option", "crtc_set_stream",
     "crtc_initialize", "crtc_set_scene", "crtc_render", "crtc_render_async", "crtc_sync", "crtc_read_accum", "crtc_get_stage_times",
     "crtc_get_counters", "crtc_get_scene_info", "crtc_trace_closest", "crtc_trace_any", "crtc_bench_trace",
-    "crtc_local_buffers", "crtc_assemble_rank", "crtc_read_img",
+    "crtc_local_buffers", "crtc_assemble_rank", "crtc_export_frame", "crtc_import_frame", "crtc_read_img",
 )
 
 
@@ -77,6 +77,8 @@ def load_lib() -> C.CDLL:
     lib.crtc_bench_trace.argtypes = [vp, vp, C.c_uint64, C.c_int, C.c_int, fp]
     lib.crtc_local_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint32)]
     lib.crtc_assemble_rank.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    lib.crtc_export_frame.argtypes = [vp, C.c_char_p]
+    lib.crtc_import_frame.argtypes = [vp, C.c_char_p]
     _lib = lib
     return lib
 
@@ -245,6 +247,19 @@ class RenderCUDA:
         a, i, n = C.c_void_p(), C.c_void_p(), C.c_uint32()
         self._check(self.lib.crtc_local_buffers(self.h, C.byref(a), C.byref(i), C.byref(n)))
         return a.value, i.value, n.value
+
+    def export_frame(self) -> bytes:
+        """On the assembling rank: 128 bytes (two CUDA IPC handles) that let the other ranks' renderers write their
+        tiles straight into this renderer's full frame (crtc_export_frame)."""
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.crtc_export_frame(self.h, buf))
+        return buf.raw
+
+    def import_frame(self, handles: Optional[bytes]) -> None:
+        """On every other rank: map the assembling rank's frame (crtc_import_frame); None unmaps."""
+        if handles is not None and len(handles) != 128:
+            raise ValueError("import_frame expects the 128 bytes of export_frame")
+        self._check(self.lib.crtc_import_frame(self.h, handles))
 
     def assemble_rank(self, src_rank: int, world_size: int, accum_dev_ptr: int, img_dev_ptr: int) -> None:
         self._check(self.lib.crtc_assemble_rank(self.h, src_rank, world_size, C.c_void_p(accum_dev_ptr),

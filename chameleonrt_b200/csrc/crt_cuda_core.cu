@@ -231,8 +231,58 @@ struct crtc_renderer {
     float stage_ms[kNumStages] = {0};   // last collected frame
     uint64_t counters_out[8] = {0};     // last collected frame
 
+    // Peer-written frames (multi-GPU without a gather): the assembling rank exports its full-frame buffers as CUDA
+    // IPC handles, the other ranks map them and their k_resolve stores each pixel there as well (st.global to a
+    // peer address over NVLink). Tile ownership is disjoint, so there is nothing to reduce.
+    bool frame_exported = false;
+    float *peer_accum_full = nullptr;
+    uint32_t *peer_img_full = nullptr;
+
+    void close_peer_frame()
+    {
+        if (peer_accum_full) {
+            cudaIpcCloseMemHandle(peer_accum_full);
+            cudaIpcCloseMemHandle(peer_img_full);
+            peer_accum_full = nullptr;
+            peer_img_full = nullptr;
+        }
+    }
+    void export_frame(void *handles_out)
+    {
+        if (fb_w == 0) {
+            throw std::runtime_error("crtc_export_frame: initialize() has not been called");
+        }
+        make_current();
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "two 64-byte handles");
+        cudaIpcMemHandle_t h[2];
+        CUDA_CHECK(cudaIpcGetMemHandle(&h[0], d_accum_full.ptr));
+        CUDA_CHECK(cudaIpcGetMemHandle(&h[1], d_img_full.ptr));
+        std::memcpy(handles_out, h, sizeof(h));
+        frame_exported = true;
+    }
+    void import_frame(const void *handles)
+    {
+        make_current();
+        close_peer_frame();
+        if (!handles) {
+            return;
+        }
+        cudaIpcMemHandle_t h[2];
+        std::memcpy(h, handles, sizeof(h));
+        void *a = nullptr, *i = nullptr;
+        CUDA_CHECK(cudaIpcOpenMemHandle(&a, h[0], cudaIpcMemLazyEnablePeerAccess));
+        const cudaError_t err = cudaIpcOpenMemHandle(&i, h[1], cudaIpcMemLazyEnablePeerAccess);
+        if (err != cudaSuccess) {
+            cudaIpcCloseMemHandle(a);
+            CUDA_CHECK(err);
+        }
+        peer_accum_full = static_cast<float *>(a);
+        peer_img_full = static_cast<uint32_t *>(i);
+    }
+
     ~crtc_renderer()
     {
+        close_peer_frame();
         in_flight.clear();
         record_pool.clear();
         if (own_stream) {
@@ -356,6 +406,9 @@ struct crtc_renderer {
             throw std::runtime_error("initialize: framebuffer dimensions must be positive");
         }
         make_current();
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+        close_peer_frame();      // the frame's shape (and on the exporting rank, its buffers) change:
+        frame_exported = false;  // crtc_export_frame / crtc_import_frame must be called again
         frame_id = 0;
         fb_w = w;
         fb_h = h;
@@ -914,9 +967,19 @@ struct crtc_renderer {
                 rec.launches += 3;
             }
             const unsigned gpx = (unsigned)((npx_local + 255) / 256);
-            const bool full = world_size == 1;
-            crt::k_resolve<<<gpx, 256, 0, stream>>>(fl, ps, frame_id, d_accum_local.ptr, d_img_local.ptr,
-                                                    full ? d_accum_full.ptr : nullptr, full ? d_img_full.ptr : nullptr);
+            // where the resolved pixels also go as a full row-major frame: this renderer's own full frame (single
+            // GPU, or the assembling rank of a peer-written frame), the assembling rank's full frame over NVLink
+            // (crtc_import_frame), or nowhere (tiles are gathered afterwards: crtc_local_buffers)
+            float *full_accum = nullptr;
+            uint32_t *full_img = nullptr;
+            if (world_size == 1 || frame_exported) {
+                full_accum = d_accum_full.ptr;
+                full_img = d_img_full.ptr;
+            } else if (peer_accum_full) {
+                full_accum = peer_accum_full;
+                full_img = peer_img_full;
+            }
+            crt::k_resolve<<<gpx, 256, 0, stream>>>(fl, ps, frame_id, d_accum_local.ptr, d_img_local.ptr, full_accum, full_img);
             rec.launches += 1;
             rec.mark(stream, kStResolve);
         }
@@ -1486,5 +1549,20 @@ int crtc_local_buffers(crtc_renderer *r, void **accum_dev, void **img_dev, uint3
 int crtc_assemble_rank(crtc_renderer *r, int src_rank, int world_size, const void *accum_dev, const void *img_dev)
 {
     CRTC_TRY({ r->assemble_rank(src_rank, world_size, accum_dev, img_dev); })
+}
+
+int crtc_export_frame(crtc_renderer *r, void *handles_out)
+{
+    CRTC_TRY({
+        if (!handles_out) {
+            throw std::runtime_error("crtc_export_frame: null output");
+        }
+        r->export_frame(handles_out);
+    })
+}
+
+int crtc_import_frame(crtc_renderer *r, const void *handles)
+{
+    CRTC_TRY({ r->import_frame(handles); })
 }
 }

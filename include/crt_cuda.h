@@ -160,8 +160,17 @@ int crtc_local_buffers(crtc_renderer *r, void **accum_dev, void **img_dev, uint3
  * the full row-major frame of this renderer. */
 int crtc_assemble_rank(crtc_renderer *r, int src_rank, int world_size, const void *accum_dev,
                        const void *img_dev);
-/* Read the assembled full frame (after crtc_assemble_rank for every rank, or after a
- * world_size==1 render). */
+/* Multi-GPU without a gather (one process per GPU): the assembling rank exports its full-frame buffers
+ * (handles_out: 128 bytes = two cudaIpcMemHandle_t, accum then img) and keeps writing its own tiles there; every
+ * other rank imports them (ship the 128 bytes with any transport, e.g. torch.distributed.broadcast) and from then
+ * on its frame-end resolve stores each of its pixels straight into the assembling rank's frame over NVLink, next to
+ * its tile-local copy. Tile ownership is disjoint: nothing is reduced, no copy kernel runs. The assembling rank must
+ * not read the frame before every rank's frame has completed (a stream-ordered barrier, e.g. a one-element
+ * all-reduce, is enough). crtc_initialize undoes both; crtc_import_frame(r, NULL) unmaps. */
+int crtc_export_frame(crtc_renderer *r, void *handles_out);
+int crtc_import_frame(crtc_renderer *r, const void *handles);
+/* Read the assembled full frame (after crtc_assemble_rank for every rank, after every rank's peer-written
+ * frame has completed, or after a world_size==1 render). */
 int crtc_read_img(crtc_renderer *r, uint32_t *img);
 
 #ifdef __cplusplus

@@ -106,4 +106,18 @@ cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b)
     *ms = std::chrono::duration<float, std::milli>(reinterpret_cast<EmuEvent *>(b)->t - reinterpret_cast<EmuEvent *>(a)->t).count();
     return cudaSuccess;
 }
+// CUDA IPC inside one process: the handle carries the pointer (real CUDA refuses to open a handle in the process
+// that exported it; with the emulation all "ranks" of a test live in one process)
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *handle, void *dev_ptr)
+{
+    std::memset(handle, 0, sizeof(*handle));
+    std::memcpy(handle, &dev_ptr, sizeof(dev_ptr));
+    return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void **dev_ptr, cudaIpcMemHandle_t handle, unsigned int)
+{
+    std::memcpy(dev_ptr, &handle, sizeof(*dev_ptr));
+    return *dev_ptr ? cudaSuccess : cudaErrorInvalidValue;
+}
+cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
 }

@@ -98,6 +98,23 @@ def test_frames_in_flight_sharding_and_shadow_order_on_the_emulated_renderer(mod
         ranks[0].assemble_rank(src, 2, acc, img)
     assert got == rays and (ranks[0].read_accum().view(np.uint32) == want.view(np.uint32)).all()
     assert (ranks[0].read_img() == want_img).all()
+    # the same two ranks WITHOUT a gather: rank 0 exports its frame, rank 1 maps it, both resolve kernels write into it
+    ranks, got = [], 0
+    for rank in range(2):
+        r = RenderCUDA(0, rank=rank, world_size=2)
+        r.initialize(w, h)
+        r.set_scene(scene)
+        ranks.append(r)
+    ranks[1].import_frame(ranks[0].export_frame())
+    for r in ranks:
+        r.render_async(*args, True, 2)
+        r.render_async(*args, False, 1)
+        got += r.sync()[0].num_rays
+    assert got == rays and (ranks[0].read_accum().view(np.uint32) == want.view(np.uint32)).all()
+    assert (ranks[0].read_img() == want_img).all()
+    ranks[1].import_frame(None)
+    with pytest.raises(ValueError):
+        ranks[1].import_frame(b"short")
     # shadow rays far-first: on, and decided per scene from frames 1 and 2 — same image
     for mode in (1, 2):
         r = RenderCUDA(0, any_far_first=mode)

@@ -203,3 +203,26 @@ def test_triangle_pass_deferral_does_not_change_the_image(mods, size=(256, 144),
         assert cn["closest_tris_tested"] > 0 and cn["closest_nodes_visited"] >= c0["closest_nodes_visited"]
     with pytest.raises(RuntimeError, match="tri_pass_defer"):
         RenderCUDA(0, tri_pass_defer=8)
+
+
+def test_peer_written_frame_two_processes_one_gpu(built):
+    """Frame assembly without a gather (crtc_export_frame / crtc_import_frame): two PROCESSES, both on cuda:0 (gloo
+    carries the 128 handle bytes; NCCL would refuse two ranks on one GPU), rank 1's resolve kernel writes its tiles
+    into rank 0's frame through the CUDA IPC mapping; the assembled frame must equal the single-renderer frame bit for
+    bit. The N-GPU form of the same check (NVLink, NCCL barrier) is tests/test_multi_gpu.py."""
+    import os
+    import socket
+    import subprocess
+    import sys
+
+    from helpers import ROOT
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "scripts", "mgpu_check.py"), "320", "200", "--one-gpu"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MGPU_OK 2 peer" in r.stdout, r.stdout[-2000:]
