@@ -6,9 +6,12 @@
 // copied on this side; the core library copies what it needs (the reference destroys its Scene
 // right after set_scene, main.cpp:185-214).
 #include "render_cuda.h"
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <stdexcept>
+#include <thread>
 #include <vector>
 #include "crt_cuda.h"
 #include "scene.h"
@@ -33,21 +36,62 @@ long env_or(const char *name, long fallback)
     const char *v = std::getenv(name);
     return v && *v ? std::strtol(v, nullptr, 10) : fallback;
 }
+
+// CRT_CUDA_DEVICES: a comma-separated list of CUDA device ordinals ("0,1,2,3"; a device may be named twice, which
+// shards the image over two renderers on the same GPU — only useful for testing the fan-out on a one-GPU machine).
+std::vector<int> devices_from_env()
+{
+    std::vector<int> devices;
+    if (const char *v = std::getenv("CRT_CUDA_DEVICES")) {
+        const char *p = v;
+        while (*p) {
+            char *end = nullptr;
+            const long d = std::strtol(p, &end, 10);
+            if (end == p) {
+                throw std::runtime_error(std::string("crt_cuda: cannot parse CRT_CUDA_DEVICES='") + v + "'");
+            }
+            devices.push_back(static_cast<int>(d));
+            p = *end == ',' ? end + 1 : end;
+        }
+    }
+    if (devices.empty()) {
+        devices.push_back(static_cast<int>(env_or("CRT_CUDA_DEVICE", 0)));
+    }
+    return devices;
+}
 }
 
 RenderCUDA::RenderCUDA()
 {
     // The plugin API has no option channel: knobs come from the environment.
-    check(crtc_create(&renderer, static_cast<int>(env_or("CRT_CUDA_DEVICE", 0))));
-    check(crtc_set_option(renderer, "max_depth", env_or("CRT_CUDA_MAX_DEPTH", 5)));
-    check(crtc_set_option(renderer, "bvh_threads", env_or("CRT_CUDA_BVH_THREADS", 0)));
-    check(crtc_set_option(renderer, "bvh_builder", env_or("CRT_CUDA_BVH_BUILDER", 0)));  // 1 / 2 = build on the device (crt_cuda.h)
-    check(crtc_set_option(renderer, "any_far_first", env_or("CRT_CUDA_ANY_FAR_FIRST", 2)));  // crt_cuda.h; 2 = per scene
+    const std::vector<int> devices = devices_from_env();
+    try {
+        for (size_t i = 0; i < devices.size(); ++i) {
+            crtc_renderer *r = nullptr;
+            check(crtc_create(&r, devices[i]));
+            renderers.push_back(r);
+            check(crtc_set_option(r, "world_size", static_cast<int64_t>(devices.size())));
+            check(crtc_set_option(r, "rank", static_cast<int64_t>(i)));
+            check(crtc_set_option(r, "max_depth", env_or("CRT_CUDA_MAX_DEPTH", 5)));
+            check(crtc_set_option(r, "bvh_threads", env_or("CRT_CUDA_BVH_THREADS", 0)));
+            check(crtc_set_option(r, "bvh_builder", env_or("CRT_CUDA_BVH_BUILDER", 0)));  // 1 / 2 = build on the device (crt_cuda.h)
+            check(crtc_set_option(r, "any_far_first", env_or("CRT_CUDA_ANY_FAR_FIRST", 2)));  // crt_cuda.h; 2 = per scene
+        }
+    } catch (...) {
+        for (crtc_renderer *r : renderers) {
+            crtc_destroy(r);
+        }
+        throw;
+    }
+    renderer = renderers[0];
 }
 
 RenderCUDA::~RenderCUDA()
 {
-    crtc_destroy(renderer);
+    // the renderers that write into renderers[0]'s frame go first
+    for (size_t i = renderers.size(); i-- > 0;) {
+        crtc_destroy(renderers[i]);
+    }
 }
 
 std::string RenderCUDA::name()
@@ -59,7 +103,12 @@ void RenderCUDA::initialize(const int fb_width, const int fb_height)
 {
     fb_dims = glm::ivec2(fb_width, fb_height);
     img.resize(static_cast<size_t>(fb_width) * fb_height);
-    check(crtc_initialize(renderer, fb_width, fb_height));
+    for (crtc_renderer *r : renderers) {
+        check(crtc_initialize(r, fb_width, fb_height));
+    }
+    for (size_t i = 1; i < renderers.size(); ++i) {
+        check(crtc_share_frame(renderers[0], renderers[i]));
+    }
 }
 
 void RenderCUDA::set_scene(const Scene &scene)
@@ -124,7 +173,31 @@ void RenderCUDA::set_scene(const Scene &scene)
     c.num_textures = static_cast<uint32_t>(textures.size());
     c.num_lights = static_cast<uint32_t>(scene.lights.size());
     c.samples_per_pixel = scene.samples_per_pixel;
-    check(crtc_set_scene(renderer, &c));
+    if (renderers.size() == 1) {
+        check(crtc_set_scene(renderer, &c));
+        return;
+    }
+    // every GPU gets its own copy of the scene and builds its own BVH (the scene is replicated): one
+    // host thread per renderer, errors collected and rethrown here as the reference would throw them
+    std::vector<std::exception_ptr> errors(renderers.size());
+    std::vector<std::thread> workers;
+    for (size_t i = 0; i < renderers.size(); ++i) {
+        workers.emplace_back([&, i] {
+            try {
+                check(crtc_set_scene(renderers[i], &c));
+            } catch (...) {
+                errors[i] = std::current_exception();
+            }
+        });
+    }
+    for (std::thread &w : workers) {
+        w.join();
+    }
+    for (const std::exception_ptr &e : errors) {
+        if (e) {
+            std::rethrow_exception(e);
+        }
+    }
 }
 
 RenderStats RenderCUDA::render(const glm::vec3 &pos,
@@ -134,9 +207,30 @@ RenderStats RenderCUDA::render(const glm::vec3 &pos,
                                const bool camera_changed,
                                const bool readback_framebuffer)
 {
-    crt_render_stats_t s;
     // with a non-native display the app reads `img` every frame (gldisplay.cpp:111-123)
     const bool readback = readback_framebuffer || !native_display;
+    if (renderers.size() > 1) {
+        // fan out: every GPU is handed its share of the frame before any of them is waited for; each resolves its
+        // tiles into renderers[0]'s frame, which is complete once all of them have finished
+        const auto t0 = std::chrono::steady_clock::now();
+        for (crtc_renderer *r : renderers) {
+            check(crtc_render_async(r, &pos.x, &dir.x, &up.x, fovy, camera_changed ? 1 : 0, 1));
+        }
+        uint64_t rays = 0;
+        for (crtc_renderer *r : renderers) {
+            crt_render_stats_t part;
+            check(crtc_sync(r, &part, nullptr, nullptr, nullptr));
+            rays += part.num_rays;
+        }
+        if (readback) {
+            check(crtc_read_img(renderers[0], img.data()));
+        }
+        RenderStats stats;
+        stats.render_time = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        stats.rays_per_second = static_cast<float>(static_cast<double>(rays) / (stats.render_time * 1e-3));
+        return stats;
+    }
+    crt_render_stats_t s;
     check(crtc_render(renderer,
                       &pos.x,
                       &dir.x,

@@ -9,12 +9,17 @@
 #pragma once
 
 #include <string>
+#include <vector>
 #include "render_backend.h"
 
 struct crtc_renderer;
 
 struct RenderCUDA : RenderBackend {
-    crtc_renderer *renderer = nullptr;
+    // One renderer per GPU (CRT_CUDA_DEVICES, default: the single device CRT_CUDA_DEVICE). Renderer i owns the image
+    // tiles with tile_id % N == i (the reference's tile ids, render_embree.cpp:178-180) and resolves them straight
+    // into the frame of renderers[0] over NVLink (crtc_share_frame), which is the one `img` is read from.
+    std::vector<crtc_renderer *> renderers;
+    crtc_renderer *renderer = nullptr;  // = renderers[0]
     glm::ivec2 fb_dims = glm::ivec2(0);
     bool native_display = false;
 

@@ -34,7 +34,7 @@ C_ABI_SYMBOLS = (
     "crtc_last_error", "crtc_name", "crtc_create", "crtc_destroy", "crtc_set_option", "crtc_get_option", "crtc_set_stream",
     "crtc_initialize", "crtc_set_scene", "crtc_render", "crtc_render_async", "crtc_sync", "crtc_read_accum", "crtc_get_stage_times",
     "crtc_get_counters", "crtc_get_scene_info", "crtc_trace_closest", "crtc_trace_any", "crtc_bench_trace",
-    "crtc_local_buffers", "crtc_assemble_rank", "crtc_export_frame", "crtc_import_frame", "crtc_read_img",
+    "crtc_local_buffers", "crtc_assemble_rank", "crtc_export_frame", "crtc_import_frame", "crtc_share_frame", "crtc_read_img",
 )
 
 
@@ -79,6 +79,7 @@ def load_lib() -> C.CDLL:
     lib.crtc_assemble_rank.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     lib.crtc_export_frame.argtypes = [vp, C.c_char_p]
     lib.crtc_import_frame.argtypes = [vp, C.c_char_p]
+    lib.crtc_share_frame.argtypes = [vp, vp]
     _lib = lib
     return lib
 
@@ -260,6 +261,11 @@ class RenderCUDA:
         if handles is not None and len(handles) != 128:
             raise ValueError("import_frame expects the 128 bytes of export_frame")
         self._check(self.lib.crtc_import_frame(self.h, handles))
+
+    def share_frame_with(self, src: "RenderCUDA") -> None:
+        """In-process multi-GPU: ``src`` (another RenderCUDA of this process, same size) resolves its tiles into this
+        renderer's full frame from now on (crtc_share_frame)."""
+        self._check(self.lib.crtc_share_frame(self.h, src.h))
 
     def assemble_rank(self, src_rank: int, world_size: int, accum_dev_ptr: int, img_dev_ptr: int) -> None:
         self._check(self.lib.crtc_assemble_rank(self.h, src_rank, world_size, C.c_void_p(accum_dev_ptr),

@@ -237,15 +237,47 @@ struct crtc_renderer {
     bool frame_exported = false;
     float *peer_accum_full = nullptr;
     uint32_t *peer_img_full = nullptr;
+    bool peer_is_ipc = false;  // mapped through cudaIpcOpenMemHandle (another process) or a plain peer pointer (this one)
 
     void close_peer_frame()
     {
-        if (peer_accum_full) {
+        if (peer_accum_full && peer_is_ipc) {
             cudaIpcCloseMemHandle(peer_accum_full);
             cudaIpcCloseMemHandle(peer_img_full);
-            peer_accum_full = nullptr;
-            peer_img_full = nullptr;
         }
+        peer_accum_full = nullptr;
+        peer_img_full = nullptr;
+    }
+    // The in-process form (one host thread driving several renderers, as the ChameleonRT plugin does): this renderer
+    // resolves its tiles into `dst`'s full frame; different devices need peer access, which NVSwitch gives every pair.
+    void share_frame_of(crtc_renderer *dst)
+    {
+        if (dst == this) {
+            throw std::runtime_error("crtc_share_frame: source and destination are the same renderer");
+        }
+        if (fb_w == 0 || dst->fb_w != fb_w || dst->fb_h != fb_h) {
+            throw std::runtime_error("crtc_share_frame: both renderers must be initialized with the same size");
+        }
+        make_current();
+        close_peer_frame();
+        if (dst->device != device) {
+            int can = 0;
+            CUDA_CHECK(cudaDeviceCanAccessPeer(&can, device, dst->device));
+            if (!can) {
+                throw std::runtime_error("crtc_share_frame: device " + std::to_string(device) + " cannot access device " +
+                                         std::to_string(dst->device));
+            }
+            const cudaError_t err = cudaDeviceEnablePeerAccess(dst->device, 0);
+            if (err == cudaErrorPeerAccessAlreadyEnabled) {
+                cudaGetLastError();  // not an error: clear it
+            } else {
+                CUDA_CHECK(err);
+            }
+        }
+        peer_accum_full = dst->d_accum_full.ptr;
+        peer_img_full = dst->d_img_full.ptr;
+        peer_is_ipc = false;
+        dst->frame_exported = true;
     }
     void export_frame(void *handles_out)
     {
@@ -278,6 +310,7 @@ struct crtc_renderer {
         }
         peer_accum_full = static_cast<float *>(a);
         peer_img_full = static_cast<uint32_t *>(i);
+        peer_is_ipc = true;
     }
 
     ~crtc_renderer()
@@ -1564,5 +1597,15 @@ int crtc_export_frame(crtc_renderer *r, void *handles_out)
 int crtc_import_frame(crtc_renderer *r, const void *handles)
 {
     CRTC_TRY({ r->import_frame(handles); })
+}
+
+int crtc_share_frame(crtc_renderer *dst, crtc_renderer *src)
+{
+    CRTC_TRY({
+        if (!dst || !src) {
+            throw std::runtime_error("crtc_share_frame: null renderer");
+        }
+        src->share_frame_of(dst);
+    })
 }
 }

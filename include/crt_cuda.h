@@ -169,6 +169,10 @@ int crtc_assemble_rank(crtc_renderer *r, int src_rank, int world_size, const voi
  * all-reduce, is enough). crtc_initialize undoes both; crtc_import_frame(r, NULL) unmaps. */
 int crtc_export_frame(crtc_renderer *r, void *handles_out);
 int crtc_import_frame(crtc_renderer *r, const void *handles);
+/* The same within ONE process (one host thread driving a renderer per GPU, as backends/cuda does for
+ * CRT_CUDA_DEVICES): from now on `src` resolves its tiles into `dst`'s full frame; peer access between the two
+ * devices is enabled if they differ. Both must be initialized with the same size; crtc_initialize undoes it. */
+int crtc_share_frame(crtc_renderer *dst, crtc_renderer *src);
 /* Read the assembled full frame (after crtc_assemble_rank for every rank, after every rank's peer-written
  * frame has completed, or after a world_size==1 render). */
 int crtc_read_img(crtc_renderer *r, uint32_t *img);

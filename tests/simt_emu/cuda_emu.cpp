@@ -120,4 +120,10 @@ cudaError_t cudaIpcOpenMemHandle(void **dev_ptr, cudaIpcMemHandle_t handle, unsi
     return *dev_ptr ? cudaSuccess : cudaErrorInvalidValue;
 }
 cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+cudaError_t cudaDeviceCanAccessPeer(int *can, int, int)
+{
+    *can = 1;
+    return cudaSuccess;
+}
+cudaError_t cudaDeviceEnablePeerAccess(int, unsigned int) { return cudaSuccess; }
 }

@@ -159,6 +159,12 @@ def test_drop_in_plugin_on_the_emulated_core(built, tmp_path):
     for builder in ("1", "2"):
         a_dev, _, _ = run_headless("cuda_simt", obj, cam, 96, 64, 2, 2, tmp_path, extra_env={"CRT_CUDA_BVH_BUILDER": builder})
         assert np.array_equal(a_dev.view(np.uint32), a_gpu.view(np.uint32))
+    # CRT_CUDA_DEVICES: the plugin drives one renderer per GPU from its single host thread, tiles interleaved, every
+    # renderer resolving into the first one's frame (crtc_share_frame) — same frame, bit for bit (the emulation has 8
+    # "devices"); also two renderers on one device, the form a one-GPU box can run
+    for devices in ("0,1,2", "0,0"):
+        a_multi, _, out_multi = run_headless("cuda_simt", obj, cam, 96, 64, 2, 2, tmp_path, extra_env={"CRT_CUDA_DEVICES": devices})
+        assert np.array_equal(a_multi.view(np.uint32), a_gpu.view(np.uint32)), devices
     with pytest.raises(AssertionError, match="bvh_builder must be"):  # the knob does reach the core
         run_headless("cuda_simt", obj, cam, 96, 64, 2, 2, tmp_path, extra_env={"CRT_CUDA_BVH_BUILDER": "7"})
     if not FULL:
@@ -195,7 +201,7 @@ def test_device_bvh_builder_on_the_emulated_renderer(mods):
              ("instances", lambda: san_miguel_like(spp=1, scale=0.02, tex_size=32), 48, 32, 1, 5)]
     if FULL:
         cases.append(("voxels", lambda: rungholt_like(spp=1, scale=0.1), 48, 32, 1, 5))
-    import test_z_device_bvh_build as dev_tests
+    import test_z_new_gpu_paths as dev_tests
 
     dev_tests.test_device_built_bvh_renders_the_same_image(mods, cases)
     dev_tests.test_device_built_bvh_edge_cases(mods, big=4099 if FULL else 2500)
@@ -205,6 +211,6 @@ def test_device_bvh_builder_on_the_emulated_renderer(mods):
 
 def test_triangle_pass_deferral_on_the_emulated_renderer(mods):
     """k_traverse<COUNT, DEFER> (option tri_pass_defer) in the whole renderer: same frames, same ray counts."""
-    import test_z_device_bvh_build as dev_tests
+    import test_z_new_gpu_paths as dev_tests
 
     dev_tests.test_triangle_pass_deferral_does_not_change_the_image(mods, size=(48, 32), detail=0.2)

@@ -226,3 +226,31 @@ def test_peer_written_frame_two_processes_one_gpu(built):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MGPU_OK 2 peer" in r.stdout, r.stdout[-2000:]
+
+
+def test_cuda_plugin_fans_out_over_renderers(built, tmp_path):
+    """CRT_CUDA_DEVICES: the C++ plugin drives one renderer per listed device from the application's single thread
+    (tiles interleaved, every renderer resolving into the first one's frame: crtc_share_frame). A one-GPU box can list
+    its device twice — two renderers, two streams, one frame; with more GPUs the list names each once (peer access over
+    NVLink). Same frame as the single renderer, bit for bit; also through the device BVH builder."""
+    import torch
+
+    from chameleonrt_b200.obj_io import write_obj
+    from chameleonrt_b200.scenes import sponza_like
+    from test_reference_plugin import HEADLESS, run_headless
+
+    import os
+    if not os.path.exists(HEADLESS):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    scene, cam = sponza_like(spp=2, detail=0.3, tex_size=64)
+    obj = write_obj(scene, str(tmp_path / "scene.obj"))
+    a_one, v1, out = run_headless("cuda", obj, cam, 200, 136, 2, 3, tmp_path)
+    assert "CUDA wavefront" in out
+    lists = ["0,0"]
+    if torch.cuda.device_count() >= 2:
+        lists.append(",".join(str(d) for d in range(min(4, torch.cuda.device_count()))))
+    for devices in lists:
+        for builder in ("0", "1"):
+            a_multi, v2, _ = run_headless("cuda", obj, cam, 200, 136, 2, 3, tmp_path,
+                                          extra_env={"CRT_CUDA_DEVICES": devices, "CRT_CUDA_BVH_BUILDER": builder})
+            assert v1 == v2 and np.array_equal(a_multi.view(np.uint32), a_one.view(np.uint32)), (devices, builder)
