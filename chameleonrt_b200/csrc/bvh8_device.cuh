@@ -1,4 +1,5 @@
-// bvh8_device.cuh — the BVH8 of bvh8.h built ON THE DEVICE (option "bvh_builder" = 1).
+// bvh8_device.cuh — set_scene ON THE DEVICE: flattening + the BVH8 of bvh8.h (option "bvh_builder" = 1 / 2;
+// SURVEY.md §8(f) rank 1). Opt-in; so far verified under the CPU SIMT emulation only (tests/simt_emu).
 //
 // Replaces, like bvh8_build.cpp, what the reference delegates to Embree / OptiX (rtcCommitScene,
 // backends/embree/embree_utils.cpp:75,128; optixAccelBuild + compaction, backends/optix/optix_utils.cpp:183-245).
@@ -25,8 +26,9 @@
 //
 // The closest hit of a ray does not depend on the tree (ties break on the flattened primitive id), so
 // frames rendered over this tree are bit-identical to frames over the host-built one: that is the test
-// (tests/test_simt_renderer.py on the CPU under the SIMT emulation, tests/test_gpu_parity.py on the GPU).
-// No kernel here waits on another block (no look-back scans): every pass is a separate launch.
+// (tests/test_simt_renderer.py on the CPU under the SIMT emulation, tests/test_z_new_gpu_paths.py on the GPU).
+// No kernel here waits on another block (no look-back scans): every pass is a separate launch; the one exception is
+// k_lbvh_refit's classic fence + arrival-counter hand-over between the two threads that meet at a node.
 #pragma once
 
 #include <cstdint>
