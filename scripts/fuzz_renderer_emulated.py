@@ -3,7 +3,8 @@ the CPU SIMT emulation (tests/simt_emu) against the oracle: random scenes as in 
 instance transforms; sheared ones only statistically), random spp / depth / frame counts / ragged sizes, frames
 rendered blocking, asynchronously and as batches, random shadow-order mode, random BVH builder (host / device PLOC /
 device LBVH). All pixels within the parity tolerance, ray counts equal (NaN paths aside); frames over a device-built
-tree bit-identical to frames over the host-built one.   python scripts/fuzz_renderer_emulated.py [n] [first_seed]"""
+tree bit-identical to frames over the host-built one; in a third of the cases the frame is also rendered by 2-3
+renderers that share one frame (tile sharding without a gather) and must come out the same.   python scripts/fuzz_renderer_emulated.py [n] [first_seed]"""
 import os
 import sys
 import warnings
@@ -59,6 +60,22 @@ def one(seed):
     frac, rel_l1 = parity(got, want)
     ok = frac >= (0.98 if sheared else 0.999) and rel_l1 <= (5e-2 if sheared else 1e-4)
     ok = ok and (has_nan or sheared or rays == rays_cpu)
+    if rng.random() < 0.3:  # 2-3 renderers sharing rank 0's frame (crtc_share_frame), as the plugin does for CRT_CUDA_DEVICES
+        n = int(rng.integers(2, 4))
+        shards = [backend.RenderCUDA(int(rng.integers(0, 8)), max_depth=depth, rank=i, world_size=n, any_far_first=0,
+                                     bvh_builder=builder) for i in range(n)]
+        for sh in shards:
+            sh.initialize(w, h)
+            sh.set_scene(scene)
+        for sh in shards[1:]:
+            shards[0].share_frame_with(sh)
+        rays_sh = 0
+        for f in range(frames):
+            for sh in shards:
+                sh.render_async(*view, f == 0, 1)
+            rays_sh += sum(sh.sync()[0].num_rays for sh in shards)
+        ok = ok and rays_sh == rays and np.array_equal(shards[0].read_accum().view(np.uint32), got.view(np.uint32))
+        del shards
     if builder != "host":  # the tree must not matter, bit for bit
         ref = backend.RenderCUDA(0, max_depth=depth, any_far_first=0, bvh_builder="host")
         ref.initialize(w, h)
