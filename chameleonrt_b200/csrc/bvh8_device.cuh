@@ -439,9 +439,24 @@ __global__ void __launch_bounds__(kBuildBlock) k_bvh2_leaves(Lbvh b, const uint3
 
 // Node p over the finished subtrees l and r: box, triangle count, and cost[i] = the cheapest way to represent the
 // subtree as a forest of at most i+1 BVH8 children, with the decision that achieves it.
+// L2_ONLY: the children were written by OTHER blocks of the SAME launch (k_lbvh_refit): their records are read with
+// ld.global.cg, so that a line this SM cached before the sibling thread wrote it cannot be served from L1.
+template <bool L2_ONLY>
+__device__ __forceinline__ float4 load_node4(const float4 *p)
+{
+    return L2_ONLY ? __ldcg(p) : *p;
+}
+template <bool L2_ONLY>
+__device__ __forceinline__ float load_node1(const float *p)
+{
+    return L2_ONLY ? __ldcg(p) : *p;
+}
+
+template <bool L2_ONLY = false>
 __device__ __forceinline__ void collapse_dp(const Lbvh &b, uint32_t p, uint32_t l, uint32_t r)
 {
-    const float4 llo = b.box_lo[l], lhi = b.box_hi[l], rlo = b.box_lo[r], rhi = b.box_hi[r];
+    const float4 llo = load_node4<L2_ONLY>(b.box_lo + l), lhi = load_node4<L2_ONLY>(b.box_hi + l);
+    const float4 rlo = load_node4<L2_ONLY>(b.box_lo + r), rhi = load_node4<L2_ONLY>(b.box_hi + r);
     const uint32_t cnt = __float_as_uint(llo.w) + __float_as_uint(rlo.w);
     const float4 lo = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), __uint_as_float(cnt));
     const float4 hi = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
@@ -451,8 +466,8 @@ __device__ __forceinline__ void collapse_dp(const Lbvh &b, uint32_t p, uint32_t 
     float cl[7], cr[7], cn[7];
     uint8_t dn[7];
     for (int i = 0; i < 7; ++i) {
-        cl[i] = b.cost[7 * (size_t)l + i];
-        cr[i] = b.cost[7 * (size_t)r + i];
+        cl[i] = load_node1<L2_ONLY>(b.cost + 7 * (size_t)l + i);
+        cr[i] = load_node1<L2_ONLY>(b.cost + 7 * (size_t)r + i);
     }
     {
         // i = 0: a single root — a leaf (<= 3 triangles) or an internal node whose 8 slots go to the two subtrees
@@ -507,7 +522,7 @@ __global__ void __launch_bounds__(kBuildBlock) k_lbvh_refit(Lbvh b)
             }
             __threadfence();
             const uint2 ch = b.children[p - n];
-            collapse_dp(b, p, ch.x, ch.y);
+            collapse_dp<true>(b, p, ch.x, ch.y);
             p = b.parent[p];
         }
     }

@@ -98,6 +98,11 @@ static inline T __ldg(const T *p)
 {
     return *p;
 }
+template <typename T>
+static inline T __ldcg(const T *p)
+{
+    return *p;
+}
 static inline uint32_t __float_as_uint(float f)
 {
     uint32_t u;
