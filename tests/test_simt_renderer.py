@@ -115,6 +115,55 @@ def test_frames_in_flight_sharding_and_shadow_order_on_the_emulated_renderer(mod
     ranks[1].import_frame(None)
     with pytest.raises(ValueError):
         ranks[1].import_frame(b"short")
+    # the torch.distributed wrapper of the same (distributed.PeerFrame), its collectives replaced by an in-process stand-in:
+    # rank 0 exports + "broadcasts", rank 1 receives + imports, finish() is the barrier
+    import torch
+    import torch.distributed as dist
+
+    from chameleonrt_b200.distributed import PeerFrame
+
+    state = {"rank": 0, "wire": None, "barriers": 0}
+    saved = {k: getattr(dist, k) for k in ("get_world_size", "get_rank", "get_backend", "broadcast", "barrier")}
+    saved_stream = torch.cuda.current_stream
+
+    def fake_broadcast(t, src, group=None):
+        if state["rank"] == src:
+            state["wire"] = t.clone()
+        else:
+            t.copy_(state["wire"])
+
+    class _NoStream:
+        def synchronize(self):
+            pass
+
+    try:
+        dist.get_world_size, dist.get_rank, dist.get_backend = (lambda g=None: 2), (lambda g=None: state["rank"]), (lambda g=None: "gloo")
+        dist.broadcast = fake_broadcast
+        dist.barrier = lambda group=None: state.__setitem__("barriers", state["barriers"] + 1)
+        torch.cuda.current_stream = lambda d=None: _NoStream()
+        ranks, frames_ = [], []
+        for rank in range(2):
+            r = RenderCUDA(0, rank=rank, world_size=2)
+            r.initialize(w, h)
+            r.set_scene(scene)
+            ranks.append(r)
+            state["rank"] = rank
+            frames_.append(PeerFrame(r))
+        got = 0
+        for rank, r in enumerate(ranks):
+            state["rank"] = rank
+            r.render_async(*args, True, 2)
+            r.render_async(*args, False, 1)
+            got += r.sync()[0].num_rays
+            frames_[rank].submit()
+            assert frames_[rank].finish() == (rank == 0)
+        assert got == rays and state["barriers"] == 2
+        assert (ranks[0].read_accum().view(np.uint32) == want.view(np.uint32)).all() and (ranks[0].read_img() == want_img).all()
+        ranks[1].import_frame(None)
+    finally:
+        for k, v in saved.items():
+            setattr(dist, k, v)
+        torch.cuda.current_stream = saved_stream
     # shadow rays far-first: on, and decided per scene from frames 1 and 2 — same image
     for mode in (1, 2):
         r = RenderCUDA(0, any_far_first=mode)
