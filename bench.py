@@ -252,7 +252,9 @@ def run_set_scene_probe() -> None:
         for f in range(2):
             r.render(*view, f == 0, False)
         info, c, st = r.scene_info(), r.counters(), r.stage_times()
-        out[builder] = {"set_scene_ms": wall, "bvh_build_ms": info["bvh_build_ms"], "bvh8_nodes": int(info["bvh8_nodes"]),
+        out[builder] = {"set_scene_ms": wall, "bvh_build_ms": info["bvh_build_ms"],
+                        "phases_ms": {k: round(info[k + "_ms"], 3) for k in ("flatten", "sort", "tree", "emit", "pack")},
+                        "ploc_rounds": int(info["ploc_rounds"]), "bvh8_nodes": int(info["bvh8_nodes"]),
                         "bvh8_depth": int(info["bvh8_depth"]),
                         "closest_nodes_per_ray": c["closest_nodes_visited"] / max(1, c["closest_rays"]),
                         "any_hit_nodes_per_ray": c["any_nodes_visited"] / max(1, c["occlusion_rays"]),

@@ -27,7 +27,8 @@ _lib: Optional[C.CDLL] = None
 STAGE_NAMES = ("raygen", "traverse_primary", "shade", "traverse", "nee_resolve", "resolve", "frame")
 COUNTER_NAMES = ("closest_rays", "occlusion_rays", "kernel_launches", "closest_nodes_visited", "closest_tris_tested",
                  "paths", "any_nodes_visited", "any_tris_tested")
-SCENE_INFO_NAMES = ("triangles", "bvh8_nodes", "bvh8_depth", "bvh_build_ms", "node_bytes", "triangle_bytes")
+SCENE_INFO_NAMES = ("triangles", "bvh8_nodes", "bvh8_depth", "bvh_build_ms", "node_bytes", "triangle_bytes",
+                    "flatten_ms", "sort_ms", "tree_ms", "emit_ms", "pack_ms", "ploc_rounds")
 
 # Every symbol include/crt_cuda.h declares (tests check the library exports all of them).
 C_ABI_SYMBOLS = (

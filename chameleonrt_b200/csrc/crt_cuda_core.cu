@@ -5,6 +5,7 @@
 // frame, time it, read the framebuffer back. Everything per-frame runs on the GPU as the
 // kernel chain of kernels.cuh; there is no CPU fallback anywhere in this file.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <memory>
@@ -211,7 +212,8 @@ struct crtc_renderer {
     DeviceBuffer<crt::DevTex> d_tex;
     uint32_t num_lights = 0;
     std::vector<uint32_t> leaf_flat_ids;  // host copy: leaf-order triangle -> flattened prim id
-    double scene_info[6] = {0, 0, 0, 0, 0, 0};
+    double scene_info[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // crtc_get_scene_info
+    double phase_ms[5] = {0, 0, 0, 0, 0};  // last set_scene: flatten, keys + sort, binary tree, BVH8 emission, packing
 
     // path state
     size_t path_capacity = 0;
@@ -614,9 +616,12 @@ struct crtc_renderer {
         auto grid_for = [&](uint32_t items) {
             return std::max(1u, std::min((items + crt::kBuildBlock - 1) / crt::kBuildBlock, (uint32_t)sms * 8u));
         };
-        cudaEvent_t ev0, ev1;
+        cudaEvent_t ev0, ev1, ev_sorted, ev_tree, ev_emitted;
         CUDA_CHECK(cudaEventCreate(&ev0));
         CUDA_CHECK(cudaEventCreate(&ev1));
+        CUDA_CHECK(cudaEventCreate(&ev_sorted));
+        CUDA_CHECK(cudaEventCreate(&ev_tree));
+        CUDA_CHECK(cudaEventCreate(&ev_emitted));
         const uint32_t num_b2 = 2 * n - 1, max_nodes = std::max(1u, n - 1);
         DeviceArena arena;
         ArenaBuf<float4> tri_lo(arena), tri_hi(arena), box_lo(arena), box_hi(arena), nodes_tmp(arena);
@@ -691,6 +696,7 @@ struct crtc_renderer {
             std::swap(kin, kout);
             std::swap(vin, vout);
         }
+        CUDA_CHECK(cudaEventRecord(ev_sorted, stream));
         crt::u64 *h_tail = nullptr;  // pinned: last offset + last count of a scan = its total
         CUDA_CHECK(cudaMallocHost(&h_tail, 2 * sizeof(crt::u64)));
         struct FreeHost {
@@ -757,6 +763,7 @@ struct crtc_renderer {
         }
 
         // BVH8 levels: the host only learns each level's size
+        CUDA_CHECK(cudaEventRecord(ev_tree, stream));
         CUDA_CHECK(cudaMemcpyAsync(work0.ptr, &root, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
         uint32_t *work = work0.ptr, *next_work = work1.ptr;
         uint32_t node_begin = 0, count = 1, tri_total = 0;
@@ -795,6 +802,7 @@ struct crtc_renderer {
                                      " triangles");
         }
         check_depth(depth);
+        CUDA_CHECK(cudaEventRecord(ev_emitted, stream));
         num_nodes = node_begin;
         d_nodes.alloc((size_t)num_nodes * 5);
         CUDA_CHECK(cudaMemcpyAsync(d_nodes.ptr, nodes_tmp.ptr, (size_t)num_nodes * 80, cudaMemcpyDeviceToDevice, stream));
@@ -810,8 +818,17 @@ struct crtc_renderer {
         float t = 0.f;
         CUDA_CHECK(cudaEventElapsedTime(&t, ev0, ev1));
         ms = t;
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
+        CUDA_CHECK(cudaEventElapsedTime(&t, ev0, ev_sorted));
+        phase_ms[1] = t;
+        CUDA_CHECK(cudaEventElapsedTime(&t, ev_sorted, ev_tree));
+        phase_ms[2] = t;
+        CUDA_CHECK(cudaEventElapsedTime(&t, ev_tree, ev_emitted));
+        phase_ms[3] = t;
+        CUDA_CHECK(cudaEventElapsedTime(&t, ev_emitted, ev1));
+        phase_ms[4] = t;
+        for (cudaEvent_t e : {ev0, ev1, ev_sorted, ev_tree, ev_emitted}) {
+            cudaEventDestroy(e);
+        }
         leaf_flat_ids.resize(n);
         for (uint32_t i = 0; i < n; ++i) {
             if (order[i] >= n) {
@@ -840,18 +857,25 @@ struct crtc_renderer {
             crt::convert_shading_inputs(scene, hs, bvh_threads);
             DeviceBuffer<float> d_verts;
             DeviceBuffer<float4> d_shade_in;
-            flatten_on_device(scene, plan, d_verts, d_shade_in);
+            const auto t0 = std::chrono::steady_clock::now();
+            flatten_on_device(scene, plan, d_verts, d_shade_in);  // (ends with a stream synchronisation)
+            phase_ms[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             num_tris = plan.total_tris;
             build_on_device((uint32_t)num_tris, d_verts, d_shade_in, bvh_nodes, bvh_depth, bvh_ms);
         } else {
+            const auto t0 = std::chrono::steady_clock::now();
             crt::flatten_scene(scene, hs, bvh_threads);
+            phase_ms[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            phase_ms[1] = phase_ms[2] = phase_ms[3] = 0.0;  // the host builder reports one figure: scene_info[3]
             num_tris = hs.num_tris();
             crt::Bvh8 bvh;
             crt::build_bvh8(hs.tri_verts.data(), hs.num_tris(), bvh_threads, bvh);
             check_depth(bvh.max_depth);
             std::vector<float> tri_records;
             std::vector<crt::TriShade> shade;
+            const auto t_pack = std::chrono::steady_clock::now();
             crt::pack_triangles(hs, bvh, tri_records, shade, bvh_threads);
+            phase_ms[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_pack).count();
             leaf_flat_ids.resize(shade.size());
             for (size_t i = 0; i < shade.size(); ++i) {
                 leaf_flat_ids[i] = shade[i].flat_id;
@@ -897,6 +921,10 @@ struct crtc_renderer {
         scene_info[3] = bvh_ms;
         scene_info[4] = (double)bvh_nodes * 80.0;
         scene_info[5] = (double)num_tris * 48.0;
+        for (int i = 0; i < 5; ++i) {
+            scene_info[6 + i] = phase_ms[i];
+        }
+        scene_info[11] = bvh_builder == 1 ? (double)build_rounds : 0.0;
         if (npx_local) {
             CUDA_CHECK(cudaMemsetAsync(d_accum_local.ptr, 0, (size_t)npx_local * 3 * sizeof(float), stream));
         }
@@ -1548,7 +1576,7 @@ int crtc_get_counters(crtc_renderer *r, uint64_t *out, int n)
 
 int crtc_get_scene_info(crtc_renderer *r, double *out, int n)
 {
-    const int m = std::min(n, 6);
+    const int m = std::min(n, 12);
     for (int i = 0; i < m; ++i) {
         out[i] = r->scene_info[i];
     }

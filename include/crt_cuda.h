@@ -138,7 +138,9 @@ int crtc_get_stage_times(crtc_renderer *r, float *ms_out, int n);
 int crtc_get_counters(crtc_renderer *r, uint64_t *out, int n);
 
 /* Scene/BVH facts: [0] triangles [1] BVH8 nodes [2] BVH depth [3] build ms [4] node bytes
- * [5] triangle bytes. */
+ * [5] triangle bytes; the last crtc_set_scene in phases, ms: [6] flattening (host wall clock: host work, or uploads +
+ * k_flatten), and for the device builders (CUDA events) [7] Morton keys + sort [8] binary tree (PLOC / LBVH) [9] BVH8
+ * emission [10] record packing ([10] is host wall clock for the host builder, [7]-[9] are 0 there); [11] PLOC rounds. */
 int crtc_get_scene_info(crtc_renderer *r, double *out, int n);
 
 /* Kernel-level access for parity tests and micro-benchmarks: trace a batch of rays against

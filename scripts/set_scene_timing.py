@@ -42,8 +42,9 @@ def main():
                 walls.append((time.perf_counter() - t0) * 1e3)
             info = r.scene_info()
             row = {"set_scene_ms": [round(w, 2) for w in walls], "bvh_build_ms": round(info["bvh_build_ms"], 3),
+                   "phases_ms": {k: round(info[k + "_ms"], 3) for k in ("flatten", "sort", "tree", "emit", "pack")},
                    "bvh8_nodes": int(info["bvh8_nodes"]), "bvh8_depth": int(info["bvh8_depth"]),
-                   "ploc_rounds": r.get_option("bvh_build_rounds") if builder == "device" else None}
+                   "ploc_rounds": int(info["ploc_rounds"]) if builder == "device" else None}
             if render:
                 for f in range(2):
                     r.render(*view, f == 0, False)
