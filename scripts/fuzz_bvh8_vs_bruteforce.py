@@ -4,7 +4,9 @@ triangle soups at wildly different scales, slivers, duplicated triangles, grids 
 vertices, huge + tiny triangles in one scene; rays from random points, from points ON triangles, axis-parallel
 rays with exactly zero components travelling along grid lines, short shadow-ray segments. Closest hits must be
 bit-identical (t, u, v, primitive id), occlusion answers equal. CPU only.
-    python scripts/fuzz_bvh8_vs_bruteforce.py [n] [first_seed]"""
+With --device the same scenes and rays also go through the DEVICE builders (bvh8_device.cuh: PLOC and LBVH, run under
+the SIMT emulation of tests/simt_emu) and the production traversal kernel over their trees: same hits, bit for bit.
+    python scripts/fuzz_bvh8_vs_bruteforce.py [n] [first_seed] [--device]"""
 import os
 import sys
 import warnings
@@ -72,7 +74,28 @@ def random_rays(rng, scene, n):
     return np.ascontiguousarray(np.concatenate([o, tnear[:, None], d, tfar[:, None]], 1), np.float32)
 
 
-def one(seed):
+_backend = None
+
+
+def device_builders_agree(scene, rays, hb):
+    """The emulated renderer over a device-built tree: closest hits == the host check's (already compared with brute
+    force); occlusion == the same kernel's answer over the host-built tree."""
+    want_any = None
+    for builder in ("host", "device", "device_lbvh"):
+        r = _backend.RenderCUDA(0, bvh_builder=builder)
+        r.initialize(8, 8)
+        r.set_scene(scene)
+        if not np.array_equal(r.trace_closest(rays).view(np.uint32), hb.view(np.uint32)):
+            return False
+        got_any = r.trace_any(rays)
+        if want_any is None:
+            want_any = got_any
+        elif not np.array_equal(got_any, want_any):
+            return False
+    return True
+
+
+def one(seed, device=False):
     rng = np.random.default_rng(seed)
     scene_scale = 10.0 ** rng.uniform(-3, 3)
     geoms = [random_geometry(rng, scene_scale) for _ in range(int(rng.integers(1, 4)))]
@@ -118,16 +141,27 @@ def one(seed):
     hf, _, _ = hc.trace(rays, any_hit=True, far_first=True)
     occ = brute.trace_any(rays).astype(bool)
     same_any = np.array_equal(ha[:, 3].view(np.uint32) != 0xFFFFFFFF, occ) and np.array_equal(hf[:, 3].view(np.uint32) != 0xFFFFFFFF, occ)
-    return same_closest and same_any, (same_closest, same_any, scene.total_tris())
+    same_device = True
+    if device and scene.total_tris() > 0:
+        same_device = device_builders_agree(scene, rays, hb)
+    return same_closest and same_any and same_device, (same_closest, same_any, same_device, scene.total_tris())
 
 
 if __name__ == "__main__":
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
-    first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    device = "--device" in sys.argv
+    args = [a for a in sys.argv[1:] if a != "--device"]
+    n = int(args[0]) if len(args) > 0 else 100
+    first = int(args[1]) if len(args) > 1 else 0
+    if device:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "simt_emu"))
+        import build as simt_build
+        import chameleonrt_b200.backend as _backend
+
+        _backend._LIB_PATH, _backend._lib = simt_build.build(), None
     bad = 0
     for seed in range(first, first + n):
-        ok, info = one(seed)
+        ok, info = one(seed, device)
         if not ok:
             bad += 1
             print("MISMATCH seed", seed, info)
-    print(f"{n} random scenes x 600 rays, {bad} mismatches")
+    print(f"{n} random scenes x 600 rays, {bad} mismatches" + (" (host + device builders)" if device else ""))
