@@ -531,9 +531,20 @@ __global__ void __launch_bounds__(kBuildBlock) k_lbvh_refit(Lbvh b)
 // ---- PLOC ----
 constexpr int kPlocRadius = 16, kPlocMaxRadius = 32;
 
-// nn[i] = the cluster within `radius` (<= kPlocMaxRadius) positions of i whose union with i has the smallest surface area (ties: the
-// lower position, so that the relation is symmetric and some pair is always mutual). forced: pair up neighbours
-// (i ^ 1) regardless of distance — the way out if an adversarial input makes the mutual pairs too few.
+// Among candidates with EQUAL merged area (everywhere on regular geometry: a row of identical quads) the "aligned"
+// partner i ^ 1 wins, then the lower position. Lowest-position-first alone turns such a row into a chain — every
+// cluster points at its left neighbour and only the first pair is mutual, one merge per round; with the aligned
+// partner preferred the row pairs up (0,1), (2,3), ... in a single round (rungholt_like, 179 K: 65 -> 43 rounds).
+// The rank is symmetric (j == i ^ 1 <=> i == j ^ 1), so the lowest-positioned cluster of the globally best
+// (area, rank) pairs and its lowest such partner always choose each other: every round merges at least one pair.
+__device__ __forceinline__ uint32_t ploc_tie_rank(uint32_t i, uint32_t j)
+{
+    return j == (i ^ 1u) ? 0u : 1u;
+}
+
+// nn[i] = the cluster within `radius` (<= kPlocMaxRadius) positions of i whose union with i has the smallest surface area (ties:
+// ploc_tie_rank). forced: pair up neighbours (i ^ 1) regardless of distance — the way out if an adversarial input
+// leaves too few mutual pairs per round.
 __global__ void __launch_bounds__(kBuildBlock) k_ploc_nn(Lbvh b, const uint32_t *clusters, uint32_t m, uint32_t *nn, int radius,
                                                          int forced)
 {
@@ -565,7 +576,8 @@ __global__ void __launch_bounds__(kBuildBlock) k_ploc_nn(Lbvh b, const uint32_t 
                 const float4 ul = make_float4(fminf(lo.x, ol.x), fminf(lo.y, ol.y), fminf(lo.z, ol.z), 0.f);
                 const float4 uh = make_float4(fmaxf(hi.x, oh.x), fmaxf(hi.y, oh.y), fmaxf(hi.z, oh.z), 0.f);
                 const float a = box_half_area(ul, uh);
-                if (a < best || best_j == (uint32_t)i) {  // (the second test also takes a NaN / inf area)
+                // (the first test also takes a NaN / inf area as the first candidate)
+                if (best_j == (uint32_t)i || a < best || (a == best && ploc_tie_rank((uint32_t)i, (uint32_t)j) < ploc_tie_rank((uint32_t)i, best_j))) {
                     best = a;
                     best_j = (uint32_t)j;
                 }
@@ -654,7 +666,7 @@ __global__ void __launch_bounds__(kBuildBlock) k_ploc_tail(Lbvh b, const uint32_
                     const float4 ul = make_float4(fminf(lo.x, ol.x), fminf(lo.y, ol.y), fminf(lo.z, ol.z), 0.f);
                     const float4 uh = make_float4(fmaxf(hi.x, oh.x), fmaxf(hi.y, oh.y), fmaxf(hi.z, oh.z), 0.f);
                     const float a = box_half_area(ul, uh);
-                    if (a < best || best_j == i) {
+                    if (best_j == i || a < best || (a == best && ploc_tie_rank(i, (uint32_t)j) < ploc_tie_rank(i, best_j))) {
                         best = a;
                         best_j = (uint32_t)j;
                     }
