@@ -260,3 +260,30 @@ extern "C" int crt_cuda_read_accum(RenderBackend *backend, float *rgb_out)
     r->read_accum(rgb_out);
     return 0;
 }
+
+extern "C" int crt_cuda_get_stats(RenderBackend *backend, float *stage_ms, int num_stages, uint64_t *counters, int num_counters)
+{
+    RenderCUDA *r = dynamic_cast<RenderCUDA *>(backend);
+    if (!r) {
+        return 1;
+    }
+    if (stage_ms && num_stages > 0) {
+        const int n = crtc_get_stage_times(r->renderers[0], stage_ms, num_stages);
+        for (int i = n; i < num_stages; ++i) {
+            stage_ms[i] = 0.f;
+        }
+    }
+    if (counters && num_counters > 0) {
+        for (int i = 0; i < num_counters; ++i) {
+            counters[i] = 0;
+        }
+        for (crtc_renderer *shard : r->renderers) {
+            uint64_t part[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const int n = crtc_get_counters(shard, part, 8);
+            for (int i = 0; i < n && i < num_counters; ++i) {
+                counters[i] += part[i];
+            }
+        }
+    }
+    return 0;
+}

@@ -8,6 +8,7 @@
 // sm_100a wavefront kernels).
 #pragma once
 
+#include <cstdint>
 #include <string>
 #include <vector>
 #include "render_backend.h"
@@ -41,5 +42,8 @@ struct RenderCUDA : RenderBackend {
     void read_accum(float *rgb_out);
 };
 
-// C entry point so a harness that only has the RenderBackend* can read the float framebuffer
+// C entry points so a harness that only has the RenderBackend* can read the float framebuffer and the last frame's
+// per-stage device times / counters (layouts of crtc_get_stage_times / crtc_get_counters in crt_cuda.h:
+// up to 7 floats and 8 counters; with several renderers the times are the first one's, the counters are summed)
 extern "C" int crt_cuda_read_accum(RenderBackend *backend, float *rgb_out);
+extern "C" int crt_cuda_get_stats(RenderBackend *backend, float *stage_ms, int num_stages, uint64_t *counters, int num_counters);

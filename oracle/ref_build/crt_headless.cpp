@@ -137,6 +137,29 @@ int main(int argc, const char **argv)
             std::cout << "Rays/s (mean of per-frame rates): "
                       << pretty_print_count(rays_per_second / benchmark_frames) << "\n";
         }
+        {
+            // the other extra export of the cuda / oracle plugins: per-stage times and counters of the last frame
+            using GetStatsFn = int (*)(RenderBackend *, float *, int, uint64_t *, int);
+            const std::string sym = "crt_" + args[1] + "_get_stats";
+            GetStatsFn fn = reinterpret_cast<GetStatsFn>(dlsym(RTLD_DEFAULT, sym.c_str()));
+            if (!fn) {
+                void *h = dlopen((std::string(SDL_GetBasePath()) + "libcrt_" + args[1] + ".so").c_str(), RTLD_LAZY | RTLD_NOLOAD);
+                fn = h ? reinterpret_cast<GetStatsFn>(dlsym(h, sym.c_str())) : nullptr;
+            }
+            float stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
+            uint64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (fn && fn(renderer.get(), stage_ms, 7, counters, 8) == 0) {
+                std::cout << "last frame: stage ms";
+                for (float v : stage_ms) {
+                    std::cout << " " << v;
+                }
+                std::cout << " | counters";
+                for (uint64_t v : counters) {
+                    std::cout << " " << v;
+                }
+                std::cout << "\n";
+            }
+        }
         if (!accum_out.empty()) {
             // the extra export of the cuda / oracle plugins (not part of the reference API)
             const std::string sym = "crt_" + args[1] + "_read_accum";

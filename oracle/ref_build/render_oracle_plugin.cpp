@@ -25,6 +25,7 @@ void oracle_read_accum(void *, float *);
 struct RenderOracle : RenderBackend {
     void *o;
     int w = 0, h = 0;
+    crt_render_stats_t last{};  // the last frame's stats, for crt_oracle_get_stats
     RenderOracle() : o(oracle_create())
     {
         const char *d = std::getenv("CRT_CUDA_MAX_DEPTH");
@@ -95,6 +96,7 @@ struct RenderOracle : RenderBackend {
     {
         crt_render_stats_t s;
         oracle_render(o, &pos.x, &dir.x, &up.x, fovy, camera_changed ? 1 : 0, &s);
+        last = s;
         oracle_read_img(o, img.data());
         RenderStats stats;
         stats.render_time = s.render_time;
@@ -102,6 +104,23 @@ struct RenderOracle : RenderBackend {
         return stats;
     }
 };
+
+// the twin of crt_cuda_get_stats: a CPU frame has one stage (entry 6, whole frame) and one ray count (entry 0: closest-hit
+// + occlusion rays together); everything else reads 0
+extern "C" int crt_oracle_get_stats(RenderBackend *backend, float *stage_ms, int num_stages, uint64_t *counters, int num_counters)
+{
+    RenderOracle *r = dynamic_cast<RenderOracle *>(backend);
+    if (!r) {
+        return 1;
+    }
+    for (int i = 0; stage_ms && i < num_stages; ++i) {
+        stage_ms[i] = i == 6 ? r->last.render_time : 0.f;
+    }
+    for (int i = 0; counters && i < num_counters; ++i) {
+        counters[i] = i == 0 ? r->last.num_rays : 0;
+    }
+    return 0;
+}
 
 extern "C" int crt_oracle_read_accum(RenderBackend *backend, float *rgb_out)
 {

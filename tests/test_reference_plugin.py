@@ -63,9 +63,17 @@ def test_cuda_plugin_drop_in(built, tmp_path, name):
     scene, cam = cornell_box(spp=2) if name == "cornell" else sponza_like(spp=2, detail=0.3, tex_size=64)
     obj = write_obj(scene, str(tmp_path / "scene.obj"))
     a_gpu, v1, out = run_headless("cuda", obj, cam, 160, 96, 2, 2, tmp_path)
-    a_cpu, v2, _ = run_headless("oracle", obj, cam, 160, 96, 2, 2, tmp_path)
+    a_cpu, v2, out_cpu = run_headless("oracle", obj, cam, 160, 96, 2, 2, tmp_path)
     assert v1 == v2 and "CUDA wavefront" in out
     assert_parity(a_gpu, a_cpu)
+    # both plugins export crt_<backend>_get_stats: stage times + counters of the last frame; the ray
+    # counts of the two backends agree (closest-hit + occlusion on the GPU side = the CPU side's single count)
+    def last_frame(text):
+        line = [l for l in text.splitlines() if l.startswith("last frame: stage ms")][0]
+        stage, counters = (list(map(float, part.split())) for part in line[len("last frame: stage ms"):].split("| counters"))
+        return stage, counters
+    (sg, cg), (sc, cc) = last_frame(out), last_frame(out_cpu)
+    assert sg[6] > 0 and sc[6] > 0 and cg[0] + cg[1] == cc[0] > 0
 
 
 @needs_ref

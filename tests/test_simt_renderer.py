@@ -204,6 +204,12 @@ def test_drop_in_plugin_on_the_emulated_core(built, tmp_path):
     a_cpu, v2, _ = run_headless("oracle", obj, cam, 96, 64, 2, 2, tmp_path)
     assert v1 == v2 and "CUDA wavefront" in out
     assert_parity(a_gpu, a_cpu)
+    # the plugins' second extra export (crt_<backend>_get_stats): per-stage times and counters of the last frame
+    stats = [l for l in out.splitlines() if l.startswith("last frame: stage ms")]
+    assert len(stats) == 1
+    stage, counters = (list(map(float, part.split())) for part in stats[0][len("last frame: stage ms"):].split("| counters"))
+    assert len(stage) == 7 and stage[6] > 0 and stage[2] > 0 and len(counters) == 8 and counters[0] > 0 and counters[1] > 0
+    assert counters[2] == 2 + 3 * 5 + 1  # kernel launches of one depth-5 frame
     # the plugin's environment knob for the device BVH builders: same frame, bit for bit
     for builder in ("1", "2"):
         a_dev, _, _ = run_headless("cuda_simt", obj, cam, 96, 64, 2, 2, tmp_path, extra_env={"CRT_CUDA_BVH_BUILDER": builder})
