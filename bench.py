@@ -36,6 +36,10 @@ import numpy as np  # noqa: E402
 # BASELINE.json configs. The default (what the driver runs) is configs[1] = "c2"; c3 / c4 are the
 # HBM-resident stress cases and are run by hand (results under profiles/).
 WORKLOADS = {
+    # configs[0] is the reference's own CPU-runnable plumbing case; here for completeness (a 34-triangle scene says
+    # nothing about a GPU)
+    "c1": dict(name="C1 cornell_box OBJ-class scene (34 tris), 512x512, 1 spp, max depth 5", gen="cornell_box", kw={}, w=512, h=512,
+               spp=1, depth=5),
     "c2": dict(name="C2 sponza_like OBJ-class scene (263,792 tris, 25 materials, 8 sRGB 1024^2 textures), "
                     "1280x720, 4 spp, max depth 8", gen="sponza_like", kw={}, w=1280, h=720, spp=4, depth=8),
     "c3": dict(name="C3 san_miguel_like glTF-class scene (10.5 M instanced tris, 961 instances, 100 materials, "
