@@ -115,6 +115,25 @@ def test_frames_in_flight_sharding_and_shadow_order_on_the_emulated_renderer(mod
     ranks[1].import_frame(None)
     with pytest.raises(ValueError):
         ranks[1].import_frame(b"short")
+    # error behaviour of the frame-sharing entry points
+    fresh = RenderCUDA(0, rank=1, world_size=2)
+    with pytest.raises(RuntimeError, match="initialize"):
+        fresh.export_frame()
+    with pytest.raises(RuntimeError, match="same size"):
+        ranks[0].share_frame_with(fresh)  # not initialized
+    fresh.initialize(w + 64, h)
+    with pytest.raises(RuntimeError, match="same size"):
+        ranks[0].share_frame_with(fresh)
+    with pytest.raises(RuntimeError, match="same renderer"):
+        ranks[0].share_frame_with(ranks[0])
+    # a resize undoes the sharing: both renderers are back to tile-local results that wait for a gather
+    ranks[0].share_frame_with(ranks[1])
+    for r in ranks:
+        r.initialize(w, h)
+        r.set_scene(scene)
+    ranks[0].render(*args, True, True)
+    ranks[1].render(*args, True, True)
+    assert (ranks[0].read_accum() == 0).all()  # nothing has been written into rank 0's full frame
     # the torch.distributed wrapper of the same (distributed.PeerFrame), its collectives replaced by an in-process stand-in:
     # rank 0 exports + "broadcasts", rank 1 receives + imports, finish() is the barrier
     import torch
