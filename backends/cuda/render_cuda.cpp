@@ -173,6 +173,7 @@ void RenderCUDA::set_scene(const Scene &scene)
     c.num_textures = static_cast<uint32_t>(textures.size());
     c.num_lights = static_cast<uint32_t>(scene.lights.size());
     c.samples_per_pixel = scene.samples_per_pixel;
+    frames_since_scene = 0;
     if (renderers.size() == 1) {
         check(crtc_set_scene(renderer, &c));
         return;
@@ -213,15 +214,26 @@ RenderStats RenderCUDA::render(const glm::vec3 &pos,
         // fan out: every GPU is handed its share of the frame before any of them is waited for; each resolves its
         // tiles into renderers[0]'s frame, which is complete once all of them have finished
         const auto t0 = std::chrono::steady_clock::now();
-        for (crtc_renderer *r : renderers) {
-            check(crtc_render_async(r, &pos.x, &dir.x, &up.x, fovy, camera_changed ? 1 : 0, 1));
-        }
         uint64_t rays = 0;
-        for (crtc_renderer *r : renderers) {
-            crt_render_stats_t part;
-            check(crtc_sync(r, &part, nullptr, nullptr, nullptr));
-            rays += part.num_rays;
+        if (frames_since_scene < 3) {
+            // the per-scene choice of the shadow-ray order (any_far_first = 2, crt_cuda.h) is made from the stage times
+            // of blocking frames 1 and 2: the first three frames go through crtc_render, one renderer after the other
+            for (crtc_renderer *r : renderers) {
+                crt_render_stats_t part;
+                check(crtc_render(r, &pos.x, &dir.x, &up.x, fovy, camera_changed ? 1 : 0, 0, nullptr, &part));
+                rays += part.num_rays;
+            }
+        } else {
+            for (crtc_renderer *r : renderers) {
+                check(crtc_render_async(r, &pos.x, &dir.x, &up.x, fovy, camera_changed ? 1 : 0, 1));
+            }
+            for (crtc_renderer *r : renderers) {
+                crt_render_stats_t part;
+                check(crtc_sync(r, &part, nullptr, nullptr, nullptr));
+                rays += part.num_rays;
+            }
         }
+        ++frames_since_scene;
         if (readback) {
             check(crtc_read_img(renderers[0], img.data()));
         }

@@ -23,6 +23,7 @@ struct RenderCUDA : RenderBackend {
     crtc_renderer *renderer = nullptr;  // = renderers[0]
     glm::ivec2 fb_dims = glm::ivec2(0);
     bool native_display = false;
+    int frames_since_scene = 0;  // multi-renderer mode: the first frames after set_scene are rendered blocking
 
     RenderCUDA();
     ~RenderCUDA() override;

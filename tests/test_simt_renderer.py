@@ -236,9 +236,12 @@ def test_drop_in_plugin_on_the_emulated_core(built, tmp_path):
     # CRT_CUDA_DEVICES: the plugin drives one renderer per GPU from its single host thread, tiles interleaved, every
     # renderer resolving into the first one's frame (crtc_share_frame) — same frame, bit for bit (the emulation has 8
     # "devices"); also two renderers on one device, the form a one-GPU box can run
+    # (five frames: the first three after set_scene are rendered blocking — the shadow-ray order is chosen from their stage
+    # times —, the rest fanned out with crtc_render_async)
+    a_five, _, _ = run_headless("cuda_simt", obj, cam, 96, 64, 2, 5, tmp_path)
     for devices in ("0,1,2", "0,0"):
-        a_multi, _, out_multi = run_headless("cuda_simt", obj, cam, 96, 64, 2, 2, tmp_path, extra_env={"CRT_CUDA_DEVICES": devices})
-        assert np.array_equal(a_multi.view(np.uint32), a_gpu.view(np.uint32)), devices
+        a_multi, _, out_multi = run_headless("cuda_simt", obj, cam, 96, 64, 2, 5, tmp_path, extra_env={"CRT_CUDA_DEVICES": devices})
+        assert np.array_equal(a_multi.view(np.uint32), a_five.view(np.uint32)), devices
     with pytest.raises(AssertionError, match="bvh_builder must be"):  # the knob does reach the core
         run_headless("cuda_simt", obj, cam, 96, 64, 2, 2, tmp_path, extra_env={"CRT_CUDA_BVH_BUILDER": "7"})
     if not FULL:

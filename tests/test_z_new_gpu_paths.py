@@ -244,13 +244,13 @@ def test_cuda_plugin_fans_out_over_renderers(built, tmp_path):
         pytest.skip("oracle/_ref not built (needs /root/reference)")
     scene, cam = sponza_like(spp=2, detail=0.3, tex_size=64)
     obj = write_obj(scene, str(tmp_path / "scene.obj"))
-    a_one, v1, out = run_headless("cuda", obj, cam, 200, 136, 2, 3, tmp_path)
+    a_one, v1, out = run_headless("cuda", obj, cam, 200, 136, 2, 6, tmp_path)
     assert "CUDA wavefront" in out
     lists = ["0,0"]
     if torch.cuda.device_count() >= 2:
         lists.append(",".join(str(d) for d in range(min(4, torch.cuda.device_count()))))
     for devices in lists:
         for builder in ("0", "1"):
-            a_multi, v2, _ = run_headless("cuda", obj, cam, 200, 136, 2, 3, tmp_path,
+            a_multi, v2, _ = run_headless("cuda", obj, cam, 200, 136, 2, 6, tmp_path,
                                           extra_env={"CRT_CUDA_DEVICES": devices, "CRT_CUDA_BVH_BUILDER": builder})
             assert v1 == v2 and np.array_equal(a_multi.view(np.uint32), a_one.view(np.uint32)), (devices, builder)
