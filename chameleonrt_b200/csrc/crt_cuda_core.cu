@@ -18,92 +18,18 @@
 
 #include "../../include/crt_cuda.h"
 #include "bvh8.h"
-#include "bvh8_device.cuh"
+#include "cuda_host_utils.h"
 #include "host_scene.h"
 #include "kernels.cuh"
+#include "scene_device_build.cuh"
 
 namespace {
 
 thread_local std::string g_last_error;
 
-#define CUDA_CHECK(expr)                                                                              \
-    do {                                                                                              \
-        cudaError_t err__ = (expr);                                                                   \
-        if (err__ != cudaSuccess) {                                                                   \
-            throw std::runtime_error(std::string(#expr) + " failed: " + cudaGetErrorString(err__) +    \
-                                     " (" __FILE__ ":" + std::to_string(__LINE__) + ")");             \
-        }                                                                                             \
-    } while (0)
-
-template <typename T>
-struct DeviceBuffer {
-    T *ptr = nullptr;
-    size_t count = 0;
-    ~DeviceBuffer() { release(); }
-    void release()
-    {
-        if (ptr) {
-            cudaFree(ptr);
-            ptr = nullptr;
-            count = 0;
-        }
-    }
-    void alloc(size_t n)
-    {
-        if (n == count && ptr) {
-            return;
-        }
-        release();
-        if (n) {
-            CUDA_CHECK(cudaMalloc(&ptr, n * sizeof(T)));
-        }
-        count = n;
-    }
-    void upload(const T *src, size_t n, cudaStream_t s)
-    {
-        alloc(n);
-        if (n) {
-            CUDA_CHECK(cudaMemcpyAsync(ptr, src, n * sizeof(T), cudaMemcpyHostToDevice, s));
-        }
-    }
-};
-
-// One cudaMalloc / cudaFree for a group of temporaries (the device set_scene needs ~25 of them, and cudaMalloc /
-// cudaFree cost more than most of its kernels). Used in two passes: the ArenaBuf::alloc calls run once to add up the
-// sizes, commit() allocates, and the same calls run again to hand out the pointers.
-struct DeviceArena {
-    char *base = nullptr;
-    size_t used = 0, capacity = 0;
-    ~DeviceArena()
-    {
-        if (base) {
-            cudaFree(base);
-        }
-    }
-    void commit()
-    {
-        capacity = used;
-        used = 0;
-        CUDA_CHECK(cudaMalloc(&base, std::max<size_t>(capacity, 256)));
-    }
-    void *take(size_t bytes)
-    {
-        used = (used + 255) & ~(size_t)255;
-        void *p = base ? base + used : nullptr;
-        used += bytes;
-        if (base && used > capacity) {
-            throw std::runtime_error("DeviceArena: the second pass asked for more than the first");
-        }
-        return p;
-    }
-};
-template <typename T>
-struct ArenaBuf {
-    DeviceArena *arena;
-    T *ptr = nullptr;
-    explicit ArenaBuf(DeviceArena &a) : arena(&a) {}
-    void alloc(size_t n) { ptr = static_cast<T *>(arena->take(std::max<size_t>(n, 1) * sizeof(T))); }
-};
+using crt_host::ArenaBuf;
+using crt_host::DeviceArena;
+using crt_host::DeviceBuffer;
 
 enum Stage { kStRaygen = 0, kStPrimary, kStShade, kStTraverse, kStNee, kStResolve, kStFrame, kNumStages };
 
@@ -472,371 +398,7 @@ struct crtc_renderer {
         CUDA_CHECK(cudaStreamSynchronize(stream));
     }
 
-    static void check_depth(uint32_t depth)
-    {
-        if (depth + 2 > CRT_STACK_SIZE) {
-            throw std::runtime_error("BVH8 depth " + std::to_string(depth) + " exceeds the traversal stack (CRT_STACK_SIZE)");
-        }
-    }
-
-    // exclusive scan of n items (in place allowed); `scratch` holds the tile sums of every recursion level
-    template <typename T>
-    void device_scan(const T *in, T *out, uint32_t n, T *scratch)
-    {
-        const unsigned tiles = (n + crt::kBuildTile - 1) / crt::kBuildTile;
-        T *sums = tiles > 1 ? scratch : nullptr;
-        crt::k_scan_tile<T><<<tiles, crt::kBuildBlock, 0, stream>>>(in, out, n, sums);
-        if (tiles > 1) {
-            device_scan<T>(scratch, scratch, tiles, scratch + tiles);
-            crt::k_scan_add<T><<<tiles, crt::kBuildBlock, 0, stream>>>(out, n, scratch);
-        }
-    }
-    static size_t scan_scratch_items(size_t n)
-    {
-        size_t total = 0;
-        while (n > (size_t)crt::kBuildTile) {
-            n = (n + crt::kBuildTile - 1) / crt::kBuildTile;
-            total += n;
-        }
-        return total + 1;
-    }
-
-    // set_scene with option bvh_builder = 1: everything after the flattening happens on the device
-    // (bvh8_device.cuh); fills d_nodes, d_tris, d_shade and leaf_flat_ids like the host path.
-    // The triangle half of flatten_scene on the device: the unique geometries are uploaded once (not once per
-    // instance) and k_flatten writes the world-space soup and the shading records in flattened order.
-    void flatten_on_device(const crt_scene_t *scene, const crt::FlattenPlan &plan, DeviceBuffer<float> &d_verts,
-                           DeviceBuffer<float4> &d_shade_in)
-    {
-        const uint32_t total = (uint32_t)plan.total_tris;
-        struct Placed {
-            uint32_t vert_off, tri_off, uv_off;
-        };
-        std::vector<std::vector<Placed>> placed(scene->num_meshes);  // [mesh][geometry], filled on first use
-        std::vector<crt::DevSegment> segs;
-        size_t nv = 0, nt = 0, nuv = 0;
-        struct Copy {
-            const crt_geometry_t *geom;
-            Placed at;
-        };
-        std::vector<Copy> copies;
-        for (const crt::FlattenSegment &fs : plan.segments) {
-            const crt_mesh_t &mesh = scene->meshes[fs.mesh];
-            const crt_geometry_t &geom = mesh.geometries[fs.geometry];
-            if (geom.num_tris == 0) {
-                continue;
-            }
-            std::vector<Placed> &pm = placed[fs.mesh];
-            if (pm.empty()) {
-                pm.assign(mesh.num_geometries, Placed{crt::kB2Invalid, crt::kB2Invalid, crt::kB2Invalid});
-            }
-            Placed &pl = pm[fs.geometry];
-            if (pl.tri_off == crt::kB2Invalid) {
-                if (nv + geom.num_vertices >= 0xffffffffull || nt + geom.num_tris >= 0xffffffffull) {
-                    throw std::runtime_error("device set_scene: geometry arenas exceed 2^32 - 1 elements");
-                }
-                pl.vert_off = (uint32_t)nv;
-                pl.tri_off = (uint32_t)nt;
-                nv += geom.num_vertices;
-                nt += geom.num_tris;
-                if (geom.uvs) {
-                    pl.uv_off = (uint32_t)nuv;
-                    nuv += geom.num_vertices;
-                }
-                copies.push_back(Copy{&geom, pl});
-            }
-            crt::DevSegment ds;
-            ds.flat_base = (uint32_t)fs.flat_base;
-            ds.num_tris = geom.num_tris;
-            ds.vert_off = pl.vert_off;
-            ds.num_verts = geom.num_vertices;
-            ds.tri_off = pl.tri_off;
-            ds.uv_off = pl.uv_off;
-            ds.mat_id = fs.mat_id;
-            ds.instance = fs.instance;
-            segs.push_back(ds);
-        }
-        DeviceArena arena;
-        ArenaBuf<float> vert_arena(arena), uv_arena(arena), xforms(arena);
-        ArenaBuf<uint32_t> index_arena(arena), bad(arena);
-        ArenaBuf<crt::DevSegment> d_segs(arena);
-        auto carve = [&] {
-            vert_arena.alloc(nv * 3);
-            index_arena.alloc(nt * 3);
-            uv_arena.alloc(nuv * 2);
-            xforms.alloc((size_t)scene->num_instances * 32);
-            d_segs.alloc(segs.size());
-            bad.alloc(1);
-        };
-        carve();
-        arena.commit();
-        carve();
-        for (const Copy &c : copies) {
-            CUDA_CHECK(cudaMemcpyAsync(vert_arena.ptr + (size_t)c.at.vert_off * 3, c.geom->vertices,
-                                       (size_t)c.geom->num_vertices * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
-            CUDA_CHECK(cudaMemcpyAsync(index_arena.ptr + (size_t)c.at.tri_off * 3, c.geom->indices,
-                                       (size_t)c.geom->num_tris * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-            if (c.geom->uvs) {
-                CUDA_CHECK(cudaMemcpyAsync(uv_arena.ptr + (size_t)c.at.uv_off * 2, c.geom->uvs,
-                                           (size_t)c.geom->num_vertices * 2 * sizeof(float), cudaMemcpyHostToDevice, stream));
-            }
-        }
-        std::vector<float> xf((size_t)scene->num_instances * 32);
-        for (uint32_t i = 0; i < scene->num_instances; ++i) {
-            std::memcpy(&xf[(size_t)i * 32], scene->instances[i].transform, 16 * sizeof(float));
-            std::memcpy(&xf[(size_t)i * 32 + 16], &plan.w2o_all[(size_t)i * 16], 16 * sizeof(float));
-        }
-        CUDA_CHECK(cudaMemcpyAsync(xforms.ptr, xf.data(), xf.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
-        CUDA_CHECK(cudaMemcpyAsync(d_segs.ptr, segs.data(), segs.size() * sizeof(crt::DevSegment), cudaMemcpyHostToDevice, stream));
-        CUDA_CHECK(cudaMemsetAsync(bad.ptr, 0, sizeof(uint32_t), stream));
-        d_verts.alloc((size_t)total * 9);
-        d_shade_in.alloc((size_t)total * 3);
-        int sms = 0;
-        CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-        const unsigned g = std::max(1u, std::min((total + crt::kBuildBlock - 1) / crt::kBuildBlock, (uint32_t)sms * 8u));
-        crt::k_flatten<<<g, crt::kBuildBlock, 0, stream>>>(d_segs.ptr, (uint32_t)segs.size(), xforms.ptr, vert_arena.ptr,
-                                                          index_arena.ptr, uv_arena.ptr, total, d_verts.ptr, d_shade_in.ptr,
-                                                          bad.ptr);
-        uint32_t bad_host = 0u;
-        CUDA_CHECK(cudaMemcpyAsync(&bad_host, bad.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-        CUDA_CHECK(cudaStreamSynchronize(stream));  // also: the staging vectors and arenas go out of scope
-        if (bad_host) {
-            throw std::runtime_error("triangle index out of range");
-        }
-    }
-
-    void build_on_device(uint32_t n, DeviceBuffer<float> &d_verts, DeviceBuffer<float4> &d_shade_in, uint32_t &num_nodes,
-                         uint32_t &depth, double &ms)
-    {
-        if (n >= (1u << 30)) {
-            throw std::runtime_error("device BVH build: at most 2^30 - 1 triangles");
-        }
-        int sms = 0;
-        CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-        auto grid_for = [&](uint32_t items) {
-            return std::max(1u, std::min((items + crt::kBuildBlock - 1) / crt::kBuildBlock, (uint32_t)sms * 8u));
-        };
-        cudaEvent_t ev0, ev1, ev_sorted, ev_tree, ev_emitted;
-        CUDA_CHECK(cudaEventCreate(&ev0));
-        CUDA_CHECK(cudaEventCreate(&ev1));
-        CUDA_CHECK(cudaEventCreate(&ev_sorted));
-        CUDA_CHECK(cudaEventCreate(&ev_tree));
-        CUDA_CHECK(cudaEventCreate(&ev_emitted));
-        const uint32_t num_b2 = 2 * n - 1, max_nodes = std::max(1u, n - 1);
-        DeviceArena arena;
-        ArenaBuf<float4> tri_lo(arena), tri_hi(arena), box_lo(arena), box_hi(arena), nodes_tmp(arena);
-        ArenaBuf<uint32_t> cbounds(arena), vals0(arena), vals1(arena), hist(arena), d_parent(arena), arrivals(arena), slots(arena),
-            work0(arena), work1(arena), tri_order(arena), clusters0(arena), clusters1(arena), nn(arena);
-        ArenaBuf<crt::u64> keys0(arena), keys1(arena), counts(arena), offsets(arena), scan_scratch(arena);
-        ArenaBuf<uint2> d_children(arena);
-        ArenaBuf<float> cost(arena);
-        ArenaBuf<uint8_t> decision(arena);
-        static_assert(sizeof(crt::TriShade) == 3 * sizeof(float4), "TriShade = 3 float4");
-        CUDA_CHECK(cudaEventRecord(ev0, stream));
-        const uint32_t tiles = (n + crt::kBuildTile - 1) / crt::kBuildTile;
-        auto carve = [&] {
-            tri_lo.alloc(n);
-            tri_hi.alloc(n);
-            cbounds.alloc(6);
-            keys0.alloc(n);
-            keys1.alloc(n);
-            vals0.alloc(n);
-            vals1.alloc(n);
-            hist.alloc((size_t)tiles * 256);
-            d_children.alloc(n);
-            box_lo.alloc(num_b2);
-            box_hi.alloc(num_b2);
-            cost.alloc((size_t)num_b2 * 7);
-            decision.alloc((size_t)num_b2 * 7);
-            slots.alloc((size_t)max_nodes * 8);
-            work0.alloc(max_nodes);
-            work1.alloc(max_nodes);
-            counts.alloc(n);
-            offsets.alloc(n);
-            scan_scratch.alloc(std::max(scan_scratch_items(n), (scan_scratch_items((size_t)tiles * 256) + 1) / 2 + 1));
-            nodes_tmp.alloc((size_t)max_nodes * 5);
-            tri_order.alloc(n);
-            if (bvh_builder == 2) {
-                d_parent.alloc(num_b2);
-                arrivals.alloc(n);
-            } else {
-                clusters0.alloc(n);
-                clusters1.alloc(n);
-                nn.alloc(n);
-            }
-        };
-        carve();
-        arena.commit();
-        carve();
-        const uint32_t cb_init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
-        CUDA_CHECK(cudaMemcpyAsync(cbounds.ptr, cb_init, sizeof(cb_init), cudaMemcpyHostToDevice, stream));
-
-        crt::Lbvh b;
-        b.n = n;
-        b.verts = d_verts.ptr;
-        b.tri_lo = tri_lo.ptr;
-        b.tri_hi = tri_hi.ptr;
-        b.cbounds = cbounds.ptr;
-        b.children = d_children.ptr;
-        b.parent = d_parent.ptr;
-        b.box_lo = box_lo.ptr;
-        b.box_hi = box_hi.ptr;
-        b.arrivals = arrivals.ptr;
-        b.cost = cost.ptr;
-        b.decision = decision.ptr;
-        const unsigned g = grid_for(n);
-        crt::k_lbvh_bounds<<<g, crt::kBuildBlock, 0, stream>>>(b);
-        crt::k_lbvh_keys<<<g, crt::kBuildBlock, 0, stream>>>(b, keys0.ptr, vals0.ptr);
-        crt::u64 *kin = keys0.ptr, *kout = keys1.ptr;
-        uint32_t *vin = vals0.ptr, *vout = vals1.ptr;
-        for (int shift = 0; shift < 64; shift += 8) {  // 63 key bits
-            crt::k_radix_hist<<<tiles, crt::kBuildBlock, 0, stream>>>(kin, n, shift, hist.ptr, tiles);
-            device_scan<uint32_t>(hist.ptr, hist.ptr, tiles * 256u, reinterpret_cast<uint32_t *>(scan_scratch.ptr));
-            crt::k_radix_scatter<<<tiles, crt::kBuildBlock, 0, stream>>>(kin, vin, kout, vout, n, shift, hist.ptr, tiles);
-            std::swap(kin, kout);
-            std::swap(vin, vout);
-        }
-        CUDA_CHECK(cudaEventRecord(ev_sorted, stream));
-        crt::u64 *h_tail = nullptr;  // pinned: last offset + last count of a scan = its total
-        CUDA_CHECK(cudaMallocHost(&h_tail, 2 * sizeof(crt::u64)));
-        struct FreeHost {
-            void *p;
-            ~FreeHost() { cudaFreeHost(p); }
-        } free_tail{h_tail};
-        auto scan_total = [&](uint32_t items) {  // enqueue after device_scan(counts -> offsets); valid after a sync
-            CUDA_CHECK(cudaMemcpyAsync(h_tail, offsets.ptr + (items - 1), sizeof(crt::u64), cudaMemcpyDeviceToHost, stream));
-            CUDA_CHECK(cudaMemcpyAsync(h_tail + 1, counts.ptr + (items - 1), sizeof(crt::u64), cudaMemcpyDeviceToHost, stream));
-        };
-        uint32_t root = 0u;  // a single triangle: the leaf is the root
-        if (bvh_builder == 2) {
-            crt::k_bvh2_leaves<<<g, crt::kBuildBlock, 0, stream>>>(b, vin, nullptr);
-            if (n > 1) {
-                crt::k_lbvh_hierarchy<<<grid_for(n - 1), crt::kBuildBlock, 0, stream>>>(b, kin);
-                crt::k_lbvh_refit<<<g, crt::kBuildBlock, 0, stream>>>(b);
-                root = n;
-            }
-        } else {
-            uint32_t *cl = clusters0.ptr, *cl_next = clusters1.ptr;
-            crt::k_bvh2_leaves<<<g, crt::kBuildBlock, 0, stream>>>(b, vin, cl);
-            uint32_t m = n, nodes_made = 0;
-            build_rounds = 0;
-            while (m > 1) {
-                if (ploc_tail && m <= (uint32_t)crt::kPlocTailMax) {
-                    // the remaining rounds in one block (k_ploc_tail): no more round trips
-                    uint32_t *rounds_dev = nn.ptr;  // free from here on
-                    uint32_t rounds_host = (uint32_t)build_rounds;
-                    CUDA_CHECK(cudaMemcpyAsync(rounds_dev, &rounds_host, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-                    crt::k_ploc_tail<<<1, crt::kBuildBlock, 0, stream>>>(b, cl, m, nodes_made, ploc_radius, rounds_dev);
-                    CUDA_CHECK(cudaMemcpyAsync(&rounds_host, rounds_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-                    CUDA_CHECK(cudaStreamSynchronize(stream));
-                    build_rounds = (int)rounds_host;
-                    nodes_made += m - 1;
-                    m = 1;
-                    break;
-                }
-                // (an adversarial input can leave one mutual pair per round; after 256 rounds neighbours are paired up)
-                const int forced = build_rounds >= 256 ? 1 : 0;
-                const unsigned gm = (m + crt::kBuildBlock - 1) / crt::kBuildBlock;
-                crt::k_ploc_nn<<<gm, crt::kBuildBlock, 0, stream>>>(b, cl, m, nn.ptr, ploc_radius, forced);
-                crt::k_ploc_mark<<<grid_for(m), crt::kBuildBlock, 0, stream>>>(nn.ptr, m, counts.ptr);
-                device_scan<crt::u64>(counts.ptr, offsets.ptr, m, scan_scratch.ptr);
-                scan_total(m);
-                crt::k_ploc_merge<<<grid_for(m), crt::kBuildBlock, 0, stream>>>(b, cl, nn.ptr, m, offsets.ptr, nodes_made, cl_next);
-                CUDA_CHECK(cudaStreamSynchronize(stream));
-                const crt::u64 total = h_tail[0] + h_tail[1];
-                const uint32_t merged = (uint32_t)total, left = (uint32_t)(total >> 32);
-                if (merged == 0 || left + merged != m) {
-                    throw std::runtime_error("device BVH build: a PLOC round made no progress");
-                }
-                nodes_made += merged;
-                m = left;
-                std::swap(cl, cl_next);
-                ++build_rounds;
-            }
-            if (n > 1) {
-                if (nodes_made != n - 1) {
-                    throw std::runtime_error("device BVH build: PLOC made " + std::to_string(nodes_made) + " of " +
-                                             std::to_string(n - 1) + " nodes");
-                }
-                root = n + (n - 2);
-            }
-        }
-
-        // BVH8 levels: the host only learns each level's size
-        CUDA_CHECK(cudaEventRecord(ev_tree, stream));
-        CUDA_CHECK(cudaMemcpyAsync(work0.ptr, &root, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-        uint32_t *work = work0.ptr, *next_work = work1.ptr;
-        uint32_t node_begin = 0, count = 1, tri_total = 0;
-        depth = 0;
-        while (count) {
-            ++depth;
-            if ((size_t)node_begin + count > max_nodes) {
-                throw std::runtime_error("device BVH build: node count exceeds its bound");
-            }
-            crt::LevelArgs lv;
-            lv.work = work;
-            lv.count = count;
-            lv.node_begin = node_begin;
-            lv.next_begin = node_begin + count;
-            lv.tri_begin = tri_total;
-            lv.slots = slots.ptr;
-            lv.counts = counts.ptr;
-            lv.offsets = offsets.ptr;
-            lv.next_work = next_work;
-            lv.nodes = reinterpret_cast<crt::Bvh8Node *>(nodes_tmp.ptr);
-            lv.tri_order = tri_order.ptr;
-            const unsigned gl = grid_for(count);
-            crt::k_plan_level<<<gl, crt::kBuildBlock, 0, stream>>>(b, lv);
-            device_scan<crt::u64>(counts.ptr, offsets.ptr, count, scan_scratch.ptr);
-            scan_total(count);
-            crt::k_emit_level<<<gl, crt::kBuildBlock, 0, stream>>>(b, lv, vin);
-            CUDA_CHECK(cudaStreamSynchronize(stream));
-            const crt::u64 total = h_tail[0] + h_tail[1];
-            node_begin += count;
-            count = (uint32_t)(total >> 32);
-            tri_total += (uint32_t)total;
-            std::swap(work, next_work);
-        }
-        if (tri_total != n) {
-            throw std::runtime_error("device BVH build: emitted " + std::to_string(tri_total) + " of " + std::to_string(n) +
-                                     " triangles");
-        }
-        check_depth(depth);
-        CUDA_CHECK(cudaEventRecord(ev_emitted, stream));
-        num_nodes = node_begin;
-        d_nodes.alloc((size_t)num_nodes * 5);
-        CUDA_CHECK(cudaMemcpyAsync(d_nodes.ptr, nodes_tmp.ptr, (size_t)num_nodes * 80, cudaMemcpyDeviceToDevice, stream));
-        d_tris.alloc((size_t)n * 3);
-        d_shade.alloc((size_t)n * 3);
-        crt::k_pack_leaf_order<<<g, crt::kBuildBlock, 0, stream>>>(d_verts.ptr, d_shade_in.ptr, tri_order.ptr, n, d_tris.ptr,
-                                                                  d_shade.ptr);
-        CUDA_CHECK(cudaEventRecord(ev1, stream));
-        CUDA_CHECK(cudaGetLastError());
-        std::vector<uint32_t> order(n);
-        CUDA_CHECK(cudaMemcpyAsync(order.data(), tri_order.ptr, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-        CUDA_CHECK(cudaStreamSynchronize(stream));
-        float t = 0.f;
-        CUDA_CHECK(cudaEventElapsedTime(&t, ev0, ev1));
-        ms = t;
-        CUDA_CHECK(cudaEventElapsedTime(&t, ev0, ev_sorted));
-        phase_ms[1] = t;
-        CUDA_CHECK(cudaEventElapsedTime(&t, ev_sorted, ev_tree));
-        phase_ms[2] = t;
-        CUDA_CHECK(cudaEventElapsedTime(&t, ev_tree, ev_emitted));
-        phase_ms[3] = t;
-        CUDA_CHECK(cudaEventElapsedTime(&t, ev_emitted, ev1));
-        phase_ms[4] = t;
-        for (cudaEvent_t e : {ev0, ev1, ev_sorted, ev_tree, ev_emitted}) {
-            cudaEventDestroy(e);
-        }
-        leaf_flat_ids.resize(n);
-        for (uint32_t i = 0; i < n; ++i) {
-            if (order[i] >= n) {
-                throw std::runtime_error("device BVH build: triangle order out of range");
-            }
-            leaf_flat_ids[i] = order[i];  // the flattened primitive id IS the index in flattened order
-        }
-    }
+    static void check_depth(uint32_t depth) { crt_host::check_bvh_depth(depth); }
 
     void set_scene(const crt_scene_t *scene)
     {
@@ -855,13 +417,25 @@ struct crtc_renderer {
         if (bvh_builder != 0 && plan.total_tris > 0) {
             // set_scene on the device: only the references are checked and the materials / textures converted on the host
             crt::convert_shading_inputs(scene, hs, bvh_threads);
-            DeviceBuffer<float> d_verts;
-            DeviceBuffer<float4> d_shade_in;
-            const auto t0 = std::chrono::steady_clock::now();
-            flatten_on_device(scene, plan, d_verts, d_shade_in);  // (ends with a stream synchronisation)
-            phase_ms[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            crt_host::DeviceSceneBuild job;
+            job.stream = stream;
+            job.device = device;
+            job.builder = bvh_builder;
+            job.ploc_radius = ploc_radius;
+            job.ploc_tail = ploc_tail;
+            job.d_nodes = &d_nodes;
+            job.d_tris = &d_tris;
+            job.d_shade = &d_shade;
+            job.leaf_flat_ids = &leaf_flat_ids;
+            job.run(scene, plan);
             num_tris = plan.total_tris;
-            build_on_device((uint32_t)num_tris, d_verts, d_shade_in, bvh_nodes, bvh_depth, bvh_ms);
+            bvh_nodes = job.num_nodes;
+            bvh_depth = job.depth;
+            bvh_ms = job.build_ms;
+            build_rounds = job.rounds;
+            for (int i = 0; i < 5; ++i) {
+                phase_ms[i] = job.phase_ms[i];
+            }
         } else {
             const auto t0 = std::chrono::steady_clock::now();
             crt::flatten_scene(scene, hs, bvh_threads);

@@ -5,7 +5,7 @@ TEST INFRASTRUCTURE: the only edit made to the product source is mechanical — 
     kernel<<<grid, block, 0, stream>>>(args);
 becomes
     simt::launch(grid, block, [&] { kernel(args); });
-(g++ cannot parse the chevrons). Nothing in chameleonrt_b200/ loads this library; tests/test_simt_renderer.py
+(g++ cannot parse the chevrons; crt_cuda_core.cu and its header scene_device_build.cuh are translated). Nothing in chameleonrt_b200/ loads this library; tests/test_simt_renderer.py
 points a RenderCUDA at it explicitly."""
 import os
 import re
@@ -18,7 +18,7 @@ OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libcrt_cuda_core_simt.so")
 
 
-def translate(src: str) -> str:
+def translate(src: str, expected: int) -> str:
     out, pos = [], 0
     pat = re.compile(r"(crt::k_\w+(?:<[\w, ]+>)?)<<<([^,]+),\s*([^,]+),\s*0,\s*stream>>>\(")
     n = 0
@@ -36,20 +36,25 @@ def translate(src: str) -> str:
         pos = i + 1
         n += 1
     out.append(src[pos:])
-    assert n == 29, f"expected 29 kernel launches in crt_cuda_core.cu, found {n}"
-    return '#include "simt_env.h"\n' + "".join(out)
+    assert n == expected, f"expected {expected} kernel launches, found {n}"
+    return "".join(out)
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(CSRC, f) for f in ("crt_cuda_core.cu", "bvh8_device.cuh", "kernels.cuh", "shade_math.cuh", "bvh8_traverse.h", "simt_env.h",
+    srcs = [os.path.join(CSRC, f) for f in ("crt_cuda_core.cu", "scene_device_build.cuh", "cuda_host_utils.h", "bvh8_device.cuh", "kernels.cuh", "shade_math.cuh", "bvh8_traverse.h", "simt_env.h",
                                             "host_scene.cpp", "bvh8_build.cpp")] + [os.path.join(HERE, "cuda_emu.cpp"), __file__]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB
     os.makedirs(OUT, exist_ok=True)
     gen = os.path.join(OUT, "crt_cuda_core_simt.cpp")
     with open(gen, "w") as f:
-        f.write(translate(open(os.path.join(CSRC, "crt_cuda_core.cu")).read().replace('"../../include/crt_cuda.h"',
-                                                                                          f'"{ROOT}/include/crt_cuda.h"')))
+        f.write('#include "simt_env.h"\n' + translate(open(os.path.join(CSRC, "crt_cuda_core.cu")).read().replace(
+            '"../../include/crt_cuda.h"', f'"{ROOT}/include/crt_cuda.h"'), 11))
+    # the device set_scene driver is a header of the same translation unit: its translated copy sits next to the
+    # generated source, where the quoted include finds it first
+    with open(os.path.join(OUT, "scene_device_build.cuh"), "w") as f:
+        f.write(translate(open(os.path.join(CSRC, "scene_device_build.cuh")).read().replace(
+            '"../../include/crt_scene.h"', f'"{ROOT}/include/crt_scene.h"'), 18))
     cuda_inc = os.path.join(os.path.dirname(os.path.dirname(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"))), "include")
     subprocess.check_call(["make", "-s", "-C", CSRC, "host_scene.o", "bvh8_build.o"])
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-pthread", "-march=x86-64-v3", "-ffp-contract=off", "-Wno-attributes",
