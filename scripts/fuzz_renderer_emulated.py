@@ -63,9 +63,11 @@ def one(seed):
         # one in the last bits): a path that diverges may land on a firefly of the fuzzer's unphysical
         # materials (seed 300109: one pixel of -106 against 1e-4 in a frame that sums to 1059), so the three worst pixels
         # are left out of the L1 figure; the fraction of matching pixels still counts all of them.
-        err = np.abs(got - want).sum(axis=2).ravel()
+        both = (np.isfinite(got).all(axis=2) & np.isfinite(want).all(axis=2)).ravel()  # as helpers.parity: finite in both
+        err = np.abs(got - want).sum(axis=2).ravel()[both]
+        ref = np.abs(want).sum(axis=2).ravel()[both]
         keep = np.argsort(err)[: max(1, err.size - 3)]
-        rel_l1 = float(err[keep].sum() / max(1e-12, np.abs(want).sum(axis=2).ravel()[keep].sum()))
+        rel_l1 = float(err[keep].sum() / max(1e-12, ref[keep].sum())) if err.size else 0.0
     ok = frac >= (0.98 if sheared else 0.999) and rel_l1 <= (5e-2 if sheared else 1e-4)
     ok = ok and (has_nan or sheared or rays == rays_cpu)
     if rng.random() < 0.3:  # 2-3 renderers sharing rank 0's frame (crtc_share_frame), as the plugin does for CRT_CUDA_DEVICES
