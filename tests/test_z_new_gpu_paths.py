@@ -9,7 +9,9 @@ import pytest
 from helpers import bounce_rays
 from test_gpu_parity import _render, mods  # noqa: F401  (fixture)
 
-pytestmark = pytest.mark.gpu
+# These kernels have not run on a GPU yet: a per-test limit (pytest-timeout, thread method = the process exits with a
+# traceback) keeps a hung launch from holding the box until the caller's own limit. Subprocess tests carry their own.
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900, method="thread")]
 
 
 BUILDERS = ("host", "device", "device_lbvh")
