@@ -96,7 +96,7 @@ class RenderCUDA:
     def __init__(self, device: int = 0, max_depth: int = 5, rank: int = 0, world_size: int = 1,
                  count_traversal: bool = False, bvh_threads: int = 0, stream: Optional[int] = None,
                  any_far_first: Optional[int] = None, bvh_builder: Optional[str] = None,
-                 tri_pass_defer: Optional[int] = None):
+                 tri_pass_defer: Optional[int] = None, shade_sort: Optional[int] = None):
         self.lib = load_lib()
         self.h = C.c_void_p()
         self._check(self.lib.crtc_create(C.byref(self.h), device))
@@ -108,11 +108,14 @@ class RenderCUDA:
             self._check(self.lib.crtc_set_option(self.h, key.encode(), val))
         # developer knobs of the traversal kernels (defaults are the tuned values)
         for env, key in (("CRT_CUDA_REFILL_IDLE", "refill_idle"), ("CRT_CUDA_ANY_FAR_FIRST", "any_far_first"),
-                         ("CRT_CUDA_PLOC_RADIUS", "bvh_ploc_radius"), ("CRT_CUDA_TRI_PASS_DEFER", "tri_pass_defer")):
+                         ("CRT_CUDA_PLOC_RADIUS", "bvh_ploc_radius"), ("CRT_CUDA_TRI_PASS_DEFER", "tri_pass_defer"),
+                         ("CRT_CUDA_SHADE_SORT", "shade_sort")):
             if os.environ.get(env):
                 self._check(self.lib.crtc_set_option(self.h, key.encode(), int(os.environ[env])))
         if tri_pass_defer is not None:  # 0 / 16 / 24: experimental scheduling variant of k_traverse; never changes a result
             self._check(self.lib.crtc_set_option(self.h, b"tri_pass_defer", int(tri_pass_defer)))
+        if shade_sort is not None:  # 0 / 1 / 2: shade queue bucketed by material id before k_shade; never changes a result
+            self._check(self.lib.crtc_set_option(self.h, b"shade_sort", int(shade_sort)))
         if any_far_first is not None:  # 0 / 1 / 2 = auto: traversal order of shadow rays; never changes a result (crt_cuda.h)
             self._check(self.lib.crtc_set_option(self.h, b"any_far_first", int(any_far_first)))
         # where set_scene builds the BVH8: "host" (binned SAH, the default), "device" (PLOC on the GPU: much faster

@@ -89,6 +89,9 @@ struct crtc_renderer {
     bool count_traversal = false;
     int refill_idle = crt::kRefillIdle;  // idle lanes that trigger a refill of the traversal warps
     int tri_pass_defer = 0;              // 0 (default) / 16 / 24: pooled pairs a triangle pass waits for (kernels.cuh)
+    // The shade queue bucketed by material id before k_shade (k_queue_hist / k_queue_scatter): 0 = off (default),
+    // 1 = from the first bounce on (primary hits keep their screen order), 2 = every shade launch. Same image.
+    int shade_sort = 0;
     // Shadow rays visit the children of a node farthest-first: 0 = no, 1 = yes, 2 = auto (default) — frame 1
     // after set_scene is rendered far-first, frame 2 near-first, and far-first is kept from frame 3 on only if its
     // traversal stage was at least 3 % faster (blocking render() calls only; the image is the same either way).
@@ -147,6 +150,7 @@ struct crtc_renderer {
         d_sray_d;
     DeviceBuffer<uint8_t> d_vis;
     DeviceBuffer<uint32_t> d_queue0, d_queue1, d_counters;
+    DeviceBuffer<uint32_t> d_queue_sorted, d_sort_hist, d_sort_scratch;  // option shade_sort
     DeviceBuffer<unsigned long long> d_trav_counters;
 
     // framebuffers
@@ -287,6 +291,42 @@ struct crtc_renderer {
             crt::k_traverse<true, 24><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any, work_counter, sched);
             break;
         }
+    }
+
+    // exclusive scan of n uint32 in place; `scratch` holds the tile sums of every recursion level. Returns its launches.
+    int scan_u32(uint32_t *data, uint32_t n, uint32_t *scratch)
+    {
+        const unsigned tiles = (n + crt::kBuildTile - 1) / crt::kBuildTile;
+        crt::k_scan_tile<uint32_t><<<tiles, crt::kBuildBlock, 0, stream>>>(data, data, n, tiles > 1 ? scratch : nullptr);
+        if (tiles <= 1) {
+            return 1;
+        }
+        const int below = scan_u32(scratch, tiles, scratch + tiles);
+        crt::k_scan_add<uint32_t><<<tiles, crt::kBuildBlock, 0, stream>>>(data, n, scratch);
+        return below + 2;
+    }
+
+    // Option shade_sort: queue `queue_in` of bounce `bounce` (length on the device, capacity `npaths`) bucketed by the
+    // material of each path's hit into d_queue_sorted. Returns the number of launches.
+    int sort_shade_queue(const crt::DeviceScene &sc, const crt::PathState &ps, const uint32_t *queue_in, int bounce, size_t npaths)
+    {
+        const uint32_t num_tiles = (uint32_t)((npaths + crt::kSortTile - 1) / crt::kSortTile);
+        const uint32_t hist_items = 256u * num_tiles;
+        size_t scratch_items = 1, left = hist_items;
+        while (left > (size_t)crt::kBuildTile) {
+            left = (left + crt::kBuildTile - 1) / crt::kBuildTile;
+            scratch_items += left;
+        }
+        if (d_queue_sorted.count < npaths || d_sort_hist.count < hist_items || d_sort_scratch.count < scratch_items) {
+            CUDA_CHECK(cudaStreamSynchronize(stream));  // (first frame with the option on, or a larger batch)
+            d_queue_sorted.alloc(npaths);
+            d_sort_hist.alloc(hist_items);
+            d_sort_scratch.alloc(scratch_items);
+        }
+        crt::k_queue_hist<256><<<num_tiles, crt::kSortBlock, 0, stream>>>(sc, ps, queue_in, bounce, d_sort_hist.ptr, num_tiles);
+        const int scans = scan_u32(d_sort_hist.ptr, hist_items, d_sort_scratch.ptr);
+        crt::k_queue_scatter<256><<<num_tiles, crt::kSortBlock, 0, stream>>>(sc, ps, queue_in, d_queue_sorted.ptr, bounce, d_sort_hist.ptr, num_tiles);
+        return scans + 2;
     }
 
     crt::DeviceScene device_scene() const
@@ -590,7 +630,13 @@ struct crtc_renderer {
             rec.mark(stream, kStPrimary);
             rec.launches += 2;
             for (int b = 0; b < max_depth; ++b) {
-                uint32_t *qin = ps.queue[b & 1], *qout = ps.queue[(b + 1) & 1];
+                const uint32_t *qin = ps.queue[b & 1];
+                uint32_t *qout = ps.queue[(b + 1) & 1];
+                if (shade_sort == 2 || (shade_sort == 1 && b > 0)) {
+                    // (its time counts as shading: the next mark closes the stage)
+                    rec.launches += sort_shade_queue(sc, ps, qin, b, npaths);
+                    qin = d_queue_sorted.ptr;
+                }
                 crt::k_shade<<<g128, 128, 0, stream>>>(sc, ps, qin, qout, b, max_depth);
                 rec.mark(stream, kStShade);
                 const bool last = b + 1 == max_depth;
@@ -992,6 +1038,11 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
                 throw std::runtime_error("tri_pass_defer must be 0, 16 or 24");
             }
             r->tri_pass_defer = (int)value;
+        } else if (k == "shade_sort") {
+            if (value < 0 || value > 2) {
+                throw std::runtime_error("shade_sort must be 0, 1 or 2");
+            }
+            r->shade_sort = (int)value;
         } else if (k == "bvh_ploc_tail") {
             r->ploc_tail = value != 0;
         } else if (k == "bvh_ploc_radius") {
@@ -1043,6 +1094,8 @@ int crtc_get_option(crtc_renderer *r, const char *key, int64_t *value)
             *value = r->bvh_threads;
         } else if (k == "tri_pass_defer") {
             *value = r->tri_pass_defer;
+        } else if (k == "shade_sort") {
+            *value = r->shade_sort;
         } else if (k == "bvh_builder") {
             *value = r->bvh_builder;
         } else if (k == "bvh_build_rounds") {

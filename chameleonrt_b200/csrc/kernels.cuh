@@ -603,6 +603,99 @@ __global__ void __launch_bounds__(128, 6) k_shade(DeviceScene sc, PathState ps, 
     }
 }
 
+// ---- option "shade_sort" (off by default): the shade queue bucketed by material id ----
+// A stable one-pass counting sort of queue_in on the material of each path's hit, so that the lanes of a k_shade warp
+// unpack the same material, sample the same textures and run the same BSDF lobes. 256 buckets: material ids 0..253 their
+// own, every id >= 254 shares bucket 254, paths that missed are bucket 255. The image does not depend on the order of
+// a queue (fixed accumulation order), so frames are bit-identical with and without the sort.
+// The queue length lives on the device: the grids cover the queue's capacity and tiles beyond the length count zero.
+// k_queue_hist -> exclusive scan of hist (digit-major: one scan yields every (bucket, tile) offset) -> k_queue_scatter.
+constexpr int kSortBlock = 256, kSortItems = 8, kSortTile = kSortBlock * kSortItems;
+
+__device__ __forceinline__ uint32_t shade_bucket(const DeviceScene &sc, const PathState &ps, uint32_t slot)
+{
+    const uint32_t tri = __float_as_uint(reinterpret_cast<const float *>(ps.hit + slot)[3]);
+    if (tri == kMiss) {
+        return 255u;
+    }
+    const uint32_t material_id = __float_as_uint(reinterpret_cast<const float *>(sc.shade + 3 * (size_t)tri)[3]);
+    return material_id < 254u ? material_id : 254u;
+}
+
+template <int BUCKETS>  // 256 (a template so that the one-thread host build of this header never sees its barriers)
+__global__ void __launch_bounds__(kSortBlock) k_queue_hist(DeviceScene sc, PathState ps, const uint32_t *queue_in, int bounce,
+                                                           uint32_t *hist, uint32_t num_tiles)
+{
+    static_assert(BUCKETS == kSortBlock, "one thread per bucket");
+    __shared__ uint32_t h[BUCKETS];
+    const uint32_t n = ps.counters[kCntQueue + bounce];
+    h[threadIdx.x] = 0u;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * (uint32_t)kSortTile;
+    for (int k = 0; k < kSortItems; ++k) {
+        const uint32_t i = base + (uint32_t)k * kSortBlock + threadIdx.x;
+        if (i < n) {
+            atomicAdd(&h[shade_bucket(sc, ps, queue_in[i])], 1u);
+        }
+    }
+    __syncthreads();
+    hist[threadIdx.x * num_tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// block = one tile of 2048 queue entries, warp w = entries [w * 256, w * 256 + 256) of it, 8 rounds of 32. An entry's
+// rank among the equal buckets of its tile: earlier warps, then earlier rounds, then lower lanes (stable).
+template <int BUCKETS>
+__global__ void __launch_bounds__(kSortBlock) k_queue_scatter(DeviceScene sc, PathState ps, const uint32_t *queue_in,
+                                                              uint32_t *queue_sorted, int bounce, const uint32_t *hist_scanned,
+                                                              uint32_t num_tiles)
+{
+    __shared__ uint32_t cnt[kSortBlock / 32][BUCKETS];
+    __shared__ uint32_t goff[BUCKETS];
+    const uint32_t n = ps.counters[kCntQueue + bounce];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lanemask_lt = (1u << lane) - 1u;
+    for (int w = 0; w < kSortBlock / 32; ++w) {
+        cnt[w][threadIdx.x] = 0u;
+    }
+    goff[threadIdx.x] = hist_scanned[threadIdx.x * num_tiles + blockIdx.x];
+    __syncthreads();
+    const uint32_t base = blockIdx.x * (uint32_t)kSortTile + (uint32_t)warp * 256u;
+    uint32_t slot[kSortItems], where[kSortItems];  // where = bucket << 16 | rank within (warp, bucket)
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t i = base + (uint32_t)r * 32u + lane;
+        const bool valid = i < n;
+        slot[r] = valid ? queue_in[i] : 0u;
+        const uint32_t d = valid ? shade_bucket(sc, ps, slot[r]) : (uint32_t)BUCKETS;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t before = 0u;
+        if (lane == leader && valid) {
+            before = cnt[warp][d];
+            cnt[warp][d] = before + (uint32_t)__popc(peers);
+        }
+        before = __shfl_sync(0xffffffffu, before, leader);
+        where[r] = (d << 16) | (before + (uint32_t)__popc(peers & lanemask_lt));
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // per bucket: exclusive prefix of the warps' counts
+        uint32_t run = 0u;
+        for (int w = 0; w < kSortBlock / 32; ++w) {
+            const uint32_t c = cnt[w][threadIdx.x];
+            cnt[w][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t i = base + (uint32_t)r * 32u + lane;
+        if (i < n) {
+            const uint32_t d = where[r] >> 16;
+            queue_sorted[goff[d] + cnt[warp][d] + (where[r] & 0xffffu)] = slot[r];
+        }
+    }
+}
+
 // illum = illum + path_throughput * (L1 [if unoccluded] + L2 [if traced and unoccluded])
 __global__ void __launch_bounds__(256) k_nee_resolve(PathState ps, const uint32_t *queue_in, int bounce)
 {

@@ -172,4 +172,43 @@ void crt_simt_traverse(void *p, const float *closest, uint32_t n_closest, const 
         std::memcpy(vis_out, vis.data(), n_any);
     }
 }
+
+// Option "shade_sort" at kernel level: k_queue_hist -> exclusive scan (done here on the host; the product scans with
+// the k_scan_tile / k_scan_add kernels the device BVH build uses) -> k_queue_scatter over a queue of `n` path slots
+// whose capacity is `capacity` (grids cover the capacity, the length is read from the counters as on the device).
+// hit_tri[slot] = leaf-order triangle of the slot's hit or kMiss; tri_material[tri] = its material id.
+void crt_simt_sort_queue(const uint32_t *hit_tri, uint32_t num_slots, const uint32_t *tri_material, uint32_t num_tris,
+                         const uint32_t *queue, uint32_t n, uint32_t capacity, uint32_t *sorted_out)
+{
+    g_err.clear();
+    std::vector<float4> hit(std::max(1u, num_slots)), shade(3 * (size_t)std::max(1u, num_tris));
+    for (uint32_t i = 0; i < num_slots; ++i) {
+        hit[i] = make_float4(1.f, 0.f, 0.f, __uint_as_float(hit_tri[i]));
+    }
+    for (uint32_t t = 0; t < num_tris; ++t) {
+        shade[3 * (size_t)t] = make_float4(0.f, 0.f, 1.f, __uint_as_float(tri_material[t]));
+    }
+    std::vector<uint32_t> counters(crt::kNumCounters, 0u);
+    const int bounce = 2;
+    counters[crt::kCntQueue + bounce] = n;
+    crt::DeviceScene sc{};
+    sc.shade = shade.data();
+    crt::PathState ps{};
+    ps.hit = hit.data();
+    ps.counters = counters.data();
+    const uint32_t num_tiles = (capacity + crt::kSortTile - 1) / crt::kSortTile;
+    std::vector<uint32_t> hist(256 * (size_t)num_tiles, 0xdeadbeefu), out(std::max(1u, capacity), 0xffffffffu);
+    simt::launch(num_tiles, crt::kSortBlock, [&] { crt::k_queue_hist<256>(sc, ps, queue, bounce, hist.data(), num_tiles); });
+    uint32_t run = 0;
+    for (uint32_t &h : hist) {
+        const uint32_t c = h;
+        h = run;
+        run += c;
+    }
+    if (run != n) {
+        g_err = "crt_simt_sort_queue: the histogram does not add up to the queue length";
+    }
+    simt::launch(num_tiles, crt::kSortBlock, [&] { crt::k_queue_scatter<256>(sc, ps, queue, out.data(), bounce, hist.data(), num_tiles); });
+    std::memcpy(sorted_out, out.data(), sizeof(uint32_t) * capacity);
+}
 }

@@ -65,6 +65,13 @@ static inline T __shfl_down_sync(unsigned, T, int)
     return T(0);  // lanes 1..31 do not exist: they contribute nothing to a reduction
 }
 static inline void __syncwarp() {}
+// (declarations for the block-level kernels of kernels.cuh, which are templates and never instantiated in this build)
+static inline void __syncthreads() {}
+template <typename T>
+static inline unsigned __match_any_sync(unsigned, T)
+{
+    return 1u;
+}
 template <typename T>
 static inline T atomicAdd(T *p, T v)
 {

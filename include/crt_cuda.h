@@ -61,6 +61,10 @@ void crtc_destroy(crtc_renderer *r);
  *   "tri_pass_defer" 0 (default), 16 or 24: experimental scheduling variant of the traversal kernel — a warp's pooled
  *                 triangle pass waits until that many (ray, triangle) pairs are pending or no lane can descend.
  *                 Never changes a result; not yet timed on a GPU.
+ *   "shade_sort"  0 (default), 1 or 2: the queue of paths to shade is bucketed by the material id of each path's hit
+ *                 (one stable counting-sort pass on the device, 256 buckets) before the shading kernel runs, so that a
+ *                 warp unpacks one material and runs the same BSDF lobes: 1 = from the first bounce on (primary hits
+ *                 keep their screen order), 2 = every bounce. Never changes a result; not yet timed on a GPU.
  *   "bvh_builder" where crtc_set_scene builds the BVH8: 0 = on the host (binned SAH, the default); on the device
  *                 (chameleonrt_b200/csrc/bvh8_device.cuh): 1 = PLOC (mutual nearest neighbours in Morton order),
  *                 2 = LBVH (Karras), both followed by the host builder's 8-wide collapse — a much shorter set_scene

@@ -88,3 +88,31 @@ def test_k_traverse_under_simt_emulation_equals_single_ray_traversal(lib, name):
         got, vis = _run(lib, h, closest, shadow, sched, perm, blocks=2)
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)) and np.array_equal(vis == 0, occluded)
     lib.crt_simt_destroy(h)
+
+
+@pytest.mark.parametrize("n,capacity,materials", [(0, 1, 3), (1, 1, 1), (31, 2048, 2), (2048, 2048, 5), (5000, 9000, 300),
+                                                  (4097, 4097, 255)])
+def test_shade_queue_sort_kernels_are_a_stable_sort_by_material_bucket(lib, n, capacity, materials):
+    """k_queue_hist + k_queue_scatter (option shade_sort) under the SIMT emulation: the sorted queue is the stable
+    sort of the input queue by bucket (material id, ids >= 254 share bucket 254, misses are bucket 255); entries
+    beyond the device-side length are neither counted nor written."""
+    rng = np.random.default_rng(n + 7 * materials)
+    num_slots, num_tris = capacity + 5, 97
+    tri_material = rng.integers(0, materials, num_tris).astype(np.uint32)
+    hit_tri = rng.integers(0, num_tris, num_slots).astype(np.uint32)
+    hit_tri[rng.random(num_slots) < 0.2] = 0xFFFFFFFF
+    queue = rng.permutation(num_slots)[:capacity].astype(np.uint32)  # entries [n, capacity) are stale
+    out = np.zeros(capacity, np.uint32)
+    lib.crt_simt_sort_queue.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.crt_simt_sort_queue.restype = None
+    lib.crt_simt_last_error.restype = C.c_char_p
+    lib.crt_simt_sort_queue(hit_tri.ctypes.data, num_slots, tri_material.ctypes.data, num_tris, queue.ctypes.data, n, capacity,
+                            out.ctypes.data)
+    assert not lib.crt_simt_last_error(), lib.crt_simt_last_error()
+    live = queue[:n]
+    tri = hit_tri[live]
+    bucket = np.where(tri == 0xFFFFFFFF, 255, np.minimum(tri_material[np.minimum(tri, num_tris - 1)], 254))
+    expect = live[np.argsort(bucket, kind="stable")]
+    assert (out[:n] == expect).all()
+    assert (out[n:] == 0xFFFFFFFF).all()
+

@@ -291,3 +291,10 @@ def test_triangle_pass_deferral_on_the_emulated_renderer(mods):
     import test_z_new_gpu_paths as dev_tests
 
     dev_tests.test_triangle_pass_deferral_does_not_change_the_image(mods, size=(48, 32), detail=0.2)
+
+
+def test_shade_queue_sort_on_the_emulated_renderer(mods):
+    """The material-id bucketing of the shade queue (option shade_sort) through the real launch sequence."""
+    import test_z_new_gpu_paths as dev_tests
+
+    dev_tests.test_shade_queue_sort_does_not_change_the_image(mods, size=(48, 32), detail=0.2, frames=1, batch=2)

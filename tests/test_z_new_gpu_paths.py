@@ -207,6 +207,44 @@ def test_triangle_pass_deferral_does_not_change_the_image(mods, size=(256, 144),
         RenderCUDA(0, tri_pass_defer=8)
 
 
+def test_shade_queue_sort_does_not_change_the_image(mods, size=(256, 144), detail=0.3, frames=2, batch=3):
+    """Option shade_sort = 1 / 2: the queue k_shade reads is bucketed by material id first (k_queue_hist, scan,
+    k_queue_scatter — a stable counting sort whose length lives on the device). Accumulation order is fixed per path and
+    per pixel, so frames, ray counts and work counters are the same bit for bit; only the launch count grows. Also with
+    several frames in one wavefront (a larger queue capacity, then a smaller one again) and on a scene with instancing."""
+    from chameleonrt_b200.scenes import san_miguel_like, sponza_like
+    from helpers import camera_for
+
+    RenderCUDA = mods[0]
+    for make, depth in ((lambda: sponza_like(spp=2, detail=detail, tex_size=64), 5),
+                        (lambda: san_miguel_like(spp=1, scale=0.03, tex_size=64), 3)):
+        scene, cam = make()
+        c = camera_for(cam)
+        view = (c.eye(), c.dir(), c.up(), cam["fov_y"])
+        out = []
+        for mode in (0, 1, 2):
+            r = RenderCUDA(0, max_depth=depth, count_traversal=True, any_far_first=0, shade_sort=mode)
+            r.initialize(*size)
+            r.set_scene(scene)
+            for f in range(frames):
+                st = r.render(*view, f == 0, True)
+            launches = r.counters()["kernel_launches"]
+            r.render_async(*view, False, batch)  # `batch` frames as one wavefront
+            r.sync()
+            st2 = r.render(*view, False, True)
+            out.append((r.read_accum(), r.read_img(), st.num_rays, st2.num_rays, r.counters(), launches))
+            assert r.get_option("shade_sort") == mode
+        a0, i0, n0, m0, c0, l0 = out[0]
+        assert l0 == 3 + 3 * depth
+        for mode, (a, i, n, m, cn, l) in zip((1, 2), out[1:]):
+            assert (a0.view(np.uint32) == a.view(np.uint32)).all() and (i0 == i).all() and (n0, m0) == (n, m), mode
+            for k in ("closest_rays", "occlusion_rays", "paths", "closest_nodes_visited", "any_nodes_visited"):
+                assert c0[k] == cn[k], (mode, k)
+            assert l > l0 + 3 * (depth - (2 - mode)) - 1, (mode, l, l0)  # >= 3 more launches per sorted bounce
+    with pytest.raises(RuntimeError, match="shade_sort"):
+        RenderCUDA(0, shade_sort=3)
+
+
 def test_peer_written_frame_two_processes_one_gpu(built):
     """Frame assembly without a gather (crtc_export_frame / crtc_import_frame): two PROCESSES, both on cuda:0 (gloo
     carries the 128 handle bytes; NCCL would refuse two ranks on one GPU), rank 1's resolve kernel writes its tiles
