@@ -76,6 +76,7 @@ RenderCUDA::RenderCUDA()
             check(crtc_set_option(r, "bvh_threads", env_or("CRT_CUDA_BVH_THREADS", 0)));
             check(crtc_set_option(r, "bvh_builder", env_or("CRT_CUDA_BVH_BUILDER", 0)));  // 1 / 2 = build on the device (crt_cuda.h)
             check(crtc_set_option(r, "any_far_first", env_or("CRT_CUDA_ANY_FAR_FIRST", 2)));  // crt_cuda.h; 2 = per scene
+            check(crtc_set_option(r, "shade_sort", env_or("CRT_CUDA_SHADE_SORT", 0)));  // 1 / 2 = shade queue bucketed by material
         }
     } catch (...) {
         for (crtc_renderer *r : renderers) {

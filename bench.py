@@ -519,7 +519,8 @@ def main():
                                        "; e2e: frame by frame, assembly + readback every frame") if world > 1 else "single GPU",
                        "frames_in_flight": frames_in_flight,
                        "bvh_builder": ("host (binned SAH)", "device (PLOC)", "device (LBVH)")[gpu.get_option("bvh_builder")],
-                       "traversal_variant": {"tri_pass_defer": gpu.get_option("tri_pass_defer"), "refill_idle": gpu.get_option("refill_idle")},
+                       "traversal_variant": {"tri_pass_defer": gpu.get_option("tri_pass_defer"), "refill_idle": gpu.get_option("refill_idle"),
+                                             "shade_sort": gpu.get_option("shade_sort")},
                        "shadow_ray_order": {1: "far-first", 0: "near-first"}.get(shadow_far_first, "undecided (near-first)") +
                                            " (chosen per scene from the traversal times of warm-up frames 1 and 2; same image either way)",
                        "l2": f"inputs larger than L2: ~{WIDTH * HEIGHT * SPP * 250 / 1e9:.1f} GB of per-frame path state "

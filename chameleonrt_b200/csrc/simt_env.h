@@ -262,12 +262,15 @@ struct Pool {
     }
 };
 
-inline Pool &pool()
+// (internal linkage: two test libraries in one process — libcrt_simt_hostcheck.so and the emulated renderer — must not
+// share one pool through the unified function-local static of an inline function: its workers set the thread-local
+// threadIdx / warp pointers of the library that created them)
+static inline Pool &pool()
 {
     static Pool p;
     return p;
 }
-inline std::mutex &launch_mutex()
+static inline std::mutex &launch_mutex()
 {
     static std::mutex m;
     return m;

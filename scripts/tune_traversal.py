@@ -36,3 +36,23 @@ for builder, refill, far, defer in grid:
     print(f"builder={builder:6s} refill_idle={refill:2d} far_first={far} tri_pass_defer={defer:2d}  traverse {trav:7.3f} "
           f"({trav / base - 1:+.1%})  frame {acc['frame']:7.3f}  " + " ".join(f"{k}={v:.3f}" for k, v in acc.items()
                                                                                 if k not in ("frame",)), flush=True)
+
+# The shade queue bucketed by material id (option shade_sort): the sort's launches are inside the "shade" stage, so the
+# shade time says whether the more coherent k_shade pays for them; the traversal that follows sees a differently
+# ordered queue of continuation rays, so its time is printed as well.
+print("# shade_sort (host tree, default traversal)", flush=True)
+base_shade = None
+for mode in (0, 1, 2):
+    gpu = RenderCUDA(0, max_depth=bench.MAX_DEPTH, shade_sort=mode)
+    gpu.initialize(bench.WIDTH, bench.HEIGHT)
+    gpu.set_scene(scene)
+    acc = {}
+    for f in range(8):
+        gpu.render(*view, f == 0, False)
+        if f >= 3:
+            for k, v in gpu.stage_times().items():
+                acc[k] = acc.get(k, 0) + v / 5
+    base_shade = base_shade or (acc["shade"], acc["frame"])
+    print(f"shade_sort={mode}  shade {acc['shade']:7.3f} ({acc['shade'] / base_shade[0] - 1:+.1%})  traverse {acc['traverse']:7.3f}  "
+          f"frame {acc['frame']:7.3f} ({acc['frame'] / base_shade[1] - 1:+.1%})", flush=True)
+
