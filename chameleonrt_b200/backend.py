@@ -180,6 +180,11 @@ class RenderCUDA:
         self._check(self.lib.crtc_render_async(self.h, pp, dp, up_, C.c_float(fovy), 1 if camera_changed else 0,
                                                num_frames))
 
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        """crtc_set_stream: the CUDA stream (a cudaStream_t as an integer) every later launch and copy of this renderer
+        goes to; None = the renderer's own non-blocking stream."""
+        self._check(self.lib.crtc_set_stream(self.h, C.c_void_p(cuda_stream)))
+
     def set_option(self, key: str, value: int) -> None:
         """crtc_set_option (include/crt_cuda.h lists the keys); options apply to the next set_scene / frame."""
         self._check(self.lib.crtc_set_option(self.h, key.encode(), int(value)))

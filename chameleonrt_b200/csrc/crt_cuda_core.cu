@@ -103,12 +103,15 @@ struct crtc_renderer {
     bool auto_decided = false, auto_choice = false;
     bool frame_far_first = false;   // the order used by the frame being enqueued
 
-    bool pick_far_first() const
+    // `blocking`: the frame comes from render(), whose stage times feed auto_tune_step(). Frames enqueued with
+    // crtc_render_async never advance the trial, so while it is undecided they run near-first (the order the
+    // instrumented counting pass of bench.py assumes for "undecided").
+    bool pick_far_first(bool blocking) const
     {
         if (any_far_first != 2) {
             return any_far_first == 1;
         }
-        return auto_decided ? auto_choice : auto_frames == 1;
+        return auto_decided ? auto_choice : (blocking && auto_frames == 1);
     }
     // after a blocking frame's stage times are known
     void auto_tune_step()
@@ -439,6 +442,15 @@ struct crtc_renderer {
     }
 
     static void check_depth(uint32_t depth) { crt_host::check_bvh_depth(depth); }
+    // k_traverse packs a pooled (owner lane, leaf-order triangle index) pair into one 32-bit slot: 5 + 27 bits
+    static void check_triangle_count(size_t n)
+    {
+        if (n >= (size_t)crt::kMaxTriangles) {
+            throw std::runtime_error("set_scene: " + std::to_string(n) + " triangles; this backend holds at most 2^27 - 1 (" +
+                                     std::to_string(crt::kMaxTriangles - 1) + ") per scene");
+        }
+    }
+    int builder_fallbacks = 0;  // device builds that fell back to the host builder (crtc_get_option "bvh_builder_fallbacks")
 
     void set_scene(const crt_scene_t *scene)
     {
@@ -454,7 +466,9 @@ struct crtc_renderer {
         if (bvh_builder != 0) {
             crt::plan_flatten(scene, plan);
         }
+        bool built_on_device = false;
         if (bvh_builder != 0 && plan.total_tris > 0) {
+            check_triangle_count(plan.total_tris);
             // set_scene on the device: only the references are checked and the materials / textures converted on the host
             crt::convert_shading_inputs(scene, hs, bvh_threads);
             crt_host::DeviceSceneBuild job;
@@ -467,21 +481,35 @@ struct crtc_renderer {
             job.d_tris = &d_tris;
             job.d_shade = &d_shade;
             job.leaf_flat_ids = &leaf_flat_ids;
-            job.run(scene, plan);
-            num_tris = plan.total_tris;
-            bvh_nodes = job.num_nodes;
-            bvh_depth = job.depth;
-            bvh_ms = job.build_ms;
-            build_rounds = job.rounds;
-            for (int i = 0; i < 5; ++i) {
-                phase_ms[i] = job.phase_ms[i];
+            try {
+                job.run(scene, plan);
+                built_on_device = true;
+            } catch (const crt_host::DeviceBuildFailure &e) {
+                // the builder gave up on this input (no PLOC progress, a tree deeper than the traversal stack, ...): the
+                // host builder takes over; scene errors and CUDA errors are not caught here
+                std::fprintf(stderr, "crt_cuda: %s; building the BVH on the host instead\n", e.what());
+                CUDA_CHECK(cudaStreamSynchronize(stream));
+                hs = crt::HostScene();
+                builder_fallbacks++;
             }
-        } else {
+            if (built_on_device) {
+                num_tris = plan.total_tris;
+                bvh_nodes = job.num_nodes;
+                bvh_depth = job.depth;
+                bvh_ms = job.build_ms;
+                build_rounds = job.rounds;
+                for (int i = 0; i < 5; ++i) {
+                    phase_ms[i] = job.phase_ms[i];
+                }
+            }
+        }
+        if (!built_on_device) {
             const auto t0 = std::chrono::steady_clock::now();
             crt::flatten_scene(scene, hs, bvh_threads);
             phase_ms[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             phase_ms[1] = phase_ms[2] = phase_ms[3] = 0.0;  // the host builder reports one figure: scene_info[3]
             num_tris = hs.num_tris();
+            check_triangle_count(num_tris);
             crt::Bvh8 bvh;
             crt::build_bvh8(hs.tri_verts.data(), hs.num_tris(), bvh_threads, bvh);
             check_depth(bvh.max_depth);
@@ -538,7 +566,7 @@ struct crtc_renderer {
         for (int i = 0; i < 5; ++i) {
             scene_info[6 + i] = phase_ms[i];
         }
-        scene_info[11] = bvh_builder == 1 ? (double)build_rounds : 0.0;
+        scene_info[11] = (bvh_builder == 1 && built_on_device) ? (double)build_rounds : 0.0;
         if (npx_local) {
             CUDA_CHECK(cudaMemsetAsync(d_accum_local.ptr, 0, (size_t)npx_local * 3 * sizeof(float), stream));
         }
@@ -579,7 +607,7 @@ struct crtc_renderer {
     // `num_frames` consecutive frames are rendered as ONE wavefront (their samples are in flight
     // together) and folded into the running mean in order — bit-identical to num_frames calls.
     FrameRecord &enqueue_frame(const float *pos, const float *dir, const float *up, float fovy, bool camera_changed,
-                               uint32_t num_frames = 1)
+                               uint32_t num_frames = 1, bool blocking = false)
     {
         if (num_frames < 1 || num_frames > 64) {
             throw std::runtime_error("render: num_frames must be in [1, 64]");
@@ -600,7 +628,7 @@ struct crtc_renderer {
             throw std::runtime_error("render: more than 2^31 paths in flight on one device");
         }
         ensure_path_buffers(npaths);
-        frame_far_first = pick_far_first();
+        frame_far_first = pick_far_first(blocking);
         const crt::DeviceScene sc = device_scene();
         crt::FrameLayout fl = frame_layout();
         fl.frames = num_frames;
@@ -727,7 +755,7 @@ struct crtc_renderer {
     void render(const float *pos, const float *dir, const float *up, float fovy, bool camera_changed, bool readback,
                 uint32_t *img, crt_render_stats_t *stats)
     {
-        enqueue_frame(pos, dir, up, fovy, camera_changed);
+        enqueue_frame(pos, dir, up, fovy, camera_changed, 1, true);
         if (readback && img && world_size == 1) {
             CUDA_CHECK(cudaMemcpyAsync(img, d_img_full.ptr, (size_t)fb_w * fb_h * 4, cudaMemcpyDeviceToHost, stream));
         }
@@ -957,6 +985,13 @@ struct crtc_renderer {
 // ---------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------
+static void require_renderer(const crtc_renderer *r)
+{
+    if (!r) {
+        throw std::runtime_error("renderer handle is NULL");
+    }
+}
+
 #define CRTC_TRY(body)                      \
     try {                                   \
         body;                               \
@@ -1017,7 +1052,7 @@ void crtc_destroy(crtc_renderer *r)
 
 int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
 {
-    CRTC_TRY({
+    CRTC_TRY({ require_renderer(r);
         const std::string k = key ? key : "";
         if (k == "max_depth") {
             if (value < 1 || value > crt::kMaxDepthSupported) {
@@ -1069,17 +1104,13 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
         } else {
             throw std::runtime_error("unknown option '" + k + "'");
         }
-        if (r->rank < 0 || r->rank >= r->world_size) {
-            if (k == "rank" || k == "world_size") {
-                // allow setting world_size before rank; validated again in initialize
-            }
-        }
+        // (rank may be set before world_size: the pair is validated in crtc_initialize)
     })
 }
 
 int crtc_get_option(crtc_renderer *r, const char *key, int64_t *value)
 {
-    CRTC_TRY({
+    CRTC_TRY({ require_renderer(r);
         const std::string k = key ? key : "";
         if (!value) {
             throw std::runtime_error("crtc_get_option: value is null");
@@ -1098,6 +1129,8 @@ int crtc_get_option(crtc_renderer *r, const char *key, int64_t *value)
             *value = r->shade_sort;
         } else if (k == "bvh_builder") {
             *value = r->bvh_builder;
+        } else if (k == "bvh_builder_fallbacks") {
+            *value = r->builder_fallbacks;
         } else if (k == "bvh_build_rounds") {
             *value = r->build_rounds;  // PLOC rounds of the last device build
         } else if (k == "count_traversal") {
@@ -1117,12 +1150,12 @@ int crtc_get_option(crtc_renderer *r, const char *key, int64_t *value)
 
 int crtc_set_stream(crtc_renderer *r, void *cuda_stream)
 {
-    CRTC_TRY({ r->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : r->own_stream; })
+    CRTC_TRY({ require_renderer(r); r->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : r->own_stream; })
 }
 
 int crtc_initialize(crtc_renderer *r, int fb_width, int fb_height)
 {
-    CRTC_TRY({
+    CRTC_TRY({ require_renderer(r);
         if (r->rank < 0 || r->rank >= r->world_size) {
             throw std::runtime_error("rank must be in [0, world_size)");
         }
@@ -1132,7 +1165,7 @@ int crtc_initialize(crtc_renderer *r, int fb_width, int fb_height)
 
 int crtc_set_scene(crtc_renderer *r, const crt_scene_t *scene)
 {
-    CRTC_TRY({
+    CRTC_TRY({ require_renderer(r);
         if (!scene) {
             throw std::runtime_error("crtc_set_scene: scene is NULL");
         }
@@ -1143,19 +1176,19 @@ int crtc_set_scene(crtc_renderer *r, const crt_scene_t *scene)
 int crtc_render(crtc_renderer *r, const float *pos, const float *dir, const float *up, float fovy, int camera_changed,
                 int readback_framebuffer, uint32_t *img, crt_render_stats_t *stats)
 {
-    CRTC_TRY({ r->render(pos, dir, up, fovy, camera_changed != 0, readback_framebuffer != 0, img, stats); })
+    CRTC_TRY({ require_renderer(r); r->render(pos, dir, up, fovy, camera_changed != 0, readback_framebuffer != 0, img, stats); })
 }
 
 int crtc_render_async(crtc_renderer *r, const float *pos, const float *dir, const float *up, float fovy,
                       int camera_changed, uint32_t num_frames)
 {
-    CRTC_TRY({ r->enqueue_frame(pos, dir, up, fovy, camera_changed != 0, num_frames); })
+    CRTC_TRY({ require_renderer(r); r->enqueue_frame(pos, dir, up, fovy, camera_changed != 0, num_frames); })
 }
 
 int crtc_sync(crtc_renderer *r, crt_render_stats_t *total, float *stage_ms_sum, uint64_t *counters_sum,
               uint32_t *num_frames)
 {
-    CRTC_TRY({
+    CRTC_TRY({ require_renderer(r);
         const uint32_t n = r->sync_frames(total, stage_ms_sum, counters_sum);
         if (num_frames) {
             *num_frames = n;
@@ -1165,7 +1198,7 @@ int crtc_sync(crtc_renderer *r, crt_render_stats_t *total, float *stage_ms_sum, 
 
 int crtc_read_accum(crtc_renderer *r, float *rgb_out)
 {
-    CRTC_TRY({
+    CRTC_TRY({ require_renderer(r);
         r->make_current();
         CUDA_CHECK(cudaMemcpyAsync(rgb_out, r->d_accum_full.ptr, (size_t)r->fb_w * r->fb_h * 3 * sizeof(float),
                                    cudaMemcpyDeviceToHost, r->stream));
@@ -1175,7 +1208,7 @@ int crtc_read_accum(crtc_renderer *r, float *rgb_out)
 
 int crtc_read_img(crtc_renderer *r, uint32_t *img)
 {
-    CRTC_TRY({
+    CRTC_TRY({ require_renderer(r);
         r->make_current();
         CUDA_CHECK(cudaMemcpyAsync(img, r->d_img_full.ptr, (size_t)r->fb_w * r->fb_h * 4, cudaMemcpyDeviceToHost,
                                    r->stream));
@@ -1185,6 +1218,9 @@ int crtc_read_img(crtc_renderer *r, uint32_t *img)
 
 int crtc_get_stage_times(crtc_renderer *r, float *ms_out, int n)
 {
+    if (!r || !ms_out || n <= 0) {
+        return 0;
+    }
     const int m = std::min(n, (int)kNumStages);
     for (int i = 0; i < m; ++i) {
         ms_out[i] = r->stage_ms[i];
@@ -1194,6 +1230,9 @@ int crtc_get_stage_times(crtc_renderer *r, float *ms_out, int n)
 
 int crtc_get_counters(crtc_renderer *r, uint64_t *out, int n)
 {
+    if (!r || !out || n <= 0) {
+        return 0;
+    }
     const int m = std::min(n, 8);
     for (int i = 0; i < m; ++i) {
         out[i] = r->counters_out[i];
@@ -1203,6 +1242,9 @@ int crtc_get_counters(crtc_renderer *r, uint64_t *out, int n)
 
 int crtc_get_scene_info(crtc_renderer *r, double *out, int n)
 {
+    if (!r || !out || n <= 0) {
+        return 0;
+    }
     const int m = std::min(n, 12);
     for (int i = 0; i < m; ++i) {
         out[i] = r->scene_info[i];
@@ -1212,22 +1254,22 @@ int crtc_get_scene_info(crtc_renderer *r, double *out, int n)
 
 int crtc_trace_closest(crtc_renderer *r, const float *rays, uint64_t n, float *hits)
 {
-    CRTC_TRY({ r->trace_closest(rays, n, hits); })
+    CRTC_TRY({ require_renderer(r); r->trace_closest(rays, n, hits); })
 }
 
 int crtc_trace_any(crtc_renderer *r, const float *rays, uint64_t n, uint8_t *occluded)
 {
-    CRTC_TRY({ r->trace_any(rays, n, occluded); })
+    CRTC_TRY({ require_renderer(r); r->trace_any(rays, n, occluded); })
 }
 
 int crtc_bench_trace(crtc_renderer *r, const float *rays_host, uint64_t n, int any_hit, int iters, float *ms_out)
 {
-    CRTC_TRY({ *ms_out = r->bench_trace(rays_host, n, any_hit != 0, iters); })
+    CRTC_TRY({ require_renderer(r); *ms_out = r->bench_trace(rays_host, n, any_hit != 0, iters); })
 }
 
 int crtc_local_buffers(crtc_renderer *r, void **accum_dev, void **img_dev, uint32_t *num_local_tiles)
 {
-    CRTC_TRY({
+    CRTC_TRY({ require_renderer(r);
         *accum_dev = r->d_accum_local.ptr;
         *img_dev = r->d_img_local.ptr;
         *num_local_tiles = (uint32_t)r->local_tiles.size();
@@ -1236,12 +1278,12 @@ int crtc_local_buffers(crtc_renderer *r, void **accum_dev, void **img_dev, uint3
 
 int crtc_assemble_rank(crtc_renderer *r, int src_rank, int world_size, const void *accum_dev, const void *img_dev)
 {
-    CRTC_TRY({ r->assemble_rank(src_rank, world_size, accum_dev, img_dev); })
+    CRTC_TRY({ require_renderer(r); r->assemble_rank(src_rank, world_size, accum_dev, img_dev); })
 }
 
 int crtc_export_frame(crtc_renderer *r, void *handles_out)
 {
-    CRTC_TRY({
+    CRTC_TRY({ require_renderer(r);
         if (!handles_out) {
             throw std::runtime_error("crtc_export_frame: null output");
         }
@@ -1251,7 +1293,7 @@ int crtc_export_frame(crtc_renderer *r, void *handles_out)
 
 int crtc_import_frame(crtc_renderer *r, const void *handles)
 {
-    CRTC_TRY({ r->import_frame(handles); })
+    CRTC_TRY({ require_renderer(r); r->import_frame(handles); })
 }
 
 int crtc_share_frame(crtc_renderer *dst, crtc_renderer *src)

@@ -30,6 +30,7 @@ constexpr uint32_t kMiss = 0xffffffffu;
 constexpr int kTile = 64;                 // render_embree.h:25
 constexpr uint32_t kTilePixels = kTile * kTile;
 constexpr int kMaxDepthSupported = 16;
+constexpr uint32_t kMaxTriangles = 1u << 27;  // k_traverse's pooled pairs: owner lane << 27 | leaf-order triangle index
 // counters layout (uint32): [0..16] queue length entering bounce b; [17..33] shadow rays
 // emitted at bounce b; [34] paths started
 constexpr int kCntQueue = 0;

@@ -17,6 +17,35 @@
 
 namespace crt_host {
 
+// The device builder itself gave up on this input (as opposed to a scene error or a CUDA error): set_scene catches it
+// and builds on the host instead.
+struct DeviceBuildFailure : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// cudaEvents that are destroyed on every exit path, exceptions included
+struct EventSet {
+    std::vector<cudaEvent_t> ev;
+    explicit EventSet(size_t n)
+    {
+        ev.reserve(n);
+        for (size_t i = 0; i < n; ++i) {
+            cudaEvent_t e;
+            CUDA_CHECK(cudaEventCreate(&e));
+            ev.push_back(e);
+        }
+    }
+    ~EventSet()
+    {
+        for (cudaEvent_t e : ev) {
+            cudaEventDestroy(e);
+        }
+    }
+    EventSet(const EventSet &) = delete;
+    EventSet &operator=(const EventSet &) = delete;
+    cudaEvent_t operator[](size_t i) const { return ev[i]; }
+};
+
 inline void check_bvh_depth(uint32_t depth)
 {
     if (depth + 2 > CRT_STACK_SIZE) {
@@ -183,12 +212,8 @@ struct DeviceSceneBuild {
         auto grid_for = [&](uint32_t items) {
             return std::max(1u, std::min((items + crt::kBuildBlock - 1) / crt::kBuildBlock, (uint32_t)sms * 8u));
         };
-        cudaEvent_t ev0, ev1, ev_sorted, ev_tree, ev_emitted;
-        CUDA_CHECK(cudaEventCreate(&ev0));
-        CUDA_CHECK(cudaEventCreate(&ev1));
-        CUDA_CHECK(cudaEventCreate(&ev_sorted));
-        CUDA_CHECK(cudaEventCreate(&ev_tree));
-        CUDA_CHECK(cudaEventCreate(&ev_emitted));
+        const EventSet events(5);
+        const cudaEvent_t ev0 = events[0], ev1 = events[1], ev_sorted = events[2], ev_tree = events[3], ev_emitted = events[4];
         const uint32_t num_b2 = 2 * n - 1, max_nodes = std::max(1u, n - 1);
         DeviceArena arena;
         ArenaBuf<float4> tri_lo(arena), tri_hi(arena), box_lo(arena), box_hi(arena), nodes_tmp(arena);
@@ -313,7 +338,7 @@ struct DeviceSceneBuild {
                 const crt::u64 total = h_tail[0] + h_tail[1];
                 const uint32_t merged = (uint32_t)total, left = (uint32_t)(total >> 32);
                 if (merged == 0 || left + merged != m) {
-                    throw std::runtime_error("device BVH build: a PLOC round made no progress");
+                    throw DeviceBuildFailure("device BVH build: a PLOC round made no progress");
                 }
                 nodes_made += merged;
                 m = left;
@@ -322,7 +347,7 @@ struct DeviceSceneBuild {
             }
             if (n > 1) {
                 if (nodes_made != n - 1) {
-                    throw std::runtime_error("device BVH build: PLOC made " + std::to_string(nodes_made) + " of " +
+                    throw DeviceBuildFailure("device BVH build: PLOC made " + std::to_string(nodes_made) + " of " +
                                              std::to_string(n - 1) + " nodes");
                 }
                 root = n + (n - 2);
@@ -338,7 +363,7 @@ struct DeviceSceneBuild {
         while (count) {
             ++depth;
             if ((size_t)node_begin + count > max_nodes) {
-                throw std::runtime_error("device BVH build: node count exceeds its bound");
+                throw DeviceBuildFailure("device BVH build: node count exceeds its bound");
             }
             crt::LevelArgs lv;
             lv.work = work;
@@ -365,10 +390,12 @@ struct DeviceSceneBuild {
             std::swap(work, next_work);
         }
         if (tri_total != n) {
-            throw std::runtime_error("device BVH build: emitted " + std::to_string(tri_total) + " of " + std::to_string(n) +
+            throw DeviceBuildFailure("device BVH build: emitted " + std::to_string(tri_total) + " of " + std::to_string(n) +
                                      " triangles");
         }
-        check_bvh_depth(depth);
+        if (depth + 2 > CRT_STACK_SIZE) {
+            throw DeviceBuildFailure("device BVH build: BVH8 depth " + std::to_string(depth) + " exceeds the traversal stack");
+        }
         CUDA_CHECK(cudaEventRecord(ev_emitted, stream));
         num_nodes = node_begin;
         d_nodes->alloc((size_t)num_nodes * 5);
@@ -393,9 +420,6 @@ struct DeviceSceneBuild {
         phase_ms[3] = t;
         CUDA_CHECK(cudaEventElapsedTime(&t, ev_emitted, ev1));
         phase_ms[4] = t;
-        for (cudaEvent_t e : {ev0, ev1, ev_sorted, ev_tree, ev_emitted}) {
-            cudaEventDestroy(e);
-        }
         leaf_flat_ids->resize(n);
         for (uint32_t i = 0; i < n; ++i) {
             if (order[i] >= n) {

@@ -52,10 +52,18 @@ class FrameGatherer:
         import torch
         import torch.distributed as dist
 
+        # `dst` is a rank of `group` (like self.rank); dist.gather wants the global rank
         self.r, self.group, self.dst = renderer, group, dst
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.dst_global = dist.get_global_rank(group, dst) if group is not None else dst
         self.dev = torch.device("cuda", renderer.device)
+        # The staging copies and k_assemble are ordered against the frame only if they run on the renderer's stream:
+        # make the current torch stream the renderer's (a default-constructed RenderCUDA owns a non-blocking stream
+        # that the current torch stream would otherwise race)
+        # (no CUDA runtime = the CPU dry run of tests/test_bench_contract.py over the emulated renderer)
+        if torch.cuda.is_available():
+            renderer.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
         accum_ptr, img_ptr, nloc = renderer.local_buffers()
         self.nloc = nloc
         max_tiles = tiles.max_local_tiles(renderer.width, renderer.height, self.world)
@@ -77,8 +85,8 @@ class FrameGatherer:
         if self.nloc:
             self.send_a[: self.src_a.numel()].copy_(self.src_a)
             self.send_i[: self.src_i.numel()].copy_(self.src_i)
-        self.work = [dist.gather(self.send_a, self.recv_a, dst=self.dst, group=self.group, async_op=True),
-                     dist.gather(self.send_i, self.recv_i, dst=self.dst, group=self.group, async_op=True)]
+        self.work = [dist.gather(self.send_a, self.recv_a, dst=self.dst_global, group=self.group, async_op=True),
+                     dist.gather(self.send_i, self.recv_i, dst=self.dst_global, group=self.group, async_op=True)]
 
     def finish(self) -> bool:
         """Returns True on ``dst`` when a frame was assembled."""

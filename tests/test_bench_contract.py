@@ -78,6 +78,7 @@ torch.cuda.is_available = lambda: True
 torch.cuda.set_device = lambda d: None
 torch.cuda.Stream = _Stream
 torch.cuda.set_stream = lambda s: None
+torch.cuda.current_stream = lambda d=None: _Stream()
 torch.cuda.Event = _Event
 torch.cuda.synchronize = lambda d=None: None
 import chameleonrt_b200.backend as backend
@@ -140,6 +141,7 @@ torch.cuda.is_available = lambda: True
 torch.cuda.set_device = lambda d: None
 torch.cuda.Stream = _Stream
 torch.cuda.set_stream = lambda s: None
+torch.cuda.current_stream = lambda d=None: _Stream()
 torch.cuda.Event = _Event
 torch.cuda.synchronize = lambda d=None: None
 _real_device = torch.device
