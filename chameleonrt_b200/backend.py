@@ -112,6 +112,10 @@ class RenderCUDA:
                          ("CRT_CUDA_SHADE_SORT", "shade_sort")):
             if os.environ.get(env):
                 self._check(self.lib.crtc_set_option(self.h, key.encode(), int(os.environ[env])))
+        # CRT_CUDA_OPTIONS="key=value,key=value": any crtc_set_option key (experiments, profiling runs)
+        for kv in filter(None, os.environ.get("CRT_CUDA_OPTIONS", "").split(",")):
+            key, val = kv.split("=")
+            self._check(self.lib.crtc_set_option(self.h, key.strip().encode(), int(val)))
         if tri_pass_defer is not None:  # 0 / 16 / 24: experimental scheduling variant of k_traverse; never changes a result
             self._check(self.lib.crtc_set_option(self.h, b"tri_pass_defer", int(tri_pass_defer)))
         if shade_sort is not None:  # 0 / 1 / 2: shade queue bucketed by material id before k_shade; never changes a result
