@@ -144,6 +144,17 @@ static inline T __shfl_down_sync(unsigned, T v, int delta)
 {
     return simt::exchange(v, simt::lane + delta > 31 ? -1 : simt::lane + delta);
 }
+static inline unsigned __reduce_add_sync(unsigned, unsigned v)
+{
+    simt::warp->slots[simt::lane] = v;
+    simt::warp->sync();
+    unsigned sum = 0;
+    for (int l = 0; l < 32; ++l) {
+        sum += (unsigned)simt::warp->slots[l];
+    }
+    simt::warp->sync();
+    return sum;
+}
 static inline void __syncwarp() { simt::warp->sync(); }
 static inline void __syncthreads() { simt::block_barrier->wait(); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }

@@ -65,6 +65,7 @@ static inline T __shfl_down_sync(unsigned, T, int)
     return T(0);  // lanes 1..31 do not exist: they contribute nothing to a reduction
 }
 static inline void __syncwarp() {}
+static inline unsigned __reduce_add_sync(unsigned, unsigned v) { return v; }
 // (declarations for the block-level kernels of kernels.cuh, which are templates and never instantiated in this build)
 static inline void __syncthreads() {}
 template <typename T>
