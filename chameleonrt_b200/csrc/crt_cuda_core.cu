@@ -89,8 +89,6 @@ struct crtc_renderer {
     bool count_traversal = false;
     int refill_idle = crt::kRefillIdle;  // idle lanes that trigger a refill of the traversal warps
     int tri_pass_defer = 0;              // 0 (default) / 16 / 24: pooled pairs a triangle pass waits for (kernels.cuh)
-    int trav_kernel = 0;                 // 0 = k_traverse (a triangle pass after every node phase), 1 = k_traverse_pool (pairs queued per warp)
-    int flush_wait = 0;                  // k_traverse_pool: waiting lanes that force a partial pass (0 = kernel default)
     // The shade queue bucketed by material id before k_shade (k_queue_hist / k_queue_scatter): 0 = off (default),
     // 1 = from the first bounce on (primary hits keep their screen order), 2 = every shade launch. Same image.
     int shade_sort = 0;
@@ -273,16 +271,7 @@ struct crtc_renderer {
             CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, crt::k_traverse<false>, crt::kTravBlock, 0));
             trav_grid = (unsigned)(sms * std::max(1, per_sm));
         }
-        int sched = (refill_idle & 0xff) | (frame_far_first ? 0x100 : 0);
-        if (trav_kernel == 1) {  // the pooled kernel (kernels.cuh: k_traverse_pool)
-            sched |= (flush_wait & 0xff) << 16;
-            if (count_traversal) {
-                crt::k_traverse_pool<true><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any, work_counter, sched);
-            } else {
-                crt::k_traverse_pool<false><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any, work_counter, sched);
-            }
-            return;
-        }
+        const int sched = (refill_idle & 0xff) | (frame_far_first ? 0x100 : 0);
         // (one instantiation per variant, so that the default kernel's code does not change with the options)
         const int variant = (count_traversal ? 1 : 0) | (tri_pass_defer == 16 ? 2 : (tri_pass_defer == 24 ? 4 : 0));
         switch (variant) {
@@ -1084,16 +1073,6 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
                 throw std::runtime_error("tri_pass_defer must be 0, 16 or 24");
             }
             r->tri_pass_defer = (int)value;
-        } else if (k == "trav_kernel") {
-            if (value < 0 || value > 1) {
-                throw std::runtime_error("trav_kernel must be 0 or 1");
-            }
-            r->trav_kernel = (int)value;
-        } else if (k == "flush_wait") {
-            if (value < 0 || value > 32) {
-                throw std::runtime_error("flush_wait must be in [0, 32]");
-            }
-            r->flush_wait = (int)value;
         } else if (k == "shade_sort") {
             if (value < 0 || value > 2) {
                 throw std::runtime_error("shade_sort must be 0, 1 or 2");
@@ -1146,10 +1125,6 @@ int crtc_get_option(crtc_renderer *r, const char *key, int64_t *value)
             *value = r->bvh_threads;
         } else if (k == "tri_pass_defer") {
             *value = r->tri_pass_defer;
-        } else if (k == "trav_kernel") {
-            *value = r->trav_kernel;
-        } else if (k == "flush_wait") {
-            *value = r->flush_wait;
         } else if (k == "shade_sort") {
             *value = r->shade_sort;
         } else if (k == "bvh_builder") {

@@ -167,32 +167,6 @@ constexpr int kSmemStack = 8;
 constexpr int kRefillIdle = 4;
 constexpr uint32_t kFetchBatch = 64;
 
-struct HybridStack {
-    uint2 *sm;  // this thread's column of the block's shared stack: sm[i * kTravBlock]
-    uint2 local[CRT_STACK_SIZE - kSmemStack];
-    int sp;
-    __device__ __forceinline__ void push(const uint2 v)
-    {
-        if (sp < kSmemStack) {
-            sm[sp * kTravBlock] = v;
-        } else {
-            local[sp - kSmemStack] = v;
-        }
-        ++sp;
-    }
-    __device__ __forceinline__ uint2 pop()
-    {
-        --sp;
-        return sp < kSmemStack ? sm[sp * kTravBlock] : local[sp - kSmemStack];
-    }
-    __device__ __forceinline__ uint2 peek() const
-    {
-        return sp - 1 < kSmemStack ? sm[(sp - 1) * kTravBlock] : local[sp - 1 - kSmemStack];
-    }
-    __device__ __forceinline__ void drop() { --sp; }
-    __device__ __forceinline__ bool empty() const { return sp == 0; }
-};
-
 // One launch serves both ray kinds so that the shadow rays of bounce b and the continuation rays
 // of bounce b+1 (both known once k_shade(b) has run) share a launch: half as many traversal
 // launches per frame and twice the rays per launch, which matters when a GPU only holds 1/8 of the
@@ -218,7 +192,8 @@ __global__ void __launch_bounds__(kTravBlock, 8)
     __shared__ unsigned long long sm_key[kTravBlock / 32][32];  // bits(t) << 32 | flat id  (atomicMin)
     __shared__ float sm_hit_u[kTravBlock / 32][32], sm_hit_v[kTravBlock / 32][32];
     __shared__ uint32_t sm_hit_tri[kTravBlock / 32][32];
-    __shared__ uint32_t sm_slot[kTravBlock / 32][32];           // owner lane << 27 | triangle index
+    __shared__ uint32_t sm_owner[kTravBlock / 32][32];          // owner lane of the group that starts at slot s
+    __shared__ uint32_t sm_cursor[kTravBlock / 32];             // running slot cursor of the warp (never reset)
     __shared__ uint32_t sm_is_any[kTravBlock / 32][32];         // ray kind per lane (instrumented build only)
     const int warp = threadIdx.x >> 5;
     const uint32_t n_any = count_any_ptr ? *count_any_ptr : 0u;
@@ -226,9 +201,12 @@ __global__ void __launch_bounds__(kTravBlock, 8)
     const int lane = threadIdx.x & 31;
     const unsigned lanemask_lt = (1u << lane) - 1u;
     const uint32_t batch = count > 8u * gridDim.x * kTravBlock ? kFetchBatch : 32u;
-    HybridStack stack;
-    stack.sm = sm_stack + threadIdx.x;
-    stack.sp = 0;
+    // traversal stack: entries [0, kSmemStack) in this thread's column of shared memory, deeper ones (rare) in local
+    // memory. The depth and the column pointer are plain locals: as members of one struct with the spill array they
+    // lived in local memory too (the round-2 SASS had an LDL / STL pair around every push).
+    uint2 *const stack_sm = sm_stack + threadIdx.x;
+    uint2 stack_spill[CRT_STACK_SIZE - kSmemStack];
+    int sp = 0;
     TravState st;
     uint2 tri = make_uint2(0u, 0u);  // triangle group yielded by this lane's last node step
     TraversalCounters cnt, cnt_any;
@@ -237,6 +215,11 @@ __global__ void __launch_bounds__(kTravBlock, 8)
     uint32_t out_index = 0;
     uint32_t batch_next = 0, batch_end = 0;  // warp-uniform
     bool drained = false;                    // warp-uniform: the queue has no more rays
+    uint32_t cursor_base = 0;                // warp-uniform: value of sm_cursor[warp] before the current pass
+    if (lane == 0) {
+        sm_cursor[warp] = 0u;
+    }
+    __syncwarp();
 
     for (;;) {
         // ---- refill idle lanes ----
@@ -274,7 +257,7 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                 if (is_any && any_far_first) {
                     trav_reverse_order(st);  // same answer, different order (bvh8_traverse.h)
                 }
-                stack.sp = 0;
+                sp = 0;
                 tri = make_uint2(0u, 0u);
                 alive = true;
                 {
@@ -319,7 +302,12 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                 if (can_step) {
                     const uint32_t node_index = next_child(st.cur, st.oct_inv4);
                     if (st.cur.y & 0xff000000u) {
-                        stack.push(st.cur);
+                        if (sp < kSmemStack) {
+                            stack_sm[sp * kTravBlock] = st.cur;
+                        } else {
+                            stack_spill[sp - kSmemStack] = st.cur;
+                        }
+                        ++sp;
                     }
                     if (COUNT) {
                         if (is_any) {
@@ -330,45 +318,67 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                     }
                     node_intersect(sc.nodes, st, node_index, st.cur, tri);
                 }
-                // triangle phase: pack pairs into slots, 32 at a time
+                // triangle phase: the pairs (owner lane, triangle) of this step, 32 per pass. Slots are PULLED by the
+                // testing lanes: an owner only claims a range of slots (one shared-memory atomicAdd on a running
+                // cursor: no scan over the lanes) and marks where it starts; slot lane p finds the last start at or
+                // before p, reads the owner's group by shuffle and picks its (p - start)-th triangle. (Round 1 had the
+                // owners write one slot per pair in a loop: 5 trips per pass at 3 active lanes, 12 % of the kernel's
+                // issued instructions with the scan that placed them — profiles/r2_experiments.md.)
                 for (;;) {
                     const uint32_t k = alive ? (uint32_t)__popc(tri.y) : 0u;
-                    uint32_t pre = k;  // inclusive prefix sum over lanes
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const uint32_t o = __shfl_up_sync(0xffffffffu, pre, off);
-                        if (lane >= off) {
-                            pre += o;
-                        }
-                    }
-                    const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
+                    const uint32_t total = __reduce_add_sync(0xffffffffu, k);
                     if (total == 0u) {
                         break;
                     }
                     if (DEFER > 0) {
                         // wait for a fuller pool while some lane without a pending group can still descend
-                        const bool free_lane = alive && tri.y == 0u && ((st.cur.y & 0xff000000u) || !stack.empty());
+                        const bool free_lane = alive && tri.y == 0u && ((st.cur.y & 0xff000000u) || sp > 0);
                         if (total < (uint32_t)DEFER && __ballot_sync(0xffffffffu, free_lane) != 0u) {
                             break;
                         }
                     }
-                    uint32_t pos = pre - k;
-                    while (tri.y && pos < 32u) {
-                        const int ti = msb(tri.y);
-                        tri.y &= ~(1u << ti);
-                        sm_slot[warp][pos++] = ((uint32_t)lane << 27) | (tri.x + (uint32_t)ti);
+                    uint32_t start = 32u;  // first slot of this lane's pairs (any order among the owners)
+                    if (k != 0u) {
+                        start = atomicAdd(&sm_cursor[warp], k) - cursor_base;
+                        if (start < 32u) {
+                            sm_owner[warp][start] = (uint32_t)lane;
+                        }
                     }
+                    cursor_base += total;
+                    const uint32_t starts = __reduce_or_sync(0xffffffffu, start < 32u ? 1u << start : 0u);
                     __syncwarp();
                     const uint32_t npairs = min(total, 32u);
                     CRT_PROF_TRI_PASS((uint32_t)lane < npairs);
+                    uint32_t owner = 0u, rank = 0u;
+                    if ((uint32_t)lane < npairs) {
+                        const uint32_t s0 = (uint32_t)msb(starts & (0xffffffffu >> (31 - lane)));  // slot 0 is always a start
+                        owner = sm_owner[warp][s0];
+                        rank = (uint32_t)lane - s0;
+                    }
+                    const uint32_t gx = __shfl_sync(0xffffffffu, tri.x, (int)owner);
+                    uint32_t gy = __shfl_sync(0xffffffffu, tri.y, (int)owner);
+                    // the owner's pairs that fit into this pass are consumed: its highest min(k, 32 - start) bits
+                    if (k != 0u) {
+                        const uint32_t fit = start < 32u ? min(k, 32u - start) : 0u;
+                        if (fit == k) {
+                            tri.y = 0u;
+                        } else {
+#pragma unroll 1
+                            for (uint32_t i = 0; i < fit; ++i) {
+                                tri.y ^= 1u << msb(tri.y);
+                            }
+                        }
+                    }
                     bool won = false;
                     unsigned long long cand = 0ull;
-                    uint32_t owner = 0u, tri_index = 0u;
+                    uint32_t tri_index = 0u;
                     float hu = 0.f, hv = 0.f;
                     if ((uint32_t)lane < npairs) {
-                        const uint32_t e = sm_slot[warp][lane];
-                        owner = e >> 27;
-                        tri_index = e & 0x07ffffffu;
+#pragma unroll 1
+                        for (uint32_t i = 0; i < rank; ++i) {
+                            gy ^= 1u << msb(gy);
+                        }
+                        tri_index = gx + (uint32_t)msb(gy);
                         if (COUNT) {  // attribute the test to the kind of the owner's ray
                             if (sm_is_any[warp][owner]) {
                                 cnt_any.tris++;
@@ -412,8 +422,9 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                         tri.y = 0u;  // an occluded shadow ray needs no further tests
                     }
                     if (!finished && (DEFER == 0 || tri.y == 0u) && (st.cur.y & 0xff000000u) == 0u) {
-                        if (!stack.empty()) {
-                            st.cur = stack.pop();
+                        if (sp > 0) {
+                            --sp;
+                            st.cur = sp < kSmemStack ? stack_sm[sp * kTravBlock] : stack_spill[sp - kSmemStack];
                         } else {
                             finished = true;
                         }
@@ -435,276 +446,6 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                 if (n_alive == 0 || (!drained && 32 - n_alive >= refill_idle)) {
                     break;
                 }
-            }
-        }
-    }
-    if (COUNT) {
-        unsigned long long n = cnt.nodes, t = cnt.tris, na = cnt_any.nodes, ta = cnt_any.tris;
-        for (int off = 16; off > 0; off >>= 1) {
-            n += __shfl_down_sync(0xffffffffu, n, off);
-            t += __shfl_down_sync(0xffffffffu, t, off);
-            na += __shfl_down_sync(0xffffffffu, na, off);
-            ta += __shfl_down_sync(0xffffffffu, ta, off);
-        }
-        if (lane == 0) {
-            atomicAdd(ps.trav_counters, n);
-            atomicAdd(ps.trav_counters + 1, t);
-            atomicAdd(ps.trav_counters + 2, na);
-            atomicAdd(ps.trav_counters + 3, ta);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// k_traverse_pool: the same traversal with the (owner lane, triangle) pairs QUEUED per warp instead of tested right
-// after the node step that produced them.
-//
-// Why (round-2 ncu capture of k_traverse, SASS-level attribution, profiles/r2_experiments.md): a triangle pass cost
-// ~245 warp instructions — inclusive scan over the lanes, a per-lane loop packing pairs into slots at 3 active lanes,
-// the test, the winners' bookkeeping — and ran after EVERY node phase with only ~14 of its 32 slots filled, so the
-// triangle side issued as many instructions as the 14-nodes-per-ray node side. Here every warp keeps a ring of
-// kPoolSize pairs in shared memory: lanes append the pairs of their last node step (position from one shared-memory
-// atomicAdd per lane, no scan) and go on descending; a pass runs when 32 pairs are queued (or when nothing else can make
-// progress), so passes are full and there are ~2.3x fewer of them. A ray is finished once its traversal is done AND
-// the queue head has moved past its last pair; a lane is refilled only then, so a queued pair always refers to the ray
-// its owner lane still holds. The price: tfar shrinks (and an occluded shadow ray stops) a few node steps later than
-// with immediate testing. Results are unchanged — the closest hit is the minimum over (t, primitive id) whatever the
-// order of the tests, an occlusion answer is a boolean.
-constexpr int kPoolSize = 128;  // pairs per warp (power of two); a lane appends at most kPushMax per iteration
-constexpr int kPushMax = 4;     // 32 lanes x 4 = kPoolSize: an append always fits into an empty ring
-constexpr int kFlushWaitDefault = 8;
-
-template <bool COUNT>
-__global__ void __launch_bounds__(kTravBlock, 8)
-    k_traverse_pool(DeviceScene sc, PathState ps, const uint32_t *queue, const uint32_t *count_closest_ptr,
-                    const uint32_t *count_any_ptr, uint32_t *work_counter, int sched)
-{
-    // sched: bits 0-7 = idle lanes that trigger a refill; bit 8 = shadow rays visit children far-first; bits 16-23 =
-    // lanes waiting for their queued pairs that trigger a (possibly partial) pass (0 = kFlushWaitDefault)
-    const int refill_idle = sched & 0xff;
-    const bool any_far_first = (sched & 0x100) != 0;
-    const int flush_wait = ((sched >> 16) & 0xff) ? ((sched >> 16) & 0xff) : kFlushWaitDefault;
-    __shared__ uint2 sm_stack[kSmemStack * kTravBlock];
-    __shared__ float sm_ray[kTravBlock / 32][8][32];            // ox oy oz tnear dx dy dz tfar0
-    __shared__ unsigned long long sm_key[kTravBlock / 32][32];  // bits(t) << 32 | flat id  (atomicMin)
-    __shared__ float sm_hit_u[kTravBlock / 32][32], sm_hit_v[kTravBlock / 32][32];
-    __shared__ uint32_t sm_hit_tri[kTravBlock / 32][32];
-    __shared__ uint32_t sm_pool[kTravBlock / 32][kPoolSize];    // owner lane << 27 | leaf-order triangle index
-    __shared__ uint32_t sm_tail[kTravBlock / 32];               // allocation cursor of the ring (monotonic)
-    __shared__ uint32_t sm_is_any[kTravBlock / 32][32];         // ray kind per lane (instrumented build only)
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const uint32_t n_any = count_any_ptr ? *count_any_ptr : 0u;
-    const uint32_t count = n_any + (count_closest_ptr ? *count_closest_ptr : 0u);
-    const unsigned lanemask_lt = (1u << lane) - 1u;
-    const uint32_t batch = count > 8u * gridDim.x * kTravBlock ? kFetchBatch : 32u;
-    uint2 *const stack_sm = sm_stack + threadIdx.x;  // this thread's column: entry i at stack_sm[i * kTravBlock]
-    uint2 stack_spill[CRT_STACK_SIZE - kSmemStack];  // deeper entries (rare): local memory
-    int sp = 0;
-    TravState st;
-    uint2 tri = make_uint2(0u, 0u);  // triangle group of this lane's last node step not yet queued
-    TraversalCounters cnt, cnt_any;
-    bool alive = false;     // the lane holds a ray whose result has not been written
-    bool stepping = false;  // ... and that ray still has nodes to visit
-    bool is_any = false;
-    uint32_t out_index = 0;
-    uint32_t pend_end = 0;                 // ring position just past this lane's last queued pair
-    uint32_t head = 0, tail = 0;           // warp-uniform copies; pairs [head, tail) are queued
-    uint32_t batch_next = 0, batch_end = 0;
-    bool drained = false;
-    if (lane == 0) {
-        sm_tail[warp] = 0u;
-    }
-    __syncwarp();
-
-    for (;;) {
-        // ---- refill idle lanes ----
-        unsigned need = __ballot_sync(0xffffffffu, !alive);
-        while (need && !drained) {
-            if (batch_next == batch_end) {
-                uint32_t b = 0;
-                if (lane == 0) {
-                    b = atomicAdd(work_counter, batch);
-                }
-                b = __shfl_sync(0xffffffffu, b, 0);
-                if (b >= count) {
-                    drained = true;
-                    break;
-                }
-                batch_next = b;
-                batch_end = min(b + batch, count);
-            }
-            const uint32_t avail = batch_end - batch_next;
-            const uint32_t r = (uint32_t)__popc(need & lanemask_lt);
-            if (((need >> lane) & 1u) && r < avail) {
-                const uint32_t j = batch_next + r;
-                Ray ray;
-                is_any = j < n_any;
-                if (is_any) {
-                    const float4 o = ps.sray_o[j], d = ps.sray_d[j];
-                    ray = Ray{o.x, o.y, o.z, kEpsilon, d.x, d.y, d.z, o.w};
-                    out_index = __float_as_uint(d.w);
-                } else {
-                    out_index = queue ? queue[j - n_any] : j - n_any;
-                    const float4 o = ps.ray_o[out_index], d = ps.ray_d[out_index];
-                    ray = Ray{o.x, o.y, o.z, o.w, d.x, d.y, d.z, d.w};
-                }
-                trav_init(st, ray, sc.float_one);
-                if (is_any && any_far_first) {
-                    trav_reverse_order(st);
-                }
-                sp = 0;
-                tri = make_uint2(0u, 0u);
-                alive = true;
-                stepping = true;
-                pend_end = head;
-                sm_ray[warp][0][lane] = ray.ox;
-                sm_ray[warp][1][lane] = ray.oy;
-                sm_ray[warp][2][lane] = ray.oz;
-                sm_ray[warp][3][lane] = ray.tnear;
-                sm_ray[warp][4][lane] = ray.dx;
-                sm_ray[warp][5][lane] = ray.dy;
-                sm_ray[warp][6][lane] = ray.dz;
-                sm_ray[warp][7][lane] = ray.tfar;
-                sm_key[warp][lane] = ((unsigned long long)__float_as_uint(ray.tfar) << 32) | 0xffffffffull;
-                sm_hit_tri[warp][lane] = kMiss;
-                if (COUNT) {
-                    sm_is_any[warp][lane] = is_any ? 1u : 0u;
-                }
-            }
-            batch_next += min((uint32_t)__popc(need), avail);
-            need = __ballot_sync(0xffffffffu, !alive);
-        }
-        unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
-        if (alive_mask == 0u) {
-            break;
-        }
-        __syncwarp();
-        for (;;) {
-            // ---- node phase: every lane that can descends one node ----
-            const bool can_step = stepping && (st.cur.y & 0xff000000u) && tri.y == 0u;
-            CRT_PROF_NODE_PHASE(can_step);
-            if (can_step) {
-                const uint32_t node_index = next_child(st.cur, st.oct_inv4);
-                if (st.cur.y & 0xff000000u) {
-                    if (sp < kSmemStack) {
-                        stack_sm[sp * kTravBlock] = st.cur;
-                    } else {
-                        stack_spill[sp - kSmemStack] = st.cur;
-                    }
-                    ++sp;
-                }
-                if (COUNT) {
-                    if (is_any) {
-                        cnt_any.nodes++;
-                    } else {
-                        cnt.nodes++;
-                    }
-                }
-                node_intersect(sc.nodes, st, node_index, st.cur, tri);
-            }
-            // ---- append this step's pairs to the warp's ring (at most kPushMax per lane and iteration) ----
-            const uint32_t k = stepping ? min((uint32_t)__popc(tri.y), (uint32_t)kPushMax) : 0u;
-            const uint32_t total = __reduce_add_sync(0xffffffffu, k);
-            bool no_room = false;
-            if (total != 0u) {
-                no_room = tail - head + total > (uint32_t)kPoolSize;
-                if (!no_room) {
-                    if (k != 0u) {
-                        uint32_t pos = atomicAdd(&sm_tail[warp], k);
-                        pend_end = pos + k;
-                        const uint32_t base = ((uint32_t)lane << 27) | tri.x;
-                        for (uint32_t i = 0; i < k; ++i) {
-                            const int ti = msb(tri.y);
-                            tri.y ^= 1u << ti;
-                            sm_pool[warp][pos & (uint32_t)(kPoolSize - 1)] = base + (uint32_t)ti;
-                            ++pos;
-                        }
-                    }
-                    tail += total;
-                }
-            }
-            // ---- next node group ----
-            if (stepping && tri.y == 0u && (st.cur.y & 0xff000000u) == 0u) {
-                if (sp > 0) {
-                    --sp;
-                    st.cur = sp < kSmemStack ? stack_sm[sp * kTravBlock] : stack_spill[sp - kSmemStack];
-                } else {
-                    stepping = false;
-                }
-            }
-            // ---- a triangle pass when 32 pairs are queued, or when that is the only way forward ----
-            const unsigned step_mask = __ballot_sync(0xffffffffu, stepping);
-            const uint32_t queued = tail - head;
-            if (queued >= 32u ||
-                (queued != 0u && (no_room || step_mask == 0u || __popc(alive_mask & ~step_mask) >= flush_wait))) {
-                __syncwarp();  // the ring entries written above are visible to every lane
-                const uint32_t npairs = min(queued, 32u);
-                CRT_PROF_TRI_PASS((uint32_t)lane < npairs);
-                bool won = false;
-                unsigned long long cand = 0ull;
-                uint32_t owner = 0u, tri_index = 0u;
-                float hu = 0.f, hv = 0.f;
-                if ((uint32_t)lane < npairs) {
-                    const uint32_t e = sm_pool[warp][(head + (uint32_t)lane) & (uint32_t)(kPoolSize - 1)];
-                    owner = e >> 27;
-                    tri_index = e & 0x07ffffffu;
-                    if (COUNT) {
-                        if (sm_is_any[warp][owner]) {
-                            cnt_any.tris++;
-                        } else {
-                            cnt.tris++;
-                        }
-                    }
-                    Ray r;
-                    r.ox = sm_ray[warp][0][owner];
-                    r.oy = sm_ray[warp][1][owner];
-                    r.oz = sm_ray[warp][2][owner];
-                    r.tnear = sm_ray[warp][3][owner];
-                    r.dx = sm_ray[warp][4][owner];
-                    r.dy = sm_ray[warp][5][owner];
-                    r.dz = sm_ray[warp][6][owner];
-                    r.tfar = sm_ray[warp][7][owner];
-                    const float4 *tp = sc.tris + (size_t)tri_index * 3;
-                    const float4 t0 = tp[0], t1 = tp[1], t2 = tp[2];
-                    float t;
-                    if (tri_test(r, r.tfar, t0, t1, t2, t, hu, hv)) {
-                        cand = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)__float_as_uint(t0.w);
-                        won = atomicMin(&sm_key[warp][owner], cand) > cand;
-                    }
-                }
-                __syncwarp();
-                if (won && sm_key[warp][owner] == cand) {  // the pair that holds the minimum records u, v
-                    sm_hit_u[warp][owner] = hu;
-                    sm_hit_v[warp][owner] = hv;
-                    sm_hit_tri[warp][owner] = tri_index;
-                }
-                __syncwarp();
-                head += npairs;
-                if (alive) {
-                    st.tfar = __uint_as_float((uint32_t)(sm_key[warp][lane] >> 32));
-                    if (is_any && sm_hit_tri[warp][lane] != kMiss) {
-                        stepping = false;  // occluded: nothing more to visit (pairs still queued are tested in vain)
-                        tri.y = 0u;
-                    }
-                }
-            }
-            // ---- finish: traversal done and every queued pair of this ray tested ----
-            if (alive && !stepping && (int32_t)(pend_end - head) <= 0) {
-                const uint32_t htri = sm_hit_tri[warp][lane];
-                if (is_any) {
-                    ps.vis[out_index] = htri != kMiss ? 0 : 1;
-                } else {
-                    ps.hit[out_index] = make_float4(__uint_as_float((uint32_t)(sm_key[warp][lane] >> 32)),
-                                                    htri != kMiss ? sm_hit_u[warp][lane] : 0.f,
-                                                    htri != kMiss ? sm_hit_v[warp][lane] : 0.f, __uint_as_float(htri));
-                }
-                alive = false;
-            }
-            alive_mask = __ballot_sync(0xffffffffu, alive);
-            const int n_alive = __popc(alive_mask);
-            if (n_alive == 0 || (!drained && 32 - n_alive >= refill_idle)) {
-                break;
             }
         }
     }

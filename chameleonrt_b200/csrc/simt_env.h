@@ -155,6 +155,17 @@ static inline unsigned __reduce_add_sync(unsigned, unsigned v)
     simt::warp->sync();
     return sum;
 }
+static inline unsigned __reduce_or_sync(unsigned, unsigned v)
+{
+    simt::warp->slots[simt::lane] = v;
+    simt::warp->sync();
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l) {
+        r |= (unsigned)simt::warp->slots[l];
+    }
+    simt::warp->sync();
+    return r;
+}
 static inline void __syncwarp() { simt::warp->sync(); }
 static inline void __syncthreads() { simt::block_barrier->wait(); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }

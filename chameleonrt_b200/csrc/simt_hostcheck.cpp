@@ -144,10 +144,6 @@ void crt_simt_traverse(void *p, const float *closest, uint32_t n_closest, const 
                 simt::warp = &warps[t / 32];
                 simt::lane = t % 32;
                 const uint32_t *any_count = n_any ? counters.data() + crt::kCntShadow : nullptr;
-                if ((sched >> 24) & 1) {  // test-only selector: the pooled kernel (option "trav_kernel" = 1); bits 16-23 = flush_wait
-                    crt::k_traverse_pool<false>(sc, ps, ps.queue[0], counters.data() + crt::kCntQueue, any_count, work_counter, sched & 0xffffff);
-                    return;
-                }
                 switch ((sched >> 16) & 0xff) {  // test-only selector of the instantiation (option "tri_pass_defer")
                 case 16:
                     crt::k_traverse<false, 16>(sc, ps, ps.queue[0], counters.data() + crt::kCntQueue, any_count, work_counter, sched & 0xffff);

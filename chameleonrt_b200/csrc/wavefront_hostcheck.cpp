@@ -66,6 +66,7 @@ static inline T __shfl_down_sync(unsigned, T, int)
 }
 static inline void __syncwarp() {}
 static inline unsigned __reduce_add_sync(unsigned, unsigned v) { return v; }
+static inline unsigned __reduce_or_sync(unsigned, unsigned v) { return v; }
 // (declarations for the block-level kernels of kernels.cuh, which are templates and never instantiated in this build)
 static inline void __syncthreads() {}
 template <typename T>

@@ -86,10 +86,6 @@ def main():
     run(b1, sh0, 4 | (24 << 16), "triangle pass deferred until 24 pairs are pooled")
     run(b1, sh0, 4 | 0x100 | (16 << 16), "deferred (16) + shadow rays far-first")
     run(b1, sh0, 1 | 0x100 | (16 << 16), "deferred (16) + far-first + refill at 1 idle lane")
-    POOL = 1 << 24  # k_traverse_pool (bits 16-23: waiting lanes that force a partial pass)
-    for fw in (0, 2, 4, 16, 32):
-        run(b1, sh0, POOL | 4 | 0x100 | (fw << 16), f"pooled kernel, far-first, flush_wait {fw or 'default (8)'}")
-    run(b1, sh0, POOL | 8 | 0x100, "pooled kernel, far-first, refill at 8")
     run(np.ascontiguousarray(b1[sort_key(b1)]), np.ascontiguousarray(sh0[sort_key(sh0)]), 4, "rays sorted by octant, then position")
     run(np.ascontiguousarray(b1[sort_key(b1)]), np.ascontiguousarray(sh0[sort_key(sh0)]), 4 | 0x100, "sorted + shadow rays far-first")
     print("the same rays as two launches (shadow rays alone, continuation rays alone):")

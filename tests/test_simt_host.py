@@ -69,11 +69,7 @@ def test_k_traverse_under_simt_emulation_equals_single_ray_traversal(lib, name):
     occluded = hc.trace(shadow, any_hit=True)[0][:, 3].view(np.uint32) != 0xFFFFFFFF
     # default scheduling, far-first shadow rays, refill as soon as one lane idles, refill only when the warp is empty,
     # and the deferred-triangle-pass instantiations (option tri_pass_defer = 16 / 24), alone and with far-first / refill 1
-    # ... and the pooled kernel k_traverse_pool (bit 24; bits 16-23 = waiting lanes that force a partial pass): default,
-    # far-first, refill at 1 / 32 idle lanes, a pass forced by one waiting lane / only when nothing else can move
-    POOL = 1 << 24
-    for sched in (4, 4 | 0x100, 1, 32, 4 | (16 << 16), 4 | (24 << 16), 1 | 0x100 | (16 << 16), 32 | (24 << 16),
-                  POOL | 4, POOL | 4 | 0x100, POOL | 1, POOL | 32, POOL | 4 | (1 << 16), POOL | 8 | (32 << 16), POOL | 1 | 0x100 | (2 << 16)):
+    for sched in (4, 4 | 0x100, 1, 32, 4 | (16 << 16), 4 | (24 << 16), 1 | 0x100 | (16 << 16), 32 | (24 << 16)):
         got, vis = _run(lib, h, closest, shadow, sched)
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), hex(sched)
         assert np.array_equal(vis == 0, occluded) and set(np.unique(vis)) <= {0, 1}
@@ -82,18 +78,13 @@ def test_k_traverse_under_simt_emulation_equals_single_ray_traversal(lib, name):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     _, vis = _run(lib, h, closest[:0], shadow, 4)
     assert np.array_equal(vis == 0, occluded)
-    got, _ = _run(lib, h, closest, shadow[:0], POOL | 4)
-    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
-    _, vis = _run(lib, h, closest[:0], shadow, POOL | 4)
-    assert np.array_equal(vis == 0, occluded)
-    _run(lib, h, closest[:0], shadow[:0], POOL | 4)
-    for sched in (4, 4 | (16 << 16), POOL | 4):
+    for sched in (4, 4 | (16 << 16)):
         got, vis = _run(lib, h, closest[:37], shadow[:5], sched)
         assert np.array_equal(got.view(np.uint32), want[:37].view(np.uint32)) and np.array_equal(vis == 0, occluded[:5])
     _run(lib, h, closest[:0], shadow[:0], 4)
     # queue indirection (the compacted queue of a later bounce): slots visited in a permuted order, two blocks
     perm = np.random.default_rng(1).permutation(len(closest)).astype(np.uint32)
-    for sched in (4, 4 | (24 << 16), POOL | 4):
+    for sched in (4, 4 | (24 << 16)):
         got, vis = _run(lib, h, closest, shadow, sched, perm, blocks=2)
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)) and np.array_equal(vis == 0, occluded)
     lib.crt_simt_destroy(h)
