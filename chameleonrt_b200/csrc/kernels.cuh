@@ -190,8 +190,7 @@ __global__ void __launch_bounds__(kTravBlock, 8)
     // shared memory so that ANY lane can test a (ray, triangle) pair for its owner
     __shared__ float sm_ray[kTravBlock / 32][8][32];            // ox oy oz tnear dx dy dz tfar0
     __shared__ unsigned long long sm_key[kTravBlock / 32][32];  // bits(t) << 32 | flat id  (atomicMin)
-    __shared__ float sm_hit_u[kTravBlock / 32][32], sm_hit_v[kTravBlock / 32][32];
-    __shared__ uint32_t sm_hit_tri[kTravBlock / 32][32];
+    __shared__ float4 sm_hit[kTravBlock / 32][32];              // u, v, bits(leaf-order triangle | kMiss) of the best hit: one 128-bit store
     __shared__ uint32_t sm_owner[kTravBlock / 32][32];          // owner lane of the group that starts at slot s
     __shared__ uint32_t sm_cursor[kTravBlock / 32];             // running slot cursor of the warp (never reset)
     __shared__ uint32_t sm_is_any[kTravBlock / 32][32];         // ray kind per lane (instrumented build only)
@@ -270,7 +269,7 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                     sm_ray[warp][6][lane] = ray.dz;
                     sm_ray[warp][7][lane] = ray.tfar;
                     sm_key[warp][lane] = ((unsigned long long)__float_as_uint(ray.tfar) << 32) | 0xffffffffull;
-                    sm_hit_tri[warp][lane] = kMiss;
+                    sm_hit[warp][lane] = make_float4(0.f, 0.f, __uint_as_float(kMiss), 0.f);
                     if (COUNT) {
                         sm_is_any[warp][lane] = is_any ? 1u : 0u;
                     }
@@ -374,9 +373,19 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                     uint32_t tri_index = 0u;
                     float hu = 0.f, hv = 0.f;
                     if ((uint32_t)lane < npairs) {
+                        // the rank-th highest set bit of the group: two predicated steps cover a leaf (<= 3 triangles)
+                        uint32_t skip = rank;
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            if (skip) {
+                                gy ^= 1u << msb(gy);
+                                --skip;
+                            }
+                        }
 #pragma unroll 1
-                        for (uint32_t i = 0; i < rank; ++i) {
+                        while (skip) {
                             gy ^= 1u << msb(gy);
+                            --skip;
                         }
                         tri_index = gx + (uint32_t)msb(gy);
                         if (COUNT) {  // attribute the test to the kind of the owner's ray
@@ -405,9 +414,7 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                     }
                     __syncwarp();
                     if (won && sm_key[warp][owner] == cand) {  // the pair that holds the minimum records u, v
-                        sm_hit_u[warp][owner] = hu;
-                        sm_hit_v[warp][owner] = hv;
-                        sm_hit_tri[warp][owner] = tri_index;
+                        sm_hit[warp][owner] = make_float4(hu, hv, __uint_as_float(tri_index), 0.f);
                     }
                     __syncwarp();
                     if (total <= 32u) {
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                 // refresh tfar, pop, finish
                 if (alive) {
                     st.tfar = __uint_as_float((uint32_t)(sm_key[warp][lane] >> 32));
-                    bool finished = is_any && sm_hit_tri[warp][lane] != kMiss;
+                    bool finished = is_any && __float_as_uint(sm_hit[warp][lane].z) != kMiss;
                     if (DEFER > 0 && finished) {
                         tri.y = 0u;  // an occluded shadow ray needs no further tests
                     }
@@ -430,13 +437,13 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                         }
                     }
                     if (finished) {
-                        const uint32_t htri = sm_hit_tri[warp][lane];
+                        const float4 best = sm_hit[warp][lane];
+                        const uint32_t htri = __float_as_uint(best.z);
                         if (is_any) {
                             ps.vis[out_index] = htri != kMiss ? 0 : 1;
                         } else {
                             ps.hit[out_index] = make_float4(__uint_as_float((uint32_t)(sm_key[warp][lane] >> 32)),
-                                                            htri != kMiss ? sm_hit_u[warp][lane] : 0.f,
-                                                            htri != kMiss ? sm_hit_v[warp][lane] : 0.f,
+                                                            htri != kMiss ? best.x : 0.f, htri != kMiss ? best.y : 0.f,
                                                             __uint_as_float(htri));
                         }
                         alive = false;
