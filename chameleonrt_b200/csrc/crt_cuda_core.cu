@@ -88,7 +88,7 @@ struct crtc_renderer {
     bool ploc_tail = true;  // the last rounds of PLOC in one block (k_ploc_tail); off only to test that the tree is the same
     bool count_traversal = false;
     int refill_idle = crt::kRefillIdle;  // idle lanes that trigger a refill of the traversal warps
-    int tri_pass_defer = 0;              // 0 (default) / 16 / 24: pooled pairs a triangle pass waits for (kernels.cuh)
+    int tri_pass_defer = 16;             // 0 / 16 (default) / 24: pooled pairs a triangle pass waits for (kernels.cuh)
     // The shade queue bucketed by material id before k_shade (k_queue_hist / k_queue_scatter): 0 = off (default),
     // 1 = from the first bounce on (primary hits keep their screen order), 2 = every shade launch. Same image.
     int shade_sort = 0;

@@ -17,9 +17,9 @@ def mods(built):
     return RenderCUDA, OracleBackend, primary_rays
 
 
-def _pair(mods, scene, w, h, depth=5):
+def _pair(mods, scene, w, h, depth=5, bvh_builder=None):
     RenderCUDA, OracleBackend, _ = mods
-    gpu, cpu = RenderCUDA(0, max_depth=depth), OracleBackend(max_depth=depth)
+    gpu, cpu = RenderCUDA(0, max_depth=depth, bvh_builder=bvh_builder), OracleBackend(max_depth=depth)
     for r in (gpu, cpu):
         r.initialize(w, h)
         r.set_scene(scene)
@@ -50,8 +50,9 @@ def _ref_case_names():
     return list(FRAME_CASES)
 
 
+@pytest.mark.parametrize("bvh_builder", ["host", "device"])
 @pytest.mark.parametrize("name", _ref_case_names())
-def test_cuda_matches_reference_embree_frames(mods, ref_golden, name):
+def test_cuda_matches_reference_embree_frames(mods, ref_golden, name, bvh_builder):
     """The CUDA backend against float framebuffers rendered by the REFERENCE'S OWN Embree/ISPC backend
     (tests/golden/ref_embree_frames.npz, made by tests/golden/make_ref_embree_golden.py from
     /root/reference/backends/embree compiled as described in oracle/ref_build/Makefile): same scene, camera,
@@ -61,7 +62,7 @@ def test_cuda_matches_reference_embree_frames(mods, ref_golden, name):
 
     RenderCUDA = mods[0]
     scene, view, w, h, frames, depth = make_case(name)
-    gpu = RenderCUDA(0, max_depth=depth)
+    gpu = RenderCUDA(0, max_depth=depth, bvh_builder=bvh_builder)  # "device": the BVH8 built by the kernels of bvh8_device.cuh
     gpu.initialize(w, h)
     gpu.set_scene(scene)
     st = None
@@ -73,13 +74,14 @@ def test_cuda_matches_reference_embree_frames(mods, ref_golden, name):
 
 
 # ---------------------------------------------------------------- kernel level: traversal
+@pytest.mark.parametrize("bvh_builder", ["host", "device", "device_lbvh"])
 @pytest.mark.parametrize("name", ["cornell", "sponza", "materials"])
-def test_traversal_kernels_bit_exact(mods, name):
+def test_traversal_kernels_bit_exact(mods, name, bvh_builder):
     from chameleonrt_b200.scenes import cornell_box, sponza_like
 
     scene, cam = {"cornell": lambda: cornell_box(), "sponza": lambda: sponza_like(detail=0.5, tex_size=16),
                   "materials": lambda: synthetic_material_scene()}[name]()
-    gpu, cpu = _pair(mods, scene, 64, 64)
+    gpu, cpu = _pair(mods, scene, 64, 64, bvh_builder=bvh_builder)
     c = camera_for(cam)
     rays = mods[2](160, 90, c.eye(), c.dir(), c.up(), cam["fov_y"])
     h0 = cpu.trace_closest(rays)
