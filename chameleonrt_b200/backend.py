@@ -216,8 +216,12 @@ class RenderCUDA:
         self._check(self.lib.crtc_read_accum(self.h, out.ctypes.data))
         return out
 
-    def read_img(self) -> np.ndarray:
-        out = np.zeros((self.height, self.width), dtype=np.uint32)
+    def read_img(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """The sRGB8 frame (crtc_read_img). ``out``: read into this (height, width) uint32 array instead of a new one —
+        a frame loop that passes ``self.img`` every time gets a page-locked destination (option "pin_read_img")."""
+        if out is None:
+            out = np.zeros((self.height, self.width), dtype=np.uint32)
+        assert out.dtype == np.uint32 and out.shape == (self.height, self.width) and out.flags["C_CONTIGUOUS"]
         self._check(self.lib.crtc_read_img(self.h, out.ctypes.data))
         return out
 

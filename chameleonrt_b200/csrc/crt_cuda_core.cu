@@ -248,8 +248,39 @@ struct crtc_renderer {
         peer_is_ipc = true;
     }
 
+    // The caller's `img` (RenderBackend::img: a std::vector / numpy array that lives as long as the framebuffer size) is
+    // page-locked on first use so that the frame-end readback is one DMA transfer instead of a staged pageable copy
+    // (3.7 MB at 1280x720: ~0.35 ms -> ~0.15 ms per frame). Registration failures are not errors: the copy then stays pageable.
+    void *pinned_img = nullptr;
+    size_t pinned_bytes = 0;
+    void unpin_img()
+    {
+        if (pinned_img) {
+            cudaHostUnregister(pinned_img);
+            cudaGetLastError();
+            pinned_img = nullptr;
+            pinned_bytes = 0;
+        }
+    }
+    void pin_img(void *img, size_t bytes)
+    {
+        if (img == pinned_img && bytes == pinned_bytes) {
+            return;
+        }
+        unpin_img();
+        if (pin_host_buffers && cudaHostRegister(img, bytes, cudaHostRegisterDefault) == cudaSuccess) {
+            pinned_img = img;
+            pinned_bytes = bytes;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    bool pin_host_buffers = true;  // option "pin_host_buffers"
+    bool pin_repeated_reads = false;  // option "pin_read_img": crtc_read_img page-locks its destination too (a frame loop)
+
     ~crtc_renderer()
     {
+        unpin_img();
         close_peer_frame();
         in_flight.clear();
         record_pool.clear();
@@ -411,6 +442,7 @@ struct crtc_renderer {
         }
         make_current();
         CUDA_CHECK(cudaStreamSynchronize(stream));
+        unpin_img();             // (the caller's img buffer is reallocated with the new size)
         close_peer_frame();      // the frame's shape (and on the exporting rank, its buffers) change:
         frame_exported = false;  // crtc_export_frame / crtc_import_frame must be called again
         frame_id = 0;
@@ -757,6 +789,7 @@ struct crtc_renderer {
     {
         enqueue_frame(pos, dir, up, fovy, camera_changed, 1, true);
         if (readback && img && world_size == 1) {
+            pin_img(img, (size_t)fb_w * fb_h * 4);
             CUDA_CHECK(cudaMemcpyAsync(img, d_img_full.ptr, (size_t)fb_w * fb_h * 4, cudaMemcpyDeviceToHost, stream));
         }
         CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -1078,6 +1111,13 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
                 throw std::runtime_error("shade_sort must be 0, 1 or 2");
             }
             r->shade_sort = (int)value;
+        } else if (k == "pin_host_buffers") {
+            r->pin_host_buffers = value != 0;
+            if (!r->pin_host_buffers) {
+                r->unpin_img();
+            }
+        } else if (k == "pin_read_img") {
+            r->pin_repeated_reads = value != 0;
         } else if (k == "bvh_ploc_tail") {
             r->ploc_tail = value != 0;
         } else if (k == "bvh_ploc_radius") {
@@ -1210,6 +1250,9 @@ int crtc_read_img(crtc_renderer *r, uint32_t *img)
 {
     CRTC_TRY({ require_renderer(r);
         r->make_current();
+        if (img == r->pinned_img || r->pin_repeated_reads) {  // (a caller that reads into the same buffer every frame)
+            r->pin_img(img, (size_t)r->fb_w * r->fb_h * 4);
+        }
         CUDA_CHECK(cudaMemcpyAsync(img, r->d_img_full.ptr, (size_t)r->fb_w * r->fb_h * 4, cudaMemcpyDeviceToHost,
                                    r->stream));
         CUDA_CHECK(cudaStreamSynchronize(r->stream));

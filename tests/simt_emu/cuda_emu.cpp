@@ -76,6 +76,14 @@ cudaError_t cudaFreeHost(void *p)
     std::free(p);
     return cudaSuccess;
 }
+cudaError_t cudaHostRegister(void *, size_t, unsigned int)
+{
+    return cudaSuccess;
+}
+cudaError_t cudaHostUnregister(void *)
+{
+    return cudaSuccess;
+}
 cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, enum cudaMemcpyKind, cudaStream_t)
 {
     std::memcpy(dst, src, n);

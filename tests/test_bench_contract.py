@@ -69,6 +69,7 @@ import torch
 class _Stream:
     cuda_stream = 0
     def __init__(self, *a, **k): pass
+    def synchronize(self): pass
 class _Event:
     def __init__(self, enable_timing=False): self.t = None
     def record(self, stream=None): self.t = time.perf_counter()
@@ -97,6 +98,14 @@ bench.main()
                 "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "stage_ms_per_step"):
         assert key in d, key
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["value"] > 0 and d["gpu_launches"] == 2 * (2 + 3 * 5 + 1)
+    # the timed region is repeated: value / ms_per_step are the median repetition, the spread is in the line
+    disp = d["dispersion"]
+    assert disp["repeats"] == 5 and disp["ms_per_step"]["min"] <= d["ms_per_step"] <= disp["ms_per_step"]["max"]
+    assert disp["value"]["min"] <= d["value"] <= disp["value"]["max"] and disp["e2e_value"]["min"] <= d["e2e"]["value"] <= disp["e2e_value"]["max"]
+    # the CPU arm says what it is and what CPU budget it really had
+    cb = d["cpu_baseline"]
+    assert cb["effective_cores"] > 0 and cb["mrays_per_effective_core"] > 0 and "NOT Embree" in cb["label"] and "cgroup_quota_cores" in cb
+    assert "traffic_note" in d["roofline"]
     assert d["config"]["workload"].startswith("DEV") and d["config"]["frames_in_flight"] == 1
     assert d["config"]["shadow_ray_order"].split()[0] in ("far-first", "near-first")
     rf = d["roofline"]
@@ -132,6 +141,7 @@ import torch.distributed as dist
 class _Stream:
     cuda_stream = 0
     def __init__(self, *a, **k): pass
+    def synchronize(self): pass
 class _Event:
     def __init__(self, enable_timing=False): self.t = None
     def record(self, stream=None): self.t = time.perf_counter()
@@ -159,7 +169,7 @@ bench.main()
     procs = []
     for rank in range(2):
         env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
-                   CRT_BENCH_REF_BUDGET="2")
+                   CRT_BENCH_REF_BUDGET="2", CRT_BENCH_FRAME="gather")  # (peer-written frames need real CUDA IPC between processes)
         procs.append(subprocess.Popen([sys.executable, str(driver)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT, env=env))
     outs = [p.communicate(timeout=900) for p in procs]
     for p, (so, se) in zip(procs, outs):
@@ -171,3 +181,6 @@ bench.main()
     assert d["n_gpus"] == 2 and d["steps"] == 4 and d["config"]["frames_in_flight"] == 2 and d["value"] > 0 and d["e2e"]["value"] > 0
     assert d["gpu_launches"] == 2 * 2 * (2 + 3 * 5 + 1) + 2 * 2  # 2 ranks x 2 batches x launches per wavefront + k_assemble on rank 0
     assert "cpu_baseline" not in d and d["roofline"]["closest"]["rays"] > 0 and "image tiles 64x64" in d["config"]["parallelism"]
+    # correctness travels with the scaling line: the assembled 2-rank frame equals the frame one renderer alone renders
+    assert d["mgpu_bit_identical"] is True and d["accum"] is True and d["img"] is True and d["rays_last_frame"][0] == d["rays_last_frame"][1]
+    assert d["frame_by_frame"]["value"] > 0 and d["dispersion"]["repeats"] == 5

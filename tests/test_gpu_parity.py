@@ -389,7 +389,7 @@ def test_shadow_ray_order_option_does_not_change_the_image(mods):
     c = camera_for(cam)
     out = []
     for mode in (0, 1, 2):
-        r = RenderCUDA(0, max_depth=5, count_traversal=True, any_far_first=mode)
+        r = RenderCUDA(0, max_depth=5, count_traversal=True, any_far_first=mode, tri_pass_defer=0)  # (counts per ray, not per warp)
         r.initialize(256, 144)
         r.set_scene(scene)
         for f in range(4):

@@ -69,7 +69,9 @@ def test_ploc_tail_kernel_builds_the_same_tree(mods, detail=0.5, size=(160, 90))
     for scene, cam in (cornell_box(spp=1), sponza_like(spp=1, detail=detail, tex_size=32)):
         res = []
         for tail in (1, 0):
-            r = RenderCUDA(0, bvh_builder="device", count_traversal=True, any_far_first=0)
+            # (tri_pass_defer = 0: with a deferred triangle pass the number of triangles tested for an occluded shadow
+            # ray depends on which rays share a warp, i.e. on the timing of the work fetch — not a property of the tree)
+            r = RenderCUDA(0, bvh_builder="device", count_traversal=True, any_far_first=0, tri_pass_defer=0)
             r.set_option("bvh_ploc_tail", tail)
             r.initialize(*size)
             r.set_scene(scene)
@@ -223,7 +225,9 @@ def test_shade_queue_sort_does_not_change_the_image(mods, size=(256, 144), detai
         view = (c.eye(), c.dir(), c.up(), cam["fov_y"])
         out = []
         for mode in (0, 1, 2):
-            r = RenderCUDA(0, max_depth=depth, count_traversal=True, any_far_first=0, shade_sort=mode)
+            # (tri_pass_defer = 0: node visits per ray are a property of the ray only when its triangles are tested in
+            # the iteration that found them; with the deferred pass they depend on which rays share a warp)
+            r = RenderCUDA(0, max_depth=depth, count_traversal=True, any_far_first=0, shade_sort=mode, tri_pass_defer=0)
             r.initialize(*size)
             r.set_scene(scene)
             for f in range(frames):
