@@ -293,6 +293,7 @@ struct crtc_renderer {
 
     // persistent traversal grid: every SM filled with as many blocks as fit
     unsigned trav_grid = 0;
+    int num_sms = 0;
     void launch_traverse(const crt::DeviceScene &sc, const crt::PathState &ps, const uint32_t *queue,
                          const uint32_t *count_closest, const uint32_t *count_any, uint32_t *work_counter)
     {
@@ -681,7 +682,12 @@ struct crtc_renderer {
         }
         if (npaths) {
             const unsigned g256 = (unsigned)((npaths + 255) / 256);
+            // k_nee_resolve strides over its queue: two waves of resident blocks cover any queue length
+            if (num_sms == 0) {
+                CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+            }
             const unsigned g128 = (unsigned)((npaths + 127) / 128);
+            const unsigned g_nee = (unsigned)std::min<size_t>((npaths + 255) / 256, (size_t)num_sms * 8 * 2);
             crt::k_raygen<<<g256, 256, 0, stream>>>(view, fl, ps);
             rec.mark(stream, kStRaygen);
             // closest hit of the primary rays, then per bounce: shade -> one traversal launch for this
@@ -703,7 +709,7 @@ struct crtc_renderer {
                 launch_traverse(sc, ps, qout, last ? nullptr : ps.counters + crt::kCntQueue + b + 1,
                                 ps.counters + crt::kCntShadow + b, ps.counters + crt::kCntWork + 1 + b);
                 rec.mark(stream, kStTraverse);
-                crt::k_nee_resolve<<<g256, 256, 0, stream>>>(ps, qin, b);
+                crt::k_nee_resolve<<<g_nee, 256, 0, stream>>>(ps, qin, b);
                 rec.mark(stream, kStNee);
                 rec.launches += 3;
             }

@@ -477,6 +477,9 @@ __global__ void __launch_bounds__(kTravBlock, 8)
 // 80 registers (6 blocks of 128 per SM) with the three BSDF evaluations inlined measured fastest:
 // 3.19 ms/frame -> 2.67 ms on C2 against 4 blocks x 106 registers with out-of-line BSDF calls
 // (inlining lets the compiler share sub-expressions between disney_pdf and disney_brdf).
+// (A grid-stride form for the thin queues of the late bounces was measured in round 2 and dropped: those launches take
+// ~49 us whatever the grid, and ncu shows why — 12 no-instruction stalls per issued instruction: a warp's first walk
+// through this kernel's ~4000 executed instructions is a chain of instruction-cache misses.)
 __global__ void __launch_bounds__(128, 6) k_shade(DeviceScene sc, PathState ps, const uint32_t *queue_in,
                                                uint32_t *queue_out, int bounce, int max_depth)
 {
@@ -718,14 +721,12 @@ __global__ void __launch_bounds__(kSortBlock) k_queue_scatter(DeviceScene sc, Pa
 // illum = illum + path_throughput * (L1 [if unoccluded] + L2 [if traced and unoccluded])
 __global__ void __launch_bounds__(256) k_nee_resolve(PathState ps, const uint32_t *queue_in, int bounce)
 {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= ps.counters[kCntQueue + bounce]) {
-        return;
-    }
+    const uint32_t count = ps.counters[kCntQueue + bounce];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {  // grid-stride, as k_shade
     const uint32_t slot = queue_in[j];
     const float4 T = ps.nee_T[slot];
     if ((__float_as_uint(T.w) & 2u) == 0u) {
-        return;  // the path missed at this bounce
+        continue;  // the path missed at this bounce
     }
     float3 illum = mk3(0.f);
     if (ps.vis[2 * slot]) {
@@ -743,6 +744,7 @@ __global__ void __launch_bounds__(256) k_nee_resolve(PathState ps, const uint32_
     rad.y = rad.y + T.y * illum.y;
     rad.z = rad.z + T.z * illum.z;
     ps.radiance[slot] = rad;
+    }
 }
 
 // render_embree.ispc:339-353 (sample mean + running mean) and :358-370 (sRGB8)

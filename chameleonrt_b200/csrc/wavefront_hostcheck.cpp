@@ -235,6 +235,7 @@ struct HostWavefront {
     {
         blockDim.x = 1;
         threadIdx.x = 0;
+        gridDim.x = (unsigned)nthreads;  // (k_shade / k_nee_resolve stride over their queue by gridDim.x * blockDim.x)
         for (size_t i = 0; i < nthreads; ++i) {
             blockIdx.x = (unsigned)i;
             kernel();
