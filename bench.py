@@ -530,17 +530,23 @@ def main():
     gatherer = (PeerFrame(gpu) if peer_frame else FrameGatherer(gpu)) if world > 1 else None
 
     def frame(f, readback):
-        """One step through the public call. N > 1: the frame-end exchange of frame f is started here; without
-        readback it overlaps the rendering of frame f+1 (completed by the next submit or by flush()); with readback the
-        assembled frame is needed now: the exchange is finished and rank 0 reads `img` into its host buffer."""
-        st = gpu.render(*view, f == 0, readback and world == 1)
-        if world > 1:
+        """One step through the public call. N = 1: the blocking RenderBackend::render with `img` read back. N > 1:
+        without readback (warm-up) the blocking call, the frame-end exchange left pending; with readback the frame is
+        enqueued, rank 0's stream waits for every rank's tiles (completion flags over peer memory, or the gather), rank 0
+        reads `img` into its page-locked host buffer, and every rank waits for its own frame (one host wait per frame)."""
+        if world == 1:
+            return gpu.render(*view, f == 0, readback)
+        if not readback:
+            st = gpu.render(*view, f == 0, False)
             gatherer.submit()
-            if readback:
-                gatherer.finish()
-                if rank == 0:
-                    gpu.read_img(gpu.img)
-        return st
+            return st
+        gpu.render_async(*view, f == 0, 1)
+        gatherer.submit()
+        gatherer.finish()
+        if rank == 0:
+            gpu.read_img(gpu.img)
+        totals, _, _, _ = gpu.sync()
+        return totals
 
     def flush():
         if world > 1:

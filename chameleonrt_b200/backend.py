@@ -35,7 +35,7 @@ C_ABI_SYMBOLS = (
     "crtc_last_error", "crtc_name", "crtc_create", "crtc_destroy", "crtc_set_option", "crtc_get_option", "crtc_set_stream",
     "crtc_initialize", "crtc_set_scene", "crtc_render", "crtc_render_async", "crtc_sync", "crtc_read_accum", "crtc_get_stage_times",
     "crtc_get_counters", "crtc_get_scene_info", "crtc_trace_closest", "crtc_trace_any", "crtc_bench_trace",
-    "crtc_local_buffers", "crtc_assemble_rank", "crtc_export_frame", "crtc_import_frame", "crtc_share_frame", "crtc_read_img",
+    "crtc_local_buffers", "crtc_assemble_rank", "crtc_export_frame", "crtc_import_frame", "crtc_share_frame", "crtc_read_img", "crtc_frame_wait",
 )
 
 
@@ -70,6 +70,7 @@ def load_lib() -> C.CDLL:
     lib.crtc_sync.argtypes = [vp, C.POINTER(CRenderStats), vp, vp, C.POINTER(C.c_uint32)]
     lib.crtc_read_accum.argtypes = [vp, vp]
     lib.crtc_read_img.argtypes = [vp, vp]
+    lib.crtc_frame_wait.argtypes = [vp]
     lib.crtc_get_stage_times.argtypes = [vp, vp, C.c_int]
     lib.crtc_get_counters.argtypes = [vp, vp, C.c_int]
     lib.crtc_get_scene_info.argtypes = [vp, vp, C.c_int]
@@ -278,6 +279,10 @@ class RenderCUDA:
         if handles is not None and len(handles) != 128:
             raise ValueError("import_frame expects the 128 bytes of export_frame")
         self._check(self.lib.crtc_import_frame(self.h, handles))
+
+    def frame_wait(self) -> None:
+        """crtc_frame_wait: on the assembling rank of a shared frame, orders the stream after every rank's stores."""
+        self._check(self.lib.crtc_frame_wait(self.h))
 
     def share_frame_with(self, src: "RenderCUDA") -> None:
         """In-process multi-GPU: ``src`` (another RenderCUDA of this process, same size) resolves its tiles into this

@@ -170,6 +170,54 @@ struct crtc_renderer {
     // IPC handles, the other ranks map them and their k_resolve stores each pixel there as well (st.global to a
     // peer address over NVLink). Tile ownership is disjoint, so there is nothing to reduce.
     bool frame_exported = false;
+    // Completion flags of a shared frame (kernels.cuh "frame completion flags"): share_seq counts the wavefronts enqueued
+    // since the frame was shared (every rank enqueues the same sequence of crtc_render / crtc_render_async calls).
+    uint32_t share_seq = 0;
+    DeviceBuffer<uint32_t> d_done_counter;
+    uint32_t *h_sync_err = nullptr, *d_sync_err = nullptr;  // one mapped host word: a flag wait that timed out
+    uint32_t *sync_words() { return d_img_full.ptr + (size_t)fb_w * fb_h; }
+    uint32_t *peer_sync_words() { return peer_img_full + (size_t)fb_w * fb_h; }
+    void ensure_sync_state()
+    {
+        if (!d_done_counter.ptr) {
+            d_done_counter.alloc(1);
+            CUDA_CHECK(cudaMemsetAsync(d_done_counter.ptr, 0, sizeof(uint32_t), stream));
+        }
+        if (!h_sync_err) {
+            CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void **>(&h_sync_err), sizeof(uint32_t), cudaHostAllocMapped));
+            *h_sync_err = 0u;
+            CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_sync_err), h_sync_err, 0));
+        }
+    }
+    void reset_share_sequence()
+    {
+        share_seq = 0;
+        if (d_img_full.ptr && fb_w) {
+            CUDA_CHECK(cudaMemsetAsync(sync_words(), 0, crt::kSyncWords * sizeof(uint32_t), stream));
+            CUDA_CHECK(cudaStreamSynchronize(stream));
+        }
+    }
+    void check_sync_error()
+    {
+        if (h_sync_err && *h_sync_err) {
+            const uint32_t who = *h_sync_err - 1u;
+            *h_sync_err = 0u;
+            throw std::runtime_error("shared frame: rank " + std::to_string(who) + "'s completion flag did not arrive within 20 s "
+                                     "(every rank must enqueue the same sequence of frames)");
+        }
+    }
+    // On the assembling rank, stream-ordered: everything enqueued afterwards sees the frame of the last enqueued
+    // wavefront complete, every rank's tiles included.
+    void frame_wait()
+    {
+        if (!frame_exported || world_size < 2 || share_seq == 0) {
+            return;
+        }
+        make_current();
+        ensure_sync_state();
+        crt::k_wait_words<<<1, 32, 0, stream>>>(sync_words(), (uint32_t)world_size, (uint32_t)rank, share_seq, d_sync_err);
+        CUDA_CHECK(cudaGetLastError());
+    }
     float *peer_accum_full = nullptr;
     uint32_t *peer_img_full = nullptr;
     bool peer_is_ipc = false;  // mapped through cudaIpcOpenMemHandle (another process) or a plain peer pointer (this one)
@@ -212,6 +260,12 @@ struct crtc_renderer {
         peer_accum_full = dst->d_accum_full.ptr;
         peer_img_full = dst->d_img_full.ptr;
         peer_is_ipc = false;
+        share_seq = 0;
+        if (!dst->frame_exported) {
+            dst->make_current();
+            dst->reset_share_sequence();
+            make_current();
+        }
         dst->frame_exported = true;
     }
     void export_frame(void *handles_out)
@@ -225,6 +279,7 @@ struct crtc_renderer {
         CUDA_CHECK(cudaIpcGetMemHandle(&h[0], d_accum_full.ptr));
         CUDA_CHECK(cudaIpcGetMemHandle(&h[1], d_img_full.ptr));
         std::memcpy(handles_out, h, sizeof(h));
+        reset_share_sequence();
         frame_exported = true;
     }
     void import_frame(const void *handles)
@@ -246,6 +301,7 @@ struct crtc_renderer {
         peer_accum_full = static_cast<float *>(a);
         peer_img_full = static_cast<uint32_t *>(i);
         peer_is_ipc = true;
+        share_seq = 0;
     }
 
     // The caller's `img` (RenderBackend::img: a std::vector / numpy array that lives as long as the framebuffer size) is
@@ -286,6 +342,9 @@ struct crtc_renderer {
         record_pool.clear();
         if (own_stream) {
             cudaStreamDestroy(own_stream);
+        }
+        if (h_sync_err) {
+            cudaFreeHost(h_sync_err);
         }
     }
 
@@ -464,13 +523,14 @@ struct crtc_renderer {
         d_accum_local.alloc((size_t)npx_local * 3);
         d_img_local.alloc(npx_local);
         d_accum_full.alloc((size_t)w * h * 3);
-        d_img_full.alloc((size_t)w * h);
+        d_img_full.alloc((size_t)w * h + crt::kSyncWords);  // + the frame completion flags (kernels.cuh)
         if (npx_local) {
             CUDA_CHECK(cudaMemsetAsync(d_accum_local.ptr, 0, (size_t)npx_local * 3 * sizeof(float), stream));
             CUDA_CHECK(cudaMemsetAsync(d_img_local.ptr, 0, (size_t)npx_local * 4, stream));
         }
         CUDA_CHECK(cudaMemsetAsync(d_accum_full.ptr, 0, (size_t)w * h * 3 * sizeof(float), stream));
-        CUDA_CHECK(cudaMemsetAsync(d_img_full.ptr, 0, (size_t)w * h * 4, stream));
+        CUDA_CHECK(cudaMemsetAsync(d_img_full.ptr, 0, ((size_t)w * h + crt::kSyncWords) * 4, stream));
+        share_seq = 0;
         CUDA_CHECK(cudaStreamSynchronize(stream));
     }
 
@@ -675,7 +735,15 @@ struct crtc_renderer {
         rec.num_events = 0;
         rec.launches = 0;
 
+        const bool shared_dst = frame_exported && world_size > 1, shared_src = peer_accum_full != nullptr && !frame_exported;
+        if (shared_dst || shared_src) {
+            ensure_sync_state();
+        }
         rec.mark(stream, -1);
+        if (shared_dst && share_seq > 0) {
+            // starting the next wavefront: the assembling rank is done with the previous frame, peers may overwrite it
+            crt::k_set_word<<<1, 32, 0, stream>>>(sync_words() + crt::kSyncConsumed, share_seq);
+        }
         CUDA_CHECK(cudaMemsetAsync(d_counters.ptr, 0, crt::kNumCounters * sizeof(uint32_t), stream));
         if (count_traversal) {
             CUDA_CHECK(cudaMemsetAsync(d_trav_counters.ptr, 0, 4 * sizeof(unsigned long long), stream));
@@ -726,9 +794,20 @@ struct crtc_renderer {
                 full_accum = peer_accum_full;
                 full_img = peer_img_full;
             }
-            crt::k_resolve<<<gpx, 256, 0, stream>>>(fl, ps, frame_id, d_accum_local.ptr, d_img_local.ptr, full_accum, full_img);
+            uint32_t *arrive = nullptr;
+            if (shared_src) {
+                if (share_seq > 0) {  // not before the assembling rank is done with the frame this one overwrites
+                    crt::k_wait_words<<<1, 32, 0, stream>>>(peer_sync_words() + crt::kSyncConsumed, 1u, 0xffffffffu, share_seq, d_sync_err);
+                }
+                arrive = peer_sync_words() + rank;
+            }
+            crt::k_resolve<<<gpx, 256, 0, stream>>>(fl, ps, frame_id, d_accum_local.ptr, d_img_local.ptr, full_accum, full_img,
+                                                   d_done_counter.ptr, arrive, share_seq + 1u);
             rec.launches += 1;
             rec.mark(stream, kStResolve);
+        } else if (shared_src) {
+            // a rank that owns no tile of this frame (more ranks than tiles) still has to say "done"
+            crt::k_set_word<<<1, 32, 0, stream>>>(peer_sync_words() + rank, share_seq + 1u);
         }
         CUDA_CHECK(cudaMemcpyAsync(rec.h_counters, d_counters.ptr, crt::kNumCounters * sizeof(uint32_t),
                                    cudaMemcpyDeviceToHost, stream));
@@ -739,6 +818,9 @@ struct crtc_renderer {
         CUDA_CHECK(cudaGetLastError());
         frame_id += num_frames;
         rec.frames = num_frames;
+        if (shared_dst || shared_src) {
+            ++share_seq;
+        }
         return rec;
     }
 
@@ -800,6 +882,7 @@ struct crtc_renderer {
         }
         CUDA_CHECK(cudaStreamSynchronize(stream));
         CUDA_CHECK(cudaGetLastError());
+        check_sync_error();
         collect(nullptr, nullptr);
         auto_tune_step();
         if (stats) {
@@ -817,6 +900,7 @@ struct crtc_renderer {
         make_current();
         CUDA_CHECK(cudaStreamSynchronize(stream));
         CUDA_CHECK(cudaGetLastError());
+        check_sync_error();
         float ssum[kNumStages] = {0};
         uint64_t csum[8] = {0};
         const uint32_t n = collect(ssum, csum);
@@ -1246,9 +1330,11 @@ int crtc_read_accum(crtc_renderer *r, float *rgb_out)
 {
     CRTC_TRY({ require_renderer(r);
         r->make_current();
+        r->frame_wait();
         CUDA_CHECK(cudaMemcpyAsync(rgb_out, r->d_accum_full.ptr, (size_t)r->fb_w * r->fb_h * 3 * sizeof(float),
                                    cudaMemcpyDeviceToHost, r->stream));
         CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        r->check_sync_error();
     })
 }
 
@@ -1256,12 +1342,14 @@ int crtc_read_img(crtc_renderer *r, uint32_t *img)
 {
     CRTC_TRY({ require_renderer(r);
         r->make_current();
+        r->frame_wait();  // (a shared frame: every rank's tiles first; no-op otherwise)
         if (img == r->pinned_img || r->pin_repeated_reads) {  // (a caller that reads into the same buffer every frame)
             r->pin_img(img, (size_t)r->fb_w * r->fb_h * 4);
         }
         CUDA_CHECK(cudaMemcpyAsync(img, r->d_img_full.ptr, (size_t)r->fb_w * r->fb_h * 4, cudaMemcpyDeviceToHost,
                                    r->stream));
         CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        r->check_sync_error();
     })
 }
 
@@ -1343,6 +1431,11 @@ int crtc_export_frame(crtc_renderer *r, void *handles_out)
 int crtc_import_frame(crtc_renderer *r, const void *handles)
 {
     CRTC_TRY({ require_renderer(r); r->import_frame(handles); })
+}
+
+int crtc_frame_wait(crtc_renderer *r)
+{
+    CRTC_TRY({ require_renderer(r); r->frame_wait(); })
 }
 
 int crtc_share_frame(crtc_renderer *dst, crtc_renderer *src)

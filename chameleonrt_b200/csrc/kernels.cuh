@@ -747,43 +747,116 @@ __global__ void __launch_bounds__(256) k_nee_resolve(PathState ps, const uint32_
     }
 }
 
+// ---- frame completion flags over peer memory (multi-GPU frames written by every rank's k_resolve) ----
+// The assembling rank's full-frame image buffer ends with kSyncWords words that every rank can reach through the same
+// peer mapping as the pixels: word [r] = the last frame sequence number rank r has completely stored into this frame
+// (written by rank r's k_resolve: its last block to finish, after a system-scope fence, with a release store);
+// word [kSyncConsumed] = the last sequence number the assembling rank is done with (it sets it when it starts its
+// next frame; a peer's k_resolve of frame s + 1 waits for it, so it cannot overwrite frame s under a reader).
+// No collective library and no host thread is involved in the exchange: the stores ARE the transfer, the flags the barrier.
+constexpr uint32_t kSyncWords = 64;
+constexpr uint32_t kSyncConsumed = 32;
+constexpr unsigned long long kSyncTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#else
+    return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#endif
+}
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+    __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#endif
+}
+__device__ __forceinline__ unsigned long long sync_clock_ns()
+{
+#if defined(__CUDA_ARCH__)
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+#elif defined(__CUDACC__)
+    return 0ull;  // (nvcc's host pass; never called)
+#else
+    return crt_host_clock_ns();  // the test-only host builds of this header
+#endif
+}
+// lane i < n (i != skip) waits until words[i] has reached `need` (sequence numbers: wrap-safe signed distance).
+// A flag that does not arrive within kSyncTimeoutNs sets *err (a mapped host word) instead of hanging the GPU.
+__global__ void __launch_bounds__(32) k_wait_words(const uint32_t *words, uint32_t n, uint32_t skip, uint32_t need, uint32_t *err)
+{
+    const uint32_t i = threadIdx.x;
+    if (i >= n || i == skip) {
+        return;
+    }
+    const unsigned long long t0 = sync_clock_ns();
+    while ((int32_t)(ld_acquire_sys(words + i) - need) < 0) {
+        if (sync_clock_ns() - t0 > kSyncTimeoutNs) {
+            *err = 1u + i;
+            return;
+        }
+    }
+}
+__global__ void __launch_bounds__(32) k_set_word(uint32_t *word, uint32_t v)
+{
+    if (threadIdx.x == 0) {
+        st_release_sys(word, v);
+    }
+}
+
 // render_embree.ispc:339-353 (sample mean + running mean) and :358-370 (sRGB8)
 __global__ void __launch_bounds__(256) k_resolve(FrameLayout f, PathState ps, uint32_t frame_id, float *accum_local,
-                                                uint32_t *img_local, float *accum_full, uint32_t *img_full)
+                                                uint32_t *img_local, float *accum_full, uint32_t *img_full,
+                                                uint32_t *done_counter, uint32_t *arrive_word, uint32_t seq)
 {
     const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lp >= f.npx_local) {
-        return;
-    }
     uint32_t x, y;
-    if (!local_pixel_coords(f, lp, x, y)) {
-        return;
-    }
-    // the frames of the batch are folded into the running mean one after the other, exactly as if
-    // they had been rendered by separate calls
-    float3 illum = mk3(accum_local[3 * (size_t)lp], accum_local[3 * (size_t)lp + 1], accum_local[3 * (size_t)lp + 2]);
-    for (uint32_t k = 0; k < f.frames; ++k) {
-        const float3 accum = illum;
-        illum = mk3(0.f);
-        for (uint32_t s = 0; s < f.spp; ++s) {
-            const float4 r = ps.radiance[(size_t)(k * f.spp + s) * f.npx_local + lp];
-            illum = illum + mk3(r.x, r.y, r.z);
+    if (lp < f.npx_local && local_pixel_coords(f, lp, x, y)) {
+        // the frames of the batch are folded into the running mean one after the other, exactly as if
+        // they had been rendered by separate calls
+        float3 illum = mk3(accum_local[3 * (size_t)lp], accum_local[3 * (size_t)lp + 1], accum_local[3 * (size_t)lp + 2]);
+        for (uint32_t k = 0; k < f.frames; ++k) {
+            const float3 accum = illum;
+            illum = mk3(0.f);
+            for (uint32_t s = 0; s < f.spp; ++s) {
+                const float4 r = ps.radiance[(size_t)(k * f.spp + s) * f.npx_local + lp];
+                illum = illum + mk3(r.x, r.y, r.z);
+            }
+            illum = illum / (float)f.spp;
+            illum = (illum + (float)(frame_id + k) * accum) / (float)(frame_id + k + 1u);
         }
-        illum = illum / (float)f.spp;
-        illum = (illum + (float)(frame_id + k) * accum) / (float)(frame_id + k + 1u);
+        accum_local[3 * (size_t)lp] = illum.x;
+        accum_local[3 * (size_t)lp + 1] = illum.y;
+        accum_local[3 * (size_t)lp + 2] = illum.z;
+        const uint32_t rgba = float_to_srgb8(illum.x) | (float_to_srgb8(illum.y) << 8) | (float_to_srgb8(illum.z) << 16) |
+                              0xff000000u;
+        img_local[lp] = rgba;
+        if (accum_full) {
+            const size_t p = (size_t)y * f.fb_w + x;
+            accum_full[3 * p] = illum.x;
+            accum_full[3 * p + 1] = illum.y;
+            accum_full[3 * p + 2] = illum.z;
+            img_full[p] = rgba;
+        }
     }
-    accum_local[3 * (size_t)lp] = illum.x;
-    accum_local[3 * (size_t)lp + 1] = illum.y;
-    accum_local[3 * (size_t)lp + 2] = illum.z;
-    const uint32_t rgba = float_to_srgb8(illum.x) | (float_to_srgb8(illum.y) << 8) | (float_to_srgb8(illum.z) << 16) |
-                          0xff000000u;
-    img_local[lp] = rgba;
-    if (accum_full) {
-        const size_t p = (size_t)y * f.fb_w + x;
-        accum_full[3 * p] = illum.x;
-        accum_full[3 * p + 1] = illum.y;
-        accum_full[3 * p + 2] = illum.z;
-        img_full[p] = rgba;
+    // Peer-written frame: the block that finishes LAST publishes "this rank has stored frame `seq`" to the assembling
+    // rank (every block fences its pixel stores at system scope before it takes a ticket).
+    if (arrive_word) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (atomicAdd(done_counter, 1u) == gridDim.x - 1u) {
+                *done_counter = 0u;
+                st_release_sys(arrive_word, seq);
+            }
+        }
     }
 }
 

@@ -169,6 +169,11 @@ static inline unsigned __reduce_or_sync(unsigned, unsigned v)
 static inline void __syncwarp() { simt::warp->sync(); }
 static inline void __syncthreads() { simt::block_barrier->wait(); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline unsigned long long crt_host_clock_ns()
+{
+    return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 // lanes holding the same value
 template <typename T>
 static inline unsigned __match_any_sync(unsigned, T v)

@@ -69,6 +69,8 @@ static inline unsigned __reduce_add_sync(unsigned, unsigned v) { return v; }
 static inline unsigned __reduce_or_sync(unsigned, unsigned v) { return v; }
 // (declarations for the block-level kernels of kernels.cuh, which are templates and never instantiated in this build)
 static inline void __syncthreads() {}
+static inline void __threadfence_system() {}
+static inline unsigned long long crt_host_clock_ns() { return 0ull; }
 template <typename T>
 static inline unsigned __match_any_sync(unsigned, T)
 {
@@ -320,7 +322,7 @@ struct HostWavefront {
             const bool full = world == 1;
             launch(npx_local, [&] {
                 crt::k_resolve(fl, ps, frame_id, accum_local.data(), img_local.data(), full ? accum_full.data() : nullptr,
-                               full ? img_full.data() : nullptr);
+                               full ? img_full.data() : nullptr, nullptr, nullptr, 0u);
             });
         }
         last_rays = 0;

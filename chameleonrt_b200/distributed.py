@@ -8,8 +8,8 @@ accumulated tiles to rank 0:
   tensors (zero copy) and moved with ``dist.gather`` over NVLink/NVSwitch; rank 0 scatters each
   gathered chunk into the full frame with the ``k_assemble`` kernel (``crtc_assemble_rank``).
 * or no gather at all (``PeerFrame``): rank 0 exports its full-frame buffers as CUDA IPC handles, the other ranks
-  map them, and every rank's frame-end resolve kernel stores its pixels straight into rank 0's frame over NVLink;
-  the only collective left is a one-element all-reduce that orders rank 0's stream after everybody's frame.
+  map them, and every rank's frame-end resolve kernel stores its pixels straight into rank 0's frame over NVLink,
+  followed by a completion flag written the same way; rank 0's stream waits for the flags. No collective per frame.
 * backend "gloo" (CPU tests): the same plumbing with numpy buffers and ``tiles.assemble``.
 """
 from __future__ import annotations
@@ -103,12 +103,14 @@ class FrameGatherer:
 
 
 class PeerFrame:
-    """Frame assembly WITHOUT a gather: the resolve kernel of every rank writes its tiles directly into the assembling
-    rank's full frame through peer-mapped memory (``crtc_export_frame`` / ``crtc_import_frame``; st.global over
-    NVLink, fused into the kernel that produces the pixels). Same interface as ``FrameGatherer``: ``submit()`` does
-    nothing (the data is already on its way when the frame's last kernel runs), ``finish()`` orders the current stream
-    after every rank's frames so far (a one-element all-reduce: a barrier, not a transfer) — after it, ``read_accum`` /
-    ``read_img`` on ``dst`` see the assembled frame. Call again after ``initialize`` (a resize)."""
+    """Frame assembly WITHOUT a gather and without a collective: the resolve kernel of every rank writes its tiles directly
+    into the assembling rank's full frame through peer-mapped memory (``crtc_export_frame`` / ``crtc_import_frame``;
+    st.global over NVLink, fused into the kernel that produces the pixels) and then publishes a completion flag the same
+    way; the assembling rank's stream waits for the flags (``crtc_frame_wait``). torch.distributed is used ONCE, to ship
+    the 128 handle bytes. Same interface as ``FrameGatherer``: ``submit()`` does nothing (the data is already on its way
+    when the frame's last kernel runs), ``finish()`` orders ``dst``'s stream after every rank's stores of the last frame —
+    after it, ``read_accum`` / ``read_img`` on ``dst`` see the assembled frame (they also wait by themselves). Every
+    rank must enqueue the same sequence of frames. Call again after ``initialize`` (a resize)."""
 
     def __init__(self, renderer, group=None, dst: int = 0):
         import torch
@@ -117,36 +119,30 @@ class PeerFrame:
         self.r, self.group, self.dst = renderer, group, dst
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.dev = torch.device("cuda", renderer.device)
         # NCCL moves device tensors; with gloo (two processes sharing one GPU in the tests) the 128 bytes travel as a
-        # host tensor and the barrier is a host one
-        self.nccl = dist.get_backend(group) == "nccl"
-        handles = torch.zeros(128, dtype=torch.uint8, device=self.dev if self.nccl else "cpu")
+        # host tensor
+        nccl = dist.get_backend(group) == "nccl"
+        handles = torch.zeros(128, dtype=torch.uint8, device=torch.device("cuda", renderer.device) if nccl else "cpu")
         if self.rank == dst:
             handles.copy_(torch.frombuffer(bytearray(renderer.export_frame()), dtype=torch.uint8))
         dist.broadcast(handles, src=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
         if self.rank != dst:
             renderer.import_frame(handles.cpu().numpy().tobytes())
-        self.token = torch.zeros(1, dtype=torch.float32, device=self.dev if self.nccl else "cpu")
+        dist.barrier(group=group)  # nobody renders into the frame before everybody has mapped it
         self.pending = False
 
     def submit(self):
         self.pending = True
 
     def finish(self) -> bool:
-        """Returns True on ``dst`` when a frame is complete there."""
-        import torch
-        import torch.distributed as dist
-
+        """Returns True on ``dst`` when a frame is complete there (stream-ordered, no host wait)."""
         if not self.pending:
             return False
-        if self.nccl:
-            dist.all_reduce(self.token, group=self.group)  # stream-ordered on the current (= the renderer's) stream
-        else:
-            torch.cuda.current_stream(self.dev).synchronize()
-            dist.barrier(group=self.group)
         self.pending = False
-        return self.rank == self.dst
+        if self.rank != self.dst:
+            return False
+        self.r.frame_wait()
+        return True
 
 
 _GATHERERS = {}

@@ -173,11 +173,19 @@ int crtc_assemble_rank(crtc_renderer *r, int src_rank, int world_size, const voi
  * (handles_out: 128 bytes = two cudaIpcMemHandle_t, accum then img) and keeps writing its own tiles there; every
  * other rank imports them (ship the 128 bytes with any transport, e.g. torch.distributed.broadcast) and from then
  * on its frame-end resolve stores each of its pixels straight into the assembling rank's frame over NVLink, next to
- * its tile-local copy. Tile ownership is disjoint: nothing is reduced, no copy kernel runs. The assembling rank must
- * not read the frame before every rank's frame has completed (a stream-ordered barrier, e.g. a one-element
- * all-reduce, is enough). crtc_initialize undoes both; crtc_import_frame(r, NULL) unmaps. */
+ * its tile-local copy. Tile ownership is disjoint: nothing is reduced, no copy kernel runs, no collective library is
+ * involved: the frame ends with a few flag words that travel through the same mapping — every rank's resolve kernel
+ * publishes "frame s stored" there (system-scope fence + release store by its last block), the assembling rank's
+ * stream waits for all of them before anything reads the frame (crtc_frame_wait; crtc_read_img / crtc_read_accum do it
+ * themselves), and a rank does not store frame s + 1 before the assembling rank has started its own frame s + 1.
+ * Every rank must therefore enqueue the same sequence of crtc_render / crtc_render_async calls; a flag that does not
+ * arrive within 20 s becomes an error of the next synchronising call, not a hang.
+ * crtc_initialize undoes both; crtc_import_frame(r, NULL) unmaps. */
 int crtc_export_frame(crtc_renderer *r, void *handles_out);
 int crtc_import_frame(crtc_renderer *r, const void *handles);
+/* On the assembling rank of a shared frame (exported or crtc_share_frame'd): orders the renderer's stream after every
+ * rank's stores of the last enqueued frame (a 1-warp kernel that spins on the flags). A no-op on other renderers. */
+int crtc_frame_wait(crtc_renderer *r);
 /* The same within ONE process (one host thread driving a renderer per GPU, as backends/cuda does for
  * CRT_CUDA_DEVICES): from now on `src` resolves its tiles into `dst`'s full frame; peer access between the two
  * devices is enabled if they differ. Both must be initialized with the same size; crtc_initialize undoes it. */

@@ -76,6 +76,11 @@ cudaError_t cudaFreeHost(void *p)
     std::free(p);
     return cudaSuccess;
 }
+cudaError_t cudaHostGetDevicePointer(void **dev, void *host, unsigned int)
+{
+    *dev = host;
+    return cudaSuccess;
+}
 cudaError_t cudaHostRegister(void *, size_t, unsigned int)
 {
     return cudaSuccess;

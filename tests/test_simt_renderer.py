@@ -176,9 +176,13 @@ def test_frames_in_flight_sharding_and_shadow_order_on_the_emulated_renderer(mod
             r.render_async(*args, True, 2)
             r.render_async(*args, False, 1)
             got += r.sync()[0].num_rays
+        # (the emulation runs the ranks one after the other: the assembling rank's wait for the others' completion flags
+        # comes after they have rendered; on GPUs the ranks run side by side and the wait kernel simply spins)
+        for rank in (1, 0):
+            state["rank"] = rank
             frames_[rank].submit()
             assert frames_[rank].finish() == (rank == 0)
-        assert got == rays and state["barriers"] == 2
+        assert got == rays and state["barriers"] == 2  # (one per PeerFrame constructor: the frame is mapped everywhere)
         assert (ranks[0].read_accum().view(np.uint32) == want.view(np.uint32)).all() and (ranks[0].read_img() == want_img).all()
         ranks[1].import_frame(None)
     finally:
