@@ -629,9 +629,13 @@ def main():
         return e0.elapsed_time(e1), totals.num_rays, stage_acc, launches
 
     # ---- device-timed region: inputs resident in HBM, no readback; `repeats` repetitions of K steps ----
+    # The first repetition records a CUDA event after every launch (the per-stage times the roofline needs); the others —
+    # and the frame-by-frame and end-to-end regions — only at the start and the end of a frame: the 28 event records of a
+    # frame cost ~0.07 ms (0.8 % of a full C2 frame, 5.5 % of a 1/8 shard's; profiles/r2_experiments.md).
     reps = []
     with ClockSampler(local_rank) as clocks:
-        for _ in range(repeats):
+        for rep in range(repeats):
+            gpu.set_option("stage_events", 1 if rep == 0 else 0)
             reps.append(timed_region(frames_in_flight))
     clock_summary = clocks.summary()
     # frame by frame (one frame per wavefront) on the device clock as well, for N > 1: what a camera that moves every
@@ -678,21 +682,27 @@ def main():
     if world > 1:
         barrier()
         if rank == 0:
-            solo = RenderCUDA(local_rank, max_depth=MAX_DEPTH, stream=stream.cuda_stream)
-            solo.initialize(WIDTH, HEIGHT)
-            solo.set_scene(scene)
-            done = 0
-            while done < f - 1:  # the same frame ids 0 .. f-1 (accumulation never restarted), in wavefronts of <= 16 frames
-                nb = min(16, f - 1 - done)
-                solo.render_async(*view, done == 0, nb)
-                solo.sync()
-                done += nb
-            st_solo = solo.render(*view, f == 1, False)
-            same_accum = bool(np.array_equal(solo.read_accum().view(np.uint32), gpu.read_accum().view(np.uint32)))
-            same_img = bool(np.array_equal(solo.read_img(), gpu.read_img()))
-            mgpu_check = {"mgpu_bit_identical": bool(same_accum and same_img and int(st_solo.num_rays) == int(last_rays_all)),
-                          "accum": same_accum, "img": same_img, "frames_accumulated": f,
-                          "rays_last_frame": [int(last_rays_all), int(st_solo.num_rays)]}
+            try:
+                solo = RenderCUDA(local_rank, max_depth=MAX_DEPTH, stream=stream.cuda_stream)
+                solo.initialize(WIDTH, HEIGHT)
+                solo.set_scene(scene)
+                # the same frame ids 0 .. f-1 (accumulation never restarted), in wavefronts of at most ~32 M paths
+                per_wave = max(1, min(16, (32 << 20) // max(1, WIDTH * HEIGHT * SPP)))
+                done = 0
+                while done < f - 1:
+                    nb = min(per_wave, f - 1 - done)
+                    solo.render_async(*view, done == 0, nb)
+                    solo.sync()
+                    done += nb
+                st_solo = solo.render(*view, f == 1, False)
+                same_accum = bool(np.array_equal(solo.read_accum().view(np.uint32), gpu.read_accum().view(np.uint32)))
+                same_img = bool(np.array_equal(solo.read_img(), gpu.read_img()))
+                mgpu_check = {"mgpu_bit_identical": bool(same_accum and same_img and int(st_solo.num_rays) == int(last_rays_all)),
+                              "accum": same_accum, "img": same_img, "frames_accumulated": f,
+                              "rays_last_frame": [int(last_rays_all), int(st_solo.num_rays)]}
+            except Exception as e:  # (e.g. out of memory: the check must not cost the line its measurements)
+                mgpu_check = {"mgpu_bit_identical": None, "mgpu_check_error": f"{type(e).__name__}: {e}"[:300]}
+                solo = None
             del solo
         barrier()
 
@@ -737,7 +747,8 @@ def main():
                              f"streams through every bounce (L2 126 MB); scene = {gpu.scene_info()['node_bytes'] / 1e6:.0f} MB "
                              f"nodes + {2 * gpu.scene_info()['triangle_bytes'] / 1e6:.0f} MB triangle/shading records"},
             # value / ms_per_step are the MEDIAN repetition of `repeats` repetitions of `steps` frames each
-            "dispersion": {"repeats": len(rep_ms), "of": "the device-timed region, repeated",
+            "dispersion": {"repeats": len(rep_ms), "of": "the device-timed region, repeated (repetition 1 with a CUDA event after every launch, "
+                                                          "for the stage times; the others with frame start / end events only)",
                            "ms_per_step": {"min": min(rep_ms) / args.steps, "median": elapsed_ms / args.steps, "max": max(rep_ms) / args.steps},
                            "value": {"min": min(rep_value), "median": value, "max": max(rep_value)},
                            "e2e_value": {"min": min(e2e_value), "median": e2e_value[e2e_med], "max": max(e2e_value), "repeats": len(e2e_ms)}},

@@ -239,12 +239,20 @@ CRT_HD float byte_unit(uint32_t packed, int j, uint32_t one)
 // Intersects the 8 quantised child boxes of one node. Returns the node's child group in `cur`
 // (x = child_base, y = hit bits of inner children | imask) and its triangle group in `tri`
 // (x = tri_base, y = hit bits of leaf triangles).
+CRT_HD void node_intersect_loaded(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4,
+                                  const TravState &s, uint2 &cur, uint2 &tri);
 CRT_HD void node_intersect(const float4 *__restrict__ nodes, const TravState &s, uint32_t node_index, uint2 &cur,
                            uint2 &tri)
 {
-    const Ray &ray = s.ray;
     const float4 *np = nodes + (size_t)node_index * 5;
-    const float4 n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
+    node_intersect_loaded(np[0], np[1], np[2], np[3], np[4], s, cur, tri);
+}
+// (the five 128-bit words of the node already in registers: k_traverse's TOP variant reads the first levels of the tree
+// from a shared-memory copy)
+CRT_HD void node_intersect_loaded(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4,
+                                  const TravState &s, uint2 &cur, uint2 &tri)
+{
+    const Ray &ray = s.ray;
     const uint32_t e_imask = f2u(n0.w);
     // plane distance = q * ad0 + ob0 with ad0 = 2^e / d, ob0 = (p - o) / d. q enters as
     // qf = 1 + q * 2^-15 (byte_unit), so t = qf * ad + ob with ad = 2^15 ad0 and ob = ob0 - ad.

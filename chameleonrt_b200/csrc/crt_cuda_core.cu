@@ -58,8 +58,12 @@ struct FrameRecord {
         cudaFreeHost(h_counters);
         cudaFreeHost(h_trav);
     }
+    bool all_stages = true;  // false: only the first and the last mark of a frame are recorded (option "stage_events" = 0)
     void mark(cudaStream_t s, int stage_ended)
     {
+        if (!all_stages && stage_ended != -1 && stage_ended != kStResolve) {
+            return;
+        }
         if (num_events >= events.size()) {
             cudaEvent_t e;
             CUDA_CHECK(cudaEventCreate(&e));
@@ -88,6 +92,7 @@ struct crtc_renderer {
     bool ploc_tail = true;  // the last rounds of PLOC in one block (k_ploc_tail); off only to test that the tree is the same
     bool count_traversal = false;
     int refill_idle = crt::kRefillIdle;  // idle lanes that trigger a refill of the traversal warps
+    bool bvh_top_smem = false;           // option "bvh_top_smem": the first 73 BVH nodes read from a shared-memory copy (measured: no gain)
     int tri_pass_defer = 16;             // 0 / 16 (default) / 24: pooled pairs a triangle pass waits for (kernels.cuh)
     // The shade queue bucketed by material id before k_shade (k_queue_hist / k_queue_scatter): 0 = off (default),
     // 1 = from the first bounce on (primary hits keep their screen order), 2 = every shade launch. Same image.
@@ -331,6 +336,10 @@ struct crtc_renderer {
             cudaGetLastError();
         }
     }
+    // Option "stage_events": 1 (default) = a CUDA event after every launch, for the per-stage times of
+    // crtc_get_stage_times; 0 = only at the start and the end of a frame (the stage times then read 0 except [6], the
+    // whole frame; with a 1/8 shard per GPU the 27 event records are a measurable part of a 2 ms frame).
+    bool stage_events = true;
     bool pin_host_buffers = true;  // option "pin_host_buffers"
     bool pin_repeated_reads = false;  // option "pin_read_img": crtc_read_img page-locks its destination too (a frame loop)
 
@@ -363,6 +372,11 @@ struct crtc_renderer {
             trav_grid = (unsigned)(sms * std::max(1, per_sm));
         }
         const int sched = (refill_idle & 0xff) | (frame_far_first ? 0x100 : 0);
+        if (bvh_top_smem && !count_traversal && tri_pass_defer == 16) {  // experiment (kernels.cuh: TOP), default scheduling only
+            crt::k_traverse<false, 16, true><<<trav_grid, crt::kTravBlock, 0, stream>>>(sc, ps, queue, count_closest, count_any, work_counter, sched,
+                                                                                         (uint32_t)scene_info[1]);
+            return;
+        }
         // (one instantiation per variant, so that the default kernel's code does not change with the options)
         const int variant = (count_traversal ? 1 : 0) | (tri_pass_defer == 16 ? 2 : (tri_pass_defer == 24 ? 4 : 0));
         switch (variant) {
@@ -734,6 +748,7 @@ struct crtc_renderer {
         FrameRecord &rec = *in_flight.back();
         rec.num_events = 0;
         rec.launches = 0;
+        rec.all_stages = stage_events || (any_far_first == 2 && !auto_decided);  // (the shadow-order trial reads the traversal stage)
 
         const bool shared_dst = frame_exported && world_size > 1, shared_src = peer_accum_full != nullptr && !frame_exported;
         if (shared_dst || shared_src) {
@@ -835,7 +850,7 @@ struct crtc_renderer {
             for (int s = 0; s < kNumStages; ++s) {
                 stage_ms[s] = 0.f;
             }
-            for (size_t i = 1; i < rec.num_events; ++i) {
+            for (size_t i = 1; rec.all_stages && i < rec.num_events; ++i) {
                 float ms = 0.f;
                 CUDA_CHECK(cudaEventElapsedTime(&ms, rec.events[i - 1], rec.events[i]));
                 stage_ms[rec.event_stage[i]] += ms;
@@ -1201,6 +1216,10 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
                 throw std::runtime_error("shade_sort must be 0, 1 or 2");
             }
             r->shade_sort = (int)value;
+        } else if (k == "stage_events") {
+            r->stage_events = value != 0;
+        } else if (k == "bvh_top_smem") {
+            r->bvh_top_smem = value != 0;
         } else if (k == "pin_host_buffers") {
             r->pin_host_buffers = value != 0;
             if (!r->pin_host_buffers) {

@@ -177,11 +177,24 @@ constexpr uint32_t kFetchBatch = 64;
 // are pooled or no lane can descend any further; a lane whose triangle group is still untested waits. Fewer,
 // fuller passes for emptier node phases (DESIGN.md §2 "Warp-level work": 0.571 -> 0.523 in the emulation's cost
 // model at DEFER = 16); same results, since the closest hit does not depend on the order of the tests.
-template <bool COUNT, int DEFER = 0>
+// TOP (option "bvh_top_smem", off by default): the first kTopNodes nodes of the tree (BFS order: the root, its children,
+// their children = 1 + 8 + 64) are copied into shared memory at block start and read from there. BASELINE.json's
+// north_star asks for BVH nodes staged in shared memory; measured on the B200 (profiles/r2_experiments.md) it does not
+// pay: those nodes are the hottest lines of the L1 anyway and the copy takes 5.8 KB per block = 47 KB of L1 per SM away.
+constexpr uint32_t kTopNodes = 73;
+template <bool COUNT, int DEFER = 0, bool TOP = false>
 __global__ void __launch_bounds__(kTravBlock, 8)
     k_traverse(DeviceScene sc, PathState ps, const uint32_t *queue, const uint32_t *count_closest_ptr,
-               const uint32_t *count_any_ptr, uint32_t *work_counter, int sched)
+               const uint32_t *count_any_ptr, uint32_t *work_counter, int sched, uint32_t num_nodes = 0)
 {
+    __shared__ float4 sm_top[TOP ? kTopNodes * 5 : 1];
+    const uint32_t top_nodes = TOP ? min(num_nodes, kTopNodes) : 0u;
+    if (TOP) {
+        for (uint32_t i = threadIdx.x; i < top_nodes * 5u; i += blockDim.x) {
+            sm_top[i] = sc.nodes[i];
+        }
+        __syncthreads();
+    }
     // sched: bits 0-7 = idle lanes that trigger a refill; bit 8 = shadow rays visit children far-first
     const int refill_idle = sched & 0xff;
     const bool any_far_first = (sched & 0x100) != 0;
@@ -315,7 +328,19 @@ __global__ void __launch_bounds__(kTravBlock, 8)
                             cnt.nodes++;
                         }
                     }
-                    node_intersect(sc.nodes, st, node_index, st.cur, tri);
+                    if (TOP) {  // (only the five loads differ: the test itself must not be duplicated into two divergent paths)
+                        float4 n0, n1, n2, n3, n4;
+                        if (node_index < top_nodes) {
+                            const float4 *np = sm_top + node_index * 5u;
+                            n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
+                        } else {
+                            const float4 *np = sc.nodes + (size_t)node_index * 5;
+                            n0 = np[0], n1 = np[1], n2 = np[2], n3 = np[3], n4 = np[4];
+                        }
+                        node_intersect_loaded(n0, n1, n2, n3, n4, st, st.cur, tri);
+                    } else {
+                        node_intersect(sc.nodes, st, node_index, st.cur, tri);
+                    }
                 }
                 // triangle phase: the pairs (owner lane, triangle) of this step, 32 per pass. Slots are PULLED by the
                 // testing lanes: an owner only claims a range of slots (one shared-memory atomicAdd on a running

@@ -68,6 +68,11 @@ void crtc_destroy(crtc_renderer *r);
  *                 keep their screen order), 2 = every bounce. Never changes a result. Measured on B200 (round 2): the
  *                 frame gets 10 % LONGER (the sort passes and the scattered path-state accesses cost more than the
  *                 coherence buys); kept as an option, off.
+ *   "stage_events" 1 (default): a CUDA event after every launch feeds crtc_get_stage_times; 0: events only at the start
+ *                 and the end of a frame ([6], the frame time, stays; the other stage times read 0) — 28 event records cost
+ *                 ~0.07 ms per frame, which matters when a GPU renders a 1/8 shard in 2 ms. May be changed between frames.
+ *   "pin_host_buffers" 1 (default): the caller's img buffer is page-locked on first readback (cudaHostRegister);
+ *   "pin_read_img" 1: crtc_read_img page-locks its destination too (a frame loop reading into one buffer). Default 0.
  *   "bvh_builder" where crtc_set_scene builds the BVH8: 0 = on the host (binned SAH, the default); on the device
  *                 (chameleonrt_b200/csrc/bvh8_device.cuh): 1 = PLOC (mutual nearest neighbours in Morton order),
  *                 2 = LBVH (Karras), both followed by the host builder's 8-wide collapse — a much shorter set_scene
