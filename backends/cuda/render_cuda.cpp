@@ -77,6 +77,7 @@ RenderCUDA::RenderCUDA()
             check(crtc_set_option(r, "bvh_builder", env_or("CRT_CUDA_BVH_BUILDER", 0)));  // 1 / 2 = build on the device (crt_cuda.h)
             check(crtc_set_option(r, "any_far_first", env_or("CRT_CUDA_ANY_FAR_FIRST", 2)));  // crt_cuda.h; 2 = per scene
             check(crtc_set_option(r, "shade_sort", env_or("CRT_CUDA_SHADE_SORT", 0)));  // 1 / 2 = shade queue bucketed by material
+            check(crtc_set_option(r, "hw_textures", env_or("CRT_CUDA_HW_TEXTURES", 0)));  // 1 = texels through cudaTextureObject_t (crt_cuda.h)
             check(crtc_set_option(r, "stage_events", env_or("CRT_CUDA_STAGE_EVENTS", 1)));  // 0 = no per-stage timings (crt_cuda_get_stats reads 0)
         }
     } catch (...) {

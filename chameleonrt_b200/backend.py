@@ -110,7 +110,7 @@ class RenderCUDA:
         # developer knobs of the traversal kernels (defaults are the tuned values)
         for env, key in (("CRT_CUDA_REFILL_IDLE", "refill_idle"), ("CRT_CUDA_ANY_FAR_FIRST", "any_far_first"),
                          ("CRT_CUDA_PLOC_RADIUS", "bvh_ploc_radius"), ("CRT_CUDA_TRI_PASS_DEFER", "tri_pass_defer"),
-                         ("CRT_CUDA_SHADE_SORT", "shade_sort")):
+                         ("CRT_CUDA_SHADE_SORT", "shade_sort"), ("CRT_CUDA_HW_TEXTURES", "hw_textures")):
             if os.environ.get(env):
                 self._check(self.lib.crtc_set_option(self.h, key.encode(), int(os.environ[env])))
         # CRT_CUDA_OPTIONS="key=value,key=value": any crtc_set_option key (experiments, profiling runs)

@@ -147,6 +147,66 @@ struct crtc_renderer {
     DeviceBuffer<float4> d_nodes, d_tris, d_shade, d_materials, d_lights;
     DeviceBuffer<uint32_t> d_texels;
     DeviceBuffer<crt::DevTex> d_tex;
+    // option "hw_textures": one CUDA array + texture object per scene texture (wrap, linear, normalised coordinates, sRGB
+    // decode in the texture unit — the reference's OptiX backend, backends/optix/optix_utils.cpp:60-85)
+    bool hw_textures = false;
+    std::vector<cudaArray_t> tex_arrays;
+    std::vector<cudaTextureObject_t> tex_objects;
+    DeviceBuffer<unsigned long long> d_tex_objects;
+    void release_hw_textures()
+    {
+        for (cudaTextureObject_t t : tex_objects) {
+            cudaDestroyTextureObject(t);
+        }
+        for (cudaArray_t a : tex_arrays) {
+            cudaFreeArray(a);
+        }
+        tex_objects.clear();
+        tex_arrays.clear();
+    }
+    void build_hw_textures(const crt_scene_t *scene)
+    {
+        release_hw_textures();
+        if (!hw_textures || scene->num_textures == 0) {
+            d_tex_objects.release();
+            return;
+        }
+        std::vector<uchar4> rgba;
+        for (uint32_t i = 0; i < scene->num_textures; ++i) {
+            const crt_image_t &im = scene->textures[i];  // (shape checked by convert_shading_inputs / flatten_scene)
+            const size_t n = (size_t)im.width * im.height;
+            rgba.assign(n, make_uchar4(0, 0, 0, 0));  // channels the image lacks read as 0 (texture2d.ih:13-27)
+            for (size_t px = 0; px < n; ++px) {
+                unsigned char c[4] = {0, 0, 0, 0};
+                for (int k = 0; k < im.channels; ++k) {
+                    c[k] = im.data[px * im.channels + k];
+                }
+                rgba[px] = make_uchar4(c[0], c[1], c[2], c[3]);
+            }
+            const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+            cudaArray_t arr = nullptr;
+            CUDA_CHECK(cudaMallocArray(&arr, &fmt, (size_t)im.width, (size_t)im.height));
+            tex_arrays.push_back(arr);
+            CUDA_CHECK(cudaMemcpy2DToArrayAsync(arr, 0, 0, rgba.data(), (size_t)im.width * 4, (size_t)im.width * 4, (size_t)im.height,
+                                                cudaMemcpyHostToDevice, stream));
+            CUDA_CHECK(cudaStreamSynchronize(stream));  // `rgba` is reused
+            cudaResourceDesc res = {};
+            res.resType = cudaResourceTypeArray;
+            res.res.array.array = arr;
+            cudaTextureDesc td = {};
+            td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;
+            td.filterMode = cudaFilterModeLinear;
+            td.readMode = cudaReadModeNormalizedFloat;
+            td.sRGB = im.color_space == CRT_COLOR_SPACE_SRGB ? 1 : 0;
+            td.normalizedCoords = 1;
+            cudaTextureObject_t obj = 0;
+            CUDA_CHECK(cudaCreateTextureObject(&obj, &res, &td, nullptr));
+            tex_objects.push_back(obj);
+        }
+        static_assert(sizeof(cudaTextureObject_t) == sizeof(unsigned long long), "texture handles are 64-bit");
+        d_tex_objects.upload(reinterpret_cast<const unsigned long long *>(tex_objects.data()), tex_objects.size(), stream);
+        CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
     uint32_t num_lights = 0;
     std::vector<uint32_t> leaf_flat_ids;  // host copy: leaf-order triangle -> flattened prim id
     double scene_info[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // crtc_get_scene_info
@@ -346,6 +406,7 @@ struct crtc_renderer {
     ~crtc_renderer()
     {
         unpin_img();
+        release_hw_textures();
         close_peer_frame();
         in_flight.clear();
         record_pool.clear();
@@ -447,6 +508,7 @@ struct crtc_renderer {
         sc.lights = d_lights.ptr;
         sc.texels = d_texels.ptr;
         sc.tex = d_tex.ptr;
+        sc.tex_objects = d_tex_objects.ptr;
         sc.num_lights = num_lights;
         sc.float_one = 0x3F800000u;
         return sc;
@@ -662,6 +724,7 @@ struct crtc_renderer {
         }
         d_tex.upload(tex.data(), tex.size(), stream);
         CUDA_CHECK(cudaStreamSynchronize(stream));
+        build_hw_textures(scene);
         spp = std::max<uint32_t>(1u, hs.samples_per_pixel);
         have_scene = true;
         scene_info[0] = (double)num_tris;
@@ -786,7 +849,11 @@ struct crtc_renderer {
                     rec.launches += sort_shade_queue(sc, ps, qin, b, npaths);
                     qin = d_queue_sorted.ptr;
                 }
-                crt::k_shade<<<g128, 128, 0, stream>>>(sc, ps, qin, qout, b, max_depth);
+                if (sc.tex_objects) {
+                    crt::k_shade<true><<<g128, 128, 0, stream>>>(sc, ps, qin, qout, b, max_depth);
+                } else {
+                    crt::k_shade<false><<<g128, 128, 0, stream>>>(sc, ps, qin, qout, b, max_depth);
+                }
                 rec.mark(stream, kStShade);
                 const bool last = b + 1 == max_depth;
                 launch_traverse(sc, ps, qout, last ? nullptr : ps.counters + crt::kCntQueue + b + 1,
@@ -1216,6 +1283,8 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value)
                 throw std::runtime_error("shade_sort must be 0, 1 or 2");
             }
             r->shade_sort = (int)value;
+        } else if (k == "hw_textures") {
+            r->hw_textures = value != 0;  // takes effect at the next crtc_set_scene
         } else if (k == "stage_events") {
             r->stage_events = value != 0;
         } else if (k == "bvh_top_smem") {
@@ -1274,6 +1343,8 @@ int crtc_get_option(crtc_renderer *r, const char *key, int64_t *value)
             *value = r->bvh_threads;
         } else if (k == "tri_pass_defer") {
             *value = r->tri_pass_defer;
+        } else if (k == "hw_textures") {
+            *value = r->hw_textures ? 1 : 0;
         } else if (k == "shade_sort") {
             *value = r->shade_sort;
         } else if (k == "bvh_builder") {

@@ -52,6 +52,7 @@ struct DeviceScene {
     const float4 *lights;     // 5 per light (QuadLight, util/lights.h:6-18)
     const uint32_t *texels;
     const DevTex *tex;
+    const unsigned long long *tex_objects;  // cudaTextureObject_t per texture (option "hw_textures"), else null
     uint32_t num_lights;
     uint32_t float_one;  // 0x3F800000 as a run-time value (bvh8_traverse.h: byte_unit)
 };
@@ -505,6 +506,7 @@ __global__ void __launch_bounds__(kTravBlock, 8)
 // (A grid-stride form for the thin queues of the late bounces was measured in round 2 and dropped: those launches take
 // ~49 us whatever the grid, and ncu shows why — 12 no-instruction stalls per issued instruction: a warp's first walk
 // through this kernel's ~4000 executed instructions is a chain of instruction-cache misses.)
+template <bool HWTEX>  // option "hw_textures": texels through cudaTextureObject_t (shade_math.cuh: TexSource)
 __global__ void __launch_bounds__(128, 6) k_shade(DeviceScene sc, PathState ps, const uint32_t *queue_in,
                                                uint32_t *queue_out, int bounce, int max_depth)
 {
@@ -547,7 +549,8 @@ __global__ void __launch_bounds__(128, 6) k_shade(DeviceScene sc, PathState ps, 
                 uv.y = s1.y * bw + s1.w * h.y + s2.y * h.z;
             }
             DisneyMaterial mat;
-            unpack_material(mat, sc.materials, material_id, uv, sc.texels, sc.tex);
+            const TexSource tex_source{sc.texels, sc.tex, sc.tex_objects};
+            unpack_material<HWTEX>(mat, sc.materials, material_id, uv, tex_source);
             // render_embree.ispc:296-300
             float3 v_x, v_y;
             if (mat.specular_transmission == 0.f && dot(w_o, normal) < 0.f) {

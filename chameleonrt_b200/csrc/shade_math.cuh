@@ -581,40 +581,69 @@ CRT_D float3 sample_disney_brdf(const DisneyMaterial &mat, const float3 n, const
 }
 
 // ---- render_embree.ispc:66-103 ----
-CRT_D float textured_scalar_param(float x, const float2 uv, const uint32_t *__restrict__ texels,
-                                  const DevTex *__restrict__ tex)
+// Where texels come from: the RGBA8 arena + descriptors of the software bilinear filter (texture_rgba: the reference's
+// texture2d.ih, bit for bit), or — option "hw_textures", template parameter HW — one cudaTextureObject_t per texture
+// (wrap addressing, linear filtering, normalised coordinates, sRGB decode in the texture unit: what the reference's
+// OptiX backend does, backends/optix/optix_utils.cpp:60-85). The hardware path differs from the Embree path in the
+// filter weights (8-bit fixed point) and in not re-quantising the linearised texels to 8 bits (render_embree.cpp:96-103
+// does), so it has its own, looser parity tolerance (tests/test_z_new_gpu_paths.py).
+struct TexSource {
+    const uint32_t *texels;
+    const DevTex *tex;
+    const unsigned long long *objects;  // cudaTextureObject_t per texture (HW only)
+};
+template <bool HW>
+CRT_D float4 texture_sample(const TexSource &ts, uint32_t tex_id, const float2 uv)
+{
+#if defined(__CUDA_ARCH__)
+    if (HW) {
+        return tex2D<float4>((cudaTextureObject_t)__ldg(ts.objects + tex_id), uv.x, uv.y);
+    }
+#endif
+    return texture_rgba(ts.texels, ts.tex[tex_id], uv);
+}
+template <bool HW>
+CRT_D float textured_scalar_param(float x, const float2 uv, const TexSource &ts)
 {
     const uint32_t mask = __float_as_uint(x);
     if (mask & 0x80000000u) {
         const uint32_t tex_id = mask & 0x1fffffffu;
         const uint32_t channel = (mask >> 29) & 0x3u;
-        return channel_of(texture_rgba(texels, tex[tex_id], uv), channel);
+        return channel_of(texture_sample<HW>(ts, tex_id, uv), channel);
     }
     return x;
 }
+template <bool HW>
 CRT_D void unpack_material(DisneyMaterial &mat, const float4 *__restrict__ materials, uint32_t id, const float2 uv,
-                           const uint32_t *__restrict__ texels, const DevTex *__restrict__ tex)
+                           const TexSource &ts)
 {
     const float4 m0 = __ldg(materials + 4 * id), m1 = __ldg(materials + 4 * id + 1),
                  m2 = __ldg(materials + 4 * id + 2), m3 = __ldg(materials + 4 * id + 3);
     const uint32_t mask = __float_as_uint(m0.x);
     if (mask & 0x80000000u) {
-        const float4 c = texture_rgba(texels, tex[mask & 0x1fffffffu], uv);
+        const float4 c = texture_sample<HW>(ts, mask & 0x1fffffffu, uv);
         mat.base_color = mk3(c.x, c.y, c.z);
     } else {
         mat.base_color = mk3(m0.x, m0.y, m0.z);
     }
-    mat.metallic = textured_scalar_param(m0.w, uv, texels, tex);
-    mat.specular = textured_scalar_param(m1.x, uv, texels, tex);
-    mat.roughness = textured_scalar_param(m1.y, uv, texels, tex);
-    mat.specular_tint = textured_scalar_param(m1.z, uv, texels, tex);
-    mat.anisotropy = textured_scalar_param(m1.w, uv, texels, tex);
-    mat.sheen = textured_scalar_param(m2.x, uv, texels, tex);
-    mat.sheen_tint = textured_scalar_param(m2.y, uv, texels, tex);
-    mat.clearcoat = textured_scalar_param(m2.z, uv, texels, tex);
-    mat.clearcoat_gloss = textured_scalar_param(m2.w, uv, texels, tex);
-    mat.ior = textured_scalar_param(m3.x, uv, texels, tex);
-    mat.specular_transmission = textured_scalar_param(m3.y, uv, texels, tex);
+    mat.metallic = textured_scalar_param<HW>(m0.w, uv, ts);
+    mat.specular = textured_scalar_param<HW>(m1.x, uv, ts);
+    mat.roughness = textured_scalar_param<HW>(m1.y, uv, ts);
+    mat.specular_tint = textured_scalar_param<HW>(m1.z, uv, ts);
+    mat.anisotropy = textured_scalar_param<HW>(m1.w, uv, ts);
+    mat.sheen = textured_scalar_param<HW>(m2.x, uv, ts);
+    mat.sheen_tint = textured_scalar_param<HW>(m2.y, uv, ts);
+    mat.clearcoat = textured_scalar_param<HW>(m2.z, uv, ts);
+    mat.clearcoat_gloss = textured_scalar_param<HW>(m2.w, uv, ts);
+    mat.ior = textured_scalar_param<HW>(m3.x, uv, ts);
+    mat.specular_transmission = textured_scalar_param<HW>(m3.y, uv, ts);
+}
+// (the software path under its round-1 signature: the test-only host builds call it)
+CRT_D void unpack_material(DisneyMaterial &mat, const float4 *__restrict__ materials, uint32_t id, const float2 uv,
+                           const uint32_t *__restrict__ texels, const DevTex *__restrict__ tex)
+{
+    const TexSource ts{texels, tex, nullptr};
+    unpack_material<false>(mat, materials, id, uv, ts);
 }
 
 // render_embree.ispc:183-196

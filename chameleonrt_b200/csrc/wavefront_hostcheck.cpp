@@ -314,7 +314,7 @@ struct HostWavefront {
             traverse(ps, ps.queue[0], counters[crt::kCntQueue], 0, far_first);
             for (int b = 0; b < max_depth; ++b) {
                 uint32_t *qin = ps.queue[b & 1], *qout = ps.queue[(b + 1) & 1];
-                launch(npaths, [&] { crt::k_shade(sc, ps, qin, qout, b, max_depth); });
+                launch(npaths, [&] { crt::k_shade<false>(sc, ps, qin, qout, b, max_depth); });
                 const bool last = b + 1 == max_depth;
                 traverse(ps, qout, last ? 0u : counters[crt::kCntQueue + b + 1], counters[crt::kCntShadow + b], far_first);
                 launch(npaths, [&] { crt::k_nee_resolve(ps, qin, b); });

@@ -68,6 +68,13 @@ void crtc_destroy(crtc_renderer *r);
  *                 keep their screen order), 2 = every bounce. Never changes a result. Measured on B200 (round 2): the
  *                 frame gets 10 % LONGER (the sort passes and the scattered path-state accesses cost more than the
  *                 coherence buys); kept as an option, off.
+ *   "hw_textures" 0 (default): textures are filtered in software with the reference's own arithmetic (texture2d.ih:
+ *                 float->int truncation of texel coordinates, wrap by modulo, bilinear weights in float, over the 8-bit
+ *                 LINEARISED texels render_embree.cpp:96-103 produces) — bit-level parity with the Embree backend.
+ *                 1: one cudaTextureObject_t per texture (wrap, linear, normalised coordinates, sRGB decode in the texture
+ *                 unit), as the reference's OptiX backend does (backends/optix/optix_utils.cpp:60-85): 8-bit fixed-point
+ *                 filter weights and no re-quantisation of the linearised texels, hence a looser parity with the Embree
+ *                 path (dark sRGB texels are not crushed to 0). Takes effect at the next crtc_set_scene.
  *   "stage_events" 1 (default): a CUDA event after every launch feeds crtc_get_stage_times; 0: events only at the start
  *                 and the end of a frame ([6], the frame time, stays; the other stage times read 0) — 28 event records cost
  *                 ~0.07 ms per frame, which matters when a GPU renders a 1/8 shard in 2 ms. May be changed between frames.

@@ -49,7 +49,7 @@ def build(force: bool = False) -> str:
     gen = os.path.join(OUT, "crt_cuda_core_simt.cpp")
     with open(gen, "w") as f:
         f.write('#include "simt_env.h"\n' + translate(open(os.path.join(CSRC, "crt_cuda_core.cu")).read().replace(
-            '"../../include/crt_cuda.h"', f'"{ROOT}/include/crt_cuda.h"'), 20))
+            '"../../include/crt_cuda.h"', f'"{ROOT}/include/crt_cuda.h"'), 21))
     # the device set_scene driver is a header of the same translation unit: its translated copy sits next to the
     # generated source, where the quoted include finds it first
     with open(os.path.join(OUT, "scene_device_build.cuh"), "w") as f:

@@ -76,6 +76,24 @@ cudaError_t cudaFreeHost(void *p)
     std::free(p);
     return cudaSuccess;
 }
+// texture objects (option "hw_textures") have no host emulation: the option fails cleanly here
+cudaError_t cudaMallocArray(cudaArray_t *, const cudaChannelFormatDesc *, size_t, size_t, unsigned int) { return cudaErrorNotSupported; }
+cudaError_t cudaFreeArray(cudaArray_t) { return cudaSuccess; }
+cudaError_t cudaMemcpy2DToArrayAsync(cudaArray_t, size_t, size_t, const void *, size_t, size_t, size_t, enum cudaMemcpyKind, cudaStream_t)
+{
+    return cudaErrorNotSupported;
+}
+cudaError_t cudaCreateTextureObject(cudaTextureObject_t *, const cudaResourceDesc *, const cudaTextureDesc *, const cudaResourceViewDesc *)
+{
+    return cudaErrorNotSupported;
+}
+cudaError_t cudaDestroyTextureObject(cudaTextureObject_t) { return cudaSuccess; }
+cudaChannelFormatDesc cudaCreateChannelDesc(int x, int y, int z, int w, enum cudaChannelFormatKind f)
+{
+    cudaChannelFormatDesc d;
+    d.x = x, d.y = y, d.z = z, d.w = w, d.f = f;
+    return d;
+}
 cudaError_t cudaHostGetDevicePointer(void **dev, void *host, unsigned int)
 {
     *dev = host;
