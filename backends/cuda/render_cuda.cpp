@@ -15,6 +15,10 @@
 #include <vector>
 #include "crt_cuda.h"
 #include "scene.h"
+#ifndef CRT_CUDA_HEADLESS
+#include <cuda_gl_interop.h>
+#include <cuda_runtime_api.h>
+#endif
 
 static_assert(sizeof(DisneyMaterial) == sizeof(crt_material_t), "DisneyMaterial layout");
 static_assert(sizeof(QuadLight) == sizeof(crt_quad_light_t), "QuadLight layout");
@@ -61,8 +65,11 @@ std::vector<int> devices_from_env()
 }
 }
 
-RenderCUDA::RenderCUDA()
+RenderCUDA::RenderCUDA(bool native_display_) : native_display(native_display_)
 {
+#ifdef CRT_CUDA_HEADLESS
+    native_display = false;
+#endif
     // The plugin API has no option channel: knobs come from the environment.
     const std::vector<int> devices = devices_from_env();
     try {
@@ -89,8 +96,60 @@ RenderCUDA::RenderCUDA()
     renderer = renderers[0];
 }
 
+#ifndef CRT_CUDA_HEADLESS
+namespace {
+void check_cuda(cudaError_t e, const char *what)
+{
+    if (e != cudaSuccess) {
+        throw std::runtime_error(std::string("crt_cuda: ") + what + ": " + cudaGetErrorString(e));
+    }
+}
+}
+
+// render_optix.cpp:104-121: an RGBA8 texture of the framebuffer's size, registered with CUDA
+void RenderCUDA::create_display_texture()
+{
+    release_display_texture();
+    glGenTextures(1, &gl_display_texture);
+    glBindTexture(GL_TEXTURE_2D, gl_display_texture);
+    glTexImage2D(GL_TEXTURE_2D, 0, GL_RGBA8, fb_dims.x, fb_dims.y, 0, GL_RGBA, GL_UNSIGNED_BYTE, nullptr);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MIN_FILTER, GL_NEAREST);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_MAG_FILTER, GL_NEAREST);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_S, GL_CLAMP_TO_EDGE);
+    glTexParameteri(GL_TEXTURE_2D, GL_TEXTURE_WRAP_T, GL_CLAMP_TO_EDGE);
+    check_cuda(cudaGraphicsGLRegisterImage(&cu_display_texture, gl_display_texture, GL_TEXTURE_2D, cudaGraphicsRegisterFlagsWriteDiscard),
+               "cudaGraphicsGLRegisterImage");
+}
+
+void RenderCUDA::release_display_texture()
+{
+    if (cu_display_texture) {
+        cudaGraphicsUnregisterResource(cu_display_texture);
+        cu_display_texture = nullptr;
+    }
+    if (gl_display_texture != GLuint(-1)) {
+        glDeleteTextures(1, &gl_display_texture);
+        gl_display_texture = GLuint(-1);
+    }
+}
+
+// render_optix.cpp:410-426: map the texture, copy the frame into its array device to device, unmap
+void RenderCUDA::present_native()
+{
+    check_cuda(cudaGraphicsMapResources(1, &cu_display_texture), "cudaGraphicsMapResources");
+    cudaArray_t array = nullptr;
+    check_cuda(cudaGraphicsSubResourceGetMappedArray(&array, cu_display_texture, 0, 0), "cudaGraphicsSubResourceGetMappedArray");
+    const int rc = crtc_copy_img_to_array(renderers[0], array);  // (every GPU's tiles are in renderers[0]'s frame by then)
+    check_cuda(cudaGraphicsUnmapResources(1, &cu_display_texture), "cudaGraphicsUnmapResources");
+    check(rc);
+}
+#endif
+
 RenderCUDA::~RenderCUDA()
 {
+#ifndef CRT_CUDA_HEADLESS
+    release_display_texture();
+#endif
     // the renderers that write into renderers[0]'s frame go first
     for (size_t i = renderers.size(); i-- > 0;) {
         crtc_destroy(renderers[i]);
@@ -112,6 +171,11 @@ void RenderCUDA::initialize(const int fb_width, const int fb_height)
     for (size_t i = 1; i < renderers.size(); ++i) {
         check(crtc_share_frame(renderers[0], renderers[i]));
     }
+#ifndef CRT_CUDA_HEADLESS
+    if (native_display) {
+        create_display_texture();
+    }
+#endif
 }
 
 void RenderCUDA::set_scene(const Scene &scene)
@@ -237,6 +301,11 @@ RenderStats RenderCUDA::render(const glm::vec3 &pos,
             }
         }
         ++frames_since_scene;
+#ifndef CRT_CUDA_HEADLESS
+        if (native_display) {
+            present_native();
+        }
+#endif
         if (readback) {
             check(crtc_read_img(renderers[0], img.data()));
         }
@@ -255,6 +324,11 @@ RenderStats RenderCUDA::render(const glm::vec3 &pos,
                       readback ? 1 : 0,
                       img.data(),
                       &s));
+#ifndef CRT_CUDA_HEADLESS
+    if (native_display) {
+        present_native();
+    }
+#endif
     RenderStats stats;
     stats.render_time = s.render_time;
     stats.rays_per_second = s.rays_per_second;

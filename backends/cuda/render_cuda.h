@@ -13,9 +13,20 @@
 #include <vector>
 #include "render_backend.h"
 
+#ifndef CRT_CUDA_HEADLESS
+// interactive build: the display is the reference's GLDisplay, and a renderer that fills
+// GLNativeRenderer::gl_display_texture is shown without a trip through host memory (util/display/gldisplay.h:35-37,
+// gldisplay.cpp:107-110)
+#include "display/gldisplay.h"
+using RenderCUDABase = GLNativeRenderer;
+struct cudaGraphicsResource;
+#else
+using RenderCUDABase = RenderBackend;
+#endif
+
 struct crtc_renderer;
 
-struct RenderCUDA : RenderBackend {
+struct RenderCUDA : RenderCUDABase {
     // One renderer per GPU (CRT_CUDA_DEVICES, default: the single device CRT_CUDA_DEVICE). Renderer i owns the image
     // tiles with tile_id % N == i (the reference's tile ids, render_embree.cpp:178-180) and resolves them straight
     // into the frame of renderers[0] over NVLink (crtc_share_frame), which is the one `img` is read from.
@@ -25,8 +36,17 @@ struct RenderCUDA : RenderBackend {
     bool native_display = false;
     int frames_since_scene = 0;  // multi-renderer mode: the first frames after set_scene are rendered blocking
 
-    RenderCUDA();
+    // native_display: the Display this plugin made is a GLDisplay (render_cuda_plugin.cpp), so frames go to its texture
+    // through CUDA-GL interop and `img` is only read back when the application asks (readback_framebuffer: screenshots,
+    // main.cpp:309-314), as backends/optix/render_optix.cpp:404-430 does. Always false in headless builds.
+    explicit RenderCUDA(bool native_display = false);
     ~RenderCUDA() override;
+#ifndef CRT_CUDA_HEADLESS
+    cudaGraphicsResource *cu_display_texture = nullptr;  // gl_display_texture registered with CUDA
+    void create_display_texture();
+    void release_display_texture();
+    void present_native();
+#endif
 
     std::string name() override;
     void initialize(const int fb_width, const int fb_height) override;

@@ -46,8 +46,18 @@ struct Hooks {
 #endif
     }
 
-    // img is read back to the host every frame (render_cuda.cpp), so any display works: the Display is not needed
-    static std::unique_ptr<RenderBackend> renderer_for(Display *) { return std::unique_ptr<RenderBackend>(new RenderCUDA()); }
+    // With this plugin's GLDisplay the frame is presented through CUDA-GL interop (render_cuda.cpp: present_native) and
+    // `img` is read back only on request, as backends/optix/render_optix_plugin.cpp:22-26 decides for OptiX; with any
+    // other display (the headless NullDisplay) `img` is read back every frame.
+    static std::unique_ptr<RenderBackend> renderer_for(Display *display)
+    {
+#ifdef CRT_CUDA_HEADLESS
+        (void)display;
+        return std::unique_ptr<RenderBackend>(new RenderCUDA(false));
+#else
+        return std::unique_ptr<RenderBackend>(new RenderCUDA(dynamic_cast<GLDisplay *>(display) != nullptr));
+#endif
+    }
 };
 
 }  // namespace crt_cuda_plugin

@@ -1523,6 +1523,21 @@ int crtc_import_frame(crtc_renderer *r, const void *handles)
     CRTC_TRY({ require_renderer(r); r->import_frame(handles); })
 }
 
+int crtc_copy_img_to_array(crtc_renderer *r, void *cuda_array)
+{
+    CRTC_TRY({ require_renderer(r);
+        if (!cuda_array) {
+            throw std::runtime_error("crtc_copy_img_to_array: array is NULL");
+        }
+        r->make_current();
+        r->frame_wait();
+        CUDA_CHECK(cudaMemcpy2DToArrayAsync(static_cast<cudaArray_t>(cuda_array), 0, 0, r->d_img_full.ptr, (size_t)r->fb_w * 4,
+                                            (size_t)r->fb_w * 4, (size_t)r->fb_h, cudaMemcpyDeviceToDevice, r->stream));
+        CUDA_CHECK(cudaStreamSynchronize(r->stream));
+        r->check_sync_error();
+    })
+}
+
 int crtc_frame_wait(crtc_renderer *r)
 {
     CRTC_TRY({ require_renderer(r); r->frame_wait(); })

@@ -202,6 +202,11 @@ int crtc_frame_wait(crtc_renderer *r);
  * CRT_CUDA_DEVICES): from now on `src` resolves its tiles into `dst`'s full frame; peer access between the two
  * devices is enabled if they differ. Both must be initialized with the same size; crtc_initialize undoes it. */
 int crtc_share_frame(crtc_renderer *dst, crtc_renderer *src);
+/* Presentation without a host round trip: copies the assembled RGBA8 frame, device to device, into
+ * a cudaArray_t (passed as void*: this header needs no CUDA types) — the mapped array of an OpenGL texture registered with
+ * cudaGraphicsGLRegisterImage, as the reference's OptiX backend presents (backends/optix/render_optix.cpp:410-426). The
+ * array must live on this renderer's device and be fb_width x fb_height RGBA8. Returns when the copy has completed. */
+int crtc_copy_img_to_array(crtc_renderer *r, void *cuda_array);
 /* Read the assembled full frame (after crtc_assemble_rank for every rank, after every rank's peer-written
  * frame has completed, or after a world_size==1 render). */
 int crtc_read_img(crtc_renderer *r, uint32_t *img);
