@@ -522,9 +522,18 @@ CRT_D float disney_pdf(const DisneyMaterial &mat, const float3 n, const float3 w
     }
     return (diffuse + microfacet + microfacet_transmission + clear_coat) / n_comp;
 }
-// disney_bsdf.ih:364-429. Consumes exactly three random numbers.
-CRT_D float3 sample_disney_brdf(const DisneyMaterial &mat, const float3 n, const float3 w_o, const float3 v_x,
-                                const float3 v_y, uint32_t &rng, float3 &w_i, float &pdf)
+// disney_bsdf.ih:364-413: the sampling half of sample_disney_brdf (lobe choice + direction). Consumes exactly three
+// random numbers. Returns false where the reference returns early with pdf = 0 and a zero BSDF value (w_i is then the
+// value the reference leaves in it).
+//
+// The lobe is drawn per lane, so a warp executes every lobe's code one after the other at a third of its lanes (round-2
+// source profile of k_shade: 17 % of its instructions at 10.7 of 32 lanes). The three samplers share most of their work —
+// one cosine and one sine of an angle, the normalisation and the change of basis of a local direction, the reflection
+// about the half vector — and only what differs is left inside the per-lobe branches: the angle and the two radial
+// terms. Per lane the operations and their order are exactly those of sample_lambertian_dir / sample_gtr_2_h /
+// sample_gtr_1_h / sample_gtr_2_aniso_h above (bit-identical results: tests/test_shade_host.py).
+CRT_D bool sample_disney_dir(const DisneyMaterial &mat, const float3 n, const float3 w_o, const float3 v_x,
+                             const float3 v_y, uint32_t &rng, float3 &w_i)
 {
     int component;
     if (mat.specular_transmission == 0.f) {
@@ -536,45 +545,79 @@ CRT_D float3 sample_disney_brdf(const DisneyMaterial &mat, const float3 n, const
     }
     const float sx = lcg_randomf(rng);
     const float sy = lcg_randomf(rng);
-    if (component == 0) {
-        w_i = sample_lambertian_dir(n, v_x, v_y, sx, sy);
-    } else if (component == 1) {
-        float3 w_h;
-        const float alpha = fmaxf(0.001f, mat.roughness * mat.roughness);
-        if (mat.anisotropy == 0.f) {
-            w_h = sample_gtr_2_h(n, v_x, v_y, alpha, sx, sy);
-        } else {
-            const float aspect = sqrtf(1.f - mat.anisotropy * 0.9f);
-            w_h = sample_gtr_2_aniso_h(n, v_x, v_y, fmaxf(0.001f, alpha / aspect), fmaxf(0.001f, alpha * aspect), sx,
-                                       sy);
+    const bool aniso = component == 1 && mat.anisotropy != 0.f;
+    // ---- per lobe: the angle, and the radial terms of the local direction (a cos, a sin, z) ----
+    float angle, a = 0.f, z = 0.f;
+    if (component == 0) {  // cos_sample_hemisphere: concentric map
+        const float ux = 2.f * sx - 1.f, uy = 2.f * sy - 1.f;
+        float radius = 0.f, theta = 0.f;
+        if (!(ux == 0.f && uy == 0.f)) {
+            if (fabsf(ux) > fabsf(uy)) {
+                radius = ux;
+                theta = kPi / 4.f * (uy / ux);
+            } else {
+                radius = uy;
+                theta = kPi / 2.f - kPi / 4.f * (ux / uy);
+            }
         }
-        w_i = reflect(neg(w_o), w_h);
-        if (!same_hemisphere(w_o, w_i, n)) {
-            pdf = 0.f;
-            w_i = mk3(0.f);
-            return mk3(0.f);
-        }
-    } else if (component == 2) {
-        const float alpha = lerp(0.1f, 0.001f, mat.clearcoat_gloss);
-        const float3 w_h = sample_gtr_1_h(n, v_x, v_y, alpha, sx, sy);
-        w_i = reflect(neg(w_o), w_h);
-        if (!same_hemisphere(w_o, w_i, n)) {
-            pdf = 0.f;
-            w_i = mk3(0.f);
-            return mk3(0.f);
-        }
+        angle = theta;
+        a = radius;
     } else {
+        angle = 2.f * kPi * sx;  // phi_h (sample_gtr_1_h, sample_gtr_2_h) and x (sample_gtr_2_aniso_h)
+        if (!aniso) {
+            float cos_theta_h_sqr;
+            if (component == 2) {  // sample_gtr_1_h
+                const float alpha = lerp(0.1f, 0.001f, mat.clearcoat_gloss);
+                const float alpha_sqr = alpha * alpha;
+                cos_theta_h_sqr = (1.f - powf(alpha_sqr, 1.f - sy)) / (1.f - alpha_sqr);
+            } else {  // sample_gtr_2_h (reflection and transmission lobes)
+                const float alpha = fmaxf(0.001f, mat.roughness * mat.roughness);
+                cos_theta_h_sqr = (1.f - sy) / (1.f + (alpha * alpha - 1.f) * sy);
+            }
+            z = sqrtf(cos_theta_h_sqr);
+            a = sqrtf(1.f - cos_theta_h_sqr);
+        }
+    }
+    // ---- shared: one cosine, one sine ----
+    const float c = cosf(angle), s = sinf(angle);
+    float3 w;  // comp 0: the sampled direction; others: the half vector
+    if (aniso) {  // sample_gtr_2_aniso_h
         const float alpha = fmaxf(0.001f, mat.roughness * mat.roughness);
-        float3 w_h = sample_gtr_2_h(n, v_x, v_y, alpha, sx, sy);
-        if (dot(w_o, w_h) < 0.f) {
-            w_h = neg(w_h);
+        const float aspect = sqrtf(1.f - mat.anisotropy * 0.9f);
+        const float ax = fmaxf(0.001f, alpha / aspect), ay = fmaxf(0.001f, alpha * aspect);
+        w = normalize(sqrtf(sy / (1.f - sy)) * (ax * c * v_x + ay * s * v_y) + n);
+    } else {
+        // ---- shared: local direction -> normalise -> world ----
+        const float hx = a * c, hy = a * s;
+        const float hz = component == 0 ? sqrtf(fmaxf(0.f, 1.f - hx * hx - hy * hy)) : z;
+        w = to_world(normalize(mk3(hx, hy, hz)), n, v_x, v_y);
+    }
+    if (component == 0) {
+        w_i = w;
+        return true;
+    }
+    if (component != 3) {  // the two reflection lobes
+        w_i = reflect(neg(w_o), w);
+        if (!same_hemisphere(w_o, w_i, n)) {
+            w_i = mk3(0.f);
+            return false;
         }
-        const bool entering = dot(w_o, n) > 0.f;
-        w_i = refract(neg(w_o), w_h, entering ? 1.f / mat.ior : mat.ior);
-        if (all_zero(w_i)) {
-            pdf = 0.f;
-            return mk3(0.f);
-        }
+        return true;
+    }
+    if (dot(w_o, w) < 0.f) {
+        w = neg(w);
+    }
+    const bool entering = dot(w_o, n) > 0.f;
+    w_i = refract(neg(w_o), w, entering ? 1.f / mat.ior : mat.ior);
+    return !all_zero(w_i);
+}
+// disney_bsdf.ih:364-429
+CRT_D float3 sample_disney_brdf(const DisneyMaterial &mat, const float3 n, const float3 w_o, const float3 v_x,
+                                const float3 v_y, uint32_t &rng, float3 &w_i, float &pdf)
+{
+    if (!sample_disney_dir(mat, n, w_o, v_x, v_y, rng, w_i)) {
+        pdf = 0.f;
+        return mk3(0.f);
     }
     pdf = disney_pdf(mat, n, w_o, w_i, v_x, v_y);
     return disney_brdf(mat, n, w_o, w_i, v_x, v_y);
