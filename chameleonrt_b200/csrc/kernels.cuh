@@ -73,7 +73,7 @@ struct PathState {
     float4 *hit;       // t, u, v, bits(leaf-order triangle index | kMiss)
     float4 *thr_rng;   // path_throughput.xyz, bits(rng state)
     float4 *radiance;  // per-sample illum.xyz
-    float4 *nee_T;     // throughput before this bounce's update, bits(flags: 2 = hit (NEE valid), 1 = has shadow ray B)
+    float4 *nee_T;     // throughput before this bounce's update, bits(flags: 4 = missed (environment term pending), 2 = hit (NEE valid), 1 = has shadow ray B)
     float4 *nee_l1;    // light-sample contribution (without throughput)
     float4 *nee_l2;    // BSDF-sample contribution
     float4 *sray_o;    // shadow ray org.xyz, tfar   (indexed by shadow-queue position)
@@ -525,16 +525,13 @@ __global__ void __launch_bounds__(128, 6) k_shade(DeviceScene sc, PathState ps, 
         const float3 dir = mk3(rd.x, rd.y, rd.z);
         const float3 w_o = neg(dir);
         if (tri == kMiss) {
-            // render_embree.ispc:258-262
-            float4 rad = ps.radiance[slot];
-            const float3 c = path_throughput * miss_shader(dir);
-            rad.x = rad.x + c.x;
-            rad.y = rad.y + c.y;
-            rad.z = rad.z + c.z;
-            ps.radiance[slot] = rad;
-            // no NEE at a miss: flags = 0 (k_nee_resolve must not look at hit[], which the merged
-            // traversal launch overwrites with the NEXT bounce's hit before it runs)
-            ps.nee_T[slot] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+            // render_embree.ispc:258-262: illum += path_throughput * miss_shader(dir). The environment lookup (atan2f, acosf:
+            // ~200 instructions that a warp here would execute for its ~6 missing lanes) is left to k_nee_resolve, which adds
+            // this bounce's term to the path's radiance anyway and is memory-bound with issue slots to spare: flags = 4
+            // ("missed": no NEE; k_nee_resolve must not look at hit[], which the merged traversal launch overwrites with
+            // the NEXT bounce's hit before it runs — the ray direction in ray_d[slot] stays, a path that missed does not
+            // continue). Same position in the path's sum as before, so the same bits.
+            ps.nee_T[slot] = make_float4(path_throughput.x, path_throughput.y, path_throughput.z, __uint_as_float(4u));
         } else {
             // render_embree.ispc:264-293 (the ray-independent part was precomputed per triangle)
             hit_p = mk3(ro.x + h.x * dir.x, ro.y + h.x * dir.y, ro.z + h.x * dir.z);
@@ -753,8 +750,16 @@ __global__ void __launch_bounds__(256) k_nee_resolve(PathState ps, const uint32_
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {  // grid-stride, as k_shade
     const uint32_t slot = queue_in[j];
     const float4 T = ps.nee_T[slot];
-    if ((__float_as_uint(T.w) & 2u) == 0u) {
-        continue;  // the path missed at this bounce
+    if (__float_as_uint(T.w) & 4u) {
+        // the path left the scene at this bounce (render_embree.ispc:258-262; deferred here by k_shade)
+        const float4 rd = ps.ray_d[slot];
+        float4 rad = ps.radiance[slot];
+        const float3 c = mk3(T.x, T.y, T.z) * miss_shader(mk3(rd.x, rd.y, rd.z));
+        rad.x = rad.x + c.x;
+        rad.y = rad.y + c.y;
+        rad.z = rad.z + c.z;
+        ps.radiance[slot] = rad;
+        continue;
     }
     float3 illum = mk3(0.f);
     if (ps.vis[2 * slot]) {
