@@ -358,7 +358,7 @@ def kernel_source_sha():
 
 
 def measured_traffic(workload_key):
-    """dram__bytes_read + dram__bytes_write per k_traverse launch from the committed `ncu --set full` capture of THIS
+    """dram__bytes_read + dram__bytes_write per k_traverse launch from the committed ncu capture of THIS
     workload (profiles/traffic_k_traverse.json, written by scripts/update_traffic.py from the .ncu-rep): returned only
     if the capture was taken from the kernel source that is in the tree now; otherwise null and the reason."""
     path = os.path.join(ROOT, "profiles", "traffic_k_traverse.json")
@@ -368,8 +368,8 @@ def measured_traffic(workload_key):
         return None, "no committed ncu capture of this workload"
     if entry.get("kernel_src_sha") != kernel_source_sha():
         return None, f"stale: the committed capture ({entry.get('capture')}) is of an older k_traverse"
-    return entry["dram_bytes_per_launch"], (f"mean over the {entry['launches']} k_traverse launches of one frame, ncu --set full, "
-                                            f"{entry.get('capture')}")
+    return entry["dram_bytes_per_launch"], (f"mean over the {entry['launches']} k_traverse launches of one frame, ncu dram__bytes_read + "
+                                            f"dram__bytes_write, {entry.get('capture')}")
 
 
 def run_workload_probe(args) -> None:
