@@ -631,10 +631,10 @@ struct crtc_renderer {
         uint32_t bvh_nodes = 0, bvh_depth = 0;
         double bvh_ms = 0.0;
         size_t num_tris = 0;
+        // (the plan is cheap — reference checks and counts — and gives the triangle total before anything is allocated)
         crt::FlattenPlan plan;
-        if (bvh_builder != 0) {
-            crt::plan_flatten(scene, plan);
-        }
+        crt::plan_flatten(scene, plan);
+        check_triangle_count(plan.total_tris);
         bool built_on_device = false;
         if (bvh_builder != 0 && plan.total_tris > 0) {
             check_triangle_count(plan.total_tris);

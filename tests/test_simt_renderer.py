@@ -304,3 +304,60 @@ def test_shade_queue_sort_on_the_emulated_renderer(mods):
     import test_z_new_gpu_paths as dev_tests
 
     dev_tests.test_shade_queue_sort_does_not_change_the_image(mods, size=(48, 32), detail=0.2, frames=1, batch=2)
+
+
+def test_triangle_count_limit_is_enforced_before_anything_is_allocated(mods):
+    """k_traverse packs (owner lane, leaf-order triangle index) into 5 + 27 bits: a scene of 2^27 or more flattened triangles
+    is refused by set_scene on both the host and the device path, from the instance / geometry counts alone (ADVICE r1:
+    nothing enforced it, and ~13 GB of records fit a B200)."""
+    from chameleonrt_b200.scene import DisneyMaterial, Geometry, Instance, Mesh, ParameterizedMesh, Scene, default_obj_light
+
+    RenderCUDA = mods[0]
+    n = 1 << 16
+    verts = np.zeros((3, 3), np.float32)
+    verts[1, 0] = verts[2, 1] = 1.0
+    idx = np.tile(np.array([[0, 1, 2]], np.uint32), (n, 1))
+    inst = [Instance(np.eye(4, dtype=np.float32), 0) for _ in range((1 << 27) // n)]  # 2048 x 65536 = 2^27 triangles
+    scene = Scene(meshes=[Mesh([Geometry(verts, idx)])], parameterized_meshes=[ParameterizedMesh(0, [0])], instances=inst,
+                  materials=[DisneyMaterial()], lights=[default_obj_light()])
+    for builder in ("host", "device"):
+        r = RenderCUDA(0, bvh_builder=builder)
+        r.initialize(16, 16)
+        with pytest.raises(RuntimeError, match="at most 2\\^27 - 1"):
+            r.set_scene(scene)
+    scene.instances = inst[:-1]  # one instance fewer is fine as far as the limit goes (not built here: 134 M triangles)
+
+
+def test_round_2_options_on_the_emulated_renderer(mods):
+    """stage_events = 0 (events only at frame start / end: the frame time stays, the per-stage times read 0, the image
+    does not change — and the shadow-order trial of the first two frames still sees its traversal times), the host-buffer
+    pinning knobs, bvh_top_smem (the shared-memory copy of the top of the tree: same image), and hw_textures, which the
+    host emulation cannot provide: a textured scene's set_scene fails cleanly, an untextured one renders."""
+    from chameleonrt_b200.scenes import cornell_box, sponza_like
+
+    RenderCUDA = mods[0]
+    scene, cam = cornell_box(spp=1)
+    c = camera_for(cam)
+    args = (c.eye(), c.dir(), c.up(), cam["fov_y"])
+    out = {}
+    for name, opts in (("default", {}), ("no_stage_events", {"stage_events": 0, "pin_host_buffers": 0, "pin_read_img": 1}),
+                       ("top_smem", {"bvh_top_smem": 1}), ("hw_tex_untextured", {"hw_textures": 1})):
+        r = RenderCUDA(0)
+        for k, v in opts.items():
+            r.set_option(k, v)
+        r.initialize(48, 32)
+        r.set_scene(scene)
+        for f in range(4):
+            st = r.render(*args, f == 0, True)
+        out[name] = (r.read_accum(), r.read_img(r.img).copy(), st.num_rays, r.stage_times(), r.get_option("any_far_first_decision"))
+    a0, i0, n0, t0, d0 = out["default"]
+    for name, (a, i, n, t, d) in out.items():
+        assert np.array_equal(a.view(np.uint32), a0.view(np.uint32)) and np.array_equal(i, i0) and n == n0, name
+        assert t["frame"] > 0 and d in (0, 1), name
+    assert out["default"][3]["traverse"] > 0 and out["no_stage_events"][3]["traverse"] == 0 and out["no_stage_events"][3]["shade"] == 0
+    scene, _ = sponza_like(spp=1, detail=0.25, tex_size=16)
+    r = RenderCUDA(0)
+    r.set_option("hw_textures", 1)
+    r.initialize(16, 16)
+    with pytest.raises(RuntimeError, match="cudaMallocArray|not supported"):
+        r.set_scene(scene)
