@@ -165,6 +165,13 @@ class RenderCUDA:
         self.samples_per_pixel = scene.samples_per_pixel
         self._check(self.lib.crtc_set_scene(self.h, C.byref(ms.c)))
 
+    def set_scene_c(self, c_scene, samples_per_pixel: int = 1) -> None:
+        """crtc_set_scene on a ``crt_scene_t`` that lives in native memory — what ``scene_io.load_obj(path).c_scene`` is —
+        without a trip through the Python scene model."""
+        c_scene.contents.samples_per_pixel = samples_per_pixel
+        self.samples_per_pixel = samples_per_pixel
+        self._check(self.lib.crtc_set_scene(self.h, c_scene))
+
     def render(self, pos, dir, up, fovy: float, camera_changed: bool, readback_framebuffer: bool = True) -> RenderStats:
         _p, pp = _vec3(pos)
         _d, dp = _vec3(dir)

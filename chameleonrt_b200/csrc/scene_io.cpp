@@ -1,0 +1,1054 @@
+// scene_io.cpp — the native scene loader behind include/crt_scene_io.h.
+//
+// Produces what the reference's Scene::load_obj produces (util/scene.cpp:94-228 over tinyobjloader 1.4.x, vendored by the
+// reference as util/tiny_obj_loader.h; its parsing rules are restated here where the result depends on them, with the line
+// they follow), from a memory-mapped file parsed by several threads. Host code only: no CUDA in this translation unit.
+#include "../../include/crt_scene_io.h"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "host_parallel.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Numbers as tinyobjloader reads them (tiny_obj_loader.h:567-697): decimal digits accumulated in a double, fraction
+// digits scaled by a table / pow(10, -k), the exponent applied as ldexp(m * pow(5, e), e), then rounded to float. This is
+// not strtod (it is not correctly rounded), and the loader's output must have tinyobjloader's bits.
+// ---------------------------------------------------------------------------------------------------------------
+inline bool is_digit(char c)
+{
+    return (unsigned)(c - '0') < 10u;
+}
+
+bool try_parse_double(const char *s, const char *s_end, double *result)
+{
+    if (s >= s_end) {
+        return false;
+    }
+    double mantissa = 0.0;
+    int exponent = 0;
+    char sign = '+', exp_sign = '+';
+    const char *curr = s;
+    int read = 0;
+    bool end_not_reached = false;
+    if (*curr == '+' || *curr == '-') {
+        sign = *curr;
+        curr++;
+    } else if (!is_digit(*curr)) {
+        return false;
+    }
+    end_not_reached = curr != s_end;
+    while (end_not_reached && is_digit(*curr)) {
+        mantissa *= 10;
+        mantissa += (int)(*curr - '0');
+        curr++;
+        read++;
+        end_not_reached = curr != s_end;
+    }
+    if (read == 0) {
+        return false;
+    }
+    bool assemble = !end_not_reached;
+    if (!assemble) {
+        if (*curr == '.') {
+            curr++;
+            read = 1;
+            end_not_reached = curr != s_end;
+            static const double pow_lut[] = {1.0, 0.1, 0.01, 0.001, 0.0001, 0.00001, 0.000001, 0.0000001};
+            const int lut_entries = (int)(sizeof pow_lut / sizeof pow_lut[0]);
+            while (end_not_reached && is_digit(*curr)) {
+                mantissa += (int)(*curr - '0') * (read < lut_entries ? pow_lut[read] : std::pow(10.0, -read));
+                read++;
+                curr++;
+                end_not_reached = curr != s_end;
+            }
+        } else if (*curr == 'e' || *curr == 'E') {
+        } else {
+            assemble = true;
+        }
+    }
+    if (!assemble && end_not_reached && (*curr == 'e' || *curr == 'E')) {
+        curr++;
+        end_not_reached = curr != s_end;
+        if (end_not_reached && (*curr == '+' || *curr == '-')) {
+            exp_sign = *curr;
+            curr++;
+        } else if (end_not_reached && is_digit(*curr)) {
+        } else {
+            return false;  // empty E is not allowed
+        }
+        read = 0;
+        end_not_reached = curr != s_end;
+        while (end_not_reached && is_digit(*curr)) {
+            exponent *= 10;
+            exponent += (int)(*curr - '0');
+            curr++;
+            read++;
+            end_not_reached = curr != s_end;
+        }
+        exponent *= exp_sign == '+' ? 1 : -1;
+        if (read == 0) {
+            return false;
+        }
+    }
+    *result = (sign == '+' ? 1 : -1) * (exponent ? std::ldexp(mantissa * std::pow(5.0, exponent), exponent) : mantissa);
+    return true;
+}
+
+inline bool is_blank(char c)
+{
+    return c == ' ' || c == '\t';
+}
+
+// parseReal (tiny_obj_loader.h:680-689): skip blanks, the token runs to the next blank / '\r' / end of line
+float parse_real(const char *&tok, const char *line_end, double default_value = 0.0)
+{
+    while (tok < line_end && is_blank(*tok)) {
+        ++tok;
+    }
+    const char *end = tok;
+    while (end < line_end && !is_blank(*end) && *end != '\r') {
+        ++end;
+    }
+    double val = default_value;
+    try_parse_double(tok, end, &val);
+    tok = end;
+    return (float)val;
+}
+
+// atoi on a bounded buffer
+int parse_int(const char *tok, const char *line_end)
+{
+    while (tok < line_end && (is_blank(*tok) || *tok == '\n' || *tok == '\v' || *tok == '\f' || *tok == '\r')) {
+        ++tok;
+    }
+    bool neg = false;
+    if (tok < line_end && (*tok == '+' || *tok == '-')) {
+        neg = *tok == '-';
+        ++tok;
+    }
+    long long v = 0;
+    while (tok < line_end && is_digit(*tok)) {
+        v = v * 10 + (*tok - '0');
+        if (v > 0x7fffffffll) {
+            v = 0x7fffffffll;
+        }
+        ++tok;
+    }
+    return (int)(neg ? -v : v);
+}
+
+// fixIndex (tiny_obj_loader.h): 1-based -> 0-based, negative = relative to the elements read so far, 0 is invalid
+inline bool fix_index(int idx, int n, int *ret)
+{
+    if (idx > 0) {
+        *ret = idx - 1;
+        return true;
+    }
+    if (idx == 0) {
+        return false;
+    }
+    *ret = n + idx;
+    return true;
+}
+
+inline const char *skip_to_slash_or_blank(const char *tok, const char *line_end)
+{
+    while (tok < line_end && *tok != '/' && !is_blank(*tok) && *tok != '\r') {
+        ++tok;
+    }
+    return tok;
+}
+
+struct Triple {
+    int v, vn, vt;
+};
+
+// parseTriple (tiny_obj_loader.h:823-877): i, i/j, i//k, i/j/k
+bool parse_triple(const char *&tok, const char *line_end, int vsize, int vnsize, int vtsize, Triple *out)
+{
+    Triple t{-1, -1, -1};
+    if (!fix_index(parse_int(tok, line_end), vsize, &t.v)) {
+        return false;
+    }
+    tok = skip_to_slash_or_blank(tok, line_end);
+    if (tok >= line_end || *tok != '/') {
+        *out = t;
+        return true;
+    }
+    ++tok;
+    if (tok < line_end && *tok == '/') {  // i//k
+        ++tok;
+        if (!fix_index(parse_int(tok, line_end), vnsize, &t.vn)) {
+            return false;
+        }
+        tok = skip_to_slash_or_blank(tok, line_end);
+        *out = t;
+        return true;
+    }
+    if (!fix_index(parse_int(tok, line_end), vtsize, &t.vt)) {
+        return false;
+    }
+    tok = skip_to_slash_or_blank(tok, line_end);
+    if (tok >= line_end || *tok != '/') {
+        *out = t;
+        return true;
+    }
+    ++tok;
+    if (!fix_index(parse_int(tok, line_end), vnsize, &t.vn)) {
+        return false;
+    }
+    tok = skip_to_slash_or_blank(tok, line_end);
+    *out = t;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct MappedFile {
+    const char *data = nullptr;
+    size_t size = 0;
+    int fd = -1;
+    explicit MappedFile(const std::string &path)
+    {
+        fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) {
+            throw std::runtime_error("cannot open " + path);
+        }
+        struct stat st;
+        if (fstat(fd, &st) != 0) {
+            close(fd);
+            throw std::runtime_error("cannot stat " + path);
+        }
+        size = (size_t)st.st_size;
+        if (size) {
+            void *p = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (p == MAP_FAILED) {
+                close(fd);
+                throw std::runtime_error("cannot map " + path);
+            }
+            madvise(p, size, MADV_SEQUENTIAL);
+            data = static_cast<const char *>(p);
+        }
+    }
+    ~MappedFile()
+    {
+        if (data) {
+            munmap(const_cast<char *>(data), size);
+        }
+        if (fd >= 0) {
+            close(fd);
+        }
+    }
+    MappedFile(const MappedFile &) = delete;
+    MappedFile &operator=(const MappedFile &) = delete;
+};
+
+enum EventKind { kEvGroup, kEvObject, kEvUseMtl, kEvMtlLib };
+struct Event {
+    EventKind kind;
+    size_t face;       // faces read before this line (global after the prefix sums)
+    std::string text;  // the rest of the line
+};
+
+struct Chunk {
+    size_t begin = 0, end = 0;
+    size_t nv = 0, nvt = 0, nvn = 0, nf = 0;       // counts of this chunk
+    size_t v0 = 0, vt0 = 0, vn0 = 0, f0 = 0;       // counts before this chunk
+    std::vector<Event> events;
+    std::string error;
+};
+
+enum LineKind { kLineOther, kLineV, kLineVT, kLineVN, kLineF, kLineG, kLineO, kLineUseMtl, kLineMtlLib };
+
+// the statement of a line after tinyobjloader's own trimming (LoadObj, tiny_obj_loader.h:1845-1870)
+inline LineKind classify(const char *&tok, const char *line_end)
+{
+    while (tok < line_end && is_blank(*tok)) {
+        ++tok;
+    }
+    const size_t n = (size_t)(line_end - tok);
+    if (n < 2) {
+        return kLineOther;
+    }
+    const char c0 = tok[0], c1 = tok[1];
+    if (c0 == 'v') {
+        if (is_blank(c1)) {
+            tok += 2;
+            return kLineV;
+        }
+        if (n >= 3 && is_blank(tok[2])) {
+            if (c1 == 't') {
+                tok += 3;
+                return kLineVT;
+            }
+            if (c1 == 'n') {
+                tok += 3;
+                return kLineVN;
+            }
+        }
+        return kLineOther;
+    }
+    if (c0 == 'f' && is_blank(c1)) {
+        tok += 2;
+        return kLineF;
+    }
+    if (c0 == 'g' && is_blank(c1)) {
+        return kLineG;
+    }
+    if (c0 == 'o' && is_blank(c1)) {
+        tok += 2;
+        return kLineO;
+    }
+    if (n >= 7 && is_blank(tok[6])) {
+        if (std::memcmp(tok, "usemtl", 6) == 0) {
+            tok += 7;
+            return kLineUseMtl;
+        }
+        if (std::memcmp(tok, "mtllib", 6) == 0) {
+            tok += 7;
+            return kLineMtlLib;
+        }
+    }
+    return kLineOther;
+}
+
+// [line_begin, line_end) of the line that starts at p; line_end excludes '\n' and a '\r' before it
+inline const char *line_end_of(const char *p, const char *chunk_end, const char *&next)
+{
+    const char *nl = static_cast<const char *>(std::memchr(p, '\n', (size_t)(chunk_end - p)));
+    const char *e = nl ? nl : chunk_end;
+    next = nl ? nl + 1 : chunk_end;
+    if (e > p && e[-1] == '\r') {
+        --e;
+    }
+    return e;
+}
+
+struct Material {  // the fields of tinyobj::material_t that Scene::load_obj reads
+    std::string name;
+    float diffuse[3] = {0.f, 0.f, 0.f};  // InitMaterial, tiny_obj_loader.h:1039
+    float shininess = 1.f;               // :1046
+    std::string diffuse_texname;
+};
+
+// LoadMtl (tiny_obj_loader.h:1353-1723), the statements Scene::load_obj depends on
+void load_mtl(const std::string &path, std::vector<Material> &materials, std::map<std::string, int> &material_map, bool &found)
+{
+    std::ifstream in(path.c_str());
+    found = (bool)in;
+    if (!found) {
+        return;
+    }
+    Material material;
+    std::string linebuf;
+    while (std::getline(in, linebuf)) {
+        if (!linebuf.empty()) {
+            linebuf = linebuf.substr(0, linebuf.find_last_not_of(" \t") + 1);  // trailing blanks (:1374)
+        }
+        if (!linebuf.empty() && linebuf.back() == '\n') {
+            linebuf.pop_back();
+        }
+        if (!linebuf.empty() && linebuf.back() == '\r') {
+            linebuf.pop_back();
+        }
+        if (linebuf.empty()) {
+            continue;
+        }
+        const char *tok = linebuf.c_str();
+        const char *end = tok + linebuf.size();
+        while (tok < end && is_blank(*tok)) {
+            ++tok;
+        }
+        if (tok >= end || *tok == '#') {
+            continue;
+        }
+        const size_t n = (size_t)(end - tok);
+        if (n >= 7 && std::memcmp(tok, "newmtl", 6) == 0 && is_blank(tok[6])) {
+            if (!material.name.empty()) {  // flush the previous material (:1407-1411)
+                material_map.insert(std::make_pair(material.name, (int)materials.size()));
+                materials.push_back(material);
+            }
+            material = Material();
+            material.name = std::string(tok + 7, end);
+            continue;
+        }
+        if (n >= 3 && tok[0] == 'K' && tok[1] == 'd' && is_blank(tok[2])) {
+            tok += 2;
+            material.diffuse[0] = parse_real(tok, end);
+            material.diffuse[1] = parse_real(tok, end);
+            material.diffuse[2] = parse_real(tok, end);
+            continue;
+        }
+        if (n >= 3 && tok[0] == 'N' && tok[1] == 's' && is_blank(tok[2])) {
+            tok += 2;
+            material.shininess = parse_real(tok, end);
+            continue;
+        }
+        if (n >= 7 && std::memcmp(tok, "map_Kd", 6) == 0 && is_blank(tok[6])) {
+            // ParseTextureNameAndOption (:906-1011): options start with '-', the texture name is the remaining token
+            tok += 7;
+            std::string name;
+            while (tok < end) {
+                while (tok < end && is_blank(*tok)) {
+                    ++tok;
+                }
+                const char *e = tok;
+                while (e < end && !is_blank(*e)) {
+                    ++e;
+                }
+                if (tok < e) {
+                    if (*tok == '-') {
+                        throw std::runtime_error("map_Kd with texture options is not supported by this loader: " + linebuf);
+                    }
+                    name = std::string(tok, e);
+                }
+                tok = e;
+            }
+            material.diffuse_texname = name;
+            continue;
+        }
+    }
+    // the last material is flushed whatever its name (:1716-1719)
+    material_map.insert(std::make_pair(material.name, (int)materials.size()));
+    materials.push_back(material);
+}
+
+// ---- PNG (what stb_image decodes for this project's scenes: 8-bit, non-interlaced), to RGBA, rows flipped ----
+uint32_t be32(const uint8_t *p)
+{
+    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+}
+
+void load_png_rgba_flipped(const std::string &path, std::vector<uint8_t> &out, int &width, int &height)
+{
+    std::ifstream in(path.c_str(), std::ios::binary);
+    if (!in) {
+        throw std::runtime_error("Failed to load " + path);  // util/material.cpp:11-13
+    }
+    std::vector<uint8_t> file((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (file.size() < 8 + 25 || std::memcmp(file.data(), sig, 8) != 0) {
+        throw std::runtime_error("not a PNG file (only PNG textures are supported by this loader): " + path);
+    }
+    size_t pos = 8;
+    int bit_depth = 0, color_type = 0, interlace = 0;
+    std::vector<uint8_t> idat, palette, trns;
+    width = height = 0;
+    while (pos + 12 <= file.size()) {
+        const uint32_t len = be32(&file[pos]);
+        const char *type = reinterpret_cast<const char *>(&file[pos + 4]);
+        const uint8_t *body = &file[pos + 8];
+        if (pos + 12 + (size_t)len > file.size()) {
+            throw std::runtime_error("truncated PNG: " + path);
+        }
+        if (std::memcmp(type, "IHDR", 4) == 0 && len >= 13) {
+            width = (int)be32(body);
+            height = (int)be32(body + 4);
+            bit_depth = body[8];
+            color_type = body[9];
+            interlace = body[12];
+        } else if (std::memcmp(type, "PLTE", 4) == 0) {
+            palette.assign(body, body + len);
+        } else if (std::memcmp(type, "tRNS", 4) == 0) {
+            trns.assign(body, body + len);
+        } else if (std::memcmp(type, "IDAT", 4) == 0) {
+            idat.insert(idat.end(), body, body + len);
+        } else if (std::memcmp(type, "IEND", 4) == 0) {
+            break;
+        }
+        pos += 12 + (size_t)len;
+    }
+    if (width <= 0 || height <= 0 || bit_depth != 8 || interlace != 0) {
+        throw std::runtime_error("unsupported PNG (8-bit non-interlaced only): " + path);
+    }
+    int ch;
+    switch (color_type) {
+    case 0: ch = 1; break;
+    case 2: ch = 3; break;
+    case 3: ch = 1; break;
+    case 4: ch = 2; break;
+    case 6: ch = 4; break;
+    default: throw std::runtime_error("unsupported PNG colour type: " + path);
+    }
+    const size_t stride = (size_t)width * ch;
+    std::vector<uint8_t> raw((stride + 1) * (size_t)height);
+    uLongf raw_len = (uLongf)raw.size();
+    if (uncompress(raw.data(), &raw_len, idat.data(), (uLong)idat.size()) != Z_OK || raw_len != raw.size()) {
+        throw std::runtime_error("corrupt PNG data: " + path);
+    }
+    // undo the scanline filters (PNG specification, section 9)
+    std::vector<uint8_t> img(stride * (size_t)height);
+    for (int y = 0; y < height; ++y) {
+        const uint8_t filter = raw[(stride + 1) * (size_t)y];
+        const uint8_t *src = &raw[(stride + 1) * (size_t)y + 1];
+        uint8_t *dst = &img[stride * (size_t)y];
+        const uint8_t *up = y ? &img[stride * (size_t)(y - 1)] : nullptr;
+        for (size_t x = 0; x < stride; ++x) {
+            const int a = x >= (size_t)ch ? dst[x - ch] : 0, b = up ? up[x] : 0, c = (up && x >= (size_t)ch) ? up[x - ch] : 0;
+            int pred = 0;
+            switch (filter) {
+            case 0: pred = 0; break;
+            case 1: pred = a; break;
+            case 2: pred = b; break;
+            case 3: pred = (a + b) >> 1; break;
+            case 4: {
+                const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+                pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+                break;
+            }
+            default: throw std::runtime_error("corrupt PNG filter: " + path);
+            }
+            dst[x] = (uint8_t)(src[x] + pred);
+        }
+    }
+    // to RGBA as stbi_load(..., 4) does, rows bottom-up (stbi_set_flip_vertically_on_load(1), util/material.cpp:8)
+    out.resize((size_t)width * height * 4);
+    for (int y = 0; y < height; ++y) {
+        const uint8_t *src = &img[stride * (size_t)(height - 1 - y)];
+        uint8_t *dst = &out[(size_t)width * 4 * y];
+        for (int x = 0; x < width; ++x) {
+            uint8_t r, g, b, a = 255;
+            switch (color_type) {
+            case 0: r = g = b = src[x]; break;
+            case 2: r = src[3 * x], g = src[3 * x + 1], b = src[3 * x + 2]; break;
+            case 3: {
+                const size_t i = src[x];
+                if (3 * i + 2 >= palette.size()) {
+                    throw std::runtime_error("corrupt PNG palette: " + path);
+                }
+                r = palette[3 * i], g = palette[3 * i + 1], b = palette[3 * i + 2];
+                a = i < trns.size() ? trns[i] : 255;
+                break;
+            }
+            case 4: r = g = b = src[2 * x], a = src[2 * x + 1]; break;
+            default: r = src[4 * x], g = src[4 * x + 1], b = src[4 * x + 2], a = src[4 * x + 3]; break;
+            }
+            dst[4 * x] = r, dst[4 * x + 1] = g, dst[4 * x + 2] = b, dst[4 * x + 3] = a;
+        }
+    }
+}
+
+// glm::normalize(v) = v * inversesqrt(dot(v, v)), inversesqrt(x) = 1 / sqrt(x)
+void normalize3(float v[3])
+{
+    const float inv = 1.f / std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    v[0] *= inv, v[1] *= inv, v[2] *= inv;
+}
+void cross3(const float a[3], const float b[3], float out[3])
+{
+    out[0] = a[1] * b[2] - b[1] * a[2];
+    out[1] = a[2] * b[0] - b[2] * a[0];
+    out[2] = a[0] * b[1] - b[0] * a[1];
+}
+// ortho_basis (util/util.cpp: the host twin of backends/embree/util.ih:24-46)
+void ortho_basis(float v_x[3], float v_y[3], const float n[3])
+{
+    v_y[0] = v_y[1] = v_y[2] = 0.f;
+    if (n[0] < 0.6f && n[0] > -0.6f) {
+        v_y[0] = 1.f;
+    } else if (n[1] < 0.6f && n[1] > -0.6f) {
+        v_y[1] = 1.f;
+    } else if (n[2] < 0.6f && n[2] > -0.6f) {
+        v_y[2] = 1.f;
+    } else {
+        v_y[0] = 1.f;
+    }
+    cross3(v_y, n, v_x);
+    normalize3(v_x);
+    cross3(n, v_x, v_y);
+    normalize3(v_y);
+}
+
+struct GeometryData {
+    std::vector<float> vertices, uvs;
+    std::vector<uint32_t> indices;
+};
+
+}  // namespace
+
+struct crtio_scene {
+    std::vector<GeometryData> geometries;
+    std::vector<crt_geometry_t> geometry_views;
+    crt_mesh_t mesh{};
+    std::vector<uint32_t> material_ids;
+    crt_parameterized_mesh_t parameterized_mesh{};
+    crt_instance_t instance{};
+    std::vector<crt_material_t> materials;
+    std::vector<std::vector<uint8_t>> texture_data;
+    std::vector<crt_image_t> textures;
+    crt_quad_light_t light{};
+    crt_scene_t view{};
+    std::string warnings;
+    double timings[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+// One geometry of Scene::load_obj (util/scene.cpp:116-181): index triples -> single indices in order of first use
+void remap_shape(const std::vector<float> &V, const std::vector<float> &VT, const int32_t *faces, size_t num_faces, GeometryData &g,
+                 const std::string &what)
+{
+    size_t cap = 64;
+    while (cap < num_faces * 3 * 2) {
+        cap <<= 1;
+    }
+    struct Slot {
+        int32_t v, vn, vt;
+        uint32_t index;
+    };
+    std::vector<Slot> table(cap, Slot{-2, 0, 0, 0});
+    g.indices.resize(num_faces * 3);
+    g.vertices.reserve(num_faces * 3);
+    const size_t nv = V.size() / 3, nvt = VT.size() / 2;
+    bool any_uv = false, any_without_uv = false;
+    for (size_t c = 0; c < num_faces * 3; ++c) {
+        const int32_t v = faces[3 * c], vn = faces[3 * c + 1], vt = faces[3 * c + 2];
+        uint64_t h = (uint64_t)(uint32_t)v * 0x9E3779B97F4A7C15ull;
+        h ^= ((uint64_t)(uint32_t)vt + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
+        h ^= ((uint64_t)(uint32_t)vn + 0x165667B1ull) * 0x27D4EB2F165667C5ull;
+        size_t slot = (size_t)(h ^ (h >> 29)) & (cap - 1);
+        for (;;) {
+            Slot &s = table[slot];
+            if (s.v == -2) {
+                if (v < 0 || (size_t)v >= nv) {
+                    throw std::runtime_error("vertex index out of range in " + what);
+                }
+                s = Slot{v, vn, vt, (uint32_t)(g.vertices.size() / 3)};
+                g.vertices.push_back(V[3 * (size_t)v]);
+                g.vertices.push_back(V[3 * (size_t)v + 1]);
+                g.vertices.push_back(V[3 * (size_t)v + 2]);
+                if (vt != -1) {
+                    if (vt < 0 || (size_t)vt >= nvt) {
+                        throw std::runtime_error("texture coordinate index out of range in " + what);
+                    }
+                    g.uvs.push_back(VT[2 * (size_t)vt]);
+                    g.uvs.push_back(VT[2 * (size_t)vt + 1]);
+                    any_uv = true;
+                } else {
+                    any_without_uv = true;
+                }
+                g.indices[c] = s.index;
+                break;
+            }
+            if (s.v == v && s.vn == vn && s.vt == vt) {
+                g.indices[c] = s.index;
+                break;
+            }
+            slot = (slot + 1) & (cap - 1);
+        }
+    }
+    if (any_uv && any_without_uv) {
+        throw std::runtime_error("some corners of " + what + " have texture coordinates and some have none");
+    }
+}
+
+void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
+{
+    const double t_start = now_s();
+    const unsigned nthreads = crt::host_threads(threads);
+    MappedFile map(file);
+    // ---- chunks at line boundaries ----
+    const size_t target = std::max<size_t>((size_t)1 << 20, map.size / (std::max(1u, nthreads) * 8u) + 1);
+    std::vector<Chunk> chunks;
+    for (size_t b = 0; b < map.size;) {
+        size_t e = std::min(map.size, b + target);
+        if (e < map.size) {
+            const void *nl = std::memchr(map.data + e, '\n', map.size - e);
+            e = nl ? (size_t)(static_cast<const char *>(nl) - map.data) + 1 : map.size;
+        }
+        Chunk c;
+        c.begin = b;
+        c.end = e;
+        chunks.push_back(c);
+        b = e;
+    }
+    // ---- pass 1: count statements, collect the shape / material events ----
+    crt::parallel_blocks((uint32_t)chunks.size(), nthreads, [&](uint32_t ci) {
+        Chunk &c = chunks[ci];
+        const char *p = map.data + c.begin, *chunk_end = map.data + c.end;
+        while (p < chunk_end) {
+            const char *next;
+            const char *le = line_end_of(p, chunk_end, next);
+            const char *tok = p;
+            switch (classify(tok, le)) {
+            case kLineV: c.nv++; break;
+            case kLineVT: c.nvt++; break;
+            case kLineVN: c.nvn++; break;
+            case kLineF: c.nf++; break;
+            case kLineG: c.events.push_back(Event{kEvGroup, c.nf, std::string()}); break;
+            case kLineO: c.events.push_back(Event{kEvObject, c.nf, std::string()}); break;
+            case kLineUseMtl: c.events.push_back(Event{kEvUseMtl, c.nf, std::string(tok, le)}); break;
+            case kLineMtlLib: c.events.push_back(Event{kEvMtlLib, c.nf, std::string(tok, le)}); break;
+            default: break;
+            }
+            p = next;
+        }
+    });
+    size_t nv = 0, nvt = 0, nvn = 0, nf = 0;
+    for (Chunk &c : chunks) {
+        c.v0 = nv, c.vt0 = nvt, c.vn0 = nvn, c.f0 = nf;
+        nv += c.nv, nvt += c.nvt, nvn += c.nvn, nf += c.nf;
+    }
+    if (nv >= 0x7fffffffull || nvt >= 0x7fffffffull || nvn >= 0x7fffffffull || nf >= 0x7fffffffull / 3) {
+        throw std::runtime_error("OBJ file too large for 32-bit indices: " + file);
+    }
+    // ---- pass 2: parse into the global arrays ----
+    std::vector<float> V(nv * 3), VT(nvt * 2);
+    std::vector<int32_t> F(nf * 9);  // per face 3 x (v, vn, vt)
+    crt::parallel_blocks((uint32_t)chunks.size(), nthreads, [&](uint32_t ci) {
+        Chunk &c = chunks[ci];
+        size_t v = c.v0, vt = c.vt0, vn = c.vn0, f = c.f0;
+        const char *p = map.data + c.begin, *chunk_end = map.data + c.end;
+        while (p < chunk_end && c.error.empty()) {
+            const char *next;
+            const char *le = line_end_of(p, chunk_end, next);
+            const char *tok = p;
+            switch (classify(tok, le)) {
+            case kLineV:  // parseVertexWithColor (:733-754): x y z, then optional colours that do not matter here
+                V[3 * v] = parse_real(tok, le);
+                V[3 * v + 1] = parse_real(tok, le);
+                V[3 * v + 2] = parse_real(tok, le);
+                ++v;
+                break;
+            case kLineVT:  // parseReal2 (:1900-1907)
+                VT[2 * vt] = parse_real(tok, le);
+                VT[2 * vt + 1] = parse_real(tok, le);
+                ++vt;
+                break;
+            case kLineVN:
+                ++vn;
+                break;
+            case kLineF: {
+                while (tok < le && is_blank(*tok)) {
+                    ++tok;
+                }
+                int corners = 0;
+                Triple t[3];
+                while (tok < le && *tok != '\r') {
+                    Triple tr;
+                    if (!parse_triple(tok, le, (int)v, (int)vn, (int)vt, &tr)) {
+                        c.error = "Failed parse `f' line(e.g. zero value for face index)";  // :1945-1952
+                        break;
+                    }
+                    if (corners < 3) {
+                        t[corners] = tr;
+                    }
+                    ++corners;
+                    while (tok < le && (is_blank(*tok) || *tok == '\r')) {
+                        ++tok;
+                    }
+                }
+                if (c.error.empty() && corners != 3) {
+                    c.error = corners > 3 ? "a face with more than three corners (this loader reads triangle meshes; tinyobjloader would ear-clip it)"
+                                          : "a face with fewer than three corners";
+                }
+                if (c.error.empty()) {
+                    for (int k = 0; k < 3; ++k) {
+                        F[9 * f + 3 * k] = t[k].v;
+                        F[9 * f + 3 * k + 1] = t[k].vn;
+                        F[9 * f + 3 * k + 2] = t[k].vt;
+                    }
+                }
+                ++f;
+                break;
+            }
+            default: break;
+            }
+            p = next;
+        }
+    });
+    for (const Chunk &c : chunks) {
+        if (!c.error.empty()) {
+            throw std::runtime_error("TinyOBJ Error loading " + file + " error: " + c.error);
+        }
+    }
+    // ---- shapes, from the events in file order (LoadObj's handling of usemtl / g / o, :1979-2128 and :2200-2212) ----
+    struct Segment {
+        size_t begin, end;
+        int material;
+    };
+    struct Shape {
+        std::vector<Segment> segments;
+    };
+    std::vector<Shape> shapes;
+    std::vector<Material> obj_materials;
+    std::map<std::string, int> material_map;
+    std::string obj_base_dir = file.substr(0, file.rfind('/'));  // util/scene.cpp:105 (the whole name if there is no '/')
+    std::string mtl_base = obj_base_dir;
+    if (!mtl_base.empty() && mtl_base.back() != '/') {
+        mtl_base += "/";
+    }
+    std::ostringstream warn;
+    {
+        Shape shape;
+        int material = -1;
+        size_t group_begin = 0;  // first face of the current face group
+        auto export_group = [&](size_t pos) {
+            if (group_begin == pos) {
+                return false;
+            }
+            shape.segments.push_back(Segment{group_begin, pos, material});
+            group_begin = pos;
+            return true;
+        };
+        for (const Chunk &c : chunks) {
+            for (const Event &ev : c.events) {
+                const size_t pos = c.f0 + ev.face;
+                switch (ev.kind) {
+                case kEvUseMtl: {
+                    const auto it = material_map.find(ev.text);
+                    const int id = it != material_map.end() ? it->second : -1;
+                    if (id != material) {
+                        export_group(pos);
+                        material = id;
+                    }
+                    break;
+                }
+                case kEvMtlLib: {
+                    std::vector<std::string> names;
+                    std::stringstream ss(ev.text);
+                    std::string item;
+                    while (std::getline(ss, item, ' ')) {  // SplitString(token, ' ')
+                        names.push_back(item);
+                    }
+                    bool found = false;
+                    for (const std::string &n : names) {
+                        load_mtl(mtl_base + n, obj_materials, material_map, found);
+                        if (found) {
+                            break;
+                        }
+                        warn << "Material file [ " << mtl_base + n << " ] not found.\n";
+                    }
+                    if (!found) {
+                        warn << "Failed to load material file(s). Use default material.\n";
+                    }
+                    break;
+                }
+                case kEvGroup:
+                    export_group(pos);
+                    if (!shape.segments.empty()) {
+                        shapes.push_back(shape);
+                    }
+                    shape = Shape();
+                    break;
+                case kEvObject:
+                    if (export_group(pos)) {  // (a shape whose faces were all flushed by an earlier usemtl is dropped: :2105-2109)
+                        shapes.push_back(shape);
+                    }
+                    shape = Shape();
+                    break;
+                }
+            }
+        }
+        const bool ret = export_group(nf);
+        if (ret || !shape.segments.empty()) {
+            shapes.push_back(shape);
+        }
+    }
+    const double t_parsed = now_s();
+    // ---- Scene::load_obj: one geometry per shape ----
+    S.geometries.resize(shapes.size());
+    S.material_ids.resize(shapes.size());
+    for (size_t s = 0; s < shapes.size(); ++s) {
+        S.material_ids[s] = (uint32_t)shapes[s].segments[0].material;  // the first face's material (scene.cpp:127)
+        for (const Segment &seg : shapes[s].segments) {
+            if (seg.material != shapes[s].segments[0].material) {
+                warn << "Warning: per-face material IDs are not supported, materials may look wrong. Please reexport your mesh with each "
+                        "material group as an OBJ group\n";
+                break;
+            }
+        }
+    }
+    std::vector<std::string> shape_errors(shapes.size());
+    crt::parallel_blocks((uint32_t)shapes.size(), nthreads, [&](uint32_t s) {
+        try {
+            const size_t begin = shapes[s].segments.front().begin, end = shapes[s].segments.back().end;
+            remap_shape(V, VT, F.data() + 9 * begin, end - begin, S.geometries[s], file + " shape " + std::to_string(s));
+        } catch (const std::exception &e) {
+            shape_errors[s] = e.what();
+        }
+    });
+    for (const std::string &e : shape_errors) {
+        if (!e.empty()) {
+            throw std::runtime_error(e);
+        }
+    }
+    const double t_remapped = now_s();
+    // ---- materials (scene.cpp:188-214) ----
+    std::map<std::string, int32_t> texture_ids;
+    std::vector<std::string> texture_files;
+    for (const Material &m : obj_materials) {
+        crt_material_t d;
+        std::memset(&d, 0, sizeof(d));
+        d.base_color[0] = m.diffuse[0], d.base_color[1] = m.diffuse[1], d.base_color[2] = m.diffuse[2];
+        d.ior = 1.5f;  // DisneyMaterial's defaults, util/material.h:29-46
+        const float spec = m.shininess / 500.f;
+        d.specular = spec < 0.f ? 0.f : (spec > 1.f ? 1.f : spec);
+        const float rough = 1.f - d.specular;
+        d.roughness = rough < 0.f ? 0.f : (rough > 1.f ? 1.f : rough);
+        d.specular_transmission = 0.f;
+        if (!m.diffuse_texname.empty()) {
+            std::string path = m.diffuse_texname;
+            std::replace(path.begin(), path.end(), '\\', '/');  // canonicalize_path, util/util.cpp
+            auto it = texture_ids.find(m.diffuse_texname);
+            if (it == texture_ids.end()) {
+                it = texture_ids.insert(std::make_pair(m.diffuse_texname, (int32_t)texture_files.size())).first;
+                texture_files.push_back(obj_base_dir + "/" + path);
+            }
+            const uint32_t tex_mask = 0x80000000u | ((uint32_t)it->second & 0x1fffffffu);  // TEXTURED_PARAM_MASK, SET_TEXTURE_ID
+            std::memcpy(&d.base_color[0], &tex_mask, 4);
+        }
+        S.materials.push_back(d);
+    }
+    // validate_materials (scene.cpp:932-957): shapes without a material get a default one
+    if (std::find(S.material_ids.begin(), S.material_ids.end(), 0xffffffffu) != S.material_ids.end()) {
+        crt_material_t d;
+        std::memset(&d, 0, sizeof(d));
+        d.base_color[0] = d.base_color[1] = d.base_color[2] = 0.9f;
+        d.roughness = 1.f;
+        d.ior = 1.5f;
+        const uint32_t id = (uint32_t)S.materials.size();
+        S.materials.push_back(d);
+        for (uint32_t &m : S.material_ids) {
+            if (m == 0xffffffffu) {
+                m = id;
+            }
+        }
+        warn << "No materials assigned for some objects, generating a default\n";
+    }
+    S.texture_data.resize(texture_files.size());
+    S.textures.resize(texture_files.size());
+    std::vector<std::string> tex_errors(texture_files.size());
+    crt::parallel_blocks((uint32_t)texture_files.size(), nthreads, [&](uint32_t i) {
+        try {
+            int w = 0, h = 0;
+            load_png_rgba_flipped(texture_files[i], S.texture_data[i], w, h);
+            S.textures[i] = crt_image_t{S.texture_data[i].data(), w, h, 4, CRT_COLOR_SPACE_SRGB};
+        } catch (const std::exception &e) {
+            tex_errors[i] = e.what();
+        }
+    });
+    for (const std::string &e : tex_errors) {
+        if (!e.empty()) {
+            throw std::runtime_error(e);
+        }
+    }
+    // ---- the generated light (scene.cpp:216-227) ----
+    float n[3] = {0.5f, -0.8f, -0.5f};
+    normalize3(n);
+    crt_quad_light_t &L = S.light;
+    std::memset(&L, 0, sizeof(L));
+    L.emission[0] = L.emission[1] = L.emission[2] = L.emission[3] = 20.f;
+    L.normal[0] = n[0], L.normal[1] = n[1], L.normal[2] = n[2], L.normal[3] = 0.f;
+    for (int k = 0; k < 4; ++k) {
+        L.position[k] = -10.f * L.normal[k];
+    }
+    ortho_basis(L.v_x, L.v_y, n);
+    L.width = 5.f;
+    L.height = 5.f;
+    // ---- views ----
+    S.geometry_views.resize(S.geometries.size());
+    for (size_t g = 0; g < S.geometries.size(); ++g) {
+        const GeometryData &gd = S.geometries[g];
+        S.geometry_views[g] = crt_geometry_t{gd.vertices.data(), gd.uvs.empty() ? nullptr : gd.uvs.data(), gd.indices.data(),
+                                             (uint32_t)(gd.vertices.size() / 3), (uint32_t)(gd.indices.size() / 3)};
+    }
+    S.mesh = crt_mesh_t{S.geometry_views.data(), (uint32_t)S.geometry_views.size()};
+    S.parameterized_mesh = crt_parameterized_mesh_t{S.material_ids.data(), (uint32_t)S.material_ids.size(), 0u};
+    std::memset(&S.instance, 0, sizeof(S.instance));
+    S.instance.transform[0] = S.instance.transform[5] = S.instance.transform[10] = S.instance.transform[15] = 1.f;
+    S.instance.parameterized_mesh_id = 0;
+    S.view = crt_scene_t{&S.mesh, &S.parameterized_mesh, &S.instance, S.materials.data(), S.textures.data(), &S.light, 1u, 1u, 1u,
+                         (uint32_t)S.materials.size(), (uint32_t)S.textures.size(), 1u, 1u};
+    S.warnings = warn.str();
+    const double t_end = now_s();
+    S.timings[0] = t_end - t_start;
+    S.timings[1] = t_parsed - t_start;
+    S.timings[2] = t_remapped - t_parsed;
+    S.timings[3] = t_end - t_remapped;
+}
+
+}  // namespace
+
+extern "C" {
+
+int crtio_load_obj(const char *path, int threads, crtio_scene **out)
+{
+    try {
+        if (!path || !out) {
+            throw std::runtime_error("crtio_load_obj: null argument");
+        }
+        *out = nullptr;
+        std::unique_ptr<crtio_scene> s(new crtio_scene());
+        load_obj_impl(path, threads, *s);
+        *out = s.release();
+        return 0;
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        return 1;
+    } catch (...) {
+        g_last_error = "unknown exception";
+        return 1;
+    }
+}
+
+const crt_scene_t *crtio_scene_view(const crtio_scene *s)
+{
+    return s ? &s->view : nullptr;
+}
+
+int crtio_timings(const crtio_scene *s, double *out, int n)
+{
+    if (!s || !out) {
+        return 0;
+    }
+    const int m = std::min(n, 4);
+    for (int i = 0; i < m; ++i) {
+        out[i] = s->timings[i];
+    }
+    return m;
+}
+
+const char *crtio_warnings(const crtio_scene *s)
+{
+    return s ? s->warnings.c_str() : "";
+}
+
+void crtio_free(crtio_scene *s)
+{
+    delete s;
+}
+
+const char *crtio_last_error(void)
+{
+    return g_last_error.c_str();
+}
+}

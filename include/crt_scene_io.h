@@ -1,0 +1,48 @@
+/* crt_scene_io.h — C ABI of the native scene loader (scene-load throughput).
+ *
+ * The step in front of RenderBackend::set_scene is the reference's Scene::load_obj (util/scene.cpp:94-228): tinyobjloader
+ * parses the file on one thread, then a hash map per OBJ shape remaps tinyobj's (position, normal, texcoord) index triples
+ * to single indices (scene.cpp:116-181), single-threaded as well. crtio_load_obj produces THE SAME Scene — geometry by
+ * geometry the same vertex / uv / index arrays in the same order, the same materials, textures and generated light, bit for
+ * bit (tests/test_scene_io.py compares with the reference's own loader) — from a memory-mapped file parsed in parallel:
+ * lines are classified and counted per chunk, prefix sums place every chunk's vertices / faces, the chunks are parsed into
+ * the global arrays concurrently (floats with tinyobjloader's own decimal-to-double rule, so that the bits match), shapes are
+ * delimited from the g / o / usemtl events, and the shapes are remapped concurrently, one open-addressing table each.
+ *
+ * The result is a crt_scene_t (include/crt_scene.h) owned by the handle: pass crtio_scene_view(h) to crtc_set_scene.
+ *
+ * Supported: what Scene::load_obj supports for the scenes of this project — triangle faces (a polygon with more than three
+ * corners is an error here; tinyobjloader would ear-clip it), v / vt / vn / f / g / o / usemtl / mtllib, MTL newmtl / Kd /
+ * Ns / map_Kd (other statements are ignored as the reference ignores them), 8-bit non-interlaced PNG textures (grey, grey +
+ * alpha, RGB, RGBA, palette), which the reference loads through stb_image, flipped vertically and expanded to RGBA
+ * (util/material.cpp:5-17). */
+#ifndef CRT_SCENE_IO_H
+#define CRT_SCENE_IO_H
+
+#include "crt_scene.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct crtio_scene crtio_scene;
+
+/* Scene::load_obj (util/scene.cpp:94-228). threads: 0 = all hardware threads. Returns 0 and *out on success; otherwise a
+ * non-zero code and crtio_last_error() (the reference throws std::runtime_error). */
+int crtio_load_obj(const char *path, int threads, crtio_scene **out);
+/* The loaded scene as the plain-C view crtc_set_scene takes; valid until crtio_free. samples_per_pixel is 1 (the
+ * application sets it from its command line, main.cpp:186). */
+const crt_scene_t *crtio_scene_view(const crtio_scene *s);
+/* Wall-clock seconds of the phases of the last load: [0] total [1] parse (mmap + both passes) [2] index remap [3] materials
+ * + textures. Returns the number of entries written. */
+int crtio_timings(const crtio_scene *s, double *out, int n);
+/* Warnings the reference would print (per-face material ids, missing material file, ...), one per line. */
+const char *crtio_warnings(const crtio_scene *s);
+void crtio_free(crtio_scene *s);
+const char *crtio_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

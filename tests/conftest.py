@@ -18,7 +18,7 @@ def built():
     import __graft_entry__ as g
 
     csrc = os.path.join(ROOT, "chameleonrt_b200", "csrc")
-    need = [os.path.join(csrc, "libcrt_cuda_core.so"), os.path.join(csrc, "libcrt_bvh8_hostcheck.so"),
+    need = [os.path.join(csrc, "libcrt_cuda_core.so"), os.path.join(csrc, "libcrt_scene_io.so"), os.path.join(csrc, "libcrt_bvh8_hostcheck.so"),
             os.path.join(csrc, "libcrt_shade_hostcheck.so"), os.path.join(csrc, "libcrt_wavefront_hostcheck.so"),
             os.path.join(csrc, "libcrt_wavefront_hostcheck_powf.so"), os.path.join(csrc, "libcrt_simt_hostcheck.so"),
             os.path.join(ROOT, "oracle", "liboracle.so")]

@@ -25,6 +25,18 @@ def test_header_symbols_exported(built):
         assert hasattr(lib, sym), f"{sym} not exported by libcrt_cuda_core.so"
 
 
+def test_scene_io_header_symbols_exported(built):
+    """include/crt_scene_io.h (the native scene loader): every declared entry point is exported by libcrt_scene_io.so."""
+    from chameleonrt_b200 import scene_io
+
+    header = open(os.path.join(ROOT, "include", "crt_scene_io.h")).read()
+    declared = set(re.findall(r"\b(crtio_[a-z_]+)\s*\(", header))
+    assert declared == {"crtio_load_obj", "crtio_scene_view", "crtio_timings", "crtio_warnings", "crtio_free", "crtio_last_error"}
+    lib = C.CDLL(scene_io.lib_path())
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} not exported by libcrt_scene_io.so"
+
+
 def test_no_gpu_fails_loudly(built):
     """On a machine without a CUDA device creation must fail with a message, never fall back."""
     import torch

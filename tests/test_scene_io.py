@@ -1,0 +1,213 @@
+"""The native scene loader (include/crt_scene_io.h, chameleonrt_b200/csrc/scene_io.cpp) against its
+oracle: the REFERENCE'S OWN Scene::load_obj (util/scene.cpp:94-228 over tinyobjloader + stb_image), compiled from
+/root/reference into oracle/_ref/libcrt_refscene.so by oracle/ref_build/Makefile. Every array of the Scene must be the same,
+bit for bit: per geometry the vertices, uvs and indices in the same order (the single-index remap of scene.cpp:116-181 keeps
+the order of first use), the material ids, the DisneyMaterials (incl. texture handles), the texture pixels (RGBA, rows
+flipped) and the generated light. Where the reference library is not built (the GPU box) the comparison falls back on the
+scene the OBJ was written from."""
+import ctypes as C
+import os
+import time
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, synthetic_material_scene
+
+REFLIB = os.path.join(ROOT, "oracle", "_ref", "libcrt_refscene.so")
+
+
+def _ref():
+    lib = C.CDLL(REFLIB)
+    lib.refscene_load.restype = C.c_void_p
+    lib.refscene_load.argtypes = [C.c_char_p, C.POINTER(C.c_double)]
+    lib.refscene_error.restype = C.c_char_p
+    lib.refscene_free.argtypes = [C.c_void_p]
+    lib.refscene_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+    lib.refscene_geometry.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6
+    lib.refscene_material_ids.restype = C.POINTER(C.c_uint32)
+    lib.refscene_material_ids.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.refscene_materials.restype = C.POINTER(C.c_uint32)
+    lib.refscene_materials.argtypes = [C.c_void_p]
+    lib.refscene_light.restype = C.POINTER(C.c_uint32)
+    lib.refscene_light.argtypes = [C.c_void_p, C.c_uint32]
+    lib.refscene_instance.restype = C.POINTER(C.c_uint32)
+    lib.refscene_instance.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.refscene_texture.restype = C.POINTER(C.c_uint8)
+    lib.refscene_texture.argtypes = [C.c_void_p, C.c_uint32] + [C.POINTER(C.c_int)] * 4
+    return lib
+
+
+def _reference_arrays(path):
+    """What Scene::load_obj built, as numpy arrays (bit patterns for everything float)."""
+    lib = _ref()
+    secs = C.c_double(0)
+    h = lib.refscene_load(path.encode(), C.byref(secs))
+    assert h, lib.refscene_error().decode()
+    counts = (C.c_uint32 * 7)()
+    lib.refscene_counts(h, counts)
+    out = dict(counts=list(counts), seconds=secs.value, geometries=[])
+    for g in range(counts[1]):
+        v, uv, idx = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)()
+        nv, nuv, nt = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        lib.refscene_geometry(h, g, C.byref(v), C.byref(nv), C.byref(uv), C.byref(nuv), C.byref(idx), C.byref(nt))
+        out["geometries"].append((np.ctypeslib.as_array(v, (nv.value * 3,)).copy() if nv.value else np.zeros(0, np.uint32),
+                                  np.ctypeslib.as_array(uv, (nuv.value * 2,)).copy() if nuv.value else np.zeros(0, np.uint32),
+                                  np.ctypeslib.as_array(idx, (nt.value * 3,)).copy()))
+    n, mesh_id = C.c_uint32(), C.c_uint32()
+    p = lib.refscene_material_ids(h, C.byref(n), C.byref(mesh_id))
+    out["material_ids"] = np.ctypeslib.as_array(p, (n.value,)).copy()
+    out["materials"] = np.ctypeslib.as_array(lib.refscene_materials(h), (counts[4] * 16,)).copy() if counts[4] else np.zeros(0, np.uint32)
+    out["light"] = np.ctypeslib.as_array(lib.refscene_light(h, 0), (20,)).copy()
+    pm = C.c_uint32()
+    out["instance"] = np.ctypeslib.as_array(lib.refscene_instance(h, 0, C.byref(pm)), (16,)).copy()
+    out["textures"] = []
+    for i in range(counts[5]):
+        w, hh, ch, cs = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        d = lib.refscene_texture(h, i, C.byref(w), C.byref(hh), C.byref(ch), C.byref(cs))
+        out["textures"].append((np.ctypeslib.as_array(d, (hh.value, w.value, ch.value)).copy(), cs.value))
+    lib.refscene_free(h)
+    return out
+
+
+def _native_arrays(path, threads=0):
+    from chameleonrt_b200 import scene_io
+
+    loaded = scene_io.load_obj(path, threads)
+    s = loaded.c_scene.contents
+    out = dict(counts=[s.num_meshes, s.meshes[0].num_geometries, s.num_parameterized_meshes, s.num_instances, s.num_materials,
+                       s.num_textures, s.num_lights], seconds=loaded.timings["total_s"], timings=loaded.timings, warnings=loaded.warnings,
+               geometries=[])
+    u32 = C.POINTER(C.c_uint32)
+    for g in range(s.meshes[0].num_geometries):
+        cg = s.meshes[0].geometries[g]
+        out["geometries"].append((np.ctypeslib.as_array(C.cast(cg.vertices, u32), (cg.num_vertices * 3,)).copy(),
+                                  np.ctypeslib.as_array(C.cast(cg.uvs, u32), (cg.num_vertices * 2,)).copy() if cg.uvs else np.zeros(0, np.uint32),
+                                  np.ctypeslib.as_array(cg.indices, (cg.num_tris * 3,)).copy()))
+    pm = s.parameterized_meshes[0]
+    out["material_ids"] = np.ctypeslib.as_array(pm.material_ids, (pm.num_material_ids,)).copy()
+    out["materials"] = np.ctypeslib.as_array(C.cast(s.materials, u32), (s.num_materials * 16,)).copy() if s.num_materials else np.zeros(0, np.uint32)
+    out["light"] = np.ctypeslib.as_array(C.cast(s.lights, u32), (20,)).copy()
+    out["instance"] = np.ctypeslib.as_array(C.cast(C.pointer(s.instances[0]), u32), (16,)).copy()
+    out["textures"] = [(np.ctypeslib.as_array(s.textures[i].data, (s.textures[i].height, s.textures[i].width, s.textures[i].channels)).copy(),
+                        int(s.textures[i].color_space)) for i in range(s.num_textures)]
+    return out, loaded
+
+
+def _assert_same(a, b):
+    assert a["counts"] == b["counts"]
+    for g, (x, y) in enumerate(zip(a["geometries"], b["geometries"])):
+        for name, p, q in zip(("vertices", "uvs", "indices"), x, y):
+            assert p.shape == q.shape and np.array_equal(p, q), f"geometry {g}: {name} differ"
+    for k in ("material_ids", "materials", "light", "instance"):
+        assert np.array_equal(a[k], b[k]), k
+    for (p, cs1), (q, cs2) in zip(a["textures"], b["textures"]):
+        assert cs1 == cs2 and p.shape == q.shape and np.array_equal(p, q)
+
+
+def _cases():
+    from chameleonrt_b200.scenes import cornell_box, rungholt_like, sponza_like
+
+    return {"cornell": lambda: cornell_box()[0], "sponza_textured": lambda: sponza_like(detail=0.3, tex_size=64)[0],
+            "voxels": lambda: rungholt_like(scale=0.02)[0]}
+
+
+needs_ref = pytest.mark.skipif(not os.path.exists(REFLIB), reason="oracle/_ref/libcrt_refscene.so not built (needs /root/reference)")
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["cornell", "sponza_textured", "voxels"])
+def test_native_obj_loader_builds_the_reference_loaders_scene(built, tmp_path, name):
+    from chameleonrt_b200.obj_io import write_obj
+
+    path = write_obj(_cases()[name](), str(tmp_path / f"{name}.obj"))
+    ref = _reference_arrays(path)
+    for threads in (0, 1, 3):
+        nat, _ = _native_arrays(path, threads)
+        _assert_same(nat, ref)
+    print(f"\n{name}: reference loader {ref['seconds'] * 1e3:.1f} ms, native {nat['timings']}")
+
+
+@needs_ref
+def test_native_obj_loader_on_hand_written_obj_quirks(built, tmp_path):
+    """What tinyobjloader does with the less regular parts of the format: relative (negative) indices, v//vn and v/vt/vn
+    corners (the normal index is part of the remap key), several usemtl inside one group (the first face's material wins,
+    with a warning), an `o` statement, faces before any group, a material that no MTL defines (-> the generated default
+    material), exponents and signs in numbers, CRLF line ends, comments and blank lines."""
+    obj = tmp_path / "quirks.obj"
+    (tmp_path / "quirks.mtl").write_text("# materials\nnewmtl red\nKd 0.8 0.1 0.1\nNs 250\n\nnewmtl shiny\nKd 1e-1 2.5E-1 +0.5\nNs 1000\n")
+    obj.write_text("mtllib quirks.mtl\r\n# a quad as two triangles, no group yet\r\n"
+                   "v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvn 0 0 1\nvn 0 0 -1\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\n"
+                   "usemtl red\nf 1/1/1 2/2/1 3/3/1\nf -4/1/1 -2/3/1 -1/4/1\n"
+                   "g second\nusemtl shiny\nv 0 0 1.5e0\nv 1 0 1.5\nv 1 1 1.5\n\nf 5//1 6//1 7//1\nf 5//2 6//1 7//1\nusemtl red\nf 7//1 6//1 5//1\n"
+                   "o third\nusemtl nowhere\nv -1 -1 -1\nv -2 -1 -1\nv -1 -2 -1\nf 8 9 10\nf 10 9 8\n")
+    ref = _reference_arrays(str(obj))
+    nat, loaded = _native_arrays(str(obj))
+    _assert_same(nat, ref)
+    assert nat["counts"][1] == 3 and nat["counts"][4] == 3  # three shapes; red, shiny + the generated default material
+    assert "per-face material IDs" in loaded.warnings and "generating a default" in loaded.warnings
+
+
+def test_native_obj_loader_errors(built, tmp_path):
+    from chameleonrt_b200 import scene_io
+
+    with pytest.raises(RuntimeError, match="cannot open"):
+        scene_io.load_obj(str(tmp_path / "missing.obj"))
+    quad = tmp_path / "quad.obj"
+    quad.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1 2 3 4\n")
+    with pytest.raises(RuntimeError, match="more than three corners"):
+        scene_io.load_obj(str(quad))
+    zero = tmp_path / "zero.obj"
+    zero.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nf 0 1 2\n")
+    with pytest.raises(RuntimeError, match="zero value for face index"):
+        scene_io.load_obj(str(zero))
+    oob = tmp_path / "oob.obj"
+    oob.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nf 1 2 9\n")
+    with pytest.raises(RuntimeError, match="out of range"):
+        scene_io.load_obj(str(oob))
+
+
+def test_native_obj_loader_round_trip_and_oracle_frame(built, tmp_path):
+    """Without the reference library (the GPU box): the loaded scene equals the scene the OBJ was written from —
+    write_obj / Scene::load_obj are inverse to each other for these scenes (tests/test_reference_plugin.py) — and renders
+    the same frame through the CPU oracle."""
+    from chameleonrt_b200 import ArcballCamera, scene_io
+    from chameleonrt_b200.obj_io import write_obj
+    from chameleonrt_b200.scenes import cornell_box
+    from oracle import OracleBackend
+
+    scene, cam = cornell_box(spp=1)
+    path = write_obj(scene, str(tmp_path / "cornell.obj"))
+    loaded = scene_io.load_obj(path)
+    got = loaded.to_scene(spp=1)
+    assert len(got.meshes[0].geometries) == len(scene.meshes[0].geometries)
+    c = ArcballCamera(cam["eye"], cam["center"], cam["up"])
+    frames = []
+    for s in (scene, got):
+        o = OracleBackend(max_depth=5)
+        o.initialize(48, 32)
+        o.set_scene(s)
+        o.render(c.eye(), c.dir(), c.up(), cam["fov_y"], True, True)
+        frames.append(o.read_accum())
+    assert np.array_equal(frames[0].view(np.uint32), frames[1].view(np.uint32))
+
+
+@needs_ref
+def test_native_obj_loader_is_faster_on_a_large_file(built, tmp_path):
+    """Throughput (the point of the row): a voxel city of a few hundred thousand triangles through both loaders. The bound
+    asserted is loose (the suite runs on shared CPUs); the measured times are printed and recorded in DESIGN.md."""
+    from chameleonrt_b200.obj_io import write_obj
+    from chameleonrt_b200.scenes import rungholt_like
+
+    path = write_obj(rungholt_like(scale=0.12)[0], str(tmp_path / "city.obj"))
+    t0 = time.time()
+    ref = _reference_arrays(path)
+    t_ref = time.time() - t0
+    best = None
+    for _ in range(2):
+        nat, loaded = _native_arrays(path)
+        best = loaded.timings if best is None or loaded.timings["total_s"] < best["total_s"] else best
+    _assert_same(nat, ref)
+    tris = sum(len(g[2]) // 3 for g in nat["geometries"])
+    print(f"\n{tris} triangles, {os.path.getsize(path) / 1e6:.0f} MB: reference loader {ref['seconds']:.2f} s (call {t_ref:.2f} s), native {best}")
+    assert best["total_s"] < ref["seconds"]
