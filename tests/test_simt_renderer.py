@@ -361,3 +361,30 @@ def test_round_2_options_on_the_emulated_renderer(mods):
     r.initialize(16, 16)
     with pytest.raises(RuntimeError, match="cudaMallocArray|not supported"):
         r.set_scene(scene)
+
+
+def test_natively_loaded_obj_renders_the_same_frame(mods, tmp_path, size=(48, 32), detail=0.25):
+    """The scene-load row end to end: OBJ + MTL + PNG written by obj_io -> crtio_load_obj (native, parallel) ->
+    crtc_set_scene on the native crt_scene_t (RenderCUDA.set_scene_c) -> the frame the Python scene model renders, bit for
+    bit (on the B200 the same function runs from tests/test_z_new_gpu_paths.py)."""
+    from chameleonrt_b200 import scene_io
+    from chameleonrt_b200.obj_io import write_obj
+    from chameleonrt_b200.scenes import sponza_like
+
+    RenderCUDA = mods[0]
+    scene, cam = sponza_like(spp=2, detail=detail, tex_size=32)
+    c = camera_for(cam)
+    args = (c.eye(), c.dir(), c.up(), cam["fov_y"])
+    loaded = scene_io.load_obj(write_obj(scene, str(tmp_path / "scene.obj")))
+    frames = []
+    for native in (False, True):
+        r = RenderCUDA(0)
+        r.initialize(*size)
+        if native:
+            r.set_scene_c(loaded.c_scene, samples_per_pixel=2)
+        else:
+            r.set_scene(scene)
+        for f in range(2):
+            st = r.render(*args, f == 0, True)
+        frames.append((r.read_accum(), st.num_rays))
+    assert frames[0][1] == frames[1][1] and np.array_equal(frames[0][0].view(np.uint32), frames[1][0].view(np.uint32))

@@ -336,3 +336,10 @@ def test_hardware_textures_option(mods):
     a, ra = frame(scene, cam, 0, 96, 96)
     b, rb = frame(scene, cam, 1, 96, 96)
     assert np.array_equal(a, b) and ra == rb
+
+
+def test_natively_loaded_obj_renders_the_same_frame_on_the_gpu(mods, tmp_path):
+    """crtio_load_obj -> crtc_set_scene -> frame: tests/test_simt_renderer.py's function on the B200, at a larger size."""
+    from test_simt_renderer import test_natively_loaded_obj_renders_the_same_frame
+
+    test_natively_loaded_obj_renders_the_same_frame(mods, tmp_path, size=(320, 180), detail=0.5)
