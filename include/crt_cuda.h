@@ -75,6 +75,9 @@ void crtc_destroy(crtc_renderer *r);
  *                 unit), as the reference's OptiX backend does (backends/optix/optix_utils.cpp:60-85): 8-bit fixed-point
  *                 filter weights and no re-quantisation of the linearised texels, hence a looser parity with the Embree
  *                 path (dark sRGB texels are not crushed to 0). Takes effect at the next crtc_set_scene.
+ *   "bvh_top_smem" 0 (default) / 1: the traversal kernel reads the first 73 BVH nodes (root + two levels) from a shared-memory
+ *                 copy — BASELINE.json's north_star names this staging; measured on B200 it costs 4-5 % (those nodes are the
+ *                 L1's hottest lines anyway and the copy takes 47 KB of L1 per SM), so it is off. Never changes a result.
  *   "stage_events" 1 (default): a CUDA event after every launch feeds crtc_get_stage_times; 0: events only at the start
  *                 and the end of a frame ([6], the frame time, stays; the other stage times read 0) — 28 event records cost
  *                 ~0.07 ms per frame, which matters when a GPU renders a 1/8 shard in 2 ms. May be changed between frames.
@@ -103,6 +106,9 @@ int crtc_set_option(crtc_renderer *r, const char *key, int64_t value);
 /* Reads an option back. Besides the keys above: "any_far_first_decision" = the shadow-ray order frames are
  * rendered with from now on (0 near-first, 1 far-first, -1 = mode 2 has not decided yet); "bvh_build_rounds" = the
  * number of PLOC rounds of the last device build. */
+/* Readable keys: every key of crtc_set_option, plus "any_far_first_decision" (-1 undecided / 0 near-first / 1 far-first),
+ * "bvh_build_rounds" (PLOC rounds of the last device build) and "bvh_builder_fallbacks" (device builds that gave up on their
+ * input and were redone by the host builder). */
 int crtc_get_option(crtc_renderer *r, const char *key, int64_t *value);
 
 /* Use an existing CUDA stream (cudaStream_t) for all work of this renderer; NULL = the
