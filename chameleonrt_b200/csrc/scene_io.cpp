@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <limits>
 #include <map>
 #include <memory>
 #include <sstream>
@@ -274,15 +275,28 @@ struct MappedFile {
 enum EventKind { kEvGroup, kEvObject, kEvUseMtl, kEvMtlLib };
 struct Event {
     EventKind kind;
-    size_t face;       // faces read before this line (global after the prefix sums)
+    size_t face;       // triangle slots of the faces read before this line (chunk-local; + Chunk::f0 = global)
+    size_t nv;         // `v` statements read before this line (chunk-local; + Chunk::v0 = global)
     std::string text;  // the rest of the line
 };
 
+// A face with more than three corners: its corners wait in Chunk::poly_corners until every vertex position is known
+struct Polygon {
+    size_t slot;     // first of its corners - 2 triangle slots (global)
+    uint32_t first;  // index of its first corner in Chunk::poly_corners
+    uint32_t corners;
+};
+
+constexpr int32_t kNoTriangle = INT32_MIN;  // v index of a triangle slot that holds no triangle
+
 struct Chunk {
     size_t begin = 0, end = 0;
-    size_t nv = 0, nvt = 0, nvn = 0, nf = 0;       // counts of this chunk
+    size_t nv = 0, nvt = 0, nvn = 0, nf = 0;       // counts of this chunk (nf: triangle slots, face_slots() per face)
     size_t v0 = 0, vt0 = 0, vn0 = 0, f0 = 0;       // counts before this chunk
     std::vector<Event> events;
+    std::vector<Polygon> polys;
+    std::vector<Triple> poly_corners;
+    bool empty_slots = false;  // a face of fewer than three corners was read (its slot stays empty)
     std::string error;
 };
 
@@ -338,6 +352,29 @@ inline LineKind classify(const char *&tok, const char *line_end)
         }
     }
     return kLineOther;
+}
+
+// Corners of an `f` statement = its blank-separated tokens: LoadObj (:1950-1973) reads one index triple, then skips blanks
+// and carriage returns, until the line ends; a token that is more or less than one triple makes parseTriple fail (the
+// second pass reports that).
+inline size_t count_corners(const char *tok, const char *line_end)
+{
+    size_t n = 0;
+    bool in_token = false;
+    for (; tok < line_end; ++tok) {
+        const bool blank = is_blank(*tok) || *tok == '\r';
+        n += (!blank && !in_token) ? 1 : 0;
+        in_token = !blank;
+    }
+    return n;
+}
+
+// Triangle slots a face of `corners` corners gets: the ear clipping of exportGroupsToShape emits at most corners - 2
+// triangles; a face of fewer than three corners still is a face of its group (faceGroup.empty() decides whether a shape
+// is exported), so it keeps one slot, which stays empty.
+inline size_t face_slots(size_t corners)
+{
+    return corners > 3 ? corners - 2 : 1;
 }
 
 // [line_begin, line_end) of the line that starts at p; line_end excludes '\n' and a '\r' before it
@@ -625,11 +662,15 @@ void remap_shape(const std::vector<float> &V, const std::vector<float> &VT, cons
         uint32_t index;
     };
     std::vector<Slot> table(cap, Slot{-2, 0, 0, 0});
-    g.indices.resize(num_faces * 3);
+    g.indices.reserve(num_faces * 3);
     g.vertices.reserve(num_faces * 3);
     const size_t nv = V.size() / 3, nvt = VT.size() / 2;
     bool any_uv = false, any_without_uv = false;
     for (size_t c = 0; c < num_faces * 3; ++c) {
+        if (c % 3 == 0 && faces[3 * c] == kNoTriangle) {  // a slot no triangle was made for
+            c += 2;
+            continue;
+        }
         const int32_t v = faces[3 * c], vn = faces[3 * c + 1], vt = faces[3 * c + 2];
         uint64_t h = (uint64_t)(uint32_t)v * 0x9E3779B97F4A7C15ull;
         h ^= ((uint64_t)(uint32_t)vt + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
@@ -655,11 +696,11 @@ void remap_shape(const std::vector<float> &V, const std::vector<float> &VT, cons
                 } else {
                     any_without_uv = true;
                 }
-                g.indices[c] = s.index;
+                g.indices.push_back(s.index);
                 break;
             }
             if (s.v == v && s.vn == vn && s.vt == vt) {
-                g.indices[c] = s.index;
+                g.indices.push_back(s.index);
                 break;
             }
             slot = (slot + 1) & (cap - 1);
@@ -668,6 +709,132 @@ void remap_shape(const std::vector<float> &V, const std::vector<float> &VT, cons
     if (any_uv && any_without_uv) {
         throw std::runtime_error("some corners of " + what + " have texture coordinates and some have none");
     }
+}
+
+// pnpoly as tinyobjloader uses it on one candidate ear (tiny_obj_loader.h:1064-1076): is (tx, ty) inside the triangle?
+inline bool point_in_triangle(const float x[3], const float y[3], float tx, float ty)
+{
+    bool inside = false;
+    for (int i = 0, j = 2; i < 3; j = i++) {
+        if (((y[i] > ty) != (y[j] > ty)) && (tx < (x[j] - x[i]) * (ty - y[i]) / (y[j] - y[i]) + x[i])) {
+            inside = !inside;
+        }
+    }
+    return inside;
+}
+
+// The triangulation of one face of more than three corners, as exportGroupsToShape does it (tiny_obj_loader.h:1107-1310;
+// Scene::load_obj calls LoadObj with triangulate = true): the polygon is projected on the two axes its first non-degenerate
+// corner spans best, its signed area gives the winding, and ears are clipped — a corner that turns the polygon's way and
+// holds no other remaining corner inside — starting the search where the last ear was found. A polygon the search gets
+// stuck on (no ear in a full round) keeps the triangles found so far and loses the rest, as in tinyobjloader. All in
+// float, in tinyobjloader's order of operations, since which ear comes first decides the triangles and their order.
+// V / vcount: the positions read when the face group was exported (corners that point past them count as (0, 0) or are
+// skipped, as there). Writes up to n - 2 triangles of 3 x (v, vn, vt) to `out`, returns how many.
+size_t ear_clip(const float *V, size_t vcount, const Triple *corner, size_t n, int32_t *out)
+{
+    const auto known = [&](int v) { return (size_t)(int64_t)v < vcount; };
+    size_t axes[2] = {1, 2};
+    for (size_t k = 0; k < n; ++k) {
+        const int a = corner[k % n].v, b = corner[(k + 1) % n].v, c = corner[(k + 2) % n].v;
+        if (!known(a) || !known(b) || !known(c)) {
+            continue;
+        }
+        const float *p0 = V + 3 * (size_t)a, *p1 = V + 3 * (size_t)b, *p2 = V + 3 * (size_t)c;
+        const float e0x = p1[0] - p0[0], e0y = p1[1] - p0[1], e0z = p1[2] - p0[2];
+        const float e1x = p2[0] - p1[0], e1y = p2[1] - p1[1], e1z = p2[2] - p1[2];
+        const float cx = std::fabs(e0y * e1z - e0z * e1y);
+        const float cy = std::fabs(e0z * e1x - e0x * e1z);
+        const float cz = std::fabs(e0x * e1y - e0y * e1x);
+        const float epsilon = std::numeric_limits<float>::epsilon();
+        if (cx > epsilon || cy > epsilon || cz > epsilon) {
+            if (!(cx > cy && cx > cz)) {
+                axes[0] = 0;
+                if (cz > cx && cz > cy) {
+                    axes[1] = 1;
+                }
+            }
+            break;
+        }
+    }
+    float area = 0.f;
+    for (size_t k = 0; k < n; ++k) {
+        const int a = corner[k].v, b = corner[(k + 1) % n].v;
+        if (!known(a) || !known(b)) {
+            continue;
+        }
+        const float ax = V[3 * (size_t)a + axes[0]], ay = V[3 * (size_t)a + axes[1]];
+        const float bx = V[3 * (size_t)b + axes[0]], by = V[3 * (size_t)b + axes[1]];
+        area += (ax * by - ay * bx) * 0.5f;
+    }
+    const auto emit = [&](const Triple &a, const Triple &b, const Triple &c, size_t at) {
+        const Triple t[3] = {a, b, c};
+        for (int k = 0; k < 3; ++k) {
+            out[9 * at + 3 * k] = t[k].v;
+            out[9 * at + 3 * k + 1] = t[k].vn;
+            out[9 * at + 3 * k + 2] = t[k].vt;
+        }
+    };
+    Triple small[16];
+    std::vector<Triple> large;
+    Triple *rest = small;  // the corners not clipped yet
+    if (n > 16) {
+        large.assign(corner, corner + n);
+        rest = large.data();
+    } else {
+        std::copy(corner, corner + n, small);
+    }
+    size_t left = n, emitted = 0, guess = 0;
+    size_t rounds_left = n, left_before = n;  // iterations allowed without clipping a corner
+    while (left > 3 && rounds_left > 0) {
+        if (guess >= left) {
+            guess -= left;
+        }
+        if (left_before != left) {
+            left_before = left;
+            rounds_left = left;
+        } else {
+            --rounds_left;
+        }
+        Triple ind[3];
+        float x[3], y[3];
+        for (size_t k = 0; k < 3; ++k) {
+            ind[k] = rest[(guess + k) % left];
+            if (known(ind[k].v)) {
+                x[k] = V[3 * (size_t)ind[k].v + axes[0]];
+                y[k] = V[3 * (size_t)ind[k].v + axes[1]];
+            } else {
+                x[k] = 0.f;
+                y[k] = 0.f;
+            }
+        }
+        const float e0x = x[1] - x[0], e0y = y[1] - y[0], e1x = x[2] - x[1], e1y = y[2] - y[1];
+        const float cross = e0x * e1y - e0y * e1x;
+        if (cross * area < 0.f) {  // turns against the polygon: not an ear
+            ++guess;
+            continue;
+        }
+        bool overlap = false;
+        for (size_t other = 3; other < left && !overlap; ++other) {
+            const int ov = rest[(guess + other) % left].v;
+            if (known(ov)) {
+                overlap = point_in_triangle(x, y, V[3 * (size_t)ov + axes[0]], V[3 * (size_t)ov + axes[1]]);
+            }
+        }
+        if (overlap) {
+            ++guess;
+            continue;
+        }
+        emit(ind[0], ind[1], ind[2], emitted++);
+        for (size_t r = (guess + 1) % left; r + 1 < left; ++r) {  // the ear's tip leaves the polygon
+            rest[r] = rest[r + 1];
+        }
+        --left;
+    }
+    if (left == 3) {
+        emit(rest[0], rest[1], rest[2], emitted++);
+    }
+    return emitted;
 }
 
 void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
@@ -702,11 +869,11 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
             case kLineV: c.nv++; break;
             case kLineVT: c.nvt++; break;
             case kLineVN: c.nvn++; break;
-            case kLineF: c.nf++; break;
-            case kLineG: c.events.push_back(Event{kEvGroup, c.nf, std::string()}); break;
-            case kLineO: c.events.push_back(Event{kEvObject, c.nf, std::string()}); break;
-            case kLineUseMtl: c.events.push_back(Event{kEvUseMtl, c.nf, std::string(tok, le)}); break;
-            case kLineMtlLib: c.events.push_back(Event{kEvMtlLib, c.nf, std::string(tok, le)}); break;
+            case kLineF: c.nf += face_slots(count_corners(tok, le)); break;
+            case kLineG: c.events.push_back(Event{kEvGroup, c.nf, c.nv, std::string()}); break;
+            case kLineO: c.events.push_back(Event{kEvObject, c.nf, c.nv, std::string()}); break;
+            case kLineUseMtl: c.events.push_back(Event{kEvUseMtl, c.nf, c.nv, std::string(tok, le)}); break;
+            case kLineMtlLib: c.events.push_back(Event{kEvMtlLib, c.nf, c.nv, std::string(tok, le)}); break;
             default: break;
             }
             p = next;
@@ -747,11 +914,13 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
                 ++vn;
                 break;
             case kLineF: {
+                const size_t expected = count_corners(tok, le);
                 while (tok < le && is_blank(*tok)) {
                     ++tok;
                 }
-                int corners = 0;
+                size_t corners = 0;
                 Triple t[3];
+                const size_t poly_first = c.poly_corners.size();
                 while (tok < le && *tok != '\r') {
                     Triple tr;
                     if (!parse_triple(tok, le, (int)v, (int)vn, (int)vt, &tr)) {
@@ -761,23 +930,35 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
                     if (corners < 3) {
                         t[corners] = tr;
                     }
+                    if (expected > 3) {
+                        c.poly_corners.push_back(tr);
+                    }
                     ++corners;
                     while (tok < le && (is_blank(*tok) || *tok == '\r')) {
                         ++tok;
                     }
                 }
-                if (c.error.empty() && corners != 3) {
-                    c.error = corners > 3 ? "a face with more than three corners (this loader reads triangle meshes; tinyobjloader would ear-clip it)"
-                                          : "a face with fewer than three corners";
+                if (c.error.empty() && corners != expected) {
+                    c.error = "Failed parse `f' line(a corner that is not one index triple)";
                 }
                 if (c.error.empty()) {
-                    for (int k = 0; k < 3; ++k) {
-                        F[9 * f + 3 * k] = t[k].v;
-                        F[9 * f + 3 * k + 1] = t[k].vn;
-                        F[9 * f + 3 * k + 2] = t[k].vt;
+                    const size_t slots = face_slots(corners);
+                    for (size_t k = 0; k < slots; ++k) {
+                        F[9 * (f + k)] = kNoTriangle;
                     }
+                    if (corners == 3) {
+                        for (int k = 0; k < 3; ++k) {
+                            F[9 * f + 3 * k] = t[k].v;
+                            F[9 * f + 3 * k + 1] = t[k].vn;
+                            F[9 * f + 3 * k + 2] = t[k].vt;
+                        }
+                    } else if (corners > 3) {
+                        c.polys.push_back(Polygon{f, (uint32_t)poly_first, (uint32_t)corners});
+                    } else {
+                        c.empty_slots = true;
+                    }
+                    f += slots;
                 }
-                ++f;
                 break;
             }
             default: break;
@@ -791,9 +972,10 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
         }
     }
     // ---- shapes, from the events in file order (LoadObj's handling of usemtl / g / o, :1979-2128 and :2200-2212) ----
-    struct Segment {
-        size_t begin, end;
+    struct Segment {   // one exportGroupsToShape call
+        size_t begin, end;  // triangle slots
         int material;
+        size_t vcount;      // positions read when the group was exported (what the ear clipping may look at)
     };
     struct Shape {
         std::vector<Segment> segments;
@@ -811,23 +993,23 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
         Shape shape;
         int material = -1;
         size_t group_begin = 0;  // first face of the current face group
-        auto export_group = [&](size_t pos) {
+        auto export_group = [&](size_t pos, size_t vcount) {
             if (group_begin == pos) {
                 return false;
             }
-            shape.segments.push_back(Segment{group_begin, pos, material});
+            shape.segments.push_back(Segment{group_begin, pos, material, vcount});
             group_begin = pos;
             return true;
         };
         for (const Chunk &c : chunks) {
             for (const Event &ev : c.events) {
-                const size_t pos = c.f0 + ev.face;
+                const size_t pos = c.f0 + ev.face, vcount = c.v0 + ev.nv;
                 switch (ev.kind) {
                 case kEvUseMtl: {
                     const auto it = material_map.find(ev.text);
                     const int id = it != material_map.end() ? it->second : -1;
                     if (id != material) {
-                        export_group(pos);
+                        export_group(pos, vcount);
                         material = id;
                     }
                     break;
@@ -853,14 +1035,14 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
                     break;
                 }
                 case kEvGroup:
-                    export_group(pos);
+                    export_group(pos, vcount);
                     if (!shape.segments.empty()) {
                         shapes.push_back(shape);
                     }
                     shape = Shape();
                     break;
                 case kEvObject:
-                    if (export_group(pos)) {  // (a shape whose faces were all flushed by an earlier usemtl is dropped: :2105-2109)
+                    if (export_group(pos, vcount)) {  // (a shape whose faces were all flushed by an earlier usemtl is dropped: :2105-2109)
                         shapes.push_back(shape);
                     }
                     shape = Shape();
@@ -868,9 +1050,43 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
                 }
             }
         }
-        const bool ret = export_group(nf);
+        const bool ret = export_group(nf, nv);
         if (ret || !shape.segments.empty()) {
             shapes.push_back(shape);
+        }
+    }
+    // ---- faces of more than three corners: ear clipping into their triangle slots, now that the positions are there ----
+    bool empty_slots = false;
+    {
+        std::vector<const Segment *> exported;  // in slot order
+        size_t num_polys = 0;
+        for (const Shape &sh : shapes) {
+            for (const Segment &seg : sh.segments) {
+                exported.push_back(&seg);
+            }
+        }
+        for (const Chunk &c : chunks) {
+            num_polys += c.polys.size();
+            empty_slots = empty_slots || c.empty_slots;
+        }
+        if (num_polys) {
+            std::vector<uint8_t> chunk_lost(chunks.size(), 0);
+            crt::parallel_blocks((uint32_t)chunks.size(), nthreads, [&](uint32_t ci) {
+                const Chunk &c = chunks[ci];
+                for (const Polygon &poly : c.polys) {
+                    // the face group this polygon was exported with (none: its shape was dropped)
+                    auto it = std::upper_bound(exported.begin(), exported.end(), poly.slot,
+                                               [](size_t slot, const Segment *seg) { return slot < seg->end; });
+                    if (it == exported.end() || poly.slot < (*it)->begin) {
+                        continue;
+                    }
+                    const size_t made = ear_clip(V.data(), (*it)->vcount, c.poly_corners.data() + poly.first, poly.corners, F.data() + 9 * poly.slot);
+                    if (made != (size_t)poly.corners - 2) {
+                        chunk_lost[ci] = 1;
+                    }
+                }
+            });
+            empty_slots = empty_slots || std::find(chunk_lost.begin(), chunk_lost.end(), 1) != chunk_lost.end();
         }
     }
     const double t_parsed = now_s();
@@ -878,13 +1094,32 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
     S.geometries.resize(shapes.size());
     S.material_ids.resize(shapes.size());
     for (size_t s = 0; s < shapes.size(); ++s) {
-        S.material_ids[s] = (uint32_t)shapes[s].segments[0].material;  // the first face's material (scene.cpp:127)
+        // The material of a shape is its first triangle's (scene.cpp:127); a shape whose triangles do not all have that
+        // material gets the warning of scene.cpp:131-137. Only face groups that hold a triangle count.
+        bool first = true, mixed = false;
+        int material = -1;
         for (const Segment &seg : shapes[s].segments) {
-            if (seg.material != shapes[s].segments[0].material) {
-                warn << "Warning: per-face material IDs are not supported, materials may look wrong. Please reexport your mesh with each "
-                        "material group as an OBJ group\n";
-                break;
+            bool holds_triangle = !empty_slots;
+            for (size_t f = seg.begin; f < seg.end && !holds_triangle; ++f) {
+                holds_triangle = F[9 * f] != kNoTriangle;
             }
+            if (!holds_triangle) {
+                continue;
+            }
+            if (first) {
+                material = seg.material;
+                first = false;
+            } else if (seg.material != material) {
+                mixed = true;
+            }
+        }
+        if (first) {  // (the reference reads material_ids[0] of an empty array here)
+            throw std::runtime_error("a shape without a triangle (its faces have fewer than three corners or no area) in " + file);
+        }
+        S.material_ids[s] = (uint32_t)material;
+        if (mixed) {
+            warn << "Warning: per-face material IDs are not supported, materials may look wrong. Please reexport your mesh with each "
+                    "material group as an OBJ group\n";
         }
     }
     std::vector<std::string> shape_errors(shapes.size());

@@ -103,12 +103,10 @@ void crtc_destroy(crtc_renderer *r);
  */
 int crtc_set_option(crtc_renderer *r, const char *key, int64_t value);
 
-/* Reads an option back. Besides the keys above: "any_far_first_decision" = the shadow-ray order frames are
- * rendered with from now on (0 near-first, 1 far-first, -1 = mode 2 has not decided yet); "bvh_build_rounds" = the
- * number of PLOC rounds of the last device build. */
-/* Readable keys: every key of crtc_set_option, plus "any_far_first_decision" (-1 undecided / 0 near-first / 1 far-first),
- * "bvh_build_rounds" (PLOC rounds of the last device build) and "bvh_builder_fallbacks" (device builds that gave up on their
- * input and were redone by the host builder). */
+/* Reads an option back. Readable keys: every key of crtc_set_option, plus "any_far_first_decision" = the shadow-ray order
+ * frames are rendered with from now on (0 near-first, 1 far-first, -1 = mode 2 has not decided yet), "bvh_build_rounds" =
+ * the number of PLOC rounds of the last device build, and "bvh_builder_fallbacks" = device builds that gave up on their
+ * input and were redone by the host builder. */
 int crtc_get_option(crtc_renderer *r, const char *key, int64_t *value);
 
 /* Use an existing CUDA stream (cudaStream_t) for all work of this renderer; NULL = the

@@ -11,8 +11,10 @@
  *
  * The result is a crt_scene_t (include/crt_scene.h) owned by the handle: pass crtio_scene_view(h) to crtc_set_scene.
  *
- * Supported: what Scene::load_obj supports for the scenes of this project — triangle faces (a polygon with more than three
- * corners is an error here; tinyobjloader would ear-clip it), v / vt / vn / f / g / o / usemtl / mtllib, MTL newmtl / Kd /
+ * Supported: what Scene::load_obj supports for the scenes of this project — faces of any number of corners (more than three:
+ * cut into triangles by tinyobjloader's own ear clipping, tiny_obj_loader.h:1107-1310, restated in float in the same order of
+ * operations so that the same triangles come out in the same order — also where that clipping gives up on a degenerate
+ * polygon and drops the rest of it; fewer than three: skipped), v / vt / vn / f / g / o / usemtl / mtllib, MTL newmtl / Kd /
  * Ns / map_Kd (other statements are ignored as the reference ignores them), 8-bit non-interlaced PNG textures (grey, grey +
  * alpha, RGB, RGBA, palette), which the reference loads through stb_image, flipped vertically and expanded to RGBA
  * (util/material.cpp:5-17). */

@@ -148,15 +148,119 @@ def test_native_obj_loader_on_hand_written_obj_quirks(built, tmp_path):
     assert "per-face material IDs" in loaded.warnings and "generating a default" in loaded.warnings
 
 
+def _polygon_obj(path, seed, faces=400):
+    """An OBJ of faces with 3 to 12 corners: convex and star-shaped (concave) polygons in arbitrary planes, non-planar
+    ones, self-intersecting ones (corners in shuffled order), polygons with collinear runs, repeated corners and zero
+    area, faces of one and two corners; with and without vt / vn indices; several groups, objects and materials."""
+    rng = np.random.default_rng(seed)
+    lines, nv, nvt = ["mtllib poly.mtl"], 0, 0
+    for i in range(16):
+        lines.append(f"vn {rng.normal():.4f} {rng.normal():.4f} {rng.normal():.4f}")
+    for f in range(faces):
+        if f % 37 in (0, 19):
+            lines.append(f"g group{f}" if (f // 37) % 3 else f"o object{f}")
+        if f % 23 == 0:
+            lines.append(f"usemtl m{(f // 23) % 3}")
+        n = int(rng.integers(3, 13))
+        kind = int(rng.integers(0, 8))
+        origin, ex, ey = rng.normal(size=3) * 3, rng.normal(size=3), rng.normal(size=3)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+        rad = np.ones(n)
+        if kind == 1:
+            rad = np.where(np.arange(n) % 2, 0.35, 1.0)  # a star
+        elif kind == 2:
+            rad = rng.uniform(0.2, 1.5, n)
+        pts = origin + np.outer(np.cos(ang) * rad, ex) + np.outer(np.sin(ang) * rad, ey)
+        if kind == 3:
+            pts += rng.normal(size=(n, 3)) * 0.2  # not planar
+        elif kind == 4:
+            pts = pts[rng.permutation(n)]  # self-intersecting
+        elif kind == 5:
+            pts = origin + np.outer(np.linspace(0, 1, n), ex)  # all on one line
+        elif kind == 6 and n > 3:
+            pts[1] = pts[0]  # a repeated corner
+            pts[n - 1] = 0.5 * (pts[n - 2] + pts[0])  # and a collinear one
+        elif kind == 7 and f % 37 not in (0, 19):
+            n = int(rng.integers(1, 3))  # a face that is none
+            pts = pts[:n]
+        if rng.integers(0, 2):
+            pts = pts[::-1]
+        fmt = "%.6g" if f % 2 else "%.3f"
+        for q in pts:
+            lines.append("v " + " ".join(fmt % x for x in q))
+        style = (1 + 2 * int(rng.integers(0, 2))) if f % 37 > 18 else 2 * int(rng.integers(0, 2))  # (all corners of a shape have uvs or none)
+        if style in (1, 3):
+            for q in pts:
+                lines.append(f"vt {rng.uniform():.4f} {rng.uniform():.4f}")
+        corners = []
+        for k in range(n):
+            v = nv + k + 1 if f % 3 else k - n  # absolute or relative
+            vt, vn = nvt + k + 1, int(rng.integers(1, 17))
+            corners.append([f"{v}", f"{v}/{vt}", f"{v}//{vn}", f"{v}/{vt}/{vn}"][style])
+        lines.append("f " + ("  " if f % 5 == 0 else " ").join(corners) + (" \r" if f % 7 == 0 else ""))
+        nv += n
+        nvt += n if style in (1, 3) else 0
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    with open(os.path.join(os.path.dirname(path), "poly.mtl"), "w") as fh:
+        fh.write("newmtl m0\nKd 0.8 0.2 0.2\nnewmtl m1\nKd 0.2 0.8 0.2\nNs 100\nnewmtl m2\nKd 0.2 0.2 0.8\n")
+    return path
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_native_obj_loader_triangulates_polygons_as_tinyobjloader_does(built, tmp_path, seed):
+    """Faces of more than three corners: the ear clipping of exportGroupsToShape (tiny_obj_loader.h:1107-1310), restated in
+    ear_clip() — same triangles in the same order, also where the clipping gives up on a polygon."""
+    path = _polygon_obj(str(tmp_path / "poly.obj"), seed)
+    ref = _reference_arrays(path)
+    for threads in (0, 1):
+        nat, _ = _native_arrays(path, threads)
+        _assert_same(nat, ref)
+    tris = sum(len(g[2]) // 3 for g in nat["geometries"])
+    assert tris > 400
+    if seed == 1:
+        # corners that point at positions the file defines later: the ear clipping sees what was read when the face group
+        # was exported (here: at the `g` line), and takes (0, 0) for the rest
+        fwd = tmp_path / "forward.obj"
+        fwd.write_text("v 0 0 0\nv 2 0 0\nv 2 2 0\nv 1 0.5 0\nf 1 2 3 4 5 6\ng later\nv 0 2 0\nv -1 1 0\nf 1 2 3 4 5 6\nf 1 2 6 3 5 4\n")
+        _assert_same(_native_arrays(str(fwd))[0], _reference_arrays(str(fwd)))
+
+
+def test_native_obj_loader_quads_without_the_reference(built, tmp_path):
+    """Known answers (hold on the GPU box too): a convex quad is cut into (0, 1, 2) and (0, 2, 3); of a dart the ear that
+    would contain the reflex corner is skipped."""
+    from chameleonrt_b200 import scene_io
+
+    quad = tmp_path / "quad.obj"
+    quad.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1 2 3 4\n")
+    loaded = scene_io.load_obj(str(quad))  # (owns the arrays)
+    g = loaded.c_scene.contents.meshes[0].geometries[0]
+    assert g.num_tris == 2 and g.num_vertices == 4
+    assert list(np.ctypeslib.as_array(g.indices, (6,))) == [0, 1, 2, 0, 2, 3]
+    dart = tmp_path / "dart.obj"  # corner 2 (0.2, 0.2) is reflex
+    dart.write_text("v 0 0 0\nv 1 0 0\nv 0.2 0.2 0\nv 0 1 0\nf 1 2 3 4\n")
+    loaded = scene_io.load_obj(str(dart))
+    g = loaded.c_scene.contents.meshes[0].geometries[0]
+    idx = np.ctypeslib.as_array(g.indices, (g.num_tris * 3,)).reshape(-1, 3)
+    v = np.ctypeslib.as_array(g.vertices, (g.num_vertices * 3,)).reshape(-1, 3)
+    area = sum(0.5 * np.cross(v[t[1]] - v[t[0]], v[t[2]] - v[t[0]])[2] for t in idx)
+    assert g.num_tris == 2 and abs(area - 0.2) < 1e-6  # the dart's area: both triangles inside it
+
+
 def test_native_obj_loader_errors(built, tmp_path):
     from chameleonrt_b200 import scene_io
 
     with pytest.raises(RuntimeError, match="cannot open"):
         scene_io.load_obj(str(tmp_path / "missing.obj"))
-    quad = tmp_path / "quad.obj"
-    quad.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1 2 3 4\n")
-    with pytest.raises(RuntimeError, match="more than three corners"):
-        scene_io.load_obj(str(quad))
+    flat = tmp_path / "flat.obj"  # (the reference indexes an empty material_ids array here)
+    flat.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nf 1 2\n")
+    with pytest.raises(RuntimeError, match="without a triangle"):
+        scene_io.load_obj(str(flat))
+    glued = tmp_path / "glued.obj"
+    glued.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nf 1/1/1/1 2 3\n")
+    with pytest.raises(RuntimeError, match="Failed parse `f' line"):
+        scene_io.load_obj(str(glued))
     zero = tmp_path / "zero.obj"
     zero.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nf 0 1 2\n")
     with pytest.raises(RuntimeError, match="zero value for face index"):
