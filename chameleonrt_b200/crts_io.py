@@ -30,7 +30,9 @@ def _num(v: float) -> float:
     return float(np.float32(v))
 
 
-def write_crts(scene: Scene, path: str) -> str:
+def write_crts(scene: Scene, path: str, extra_objects=(), align: bool = True) -> str:
+    """``extra_objects``: header objects appended as they are (e.g. CAMERA objects, lights with an arbitrary frame);
+    ``align=False`` leaves the data block wherever the header ends (the loader must not rely on alignment)."""
     from PIL import Image as PILImage
 
     data = bytearray()
@@ -101,9 +103,12 @@ def write_crts(scene: Scene, path: str) -> str:
         objects.append({"type": "LIGHT", "color": [_num(x) for x in e], "energy": 1.0,
                         "size": [_num(l.width), _num(l.height)], "matrix": [_num(x) for x in mat.T.reshape(-1)]})
 
+    objects.extend(extra_objects)
     header = {"meshes": meshes, "images": images, "materials": materials, "objects": objects, "buffer_views": views}
     js = json.dumps(header).encode()
     js += b" " * ((-(len(js) + 8)) % 8)  # keep the data block 8-byte aligned
+    if not align:
+        js += b" "
     with open(path, "wb") as f:
         f.write(struct.pack("<Q", len(js)))
         f.write(js)

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cerrno>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -26,6 +27,7 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "host_parallel.h"
@@ -237,7 +239,7 @@ struct MappedFile {
     const char *data = nullptr;
     size_t size = 0;
     int fd = -1;
-    explicit MappedFile(const std::string &path)
+    explicit MappedFile(const std::string &path, bool sequential = true)
     {
         fd = open(path.c_str(), O_RDONLY);
         if (fd < 0) {
@@ -255,7 +257,7 @@ struct MappedFile {
                 close(fd);
                 throw std::runtime_error("cannot map " + path);
             }
-            madvise(p, size, MADV_SEQUENTIAL);
+            madvise(p, size, sequential ? MADV_SEQUENTIAL : MADV_WILLNEED);
             data = static_cast<const char *>(p);
         }
     }
@@ -484,13 +486,17 @@ uint32_t be32(const uint8_t *p)
     return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
 }
 
-void load_png_rgba_flipped(const std::string &path, std::vector<uint8_t> &out, int &width, int &height)
+// `file`: the bytes of a PNG file; `path`: its name for messages
+void decode_png_rgba_flipped(const uint8_t *file_data, size_t file_size, const std::string &path, std::vector<uint8_t> &out, int &width,
+                             int &height)
 {
-    std::ifstream in(path.c_str(), std::ios::binary);
-    if (!in) {
-        throw std::runtime_error("Failed to load " + path);  // util/material.cpp:11-13
-    }
-    std::vector<uint8_t> file((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    struct Bytes {  // (the body below was written against a vector)
+        const uint8_t *p;
+        size_t n;
+        size_t size() const { return n; }
+        const uint8_t *data() const { return p; }
+        const uint8_t &operator[](size_t i) const { return p[i]; }
+    } file{file_data, file_size};
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
     if (file.size() < 8 + 25 || std::memcmp(file.data(), sig, 8) != 0) {
         throw std::runtime_error("not a PNG file (only PNG textures are supported by this loader): " + path);
@@ -574,8 +580,14 @@ void load_png_rgba_flipped(const std::string &path, std::vector<uint8_t> &out, i
         for (int x = 0; x < width; ++x) {
             uint8_t r, g, b, a = 255;
             switch (color_type) {
-            case 0: r = g = b = src[x]; break;
-            case 2: r = src[3 * x], g = src[3 * x + 1], b = src[3 * x + 2]; break;
+            case 0:  // (tRNS of a grey / RGB image: the one colour that is transparent, stbi__compute_transparency)
+                r = g = b = src[x];
+                a = (trns.size() >= 2 && r == trns[1]) ? 0 : 255;
+                break;
+            case 2:
+                r = src[3 * x], g = src[3 * x + 1], b = src[3 * x + 2];
+                a = (trns.size() >= 6 && r == trns[1] && g == trns[3] && b == trns[5]) ? 0 : 255;
+                break;
             case 3: {
                 const size_t i = src[x];
                 if (3 * i + 2 >= palette.size()) {
@@ -591,6 +603,16 @@ void load_png_rgba_flipped(const std::string &path, std::vector<uint8_t> &out, i
             dst[4 * x] = r, dst[4 * x + 1] = g, dst[4 * x + 2] = b, dst[4 * x + 3] = a;
         }
     }
+}
+
+void load_png_rgba_flipped(const std::string &path, std::vector<uint8_t> &out, int &width, int &height)
+{
+    std::ifstream in(path.c_str(), std::ios::binary);
+    if (!in) {
+        throw std::runtime_error("Failed to load " + path);  // util/material.cpp:11-13
+    }
+    const std::vector<uint8_t> file((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    decode_png_rgba_flipped(file.data(), file.size(), path, out, width, height);
 }
 
 // glm::normalize(v) = v * inversesqrt(dot(v, v)), inversesqrt(x) = 1 / sqrt(x)
@@ -632,22 +654,77 @@ struct GeometryData {
 }  // namespace
 
 struct crtio_scene {
-    std::vector<GeometryData> geometries;
+    std::unique_ptr<MappedFile> mapping;  // .crts: the geometry arrays are the file's own bytes where their alignment allows
+    std::vector<GeometryData> geometries;  // OBJ: the arrays of its shapes
+    std::vector<std::vector<uint8_t>> unaligned_copies;  // .crts: arrays that sit misaligned in the file
     std::vector<crt_geometry_t> geometry_views;
-    crt_mesh_t mesh{};
-    std::vector<uint32_t> material_ids;
-    crt_parameterized_mesh_t parameterized_mesh{};
-    crt_instance_t instance{};
+    std::vector<crt_mesh_t> meshes;
+    std::vector<std::vector<uint32_t>> material_ids;  // per parameterized mesh
+    std::vector<crt_parameterized_mesh_t> parameterized_meshes;
+    std::vector<crt_instance_t> instances;
     std::vector<crt_material_t> materials;
     std::vector<std::vector<uint8_t>> texture_data;
     std::vector<crt_image_t> textures;
-    crt_quad_light_t light{};
+    std::vector<crt_quad_light_t> lights;
+    std::vector<crtio_camera_t> cameras;
     crt_scene_t view{};
     std::string warnings;
     double timings[4] = {0, 0, 0, 0};
+
+    void finish_views()  // after every vector above has its final size
+    {
+        for (size_t i = 0; i < parameterized_meshes.size(); ++i) {
+            parameterized_meshes[i].material_ids = material_ids[i].data();
+            parameterized_meshes[i].num_material_ids = (uint32_t)material_ids[i].size();
+        }
+        view = crt_scene_t{meshes.data(), parameterized_meshes.data(), instances.data(), materials.data(), textures.data(), lights.data(),
+                           (uint32_t)meshes.size(), (uint32_t)parameterized_meshes.size(), (uint32_t)instances.size(),
+                           (uint32_t)materials.size(), (uint32_t)textures.size(), (uint32_t)lights.size(), 1u};
+    }
 };
 
 namespace {
+
+// Scene::validate_materials (scene.cpp:935-957): geometries without a material get a default DisneyMaterial
+void validate_materials(crtio_scene &S, std::ostream &warn)
+{
+    bool need_default = false;
+    for (const std::vector<uint32_t> &ids : S.material_ids) {
+        need_default = need_default || std::find(ids.begin(), ids.end(), 0xffffffffu) != ids.end();
+    }
+    if (!need_default) {
+        return;
+    }
+    crt_material_t d;  // DisneyMaterial's defaults, util/material.h:29-46
+    std::memset(&d, 0, sizeof(d));
+    d.base_color[0] = d.base_color[1] = d.base_color[2] = 0.9f;
+    d.roughness = 1.f;
+    d.ior = 1.5f;
+    const uint32_t id = (uint32_t)S.materials.size();
+    S.materials.push_back(d);
+    for (std::vector<uint32_t> &ids : S.material_ids) {
+        std::replace(ids.begin(), ids.end(), 0xffffffffu, id);
+    }
+    warn << "No materials assigned for some objects, generating a default\n";
+}
+
+// The light the loaders generate for a scene that has none (scene.cpp:216-227 emits 20, :612-624 emits 10)
+crt_quad_light_t generated_light(float emission)
+{
+    float n[3] = {0.5f, -0.8f, -0.5f};
+    normalize3(n);
+    crt_quad_light_t L;
+    std::memset(&L, 0, sizeof(L));
+    L.emission[0] = L.emission[1] = L.emission[2] = L.emission[3] = emission;
+    L.normal[0] = n[0], L.normal[1] = n[1], L.normal[2] = n[2], L.normal[3] = 0.f;
+    for (int k = 0; k < 4; ++k) {
+        L.position[k] = -10.f * L.normal[k];
+    }
+    ortho_basis(L.v_x, L.v_y, n);
+    L.width = 5.f;
+    L.height = 5.f;
+    return L;
+}
 
 // One geometry of Scene::load_obj (util/scene.cpp:116-181): index triples -> single indices in order of first use
 void remap_shape(const std::vector<float> &V, const std::vector<float> &VT, const int32_t *faces, size_t num_faces, GeometryData &g,
@@ -1092,7 +1169,8 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
     const double t_parsed = now_s();
     // ---- Scene::load_obj: one geometry per shape ----
     S.geometries.resize(shapes.size());
-    S.material_ids.resize(shapes.size());
+    S.material_ids.assign(1, std::vector<uint32_t>(shapes.size()));
+    std::vector<uint32_t> &shape_material = S.material_ids[0];
     for (size_t s = 0; s < shapes.size(); ++s) {
         // The material of a shape is its first triangle's (scene.cpp:127); a shape whose triangles do not all have that
         // material gets the warning of scene.cpp:131-137. Only face groups that hold a triangle count.
@@ -1116,7 +1194,7 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
         if (first) {  // (the reference reads material_ids[0] of an empty array here)
             throw std::runtime_error("a shape without a triangle (its faces have fewer than three corners or no area) in " + file);
         }
-        S.material_ids[s] = (uint32_t)material;
+        shape_material[s] = (uint32_t)material;
         if (mixed) {
             warn << "Warning: per-face material IDs are not supported, materials may look wrong. Please reexport your mesh with each "
                     "material group as an OBJ group\n";
@@ -1163,22 +1241,7 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
         }
         S.materials.push_back(d);
     }
-    // validate_materials (scene.cpp:932-957): shapes without a material get a default one
-    if (std::find(S.material_ids.begin(), S.material_ids.end(), 0xffffffffu) != S.material_ids.end()) {
-        crt_material_t d;
-        std::memset(&d, 0, sizeof(d));
-        d.base_color[0] = d.base_color[1] = d.base_color[2] = 0.9f;
-        d.roughness = 1.f;
-        d.ior = 1.5f;
-        const uint32_t id = (uint32_t)S.materials.size();
-        S.materials.push_back(d);
-        for (uint32_t &m : S.material_ids) {
-            if (m == 0xffffffffu) {
-                m = id;
-            }
-        }
-        warn << "No materials assigned for some objects, generating a default\n";
-    }
+    validate_materials(S, warn);
     S.texture_data.resize(texture_files.size());
     S.textures.resize(texture_files.size());
     std::vector<std::string> tex_errors(texture_files.size());
@@ -1196,33 +1259,22 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
             throw std::runtime_error(e);
         }
     }
-    // ---- the generated light (scene.cpp:216-227) ----
-    float n[3] = {0.5f, -0.8f, -0.5f};
-    normalize3(n);
-    crt_quad_light_t &L = S.light;
-    std::memset(&L, 0, sizeof(L));
-    L.emission[0] = L.emission[1] = L.emission[2] = L.emission[3] = 20.f;
-    L.normal[0] = n[0], L.normal[1] = n[1], L.normal[2] = n[2], L.normal[3] = 0.f;
-    for (int k = 0; k < 4; ++k) {
-        L.position[k] = -10.f * L.normal[k];
-    }
-    ortho_basis(L.v_x, L.v_y, n);
-    L.width = 5.f;
-    L.height = 5.f;
-    // ---- views ----
+    S.lights.push_back(generated_light(20.f));  // scene.cpp:216-227
+    // ---- views: one mesh of all the geometries, one instance of it ----
     S.geometry_views.resize(S.geometries.size());
     for (size_t g = 0; g < S.geometries.size(); ++g) {
         const GeometryData &gd = S.geometries[g];
         S.geometry_views[g] = crt_geometry_t{gd.vertices.data(), gd.uvs.empty() ? nullptr : gd.uvs.data(), gd.indices.data(),
                                              (uint32_t)(gd.vertices.size() / 3), (uint32_t)(gd.indices.size() / 3)};
     }
-    S.mesh = crt_mesh_t{S.geometry_views.data(), (uint32_t)S.geometry_views.size()};
-    S.parameterized_mesh = crt_parameterized_mesh_t{S.material_ids.data(), (uint32_t)S.material_ids.size(), 0u};
-    std::memset(&S.instance, 0, sizeof(S.instance));
-    S.instance.transform[0] = S.instance.transform[5] = S.instance.transform[10] = S.instance.transform[15] = 1.f;
-    S.instance.parameterized_mesh_id = 0;
-    S.view = crt_scene_t{&S.mesh, &S.parameterized_mesh, &S.instance, S.materials.data(), S.textures.data(), &S.light, 1u, 1u, 1u,
-                         (uint32_t)S.materials.size(), (uint32_t)S.textures.size(), 1u, 1u};
+    S.meshes.push_back(crt_mesh_t{S.geometry_views.data(), (uint32_t)S.geometry_views.size()});
+    S.parameterized_meshes.push_back(crt_parameterized_mesh_t{nullptr, 0u, 0u});
+    crt_instance_t instance;
+    std::memset(&instance, 0, sizeof(instance));
+    instance.transform[0] = instance.transform[5] = instance.transform[10] = instance.transform[15] = 1.f;
+    instance.parameterized_mesh_id = 0;
+    S.instances.push_back(instance);
+    S.finish_views();
     S.warnings = warn.str();
     const double t_end = now_s();
     S.timings[0] = t_end - t_start;
@@ -1231,19 +1283,597 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
     S.timings[3] = t_end - t_remapped;
 }
 
-}  // namespace
+// ---------------------------------------------------------------------------------------------------------------
+// .crts (util/scene.cpp:417-625). The header is JSON, which the reference reads with nlohmann::json; what matters of that
+// library's behaviour is restated here: numbers without fraction or exponent are integers (unsigned if not negative), the
+// others go through strtod; get<float>() is a static_cast from whichever of the three the number is; a key given twice
+// keeps its last value; operator[] on a missing key yields null, whose size() is 0.
+struct Json {
+    enum Kind { kNull, kBool, kUnsigned, kSigned, kFloat, kString, kArray, kObject };
+    Kind kind = kNull;
+    bool boolean = false;
+    uint64_t u = 0;
+    int64_t i = 0;
+    double d = 0;
+    std::string str;
+    std::vector<Json> items;
+    std::vector<std::pair<std::string, Json>> members;
 
-extern "C" {
+    const Json *find(const char *key) const
+    {
+        const Json *found = nullptr;
+        for (const auto &m : members) {
+            if (m.first == key) {
+                found = &m.second;
+            }
+        }
+        return found;
+    }
+    const Json &at(const char *key, const std::string &where) const
+    {
+        const Json *j = kind == kObject ? find(key) : nullptr;
+        if (!j) {
+            throw std::runtime_error("crts header: " + where + " has no \"" + key + "\"");
+        }
+        return *j;
+    }
+    const Json &at(size_t index, const std::string &where) const
+    {
+        if (kind != kArray || index >= items.size()) {
+            throw std::runtime_error("crts header: " + where + " has no element " + std::to_string(index));
+        }
+        return items[index];
+    }
+    size_t size() const
+    {
+        return kind == kArray ? items.size() : (kind == kObject ? members.size() : (kind == kNull ? 0 : 1));
+    }
+    template <typename T>
+    T number(const std::string &where) const
+    {
+        switch (kind) {
+        case kUnsigned: return static_cast<T>(u);
+        case kSigned: return static_cast<T>(i);
+        case kFloat: return static_cast<T>(d);
+        case kBool: return static_cast<T>(boolean);
+        default: throw std::runtime_error("crts header: " + where + " is not a number");
+        }
+    }
+    const std::string &string(const std::string &where) const
+    {
+        if (kind != kString) {
+            throw std::runtime_error("crts header: " + where + " is not a string");
+        }
+        return str;
+    }
+    std::vector<float> floats(size_t at_least, const std::string &where) const
+    {
+        if (kind != kArray || items.size() < at_least) {
+            throw std::runtime_error("crts header: " + where + " is not an array of " + std::to_string(at_least) + " numbers");
+        }
+        std::vector<float> out(items.size());
+        for (size_t k = 0; k < items.size(); ++k) {
+            out[k] = items[k].number<float>(where);
+        }
+        return out;
+    }
+};
 
-int crtio_load_obj(const char *path, int threads, crtio_scene **out)
+class JsonParser {
+public:
+    JsonParser(const char *begin, const char *end) : p(begin), end(end) {}
+    Json parse_document()
+    {
+        Json j = value(0);
+        skip_space();
+        if (p != end) {
+            fail("text after the document");
+        }
+        return j;
+    }
+
+private:
+    const char *p, *end;
+    [[noreturn]] void fail(const std::string &what) const
+    {
+        throw std::runtime_error("crts header: malformed JSON (" + what + ")");
+    }
+    void skip_space()
+    {
+        while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) {
+            ++p;
+        }
+    }
+    bool literal(const char *word)
+    {
+        const size_t n = std::strlen(word);
+        if ((size_t)(end - p) >= n && std::memcmp(p, word, n) == 0) {
+            p += n;
+            return true;
+        }
+        return false;
+    }
+    static void append_utf8(std::string &out, uint32_t cp)
+    {
+        if (cp < 0x80) {
+            out += (char)cp;
+        } else if (cp < 0x800) {
+            out += (char)(0xC0 | (cp >> 6));
+            out += (char)(0x80 | (cp & 0x3F));
+        } else if (cp < 0x10000) {
+            out += (char)(0xE0 | (cp >> 12));
+            out += (char)(0x80 | ((cp >> 6) & 0x3F));
+            out += (char)(0x80 | (cp & 0x3F));
+        } else {
+            out += (char)(0xF0 | (cp >> 18));
+            out += (char)(0x80 | ((cp >> 12) & 0x3F));
+            out += (char)(0x80 | ((cp >> 6) & 0x3F));
+            out += (char)(0x80 | (cp & 0x3F));
+        }
+    }
+    uint32_t hex4()
+    {
+        if (end - p < 4) {
+            fail("short \\u escape");
+        }
+        uint32_t v = 0;
+        for (int k = 0; k < 4; ++k, ++p) {
+            const char c = *p;
+            v = v * 16 + (c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : (fail("bad \\u escape"), 0));
+        }
+        return v;
+    }
+    std::string string_body()
+    {
+        std::string out;
+        ++p;  // the opening quote
+        for (;;) {
+            if (p >= end) {
+                fail("unterminated string");
+            }
+            const char c = *p++;
+            if (c == '"') {
+                return out;
+            }
+            if (c != '\\') {
+                out += c;
+                continue;
+            }
+            if (p >= end) {
+                fail("unterminated escape");
+            }
+            const char e = *p++;
+            switch (e) {
+            case '"': out += '"'; break;
+            case '\\': out += '\\'; break;
+            case '/': out += '/'; break;
+            case 'b': out += '\b'; break;
+            case 'f': out += '\f'; break;
+            case 'n': out += '\n'; break;
+            case 'r': out += '\r'; break;
+            case 't': out += '\t'; break;
+            case 'u': {
+                uint32_t cp = hex4();
+                if (cp >= 0xD800 && cp < 0xDC00 && end - p >= 6 && p[0] == '\\' && p[1] == 'u') {
+                    p += 2;
+                    const uint32_t low = hex4();
+                    cp = 0x10000 + ((cp - 0xD800) << 10) + (low - 0xDC00);
+                }
+                append_utf8(out, cp);
+                break;
+            }
+            default: fail("unknown escape");
+            }
+        }
+    }
+    Json number()
+    {
+        const char *start = p;
+        bool integral = true;
+        if (p < end && *p == '-') {
+            ++p;
+        }
+        while (p < end && ((*p >= '0' && *p <= '9') || *p == '.' || *p == 'e' || *p == 'E' || *p == '+' || *p == '-')) {
+            integral = integral && *p >= '0' && *p <= '9';
+            ++p;
+        }
+        const std::string text(start, p);
+        if (text.empty() || text == "-") {
+            fail("a value was expected");
+        }
+        Json j;
+        char *stop = nullptr;
+        errno = 0;
+        if (integral && text[0] != '-') {
+            j.u = std::strtoull(text.c_str(), &stop, 10);
+            j.kind = Json::kUnsigned;
+        } else if (integral) {
+            j.i = std::strtoll(text.c_str(), &stop, 10);
+            j.kind = Json::kSigned;
+        }
+        if (!integral || errno == ERANGE) {  // (an integer too large for 64 bits is read as a float, as nlohmann does)
+            j.d = std::strtod(text.c_str(), &stop);
+            j.kind = Json::kFloat;
+        }
+        if (!stop || *stop != '\0') {
+            fail("bad number " + text);
+        }
+        return j;
+    }
+    Json value(int depth)
+    {
+        if (depth > 64) {
+            fail("nesting too deep");
+        }
+        skip_space();
+        if (p >= end) {
+            fail("unexpected end");
+        }
+        Json j;
+        if (*p == '{') {
+            ++p;
+            j.kind = Json::kObject;
+            skip_space();
+            if (p < end && *p == '}') {
+                ++p;
+                return j;
+            }
+            for (;;) {
+                skip_space();
+                if (p >= end || *p != '"') {
+                    fail("a member name was expected");
+                }
+                std::string key = string_body();
+                skip_space();
+                if (p >= end || *p != ':') {
+                    fail("':' was expected");
+                }
+                ++p;
+                j.members.emplace_back(std::move(key), value(depth + 1));
+                skip_space();
+                if (p < end && *p == ',') {
+                    ++p;
+                    continue;
+                }
+                if (p < end && *p == '}') {
+                    ++p;
+                    return j;
+                }
+                fail("',' or '}' was expected");
+            }
+        }
+        if (*p == '[') {
+            ++p;
+            j.kind = Json::kArray;
+            skip_space();
+            if (p < end && *p == ']') {
+                ++p;
+                return j;
+            }
+            for (;;) {
+                j.items.push_back(value(depth + 1));
+                skip_space();
+                if (p < end && *p == ',') {
+                    ++p;
+                    continue;
+                }
+                if (p < end && *p == ']') {
+                    ++p;
+                    return j;
+                }
+                fail("',' or ']' was expected");
+            }
+        }
+        if (*p == '"') {
+            j.kind = Json::kString;
+            j.str = string_body();
+            return j;
+        }
+        if (literal("true")) {
+            j.kind = Json::kBool;
+            j.boolean = true;
+            return j;
+        }
+        if (literal("false")) {
+            j.kind = Json::kBool;
+            return j;
+        }
+        if (literal("null")) {
+            return j;
+        }
+        return number();
+    }
+};
+
+// dtype_stride(parse_dtype(name)) (util/gltf_types.cpp:144-215, :431-505): "<SHAPE>_<COMPONENT>" or a scalar's long name
+size_t crts_dtype_stride(const std::string &name)
+{
+    static const struct {
+        const char *name;
+        size_t bytes;
+    } scalars[] = {{"INT_8", 1}, {"UINT_8", 1}, {"INT_16", 2}, {"UINT_16", 2}, {"INT_32", 4}, {"UINT_32", 4}, {"FLOAT_32", 4}, {"FLOAT_64", 8}};
+    for (const auto &sc : scalars) {
+        if (name == sc.name) {
+            return sc.bytes;
+        }
+    }
+    static const struct {
+        const char *prefix;
+        size_t components;
+    } shapes[] = {{"VEC2_", 2}, {"VEC3_", 3}, {"VEC4_", 4}, {"MAT2_", 4}, {"MAT3_", 9}, {"MAT4_", 16}};
+    static const struct {
+        const char *suffix;
+        size_t bytes;
+    } components[] = {{"I8", 1}, {"U8", 1}, {"I16", 2}, {"U16", 2}, {"I32", 4}, {"U32", 4}, {"F32", 4}, {"F64", 8}};
+    for (const auto &sh : shapes) {
+        if (name.compare(0, 5, sh.prefix) == 0) {
+            for (const auto &co : components) {
+                if (name.compare(5, std::string::npos, co.suffix) == 0) {
+                    return sh.components * co.bytes;
+                }
+            }
+        }
+    }
+    throw std::runtime_error("Invalid data type string " + name);
+}
+
+// glm::normalize of a vec4: v * (1 / sqrt(dot)), dot = (x*x + y*y) + (z*z + w*w) (glm's compute_dot<vec<4>>)
+void normalize4(const float v[4], float out[4])
+{
+    const float inv = 1.f / std::sqrt((v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]));
+    for (int k = 0; k < 4; ++k) {
+        out[k] = v[k] * inv;
+    }
+}
+
+void load_crts_impl(const std::string &file, int threads, crtio_scene &S)
+{
+    const double t_start = now_s();
+    const unsigned nthreads = crt::host_threads(threads);
+    S.mapping.reset(new MappedFile(file, /*sequential=*/false));
+    const MappedFile &map = *S.mapping;
+    if (map.size < sizeof(uint64_t)) {
+        throw std::runtime_error("not a crts file (too short): " + file);
+    }
+    uint64_t json_size = 0;
+    std::memcpy(&json_size, map.data, sizeof(json_size));
+    if (json_size > map.size - sizeof(uint64_t)) {
+        throw std::runtime_error("not a crts file (header size past the end): " + file);
+    }
+    const Json header = JsonParser(map.data + sizeof(uint64_t), map.data + sizeof(uint64_t) + json_size).parse_document();
+    if (header.kind != Json::kObject) {
+        throw std::runtime_error("crts header: not an object");
+    }
+    const uint8_t *data_base = reinterpret_cast<const uint8_t *>(map.data) + sizeof(uint64_t) + json_size;
+    const size_t data_size = map.size - sizeof(uint64_t) - (size_t)json_size;
+    static const Json null_json;
+    const auto section = [&](const char *key) -> const Json & {
+        const Json *j = header.find(key);
+        return j ? *j : null_json;
+    };
+    const Json &views = section("buffer_views");
+    struct View {
+        const uint8_t *data;
+        size_t bytes;  // whole elements of the view's own type (Accessor: count = length / stride)
+    };
+    const auto view_of = [&](const Json &id, const std::string &where) {
+        const uint64_t view_id = id.number<uint64_t>(where);
+        const std::string vw = "buffer view " + std::to_string(view_id);
+        const Json &v = views.at((size_t)view_id, "buffer_views");
+        const size_t stride = crts_dtype_stride(v.at("type", vw).string(vw + " type"));
+        const uint64_t offset = v.at("byte_offset", vw).number<uint64_t>(vw), length = v.at("byte_length", vw).number<uint64_t>(vw);
+        if (offset > data_size || length > data_size - offset) {
+            throw std::runtime_error("crts: " + vw + " reaches past the end of " + file);
+        }
+        return View{data_base + offset, (size_t)(length / stride) * stride};
+    };
+    // ---- meshes: one geometry each; the arrays stay where they are in the mapped file ----
+    const Json &meshes = section("meshes");
+    const size_t num_meshes = meshes.size();
+    S.geometries.resize(num_meshes);
+    S.geometry_views.resize(num_meshes);
+    S.meshes.resize(num_meshes);
+    const auto array_of = [&](const View &v, size_t element_bytes, std::vector<uint8_t> &copy, const std::string &where, size_t &count) {
+        if (v.bytes % element_bytes) {
+            throw std::runtime_error("crts: " + where + " is not a whole number of elements");
+        }
+        count = v.bytes / element_bytes;
+        if (reinterpret_cast<uintptr_t>(v.data) % 4 == 0) {
+            return v.data;
+        }
+        copy.assign(v.data, v.data + v.bytes);  // (vector storage is aligned)
+        return static_cast<const uint8_t *>(copy.data());
+    };
+    S.unaligned_copies.resize(num_meshes * 3);
+    for (size_t i = 0; i < num_meshes; ++i) {
+        const std::string where = "mesh " + std::to_string(i);
+        const Json &m = meshes.at(i, "meshes");
+        size_t nv = 0, nt = 0, nuv = 0;
+        const uint8_t *pos = array_of(view_of(m.at("positions", where), where), 12, S.unaligned_copies[3 * i], where + " positions", nv);
+        const uint8_t *idx = array_of(view_of(m.at("indices", where), where), 12, S.unaligned_copies[3 * i + 1], where + " indices", nt);
+        const uint8_t *uvs = nullptr;
+        if (m.kind == Json::kObject && m.find("texcoords")) {
+            uvs = array_of(view_of(*m.find("texcoords"), where), 8, S.unaligned_copies[3 * i + 2], where + " texcoords", nuv);
+            if (nuv == 0) {
+                uvs = nullptr;  // (Geometry::uvs empty = no texture coordinates)
+            } else if (nuv != nv) {
+                throw std::runtime_error("crts: " + where + " has " + std::to_string(nuv) + " texcoords for " + std::to_string(nv) + " positions");
+            }
+        }
+        if (nv > 0xffffffffull || nt > 0xffffffffull) {
+            throw std::runtime_error("crts: " + where + " is too large for 32-bit counts");
+        }
+        S.geometry_views[i] = crt_geometry_t{reinterpret_cast<const float *>(pos), reinterpret_cast<const float *>(uvs),
+                                             reinterpret_cast<const uint32_t *>(idx), (uint32_t)nv, (uint32_t)nt};
+        S.meshes[i] = crt_mesh_t{&S.geometry_views[i], 1u};
+    }
+    const double t_parsed = now_s();
+    // ---- images: embedded files, decoded like stbi_load_from_memory(..., 4) with the vertical flip (:488-511) ----
+    const Json &images = section("images");
+    const size_t num_images = images.size();
+    S.texture_data.resize(num_images);
+    S.textures.resize(num_images);
+    std::vector<View> image_views(num_images);
+    std::vector<std::string> image_names(num_images);
+    for (size_t i = 0; i < num_images; ++i) {
+        const std::string where = "image " + std::to_string(i);
+        const Json &img = images.at(i, "images");
+        image_views[i] = view_of(img.at("view", where), where);
+        image_names[i] = img.at("name", where).string(where + " name");
+        const int32_t cs = img.at("color_space", where).string(where + " color_space") == "LINEAR" ? CRT_COLOR_SPACE_LINEAR : CRT_COLOR_SPACE_SRGB;
+        S.textures[i] = crt_image_t{nullptr, 0, 0, 4, cs};
+    }
+    std::vector<std::string> image_errors(num_images);
+    crt::parallel_blocks((uint32_t)num_images, nthreads, [&](uint32_t i) {
+        try {
+            int w = 0, h = 0;
+            decode_png_rgba_flipped(image_views[i].data, image_views[i].bytes, image_names[i], S.texture_data[i], w, h);
+            S.textures[i].data = S.texture_data[i].data();
+            S.textures[i].width = w;
+            S.textures[i].height = h;
+        } catch (const std::exception &e) {
+            image_errors[i] = std::string("Failed to load ") + image_names[i] + " (" + e.what() + ")";
+        }
+    });
+    for (const std::string &e : image_errors) {
+        if (!e.empty()) {
+            throw std::runtime_error(e);
+        }
+    }
+    // ---- materials (:513-556) ----
+    const Json &materials = section("materials");
+    for (size_t i = 0; i < materials.size(); ++i) {
+        const std::string where = "material " + std::to_string(i);
+        const Json &m = materials.at(i, "materials");
+        crt_material_t d;
+        std::memset(&d, 0, sizeof(d));
+        const std::vector<float> base = m.at("base_color", where).floats(3, where + " base_color");
+        d.base_color[0] = base[0], d.base_color[1] = base[1], d.base_color[2] = base[2];
+        if (const Json *t = m.find("base_color_texture")) {
+            const uint32_t mask = 0x80000000u | ((uint32_t)t->number<int32_t>(where + " base_color_texture") & 0x1fffffffu);
+            std::memcpy(&d.base_color[0], &mask, 4);  // TEXTURED_PARAM_MASK, SET_TEXTURE_ID
+        }
+        const auto param = [&](const char *name, float &val) {
+            val = m.at(name, where).number<float>(where + " " + name);
+            const std::string tex_name = std::string(name) + "_texture";
+            if (const Json *t = m.find(tex_name.c_str())) {
+                const uint32_t id = (uint32_t)t->at("texture", where + " " + tex_name).number<int32_t>(where + " " + tex_name);
+                const uint32_t channel = t->at("channel", where + " " + tex_name).number<uint32_t>(where + " " + tex_name);
+                const uint32_t mask = 0x80000000u | (id & 0x1fffffffu) | ((channel & 0x3u) << 29);  // SET_TEXTURE_ID, SET_TEXTURE_CHANNEL
+                std::memcpy(&val, &mask, 4);
+            }
+        };
+        param("metallic", d.metallic);
+        param("specular", d.specular);
+        param("roughness", d.roughness);
+        param("specular_tint", d.specular_tint);
+        param("anisotropic", d.anisotropy);
+        param("sheen", d.sheen);
+        param("sheen_tint", d.sheen_tint);
+        param("clearcoat", d.clearcoat);
+        param("clearcoat_roughness", d.clearcoat_gloss);
+        param("ior", d.ior);
+        param("transmission", d.specular_transmission);
+        S.materials.push_back(d);
+    }
+    // ---- objects (:558-606): instances of (mesh, material) pairs, quad lights, cameras ----
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> pair_ids;  // (mesh, material) -> parameterized mesh, in order of first use
+    const Json &objects = section("objects");
+    for (size_t i = 0; i < objects.size(); ++i) {
+        const std::string where = "object " + std::to_string(i);
+        const Json &n = objects.at(i, "objects");
+        const std::string &type = n.at("type", where).string(where + " type");
+        const std::vector<float> mat = n.at("matrix", where).floats(16, where + " matrix");  // column major (glm::make_mat4)
+        const float *col[4] = {&mat[0], &mat[4], &mat[8], &mat[12]};
+        if (type == "MESH") {
+            const uint64_t mesh_id = n.at("mesh", where).number<uint64_t>(where + " mesh");
+            const uint32_t mat_id = n.at("material", where).number<uint32_t>(where + " material");
+            if (mesh_id >= num_meshes) {
+                throw std::runtime_error("crts: " + where + " instances mesh " + std::to_string(mesh_id) + " of " + std::to_string(num_meshes));
+            }
+            const auto key = std::make_pair((uint32_t)mesh_id, mat_id);
+            auto it = pair_ids.find(key);
+            if (it == pair_ids.end()) {
+                it = pair_ids.insert(std::make_pair(key, (uint32_t)S.parameterized_meshes.size())).first;
+                S.parameterized_meshes.push_back(crt_parameterized_mesh_t{nullptr, 0u, (uint32_t)mesh_id});
+                S.material_ids.push_back(std::vector<uint32_t>{mat_id});
+            }
+            crt_instance_t inst;
+            std::memset(&inst, 0, sizeof(inst));
+            std::memcpy(inst.transform, mat.data(), sizeof(inst.transform));
+            inst.parameterized_mesh_id = it->second;
+            S.instances.push_back(inst);
+        } else if (type == "LIGHT") {
+            crt_quad_light_t L;
+            std::memset(&L, 0, sizeof(L));
+            const std::vector<float> color = n.at("color", where).floats(3, where + " color");
+            const float energy = n.at("energy", where).number<float>(where + " energy");
+            for (int k = 0; k < 3; ++k) {
+                L.emission[k] = color[k] * energy;
+            }
+            L.emission[3] = 1.f;
+            float unit[4];
+            std::memcpy(L.position, col[3], sizeof(L.position));
+            normalize4(col[2], unit);
+            for (int k = 0; k < 4; ++k) {
+                L.normal[k] = -unit[k];
+            }
+            normalize4(col[0], unit);
+            std::memcpy(L.v_x, unit, sizeof(L.v_x));
+            normalize4(col[1], unit);
+            std::memcpy(L.v_y, unit, sizeof(L.v_y));
+            const Json &size = n.at("size", where);
+            L.width = size.at((size_t)0, where + " size").number<float>(where + " size");
+            L.height = size.at((size_t)1, where + " size").number<float>(where + " size");
+            S.lights.push_back(L);
+        } else if (type == "CAMERA") {
+            crtio_camera_t cam;
+            const float back[4] = {-col[2][0], -col[2][1], -col[2][2], -col[2][3]};
+            float dir[4], up[4];
+            normalize4(back, dir);
+            normalize4(col[1], up);
+            for (int k = 0; k < 3; ++k) {
+                cam.position[k] = col[3][k];
+                cam.center[k] = cam.position[k] + dir[k] * 10.f;
+                cam.up[k] = up[k];
+            }
+            cam.fov_y = n.at("fov_y", where).number<float>(where + " fov_y") / 1.18f;
+            S.cameras.push_back(cam);
+        } else {
+            throw std::runtime_error("Unsupported object type: not a mesh or camera?");
+        }
+    }
+    std::ostringstream warn;
+    validate_materials(S, warn);
+    if (S.lights.empty()) {
+        warn << "No lights found in scene, generating one\n";
+        S.lights.push_back(generated_light(10.f));  // :612-624
+    }
+    S.finish_views();
+    S.warnings = warn.str();
+    const double t_end = now_s();
+    S.timings[0] = t_end - t_start;
+    S.timings[1] = t_parsed - t_start;
+    S.timings[2] = 0.0;
+    S.timings[3] = t_end - t_parsed;
+}
+
+std::string file_extension(const std::string &path)  // get_file_extension, util/util.cpp
+{
+    const size_t dot = path.rfind('.');
+    return dot == std::string::npos ? std::string() : path.substr(dot + 1);
+}
+
+template <typename Fn>
+int load_with(const char *path, crtio_scene **out, const char *api, Fn &&load)
 {
     try {
         if (!path || !out) {
-            throw std::runtime_error("crtio_load_obj: null argument");
+            throw std::runtime_error(std::string(api) + ": null argument");
         }
         *out = nullptr;
         std::unique_ptr<crtio_scene> s(new crtio_scene());
-        load_obj_impl(path, threads, *s);
+        load(std::string(path), *s);
         *out = s.release();
         return 0;
     } catch (const std::exception &e) {
@@ -1253,6 +1883,45 @@ int crtio_load_obj(const char *path, int threads, crtio_scene **out)
         g_last_error = "unknown exception";
         return 1;
     }
+}
+
+}  // namespace
+
+extern "C" {
+
+int crtio_load_obj(const char *path, int threads, crtio_scene **out)
+{
+    return load_with(path, out, "crtio_load_obj", [&](const std::string &file, crtio_scene &s) { load_obj_impl(file, threads, s); });
+}
+
+int crtio_load_crts(const char *path, int threads, crtio_scene **out)
+{
+    return load_with(path, out, "crtio_load_crts", [&](const std::string &file, crtio_scene &s) { load_crts_impl(file, threads, s); });
+}
+
+int crtio_load(const char *path, int threads, crtio_scene **out)
+{
+    return load_with(path, out, "crtio_load", [&](const std::string &file, crtio_scene &s) {
+        const std::string ext = file_extension(file);
+        if (ext == "obj") {
+            load_obj_impl(file, threads, s);
+        } else if (ext == "crts") {
+            load_crts_impl(file, threads, s);
+        } else {
+            throw std::runtime_error("Unsupported file " + file);  // scene.cpp:63-66 (glTF and PBRT are not read natively)
+        }
+    });
+}
+
+int crtio_cameras(const crtio_scene *s, const crtio_camera_t **out)
+{
+    if (!s) {
+        return 0;
+    }
+    if (out) {
+        *out = s->cameras.data();
+    }
+    return (int)s->cameras.size();
 }
 
 const crt_scene_t *crtio_scene_view(const crtio_scene *s)

@@ -1,6 +1,7 @@
 """ctypes binding of the native scene loader (include/crt_scene_io.h, chameleonrt_b200/csrc/libcrt_scene_io.so): the
-parallel twin of the reference's ``Scene::load_obj`` (util/scene.cpp:94-228) — same Scene, bit for bit, from a memory-mapped
-file parsed on several threads. ``LoadedScene.c_scene`` is the ``crt_scene_t`` pointer ``RenderCUDA.set_scene_c`` takes;
+parallel twin of the reference's ``Scene::load_obj`` (util/scene.cpp:94-228) and ``Scene::load_crts`` (:417-625) — same Scene,
+bit for bit, from a memory-mapped file (an OBJ parsed on several threads; a .crts used in place, its images decoded
+concurrently). ``LoadedScene.c_scene`` is the ``crt_scene_t`` pointer ``RenderCUDA.set_scene_c`` takes;
 ``LoadedScene.to_scene()`` copies it into the Python scene model (tests, the CPU oracle)."""
 from __future__ import annotations
 
@@ -35,7 +36,9 @@ def _lib():
         if not os.path.exists(lib_path()):
             raise RuntimeError(f"{lib_path()} is missing: build it first (python -c 'import __graft_entry__ as g; g.build()')")
         lib = C.CDLL(lib_path())
-        lib.crtio_load_obj.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+        for fn in (lib.crtio_load_obj, lib.crtio_load_crts, lib.crtio_load):
+            fn.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+        lib.crtio_cameras.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_float))]
         lib.crtio_scene_view.restype = C.POINTER(CScene)
         lib.crtio_scene_view.argtypes = [C.c_void_p]
         lib.crtio_timings.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
@@ -57,6 +60,11 @@ class LoadedScene:
         _lib().crtio_timings(handle, t, 4)
         self.timings = dict(total_s=t[0], parse_s=t[1], remap_s=t[2], materials_textures_s=t[3])
         self.warnings = _lib().crtio_warnings(handle).decode()
+        cams = C.POINTER(C.c_float)()
+        n = _lib().crtio_cameras(handle, C.byref(cams))
+        raw = np.ctypeslib.as_array(cams, (n, 10)).copy() if n else np.zeros((0, 10), np.float32)
+        #: the file's cameras (util/camera.h): dicts of position / center / up (3 floats each) and fov_y
+        self.cameras = [dict(position=c[0:3], center=c[3:6], up=c[6:9], fov_y=float(c[9])) for c in raw]
 
     def __del__(self):
         try:
@@ -69,16 +77,20 @@ class LoadedScene:
     def to_scene(self, spp: int = 1) -> Scene:
         """A copy in the Python scene model (numpy arrays), e.g. for the CPU oracle."""
         s = self.c_scene.contents
-        geoms = []
-        mesh = s.meshes[0]
-        for g in range(mesh.num_geometries):
-            cg = mesh.geometries[g]
-            v = np.ctypeslib.as_array(cg.vertices, (cg.num_vertices, 3)).copy()
-            uv = np.ctypeslib.as_array(cg.uvs, (cg.num_vertices, 2)).copy() if cg.uvs else None
-            idx = np.ctypeslib.as_array(cg.indices, (cg.num_tris, 3)).copy()
-            geoms.append(Geometry(v, idx, uv))
-        pm = s.parameterized_meshes[0]
-        mat_ids = [int(pm.material_ids[i]) for i in range(pm.num_material_ids)]
+        meshes = []
+        for m in range(s.num_meshes):
+            geoms = []
+            for g in range(s.meshes[m].num_geometries):
+                cg = s.meshes[m].geometries[g]
+                v = np.ctypeslib.as_array(cg.vertices, (cg.num_vertices, 3)).copy()
+                uv = np.ctypeslib.as_array(cg.uvs, (cg.num_vertices, 2)).copy() if cg.uvs else None
+                idx = np.ctypeslib.as_array(cg.indices, (cg.num_tris, 3)).copy()
+                geoms.append(Geometry(v, idx, uv))
+            meshes.append(Mesh(geoms))
+        pms = []
+        for i in range(s.num_parameterized_meshes):
+            pm = s.parameterized_meshes[i]
+            pms.append(ParameterizedMesh(int(pm.mesh_id), [int(pm.material_ids[k]) for k in range(pm.num_material_ids)]))
         mats = []
         for i in range(s.num_materials):
             w = np.ctypeslib.as_array(C.cast(C.pointer(s.materials[i]), C.POINTER(C.c_uint32)), (16,)).copy()
@@ -91,17 +103,36 @@ class LoadedScene:
             im = s.textures[i]
             px = np.ctypeslib.as_array(im.data, (im.height, im.width, im.channels)).copy()
             texs.append(Image(f"tex{i}", px, int(im.color_space)))
-        lf = [float(x) for x in np.ctypeslib.as_array(C.cast(C.pointer(s.lights[0]), C.POINTER(C.c_float)), (20,))]
-        light = QuadLight(emission=tuple(lf[0:4]), position=tuple(lf[4:8]), normal=tuple(lf[8:11]), v_x=tuple(lf[12:15]), width=lf[15],
-                          v_y=tuple(lf[16:19]), height=lf[19])
-        xf = np.ctypeslib.as_array(s.instances[0].transform, (16,)).copy().reshape(4, 4).T
-        return Scene(meshes=[Mesh(geoms)], parameterized_meshes=[ParameterizedMesh(0, mat_ids)], instances=[Instance(xf.astype(np.float32), 0)],
-                     materials=mats, textures=texs, lights=[light], samples_per_pixel=spp)
+        lights = []
+        for i in range(s.num_lights):
+            lf = [float(x) for x in np.ctypeslib.as_array(C.cast(C.pointer(s.lights[i]), C.POINTER(C.c_float)), (20,))]
+            lights.append(QuadLight(emission=tuple(lf[0:4]), position=tuple(lf[4:8]), normal=tuple(lf[8:12]), v_x=tuple(lf[12:15]),
+                                    width=lf[15], v_y=tuple(lf[16:19]), height=lf[19]))
+        instances = []
+        for i in range(s.num_instances):
+            xf = np.ctypeslib.as_array(s.instances[i].transform, (16,)).copy().reshape(4, 4).T
+            instances.append(Instance(xf.astype(np.float32), int(s.instances[i].parameterized_mesh_id)))
+        return Scene(meshes=meshes, parameterized_meshes=pms, instances=instances, materials=mats, textures=texs, lights=lights,
+                     samples_per_pixel=spp)
+
+
+def _load(fn, path, threads) -> LoadedScene:
+    h = C.c_void_p()
+    if fn(os.fspath(path).encode(), threads, C.byref(h)) != 0:
+        raise RuntimeError(_lib().crtio_last_error().decode())
+    return LoadedScene(h)
 
 
 def load_obj(path: str, threads: int = 0) -> LoadedScene:
     """``Scene::load_obj`` (util/scene.cpp:94-228), natively and in parallel. Raises RuntimeError like the reference throws."""
-    h = C.c_void_p()
-    if _lib().crtio_load_obj(os.fspath(path).encode(), threads, C.byref(h)) != 0:
-        raise RuntimeError(_lib().crtio_last_error().decode())
-    return LoadedScene(h)
+    return _load(_lib().crtio_load_obj, path, threads)
+
+
+def load_crts(path: str, threads: int = 0) -> LoadedScene:
+    """``Scene::load_crts`` (util/scene.cpp:417-625): geometry arrays used in place in the mapped file, images decoded in parallel."""
+    return _load(_lib().crtio_load_crts, path, threads)
+
+
+def load_scene(path: str, threads: int = 0) -> LoadedScene:
+    """``Scene::Scene`` (util/scene.cpp:49-67): the loader the file's extension names (obj, crts)."""
+    return _load(_lib().crtio_load, path, threads)

@@ -9,6 +9,9 @@
  * the global arrays concurrently (floats with tinyobjloader's own decimal-to-double rule, so that the bits match), shapes are
  * delimited from the g / o / usemtl events, and the shapes are remapped concurrently, one open-addressing table each.
  *
+ * crtio_load_crts is Scene::load_crts (util/scene.cpp:417-625), the reference's binary format, with the arrays left where they
+ * are in the mapped file; crtio_load dispatches on the extension like Scene::Scene (util/scene.cpp:49-67).
+ *
  * The result is a crt_scene_t (include/crt_scene.h) owned by the handle: pass crtio_scene_view(h) to crtc_set_scene.
  *
  * Supported: what Scene::load_obj supports for the scenes of this project — faces of any number of corners (more than three:
@@ -29,14 +32,33 @@ extern "C" {
 
 typedef struct crtio_scene crtio_scene;
 
+/* Camera, util/camera.h:5-8 (what Scene::cameras holds; the application picks one with -camera, main.cpp). */
+typedef struct crtio_camera_t {
+    float position[3];
+    float center[3];
+    float up[3];
+    float fov_y;
+} crtio_camera_t;
+
 /* Scene::load_obj (util/scene.cpp:94-228). threads: 0 = all hardware threads. Returns 0 and *out on success; otherwise a
  * non-zero code and crtio_last_error() (the reference throws std::runtime_error). */
 int crtio_load_obj(const char *path, int threads, crtio_scene **out);
+/* Scene::load_crts (util/scene.cpp:417-625): the reference's own binary format (a uint64 header size, a JSON header, a data
+ * block of buffer views) — one geometry per mesh, MESH objects that instance a (mesh, material) pair under a matrix, LIGHT
+ * objects (quad lights, frame = the object's matrix), CAMERA objects, every DisneyMaterial parameter with optional texture
+ * handles, images as embedded PNG files. The geometry arrays are NOT copied: the file stays mapped for the lifetime of the
+ * handle and crt_geometry_t points into it (arrays that are not 4-byte aligned in the file are copied). Images are decoded
+ * concurrently. */
+int crtio_load_crts(const char *path, int threads, crtio_scene **out);
+/* Scene::Scene (util/scene.cpp:49-67): the loader is chosen by the file extension (obj, crts). */
+int crtio_load(const char *path, int threads, crtio_scene **out);
+/* The cameras of the file (CAMERA objects of a .crts; none for an OBJ): returns how many, *out = the array. */
+int crtio_cameras(const crtio_scene *s, const crtio_camera_t **out);
 /* The loaded scene as the plain-C view crtc_set_scene takes; valid until crtio_free. samples_per_pixel is 1 (the
  * application sets it from its command line, main.cpp:186). */
 const crt_scene_t *crtio_scene_view(const crtio_scene *s);
-/* Wall-clock seconds of the phases of the last load: [0] total [1] parse (mmap + both passes) [2] index remap [3] materials
- * + textures. Returns the number of entries written. */
+/* Wall-clock seconds of the phases of the load: [0] total [1] parse (OBJ: mmap + both passes + polygons; .crts: the header)
+ * [2] index remap (OBJ only) [3] materials + textures. Returns the number of entries written. */
 int crtio_timings(const crtio_scene *s, double *out, int n);
 /* Warnings the reference would print (per-face material ids, missing material file, ...), one per line. */
 const char *crtio_warnings(const crtio_scene *s);

@@ -1,6 +1,6 @@
 // ref_scene_api.cpp — TEST INFRASTRUCTURE: the reference's own Scene loader (util/scene.cpp, util/tiny_obj_loader.h, stb_image;
 // compiled from /root/reference by this directory's Makefile) behind a C API, so that tests/test_scene_io.py can compare what
-// Scene::load_obj builds with what the product's native loader (chameleonrt_b200/csrc/scene_io.cpp) builds, array by array.
+// Scene::load_obj / Scene::load_crts build with what the product's native loader (chameleonrt_b200/csrc/scene_io.cpp) builds, array by array.
 #include <chrono>
 #include <cstdint>
 #include <cstring>
@@ -81,6 +81,35 @@ const float *refscene_instance(void *p, uint32_t i, uint32_t *pm)
     const Instance &inst = static_cast<Scene *>(p)->instances[i];
     *pm = (uint32_t)inst.parameterized_mesh_id;
     return reinterpret_cast<const float *>(&inst.transform);
+}
+// ---- scenes of several meshes / parameterized meshes (.crts) ----
+void refscene_mesh_geometry(void *p, uint32_t mesh, uint32_t g, const float **verts, uint32_t *nv, const float **uvs, uint32_t *nuv,
+                            const uint32_t **idx, uint32_t *ntris, uint32_t *num_geometries)
+{
+    const Mesh &m = static_cast<Scene *>(p)->meshes[mesh];
+    *num_geometries = (uint32_t)m.geometries.size();
+    const Geometry &geom = m.geometries[g];
+    *verts = reinterpret_cast<const float *>(geom.vertices.data());
+    *nv = (uint32_t)geom.vertices.size();
+    *uvs = reinterpret_cast<const float *>(geom.uvs.data());
+    *nuv = (uint32_t)geom.uvs.size();
+    *idx = reinterpret_cast<const uint32_t *>(geom.indices.data());
+    *ntris = (uint32_t)geom.indices.size();
+}
+const uint32_t *refscene_parameterized_mesh(void *p, uint32_t i, uint32_t *n, uint32_t *mesh_id)
+{
+    const ParameterizedMesh &pm = static_cast<Scene *>(p)->parameterized_meshes[i];
+    *n = (uint32_t)pm.material_ids.size();
+    *mesh_id = (uint32_t)pm.mesh_id;
+    return pm.material_ids.data();
+}
+// Camera: position, center, up, fov_y = 10 floats
+const float *refscene_cameras(void *p, uint32_t *n)
+{
+    static_assert(sizeof(Camera) == 40, "layout");
+    const Scene &s = *static_cast<Scene *>(p);
+    *n = (uint32_t)s.cameras.size();
+    return reinterpret_cast<const float *>(s.cameras.data());
 }
 const uint8_t *refscene_texture(void *p, uint32_t i, int *w, int *h, int *channels, int *color_space)
 {

@@ -24,43 +24,59 @@ def _ref():
     lib.refscene_error.restype = C.c_char_p
     lib.refscene_free.argtypes = [C.c_void_p]
     lib.refscene_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
-    lib.refscene_geometry.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6
-    lib.refscene_material_ids.restype = C.POINTER(C.c_uint32)
-    lib.refscene_material_ids.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.refscene_mesh_geometry.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32] + [C.c_void_p] * 7
+    lib.refscene_parameterized_mesh.restype = C.POINTER(C.c_uint32)
+    lib.refscene_parameterized_mesh.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.refscene_materials.restype = C.POINTER(C.c_uint32)
     lib.refscene_materials.argtypes = [C.c_void_p]
     lib.refscene_light.restype = C.POINTER(C.c_uint32)
     lib.refscene_light.argtypes = [C.c_void_p, C.c_uint32]
     lib.refscene_instance.restype = C.POINTER(C.c_uint32)
     lib.refscene_instance.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.refscene_cameras.restype = C.POINTER(C.c_uint32)
+    lib.refscene_cameras.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     lib.refscene_texture.restype = C.POINTER(C.c_uint8)
     lib.refscene_texture.argtypes = [C.c_void_p, C.c_uint32] + [C.POINTER(C.c_int)] * 4
     return lib
 
 
 def _reference_arrays(path):
-    """What Scene::load_obj built, as numpy arrays (bit patterns for everything float)."""
+    """What the reference's Scene constructor built, as numpy arrays (bit patterns for everything float). `geometries` lists the
+    geometries of all meshes in order; `mesh_sizes` says how many each mesh has."""
     lib = _ref()
     secs = C.c_double(0)
     h = lib.refscene_load(path.encode(), C.byref(secs))
     assert h, lib.refscene_error().decode()
     counts = (C.c_uint32 * 7)()
     lib.refscene_counts(h, counts)
-    out = dict(counts=list(counts), seconds=secs.value, geometries=[])
-    for g in range(counts[1]):
-        v, uv, idx = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)()
-        nv, nuv, nt = C.c_uint32(), C.c_uint32(), C.c_uint32()
-        lib.refscene_geometry(h, g, C.byref(v), C.byref(nv), C.byref(uv), C.byref(nuv), C.byref(idx), C.byref(nt))
-        out["geometries"].append((np.ctypeslib.as_array(v, (nv.value * 3,)).copy() if nv.value else np.zeros(0, np.uint32),
-                                  np.ctypeslib.as_array(uv, (nuv.value * 2,)).copy() if nuv.value else np.zeros(0, np.uint32),
-                                  np.ctypeslib.as_array(idx, (nt.value * 3,)).copy()))
-    n, mesh_id = C.c_uint32(), C.c_uint32()
-    p = lib.refscene_material_ids(h, C.byref(n), C.byref(mesh_id))
-    out["material_ids"] = np.ctypeslib.as_array(p, (n.value,)).copy()
+    out = dict(counts=list(counts), seconds=secs.value, geometries=[], mesh_sizes=[])
+    for m in range(counts[0]):
+        g, ng = 0, C.c_uint32(1)
+        while g < ng.value:
+            v, uv, idx = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)()
+            nv, nuv, nt = C.c_uint32(), C.c_uint32(), C.c_uint32()
+            lib.refscene_mesh_geometry(h, m, g, C.byref(v), C.byref(nv), C.byref(uv), C.byref(nuv), C.byref(idx), C.byref(nt), C.byref(ng))
+            out["geometries"].append((np.ctypeslib.as_array(v, (nv.value * 3,)).copy() if nv.value else np.zeros(0, np.uint32),
+                                      np.ctypeslib.as_array(uv, (nuv.value * 2,)).copy() if nuv.value else np.zeros(0, np.uint32),
+                                      np.ctypeslib.as_array(idx, (nt.value * 3,)).copy() if nt.value else np.zeros(0, np.uint32)))
+            g += 1
+        out["mesh_sizes"].append(ng.value)
+    out["parameterized_meshes"] = []
+    for i in range(counts[2]):
+        n, mesh_id = C.c_uint32(), C.c_uint32()
+        p = lib.refscene_parameterized_mesh(h, i, C.byref(n), C.byref(mesh_id))
+        out["parameterized_meshes"].append((mesh_id.value, list(np.ctypeslib.as_array(p, (n.value,)))))
+    out["material_ids"] = np.array(out["parameterized_meshes"][0][1], np.uint32) if counts[2] else np.zeros(0, np.uint32)
     out["materials"] = np.ctypeslib.as_array(lib.refscene_materials(h), (counts[4] * 16,)).copy() if counts[4] else np.zeros(0, np.uint32)
-    out["light"] = np.ctypeslib.as_array(lib.refscene_light(h, 0), (20,)).copy()
-    pm = C.c_uint32()
-    out["instance"] = np.ctypeslib.as_array(lib.refscene_instance(h, 0, C.byref(pm)), (16,)).copy()
+    out["lights"] = np.concatenate([np.ctypeslib.as_array(lib.refscene_light(h, i), (20,)).copy() for i in range(counts[6])])
+    inst = []
+    for i in range(counts[3]):
+        pm = C.c_uint32()
+        inst.append(np.append(np.ctypeslib.as_array(lib.refscene_instance(h, i, C.byref(pm)), (16,)).copy(), pm.value))
+    out["instances"] = np.concatenate(inst) if inst else np.zeros(0, np.uint32)
+    n = C.c_uint32()
+    cams = lib.refscene_cameras(h, C.byref(n))
+    out["cameras"] = np.ctypeslib.as_array(cams, (n.value * 10,)).copy() if n.value else np.zeros(0, np.uint32)
     out["textures"] = []
     for i in range(counts[5]):
         w, hh, ch, cs = C.c_int(), C.c_int(), C.c_int(), C.c_int()
@@ -73,34 +89,45 @@ def _reference_arrays(path):
 def _native_arrays(path, threads=0):
     from chameleonrt_b200 import scene_io
 
-    loaded = scene_io.load_obj(path, threads)
+    loaded = scene_io.load_scene(path, threads)
     s = loaded.c_scene.contents
-    out = dict(counts=[s.num_meshes, s.meshes[0].num_geometries, s.num_parameterized_meshes, s.num_instances, s.num_materials,
-                       s.num_textures, s.num_lights], seconds=loaded.timings["total_s"], timings=loaded.timings, warnings=loaded.warnings,
-               geometries=[])
+    out = dict(counts=[s.num_meshes, s.meshes[0].num_geometries if s.num_meshes else 0, s.num_parameterized_meshes, s.num_instances,
+                       s.num_materials, s.num_textures, s.num_lights], seconds=loaded.timings["total_s"], timings=loaded.timings,
+               warnings=loaded.warnings, geometries=[], mesh_sizes=[])
     u32 = C.POINTER(C.c_uint32)
-    for g in range(s.meshes[0].num_geometries):
-        cg = s.meshes[0].geometries[g]
-        out["geometries"].append((np.ctypeslib.as_array(C.cast(cg.vertices, u32), (cg.num_vertices * 3,)).copy(),
-                                  np.ctypeslib.as_array(C.cast(cg.uvs, u32), (cg.num_vertices * 2,)).copy() if cg.uvs else np.zeros(0, np.uint32),
-                                  np.ctypeslib.as_array(cg.indices, (cg.num_tris * 3,)).copy()))
-    pm = s.parameterized_meshes[0]
-    out["material_ids"] = np.ctypeslib.as_array(pm.material_ids, (pm.num_material_ids,)).copy()
+    for m in range(s.num_meshes):
+        for g in range(s.meshes[m].num_geometries):
+            cg = s.meshes[m].geometries[g]
+            out["geometries"].append((np.ctypeslib.as_array(C.cast(cg.vertices, u32), (cg.num_vertices * 3,)).copy() if cg.num_vertices else np.zeros(0, np.uint32),
+                                      np.ctypeslib.as_array(C.cast(cg.uvs, u32), (cg.num_vertices * 2,)).copy() if cg.uvs else np.zeros(0, np.uint32),
+                                      np.ctypeslib.as_array(cg.indices, (cg.num_tris * 3,)).copy() if cg.num_tris else np.zeros(0, np.uint32)))
+        out["mesh_sizes"].append(s.meshes[m].num_geometries)
+    out["parameterized_meshes"] = []
+    for i in range(s.num_parameterized_meshes):
+        pm = s.parameterized_meshes[i]
+        out["parameterized_meshes"].append((pm.mesh_id, list(np.ctypeslib.as_array(pm.material_ids, (pm.num_material_ids,)))))
+    out["material_ids"] = np.array(out["parameterized_meshes"][0][1], np.uint32) if s.num_parameterized_meshes else np.zeros(0, np.uint32)
     out["materials"] = np.ctypeslib.as_array(C.cast(s.materials, u32), (s.num_materials * 16,)).copy() if s.num_materials else np.zeros(0, np.uint32)
-    out["light"] = np.ctypeslib.as_array(C.cast(s.lights, u32), (20,)).copy()
-    out["instance"] = np.ctypeslib.as_array(C.cast(C.pointer(s.instances[0]), u32), (16,)).copy()
+    out["lights"] = np.ctypeslib.as_array(C.cast(s.lights, u32), (20 * s.num_lights,)).copy()
+    inst = [np.append(np.ctypeslib.as_array(C.cast(C.pointer(s.instances[i]), u32), (16,)).copy(), s.instances[i].parameterized_mesh_id)
+            for i in range(s.num_instances)]
+    out["instances"] = np.concatenate(inst) if inst else np.zeros(0, np.uint32)
+    out["cameras"] = (np.concatenate([np.concatenate([c["position"], c["center"], c["up"], [np.float32(c["fov_y"])]]).astype(np.float32)
+                                      for c in loaded.cameras]).view(np.uint32) if loaded.cameras else np.zeros(0, np.uint32))
     out["textures"] = [(np.ctypeslib.as_array(s.textures[i].data, (s.textures[i].height, s.textures[i].width, s.textures[i].channels)).copy(),
                         int(s.textures[i].color_space)) for i in range(s.num_textures)]
     return out, loaded
 
 
 def _assert_same(a, b):
-    assert a["counts"] == b["counts"]
+    assert a["counts"] == b["counts"] and a["mesh_sizes"] == b["mesh_sizes"]
     for g, (x, y) in enumerate(zip(a["geometries"], b["geometries"])):
         for name, p, q in zip(("vertices", "uvs", "indices"), x, y):
             assert p.shape == q.shape and np.array_equal(p, q), f"geometry {g}: {name} differ"
-    for k in ("material_ids", "materials", "light", "instance"):
-        assert np.array_equal(a[k], b[k]), k
+    assert a["parameterized_meshes"] == b["parameterized_meshes"]
+    for k in ("material_ids", "materials", "lights", "instances", "cameras"):
+        assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), k
+    assert len(a["textures"]) == len(b["textures"])
     for (p, cs1), (q, cs2) in zip(a["textures"], b["textures"]):
         assert cs1 == cs2 and p.shape == q.shape and np.array_equal(p, q)
 
@@ -315,3 +342,148 @@ def test_native_obj_loader_is_faster_on_a_large_file(built, tmp_path):
     tris = sum(len(g[2]) // 3 for g in nat["geometries"])
     print(f"\n{tris} triangles, {os.path.getsize(path) / 1e6:.0f} MB: reference loader {ref['seconds']:.2f} s (call {t_ref:.2f} s), native {best}")
     assert best["total_s"] < ref["seconds"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# .crts (Scene::load_crts, util/scene.cpp:417-625)
+def _rotated(seed):
+    """A rotation + non-uniform scale + translation as a column-major list of 16 floats (an object's "matrix")."""
+    rng = np.random.default_rng(seed)
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    m = np.eye(4)
+    m[:3, :3] = q * rng.uniform(0.5, 2.0, 3)
+    m[:3, 3] = rng.normal(size=3) * 4
+    return [float(np.float32(x)) for x in m.T.reshape(-1)]
+
+
+def _crts_file(tmp_path, align=True, name="scene.crts"):
+    """Every material parameter and texture handle (helpers.synthetic_material_scene), three instances of the same meshes
+    under different matrices (-> shared parameterized meshes), two lights with arbitrary frames, two cameras."""
+    from chameleonrt_b200.crts_io import write_crts
+    from chameleonrt_b200.scene import Instance
+
+    scene, cam = synthetic_material_scene(spp=1)
+    scene.lights = []
+    for k in (1, 2):
+        scene.instances.append(Instance(np.array(_rotated(k), np.float32).reshape(4, 4).T, 0))
+    extra = [dict(type="LIGHT", color=[0.9, 0.8, 0.7], energy=12.5, size=[1.5, 0.75], matrix=_rotated(10)),
+             dict(type="CAMERA", fov_y=55.0, matrix=_rotated(11)),
+             dict(type="LIGHT", color=[1, 1, 1], energy=3, size=[2, 1], matrix=_rotated(12)),  # (integers in the JSON)
+             dict(type="CAMERA", fov_y=40, matrix=_rotated(13))]
+    return scene, write_crts(scene, str(tmp_path / name), extra_objects=extra, align=align)
+
+
+@needs_ref
+@pytest.mark.parametrize("align", [True, False])
+def test_native_crts_loader_builds_the_reference_loaders_scene(built, tmp_path, align):
+    """Meshes, (mesh, material) parameterized meshes in order of first use, instances, all 14 material parameters with their
+    texture handles, decoded images, lights (frames normalised with glm's vec4 arithmetic), cameras — bit for bit what
+    Scene::load_crts builds; also when the data block is not aligned in the file (the arrays are copied then)."""
+    pytest.importorskip("PIL")
+    scene, path = _crts_file(tmp_path, align)
+    ref = _reference_arrays(path)
+    for threads in (0, 1):
+        nat, loaded = _native_arrays(path, threads)
+        _assert_same(nat, ref)
+    assert nat["counts"] == [5, 1, 5, 15, 5, 2, 2] and len(loaded.cameras) == 2
+    assert len(nat["cameras"]) == 20 and nat["lights"].shape == (40,)
+
+
+@needs_ref
+def test_native_crts_loader_defaults_and_header_quirks(built, tmp_path):
+    """No lights (-> the generated one, emission 10), no materials section and material id -1 (-> the default material), a
+    key given twice (the last one counts), escapes in strings, numbers with exponents, an empty images list."""
+    import json
+    import struct
+
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0.5]], np.float32).tobytes()
+    i = np.array([[0, 1, 2], [2, 1, 3]], np.uint32).tobytes()
+    header = {"meshes": [{"positions": 0, "indices": 1}], "images": [],
+              "objects": [{"type": "MESH", "mesh": 0, "material": 4294967295, "matrix": _rotated(3)},
+                          {"type": "MESH", "mesh": 0.0, "material": 4294967295, "matrix": [1e0, 0, 0, 0, 0, 1.5E+0, 0, 0, 0, 0, 1, 0, -2.5e-1, 0, 0, 1]}],
+              "buffer_views": [{"byte_offset": 0, "byte_length": len(v), "type": "VEC3_F32"},
+                               {"byte_offset": len(v), "byte_length": len(i), "type": "UINT_32", "näme": "a \"quoted\" \\ name / \t tab"}]}
+    js = json.dumps(header)
+    js = js[:-1] + ', "objects": ' + json.dumps(header["objects"][::-1]) + "}"  # the second "objects" wins
+    path = tmp_path / "quirks.crts"
+    path.write_bytes(struct.pack("<Q", len(js)) + js.encode() + v + i)
+    ref = _reference_arrays(str(path))
+    nat, loaded = _native_arrays(str(path))
+    _assert_same(nat, ref)
+    assert nat["counts"] == [1, 1, 1, 2, 1, 0, 1]
+    assert "generating a default" in loaded.warnings and "No lights found" in loaded.warnings
+
+
+def test_native_crts_loader_errors(built, tmp_path):
+    import json
+    import struct
+
+    from chameleonrt_b200 import scene_io
+
+    def write(name, header, data=b"", raw=None):
+        js = raw if raw is not None else json.dumps(header).encode()
+        p = tmp_path / name
+        p.write_bytes(struct.pack("<Q", len(js)) + js + data)
+        return str(p)
+
+    with pytest.raises(RuntimeError, match="cannot open"):
+        scene_io.load_crts(str(tmp_path / "missing.crts"))
+    with pytest.raises(RuntimeError, match="Unsupported file"):
+        scene_io.load_scene(str(tmp_path / "scene.ply"))
+    (tmp_path / "short.crts").write_bytes(b"abc")
+    with pytest.raises(RuntimeError, match="too short"):
+        scene_io.load_crts(str(tmp_path / "short.crts"))
+    (tmp_path / "size.crts").write_bytes(struct.pack("<Q", 1000) + b"{}")
+    with pytest.raises(RuntimeError, match="header size past the end"):
+        scene_io.load_crts(str(tmp_path / "size.crts"))
+    with pytest.raises(RuntimeError, match="malformed JSON"):
+        scene_io.load_crts(write("bad.crts", None, raw=b'{"meshes": [1, 2,, ]}'))
+    views = [{"byte_offset": 0, "byte_length": 36, "type": "VEC3_F32"}, {"byte_offset": 36, "byte_length": 12, "type": "VEC3_U32"}]
+    tri = np.zeros(9, np.float32).tobytes() + np.array([0, 1, 2], np.uint32).tobytes()
+    with pytest.raises(RuntimeError, match="past the end"):
+        scene_io.load_crts(write("oob.crts", {"meshes": [{"positions": 0, "indices": 1}], "buffer_views": views}, tri[:40]))
+    with pytest.raises(RuntimeError, match="has no element 7"):
+        scene_io.load_crts(write("view.crts", {"meshes": [{"positions": 7, "indices": 1}], "buffer_views": views}, tri))
+    with pytest.raises(RuntimeError, match='has no "indices"'):
+        scene_io.load_crts(write("key.crts", {"meshes": [{"positions": 0}], "buffer_views": views}, tri))
+    with pytest.raises(RuntimeError, match="Invalid data type string"):
+        scene_io.load_crts(write("dtype.crts", {"meshes": [{"positions": 0, "indices": 1}],
+                                                "buffer_views": [dict(views[0], type="VEC3_F16"), views[1]]}, tri))
+    ok = {"meshes": [{"positions": 0, "indices": 1}], "buffer_views": views}
+    with pytest.raises(RuntimeError, match="instances mesh 3 of 1"):
+        scene_io.load_crts(write("mesh.crts", dict(ok, objects=[{"type": "MESH", "mesh": 3, "material": 0, "matrix": [0.0] * 16}]), tri))
+    with pytest.raises(RuntimeError, match="Unsupported object type"):
+        scene_io.load_crts(write("type.crts", dict(ok, objects=[{"type": "EMPTY", "matrix": [0.0] * 16}]), tri))
+    with pytest.raises(RuntimeError, match="array of 16 numbers"):
+        scene_io.load_crts(write("matrix.crts", dict(ok, objects=[{"type": "MESH", "mesh": 0, "material": 0, "matrix": [1.0] * 12}]), tri))
+    img_views = views + [{"byte_offset": 48, "byte_length": 16, "type": "UINT_8"}]
+    with pytest.raises(RuntimeError, match="Failed to load wood"):
+        scene_io.load_crts(write("image.crts", dict(ok, buffer_views=img_views, images=[{"name": "wood", "view": 2, "color_space": "SRGB"}]),
+                                 tri + b"\xff\xd8\xff\xe0JFIF" + bytes(8)))
+
+
+def test_native_crts_loader_round_trip_and_oracle_frame(built, tmp_path):
+    """Without the reference library (the GPU box): the loaded scene renders, through the CPU oracle, the frame of
+    crts_io.crts_scene_view(scene) — what Scene::load_crts builds from the file (tests/test_reference_plugin.py pins that)."""
+    pytest.importorskip("PIL")
+    from chameleonrt_b200 import scene_io
+    from chameleonrt_b200.crts_io import crts_scene_view, write_crts
+    from chameleonrt_b200.scene import QuadLight
+    from helpers import camera_for
+    from oracle import OracleBackend
+
+    scene, cam = synthetic_material_scene(spp=1)
+    scene.lights = [QuadLight(emission=(12.0, 11.0, 9.0, 1.0), position=(0.5, 4.5, 0.5, 1.0), normal=(0.0, -1.0, 0.0),
+                              v_x=(1.0, 0.0, 0.0), width=1.5, v_y=(0.0, 0.0, 1.0), height=1.0)]
+    loaded = scene_io.load_scene(write_crts(scene, str(tmp_path / "materials.crts")))
+    got = loaded.to_scene(spp=1)
+    assert len(got.meshes) == 5 and len(got.instances) == 5 and len(got.textures) == 2
+    c = camera_for(cam)
+    frames = []
+    for s in (crts_scene_view(scene), got):
+        o = OracleBackend(max_depth=5)
+        o.initialize(48, 32)
+        o.set_scene(s)
+        o.render(c.eye(), c.dir(), c.up(), cam["fov_y"], True, True)
+        frames.append(o.read_accum())
+    assert np.array_equal(frames[0].view(np.uint32), frames[1].view(np.uint32))

@@ -363,6 +363,37 @@ def test_round_2_options_on_the_emulated_renderer(mods):
         r.set_scene(scene)
 
 
+def test_natively_loaded_crts_renders_the_same_frame(mods, tmp_path, size=(48, 32)):
+    """.crts -> crtio_load_crts (geometry arrays used in place in the mapped file; several meshes, parameterized meshes and
+    instances, every material parameter, textured scalars, an explicit light) -> crtc_set_scene -> the frame of the Python
+    scene model of what Scene::load_crts builds (crts_io.crts_scene_view), bit for bit."""
+    pytest.importorskip("PIL")
+    from chameleonrt_b200 import scene_io
+    from chameleonrt_b200.crts_io import crts_scene_view, write_crts
+    from chameleonrt_b200.scene import QuadLight
+    from helpers import synthetic_material_scene
+
+    RenderCUDA = mods[0]
+    scene, cam = synthetic_material_scene(spp=2)
+    scene.lights = [QuadLight(emission=(12.0, 11.0, 9.0, 1.0), position=(0.5, 4.5, 0.5, 1.0), normal=(0.0, -1.0, 0.0),
+                              v_x=(1.0, 0.0, 0.0), width=1.5, v_y=(0.0, 0.0, 1.0), height=1.0)]
+    c = camera_for(cam)
+    args = (c.eye(), c.dir(), c.up(), cam["fov_y"])
+    loaded = scene_io.load_scene(write_crts(scene, str(tmp_path / "materials.crts")))
+    frames = []
+    for native in (False, True):
+        r = RenderCUDA(0)
+        r.initialize(*size)
+        if native:
+            r.set_scene_c(loaded.c_scene, samples_per_pixel=2)
+        else:
+            r.set_scene(crts_scene_view(scene))
+        for f in range(2):
+            st = r.render(*args, f == 0, True)
+        frames.append((r.read_accum(), st.num_rays))
+    assert frames[0][1] == frames[1][1] and np.array_equal(frames[0][0].view(np.uint32), frames[1][0].view(np.uint32))
+
+
 def test_natively_loaded_obj_renders_the_same_frame(mods, tmp_path, size=(48, 32), detail=0.25):
     """The scene-load row end to end: OBJ + MTL + PNG written by obj_io -> crtio_load_obj (native, parallel) ->
     crtc_set_scene on the native crt_scene_t (RenderCUDA.set_scene_c) -> the frame the Python scene model renders, bit for

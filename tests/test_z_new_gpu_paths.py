@@ -343,3 +343,11 @@ def test_natively_loaded_obj_renders_the_same_frame_on_the_gpu(mods, tmp_path):
     from test_simt_renderer import test_natively_loaded_obj_renders_the_same_frame
 
     test_natively_loaded_obj_renders_the_same_frame(mods, tmp_path, size=(320, 180), detail=0.5)
+
+
+def test_natively_loaded_crts_renders_the_same_frame_on_the_gpu(mods, tmp_path):
+    """crtio_load_crts (arrays in place in the mapped file) -> crtc_set_scene -> frame: tests/test_simt_renderer.py's function
+    on the B200, at a larger size."""
+    from test_simt_renderer import test_natively_loaded_crts_renders_the_same_frame
+
+    test_natively_loaded_crts_renders_the_same_frame(mods, tmp_path, size=(320, 180))
