@@ -487,8 +487,8 @@ uint32_t be32(const uint8_t *p)
 }
 
 // `file`: the bytes of a PNG file; `path`: its name for messages
-void decode_png_rgba_flipped(const uint8_t *file_data, size_t file_size, const std::string &path, std::vector<uint8_t> &out, int &width,
-                             int &height)
+void decode_png_rgba(const uint8_t *file_data, size_t file_size, const std::string &path, std::vector<uint8_t> &out, int &width,
+                     int &height, bool flip)
 {
     struct Bytes {  // (the body below was written against a vector)
         const uint8_t *p;
@@ -572,10 +572,10 @@ void decode_png_rgba_flipped(const uint8_t *file_data, size_t file_size, const s
             dst[x] = (uint8_t)(src[x] + pred);
         }
     }
-    // to RGBA as stbi_load(..., 4) does, rows bottom-up (stbi_set_flip_vertically_on_load(1), util/material.cpp:8)
+    // to RGBA as stbi_load(..., 4) does; flip: rows bottom-up (stbi_set_flip_vertically_on_load(1), util/material.cpp:8)
     out.resize((size_t)width * height * 4);
     for (int y = 0; y < height; ++y) {
-        const uint8_t *src = &img[stride * (size_t)(height - 1 - y)];
+        const uint8_t *src = &img[stride * (size_t)(flip ? height - 1 - y : y)];
         uint8_t *dst = &out[(size_t)width * 4 * y];
         for (int x = 0; x < width; ++x) {
             uint8_t r, g, b, a = 255;
@@ -612,7 +612,7 @@ void load_png_rgba_flipped(const std::string &path, std::vector<uint8_t> &out, i
         throw std::runtime_error("Failed to load " + path);  // util/material.cpp:11-13
     }
     const std::vector<uint8_t> file((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
-    decode_png_rgba_flipped(file.data(), file.size(), path, out, width, height);
+    decode_png_rgba(file.data(), file.size(), path, out, width, height, true);
 }
 
 // glm::normalize(v) = v * inversesqrt(dot(v, v)), inversesqrt(x) = 1 / sqrt(x)
@@ -656,7 +656,9 @@ struct GeometryData {
 struct crtio_scene {
     std::unique_ptr<MappedFile> mapping;  // .crts: the geometry arrays are the file's own bytes where their alignment allows
     std::vector<GeometryData> geometries;  // OBJ: the arrays of its shapes
-    std::vector<std::vector<uint8_t>> unaligned_copies;  // .crts: arrays that sit misaligned in the file
+    std::vector<std::vector<uint8_t>> unaligned_copies;  // .crts / glTF: arrays that cannot be used where they are in the file
+    std::vector<std::unique_ptr<MappedFile>> buffer_mappings;  // glTF: external .bin files
+    std::vector<std::vector<uint8_t>> decoded_buffers;         // glTF: buffers given as data: URIs
     std::vector<crt_geometry_t> geometry_views;
     std::vector<crt_mesh_t> meshes;
     std::vector<std::vector<uint32_t>> material_ids;  // per parameterized mesh
@@ -1313,14 +1315,14 @@ struct Json {
     {
         const Json *j = kind == kObject ? find(key) : nullptr;
         if (!j) {
-            throw std::runtime_error("crts header: " + where + " has no \"" + key + "\"");
+            throw std::runtime_error("scene header: " + where + " has no \"" + key + "\"");
         }
         return *j;
     }
     const Json &at(size_t index, const std::string &where) const
     {
         if (kind != kArray || index >= items.size()) {
-            throw std::runtime_error("crts header: " + where + " has no element " + std::to_string(index));
+            throw std::runtime_error("scene header: " + where + " has no element " + std::to_string(index));
         }
         return items[index];
     }
@@ -1336,20 +1338,20 @@ struct Json {
         case kSigned: return static_cast<T>(i);
         case kFloat: return static_cast<T>(d);
         case kBool: return static_cast<T>(boolean);
-        default: throw std::runtime_error("crts header: " + where + " is not a number");
+        default: throw std::runtime_error("scene header: " + where + " is not a number");
         }
     }
     const std::string &string(const std::string &where) const
     {
         if (kind != kString) {
-            throw std::runtime_error("crts header: " + where + " is not a string");
+            throw std::runtime_error("scene header: " + where + " is not a string");
         }
         return str;
     }
     std::vector<float> floats(size_t at_least, const std::string &where) const
     {
         if (kind != kArray || items.size() < at_least) {
-            throw std::runtime_error("crts header: " + where + " is not an array of " + std::to_string(at_least) + " numbers");
+            throw std::runtime_error("scene header: " + where + " is not an array of " + std::to_string(at_least) + " numbers");
         }
         std::vector<float> out(items.size());
         for (size_t k = 0; k < items.size(); ++k) {
@@ -1376,7 +1378,7 @@ private:
     const char *p, *end;
     [[noreturn]] void fail(const std::string &what) const
     {
-        throw std::runtime_error("crts header: malformed JSON (" + what + ")");
+        throw std::runtime_error("scene header: malformed JSON (" + what + ")");
     }
     void skip_space()
     {
@@ -1642,7 +1644,7 @@ void load_crts_impl(const std::string &file, int threads, crtio_scene &S)
     }
     const Json header = JsonParser(map.data + sizeof(uint64_t), map.data + sizeof(uint64_t) + json_size).parse_document();
     if (header.kind != Json::kObject) {
-        throw std::runtime_error("crts header: not an object");
+        throw std::runtime_error("scene header: not an object");
     }
     const uint8_t *data_base = reinterpret_cast<const uint8_t *>(map.data) + sizeof(uint64_t) + json_size;
     const size_t data_size = map.size - sizeof(uint64_t) - (size_t)json_size;
@@ -1727,7 +1729,7 @@ void load_crts_impl(const std::string &file, int threads, crtio_scene &S)
     crt::parallel_blocks((uint32_t)num_images, nthreads, [&](uint32_t i) {
         try {
             int w = 0, h = 0;
-            decode_png_rgba_flipped(image_views[i].data, image_views[i].bytes, image_names[i], S.texture_data[i], w, h);
+            decode_png_rgba(image_views[i].data, image_views[i].bytes, image_names[i], S.texture_data[i], w, h, true);
             S.textures[i].data = S.texture_data[i].data();
             S.textures[i].width = w;
             S.textures[i].height = h;
@@ -1858,10 +1860,631 @@ void load_crts_impl(const std::string &file, int threads, crtio_scene &S)
     S.timings[3] = t_end - t_parsed;
 }
 
-std::string file_extension(const std::string &path)  // get_file_extension, util/util.cpp
+std::string file_extension_of(const std::string &path)  // get_file_extension, util/util.cpp
 {
     const size_t dot = path.rfind('.');
     return dot == std::string::npos ? std::string() : path.substr(dot + 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// glTF 2.0 (.gltf + .bin / data: URIs, .glb) as Scene::load_gltf reads it through tinygltf (util/scene.cpp:230-415,
+// util/flatten_gltf.cpp). The float arithmetic of the node transforms (quaternion -> matrix, matrix products of the scene
+// graph flattening) is glm's, in its order of operations.
+struct Mat4 {
+    float c[4][4];  // column major: c[column][row]
+};
+Mat4 mat4_identity()
+{
+    Mat4 m;
+    std::memset(&m, 0, sizeof(m));
+    m.c[0][0] = m.c[1][1] = m.c[2][2] = m.c[3][3] = 1.f;
+    return m;
+}
+// glm: each column of the product is a * b[col], a row's four products summed left to right
+Mat4 mat4_mul(const Mat4 &a, const Mat4 &b)
+{
+    Mat4 r;
+    for (int col = 0; col < 4; ++col) {
+        for (int row = 0; row < 4; ++row) {
+            float sum = a.c[0][row] * b.c[col][0];
+            for (int k = 1; k < 4; ++k) {
+                sum += a.c[k][row] * b.c[col][k];
+            }
+            r.c[col][row] = sum;
+        }
+    }
+    return r;
+}
+std::vector<double> json_doubles(const Json &j, const std::string &where)
+{
+    if (j.kind != Json::kArray) {
+        throw std::runtime_error("scene header: " + where + " is not an array of numbers");
+    }
+    std::vector<double> out(j.items.size());
+    for (size_t k = 0; k < out.size(); ++k) {
+        out[k] = j.items[k].number<double>(where);
+    }
+    return out;
+}
+// read_node_transform (util/flatten_gltf.cpp:9-31): matrix, or translate * rotate * scale
+Mat4 gltf_node_transform(const Json &node, const std::string &where)
+{
+    Mat4 t = mat4_identity();
+    const Json *matrix = node.find("matrix");
+    if (matrix && matrix->kind == Json::kArray && !matrix->items.empty()) {  // (tinygltf: matrix and T/R/S are exclusive)
+        const std::vector<double> m = json_doubles(*matrix, where + " matrix");
+        if (m.size() < 16) {
+            throw std::runtime_error("glTF: " + where + " has a matrix of " + std::to_string(m.size()) + " numbers");
+        }
+        for (int k = 0; k < 16; ++k) {
+            t.c[k / 4][k % 4] = (float)m[k];
+        }
+        return t;
+    }
+    const auto triple = [&](const char *key, size_t n) {
+        const Json *j = node.find(key);
+        std::vector<double> v;
+        if (j && j->kind == Json::kArray && !j->items.empty()) {
+            v = json_doubles(*j, where + " " + key);
+            if (v.size() < n) {
+                throw std::runtime_error("glTF: " + where + " has a " + key + " of " + std::to_string(v.size()) + " numbers");
+            }
+        }
+        return v;
+    };
+    const std::vector<double> scale = triple("scale", 3), rotation = triple("rotation", 4), translation = triple("translation", 3);
+    if (!scale.empty()) {  // glm::scale(v): the identity's columns times v
+        const float v[3] = {(float)scale[0], (float)scale[1], (float)scale[2]};
+        const Mat4 id = mat4_identity();
+        for (int col = 0; col < 3; ++col) {
+            for (int row = 0; row < 4; ++row) {
+                t.c[col][row] = id.c[col][row] * v[col];
+            }
+        }
+    }
+    if (!rotation.empty()) {  // glm::mat4_cast(quat(w = r[3], x = r[0], y = r[1], z = r[2])) * transform
+        const float x = (float)rotation[0], y = (float)rotation[1], z = (float)rotation[2], w = (float)rotation[3];
+        const float qxx = x * x, qyy = y * y, qzz = z * z, qxz = x * z, qxy = x * y, qyz = y * z, qwx = w * x, qwy = w * y, qwz = w * z;
+        Mat4 r = mat4_identity();
+        r.c[0][0] = 1.f - 2.f * (qyy + qzz);
+        r.c[0][1] = 2.f * (qxy + qwz);
+        r.c[0][2] = 2.f * (qxz - qwy);
+        r.c[1][0] = 2.f * (qxy - qwz);
+        r.c[1][1] = 1.f - 2.f * (qxx + qzz);
+        r.c[1][2] = 2.f * (qyz + qwx);
+        r.c[2][0] = 2.f * (qxz + qwy);
+        r.c[2][1] = 2.f * (qyz - qwx);
+        r.c[2][2] = 1.f - 2.f * (qxx + qyy);
+        t = mat4_mul(r, t);
+    }
+    if (!translation.empty()) {  // glm::translate(v): column 3 = m[0] * v.x + m[1] * v.y + m[2] * v.z + m[3] of the identity
+        const float v[3] = {(float)translation[0], (float)translation[1], (float)translation[2]};
+        Mat4 tr = mat4_identity();
+        const Mat4 id = mat4_identity();
+        for (int row = 0; row < 4; ++row) {
+            tr.c[3][row] = id.c[0][row] * v[0] + id.c[1][row] * v[1] + id.c[2][row] * v[2] + id.c[3][row];
+        }
+        t = mat4_mul(tr, t);
+    }
+    return t;
+}
+
+std::string url_decode(const std::string &str)  // dlib::urldecode as vendored in tiny_gltf.h:2235-2255
+{
+    const auto hex = [](unsigned char ch) -> unsigned char {
+        if (ch <= '9' && ch >= '0') {
+            return (unsigned char)(ch - '0');
+        }
+        if (ch <= 'f' && ch >= 'a') {
+            return (unsigned char)(ch - 'a' + 10);
+        }
+        if (ch <= 'F' && ch >= 'A') {
+            return (unsigned char)(ch - 'A' + 10);
+        }
+        return 0;
+    };
+    std::string out;
+    for (size_t i = 0; i < str.size(); ++i) {
+        if (str[i] == '+') {
+            out += ' ';
+        } else if (str[i] == '%' && str.size() > i + 2) {
+            out += (char)(unsigned char)((hex((unsigned char)str[i + 1]) << 4) | hex((unsigned char)str[i + 2]));
+            i += 2;
+        } else {
+            out += str[i];
+        }
+    }
+    return out;
+}
+
+// The payload of a data: URI with one of the media types tinygltf accepts (IsDataURI, tiny_gltf.h:2820-2857), else false
+bool decode_data_uri(const std::string &uri, std::vector<uint8_t> &out)
+{
+    static const char *const headers[] = {"data:application/octet-stream;base64,", "data:image/jpeg;base64,", "data:image/png;base64,",
+                                          "data:image/bmp;base64,",  "data:image/gif;base64,", "data:text/plain;base64,",
+                                          "data:application/gltf-buffer;base64,"};
+    size_t start = 0;
+    for (const char *h : headers) {
+        if (uri.compare(0, std::strlen(h), h) == 0) {
+            start = std::strlen(h);
+        }
+    }
+    if (!start) {
+        return false;
+    }
+    out.clear();
+    out.reserve((uri.size() - start) / 4 * 3);
+    uint32_t acc = 0;
+    int bits = 0;
+    for (size_t i = start; i < uri.size(); ++i) {
+        const char ch = uri[i];
+        int v;
+        if (ch >= 'A' && ch <= 'Z') {
+            v = ch - 'A';
+        } else if (ch >= 'a' && ch <= 'z') {
+            v = ch - 'a' + 26;
+        } else if (ch >= '0' && ch <= '9') {
+            v = ch - '0' + 52;
+        } else if (ch == '+') {
+            v = 62;
+        } else if (ch == '/') {
+            v = 63;
+        } else {
+            break;  // '=' padding (or anything that is not base64) ends the data
+        }
+        acc = (acc << 6) | (uint32_t)v;
+        bits += 6;
+        if (bits >= 8) {
+            bits -= 8;
+            out.push_back((uint8_t)(acc >> bits));
+        }
+    }
+    return true;
+}
+
+void load_gltf_impl(const std::string &file, int threads, crtio_scene &S)
+{
+    const double t_start = now_s();
+    const unsigned nthreads = crt::host_threads(threads);
+    S.mapping.reset(new MappedFile(file, /*sequential=*/false));
+    const MappedFile &map = *S.mapping;
+    const bool binary = file_extension_of(file) != "gltf";
+    const char *json_begin = map.data, *json_end = map.data + map.size;
+    const uint8_t *glb_bin = nullptr;
+    size_t glb_bin_size = 0;
+    if (binary) {  // TinyGLTF::LoadBinaryFromMemory (tiny_gltf.h:6194-6260)
+        if (map.size < 20) {
+            throw std::runtime_error("TinyGLTF Error loading " + file + " error: Too short data size for glTF Binary.");
+        }
+        if (std::memcmp(map.data, "glTF", 4) != 0) {
+            throw std::runtime_error("TinyGLTF Error loading " + file + " error: Invalid magic.");
+        }
+        uint32_t length, model_length, model_format;
+        std::memcpy(&length, map.data + 8, 4);
+        std::memcpy(&model_length, map.data + 12, 4);
+        std::memcpy(&model_format, map.data + 16, 4);
+        if (20ull + model_length > map.size || model_length < 1 || length > map.size || 20ull + model_length > length ||
+            model_format != 0x4E4F534Au) {
+            throw std::runtime_error("TinyGLTF Error loading " + file + " error: Invalid glTF binary.");
+        }
+        json_begin = map.data + 20;
+        json_end = json_begin + model_length;
+        const size_t rest = (size_t)length - (20 + (size_t)model_length);
+        if (rest >= 8) {  // the BIN chunk: 4 bytes length, 4 bytes type, data
+            glb_bin = reinterpret_cast<const uint8_t *>(json_end) + 8;
+            glb_bin_size = rest - 8;
+        }
+    }
+    const Json doc = JsonParser(json_begin, json_end).parse_document();
+    if (doc.kind != Json::kObject) {
+        throw std::runtime_error("TinyGLTF Error loading " + file + " error: the document is not a JSON object");
+    }
+    static const Json null_json;
+    const auto section = [&](const char *key) -> const Json & {
+        const Json *j = doc.find(key);
+        return j ? *j : null_json;
+    };
+    const auto optional_index = [&](const Json &o, const char *key, const std::string &where) -> int64_t {
+        const Json *j = o.kind == Json::kObject ? o.find(key) : nullptr;
+        if (!j) {
+            return -1;
+        }
+        if (j->kind != Json::kUnsigned && j->kind != Json::kSigned) {
+            throw std::runtime_error("glTF: " + where + " " + key + " is not an integer");
+        }
+        return j->number<int64_t>(where);
+    };
+    const auto required_index = [&](const Json &o, const char *key, const std::string &where) -> size_t {
+        const int64_t v = optional_index(o, key, where);
+        if (v < 0) {
+            throw std::runtime_error("glTF: " + where + " has no \"" + key + "\"");
+        }
+        return (size_t)v;
+    };
+    std::string base_dir;  // GetBaseDir (tiny_gltf.h): up to the last separator, "" if there is none
+    {
+        const size_t sep = file.find_last_of("/\\");
+        base_dir = sep == std::string::npos ? std::string() : file.substr(0, sep);
+    }
+    const auto join_path = [&](const std::string &name) {
+        if (base_dir.empty()) {
+            return name;
+        }
+        return base_dir.back() == '/' ? base_dir + name : base_dir + "/" + name;
+    };
+    // ---- buffers ----
+    struct Span {
+        const uint8_t *data = nullptr;
+        size_t size = 0;
+    };
+    const Json &jbuffers = section("buffers");
+    std::vector<Span> buffers(jbuffers.size());
+    for (size_t i = 0; i < buffers.size(); ++i) {
+        const std::string where = "buffer " + std::to_string(i);
+        const Json &b = jbuffers.at(i, "buffers");
+        const size_t byte_length = required_index(b, "byteLength", where);
+        const Json *uri = b.find("uri");
+        if (!uri) {
+            if (!binary || i != 0 || !glb_bin) {
+                throw std::runtime_error("glTF: " + where + " has no uri (only the first buffer of a .glb may)");
+            }
+            buffers[i] = Span{glb_bin, glb_bin_size};
+        } else {
+            const std::string &u = uri->string(where + " uri");
+            S.decoded_buffers.emplace_back();
+            if (decode_data_uri(u, S.decoded_buffers.back())) {
+                buffers[i] = Span{S.decoded_buffers.back().data(), S.decoded_buffers.back().size()};
+            } else {
+                S.decoded_buffers.pop_back();
+                S.buffer_mappings.emplace_back(new MappedFile(join_path(url_decode(u)), /*sequential=*/false));
+                buffers[i] = Span{reinterpret_cast<const uint8_t *>(S.buffer_mappings.back()->data), S.buffer_mappings.back()->size};
+            }
+        }
+        if (buffers[i].size < byte_length) {
+            throw std::runtime_error("glTF: " + where + " holds " + std::to_string(buffers[i].size) + " bytes, byteLength says " +
+                                     std::to_string(byte_length));
+        }
+    }
+    // ---- buffer views and accessors ----
+    const Json &jviews = section("bufferViews");
+    const Json &jaccessors = section("accessors");
+    struct ViewSpan {
+        const uint8_t *data;
+        size_t length, stride, room;  // room: bytes from data to the end of the buffer
+    };
+    const auto view_of = [&](size_t id, const std::string &where) {
+        const std::string vw = where + " bufferView " + std::to_string(id);
+        const Json &v = jviews.at(id, "bufferViews");
+        const size_t buffer = required_index(v, "buffer", vw), length = required_index(v, "byteLength", vw);
+        const int64_t offset = std::max<int64_t>(0, optional_index(v, "byteOffset", vw)), stride = std::max<int64_t>(0, optional_index(v, "byteStride", vw));
+        if (buffer >= buffers.size()) {
+            throw std::runtime_error("glTF: " + vw + " names buffer " + std::to_string(buffer) + " of " + std::to_string(buffers.size()));
+        }
+        if ((size_t)offset > buffers[buffer].size || length > buffers[buffer].size - (size_t)offset) {
+            throw std::runtime_error("glTF: " + vw + " reaches past the end of its buffer");
+        }
+        return ViewSpan{buffers[buffer].data + offset, length, (size_t)stride, buffers[buffer].size - (size_t)offset};
+    };
+    struct Elements {  // Accessor<T> (util/buffer_view.h): element i at data + i * stride
+        const uint8_t *data;
+        size_t stride, count;
+        int component_type;
+        std::string type;
+    };
+    const auto accessor_of = [&](size_t id, size_t element_bytes, const std::string &where) {
+        const std::string aw = where + " accessor " + std::to_string(id);
+        const Json &a = jaccessors.at(id, "accessors");
+        if (a.find("sparse")) {
+            throw std::runtime_error("glTF: " + aw + " is sparse (not supported)");
+        }
+        const int64_t view_id = optional_index(a, "bufferView", aw);
+        if (view_id < 0) {
+            throw std::runtime_error("glTF: " + aw + " has no bufferView");
+        }
+        const ViewSpan view = view_of((size_t)view_id, aw);
+        Elements e;
+        e.component_type = (int)required_index(a, "componentType", aw);
+        e.type = a.at("type", aw).string(aw + " type");
+        e.count = required_index(a, "count", aw);
+        size_t components = 0, component_bytes = 0;
+        static const struct {
+            const char *name;
+            size_t n;
+        } types[] = {{"SCALAR", 1}, {"VEC2", 2}, {"VEC3", 3}, {"VEC4", 4}, {"MAT2", 4}, {"MAT3", 9}, {"MAT4", 16}};
+        for (const auto &t : types) {
+            components = e.type == t.name ? t.n : components;
+        }
+        switch (e.component_type) {
+        case 5120: case 5121: component_bytes = 1; break;
+        case 5122: case 5123: component_bytes = 2; break;
+        case 5124: case 5125: case 5126: component_bytes = 4; break;
+        case 5130: component_bytes = 8; break;
+        default: break;
+        }
+        if (!components || !component_bytes) {
+            throw std::runtime_error("glTF: " + aw + " has an unknown type or componentType");
+        }
+        e.stride = std::max(view.stride, components * component_bytes);  // BufferView: max(byteStride, gltf_base_stride)
+        const size_t offset = (size_t)std::max<int64_t>(0, optional_index(a, "byteOffset", aw));
+        if (e.count && (offset > view.room || (e.count - 1) * e.stride + element_bytes > view.room - offset)) {
+            throw std::runtime_error("glTF: " + aw + " reaches past the end of its buffer");
+        }
+        e.data = view.data + offset;
+        return e;
+    };
+    // elements of `bytes` bytes each as one packed, 4-byte aligned array: in place if they already are, else gathered
+    const auto packed = [&](const Elements &e, size_t bytes) {
+        if (e.stride == bytes && reinterpret_cast<uintptr_t>(e.data) % 4 == 0) {
+            return e.data;
+        }
+        S.unaligned_copies.emplace_back(e.count * bytes);
+        uint8_t *dst = S.unaligned_copies.back().data();
+        for (size_t i = 0; i < e.count; ++i) {
+            std::memcpy(dst + i * bytes, e.data + i * e.stride, bytes);
+        }
+        return static_cast<const uint8_t *>(dst);
+    };
+    // ---- meshes: a glTF mesh is a parameterized mesh, its primitives are the geometries (scene.cpp:256-330) ----
+    const Json &jmeshes = section("meshes");
+    const size_t num_meshes = jmeshes.size();
+    size_t num_geometries = 0;
+    for (size_t m = 0; m < num_meshes; ++m) {
+        num_geometries += jmeshes.at(m, "meshes").at("primitives", "mesh " + std::to_string(m)).size();
+    }
+    S.geometry_views.reserve(num_geometries);  // (crt_mesh_t points into it)
+    S.meshes.resize(num_meshes);
+    S.material_ids.resize(num_meshes);
+    S.parameterized_meshes.resize(num_meshes);
+    for (size_t m = 0; m < num_meshes; ++m) {
+        const Json &prims = jmeshes.at(m, "meshes").at("primitives", "mesh " + std::to_string(m));
+        const size_t first = S.geometry_views.size();
+        for (size_t k = 0; k < prims.size(); ++k) {
+            const std::string where = "mesh " + std::to_string(m) + " primitive " + std::to_string(k);
+            const Json &p = prims.at(k, where);
+            S.material_ids[m].push_back((uint32_t)optional_index(p, "material", where));  // -1: validate_materials
+            const int64_t mode = optional_index(p, "mode", where);
+            if (mode != -1 && mode != 4) {
+                throw std::runtime_error("Unsupported primitive mode! Only triangles are supported");
+            }
+            const Json &attributes = p.at("attributes", where);
+            const Elements pos = accessor_of(required_index(attributes, "POSITION", where), 12, where + " POSITION");
+            if (pos.component_type != 5126 || pos.type != "VEC3") {
+                throw std::runtime_error("glTF: " + where + " POSITION is not FLOAT VEC3");
+            }
+            const uint8_t *uv_data = nullptr;
+            if (attributes.find("TEXCOORD_0")) {
+                const Elements uv = accessor_of(required_index(attributes, "TEXCOORD_0", where), 8, where + " TEXCOORD_0");
+                if (uv.component_type != 5126 || uv.type != "VEC2") {
+                    throw std::runtime_error("glTF: " + where + " TEXCOORD_0 is not FLOAT VEC2 (the reference reads it as floats)");
+                }
+                if (uv.count != pos.count) {
+                    throw std::runtime_error("glTF: " + where + " has " + std::to_string(uv.count) + " texcoords for " +
+                                             std::to_string(pos.count) + " positions");
+                }
+                uv_data = uv.count ? packed(uv, 8) : nullptr;
+            }
+            const int64_t indices_id = optional_index(p, "indices", where);
+            if (indices_id < 0) {
+                throw std::runtime_error("glTF: " + where + " has no indices (the reference reads accessor -1 there)");
+            }
+            const std::string iw = where + " indices";
+            const Json &ia = jaccessors.at((size_t)indices_id, "accessors");
+            const int component_type = (int)required_index(ia, "componentType", iw);
+            const uint8_t *index_data = nullptr;
+            size_t num_tris = 0;
+            if (component_type == 5123) {  // uint16 -> uint32
+                const Elements idx = accessor_of((size_t)indices_id, 2, iw);
+                num_tris = idx.count / 3;
+                S.unaligned_copies.emplace_back(num_tris * 12);
+                uint32_t *dst = reinterpret_cast<uint32_t *>(S.unaligned_copies.back().data());
+                for (size_t i = 0; i < num_tris * 3; ++i) {
+                    uint16_t v;
+                    std::memcpy(&v, idx.data + i * idx.stride, 2);
+                    dst[i] = v;
+                }
+                index_data = S.unaligned_copies.back().data();
+            } else if (component_type == 5125) {
+                Elements idx = accessor_of((size_t)indices_id, 4, iw);
+                num_tris = idx.count / 3;
+                idx.count = num_tris * 3;
+                index_data = packed(idx, 4);
+            } else {
+                throw std::runtime_error("Unsupported index component type");
+            }
+            if (pos.count > 0xffffffffull || num_tris > 0xffffffffull) {
+                throw std::runtime_error("glTF: " + where + " is too large for 32-bit counts");
+            }
+            S.geometry_views.push_back(crt_geometry_t{reinterpret_cast<const float *>(packed(pos, 12)), reinterpret_cast<const float *>(uv_data),
+                                                      reinterpret_cast<const uint32_t *>(index_data), (uint32_t)pos.count, (uint32_t)num_tris});
+        }
+        S.meshes[m] = crt_mesh_t{S.geometry_views.data() + first, (uint32_t)prims.size()};
+        S.parameterized_meshes[m] = crt_parameterized_mesh_t{nullptr, 0u, (uint32_t)m};
+    }
+    const double t_parsed = now_s();
+    // ---- images (tinygltf's LoadImageData: stb_image, four components, rows top-down), linear until a material says otherwise ----
+    const Json &jimages = section("images");
+    const size_t num_images = jimages.size();
+    S.texture_data.resize(num_images);
+    S.textures.resize(num_images);
+    std::vector<Span> encoded(num_images);
+    std::vector<std::string> image_names(num_images);
+    std::vector<std::vector<uint8_t>> image_files(num_images);
+    for (size_t i = 0; i < num_images; ++i) {
+        const std::string where = "image " + std::to_string(i);
+        const Json &img = jimages.at(i, "images");
+        if (const Json *name = img.find("name")) {
+            image_names[i] = name->kind == Json::kString ? name->str : std::string();
+        }
+        image_names[i] = where + " \"" + image_names[i] + "\"";
+        const Json *uri = img.find("uri");
+        const int64_t view_id = optional_index(img, "bufferView", where);
+        if ((uri != nullptr) == (view_id >= 0)) {
+            throw std::runtime_error("TinyGLTF Error loading " + file + " error: " + where + " needs exactly one of `bufferView` and `uri`");
+        }
+        if (view_id >= 0) {
+            const ViewSpan v = view_of((size_t)view_id, where);
+            encoded[i] = Span{v.data, v.length};
+        } else {
+            const std::string &u = uri->string(where + " uri");
+            if (!decode_data_uri(u, image_files[i])) {
+                const std::string path = join_path(url_decode(u));
+                std::ifstream in(path.c_str(), std::ios::binary);
+                if (!in) {
+                    throw std::runtime_error("glTF: cannot read " + path + " (" + where + ")");
+                }
+                image_files[i].assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
+            }
+            encoded[i] = Span{image_files[i].data(), image_files[i].size()};
+        }
+        S.textures[i] = crt_image_t{nullptr, 0, 0, 4, CRT_COLOR_SPACE_LINEAR};
+    }
+    std::vector<std::string> image_errors(num_images);
+    crt::parallel_blocks((uint32_t)num_images, nthreads, [&](uint32_t i) {
+        try {
+            int w = 0, h = 0;
+            decode_png_rgba(encoded[i].data, encoded[i].size, image_names[i], S.texture_data[i], w, h, false);
+            S.textures[i].data = S.texture_data[i].data();
+            S.textures[i].width = w;
+            S.textures[i].height = h;
+        } catch (const std::exception &e) {
+            image_errors[i] = e.what();
+        }
+    });
+    for (const std::string &e : image_errors) {
+        if (!e.empty()) {
+            throw std::runtime_error(e);
+        }
+    }
+    // ---- materials: pbrMetallicRoughness -> DisneyMaterial (scene.cpp:353-388) ----
+    const Json &jtextures = section("textures");
+    const auto image_of_texture = [&](const Json &info, const std::string &where) {
+        const size_t tex = required_index(info, "index", where);
+        const size_t source = required_index(jtextures.at(tex, "textures"), "source", where + " texture " + std::to_string(tex));
+        if (source >= num_images) {
+            throw std::runtime_error("glTF: " + where + " names image " + std::to_string(source) + " of " + std::to_string(num_images));
+        }
+        return (uint32_t)source;
+    };
+    const Json &jmaterials = section("materials");
+    for (size_t i = 0; i < jmaterials.size(); ++i) {
+        const std::string where = "material " + std::to_string(i);
+        const Json &m = jmaterials.at(i, "materials");
+        crt_material_t d;  // DisneyMaterial's defaults, util/material.h:29-46
+        std::memset(&d, 0, sizeof(d));
+        d.ior = 1.5f;
+        double base[3] = {1.0, 1.0, 1.0}, metallic = 1.0, roughness = 1.0;  // tinygltf's PbrMetallicRoughness defaults
+        const Json *pbr = m.kind == Json::kObject ? m.find("pbrMetallicRoughness") : nullptr;
+        if (pbr && pbr->kind == Json::kObject) {
+            if (const Json *f = pbr->find("baseColorFactor")) {
+                const std::vector<double> v = json_doubles(*f, where + " baseColorFactor");
+                if (v.size() != 4) {
+                    throw std::runtime_error("TinyGLTF Error loading " + file + " error: Array length of `baseColorFactor` parameter in "
+                                             "pbrMetallicRoughness must be 4, but got " + std::to_string(v.size()));
+                }
+                base[0] = v[0], base[1] = v[1], base[2] = v[2];
+            }
+            if (const Json *f = pbr->find("metallicFactor")) {
+                metallic = f->number<double>(where + " metallicFactor");
+            }
+            if (const Json *f = pbr->find("roughnessFactor")) {
+                roughness = f->number<double>(where + " roughnessFactor");
+            }
+        }
+        d.base_color[0] = (float)base[0], d.base_color[1] = (float)base[1], d.base_color[2] = (float)base[2];
+        d.metallic = (float)metallic;
+        d.roughness = (float)roughness;
+        if (pbr && pbr->kind == Json::kObject) {
+            if (const Json *t = pbr->find("baseColorTexture")) {
+                const uint32_t id = image_of_texture(*t, where + " baseColorTexture");
+                S.textures[id].color_space = CRT_COLOR_SPACE_SRGB;
+                const uint32_t mask = 0x80000000u | (id & 0x1fffffffu);
+                std::memcpy(&d.base_color[0], &mask, 4);
+            }
+            if (const Json *t = pbr->find("metallicRoughnessTexture")) {  // metallic = blue, roughness = green
+                const uint32_t id = image_of_texture(*t, where + " metallicRoughnessTexture");
+                S.textures[id].color_space = CRT_COLOR_SPACE_LINEAR;
+                const uint32_t metal = 0x80000000u | (id & 0x1fffffffu) | (2u << 29), rough = 0x80000000u | (id & 0x1fffffffu) | (1u << 29);
+                std::memcpy(&d.metallic, &metal, 4);
+                std::memcpy(&d.roughness, &rough, 4);
+            }
+        }
+        S.materials.push_back(d);
+    }
+    // ---- instances: the nodes of the default scene that carry a mesh, the scene graph flattened (flatten_gltf.cpp) ----
+    const Json &jscenes = section("scenes"), &jnodes = section("nodes");
+    int64_t default_scene = optional_index(doc, "scene", "document");
+    if (default_scene < 0) {
+        default_scene = 0;
+    }
+    const Json &scene = jscenes.at((size_t)default_scene, "scenes");
+    const Json *roots = scene.find("nodes");
+    std::vector<size_t> root_ids;
+    for (size_t k = 0; roots && k < roots->size(); ++k) {
+        root_ids.push_back(roots->at(k, "scene nodes").number<size_t>("scene nodes"));
+    }
+    const auto node_at = [&](size_t id) -> const Json & { return jnodes.at(id, "nodes"); };
+    const auto add_instance = [&](const Json &node, const Mat4 &transform, const std::string &where) {
+        const int64_t mesh = optional_index(node, "mesh", where);
+        if (mesh < 0) {
+            return;
+        }
+        if ((size_t)mesh >= num_meshes) {
+            throw std::runtime_error("glTF: " + where + " instances mesh " + std::to_string(mesh) + " of " + std::to_string(num_meshes));
+        }
+        crt_instance_t inst;
+        std::memset(&inst, 0, sizeof(inst));
+        std::memcpy(inst.transform, transform.c, sizeof(inst.transform));
+        inst.parameterized_mesh_id = (uint32_t)mesh;
+        S.instances.push_back(inst);
+    };
+    bool single_level = true;  // gltf_is_single_level: no root has children
+    for (size_t id : root_ids) {
+        const Json *children = node_at(id).find("children");
+        single_level = single_level && !(children && children->size());
+    }
+    if (single_level) {
+        for (size_t id : root_ids) {
+            add_instance(node_at(id), gltf_node_transform(node_at(id), "node " + std::to_string(id)), "node " + std::to_string(id));
+        }
+    } else {
+        // depth first, parents before children; a node's matrix = parent * own (the float matrix goes through the flattened
+        // node's double array and back unchanged)
+        struct Visit {
+            size_t id;
+            Mat4 parent;
+            int depth;
+        };
+        std::vector<Visit> stack;
+        for (size_t k = root_ids.size(); k-- > 0;) {
+            stack.push_back(Visit{root_ids[k], mat4_identity(), 0});
+        }
+        size_t visited = 0;
+        while (!stack.empty()) {
+            const Visit v = stack.back();
+            stack.pop_back();
+            if (v.depth > 256 || ++visited > (size_t)1 << 26) {
+                throw std::runtime_error("glTF: the node hierarchy of " + file + " is cyclic or too deep");
+            }
+            const std::string where = "node " + std::to_string(v.id);
+            const Json &node = node_at(v.id);
+            const Mat4 transform = mat4_mul(v.parent, gltf_node_transform(node, where));
+            add_instance(node, transform, where);
+            const Json *children = node.find("children");
+            for (size_t k = children ? children->size() : 0; k-- > 0;) {
+                stack.push_back(Visit{children->at(k, where + " children").number<size_t>(where + " children"), transform, v.depth + 1});
+            }
+        }
+    }
+    std::ostringstream warn;
+    validate_materials(S, warn);
+    S.lights.push_back(generated_light(20.f));  // scene.cpp:403-414
+    S.finish_views();
+    S.warnings = warn.str();
+    const double t_end = now_s();
+    S.timings[0] = t_end - t_start;
+    S.timings[1] = t_parsed - t_start;
+    S.timings[2] = 0.0;
+    S.timings[3] = t_end - t_parsed;
 }
 
 template <typename Fn>
@@ -1899,16 +2522,23 @@ int crtio_load_crts(const char *path, int threads, crtio_scene **out)
     return load_with(path, out, "crtio_load_crts", [&](const std::string &file, crtio_scene &s) { load_crts_impl(file, threads, s); });
 }
 
+int crtio_load_gltf(const char *path, int threads, crtio_scene **out)
+{
+    return load_with(path, out, "crtio_load_gltf", [&](const std::string &file, crtio_scene &s) { load_gltf_impl(file, threads, s); });
+}
+
 int crtio_load(const char *path, int threads, crtio_scene **out)
 {
     return load_with(path, out, "crtio_load", [&](const std::string &file, crtio_scene &s) {
-        const std::string ext = file_extension(file);
+        const std::string ext = file_extension_of(file);
         if (ext == "obj") {
             load_obj_impl(file, threads, s);
+        } else if (ext == "gltf" || ext == "glb") {
+            load_gltf_impl(file, threads, s);
         } else if (ext == "crts") {
             load_crts_impl(file, threads, s);
         } else {
-            throw std::runtime_error("Unsupported file " + file);  // scene.cpp:63-66 (glTF and PBRT are not read natively)
+            throw std::runtime_error("Unsupported file " + file);  // scene.cpp:63-66 (PBRT is not read, as in a default build of the reference)
         }
     });
 }

@@ -36,7 +36,7 @@ def _lib():
         if not os.path.exists(lib_path()):
             raise RuntimeError(f"{lib_path()} is missing: build it first (python -c 'import __graft_entry__ as g; g.build()')")
         lib = C.CDLL(lib_path())
-        for fn in (lib.crtio_load_obj, lib.crtio_load_crts, lib.crtio_load):
+        for fn in (lib.crtio_load_obj, lib.crtio_load_crts, lib.crtio_load_gltf, lib.crtio_load):
             fn.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
         lib.crtio_cameras.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_float))]
         lib.crtio_scene_view.restype = C.POINTER(CScene)
@@ -133,6 +133,11 @@ def load_crts(path: str, threads: int = 0) -> LoadedScene:
     return _load(_lib().crtio_load_crts, path, threads)
 
 
+def load_gltf(path: str, threads: int = 0) -> LoadedScene:
+    """``Scene::load_gltf`` (util/scene.cpp:230-415): .gltf / .glb, packed accessors used in place, the scene graph flattened."""
+    return _load(_lib().crtio_load_gltf, path, threads)
+
+
 def load_scene(path: str, threads: int = 0) -> LoadedScene:
-    """``Scene::Scene`` (util/scene.cpp:49-67): the loader the file's extension names (obj, crts)."""
+    """``Scene::Scene`` (util/scene.cpp:49-67): the loader the file's extension names (obj, gltf, glb, crts)."""
     return _load(_lib().crtio_load, path, threads)

@@ -10,7 +10,7 @@
  * delimited from the g / o / usemtl events, and the shapes are remapped concurrently, one open-addressing table each.
  *
  * crtio_load_crts is Scene::load_crts (util/scene.cpp:417-625), the reference's binary format, with the arrays left where they
- * are in the mapped file; crtio_load dispatches on the extension like Scene::Scene (util/scene.cpp:49-67).
+ * are in the mapped file; crtio_load_gltf is Scene::load_gltf (:230-415); crtio_load dispatches on the extension like Scene::Scene (util/scene.cpp:49-67).
  *
  * The result is a crt_scene_t (include/crt_scene.h) owned by the handle: pass crtio_scene_view(h) to crtc_set_scene.
  *
@@ -50,7 +50,17 @@ int crtio_load_obj(const char *path, int threads, crtio_scene **out);
  * handle and crt_geometry_t points into it (arrays that are not 4-byte aligned in the file are copied). Images are decoded
  * concurrently. */
 int crtio_load_crts(const char *path, int threads, crtio_scene **out);
-/* Scene::Scene (util/scene.cpp:49-67): the loader is chosen by the file extension (obj, crts). */
+/* Scene::load_gltf (util/scene.cpp:230-415, which reads the file through tinygltf and flattens the scene graph with
+ * util/flatten_gltf.cpp): glTF 2.0 as .gltf (buffers in external files or data: URIs) or .glb. A glTF mesh becomes a mesh plus
+ * its parameterized mesh (primitives = geometries, POSITION / TEXCOORD_0 as floats, 16- or 32-bit indices), the nodes of the
+ * default scene that carry a mesh become instances (node transforms composed down the hierarchy in glm's float arithmetic),
+ * pbrMetallicRoughness becomes base colour / metallic / roughness with texture handles (base colour textures sRGB,
+ * metallic-roughness textures linear, B and G channels), images are decoded to RGBA (PNG), the light is generated. Accessors
+ * that are tightly packed and aligned are used in place in the mapped buffer; interleaved or 16-bit ones are gathered.
+ * Not read (an error): sparse accessors, non-indexed or non-triangle primitives, JPEG images, extensions that move data
+ * (Draco, meshopt). */
+int crtio_load_gltf(const char *path, int threads, crtio_scene **out);
+/* Scene::Scene (util/scene.cpp:49-67): the loader is chosen by the file extension (obj, gltf, glb, crts). */
 int crtio_load(const char *path, int threads, crtio_scene **out);
 /* The cameras of the file (CAMERA objects of a .crts; none for an OBJ): returns how many, *out = the array. */
 int crtio_cameras(const crtio_scene *s, const crtio_camera_t **out);

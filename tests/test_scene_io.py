@@ -487,3 +487,254 @@ def test_native_crts_loader_round_trip_and_oracle_frame(built, tmp_path):
         o.render(c.eye(), c.dir(), c.up(), cam["fov_y"], True, True)
         frames.append(o.read_accum())
     assert np.array_equal(frames[0].view(np.uint32), frames[1].view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# glTF (Scene::load_gltf, util/scene.cpp:230-415 over tinygltf; util/flatten_gltf.cpp)
+def _png_bytes(img):
+    import io
+
+    from PIL import Image as PILImage
+
+    buf = io.BytesIO()
+    mode = {1: "L", 3: "RGB", 4: "RGBA"}[img.shape[2]]
+    PILImage.fromarray(img[:, :, 0] if mode == "L" else img, mode).save(buf, format="PNG")
+    return buf.getvalue()
+
+
+def _gltf_hierarchy(tmp_path, container, seed=5):
+    """A glTF the way exporters write them: a node hierarchy three levels deep with translation / rotation / scale nodes and
+    matrix nodes, meshes instanced from several nodes, an interleaved vertex buffer (byteStride), 16-bit and 32-bit indices,
+    accessor byteOffsets, a primitive without material, textures (base colour + metallic-roughness) and a second, unused
+    scene. container: "gltf" (external .bin + .png files), "datauri" (everything base64 in the .gltf) or "glb" (one binary
+    file, images in buffer views)."""
+    import base64
+    import json
+    import struct
+
+    rng = np.random.default_rng(seed)
+    blob = bytearray()
+    views, accessors = [], []
+
+    def add_view(raw, stride=None):
+        while len(blob) % 4:
+            blob.append(0)
+        v = {"buffer": 0, "byteOffset": len(blob), "byteLength": len(raw)}
+        if stride:
+            v["byteStride"] = stride
+        views.append(v)
+        blob.extend(raw)
+        return len(views) - 1
+
+    def add_accessor(view, comp, typ, count, offset=0):
+        a = {"bufferView": view, "componentType": comp, "count": count, "type": typ}
+        if offset:
+            a["byteOffset"] = offset
+        accessors.append(a)
+        return len(accessors) - 1
+
+    def grid(n):
+        xs, ys = np.meshgrid(np.linspace(-1, 1, n), np.linspace(-1, 1, n))
+        pos = np.stack([xs.ravel(), ys.ravel(), 0.3 * np.sin(3 * xs.ravel()) * np.cos(2 * ys.ravel())], 1).astype(np.float32)
+        uv = np.stack([(xs.ravel() + 1) / 2, (ys.ravel() + 1) / 2], 1).astype(np.float32)
+        idx = []
+        for j in range(n - 1):
+            for i in range(n - 1):
+                a = j * n + i
+                idx += [a, a + 1, a + n, a + 1, a + n + 1, a + n]
+        return pos, uv, np.array(idx, np.uint32)
+
+    prims = []
+    # primitive 0: interleaved position / normal / uv (stride 32), 16-bit indices
+    pos, uv, idx = grid(7)
+    inter = np.zeros((len(pos), 8), np.float32)
+    inter[:, 0:3], inter[:, 3:6], inter[:, 6:8] = pos, rng.normal(size=(len(pos), 3)), uv
+    v = add_view(inter.tobytes(), stride=32)
+    prims.append({"attributes": {"POSITION": add_accessor(v, 5126, "VEC3", len(pos)), "NORMAL": add_accessor(v, 5126, "VEC3", len(pos), 12),
+                                 "TEXCOORD_0": add_accessor(v, 5126, "VEC2", len(pos), 24)},
+                  "indices": add_accessor(add_view(idx.astype(np.uint16).tobytes() + b"\0\0"), 5123, "SCALAR", len(idx)), "material": 0})
+    # primitive 1: packed arrays sharing one view through accessor byteOffsets, 32-bit indices, no uvs, no material
+    pos2, _, idx2 = grid(5)
+    v = add_view(bytes(8) + pos2.tobytes())
+    prims.append({"attributes": {"POSITION": add_accessor(v, 5126, "VEC3", len(pos2), 8)},
+                  "indices": add_accessor(add_view(idx2.tobytes()), 5125, "SCALAR", len(idx2)), "mode": 4})
+    # primitive 2: packed, uvs, material 1, an index count that is not a multiple of three (the last two are dropped)
+    pos3, uv3, idx3 = grid(4)
+    prims.append({"attributes": {"POSITION": add_accessor(add_view(pos3.tobytes()), 5126, "VEC3", len(pos3)),
+                                 "TEXCOORD_0": add_accessor(add_view(uv3.tobytes()), 5126, "VEC2", len(uv3))},
+                  "indices": add_accessor(add_view(np.append(idx3, [0, 1]).astype(np.uint32).tobytes()), 5125, "SCALAR", len(idx3) + 2),
+                  "material": 1})
+    meshes = [{"primitives": [prims[0], prims[1]], "name": "terrain"}, {"primitives": [prims[2]]}]
+
+    def quat():
+        q = rng.normal(size=4)
+        return [float(x) for x in q / np.linalg.norm(q)]
+
+    nodes = [
+        {"name": "root", "children": [1, 2], "translation": [1.5, -0.25, 3.0]},
+        {"name": "arm", "children": [3, 4], "rotation": quat(), "scale": [1.0, 2.0, 0.5], "mesh": 0},
+        {"name": "matrix node", "matrix": _rotated(21), "mesh": 1, "children": [5]},
+        {"name": "leaf a", "mesh": 1, "translation": [0.1, 0.2, 0.3], "rotation": quat(), "scale": [-1.0, 1.0, 1.0]},
+        {"name": "camera holder", "camera": 0, "rotation": quat()},
+        {"name": "leaf b", "mesh": 0, "scale": [0.5, 0.5, 0.5]},
+        {"name": "second root", "mesh": 0, "rotation": quat()},
+        {"name": "not in the scene", "mesh": 1},
+    ]
+    tex_a = (rng.integers(0, 255, (16, 8, 3))).astype(np.uint8)
+    tex_b = (rng.integers(0, 255, (4, 4, 4))).astype(np.uint8)
+    pngs = [_png_bytes(tex_a), _png_bytes(tex_b)]
+    images = []
+    for k, png in enumerate(pngs):
+        if container == "gltf":
+            (tmp_path / f"tex {k}.png").write_bytes(png)
+            images.append({"uri": f"tex%20{k}.png", "name": f"tex{k}"})  # (a percent-encoded file name)
+        elif container == "datauri":
+            images.append({"uri": "data:image/png;base64," + base64.b64encode(png).decode(), "name": f"tex{k}"})
+        else:
+            images.append({"bufferView": add_view(png), "mimeType": "image/png", "name": f"tex{k}"})
+    doc = {"asset": {"version": "2.0"}, "scene": 1, "scenes": [{"nodes": [7]}, {"nodes": [0, 6], "name": "main"}], "nodes": nodes,
+           "cameras": [{"type": "perspective", "perspective": {"yfov": 0.8, "znear": 0.1}}], "meshes": meshes,
+           "materials": [{"pbrMetallicRoughness": {"baseColorTexture": {"index": 1}, "baseColorFactor": [1, 0.5, 0.25, 1],
+                                                   "metallicRoughnessTexture": {"index": 0}}, "name": "textured"},
+                         {"pbrMetallicRoughness": {"metallicFactor": 0.25, "roughnessFactor": 0.6}}, {"name": "all defaults"}],
+           "textures": [{"source": 1}, {"source": 0, "sampler": 0}], "samplers": [{}], "images": images,
+           "accessors": accessors, "bufferViews": views}
+    if container == "gltf":
+        (tmp_path / "scene.bin").write_bytes(bytes(blob))
+        doc["buffers"] = [{"uri": "scene.bin", "byteLength": len(blob)}]
+    elif container == "datauri":
+        doc["buffers"] = [{"uri": "data:application/octet-stream;base64," + base64.b64encode(bytes(blob)).decode(), "byteLength": len(blob)}]
+    else:
+        doc["buffers"] = [{"byteLength": len(blob)}]
+    if container != "glb":
+        path = tmp_path / "scene.gltf"
+        path.write_text(json.dumps(doc))
+        return str(path)
+    js = json.dumps(doc).encode()
+    js += b" " * (-len(js) % 4)
+    while len(blob) % 4:
+        blob.append(0)
+    path = tmp_path / "scene.glb"
+    path.write_bytes(struct.pack("<4sII", b"glTF", 2, 12 + 8 + len(js) + 8 + len(blob)) + struct.pack("<II", len(js), 0x4E4F534A) + js +
+                     struct.pack("<II", len(blob), 0x004E4942) + bytes(blob))
+    return str(path)
+
+
+@needs_ref
+@pytest.mark.parametrize("container", ["gltf", "datauri", "glb"])
+def test_native_gltf_loader_builds_the_reference_loaders_scene(built, tmp_path, container):
+    """Bit for bit what Scene::load_gltf builds through tinygltf + flatten_gltf: geometries (interleaved / offset / 16-bit
+    accessors), parameterized meshes with the default material for a primitive without one, the instances of the flattened
+    hierarchy (T * R * S and matrix nodes composed in float), materials with texture handles, images (RGBA, not flipped,
+    colour spaces set by their use), the generated light."""
+    pytest.importorskip("PIL")
+    path = _gltf_hierarchy(tmp_path, container)
+    ref = _reference_arrays(path)
+    for threads in (0, 1):
+        nat, loaded = _native_arrays(path, threads)
+        _assert_same(nat, ref)
+    assert nat["counts"] == [2, 2, 2, 5, 4, 2, 1] and nat["mesh_sizes"] == [2, 1]
+    assert [cs for _, cs in nat["textures"]] == [1, 0]  # texture 1 -> image 0: base colour (sRGB); texture 0 -> image 1: metallic-roughness
+    assert "generating a default" in loaded.warnings
+
+
+@needs_ref
+def test_native_gltf_loader_on_the_writers_scene(built, tmp_path):
+    """The San-Miguel-like scene of BASELINE configs 3 and 5 as gltf_io writes it (flat node list with matrices, external .bin,
+    PNG files)."""
+    pytest.importorskip("PIL")
+    from chameleonrt_b200.gltf_io import write_gltf
+    from chameleonrt_b200.scenes import san_miguel_like
+
+    scene, _ = san_miguel_like(spp=1, scale=0.03, tex_size=32)
+    path = write_gltf(scene, str(tmp_path / "scene.gltf"))
+    ref = _reference_arrays(path)
+    nat, loaded = _native_arrays(path)
+    _assert_same(nat, ref)
+    print(f"\nglTF, {sum(len(g[2]) // 3 for g in nat['geometries'])} unique triangles: reference loader {ref['seconds'] * 1e3:.1f} ms, "
+          f"native {loaded.timings}")
+
+
+def test_native_gltf_loader_errors(built, tmp_path):
+    import json
+
+    from chameleonrt_b200 import scene_io
+
+    def write(name, doc, raw=None):
+        p = tmp_path / name
+        p.write_bytes(raw if raw is not None else json.dumps(doc).encode())
+        return str(p)
+
+    tri = np.zeros(9, np.float32).tobytes() + np.array([0, 1, 2], np.uint32).tobytes()
+    (tmp_path / "tri.bin").write_bytes(tri)
+    base = {"asset": {"version": "2.0"}, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}], "buffers": [{"uri": "tri.bin", "byteLength": 48}],
+            "bufferViews": [{"buffer": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 12}],
+            "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"},
+                          {"bufferView": 1, "componentType": 5125, "count": 3, "type": "SCALAR"}],
+            "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1}]}]}
+    loaded = scene_io.load_gltf(write("ok.gltf", base))
+    assert loaded.c_scene.contents.num_instances == 1 and loaded.c_scene.contents.meshes[0].geometries[0].num_tris == 1
+
+    def broken(**changes):
+        doc = json.loads(json.dumps(base))
+        for k, v in changes.items():
+            doc[k] = v
+        return doc
+
+    with pytest.raises(RuntimeError, match="Invalid magic"):
+        scene_io.load_scene(write("bad.glb", None, raw=b"not a glb file at all...."))
+    with pytest.raises(RuntimeError, match="Too short"):
+        scene_io.load_scene(write("short.glb", None, raw=b"glTF"))
+    with pytest.raises(RuntimeError, match="malformed JSON"):
+        scene_io.load_gltf(write("bad.gltf", None, raw=b"{\"asset\": "))
+    with pytest.raises(RuntimeError, match="cannot open"):
+        scene_io.load_gltf(write("nobin.gltf", broken(buffers=[{"uri": "missing.bin", "byteLength": 48}])))
+    with pytest.raises(RuntimeError, match="byteLength says 480"):
+        scene_io.load_gltf(write("shortbin.gltf", broken(buffers=[{"uri": "tri.bin", "byteLength": 480}])))
+    with pytest.raises(RuntimeError, match="past the end of its buffer"):
+        scene_io.load_gltf(write("view.gltf", broken(bufferViews=[{"buffer": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 40, "byteLength": 12}])))
+    with pytest.raises(RuntimeError, match="past the end of its buffer"):
+        scene_io.load_gltf(write("count.gltf", broken(accessors=[{"bufferView": 0, "componentType": 5126, "count": 30, "type": "VEC3"}, base["accessors"][1]])))
+    with pytest.raises(RuntimeError, match="POSITION is not FLOAT VEC3"):
+        scene_io.load_gltf(write("pos.gltf", broken(accessors=[{"bufferView": 0, "componentType": 5123, "count": 3, "type": "VEC3"}, base["accessors"][1]])))
+    with pytest.raises(RuntimeError, match="Unsupported index component type"):
+        scene_io.load_gltf(write("idx.gltf", broken(accessors=[base["accessors"][0], {"bufferView": 1, "componentType": 5121, "count": 3, "type": "SCALAR"}])))
+    with pytest.raises(RuntimeError, match="Only triangles are supported"):
+        scene_io.load_gltf(write("mode.gltf", broken(meshes=[{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1, "mode": 1}]}])))
+    with pytest.raises(RuntimeError, match="has no indices"):
+        scene_io.load_gltf(write("noidx.gltf", broken(meshes=[{"primitives": [{"attributes": {"POSITION": 0}}]}])))
+    with pytest.raises(RuntimeError, match="is sparse"):
+        scene_io.load_gltf(write("sparse.gltf", broken(accessors=[dict(base["accessors"][0], sparse={"count": 1}), base["accessors"][1]])))
+    with pytest.raises(RuntimeError, match="instances mesh 4 of 1"):
+        scene_io.load_gltf(write("mesh.gltf", broken(nodes=[{"mesh": 4}])))
+    with pytest.raises(RuntimeError, match="cyclic or too deep"):
+        scene_io.load_gltf(write("cycle.gltf", broken(nodes=[{"children": [0], "mesh": 0}])))
+    with pytest.raises(RuntimeError, match="not a PNG file"):
+        scene_io.load_gltf(write("jpeg.gltf", broken(images=[{"uri": "data:image/jpeg;base64,/9j/4AAQSkZJRgABAQAAAQABAAD/2wBDAAgGBgcGBQgHBwcJCQgKDBQNDAsLDBkSEw8UHRofHh0a"}])))
+    with pytest.raises(RuntimeError, match="exactly one of"):
+        scene_io.load_gltf(write("img.gltf", broken(images=[{"name": "nothing"}])))
+
+
+def test_native_gltf_loader_round_trip_and_oracle_frame(built, tmp_path):
+    """Without the reference library (the GPU box): the scene written by gltf_io comes back as the same scene (write_gltf /
+    Scene::load_gltf are inverse to each other for it, tests/test_reference_embree.py) — same frame through the CPU oracle."""
+    pytest.importorskip("PIL")
+    from chameleonrt_b200 import scene_io
+    from chameleonrt_b200.gltf_io import write_gltf
+    from chameleonrt_b200.scenes import san_miguel_like
+    from helpers import camera_for
+    from oracle import OracleBackend
+
+    scene, cam = san_miguel_like(spp=1, scale=0.02, tex_size=32)
+    loaded = scene_io.load_scene(write_gltf(scene, str(tmp_path / "scene.gltf")))
+    got = loaded.to_scene(spp=1)
+    assert len(got.instances) == len(scene.instances) and len(got.materials) == len(scene.materials)
+    c = camera_for(cam)
+    frames = []
+    for s in (scene, got):
+        o = OracleBackend(max_depth=5)
+        o.initialize(48, 32)
+        o.set_scene(s)
+        o.render(c.eye(), c.dir(), c.up(), cam["fov_y"], True, True)
+        frames.append(o.read_accum())
+    assert np.array_equal(frames[0].view(np.uint32), frames[1].view(np.uint32))

@@ -394,6 +394,33 @@ def test_natively_loaded_crts_renders_the_same_frame(mods, tmp_path, size=(48, 3
     assert frames[0][1] == frames[1][1] and np.array_equal(frames[0][0].view(np.uint32), frames[1][0].view(np.uint32))
 
 
+def test_natively_loaded_gltf_renders_the_same_frame(mods, tmp_path, size=(48, 32), scale=0.02):
+    """.gltf + .bin + PNG (the scene class of BASELINE configs 3 and 5: instances with non-identity transforms, textures) ->
+    crtio_load_gltf -> crtc_set_scene -> the frame of the scene the file was written from, bit for bit."""
+    pytest.importorskip("PIL")
+    from chameleonrt_b200 import scene_io
+    from chameleonrt_b200.gltf_io import write_gltf
+    from chameleonrt_b200.scenes import san_miguel_like
+
+    RenderCUDA = mods[0]
+    scene, cam = san_miguel_like(spp=2, scale=scale, tex_size=32)
+    c = camera_for(cam)
+    args = (c.eye(), c.dir(), c.up(), cam["fov_y"])
+    loaded = scene_io.load_scene(write_gltf(scene, str(tmp_path / "scene.gltf")))
+    frames = []
+    for native in (False, True):
+        r = RenderCUDA(0)
+        r.initialize(*size)
+        if native:
+            r.set_scene_c(loaded.c_scene, samples_per_pixel=2)
+        else:
+            r.set_scene(scene)
+        for f in range(2):
+            st = r.render(*args, f == 0, True)
+        frames.append((r.read_accum(), st.num_rays))
+    assert frames[0][1] == frames[1][1] and np.array_equal(frames[0][0].view(np.uint32), frames[1][0].view(np.uint32))
+
+
 def test_natively_loaded_obj_renders_the_same_frame(mods, tmp_path, size=(48, 32), detail=0.25):
     """The scene-load row end to end: OBJ + MTL + PNG written by obj_io -> crtio_load_obj (native, parallel) ->
     crtc_set_scene on the native crt_scene_t (RenderCUDA.set_scene_c) -> the frame the Python scene model renders, bit for

@@ -351,3 +351,10 @@ def test_natively_loaded_crts_renders_the_same_frame_on_the_gpu(mods, tmp_path):
     from test_simt_renderer import test_natively_loaded_crts_renders_the_same_frame
 
     test_natively_loaded_crts_renders_the_same_frame(mods, tmp_path, size=(320, 180))
+
+
+def test_natively_loaded_gltf_renders_the_same_frame_on_the_gpu(mods, tmp_path):
+    """crtio_load_gltf -> crtc_set_scene -> frame: tests/test_simt_renderer.py's function on the B200, at a larger size."""
+    from test_simt_renderer import test_natively_loaded_gltf_renders_the_same_frame
+
+    test_natively_loaded_gltf_renders_the_same_frame(mods, tmp_path, size=(320, 180), scale=0.05)
