@@ -1,0 +1,836 @@
+// jpeg_decode.h — JPEG textures for the native scene loader (scene_io.cpp), host code only.
+//
+// The reference decodes textures with stb_image (util/stb_image.h, pulled in by util/util.cpp:17): stbi_load / stbi_load_from_memory
+// with four requested components. For a valid JPEG stream the entropy decoding is fixed by the standard (ITU T.81): every
+// conforming decoder recovers the same quantised coefficients, so that part is written here from the standard (sequential
+// and progressive Huffman modes, restart intervals, 8-bit samples, 8- and 16-bit quantisation tables). What is NOT fixed by
+// the standard — and what decides the bytes of the texture — is restated from stb_image, with its integer arithmetic:
+//   * the inverse DCT               stbi__idct_block            (stb_image.h:2271-2332; jidctint-style, 12-bit constants,
+//                                                                 columns kept at 2 extra bits, +128 level shift folded in)
+//   * chroma upsampling             stbi__resample_row_v_2 / _h_2 / _hv_2 / _generic, driven as load_jpeg_image drives them
+//                                   (:3240-3300, :3421-3432, :3640-3700: "near" and "far" rows, 3:1 weights, nearest for
+//                                   other factors)
+//   * YCbCr -> RGB                  stbi__YCbCr_to_RGB_row      (:3435-3459: 20-bit fixed point, the Cb term of green
+//                                                                 masked to 16 bits)
+//   * which streams are RGB already load_jpeg_image's is_rgb    (:3655: component ids 'R','G','B', or an Adobe marker with
+//                                                                 transform 0 and no JFIF marker)
+// stb_image's SSE2 kernels produce the same bytes as these scalar ones (its own comments, :2334, :3433), so the build of the
+// reference does not matter. Grey and three-component streams are read; four-component (CMYK / YCCK) streams, 12-bit
+// samples and arithmetic coding are errors (the latter two are errors in stb_image as well).
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace crt_jpeg {
+
+// ---- stb_image's numeric kernels ----
+constexpr int f2f(float x)
+{
+    return (int)(x * 4096 + 0.5);
+}
+inline uint8_t clamp_u8(int x)
+{
+    return (unsigned)x > 255u ? (x < 0 ? 0 : 255) : (uint8_t)x;
+}
+
+// one pass of the separable transform over eight values; `even` / `odd` come back still scaled by 4096
+struct Idct1d {
+    int x0, x1, x2, x3, t0, t1, t2, t3;
+    Idct1d(int s0, int s1, int s2, int s3, int s4, int s5, int s6, int s7)
+    {
+        int p1, p2, p3, p4, p5;
+        p2 = s2;
+        p3 = s6;
+        p1 = (p2 + p3) * f2f(0.5411961f);
+        t2 = p1 + p3 * f2f(-1.847759065f);
+        t3 = p1 + p2 * f2f(0.765366865f);
+        p2 = s0;
+        p3 = s4;
+        t0 = (p2 + p3) * 4096;
+        t1 = (p2 - p3) * 4096;
+        x0 = t0 + t3;
+        x3 = t0 - t3;
+        x1 = t1 + t2;
+        x2 = t1 - t2;
+        t0 = s7;
+        t1 = s5;
+        t2 = s3;
+        t3 = s1;
+        p3 = t0 + t2;
+        p4 = t1 + t3;
+        p1 = t0 + t3;
+        p2 = t1 + t2;
+        p5 = (p3 + p4) * f2f(1.175875602f);
+        t0 = t0 * f2f(0.298631336f);
+        t1 = t1 * f2f(2.053119869f);
+        t2 = t2 * f2f(3.072711026f);
+        t3 = t3 * f2f(1.501321110f);
+        p1 = p5 + p1 * f2f(-0.899976223f);
+        p2 = p5 + p2 * f2f(-2.562915447f);
+        p3 = p3 * f2f(-1.961570560f);
+        p4 = p4 * f2f(-0.390180644f);
+        t3 += p1 + p4;
+        t2 += p2 + p3;
+        t1 += p2 + p4;
+        t0 += p1 + p3;
+    }
+};
+
+inline void idct_block(uint8_t *out, size_t out_stride, const short d[64])
+{
+    int val[64];
+    for (int i = 0; i < 8; ++i) {  // columns
+        int *v = val + i;
+        const short *c = d + i;
+        if (c[8] == 0 && c[16] == 0 && c[24] == 0 && c[32] == 0 && c[40] == 0 && c[48] == 0 && c[56] == 0) {
+            const int dcterm = c[0] * 4;
+            v[0] = v[8] = v[16] = v[24] = v[32] = v[40] = v[48] = v[56] = dcterm;
+        } else {
+            Idct1d k(c[0], c[8], c[16], c[24], c[32], c[40], c[48], c[56]);
+            k.x0 += 512, k.x1 += 512, k.x2 += 512, k.x3 += 512;  // the constants scaled by 1 << 12: back down, keeping two bits
+            v[0] = (k.x0 + k.t3) >> 10;
+            v[56] = (k.x0 - k.t3) >> 10;
+            v[8] = (k.x1 + k.t2) >> 10;
+            v[48] = (k.x1 - k.t2) >> 10;
+            v[16] = (k.x2 + k.t1) >> 10;
+            v[40] = (k.x2 - k.t1) >> 10;
+            v[24] = (k.x3 + k.t0) >> 10;
+            v[32] = (k.x3 - k.t0) >> 10;
+        }
+    }
+    for (int i = 0; i < 8; ++i) {  // rows: 17 bits to remove, rounded, with the +128 level shift added before the shift
+        const int *v = val + 8 * i;
+        uint8_t *o = out + out_stride * i;
+        Idct1d k(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+        const int bias = 65536 + (128 << 17);
+        k.x0 += bias, k.x1 += bias, k.x2 += bias, k.x3 += bias;
+        o[0] = clamp_u8((k.x0 + k.t3) >> 17);
+        o[7] = clamp_u8((k.x0 - k.t3) >> 17);
+        o[1] = clamp_u8((k.x1 + k.t2) >> 17);
+        o[6] = clamp_u8((k.x1 - k.t2) >> 17);
+        o[2] = clamp_u8((k.x2 + k.t1) >> 17);
+        o[5] = clamp_u8((k.x2 - k.t1) >> 17);
+        o[3] = clamp_u8((k.x3 + k.t0) >> 17);
+        o[4] = clamp_u8((k.x3 - k.t0) >> 17);
+    }
+}
+
+// one output row of a component from its two nearest stored rows; returns where the row is (in `out` or `near` itself)
+inline const uint8_t *resample_row(uint8_t *out, const uint8_t *near, const uint8_t *far, int w, int hs, int vs)
+{
+    if (hs == 1 && vs == 1) {
+        return near;
+    }
+    if (hs == 1 && vs == 2) {
+        for (int i = 0; i < w; ++i) {
+            out[i] = (uint8_t)((3 * near[i] + far[i] + 2) >> 2);
+        }
+        return out;
+    }
+    if (hs == 2 && vs == 1) {
+        if (w == 1) {
+            out[0] = out[1] = near[0];
+            return out;
+        }
+        out[0] = near[0];
+        out[1] = (uint8_t)((near[0] * 3 + near[1] + 2) >> 2);
+        int i;
+        for (i = 1; i < w - 1; ++i) {
+            const int n = 3 * near[i] + 2;
+            out[i * 2 + 0] = (uint8_t)((n + near[i - 1]) >> 2);
+            out[i * 2 + 1] = (uint8_t)((n + near[i + 1]) >> 2);
+        }
+        out[i * 2 + 0] = (uint8_t)((near[w - 2] * 3 + near[w - 1] + 2) >> 2);
+        out[i * 2 + 1] = near[w - 1];
+        return out;
+    }
+    if (hs == 2 && vs == 2) {
+        if (w == 1) {
+            out[0] = out[1] = (uint8_t)((3 * near[0] + far[0] + 2) >> 2);
+            return out;
+        }
+        int t1 = 3 * near[0] + far[0];
+        out[0] = (uint8_t)((t1 + 2) >> 2);
+        for (int i = 1; i < w; ++i) {
+            const int t0 = t1;
+            t1 = 3 * near[i] + far[i];
+            out[i * 2 - 1] = (uint8_t)((3 * t0 + t1 + 8) >> 4);
+            out[i * 2] = (uint8_t)((3 * t1 + t0 + 8) >> 4);
+        }
+        out[w * 2 - 1] = (uint8_t)((t1 + 2) >> 2);
+        return out;
+    }
+    for (int i = 0; i < w; ++i) {  // any other factor: nearest
+        for (int j = 0; j < hs; ++j) {
+            out[i * hs + j] = near[i];
+        }
+    }
+    return out;
+}
+
+constexpr int float2fixed(float x)
+{
+    return ((int)(x * 4096.0f + 0.5f)) << 8;
+}
+inline void ycbcr_to_rgba_row(uint8_t *out, const uint8_t *y, const uint8_t *pcb, const uint8_t *pcr, int count)
+{
+    for (int i = 0; i < count; ++i) {
+        const int y_fixed = (y[i] << 20) + (1 << 19);
+        const int cr = pcr[i] - 128, cb = pcb[i] - 128;
+        int r = y_fixed + cr * float2fixed(1.40200f);
+        int g = (int)((unsigned)(y_fixed + (cr * -float2fixed(0.71414f))) + ((unsigned)(cb * -float2fixed(0.34414f)) & 0xffff0000u));
+        int b = y_fixed + cb * float2fixed(1.77200f);
+        r >>= 20;
+        g >>= 20;
+        b >>= 20;
+        out[4 * i] = clamp_u8(r);
+        out[4 * i + 1] = clamp_u8(g);
+        out[4 * i + 2] = clamp_u8(b);
+        out[4 * i + 3] = 255;
+    }
+}
+
+// ---- the stream (ITU T.81) ----
+struct HuffmanTable {
+    bool defined = false;
+    uint8_t values[256];
+    int mincode[17], maxcode[18], valptr[17];  // per code length (annex F.2.2.3)
+    uint16_t fast[512];                        // 9 leading bits -> (length << 8) | symbol, 0 = longer code
+
+    void build(const uint8_t counts[16], const uint8_t *symbols, int n)
+    {
+        std::memcpy(values, symbols, (size_t)n);
+        std::memset(fast, 0, sizeof(fast));
+        int code = 0, k = 0;
+        for (int len = 1; len <= 16; ++len) {
+            valptr[len] = k;
+            mincode[len] = code;
+            for (int i = 0; i < counts[len - 1]; ++i, ++k, ++code) {
+                if (len <= 9) {
+                    const int first = code << (9 - len);
+                    for (int f = 0; f < (1 << (9 - len)); ++f) {
+                        fast[first + f] = (uint16_t)((len << 8) | values[k]);
+                    }
+                }
+            }
+            maxcode[len] = counts[len - 1] ? code - 1 : -1;
+            if (code > (1 << len)) {
+                throw std::runtime_error("bad code lengths");
+            }
+            code <<= 1;
+        }
+        maxcode[17] = 0x7fffffff;
+        defined = true;
+    }
+};
+
+class Decoder {
+public:
+    Decoder(const uint8_t *data, size_t size) : p(data), end(data + size) {}
+
+    // -> RGBA, `flip`: rows bottom-up (stbi_set_flip_vertically_on_load)
+    void decode(std::vector<uint8_t> &out, int &width, int &height, bool flip)
+    {
+        if (next_marker() != 0xD8) {
+            throw std::runtime_error("no SOI");
+        }
+        for (;;) {
+            const int m = next_marker();
+            if (m == 0xD9) {
+                break;
+            }
+            if (m == 0xC0 || m == 0xC1 || m == 0xC2) {
+                if (frame_seen) {
+                    throw std::runtime_error("second frame header");
+                }
+                frame_header(m == 0xC2);
+            } else if (m == 0xDA) {
+                if (!frame_seen) {
+                    throw std::runtime_error("scan before the frame header");
+                }
+                scan();
+            } else if (m == 0xDC) {  // DNL
+                const int len = get16(), lines = get16();
+                if (len != 4 || lines != img_y) {
+                    throw std::runtime_error("bad DNL");
+                }
+            } else if (m < 0) {
+                throw std::runtime_error("expected marker (the data ends without an EOI)");  // stb_image fails here as well
+            } else {
+                table_or_misc(m);
+            }
+        }
+        if (!frame_seen || !scans) {
+            throw std::runtime_error("no image data");
+        }
+        if (progressive) {
+            for (Component &c : comps) {
+                const int w = (c.x + 7) >> 3, h = (c.y + 7) >> 3;
+                for (int j = 0; j < h; ++j) {
+                    for (int i = 0; i < w; ++i) {
+                        short *block = &c.coeff[64 * ((size_t)i + (size_t)j * c.blocks_w)];
+                        for (int k = 0; k < 64; ++k) {
+                            block[k] = (short)(block[k] * quant[c.tq][k]);
+                        }
+                        idct_block(&c.data[(size_t)c.w2 * j * 8 + i * 8], (size_t)c.w2, block);
+                    }
+                }
+            }
+        }
+        assemble(out, flip);
+        width = img_x;
+        height = img_y;
+    }
+
+private:
+    struct Component {
+        int id = 0, h = 1, v = 1, tq = 0, hd = 0, ha = 0, dc_pred = 0;
+        int x = 0, y = 0, w2 = 0, h2 = 0, blocks_w = 0;
+        std::vector<uint8_t> data;
+        std::vector<short> coeff;  // progressive only
+    };
+    const uint8_t *p, *end;
+    bool frame_seen = false, progressive = false, jfif = false;
+    int adobe_transform = -1, scans = 0;
+    int img_x = 0, img_y = 0, h_max = 1, v_max = 1, mcu_x = 0, mcu_y = 0, restart_interval = 0;
+    std::vector<Component> comps;
+    uint16_t quant[4][64] = {};
+    HuffmanTable dc_tables[4], ac_tables[4];
+    // entropy-coded segment
+    uint32_t bit_buffer = 0;
+    int bit_count = 0;
+    int pending_marker = -1;  // a marker met while filling the bit buffer
+    int eob_run = 0;
+
+    int get8()
+    {
+        return p < end ? *p++ : 0;
+    }
+    int get16()
+    {
+        const int hi = get8();
+        return (hi << 8) | get8();
+    }
+    // the next marker code; -1 at the end of the data. Bytes that are no marker are skipped (padding, stray data)
+    int next_marker()
+    {
+        if (pending_marker >= 0) {
+            const int m = pending_marker;
+            pending_marker = -1;
+            return m;
+        }
+        while (p < end) {
+            if (*p++ != 0xFF) {
+                continue;
+            }
+            while (p < end && *p == 0xFF) {
+                ++p;
+            }
+            if (p < end && *p != 0) {
+                return *p++;
+            }
+        }
+        return -1;
+    }
+    static const uint8_t *zigzag()
+    {
+        static const uint8_t z[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                      41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                      30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+        return z;
+    }
+
+    void table_or_misc(int m)
+    {
+        if (m == 0xDD) {  // DRI
+            if (get16() != 4) {
+                throw std::runtime_error("bad DRI");
+            }
+            restart_interval = get16();
+            return;
+        }
+        if (m == 0xDB) {  // DQT
+            int len = get16() - 2;
+            while (len > 0) {
+                const int q = get8(), precision = q >> 4, t = q & 15;
+                if (precision > 1 || t > 3) {
+                    throw std::runtime_error("bad DQT");
+                }
+                for (int i = 0; i < 64; ++i) {
+                    quant[t][zigzag()[i]] = (uint16_t)(precision ? get16() : get8());
+                }
+                len -= precision ? 129 : 65;
+            }
+            if (len != 0) {
+                throw std::runtime_error("bad DQT length");
+            }
+            return;
+        }
+        if (m == 0xC4) {  // DHT
+            int len = get16() - 2;
+            while (len > 0) {
+                const int q = get8(), tc = q >> 4, th = q & 15;
+                if (tc > 1 || th > 3) {
+                    throw std::runtime_error("bad DHT");
+                }
+                uint8_t counts[16], symbols[256];
+                int n = 0;
+                for (int i = 0; i < 16; ++i) {
+                    counts[i] = (uint8_t)get8();
+                    n += counts[i];
+                }
+                if (n > 256) {
+                    throw std::runtime_error("bad DHT");
+                }
+                for (int i = 0; i < n; ++i) {
+                    symbols[i] = (uint8_t)get8();
+                }
+                (tc ? ac_tables : dc_tables)[th].build(counts, symbols, n);
+                len -= 17 + n;
+            }
+            if (len != 0) {
+                throw std::runtime_error("bad DHT length");
+            }
+            return;
+        }
+        if ((m >= 0xE0 && m <= 0xEF) || m == 0xFE) {  // APPn, COM
+            int len = get16();
+            if (len < 2) {
+                throw std::runtime_error("bad segment length");
+            }
+            len -= 2;
+            if (m == 0xE0 && len >= 5) {
+                jfif = jfif || (end - p >= 5 && std::memcmp(p, "JFIF\0", 5) == 0);
+            } else if (m == 0xEE && len >= 12 && end - p >= 12 && std::memcmp(p, "Adobe\0", 6) == 0) {
+                adobe_transform = p[11];
+            }
+            p = (size_t)(end - p) < (size_t)len ? end : p + len;
+            return;
+        }
+        if (m == 0xC3 || (m >= 0xC5 && m <= 0xCF && m != 0xC8 && m != 0xCC)) {
+            throw std::runtime_error("lossless, hierarchical or arithmetic-coded JPEG");
+        }
+        throw std::runtime_error("unknown marker");
+    }
+
+    void frame_header(bool is_progressive)
+    {
+        progressive = is_progressive;
+        const int len = get16(), precision = get8();
+        img_y = get16();
+        img_x = get16();
+        const int n = get8();
+        if (precision != 8) {
+            throw std::runtime_error("only 8-bit samples");
+        }
+        if (img_x == 0 || img_y == 0) {
+            throw std::runtime_error("no image size in the frame header");
+        }
+        if (n == 4) {
+            throw std::runtime_error("four-component (CMYK) JPEG");
+        }
+        if ((n != 1 && n != 3) || len != 8 + 3 * n) {
+            throw std::runtime_error("bad frame header");
+        }
+        if ((uint64_t)img_x * (uint64_t)img_y > ((uint64_t)1 << 28)) {
+            throw std::runtime_error("image too large");
+        }
+        comps.resize((size_t)n);
+        for (Component &c : comps) {
+            c.id = get8();
+            const int q = get8();
+            c.h = q >> 4;
+            c.v = q & 15;
+            c.tq = get8();
+            if (c.h < 1 || c.h > 4 || c.v < 1 || c.v > 4 || c.tq > 3) {
+                throw std::runtime_error("bad component");
+            }
+            h_max = std::max(h_max, c.h);
+            v_max = std::max(v_max, c.v);
+        }
+        mcu_x = (img_x + h_max * 8 - 1) / (h_max * 8);
+        mcu_y = (img_y + v_max * 8 - 1) / (v_max * 8);
+        for (Component &c : comps) {
+            c.x = (img_x * c.h + h_max - 1) / h_max;
+            c.y = (img_y * c.v + v_max - 1) / v_max;
+            c.w2 = mcu_x * c.h * 8;
+            c.h2 = mcu_y * c.v * 8;
+            c.blocks_w = c.w2 / 8;
+            c.data.assign((size_t)c.w2 * c.h2, 0);
+            if (progressive) {
+                c.coeff.assign((size_t)c.w2 * c.h2, 0);
+            }
+        }
+        frame_seen = true;
+    }
+
+    // ---- bits ----
+    void fill()
+    {
+        while (bit_count <= 24) {
+            uint32_t b = 0;
+            if (pending_marker < 0 && p < end) {
+                b = *p++;
+                if (b == 0xFF) {
+                    int c = get8();
+                    while (c == 0xFF) {
+                        c = get8();
+                    }
+                    if (c != 0) {  // a marker ends the entropy-coded data; zeros from here on
+                        pending_marker = c;
+                        b = 0;
+                    }
+                }
+            }
+            bit_buffer |= b << (24 - bit_count);
+            bit_count += 8;
+        }
+    }
+    int get_bits(int n)
+    {
+        if (n == 0) {
+            return 0;
+        }
+        if (bit_count < n) {
+            fill();
+        }
+        const int v = (int)(bit_buffer >> (32 - n));
+        bit_buffer <<= n;
+        bit_count -= n;
+        return v;
+    }
+    int receive_extend(int n)  // F.2.2.1
+    {
+        if (n == 0) {
+            return 0;
+        }
+        const int v = get_bits(n);
+        return v < (1 << (n - 1)) ? v - (1 << n) + 1 : v;
+    }
+    int huffman(const HuffmanTable &t)
+    {
+        if (bit_count < 16) {
+            fill();
+        }
+        const uint16_t f = t.fast[bit_buffer >> 23];
+        if (f) {
+            const int len = f >> 8;
+            bit_buffer <<= len;
+            bit_count -= len;
+            return f & 255;
+        }
+        int code = (int)(bit_buffer >> 22), len = 10;  // codes of 10 to 16 bits
+        for (; len <= 16; ++len, code = (int)(bit_buffer >> (32 - len))) {
+            if (t.maxcode[len] >= 0 && code <= t.maxcode[len] && code >= t.mincode[len]) {
+                bit_buffer <<= len;
+                bit_count -= len;
+                return t.values[t.valptr[len] + code - t.mincode[len]];
+            }
+        }
+        throw std::runtime_error("bad huffman code");
+    }
+    void restart()
+    {
+        bit_buffer = 0;
+        bit_count = 0;
+        eob_run = 0;
+        for (Component &c : comps) {
+            c.dc_pred = 0;
+        }
+    }
+
+    // ---- blocks ----
+    void sequential_block(Component &c, short block[64])
+    {
+        std::memset(block, 0, 64 * sizeof(short));
+        const int t = huffman(dc_tables[c.hd]);
+        if (t > 15) {
+            throw std::runtime_error("bad DC code");
+        }
+        c.dc_pred += receive_extend(t);
+        block[0] = (short)(c.dc_pred * quant[c.tq][0]);
+        const HuffmanTable &ac = ac_tables[c.ha];
+        for (int k = 1; k < 64;) {
+            const int rs = huffman(ac), r = rs >> 4, s = rs & 15;
+            if (s == 0) {
+                if (rs != 0xF0) {
+                    break;
+                }
+                k += 16;
+                continue;
+            }
+            k += r;
+            if (k > 63) {
+                throw std::runtime_error("coefficient index past the block");
+            }
+            const int z = zigzag()[k++];
+            block[z] = (short)(receive_extend(s) * quant[c.tq][z]);
+        }
+    }
+    void progressive_dc(Component &c, short block[64], int succ_high, int succ_low)
+    {
+        if (succ_high == 0) {
+            const int t = huffman(dc_tables[c.hd]);
+            if (t > 15) {
+                throw std::runtime_error("bad DC code");
+            }
+            c.dc_pred += receive_extend(t);
+            block[0] = (short)(c.dc_pred * (1 << succ_low));
+        } else if (get_bits(1)) {
+            block[0] = (short)(block[0] + (1 << succ_low));
+        }
+    }
+    void progressive_ac(Component &c, short block[64], int spec_start, int spec_end, int succ_high, int succ_low)
+    {
+        const HuffmanTable &ac = ac_tables[c.ha];
+        if (succ_high == 0) {  // first pass over this band (G.1.2.2)
+            if (eob_run) {
+                --eob_run;
+                return;
+            }
+            for (int k = spec_start; k <= spec_end;) {
+                const int rs = huffman(ac), r = rs >> 4, s = rs & 15;
+                if (s == 0) {
+                    if (r < 15) {
+                        eob_run = (1 << r) - 1 + get_bits(r);
+                        break;
+                    }
+                    k += 16;
+                    continue;
+                }
+                k += r;
+                if (k > 63) {
+                    throw std::runtime_error("coefficient index past the block");
+                }
+                block[zigzag()[k++]] = (short)(receive_extend(s) * (1 << succ_low));
+            }
+            return;
+        }
+        // refinement (G.1.2.3): one more bit for every coefficient that is already non-zero, new +-1 coefficients in between
+        const short bit = (short)(1 << succ_low);
+        const auto refine = [&](short &v) {
+            if (get_bits(1) && (v & bit) == 0) {
+                v = (short)(v > 0 ? v + bit : v - bit);
+            }
+        };
+        if (eob_run) {
+            --eob_run;
+            for (int k = spec_start; k <= spec_end; ++k) {
+                short &v = block[zigzag()[k]];
+                if (v != 0) {
+                    refine(v);
+                }
+            }
+            return;
+        }
+        for (int k = spec_start; k <= spec_end;) {
+            const int rs = huffman(ac);
+            int r = rs >> 4, s = rs & 15;
+            short value = 0;
+            if (s == 0) {
+                if (r < 15) {
+                    eob_run = (1 << r) - 1 + get_bits(r);
+                    r = 64;  // to the end of the band: only refinement bits follow for this block
+                }
+            } else {
+                if (s != 1) {
+                    throw std::runtime_error("bad refinement code");
+                }
+                value = get_bits(1) ? bit : (short)-bit;
+            }
+            while (k <= spec_end) {
+                short &v = block[zigzag()[k++]];
+                if (v != 0) {
+                    refine(v);
+                } else {
+                    if (r == 0) {
+                        v = value;
+                        break;
+                    }
+                    --r;
+                }
+            }
+        }
+    }
+
+    void scan()
+    {
+        const int len = get16(), n = get8();
+        if (n < 1 || n > (int)comps.size() || len != 6 + 2 * n) {
+            throw std::runtime_error("bad scan header");
+        }
+        Component *order[4];
+        for (int i = 0; i < n; ++i) {
+            const int id = get8(), q = get8();
+            order[i] = nullptr;
+            for (Component &c : comps) {
+                if (c.id == id) {
+                    order[i] = &c;
+                }
+            }
+            if (!order[i] || (q >> 4) > 3 || (q & 15) > 3) {
+                throw std::runtime_error("bad scan component");
+            }
+            order[i]->hd = q >> 4;
+            order[i]->ha = q & 15;
+        }
+        int spec_start = get8(), spec_end = get8();
+        const int aa = get8(), succ_high = aa >> 4, succ_low = aa & 15;
+        if (progressive) {
+            if (spec_start > 63 || spec_end > 63 || spec_start > spec_end || succ_high > 13 || succ_low > 13 ||
+                (spec_start == 0 && spec_end != 0) || (spec_start != 0 && n != 1)) {
+                throw std::runtime_error("bad progressive scan");
+            }
+        } else {
+            if (spec_start != 0 || succ_high != 0 || succ_low != 0) {
+                throw std::runtime_error("bad scan parameters");
+            }
+            spec_end = 63;
+        }
+        for (int i = 0; i < n; ++i) {
+            const bool need_dc = spec_start == 0 && succ_high == 0, need_ac = !progressive || spec_start != 0;
+            if ((need_dc && !dc_tables[order[i]->hd].defined) || (need_ac && !ac_tables[order[i]->ha].defined)) {
+                throw std::runtime_error("scan without its huffman table");
+            }
+        }
+        ++scans;
+        restart();
+        pending_marker = -1;
+        int todo = restart_interval ? restart_interval : 0x7fffffff;
+        // after every restart interval: the next marker must be RSTn; if it is not, the scan ends with what it has (stb_image)
+        const auto interval_done = [&]() {
+            if (--todo > 0) {
+                return false;
+            }
+            if (bit_count < 24) {
+                fill();
+            }
+            if (pending_marker < 0xD0 || pending_marker > 0xD7) {
+                return true;
+            }
+            pending_marker = -1;
+            restart();
+            todo = restart_interval ? restart_interval : 0x7fffffff;
+            return false;
+        };
+        short block[64];
+        const auto one_block = [&](Component &c, int bx, int by) {
+            if (!progressive) {
+                sequential_block(c, block);
+                idct_block(&c.data[(size_t)c.w2 * by * 8 + bx * 8], (size_t)c.w2, block);
+                return;
+            }
+            short *coeff = &c.coeff[64 * ((size_t)bx + (size_t)by * c.blocks_w)];
+            if (spec_start == 0) {
+                progressive_dc(c, coeff, succ_high, succ_low);
+            } else {
+                progressive_ac(c, coeff, spec_start, spec_end, succ_high, succ_low);
+            }
+        };
+        if (n == 1) {  // not interleaved: the component's own blocks, row by row
+            Component &c = *order[0];
+            const int w = (c.x + 7) >> 3, h = (c.y + 7) >> 3;
+            for (int j = 0; j < h; ++j) {
+                for (int i = 0; i < w; ++i) {
+                    one_block(c, i, j);
+                    if (interval_done()) {
+                        return;
+                    }
+                }
+            }
+            return;
+        }
+        for (int j = 0; j < mcu_y; ++j) {
+            for (int i = 0; i < mcu_x; ++i) {
+                for (int k = 0; k < n; ++k) {
+                    Component &c = *order[k];
+                    for (int y = 0; y < c.v; ++y) {
+                        for (int x = 0; x < c.h; ++x) {
+                            one_block(c, i * c.h + x, j * c.v + y);
+                        }
+                    }
+                }
+                if (interval_done()) {
+                    return;
+                }
+            }
+        }
+    }
+
+    // load_jpeg_image (stb_image.h:3640-3700) for four requested components
+    void assemble(std::vector<uint8_t> &out, bool flip)
+    {
+        const size_t n = comps.size();
+        int rgb_ids = 0;
+        for (size_t k = 0; k < n; ++k) {
+            rgb_ids += (n == 3 && comps[k].id == "RGB"[k]) ? 1 : 0;
+        }
+        const bool is_rgb = n == 3 && (rgb_ids == 3 || (adobe_transform == 0 && !jfif));
+        struct Resample {
+            int hs, vs, ystep, w_lores, ypos;
+            const uint8_t *line0, *line1;
+            std::vector<uint8_t> buffer;
+        };
+        std::vector<Resample> res(n);
+        for (size_t k = 0; k < n; ++k) {
+            Resample &r = res[k];
+            r.hs = h_max / comps[k].h;
+            r.vs = v_max / comps[k].v;
+            r.ystep = r.vs >> 1;
+            r.w_lores = (img_x + r.hs - 1) / r.hs;
+            r.ypos = 0;
+            r.line0 = r.line1 = comps[k].data.data();
+            r.buffer.resize((size_t)img_x + 3 + 8);
+        }
+        out.resize((size_t)img_x * img_y * 4);
+        const uint8_t *rows[3] = {nullptr, nullptr, nullptr};
+        for (int j = 0; j < img_y; ++j) {
+            uint8_t *dst = &out[(size_t)img_x * 4 * (flip ? img_y - 1 - j : j)];
+            for (size_t k = 0; k < n; ++k) {
+                Resample &r = res[k];
+                const bool y_bot = r.ystep >= (r.vs >> 1);
+                rows[k] = resample_row(r.buffer.data(), y_bot ? r.line1 : r.line0, y_bot ? r.line0 : r.line1, r.w_lores, r.hs, r.vs);
+                if (++r.ystep >= r.vs) {
+                    r.ystep = 0;
+                    r.line0 = r.line1;
+                    if (++r.ypos < comps[k].y) {
+                        r.line1 += comps[k].w2;
+                    }
+                }
+            }
+            if (n == 3 && !is_rgb) {
+                ycbcr_to_rgba_row(dst, rows[0], rows[1], rows[2], img_x);
+            } else {
+                for (int i = 0; i < img_x; ++i) {
+                    dst[4 * i] = rows[0][i];
+                    dst[4 * i + 1] = n == 3 ? rows[1][i] : rows[0][i];
+                    dst[4 * i + 2] = n == 3 ? rows[2][i] : rows[0][i];
+                    dst[4 * i + 3] = 255;
+                }
+            }
+        }
+    }
+};
+
+inline bool is_jpeg(const uint8_t *data, size_t size)
+{
+    return size >= 2 && data[0] == 0xFF && data[1] == 0xD8;
+}
+
+// RGBA pixels of a JPEG file as stbi_load_from_memory(..., 4) returns them; `name` for messages
+inline void decode_rgba(const uint8_t *data, size_t size, const std::string &name, std::vector<uint8_t> &out, int &width, int &height,
+                        bool flip)
+{
+    try {
+        Decoder(data, size).decode(out, width, height, flip);
+    } catch (const std::exception &e) {
+        throw std::runtime_error("JPEG " + name + ": " + e.what());
+    }
+}
+
+}  // namespace crt_jpeg

@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "host_parallel.h"
+#include "jpeg_decode.h"
 
 namespace {
 
@@ -499,7 +500,7 @@ void decode_png_rgba(const uint8_t *file_data, size_t file_size, const std::stri
     } file{file_data, file_size};
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
     if (file.size() < 8 + 25 || std::memcmp(file.data(), sig, 8) != 0) {
-        throw std::runtime_error("not a PNG file (only PNG textures are supported by this loader): " + path);
+        throw std::runtime_error("not a PNG or JPEG file (the formats this loader reads): " + path);
     }
     size_t pos = 8;
     int bit_depth = 0, color_type = 0, interlace = 0;
@@ -605,14 +606,25 @@ void decode_png_rgba(const uint8_t *file_data, size_t file_size, const std::stri
     }
 }
 
-void load_png_rgba_flipped(const std::string &path, std::vector<uint8_t> &out, int &width, int &height)
+// stbi_load_from_memory(..., 4) for the formats textures come in: PNG (above) and JPEG (jpeg_decode.h)
+void decode_image_rgba(const uint8_t *data, size_t size, const std::string &name, std::vector<uint8_t> &out, int &width, int &height,
+                       bool flip)
+{
+    if (crt_jpeg::is_jpeg(data, size)) {
+        crt_jpeg::decode_rgba(data, size, name, out, width, height, flip);
+    } else {
+        decode_png_rgba(data, size, name, out, width, height, flip);
+    }
+}
+
+void load_image_rgba_flipped(const std::string &path, std::vector<uint8_t> &out, int &width, int &height)
 {
     std::ifstream in(path.c_str(), std::ios::binary);
     if (!in) {
         throw std::runtime_error("Failed to load " + path);  // util/material.cpp:11-13
     }
     const std::vector<uint8_t> file((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
-    decode_png_rgba(file.data(), file.size(), path, out, width, height, true);
+    decode_image_rgba(file.data(), file.size(), path, out, width, height, true);
 }
 
 // glm::normalize(v) = v * inversesqrt(dot(v, v)), inversesqrt(x) = 1 / sqrt(x)
@@ -1250,7 +1262,7 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
     crt::parallel_blocks((uint32_t)texture_files.size(), nthreads, [&](uint32_t i) {
         try {
             int w = 0, h = 0;
-            load_png_rgba_flipped(texture_files[i], S.texture_data[i], w, h);
+            load_image_rgba_flipped(texture_files[i], S.texture_data[i], w, h);
             S.textures[i] = crt_image_t{S.texture_data[i].data(), w, h, 4, CRT_COLOR_SPACE_SRGB};
         } catch (const std::exception &e) {
             tex_errors[i] = e.what();
@@ -1729,7 +1741,7 @@ void load_crts_impl(const std::string &file, int threads, crtio_scene &S)
     crt::parallel_blocks((uint32_t)num_images, nthreads, [&](uint32_t i) {
         try {
             int w = 0, h = 0;
-            decode_png_rgba(image_views[i].data, image_views[i].bytes, image_names[i], S.texture_data[i], w, h, true);
+            decode_image_rgba(image_views[i].data, image_views[i].bytes, image_names[i], S.texture_data[i], w, h, true);
             S.textures[i].data = S.texture_data[i].data();
             S.textures[i].width = w;
             S.textures[i].height = h;
@@ -2342,7 +2354,7 @@ void load_gltf_impl(const std::string &file, int threads, crtio_scene &S)
     crt::parallel_blocks((uint32_t)num_images, nthreads, [&](uint32_t i) {
         try {
             int w = 0, h = 0;
-            decode_png_rgba(encoded[i].data, encoded[i].size, image_names[i], S.texture_data[i], w, h, false);
+            decode_image_rgba(encoded[i].data, encoded[i].size, image_names[i], S.texture_data[i], w, h, false);
             S.textures[i].data = S.texture_data[i].data();
             S.textures[i].width = w;
             S.textures[i].height = h;

@@ -457,7 +457,7 @@ def test_native_crts_loader_errors(built, tmp_path):
     with pytest.raises(RuntimeError, match="array of 16 numbers"):
         scene_io.load_crts(write("matrix.crts", dict(ok, objects=[{"type": "MESH", "mesh": 0, "material": 0, "matrix": [1.0] * 12}]), tri))
     img_views = views + [{"byte_offset": 48, "byte_length": 16, "type": "UINT_8"}]
-    with pytest.raises(RuntimeError, match="Failed to load wood"):
+    with pytest.raises(RuntimeError, match="Failed to load wood .*JPEG"):
         scene_io.load_crts(write("image.crts", dict(ok, buffer_views=img_views, images=[{"name": "wood", "view": 2, "color_space": "SRGB"}]),
                                  tri + b"\xff\xd8\xff\xe0JFIF" + bytes(8)))
 
@@ -709,7 +709,7 @@ def test_native_gltf_loader_errors(built, tmp_path):
         scene_io.load_gltf(write("mesh.gltf", broken(nodes=[{"mesh": 4}])))
     with pytest.raises(RuntimeError, match="cyclic or too deep"):
         scene_io.load_gltf(write("cycle.gltf", broken(nodes=[{"children": [0], "mesh": 0}])))
-    with pytest.raises(RuntimeError, match="not a PNG file"):
+    with pytest.raises(RuntimeError, match="JPEG image 0"):  # (a JPEG cut off after its first table)
         scene_io.load_gltf(write("jpeg.gltf", broken(images=[{"uri": "data:image/jpeg;base64,/9j/4AAQSkZJRgABAQAAAQABAAD/2wBDAAgGBgcGBQgHBwcJCQgKDBQNDAsLDBkSEw8UHRofHh0a"}])))
     with pytest.raises(RuntimeError, match="exactly one of"):
         scene_io.load_gltf(write("img.gltf", broken(images=[{"name": "nothing"}])))
@@ -738,3 +738,119 @@ def test_native_gltf_loader_round_trip_and_oracle_frame(built, tmp_path):
         o.render(c.eye(), c.dir(), c.up(), cam["fov_y"], True, True)
         frames.append(o.read_accum())
     assert np.array_equal(frames[0].view(np.uint32), frames[1].view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# JPEG textures (chameleonrt_b200/csrc/jpeg_decode.h against stb_image, through the reference's loaders)
+def _jpeg_cases(tmp_path):
+    """JPEG files as encoders write them: baseline and progressive, 4:4:4 / 4:2:2 / 4:2:0, optimised Huffman tables, restart
+    markers, grey images, quality 30 to 100, sizes that are no multiple of the MCU (down to one pixel)."""
+    from PIL import Image as PILImage
+
+    rng = np.random.default_rng(0)
+
+    def picture(w, h, kind):
+        y, x = np.mgrid[0:h, 0:w]
+        if kind == 0:
+            img = np.stack([(x * 255 // max(w - 1, 1)), (y * 255 // max(h - 1, 1)), ((x + y) * 7) % 256], 2)
+        elif kind == 1:
+            img = rng.integers(0, 256, (h, w, 3))
+        else:
+            img = np.stack([128 + 100 * np.sin(x / 5.0) * np.cos(y / 7.0), 128 + 90 * np.cos(x / 3.0), 128 + 80 * np.sin((x + y) / 9.0)], 2)
+        return img.astype(np.uint8)
+
+    options = [dict(quality=75, subsampling=0), dict(quality=90, subsampling=1), dict(quality=50, subsampling=2),
+               dict(quality=85, subsampling=2, progressive=True), dict(quality=95, subsampling=0, progressive=True, optimize=True),
+               dict(quality=100, subsampling=2, optimize=True), dict(quality=30, subsampling=1, progressive=True),
+               dict(quality=80, subsampling=2, restart_marker_blocks=3), dict(quality=80, subsampling=0, progressive=True, restart_marker_rows=1)]
+    names = []
+    for (w, h) in [(64, 64), (33, 17), (1, 1), (7, 40), (130, 1), (100, 75)]:
+        for opts in options:
+            names.append(f"t{len(names)}.jpg")
+            PILImage.fromarray(picture(w, h, len(names) % 3), "RGB").save(str(tmp_path / names[-1]), format="JPEG", **opts)
+        names.append(f"t{len(names)}.jpg")
+        PILImage.fromarray(picture(w, h, 2)[:, :, 0], "L").save(str(tmp_path / names[-1]), format="JPEG", quality=80)
+        names.append(f"t{len(names)}.jpg")
+        PILImage.fromarray(picture(w, h, 1)[:, :, 0], "L").save(str(tmp_path / names[-1]), format="JPEG", quality=60, progressive=True)
+    return names
+
+
+@needs_ref
+def test_native_jpeg_textures_are_stb_images_bytes(built, tmp_path):
+    """OBJ materials with JPEG map_Kd textures (stbi_load, flipped), the same files embedded in a .crts (stbi_load_from_memory,
+    flipped) and referenced from a glTF (tinygltf -> stbi_load_from_memory, not flipped): every pixel as stb_image decodes it
+    — its integer IDCT, its chroma upsampling filters and its fixed-point YCbCr conversion restated in jpeg_decode.h."""
+    pytest.importorskip("PIL")
+    import json
+    import struct
+
+    names = _jpeg_cases(tmp_path)
+    (tmp_path / "tex.mtl").write_text("".join(f"newmtl m{i}\nKd 1 1 1\nmap_Kd {n}\n" for i, n in enumerate(names)))
+    (tmp_path / "tex.obj").write_text("mtllib tex.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\n" +
+                                      "".join(f"g g{i}\nusemtl m{i}\nf 1/1 2/2 3/3\n" for i in range(len(names))))
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32).tobytes() + np.array([0, 1, 2], np.uint32).tobytes()
+    blob = bytearray(tri)
+    views = [{"byte_offset": 0, "byte_length": 36, "type": "VEC3_F32"}, {"byte_offset": 36, "byte_length": 12, "type": "VEC3_U32"}]
+    images = []
+    for n in names[::5]:
+        raw = (tmp_path / n).read_bytes()
+        views.append({"byte_offset": len(blob), "byte_length": len(raw), "type": "UINT_8"})
+        images.append({"name": n, "view": len(views) - 1, "color_space": "SRGB"})
+        blob.extend(raw)
+    js = json.dumps({"meshes": [{"positions": 0, "indices": 1}], "images": images, "buffer_views": views,
+                     "objects": [{"type": "MESH", "mesh": 0, "material": 4294967295, "matrix": _rotated(1)}]}).encode()
+    (tmp_path / "tex.crts").write_bytes(struct.pack("<Q", len(js)) + js + bytes(blob))
+    (tmp_path / "tri.bin").write_bytes(tri)
+    (tmp_path / "tex.gltf").write_text(json.dumps({
+        "asset": {"version": "2.0"}, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}], "buffers": [{"uri": "tri.bin", "byteLength": 48}],
+        "bufferViews": [{"buffer": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 12}],
+        "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}, {"bufferView": 1, "componentType": 5125, "count": 3, "type": "SCALAR"}],
+        "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1}]}], "images": [{"uri": n} for n in names[2::5]]}))
+    for scene_file, count in (("tex.obj", len(names)), ("tex.crts", len(names[::5])), ("tex.gltf", len(names[2::5]))):
+        ref = _reference_arrays(str(tmp_path / scene_file))
+        nat, _ = _native_arrays(str(tmp_path / scene_file))
+        assert len(nat["textures"]) == count
+        _assert_same(nat, ref)
+
+
+def test_native_jpeg_decoder_without_the_reference(built, tmp_path):
+    """Properties that hold without stb_image at hand (the GPU box): a flat grey JPEG decodes to its exact level (the DC-only
+    path of the IDCT), sizes and the RGBA layout are right, a decoded photo-like image is close to its source, and the bytes
+    of one fixed file are pinned by a checksum taken when the decoder agreed with stb_image on it."""
+    pytest.importorskip("PIL")
+    from PIL import Image as PILImage
+
+    from chameleonrt_b200 import scene_io
+
+    def load(img, mode, **opts):
+        PILImage.fromarray(img, mode).save(str(tmp_path / "t.jpg"), format="JPEG", **opts)
+        (tmp_path / "t.mtl").write_text("newmtl m\nKd 1 1 1\nmap_Kd t.jpg\n")
+        (tmp_path / "t.obj").write_text("mtllib t.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\nusemtl m\nf 1/1 2/2 3/3\n")
+        loaded = scene_io.load_obj(str(tmp_path / "t.obj"))
+        t = loaded.c_scene.contents.textures[0]
+        return np.ctypeslib.as_array(t.data, (t.height, t.width, 4)).copy()
+
+    flat = load(np.full((19, 35), 200, np.uint8), "L", quality=90)
+    assert flat.shape == (19, 35, 4) and np.all(flat[..., :3] == 200) and np.all(flat[..., 3] == 255)
+    y, x = np.mgrid[0:48, 0:80]
+    src = np.stack([128 + 100 * np.sin(x / 9.0), 128 + 90 * np.cos(y / 7.0), 128 + 80 * np.sin((x + y) / 11.0)], 2).astype(np.uint8)
+    for opts in (dict(quality=95, subsampling=0), dict(quality=95, subsampling=2, progressive=True)):
+        got = load(src, "RGB", **opts)
+        assert got.shape == (48, 80, 4)
+        assert np.abs(got[::-1, :, :3].astype(int) - src.astype(int)).mean() < 3.0  # (the loader flips rows like stbi)
+
+
+def test_native_jpeg_decoder_against_committed_stb_output(built):
+    """tests/golden/jpeg_*.jpg (baseline 4:2:0, progressive 4:2:2 with optimised tables, 4:4:4 with restart markers, grey)
+    against the pixels the reference's stb_image decoded from them (tests/golden/make_jpeg_fixtures.py) — runs anywhere."""
+    from chameleonrt_b200 import scene_io
+
+    golden = os.path.join(ROOT, "tests", "golden")
+    expected = np.load(os.path.join(golden, "jpeg_expected.npz"))
+    loaded = scene_io.load_obj(os.path.join(golden, "jpeg_fixture.obj"))
+    s = loaded.c_scene.contents
+    assert s.num_textures == len(expected.files) == 4
+    for i, name in enumerate(sorted(expected.files)):
+        t = s.textures[i]
+        got = np.ctypeslib.as_array(t.data, (t.height, t.width, t.channels))
+        assert got.shape == expected[name].shape and np.array_equal(got, expected[name]), name
