@@ -18,9 +18,10 @@
  * cut into triangles by tinyobjloader's own ear clipping, tiny_obj_loader.h:1107-1310, restated in float in the same order of
  * operations so that the same triangles come out in the same order — also where that clipping gives up on a degenerate
  * polygon and drops the rest of it; fewer than three: skipped), v / vt / vn / f / g / o / usemtl / mtllib, MTL newmtl / Kd /
- * Ns / map_Kd (other statements are ignored as the reference ignores them), JPEG textures (see below) and 8-bit non-interlaced PNG textures (grey, grey +
- * alpha, RGB, RGBA, palette), which the reference loads through stb_image, flipped vertically and expanded to RGBA
- * (util/material.cpp:5-17). JPEG (chameleonrt_b200/csrc/jpeg_decode.h): baseline and progressive Huffman streams, grey or
+ * Ns / map_Kd (other statements are ignored as the reference ignores them), PNG, JPEG and TGA textures, which the reference loads through stb_image, flipped vertically and expanded to RGBA
+ * (util/material.cpp:5-17) — decoded here to the bytes stb_image returns: PNG of every colour type and bit depth (1-16), Adam7
+ * interlacing and tRNS transparency included; TGA true-colour / grey / colour-mapped, raw or run-length encoded, with
+ * stb_image's reading of 15/16-bit pixels; JPEG (chameleonrt_b200/csrc/jpeg_decode.h): baseline and progressive Huffman streams, grey or
  * three components, any sampling factors, restart intervals; the inverse DCT, the chroma upsampling and the YCbCr -> RGB
  * conversion are stb_image's integer arithmetic, so the pixels are the bytes stb_image returns. */
 #ifndef CRT_SCENE_IO_H
@@ -48,7 +49,7 @@ int crtio_load_obj(const char *path, int threads, crtio_scene **out);
 /* Scene::load_crts (util/scene.cpp:417-625): the reference's own binary format (a uint64 header size, a JSON header, a data
  * block of buffer views) — one geometry per mesh, MESH objects that instance a (mesh, material) pair under a matrix, LIGHT
  * objects (quad lights, frame = the object's matrix), CAMERA objects, every DisneyMaterial parameter with optional texture
- * handles, images as embedded PNG or JPEG files. The geometry arrays are NOT copied: the file stays mapped for the lifetime of the
+ * handles, images as embedded PNG / JPEG / TGA files. The geometry arrays are NOT copied: the file stays mapped for the lifetime of the
  * handle and crt_geometry_t points into it (arrays that are not 4-byte aligned in the file are copied). Images are decoded
  * concurrently. */
 int crtio_load_crts(const char *path, int threads, crtio_scene **out);
@@ -57,7 +58,7 @@ int crtio_load_crts(const char *path, int threads, crtio_scene **out);
  * its parameterized mesh (primitives = geometries, POSITION / TEXCOORD_0 as floats, 16- or 32-bit indices), the nodes of the
  * default scene that carry a mesh become instances (node transforms composed down the hierarchy in glm's float arithmetic),
  * pbrMetallicRoughness becomes base colour / metallic / roughness with texture handles (base colour textures sRGB,
- * metallic-roughness textures linear, B and G channels), images are decoded to RGBA (PNG, JPEG), the light is generated. Accessors
+ * metallic-roughness textures linear, B and G channels), images are decoded to RGBA (PNG, JPEG, TGA), the light is generated. Accessors
  * that are tightly packed and aligned are used in place in the mapped buffer; interleaved or 16-bit ones are gathered.
  * Not read (an error): sparse accessors, non-indexed or non-triangle primitives, extensions that move data (Draco, meshopt). */
 int crtio_load_gltf(const char *path, int threads, crtio_scene **out);

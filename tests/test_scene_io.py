@@ -854,3 +854,192 @@ def test_native_jpeg_decoder_against_committed_stb_output(built):
         t = s.textures[i]
         got = np.ctypeslib.as_array(t.data, (t.height, t.width, t.channels))
         assert got.shape == expected[name].shape and np.array_equal(got, expected[name]), name
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PNG in all its variants, TGA
+def _write_png(path, samples, color_type, bit_depth, interlace=False, palette=None, trns=None, seed=0):
+    """A PNG writer for the variants encoders rarely produce: `samples` (h, w, channels) of integers below 2**bit_depth, any
+    colour type / bit depth the format allows, Adam7 interlacing, a random filter type per scanline."""
+    import struct
+    import zlib
+
+    rng = np.random.default_rng(seed)
+    h, w, ch = samples.shape
+
+    def chunk(kind, body):
+        return struct.pack(">I", len(body)) + kind + body + struct.pack(">I", zlib.crc32(kind + body) & 0xFFFFFFFF)
+
+    def pack_rows(img):  # (rows, cols, ch) -> (rows, row_bytes) uint8
+        rows, cols, _ = img.shape
+        if bit_depth == 16:
+            return np.stack([(img >> 8) & 255, img & 255], -1).reshape(rows, -1).astype(np.uint8)
+        if bit_depth == 8:
+            return img.reshape(rows, -1).astype(np.uint8)
+        per = 8 // bit_depth
+        flat = img.reshape(rows, cols)
+        pad = (-cols) % per
+        flat = np.concatenate([flat, np.zeros((rows, pad), flat.dtype)], 1).reshape(rows, -1, per)
+        shifts = (np.arange(per)[::-1] * bit_depth)
+        return (flat << shifts).sum(-1).astype(np.uint8)
+
+    bpp = max(1, ch * bit_depth // 8)
+
+    def filtered(raw):  # raw: (rows, row_bytes)
+        out = bytearray()
+        prior = np.zeros(raw.shape[1], np.int32)
+        for r in raw.astype(np.int32):
+            left = np.concatenate([np.zeros(bpp, np.int32), r[:-bpp]]) if len(r) > bpp else np.zeros_like(r)
+            upleft = np.concatenate([np.zeros(bpp, np.int32), prior[:-bpp]]) if len(r) > bpp else np.zeros_like(r)
+            f = int(rng.integers(0, 5))
+            if f == 0:
+                enc = r
+            elif f == 1:
+                enc = r - left
+            elif f == 2:
+                enc = r - prior
+            elif f == 3:
+                enc = r - ((left + prior) >> 1)
+            else:
+                p = left + prior - upleft
+                pa, pb, pc = np.abs(p - left), np.abs(p - prior), np.abs(p - upleft)
+                enc = r - np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, prior, upleft))
+            out.append(f)
+            out.extend((enc & 255).astype(np.uint8).tobytes())
+            prior = r
+        return bytes(out)
+
+    if interlace:
+        data = b""
+        for x0, y0, dx, dy in zip((0, 4, 0, 2, 0, 1, 0), (0, 0, 4, 0, 2, 0, 1), (8, 8, 4, 4, 2, 2, 1), (8, 8, 8, 4, 4, 2, 2)):
+            sub = samples[y0::dy, x0::dx]
+            if sub.shape[0] and sub.shape[1]:
+                data += filtered(pack_rows(sub))
+    else:
+        data = filtered(pack_rows(samples))
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, bit_depth, color_type, 0, 0, 1 if interlace else 0))
+    if palette is not None:
+        png += chunk(b"PLTE", np.asarray(palette).astype(np.uint8).tobytes())
+    if trns is not None:
+        png += chunk(b"tRNS", np.asarray(trns).astype(np.uint8).tobytes())
+    comp = zlib.compress(data, 6)
+    half = len(comp) // 2
+    png += chunk(b"tEXt", b"Comment\0two IDAT chunks") + chunk(b"IDAT", comp[:half]) + chunk(b"IDAT", comp[half:]) + chunk(b"IEND", b"")
+    with open(path, "wb") as f:
+        f.write(png)
+
+
+def _write_tga(path, img, image_type, bpp, top_down=False, rle=False, cmap=None, cmap_bits=24, id_text=b"", seed=0):
+    """A TGA writer: `img` (h, w, channels) uint8 in the file's channel order (B, G, R[, A]; grey[, alpha]) — or (h, w) of 16-bit
+    pixels / colour-map indices; run-length packets of random lengths when `rle`."""
+    import struct
+
+    rng = np.random.default_rng(seed)
+    h, w = img.shape[:2]
+    px_bytes = (bpp + 7) // 8
+    if img.ndim == 2:
+        rows = np.stack([(img >> (8 * k)) & 255 for k in range(px_bytes)], -1).astype(np.uint8)
+    else:
+        rows = img.astype(np.uint8)
+    rows = rows if top_down else rows[::-1]
+    pixels = rows.reshape(-1, px_bytes)
+    body = bytearray()
+    if rle:
+        i = 0
+        while i < len(pixels):
+            n = int(min(rng.integers(1, 129), len(pixels) - i))
+            if rng.integers(0, 2):
+                body.append(0x80 | (n - 1))
+                body.extend(pixels[i].tobytes())
+                pixels[i:i + n] = pixels[i]  # (what the decoder must produce)
+            else:
+                body.append(n - 1)
+                body.extend(pixels[i:i + n].tobytes())
+            i += n
+        expected_rows = pixels.reshape(rows.shape)
+    header = struct.pack("<BBBHHBHHHHBB", len(id_text), 1 if cmap is not None else 0, image_type + (8 if rle else 0), 0,
+                         len(cmap) if cmap is not None else 0, cmap_bits if cmap is not None else 0, 0, 0, w, h, bpp, 0x20 if top_down else 0)
+    with open(path, "wb") as f:
+        f.write(header + id_text)
+        if cmap is not None:
+            f.write(np.asarray(cmap).astype(np.uint16 if cmap_bits in (15, 16) else np.uint8).tobytes())
+        f.write(bytes(body) if rle else pixels.tobytes())
+
+
+def _texture_scene(tmp_path, names):
+    (tmp_path / "tex.mtl").write_text("".join(f"newmtl m{i}\nKd 1 1 1\nmap_Kd {n}\n" for i, n in enumerate(names)))
+    (tmp_path / "tex.obj").write_text("mtllib tex.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\n" +
+                                      "".join(f"g g{i}\nusemtl m{i}\nf 1/1 2/2 3/3\n" for i in range(len(names))))
+    return str(tmp_path / "tex.obj")
+
+
+@needs_ref
+def test_native_png_variants_are_stb_images_bytes(built, tmp_path):
+    """Every colour type at every bit depth the format allows (grey 1 / 2 / 4 / 8 / 16, RGB 8 / 16, palette 1 / 2 / 4 / 8,
+    grey + alpha and RGBA 8 / 16), with and without Adam7 interlacing, with the tRNS chunk where it applies, all five scanline
+    filters, sizes down to 1 x 1 — and what PIL's encoder writes — against stbi_load(..., 4)."""
+    rng = np.random.default_rng(3)
+    names = []
+    for (w, h) in [(1, 1), (5, 3), (9, 17), (33, 8)]:
+        for color_type, depths, ch in [(0, (1, 2, 4, 8, 16), 1), (2, (8, 16), 3), (3, (1, 2, 4, 8), 1), (4, (8, 16), 2), (6, (8, 16), 4)]:
+            for depth in depths:
+                for interlace in (False, True):
+                    samples = rng.integers(0, 2 ** depth, (h, w, ch))
+                    palette = rng.integers(0, 256, 3 * 2 ** depth) if color_type == 3 else None
+                    trns = None
+                    if len(names) % 2 == 0:
+                        if color_type == 3:
+                            trns = rng.integers(0, 256, max(1, 2 ** depth // 2))
+                        elif color_type in (0, 2):  # the colour of one of the pixels is the transparent one
+                            v = samples[h // 2, w // 2]
+                            trns = np.stack([v >> 8, v & 255], -1).reshape(-1)
+                    names.append(f"v{len(names)}_{color_type}_{depth}_{int(interlace)}.png")
+                    _write_png(str(tmp_path / names[-1]), samples, color_type, depth, interlace, palette, trns, seed=len(names))
+    try:
+        from PIL import Image as PILImage
+
+        y, x = np.mgrid[0:21, 0:40]
+        PILImage.fromarray(((x + y) % 2).astype(bool)).save(str(tmp_path / "pil_1bit.png"))
+        PILImage.fromarray((x * 1000 + y * 37).astype(np.uint16)).save(str(tmp_path / "pil_16bit.png"))
+        PILImage.fromarray(np.stack([x * 6, y * 12, x + y], 2).astype(np.uint8), "RGB").quantize(16).save(str(tmp_path / "pil_pal.png"), bits=4)
+        PILImage.fromarray(np.stack([x * 6, y * 12], 2).astype(np.uint8), "LA").save(str(tmp_path / "pil_la.png"), optimize=True)
+        names += ["pil_1bit.png", "pil_16bit.png", "pil_pal.png", "pil_la.png"]
+    except ImportError:
+        pass
+    path = _texture_scene(tmp_path, names)
+    ref = _reference_arrays(path)
+    nat, _ = _native_arrays(path)
+    assert len(nat["textures"]) == len(names) >= 112
+    for name, (a, _), (b, _) in zip(names, nat["textures"], ref["textures"]):
+        assert a.shape == b.shape and np.array_equal(a, b), name
+
+
+@needs_ref
+def test_native_tga_textures_are_stb_images_bytes(built, tmp_path):
+    """TGA as stb_image reads it: 24 / 32-bit true colour, 15 / 16-bit (5-5-5), 8-bit grey, 16-bit grey + alpha, colour-mapped
+    with 8-bit indices and 24 / 32 / 16-bit map entries, each raw and run-length encoded, bottom-up and top-down, with an
+    image id field."""
+    rng = np.random.default_rng(4)
+    names = []
+    for (w, h) in [(1, 1), (13, 7), (40, 9)]:
+        for rle in (False, True):
+            for top_down in (False, True):
+                def add(img, image_type, bpp, **kw):
+                    names.append(f"t{len(names)}.tga")
+                    _write_tga(str(tmp_path / names[-1]), img, image_type, bpp, top_down=top_down, rle=rle, seed=len(names), **kw)
+
+                add(rng.integers(0, 256, (h, w, 3)), 2, 24)
+                add(rng.integers(0, 256, (h, w, 4)), 2, 32, id_text=b"made by a test")
+                add(rng.integers(0, 65536, (h, w)), 2, 16)
+                add(rng.integers(0, 32768, (h, w)), 2, 15)
+                add(rng.integers(0, 256, (h, w, 1)), 3, 8)
+                add(rng.integers(0, 256, (h, w, 2)), 3, 16)
+                add(rng.integers(0, 20, (h, w, 1)), 1, 8, cmap=rng.integers(0, 256, (16, 3)), cmap_bits=24)  # (indices 16-19: past the map)
+                add(rng.integers(0, 8, (h, w, 1)), 1, 8, cmap=rng.integers(0, 256, (8, 4)), cmap_bits=32)
+                add(rng.integers(0, 8, (h, w, 1)), 1, 8, cmap=rng.integers(0, 65536, 8), cmap_bits=16)
+    path = _texture_scene(tmp_path, names)
+    ref = _reference_arrays(path)
+    nat, _ = _native_arrays(path)
+    assert len(nat["textures"]) == len(names) == 108
+    for name, (a, _), (b, _) in zip(names, nat["textures"], ref["textures"]):
+        assert a.shape == b.shape and np.array_equal(a, b), name
