@@ -890,6 +890,7 @@ struct GeometryData {
 }  // namespace
 
 struct crtio_scene {
+    bool white_diffuse = false;  // MaterialMode::WHITE_DIFFUSE (util/scene.h:21): no materials are read, every geometry gets the default one
     std::unique_ptr<MappedFile> mapping;  // .crts: the geometry arrays are the file's own bytes where their alignment allows
     std::vector<GeometryData> geometries;  // OBJ: the arrays of its shapes
     std::vector<std::vector<uint8_t>> unaligned_copies;  // .crts / glTF: arrays that cannot be used where they are in the file
@@ -1432,7 +1433,7 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
         if (first) {  // (the reference reads material_ids[0] of an empty array here)
             throw std::runtime_error("a shape without a triangle (its faces have fewer than three corners or no area) in " + file);
         }
-        shape_material[s] = (uint32_t)material;
+        shape_material[s] = S.white_diffuse ? 0xffffffffu : (uint32_t)material;  // scene.cpp:126-130
         if (mixed) {
             warn << "Warning: per-face material IDs are not supported, materials may look wrong. Please reexport your mesh with each "
                     "material group as an OBJ group\n";
@@ -1456,6 +1457,9 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
     // ---- materials (scene.cpp:188-214) ----
     std::map<std::string, int32_t> texture_ids;
     std::vector<std::string> texture_files;
+    if (S.white_diffuse) {
+        obj_materials.clear();  // scene.cpp:188
+    }
     for (const Material &m : obj_materials) {
         crt_material_t d;
         std::memset(&d, 0, sizeof(d));
@@ -1979,7 +1983,7 @@ void load_crts_impl(const std::string &file, int threads, crtio_scene &S)
         }
     }
     // ---- materials (:513-556) ----
-    const Json &materials = section("materials");
+    const Json &materials = S.white_diffuse ? null_json : section("materials");  // (:513)
     for (size_t i = 0; i < materials.size(); ++i) {
         const std::string where = "material " + std::to_string(i);
         const Json &m = materials.at(i, "materials");
@@ -2025,7 +2029,7 @@ void load_crts_impl(const std::string &file, int threads, crtio_scene &S)
         const float *col[4] = {&mat[0], &mat[4], &mat[8], &mat[12]};
         if (type == "MESH") {
             const uint64_t mesh_id = n.at("mesh", where).number<uint64_t>(where + " mesh");
-            const uint32_t mat_id = n.at("material", where).number<uint32_t>(where + " material");
+            const uint32_t mat_id = S.white_diffuse ? 0xffffffffu : n.at("material", where).number<uint32_t>(where + " material");  // (:568-571)
             if (mesh_id >= num_meshes) {
                 throw std::runtime_error("crts: " + where + " instances mesh " + std::to_string(mesh_id) + " of " + std::to_string(num_meshes));
             }
@@ -2477,7 +2481,7 @@ void load_gltf_impl(const std::string &file, int threads, crtio_scene &S)
         for (size_t k = 0; k < prims.size(); ++k) {
             const std::string where = "mesh " + std::to_string(m) + " primitive " + std::to_string(k);
             const Json &p = prims.at(k, where);
-            S.material_ids[m].push_back((uint32_t)optional_index(p, "material", where));  // -1: validate_materials
+            S.material_ids[m].push_back(S.white_diffuse ? 0xffffffffu : (uint32_t)optional_index(p, "material", where));  // -1: validate_materials
             const int64_t mode = optional_index(p, "mode", where);
             if (mode != -1 && mode != 4) {
                 throw std::runtime_error("Unsupported primitive mode! Only triangles are supported");
@@ -2538,7 +2542,7 @@ void load_gltf_impl(const std::string &file, int threads, crtio_scene &S)
     }
     const double t_parsed = now_s();
     // ---- images (tinygltf's LoadImageData: stb_image, four components, rows top-down), linear until a material says otherwise ----
-    const Json &jimages = section("images");
+    const Json &jimages = S.white_diffuse ? null_json : section("images");  // (images and materials: scene.cpp:329)
     const size_t num_images = jimages.size();
     S.texture_data.resize(num_images);
     S.textures.resize(num_images);
@@ -2601,7 +2605,7 @@ void load_gltf_impl(const std::string &file, int threads, crtio_scene &S)
         }
         return (uint32_t)source;
     };
-    const Json &jmaterials = section("materials");
+    const Json &jmaterials = S.white_diffuse ? null_json : section("materials");
     for (size_t i = 0; i < jmaterials.size(); ++i) {
         const std::string where = "material " + std::to_string(i);
         const Json &m = jmaterials.at(i, "materials");
@@ -2724,14 +2728,18 @@ void load_gltf_impl(const std::string &file, int threads, crtio_scene &S)
 }
 
 template <typename Fn>
-int load_with(const char *path, crtio_scene **out, const char *api, Fn &&load)
+int load_with(const char *path, crtio_scene **out, const char *api, Fn &&load, int material_mode = CRTIO_MATERIALS_DEFAULT)
 {
     try {
         if (!path || !out) {
             throw std::runtime_error(std::string(api) + ": null argument");
         }
         *out = nullptr;
+        if (material_mode != CRTIO_MATERIALS_DEFAULT && material_mode != CRTIO_MATERIALS_WHITE_DIFFUSE) {
+            throw std::runtime_error(std::string(api) + ": unknown material mode " + std::to_string(material_mode));
+        }
         std::unique_ptr<crtio_scene> s(new crtio_scene());
+        s->white_diffuse = material_mode == CRTIO_MATERIALS_WHITE_DIFFUSE;
         load(std::string(path), *s);
         *out = s.release();
         return 0;
@@ -2763,7 +2771,7 @@ int crtio_load_gltf(const char *path, int threads, crtio_scene **out)
     return load_with(path, out, "crtio_load_gltf", [&](const std::string &file, crtio_scene &s) { load_gltf_impl(file, threads, s); });
 }
 
-int crtio_load(const char *path, int threads, crtio_scene **out)
+int crtio_load_mode(const char *path, int threads, int material_mode, crtio_scene **out)
 {
     return load_with(path, out, "crtio_load", [&](const std::string &file, crtio_scene &s) {
         const std::string ext = file_extension_of(file);
@@ -2776,7 +2784,12 @@ int crtio_load(const char *path, int threads, crtio_scene **out)
         } else {
             throw std::runtime_error("Unsupported file " + file);  // scene.cpp:63-66 (PBRT is not read, as in a default build of the reference)
         }
-    });
+    }, material_mode);
+}
+
+int crtio_load(const char *path, int threads, crtio_scene **out)
+{
+    return crtio_load_mode(path, threads, CRTIO_MATERIALS_DEFAULT, out);
 }
 
 int crtio_cameras(const crtio_scene *s, const crtio_camera_t **out)

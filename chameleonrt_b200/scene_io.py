@@ -38,6 +38,7 @@ def _lib():
         lib = C.CDLL(lib_path())
         for fn in (lib.crtio_load_obj, lib.crtio_load_crts, lib.crtio_load_gltf, lib.crtio_load):
             fn.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+        lib.crtio_load_mode.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         lib.crtio_cameras.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_float))]
         lib.crtio_scene_view.restype = C.POINTER(CScene)
         lib.crtio_scene_view.argtypes = [C.c_void_p]
@@ -138,6 +139,10 @@ def load_gltf(path: str, threads: int = 0) -> LoadedScene:
     return _load(_lib().crtio_load_gltf, path, threads)
 
 
-def load_scene(path: str, threads: int = 0) -> LoadedScene:
-    """``Scene::Scene`` (util/scene.cpp:49-67): the loader the file's extension names (obj, gltf, glb, crts)."""
-    return _load(_lib().crtio_load, path, threads)
+def load_scene(path: str, threads: int = 0, white_diffuse: bool = False) -> LoadedScene:
+    """``Scene::Scene`` (util/scene.cpp:49-67): the loader the file's extension names (obj, gltf, glb, crts). ``white_diffuse``:
+    ``MaterialMode::WHITE_DIFFUSE`` (main.cpp's ``-mat-mode white_diffuse``) — no materials, one default material for everything."""
+    h = C.c_void_p()
+    if _lib().crtio_load_mode(os.fspath(path).encode(), threads, 1 if white_diffuse else 0, C.byref(h)) != 0:
+        raise RuntimeError(_lib().crtio_last_error().decode())
+    return LoadedScene(h)

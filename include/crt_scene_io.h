@@ -64,6 +64,10 @@ int crtio_load_crts(const char *path, int threads, crtio_scene **out);
 int crtio_load_gltf(const char *path, int threads, crtio_scene **out);
 /* Scene::Scene (util/scene.cpp:49-67): the loader is chosen by the file extension (obj, gltf, glb, crts). */
 int crtio_load(const char *path, int threads, crtio_scene **out);
+/* Scene::Scene with a MaterialMode (util/scene.h:21, main.cpp's -mat-mode): CRTIO_MATERIALS_WHITE_DIFFUSE reads no materials
+ * (and, for glTF, no images) and gives every geometry the default DisneyMaterial. */
+enum { CRTIO_MATERIALS_DEFAULT = 0, CRTIO_MATERIALS_WHITE_DIFFUSE = 1 };
+int crtio_load_mode(const char *path, int threads, int material_mode, crtio_scene **out);
 /* The cameras of the file (CAMERA objects of a .crts; none for an OBJ): returns how many, *out = the array. */
 int crtio_cameras(const crtio_scene *s, const crtio_camera_t **out);
 /* The loaded scene as the plain-C view crtc_set_scene takes; valid until crtio_free. samples_per_pixel is 1 (the

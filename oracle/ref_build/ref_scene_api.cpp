@@ -30,6 +30,20 @@ void *refscene_load(const char *path, double *seconds)
         return nullptr;
     }
 }
+void *refscene_load_mode(const char *path, int white_diffuse, double *seconds)
+{
+    try {
+        const auto t0 = std::chrono::steady_clock::now();
+        Scene *s = new Scene(path, white_diffuse ? MaterialMode::WHITE_DIFFUSE : MaterialMode::DEFAULT);
+        if (seconds) {
+            *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        }
+        return s;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
 const char *refscene_error()
 {
     return g_err.c_str();

@@ -21,6 +21,8 @@ def _ref():
     lib = C.CDLL(REFLIB)
     lib.refscene_load.restype = C.c_void_p
     lib.refscene_load.argtypes = [C.c_char_p, C.POINTER(C.c_double)]
+    lib.refscene_load_mode.restype = C.c_void_p
+    lib.refscene_load_mode.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_double)]
     lib.refscene_error.restype = C.c_char_p
     lib.refscene_free.argtypes = [C.c_void_p]
     lib.refscene_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
@@ -40,12 +42,12 @@ def _ref():
     return lib
 
 
-def _reference_arrays(path):
+def _reference_arrays(path, white_diffuse=False):
     """What the reference's Scene constructor built, as numpy arrays (bit patterns for everything float). `geometries` lists the
     geometries of all meshes in order; `mesh_sizes` says how many each mesh has."""
     lib = _ref()
     secs = C.c_double(0)
-    h = lib.refscene_load(path.encode(), C.byref(secs))
+    h = lib.refscene_load_mode(path.encode(), int(white_diffuse), C.byref(secs))
     assert h, lib.refscene_error().decode()
     counts = (C.c_uint32 * 7)()
     lib.refscene_counts(h, counts)
@@ -86,10 +88,10 @@ def _reference_arrays(path):
     return out
 
 
-def _native_arrays(path, threads=0):
+def _native_arrays(path, threads=0, white_diffuse=False):
     from chameleonrt_b200 import scene_io
 
-    loaded = scene_io.load_scene(path, threads)
+    loaded = scene_io.load_scene(path, threads, white_diffuse)
     s = loaded.c_scene.contents
     out = dict(counts=[s.num_meshes, s.meshes[0].num_geometries if s.num_meshes else 0, s.num_parameterized_meshes, s.num_instances,
                        s.num_materials, s.num_textures, s.num_lights], seconds=loaded.timings["total_s"], timings=loaded.timings,
@@ -1043,3 +1045,23 @@ def test_native_tga_textures_are_stb_images_bytes(built, tmp_path):
     assert len(nat["textures"]) == len(names) == 108
     for name, (a, _), (b, _) in zip(names, nat["textures"], ref["textures"]):
         assert a.shape == b.shape and np.array_equal(a, b), name
+
+
+@needs_ref
+def test_native_loaders_white_diffuse_material_mode(built, tmp_path):
+    """MaterialMode::WHITE_DIFFUSE (main.cpp's -mat-mode white_diffuse) for the three formats: no materials are read (glTF: no
+    images either; .crts keeps its images), every geometry ends up with the one default material."""
+    pytest.importorskip("PIL")
+    from chameleonrt_b200.gltf_io import write_gltf
+    from chameleonrt_b200.obj_io import write_obj
+    from chameleonrt_b200.scenes import san_miguel_like, sponza_like
+
+    _, crts = _crts_file(tmp_path)
+    files = [write_obj(sponza_like(detail=0.25, tex_size=16)[0], str(tmp_path / "sponza.obj")), crts,
+             write_gltf(san_miguel_like(spp=1, scale=0.02, tex_size=16)[0], str(tmp_path / "miguel.gltf")), _gltf_hierarchy(tmp_path, "glb")]
+    for path in files:
+        ref = _reference_arrays(path, white_diffuse=True)
+        nat, loaded = _native_arrays(path, white_diffuse=True)
+        _assert_same(nat, ref)
+        assert nat["counts"][4] == 1 and "generating a default" in loaded.warnings
+        assert nat["counts"][5] == (2 if path.endswith(".crts") else 0)
