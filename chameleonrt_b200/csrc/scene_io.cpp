@@ -904,6 +904,7 @@ struct crtio_scene {
     std::vector<crt_material_t> materials;
     std::vector<std::vector<uint8_t>> texture_data;
     std::vector<crt_image_t> textures;
+    std::vector<std::string> texture_names;  // Image::name
     std::vector<crt_quad_light_t> lights;
     std::vector<crtio_camera_t> cameras;
     crt_scene_t view{};
@@ -1477,6 +1478,7 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
             if (it == texture_ids.end()) {
                 it = texture_ids.insert(std::make_pair(m.diffuse_texname, (int32_t)texture_files.size())).first;
                 texture_files.push_back(obj_base_dir + "/" + path);
+                S.texture_names.push_back(m.diffuse_texname);
             }
             const uint32_t tex_mask = 0x80000000u | ((uint32_t)it->second & 0x1fffffffu);  // TEXTURED_PARAM_MASK, SET_TEXTURE_ID
             std::memcpy(&d.base_color[0], &tex_mask, 4);
@@ -1962,6 +1964,7 @@ void load_crts_impl(const std::string &file, int threads, crtio_scene &S)
         const Json &img = images.at(i, "images");
         image_views[i] = view_of(img.at("view", where), where);
         image_names[i] = img.at("name", where).string(where + " name");
+        S.texture_names.push_back(image_names[i]);
         const int32_t cs = img.at("color_space", where).string(where + " color_space") == "LINEAR" ? CRT_COLOR_SPACE_LINEAR : CRT_COLOR_SPACE_SRGB;
         S.textures[i] = crt_image_t{nullptr, 0, 0, 4, cs};
     }
@@ -2555,6 +2558,7 @@ void load_gltf_impl(const std::string &file, int threads, crtio_scene &S)
         if (const Json *name = img.find("name")) {
             image_names[i] = name->kind == Json::kString ? name->str : std::string();
         }
+        S.texture_names.push_back(image_names[i]);
         image_names[i] = where + " \"" + image_names[i] + "\"";
         const Json *uri = img.find("uri");
         const int64_t view_id = optional_index(img, "bufferView", where);
@@ -2790,6 +2794,11 @@ int crtio_load_mode(const char *path, int threads, int material_mode, crtio_scen
 int crtio_load(const char *path, int threads, crtio_scene **out)
 {
     return crtio_load_mode(path, threads, CRTIO_MATERIALS_DEFAULT, out);
+}
+
+const char *crtio_texture_name(const crtio_scene *s, uint32_t i)
+{
+    return s && i < s->texture_names.size() ? s->texture_names[i].c_str() : "";
 }
 
 int crtio_cameras(const crtio_scene *s, const crtio_camera_t **out)

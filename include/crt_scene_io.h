@@ -73,6 +73,8 @@ int crtio_cameras(const crtio_scene *s, const crtio_camera_t **out);
 /* The loaded scene as the plain-C view crtc_set_scene takes; valid until crtio_free. samples_per_pixel is 1 (the
  * application sets it from its command line, main.cpp:186). */
 const crt_scene_t *crtio_scene_view(const crtio_scene *s);
+/* Image::name of texture i (OBJ: the map_Kd string; .crts / glTF: the image's "name"); "" past the end. */
+const char *crtio_texture_name(const crtio_scene *s, uint32_t i);
 /* Wall-clock seconds of the phases of the load: [0] total [1] parse (OBJ: mmap + both passes + polygons; .crts: the header)
  * [2] index remap (OBJ only) [3] materials + textures. Returns the number of entries written. */
 int crtio_timings(const crtio_scene *s, double *out, int n);

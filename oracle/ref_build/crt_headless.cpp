@@ -22,6 +22,7 @@
 #include "imgui.h"
 #include "render_plugin.h"
 #include "scene.h"
+#include "scene_native_load.h"
 #include "stb_image_write.h"
 #include "util.h"
 
@@ -104,7 +105,12 @@ int main(int argc, const char **argv)
         display->resize(win_width, win_height);
         renderer->initialize(win_width, win_height);
         {
-            Scene scene(scene_file, material_mode);
+            // CRT_NATIVE_LOADER=1: the line a maintainer would put in main.cpp:186 instead (backends/cuda/scene_native_load.h)
+            const char *native = std::getenv("CRT_NATIVE_LOADER");
+            const auto load_t0 = std::chrono::steady_clock::now();
+            Scene scene = (native && native[0] == '1') ? crt_cuda::load_scene_native(scene_file, material_mode) : Scene(scene_file, material_mode);
+            std::cout << "scene load: " << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - load_t0).count()
+                      << " ms (" << ((native && native[0] == '1') ? "native loader" : "Scene constructor") << ")\n";
             scene.samples_per_pixel = samples_per_pixel;
             std::cout << "Scene '" << scene_file << "': tris " << scene.total_tris() << " geometries "
                       << scene.num_geometries() << " instances " << scene.instances.size() << " materials "

@@ -7,6 +7,9 @@
 #include <exception>
 #include <string>
 #include "scene.h"
+#ifdef CRT_REFSCENE_NATIVE  // the same C API over backends/cuda/scene_native_load.cpp: the shim a maintainer would call from main.cpp
+#include "scene_native_load.h"
+#endif
 
 static_assert(sizeof(DisneyMaterial) == 64 && sizeof(QuadLight) == 80, "layouts");
 
@@ -34,7 +37,11 @@ void *refscene_load_mode(const char *path, int white_diffuse, double *seconds)
 {
     try {
         const auto t0 = std::chrono::steady_clock::now();
+#ifdef CRT_REFSCENE_NATIVE
+        Scene *s = new Scene(crt_cuda::load_scene_native(path, white_diffuse ? MaterialMode::WHITE_DIFFUSE : MaterialMode::DEFAULT));
+#else
         Scene *s = new Scene(path, white_diffuse ? MaterialMode::WHITE_DIFFUSE : MaterialMode::DEFAULT);
+#endif
         if (seconds) {
             *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         }
@@ -133,5 +140,9 @@ const uint8_t *refscene_texture(void *p, uint32_t i, int *w, int *h, int *channe
     *channels = im.channels;
     *color_space = (int)im.color_space;
     return im.img.data();
+}
+const char *refscene_texture_name(void *p, uint32_t i)
+{
+    return static_cast<Scene *>(p)->textures[i].name.c_str();
 }
 }

@@ -31,7 +31,7 @@ def test_scene_io_header_symbols_exported(built):
 
     header = open(os.path.join(ROOT, "include", "crt_scene_io.h")).read()
     declared = set(re.findall(r"\b(crtio_[a-z_]+)\s*\(", header))
-    assert declared == {"crtio_load_obj", "crtio_load_crts", "crtio_load_gltf", "crtio_load", "crtio_load_mode", "crtio_cameras", "crtio_scene_view", "crtio_timings",
+    assert declared == {"crtio_load_obj", "crtio_load_crts", "crtio_load_gltf", "crtio_load", "crtio_load_mode", "crtio_cameras", "crtio_texture_name", "crtio_scene_view", "crtio_timings",
                         "crtio_warnings", "crtio_free", "crtio_last_error"}
     lib = C.CDLL(scene_io.lib_path())
     for sym in declared:

@@ -55,6 +55,20 @@ def test_reference_loader_matches_python_scene_model(built, tmp_path, name):
 
 
 @needs_ref
+def test_headless_application_with_the_native_loader(built, tmp_path):
+    """The application path with the loader swapped (CRT_NATIVE_LOADER=1: crt_cuda::load_scene_native in place of the Scene
+    constructor, backends/cuda/scene_native_load.h): same scene summary line, same camera, same frame for an OBJ with textures
+    (tests/test_scene_io.py compares the Scene structs themselves, for every format)."""
+    scene, cam = sponza_like(spp=2, detail=0.2, tex_size=32)
+    obj = write_obj(scene, str(tmp_path / "scene.obj"))
+    runs = [run_headless("oracle", obj, cam, 64, 48, 2, 2, tmp_path, extra_env={"CRT_NATIVE_LOADER": flag}) for flag in ("0", "1")]
+    assert "(Scene constructor)" in runs[0][2] and "(native loader)" in runs[1][2]
+    summary = [[l for l in r[2].splitlines() if l.startswith("Scene '")][0] for r in runs]
+    assert summary[0] == summary[1] and runs[0][1] == runs[1][1]
+    assert np.array_equal(runs[0][0].view(np.uint32), runs[1][0].view(np.uint32))
+
+
+@needs_ref
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["cornell", "sponza"])
 def test_cuda_plugin_drop_in(built, tmp_path, name):

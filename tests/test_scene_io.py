@@ -17,8 +17,13 @@ from helpers import ROOT, synthetic_material_scene
 REFLIB = os.path.join(ROOT, "oracle", "_ref", "libcrt_refscene.so")
 
 
-def _ref():
-    lib = C.CDLL(REFLIB)
+NATIVE_SHIM_LIB = os.path.join(ROOT, "oracle", "_ref", "libcrt_refscene_native.so")
+
+
+def _ref(path=None):
+    lib = C.CDLL(path or REFLIB)
+    lib.refscene_texture_name.restype = C.c_char_p
+    lib.refscene_texture_name.argtypes = [C.c_void_p, C.c_uint32]
     lib.refscene_load.restype = C.c_void_p
     lib.refscene_load.argtypes = [C.c_char_p, C.POINTER(C.c_double)]
     lib.refscene_load_mode.restype = C.c_void_p
@@ -42,10 +47,10 @@ def _ref():
     return lib
 
 
-def _reference_arrays(path, white_diffuse=False):
+def _reference_arrays(path, white_diffuse=False, lib_path=None):
     """What the reference's Scene constructor built, as numpy arrays (bit patterns for everything float). `geometries` lists the
     geometries of all meshes in order; `mesh_sizes` says how many each mesh has."""
-    lib = _ref()
+    lib = _ref(lib_path)
     secs = C.c_double(0)
     h = lib.refscene_load_mode(path.encode(), int(white_diffuse), C.byref(secs))
     assert h, lib.refscene_error().decode()
@@ -84,6 +89,7 @@ def _reference_arrays(path, white_diffuse=False):
         w, hh, ch, cs = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         d = lib.refscene_texture(h, i, C.byref(w), C.byref(hh), C.byref(ch), C.byref(cs))
         out["textures"].append((np.ctypeslib.as_array(d, (hh.value, w.value, ch.value)).copy(), cs.value))
+    out["texture_names"] = [lib.refscene_texture_name(h, i).decode() for i in range(counts[5])]
     lib.refscene_free(h)
     return out
 
@@ -1065,3 +1071,23 @@ def test_native_loaders_white_diffuse_material_mode(built, tmp_path):
         _assert_same(nat, ref)
         assert nat["counts"][4] == 1 and "generating a default" in loaded.warnings
         assert nat["counts"][5] == (2 if path.endswith(".crts") else 0)
+
+
+@pytest.mark.skipif(not (os.path.exists(REFLIB) and os.path.exists(NATIVE_SHIM_LIB)), reason="oracle/_ref not built (needs /root/reference)")
+def test_native_loader_behind_the_references_scene_type(built, tmp_path):
+    """backends/cuda/scene_native_load.cpp — `Scene scene = crt_cuda::load_scene_native(file, mode);` in place of main.cpp:186's
+    Scene constructor — fills the reference's own Scene struct: compared member by member (texture names included) with the
+    constructor's Scene, for the three formats and both material modes."""
+    pytest.importorskip("PIL")
+    from chameleonrt_b200.obj_io import write_obj
+    from chameleonrt_b200.scenes import sponza_like
+
+    _, crts = _crts_file(tmp_path)
+    files = [write_obj(sponza_like(detail=0.25, tex_size=16)[0], str(tmp_path / "sponza.obj")), _polygon_obj(str(tmp_path / "poly.obj"), 7, faces=120),
+             crts, _gltf_hierarchy(tmp_path, "gltf"), os.path.join(ROOT, "tests", "golden", "jpeg_fixture.obj")]
+    for path in files:
+        for white in (False, True):
+            ref = _reference_arrays(path, white)
+            shim = _reference_arrays(path, white, lib_path=NATIVE_SHIM_LIB)
+            _assert_same(shim, ref)
+            assert shim["texture_names"] == ref["texture_names"], path
