@@ -38,12 +38,14 @@ inline uint8_t clamp_u8(int x)
     return (unsigned)x > 255u ? (x < 0 ? 0 : 255) : (uint8_t)x;
 }
 
-// one pass of the separable transform over eight values; `even` / `odd` come back still scaled by 4096
+// one pass of the separable transform over eight values (T: int, or a vector of ints — one transform per lane); the results
+// come back still scaled by 4096
+template <typename T>
 struct Idct1d {
-    int x0, x1, x2, x3, t0, t1, t2, t3;
-    Idct1d(int s0, int s1, int s2, int s3, int s4, int s5, int s6, int s7)
+    T x0, x1, x2, x3, t0, t1, t2, t3;
+    Idct1d(T s0, T s1, T s2, T s3, T s4, T s5, T s6, T s7)
     {
-        int p1, p2, p3, p4, p5;
+        T p1, p2, p3, p4, p5;
         p2 = s2;
         p3 = s6;
         p1 = (p2 + p3) * f2f(0.5411961f);
@@ -81,7 +83,7 @@ struct Idct1d {
     }
 };
 
-inline void idct_block(uint8_t *out, size_t out_stride, const short d[64])
+inline void idct_block_scalar(uint8_t *out, size_t out_stride, const short d[64])
 {
     int val[64];
     for (int i = 0; i < 8; ++i) {  // columns
@@ -91,7 +93,7 @@ inline void idct_block(uint8_t *out, size_t out_stride, const short d[64])
             const int dcterm = c[0] * 4;
             v[0] = v[8] = v[16] = v[24] = v[32] = v[40] = v[48] = v[56] = dcterm;
         } else {
-            Idct1d k(c[0], c[8], c[16], c[24], c[32], c[40], c[48], c[56]);
+            Idct1d<int> k(c[0], c[8], c[16], c[24], c[32], c[40], c[48], c[56]);
             k.x0 += 512, k.x1 += 512, k.x2 += 512, k.x3 += 512;  // the constants scaled by 1 << 12: back down, keeping two bits
             v[0] = (k.x0 + k.t3) >> 10;
             v[56] = (k.x0 - k.t3) >> 10;
@@ -106,7 +108,7 @@ inline void idct_block(uint8_t *out, size_t out_stride, const short d[64])
     for (int i = 0; i < 8; ++i) {  // rows: 17 bits to remove, rounded, with the +128 level shift added before the shift
         const int *v = val + 8 * i;
         uint8_t *o = out + out_stride * i;
-        Idct1d k(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+        Idct1d<int> k(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
         const int bias = 65536 + (128 << 17);
         k.x0 += bias, k.x1 += bias, k.x2 += bias, k.x3 += bias;
         o[0] = clamp_u8((k.x0 + k.t3) >> 17);
@@ -119,6 +121,98 @@ inline void idct_block(uint8_t *out, size_t out_stride, const short d[64])
         o[4] = clamp_u8((k.x3 - k.t0) >> 17);
     }
 }
+
+// A block whose only non-zero coefficient is the DC term: both passes reduce to one value for all 64 samples (column 0
+// becomes d0 * 4 in every row, each row then has x0 = x1 = x2 = x3 = s0 * 4096 + bias and t0..t3 = 0).
+inline void idct_dc_only(uint8_t *out, size_t out_stride, short dc)
+{
+    const uint8_t v = clamp_u8((dc * 4 * 4096 + 65536 + (128 << 17)) >> 17);
+    for (int r = 0; r < 8; ++r) {
+        std::memset(out + out_stride * r, v, 8);
+    }
+}
+
+#if defined(__GNUC__) && !defined(CRT_JPEG_NO_VECTOR)
+// The same arithmetic on eight lanes (GCC / Clang vector extensions; AVX2 or 2 x SSE2 underneath): the column pass with one
+// lane per column, an 8 x 8 transpose, the row pass with one lane per row, a transpose back. Integer adds, multiplies and
+// arithmetic shifts lane by lane — the values are the scalar version's (the all-zero-column shortcut of the scalar code
+// computes the same numbers as the full pass: (d0 * 4096 + 512) >> 10 == d0 * 4).
+typedef int32_t v8i __attribute__((vector_size(32)));
+typedef int16_t v8s __attribute__((vector_size(16)));
+typedef uint8_t v8b __attribute__((vector_size(8)));
+
+inline void transpose8(v8i r[8])
+{
+    const v8i lo32 = {0, 8, 1, 9, 4, 12, 5, 13}, hi32 = {2, 10, 3, 11, 6, 14, 7, 15};
+    const v8i lo64 = {0, 1, 8, 9, 4, 5, 12, 13}, hi64 = {2, 3, 10, 11, 6, 7, 14, 15};
+    const v8i lo128 = {0, 1, 2, 3, 8, 9, 10, 11}, hi128 = {4, 5, 6, 7, 12, 13, 14, 15};
+    v8i t[8], u[8];
+    for (int k = 0; k < 4; ++k) {
+        t[2 * k] = __builtin_shuffle(r[2 * k], r[2 * k + 1], lo32);
+        t[2 * k + 1] = __builtin_shuffle(r[2 * k], r[2 * k + 1], hi32);
+    }
+    for (int k = 0; k < 2; ++k) {
+        u[4 * k] = __builtin_shuffle(t[4 * k], t[4 * k + 2], lo64);
+        u[4 * k + 1] = __builtin_shuffle(t[4 * k], t[4 * k + 2], hi64);
+        u[4 * k + 2] = __builtin_shuffle(t[4 * k + 1], t[4 * k + 3], lo64);
+        u[4 * k + 3] = __builtin_shuffle(t[4 * k + 1], t[4 * k + 3], hi64);
+    }
+    for (int k = 0; k < 4; ++k) {
+        r[k] = __builtin_shuffle(u[k], u[k + 4], lo128);
+        r[k + 4] = __builtin_shuffle(u[k], u[k + 4], hi128);
+    }
+}
+
+inline void idct_block(uint8_t *out, size_t out_stride, const short d[64])
+{
+    v8i v[8];
+    for (int r = 0; r < 8; ++r) {
+        v8s row;
+        std::memcpy(&row, d + 8 * r, sizeof(row));
+        v[r] = __builtin_convertvector(row, v8i);
+    }
+    {
+        Idct1d<v8i> k(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+        k.x0 += 512, k.x1 += 512, k.x2 += 512, k.x3 += 512;
+        v[0] = (k.x0 + k.t3) >> 10;
+        v[7] = (k.x0 - k.t3) >> 10;
+        v[1] = (k.x1 + k.t2) >> 10;
+        v[6] = (k.x1 - k.t2) >> 10;
+        v[2] = (k.x2 + k.t1) >> 10;
+        v[5] = (k.x2 - k.t1) >> 10;
+        v[3] = (k.x3 + k.t0) >> 10;
+        v[4] = (k.x3 - k.t0) >> 10;
+    }
+    transpose8(v);  // v[c]: column c of the intermediate, one lane per row
+    {
+        Idct1d<v8i> k(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+        const int bias = 65536 + (128 << 17);
+        k.x0 += bias, k.x1 += bias, k.x2 += bias, k.x3 += bias;
+        v[0] = (k.x0 + k.t3) >> 17;
+        v[7] = (k.x0 - k.t3) >> 17;
+        v[1] = (k.x1 + k.t2) >> 17;
+        v[6] = (k.x1 - k.t2) >> 17;
+        v[2] = (k.x2 + k.t1) >> 17;
+        v[5] = (k.x2 - k.t1) >> 17;
+        v[3] = (k.x3 + k.t0) >> 17;
+        v[4] = (k.x3 - k.t0) >> 17;
+    }
+    transpose8(v);  // back to rows
+    for (int r = 0; r < 8; ++r) {
+        v8i x = v[r];
+        x &= ~(x < 0);
+        const v8i over = x > 255;
+        x = (x & ~over) | (over & 255);
+        const v8b bytes = __builtin_convertvector(x, v8b);
+        std::memcpy(out + out_stride * r, &bytes, 8);
+    }
+}
+#else
+inline void idct_block(uint8_t *out, size_t out_stride, const short d[64])
+{
+    idct_block_scalar(out, out_stride, d);
+}
+#endif
 
 // one output row of a component from its two nearest stored rows; returns where the row is (in `out` or `near` itself)
 inline const uint8_t *resample_row(uint8_t *out, const uint8_t *near, const uint8_t *far, int w, int hs, int vs)
@@ -179,7 +273,32 @@ constexpr int float2fixed(float x)
 }
 inline void ycbcr_to_rgba_row(uint8_t *out, const uint8_t *y, const uint8_t *pcb, const uint8_t *pcr, int count)
 {
-    for (int i = 0; i < count; ++i) {
+    int i = 0;
+#if defined(__GNUC__) && !defined(CRT_JPEG_NO_VECTOR)
+    typedef uint32_t v8u __attribute__((vector_size(32)));
+    for (; i + 8 <= count; i += 8) {  // the arithmetic below on eight pixels; wrap-around sums as in the unsigned scalar expression
+        v8b yb, cbb, crb;
+        std::memcpy(&yb, y + i, 8);
+        std::memcpy(&cbb, pcb + i, 8);
+        std::memcpy(&crb, pcr + i, 8);
+        const v8i y_fixed = (__builtin_convertvector(yb, v8i) << 20) + (1 << 19);
+        const v8i cr = __builtin_convertvector(crb, v8i) - 128, cb = __builtin_convertvector(cbb, v8i) - 128;
+        v8i r = y_fixed + cr * float2fixed(1.40200f);
+        v8i g = (v8i)((v8u)(y_fixed + cr * -float2fixed(0.71414f)) + ((v8u)(cb * -float2fixed(0.34414f)) & 0xffff0000u));
+        v8i b = y_fixed + cb * float2fixed(1.77200f);
+        r >>= 20;
+        g >>= 20;
+        b >>= 20;
+        const auto clamp = [](v8i x) {
+            x &= ~(x < 0);
+            const v8i over = x > 255;
+            return (x & ~over) | (over & 255);
+        };
+        const v8u px = (v8u)clamp(r) | ((v8u)clamp(g) << 8) | ((v8u)clamp(b) << 16) | 0xff000000u;
+        std::memcpy(out + 4 * i, &px, 32);
+    }
+#endif
+    for (; i < count; ++i) {
         const int y_fixed = (y[i] << 20) + (1 << 19);
         const int cr = pcr[i] - 128, cb = pcb[i] - 128;
         int r = y_fixed + cr * float2fixed(1.40200f);
@@ -545,8 +664,10 @@ private:
     }
 
     // ---- blocks ----
-    void sequential_block(Component &c, short block[64])
+    // returns whether any AC coefficient was decoded
+    bool sequential_block(Component &c, short block[64])
     {
+        bool any_ac = false;
         std::memset(block, 0, 64 * sizeof(short));
         const int t = huffman(dc_tables[c.hd]);
         if (t > 15) {
@@ -570,7 +691,9 @@ private:
             }
             const int z = zigzag()[k++];
             block[z] = (short)(receive_extend(s) * quant[c.tq][z]);
+            any_ac = true;
         }
+        return any_ac;
     }
     void progressive_dc(Component &c, short block[64], int succ_high, int succ_low)
     {
@@ -721,8 +844,12 @@ private:
         short block[64];
         const auto one_block = [&](Component &c, int bx, int by) {
             if (!progressive) {
-                sequential_block(c, block);
-                idct_block(&c.data[(size_t)c.w2 * by * 8 + bx * 8], (size_t)c.w2, block);
+                uint8_t *dst = &c.data[(size_t)c.w2 * by * 8 + bx * 8];
+                if (sequential_block(c, block)) {
+                    idct_block(dst, (size_t)c.w2, block);
+                } else {
+                    idct_dc_only(dst, (size_t)c.w2, block[0]);
+                }
                 return;
             }
             short *coeff = &c.coeff[64 * ((size_t)bx + (size_t)by * c.blocks_w)];

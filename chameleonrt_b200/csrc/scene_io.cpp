@@ -583,49 +583,77 @@ void decode_png_rgba(const uint8_t *file_data, size_t file_size, const std::stri
             throw std::runtime_error("corrupt PNG data: " + path);
         }
     }
-    // ---- per pass: undo the scanline filters (PNG specification, section 9), then place the samples ----
+    // ---- per pass: undo the scanline filters in place (PNG specification, section 9), then place the samples ----
     const int sample_bytes = bit_depth == 16 ? 2 : 1;
-    std::vector<uint8_t> samples((size_t)width * height * ch * sample_bytes);  // one byte (two for 16 bits) per sample, unscaled
     const size_t filter_bpp = std::max<size_t>(1, (size_t)ch * bit_depth / 8);
+    const bool rows_in_place = !interlace && bit_depth >= 8;  // the defiltered scanlines already are the rows of the image
+    std::vector<uint8_t> samples;  // else: one byte (two for 16 bits) per sample, unscaled, in image order
+    if (!rows_in_place) {
+        samples.resize((size_t)width * height * ch * sample_bytes);
+    }
     size_t offset = 0;
-    std::vector<uint8_t> prev_row, row;
+    size_t longest_row = 0;
     for (const Pass &ps : passes) {
-        prev_row.assign(ps.row_bytes, 0);
-        row.resize(ps.row_bytes);
+        longest_row = std::max(longest_row, ps.row_bytes);
+    }
+    const std::vector<uint8_t> zero_row(longest_row, 0);  // the row "above" the first one of a pass
+    for (const Pass &ps : passes) {
+        const size_t n = ps.row_bytes, bpp = std::min(filter_bpp, ps.row_bytes);
+        const uint8_t *prev = zero_row.data();
         for (int y = 0; y < ps.h; ++y) {
             const uint8_t filter = raw[offset];
-            const uint8_t *src = &raw[offset + 1];
-            offset += ps.row_bytes + 1;
-            for (size_t x = 0; x < ps.row_bytes; ++x) {
-                const int a = x >= filter_bpp ? row[x - filter_bpp] : 0, b = prev_row[x], c = x >= filter_bpp ? prev_row[x - filter_bpp] : 0;
-                int pred = 0;
-                switch (filter) {
-                case 0: pred = 0; break;
-                case 1: pred = a; break;
-                case 2: pred = b; break;
-                case 3: pred = (a + b) >> 1; break;
-                case 4: {
+            uint8_t *cur = &raw[offset + 1];
+            offset += n + 1;
+            switch (filter) {
+            case 0: break;
+            case 1:
+                for (size_t x = bpp; x < n; ++x) {
+                    cur[x] = (uint8_t)(cur[x] + cur[x - bpp]);
+                }
+                break;
+            case 2:
+                for (size_t x = 0; x < n; ++x) {
+                    cur[x] = (uint8_t)(cur[x] + prev[x]);
+                }
+                break;
+            case 3:
+                for (size_t x = 0; x < bpp; ++x) {
+                    cur[x] = (uint8_t)(cur[x] + (prev[x] >> 1));
+                }
+                for (size_t x = bpp; x < n; ++x) {
+                    cur[x] = (uint8_t)(cur[x] + ((cur[x - bpp] + prev[x]) >> 1));
+                }
+                break;
+            case 4:
+                for (size_t x = 0; x < bpp; ++x) {
+                    cur[x] = (uint8_t)(cur[x] + prev[x]);  // (a = c = 0: the predictor is b)
+                }
+                for (size_t x = bpp; x < n; ++x) {
+                    const int a = cur[x - bpp], b = prev[x], c = prev[x - bpp];
                     const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
-                    pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
-                    break;
+                    cur[x] = (uint8_t)(cur[x] + ((pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c)));
                 }
-                default: throw std::runtime_error("corrupt PNG filter: " + path);
-                }
-                row[x] = (uint8_t)(src[x] + pred);
+                break;
+            default: throw std::runtime_error("corrupt PNG filter: " + path);
+            }
+            prev = cur;
+            if (rows_in_place) {
+                continue;
             }
             uint8_t *dst_row = &samples[(size_t)(ps.y0 + y * ps.dy) * width * ch * sample_bytes];
             for (int x = 0; x < ps.w; ++x) {
                 uint8_t *dst = dst_row + (size_t)(ps.x0 + x * ps.dx) * ch * sample_bytes;
                 if (bit_depth >= 8) {
-                    std::memcpy(dst, &row[(size_t)x * ch * sample_bytes], (size_t)ch * sample_bytes);
+                    std::memcpy(dst, &cur[(size_t)x * ch * sample_bytes], (size_t)ch * sample_bytes);
                 } else {  // one channel, several samples per byte, the leftmost in the high bits
                     const int per_byte = 8 / bit_depth, shift = (per_byte - 1 - x % per_byte) * bit_depth;
-                    dst[0] = (uint8_t)((row[(size_t)x / per_byte] >> shift) & ((1 << bit_depth) - 1));
+                    dst[0] = (uint8_t)((cur[(size_t)x / per_byte] >> shift) & ((1 << bit_depth) - 1));
                 }
             }
-            prev_row.swap(row);
         }
     }
+    const size_t sample_stride = rows_in_place ? passes[0].row_bytes + 1 : (size_t)width * ch * sample_bytes;
+    const uint8_t *sample_base = rows_in_place ? raw.data() + 1 : samples.data();
     // ---- to RGBA as stbi_load(..., 4) does; flip: rows bottom-up (stbi_set_flip_vertically_on_load(1), util/material.cpp:8) ----
     static const int depth_scale[9] = {0, 0xff, 0x55, 0, 0x11, 0, 0, 0, 0x01};
     const int scale = color_type == 0 && bit_depth < 8 ? depth_scale[bit_depth] : 1;
@@ -638,8 +666,18 @@ void decode_png_rgba(const uint8_t *file_data, size_t file_size, const std::stri
     }
     out.resize((size_t)width * height * 4);
     for (int y = 0; y < height; ++y) {
-        const uint8_t *src = &samples[(size_t)(flip ? height - 1 - y : y) * width * ch * sample_bytes];
+        const uint8_t *src = sample_base + (size_t)(flip ? height - 1 - y : y) * sample_stride;
         uint8_t *dst = &out[(size_t)width * 4 * y];
+        if (bit_depth == 8 && !has_key && color_type == 6) {  // the common cases without per-pixel decisions
+            std::memcpy(dst, src, (size_t)width * 4);
+            continue;
+        }
+        if (bit_depth == 8 && !has_key && color_type == 2) {
+            for (int x = 0; x < width; ++x) {
+                dst[4 * x] = src[3 * x], dst[4 * x + 1] = src[3 * x + 1], dst[4 * x + 2] = src[3 * x + 2], dst[4 * x + 3] = 255;
+            }
+            continue;
+        }
         for (int x = 0; x < width; ++x) {
             const uint8_t *px = src + (size_t)x * ch * sample_bytes;
             uint8_t r, g, b, a = 255;
