@@ -38,6 +38,43 @@ inline uint8_t clamp_u8(int x)
     return (unsigned)x > 255u ? (x < 0 ? 0 : 255) : (uint8_t)x;
 }
 
+// Wrap-around 32-bit arithmetic (what stb_image's int arithmetic does in practice): a corrupt stream can carry coefficients
+// large enough to overflow, which must give garbage pixels, not undefined behaviour.
+inline int wadd(int a, int b)
+{
+    return (int)((unsigned)a + (unsigned)b);
+}
+inline int wsub(int a, int b)
+{
+    return (int)((unsigned)a - (unsigned)b);
+}
+inline int wmul(int a, int b)
+{
+    return (int)((unsigned)a * (unsigned)b);
+}
+#if defined(__GNUC__) && !defined(CRT_JPEG_NO_VECTOR)
+typedef int32_t v8i __attribute__((vector_size(32)));
+typedef uint32_t v8u __attribute__((vector_size(32)));
+typedef int16_t v8s __attribute__((vector_size(16)));
+typedef uint8_t v8b __attribute__((vector_size(8)));
+inline v8i wadd(v8i a, v8i b)
+{
+    return (v8i)((v8u)a + (v8u)b);
+}
+inline v8i wadd(v8i a, int b)
+{
+    return (v8i)((v8u)a + (unsigned)b);
+}
+inline v8i wsub(v8i a, v8i b)
+{
+    return (v8i)((v8u)a - (v8u)b);
+}
+inline v8i wmul(v8i a, int b)
+{
+    return (v8i)((v8u)a * (unsigned)b);
+}
+#endif
+
 // one pass of the separable transform over eight values (T: int, or a vector of ints — one transform per lane); the results
 // come back still scaled by 4096
 template <typename T>
@@ -48,77 +85,76 @@ struct Idct1d {
         T p1, p2, p3, p4, p5;
         p2 = s2;
         p3 = s6;
-        p1 = (p2 + p3) * f2f(0.5411961f);
-        t2 = p1 + p3 * f2f(-1.847759065f);
-        t3 = p1 + p2 * f2f(0.765366865f);
+        p1 = wmul(wadd(p2, p3), f2f(0.5411961f));
+        t2 = wadd(p1, wmul(p3, f2f(-1.847759065f)));
+        t3 = wadd(p1, wmul(p2, f2f(0.765366865f)));
         p2 = s0;
         p3 = s4;
-        t0 = (p2 + p3) * 4096;
-        t1 = (p2 - p3) * 4096;
-        x0 = t0 + t3;
-        x3 = t0 - t3;
-        x1 = t1 + t2;
-        x2 = t1 - t2;
+        t0 = wmul(wadd(p2, p3), 4096);
+        t1 = wmul(wsub(p2, p3), 4096);
+        x0 = wadd(t0, t3);
+        x3 = wsub(t0, t3);
+        x1 = wadd(t1, t2);
+        x2 = wsub(t1, t2);
         t0 = s7;
         t1 = s5;
         t2 = s3;
         t3 = s1;
-        p3 = t0 + t2;
-        p4 = t1 + t3;
-        p1 = t0 + t3;
-        p2 = t1 + t2;
-        p5 = (p3 + p4) * f2f(1.175875602f);
-        t0 = t0 * f2f(0.298631336f);
-        t1 = t1 * f2f(2.053119869f);
-        t2 = t2 * f2f(3.072711026f);
-        t3 = t3 * f2f(1.501321110f);
-        p1 = p5 + p1 * f2f(-0.899976223f);
-        p2 = p5 + p2 * f2f(-2.562915447f);
-        p3 = p3 * f2f(-1.961570560f);
-        p4 = p4 * f2f(-0.390180644f);
-        t3 += p1 + p4;
-        t2 += p2 + p3;
-        t1 += p2 + p4;
-        t0 += p1 + p3;
+        p3 = wadd(t0, t2);
+        p4 = wadd(t1, t3);
+        p1 = wadd(t0, t3);
+        p2 = wadd(t1, t2);
+        p5 = wmul(wadd(p3, p4), f2f(1.175875602f));
+        t0 = wmul(t0, f2f(0.298631336f));
+        t1 = wmul(t1, f2f(2.053119869f));
+        t2 = wmul(t2, f2f(3.072711026f));
+        t3 = wmul(t3, f2f(1.501321110f));
+        p1 = wadd(p5, wmul(p1, f2f(-0.899976223f)));
+        p2 = wadd(p5, wmul(p2, f2f(-2.562915447f)));
+        p3 = wmul(p3, f2f(-1.961570560f));
+        p4 = wmul(p4, f2f(-0.390180644f));
+        t3 = wadd(t3, wadd(p1, p4));
+        t2 = wadd(t2, wadd(p2, p3));
+        t1 = wadd(t1, wadd(p2, p4));
+        t0 = wadd(t0, wadd(p1, p3));
+    }
+    // the eight outputs: (x_k +- t_k + rounding) >> shift, in the order 0, 7, 1, 6, 2, 5, 3, 4
+    void finish(T out[8], int rounding, int shift)
+    {
+        x0 = wadd(x0, rounding), x1 = wadd(x1, rounding), x2 = wadd(x2, rounding), x3 = wadd(x3, rounding);
+        out[0] = wadd(x0, t3) >> shift;
+        out[7] = wsub(x0, t3) >> shift;
+        out[1] = wadd(x1, t2) >> shift;
+        out[6] = wsub(x1, t2) >> shift;
+        out[2] = wadd(x2, t1) >> shift;
+        out[5] = wsub(x2, t1) >> shift;
+        out[3] = wadd(x3, t0) >> shift;
+        out[4] = wsub(x3, t0) >> shift;
     }
 };
 
 inline void idct_block_scalar(uint8_t *out, size_t out_stride, const short d[64])
 {
     int val[64];
-    for (int i = 0; i < 8; ++i) {  // columns
-        int *v = val + i;
+    for (int i = 0; i < 8; ++i) {  // columns; the constants scaled things by 1 << 12: back down, keeping two extra bits
         const short *c = d + i;
+        int v[8];
         if (c[8] == 0 && c[16] == 0 && c[24] == 0 && c[32] == 0 && c[40] == 0 && c[48] == 0 && c[56] == 0) {
-            const int dcterm = c[0] * 4;
-            v[0] = v[8] = v[16] = v[24] = v[32] = v[40] = v[48] = v[56] = dcterm;
+            v[0] = v[1] = v[2] = v[3] = v[4] = v[5] = v[6] = v[7] = c[0] * 4;
         } else {
-            Idct1d<int> k(c[0], c[8], c[16], c[24], c[32], c[40], c[48], c[56]);
-            k.x0 += 512, k.x1 += 512, k.x2 += 512, k.x3 += 512;  // the constants scaled by 1 << 12: back down, keeping two bits
-            v[0] = (k.x0 + k.t3) >> 10;
-            v[56] = (k.x0 - k.t3) >> 10;
-            v[8] = (k.x1 + k.t2) >> 10;
-            v[48] = (k.x1 - k.t2) >> 10;
-            v[16] = (k.x2 + k.t1) >> 10;
-            v[40] = (k.x2 - k.t1) >> 10;
-            v[24] = (k.x3 + k.t0) >> 10;
-            v[32] = (k.x3 - k.t0) >> 10;
+            Idct1d<int>(c[0], c[8], c[16], c[24], c[32], c[40], c[48], c[56]).finish(v, 512, 10);
+        }
+        for (int r = 0; r < 8; ++r) {
+            val[8 * r + i] = v[r];
         }
     }
     for (int i = 0; i < 8; ++i) {  // rows: 17 bits to remove, rounded, with the +128 level shift added before the shift
         const int *v = val + 8 * i;
-        uint8_t *o = out + out_stride * i;
-        Idct1d<int> k(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
-        const int bias = 65536 + (128 << 17);
-        k.x0 += bias, k.x1 += bias, k.x2 += bias, k.x3 += bias;
-        o[0] = clamp_u8((k.x0 + k.t3) >> 17);
-        o[7] = clamp_u8((k.x0 - k.t3) >> 17);
-        o[1] = clamp_u8((k.x1 + k.t2) >> 17);
-        o[6] = clamp_u8((k.x1 - k.t2) >> 17);
-        o[2] = clamp_u8((k.x2 + k.t1) >> 17);
-        o[5] = clamp_u8((k.x2 - k.t1) >> 17);
-        o[3] = clamp_u8((k.x3 + k.t0) >> 17);
-        o[4] = clamp_u8((k.x3 - k.t0) >> 17);
+        int o[8];
+        Idct1d<int>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]).finish(o, 65536 + (128 << 17), 17);
+        for (int c = 0; c < 8; ++c) {
+            out[out_stride * i + c] = clamp_u8(o[c]);
+        }
     }
 }
 
@@ -126,7 +162,7 @@ inline void idct_block_scalar(uint8_t *out, size_t out_stride, const short d[64]
 // becomes d0 * 4 in every row, each row then has x0 = x1 = x2 = x3 = s0 * 4096 + bias and t0..t3 = 0).
 inline void idct_dc_only(uint8_t *out, size_t out_stride, short dc)
 {
-    const uint8_t v = clamp_u8((dc * 4 * 4096 + 65536 + (128 << 17)) >> 17);
+    const uint8_t v = clamp_u8(wadd(wmul(dc * 4, 4096), 65536 + (128 << 17)) >> 17);
     for (int r = 0; r < 8; ++r) {
         std::memset(out + out_stride * r, v, 8);
     }
@@ -137,9 +173,6 @@ inline void idct_dc_only(uint8_t *out, size_t out_stride, short dc)
 // lane per column, an 8 x 8 transpose, the row pass with one lane per row, a transpose back. Integer adds, multiplies and
 // arithmetic shifts lane by lane — the values are the scalar version's (the all-zero-column shortcut of the scalar code
 // computes the same numbers as the full pass: (d0 * 4096 + 512) >> 10 == d0 * 4).
-typedef int32_t v8i __attribute__((vector_size(32)));
-typedef int16_t v8s __attribute__((vector_size(16)));
-typedef uint8_t v8b __attribute__((vector_size(8)));
 
 inline void transpose8(v8i r[8])
 {
@@ -171,32 +204,9 @@ inline void idct_block(uint8_t *out, size_t out_stride, const short d[64])
         std::memcpy(&row, d + 8 * r, sizeof(row));
         v[r] = __builtin_convertvector(row, v8i);
     }
-    {
-        Idct1d<v8i> k(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
-        k.x0 += 512, k.x1 += 512, k.x2 += 512, k.x3 += 512;
-        v[0] = (k.x0 + k.t3) >> 10;
-        v[7] = (k.x0 - k.t3) >> 10;
-        v[1] = (k.x1 + k.t2) >> 10;
-        v[6] = (k.x1 - k.t2) >> 10;
-        v[2] = (k.x2 + k.t1) >> 10;
-        v[5] = (k.x2 - k.t1) >> 10;
-        v[3] = (k.x3 + k.t0) >> 10;
-        v[4] = (k.x3 - k.t0) >> 10;
-    }
+    Idct1d<v8i>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]).finish(v, 512, 10);
     transpose8(v);  // v[c]: column c of the intermediate, one lane per row
-    {
-        Idct1d<v8i> k(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
-        const int bias = 65536 + (128 << 17);
-        k.x0 += bias, k.x1 += bias, k.x2 += bias, k.x3 += bias;
-        v[0] = (k.x0 + k.t3) >> 17;
-        v[7] = (k.x0 - k.t3) >> 17;
-        v[1] = (k.x1 + k.t2) >> 17;
-        v[6] = (k.x1 - k.t2) >> 17;
-        v[2] = (k.x2 + k.t1) >> 17;
-        v[5] = (k.x2 - k.t1) >> 17;
-        v[3] = (k.x3 + k.t0) >> 17;
-        v[4] = (k.x3 - k.t0) >> 17;
-    }
+    Idct1d<v8i>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]).finish(v, 65536 + (128 << 17), 17);
     transpose8(v);  // back to rows
     for (int r = 0; r < 8; ++r) {
         v8i x = v[r];
@@ -275,7 +285,6 @@ inline void ycbcr_to_rgba_row(uint8_t *out, const uint8_t *y, const uint8_t *pcb
 {
     int i = 0;
 #if defined(__GNUC__) && !defined(CRT_JPEG_NO_VECTOR)
-    typedef uint32_t v8u __attribute__((vector_size(32)));
     for (; i + 8 <= count; i += 8) {  // the arithmetic below on eight pixels; wrap-around sums as in the unsigned scalar expression
         v8b yb, cbb, crb;
         std::memcpy(&yb, y + i, 8);
@@ -329,6 +338,9 @@ struct HuffmanTable {
         for (int len = 1; len <= 16; ++len) {
             valptr[len] = k;
             mincode[len] = code;
+            if (code + counts[len - 1] > (1 << len)) {  // more codes of this length than the code space has left
+                throw std::runtime_error("bad code lengths");
+            }
             for (int i = 0; i < counts[len - 1]; ++i, ++k, ++code) {
                 if (len <= 9) {
                     const int first = code << (9 - len);
@@ -338,9 +350,6 @@ struct HuffmanTable {
                 }
             }
             maxcode[len] = counts[len - 1] ? code - 1 : -1;
-            if (code > (1 << len)) {
-                throw std::runtime_error("bad code lengths");
-            }
             code <<= 1;
         }
         maxcode[17] = 0x7fffffff;
@@ -673,8 +682,8 @@ private:
         if (t > 15) {
             throw std::runtime_error("bad DC code");
         }
-        c.dc_pred += receive_extend(t);
-        block[0] = (short)(c.dc_pred * quant[c.tq][0]);
+        c.dc_pred = wadd(c.dc_pred, receive_extend(t));
+        block[0] = (short)wmul(c.dc_pred, quant[c.tq][0]);
         const HuffmanTable &ac = ac_tables[c.ha];
         for (int k = 1; k < 64;) {
             const int rs = huffman(ac), r = rs >> 4, s = rs & 15;
@@ -702,8 +711,8 @@ private:
             if (t > 15) {
                 throw std::runtime_error("bad DC code");
             }
-            c.dc_pred += receive_extend(t);
-            block[0] = (short)(c.dc_pred * (1 << succ_low));
+            c.dc_pred = wadd(c.dc_pred, receive_extend(t));
+            block[0] = (short)wmul(c.dc_pred, 1 << succ_low);
         } else if (get_bits(1)) {
             block[0] = (short)(block[0] + (1 << succ_low));
         }
