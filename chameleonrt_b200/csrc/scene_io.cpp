@@ -31,7 +31,8 @@
 #include <vector>
 
 #include "host_parallel.h"
-#include "jpeg_decode.h"
+#include "image_decode.h"
+#include "json_reader.h"
 
 namespace {
 
@@ -481,403 +482,7 @@ void load_mtl(const std::string &path, std::vector<Material> &materials, std::ma
     materials.push_back(material);
 }
 
-// ---- PNG (what stb_image decodes for this project's scenes: 8-bit, non-interlaced), to RGBA, rows flipped ----
-uint32_t be32(const uint8_t *p)
-{
-    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
-}
-
-// `file`: the bytes of a PNG file; `path`: its name for messages. Every bit depth (1, 2, 4, 8, 16) and colour type, Adam7
-// interlacing, tRNS transparency; to 8-bit RGBA the way stbi_load(..., 4) gets there (stb_image.h: stbi__parse_png_file):
-// grey samples of fewer than 8 bits are scaled to the full range (x 0xff / 0x55 / 0x11), palette indices are looked up, a
-// 16-bit sample keeps its high byte, and the one transparent colour of a grey / RGB image (tRNS) is compared at the file's
-// own sample width.
-void decode_png_rgba(const uint8_t *file_data, size_t file_size, const std::string &path, std::vector<uint8_t> &out, int &width,
-                     int &height, bool flip)
-{
-    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
-    if (file_size < 8 + 25 || std::memcmp(file_data, sig, 8) != 0) {
-        throw std::runtime_error("not a PNG, JPEG or TGA file (the formats this loader reads): " + path);
-    }
-    size_t pos = 8;
-    int bit_depth = 0, color_type = 0, interlace = 0;
-    std::vector<uint8_t> idat, palette, trns;
-    width = height = 0;
-    while (pos + 12 <= file_size) {
-        const uint32_t len = be32(file_data + pos);
-        const char *type = reinterpret_cast<const char *>(file_data + pos + 4);
-        const uint8_t *body = file_data + pos + 8;
-        if (pos + 12 + (size_t)len > file_size) {
-            throw std::runtime_error("truncated PNG: " + path);
-        }
-        if (std::memcmp(type, "IHDR", 4) == 0 && len >= 13) {
-            width = (int)be32(body);
-            height = (int)be32(body + 4);
-            bit_depth = body[8];
-            color_type = body[9];
-            interlace = body[12];
-        } else if (std::memcmp(type, "PLTE", 4) == 0) {
-            palette.assign(body, body + len);
-        } else if (std::memcmp(type, "tRNS", 4) == 0) {
-            trns.assign(body, body + len);
-        } else if (std::memcmp(type, "IDAT", 4) == 0) {
-            idat.insert(idat.end(), body, body + len);
-        } else if (std::memcmp(type, "IEND", 4) == 0) {
-            break;
-        }
-        pos += 12 + (size_t)len;
-    }
-    int ch;
-    switch (color_type) {
-    case 0: ch = 1; break;
-    case 2: ch = 3; break;
-    case 3: ch = 1; break;
-    case 4: ch = 2; break;
-    case 6: ch = 4; break;
-    default: throw std::runtime_error("unsupported PNG colour type: " + path);
-    }
-    const bool depth_ok = bit_depth == 8 || (bit_depth == 16 && color_type != 3) ||
-                          ((bit_depth == 1 || bit_depth == 2 || bit_depth == 4) && (color_type == 0 || color_type == 3));
-    if (width <= 0 || height <= 0 || (uint64_t)width * (uint64_t)height > ((uint64_t)1 << 28) || !depth_ok || interlace > 1) {
-        throw std::runtime_error("unsupported or corrupt PNG header: " + path);
-    }
-    // ---- the passes of the image (one, or the seven of Adam7) and their sizes in the inflated stream ----
-    struct Pass {
-        int x0, y0, dx, dy, w, h;
-        size_t row_bytes;
-    };
-    std::vector<Pass> passes;
-    const auto add_pass = [&](int x0, int y0, int dx, int dy) {
-        const int w = (width - x0 + dx - 1) / dx, h = (height - y0 + dy - 1) / dy;
-        if (w > 0 && h > 0) {
-            passes.push_back(Pass{x0, y0, dx, dy, w, h, ((size_t)w * ch * bit_depth + 7) / 8});
-        }
-    };
-    if (interlace) {
-        static const int x0[7] = {0, 4, 0, 2, 0, 1, 0}, y0[7] = {0, 0, 4, 0, 2, 0, 1}, dx[7] = {8, 8, 4, 4, 2, 2, 1}, dy[7] = {8, 8, 8, 4, 4, 2, 2};
-        for (int k = 0; k < 7; ++k) {
-            add_pass(x0[k], y0[k], dx[k], dy[k]);
-        }
-    } else {
-        add_pass(0, 0, 1, 1);
-    }
-    size_t raw_size = 0;
-    for (const Pass &ps : passes) {
-        raw_size += (ps.row_bytes + 1) * (size_t)ps.h;
-    }
-    std::vector<uint8_t> raw(raw_size);
-    {
-        z_stream zs;
-        std::memset(&zs, 0, sizeof(zs));
-        if (inflateInit(&zs) != Z_OK) {
-            throw std::runtime_error("zlib: " + path);
-        }
-        zs.next_in = idat.data();
-        zs.avail_in = (uInt)idat.size();
-        zs.next_out = raw.data();
-        zs.avail_out = (uInt)raw.size();
-        const int rc = inflate(&zs, Z_FINISH);
-        const size_t got = raw.size() - zs.avail_out;
-        inflateEnd(&zs);
-        if ((rc != Z_STREAM_END && rc != Z_OK && rc != Z_BUF_ERROR) || got != raw.size()) {  // (more data than the image needs is ignored)
-            throw std::runtime_error("corrupt PNG data: " + path);
-        }
-    }
-    // ---- per pass: undo the scanline filters in place (PNG specification, section 9), then place the samples ----
-    const int sample_bytes = bit_depth == 16 ? 2 : 1;
-    const size_t filter_bpp = std::max<size_t>(1, (size_t)ch * bit_depth / 8);
-    const bool rows_in_place = !interlace && bit_depth >= 8;  // the defiltered scanlines already are the rows of the image
-    std::vector<uint8_t> samples;  // else: one byte (two for 16 bits) per sample, unscaled, in image order
-    if (!rows_in_place) {
-        samples.resize((size_t)width * height * ch * sample_bytes);
-    }
-    size_t offset = 0;
-    size_t longest_row = 0;
-    for (const Pass &ps : passes) {
-        longest_row = std::max(longest_row, ps.row_bytes);
-    }
-    const std::vector<uint8_t> zero_row(longest_row, 0);  // the row "above" the first one of a pass
-    for (const Pass &ps : passes) {
-        const size_t n = ps.row_bytes, bpp = std::min(filter_bpp, ps.row_bytes);
-        const uint8_t *prev = zero_row.data();
-        for (int y = 0; y < ps.h; ++y) {
-            const uint8_t filter = raw[offset];
-            uint8_t *cur = &raw[offset + 1];
-            offset += n + 1;
-            switch (filter) {
-            case 0: break;
-            case 1:
-                for (size_t x = bpp; x < n; ++x) {
-                    cur[x] = (uint8_t)(cur[x] + cur[x - bpp]);
-                }
-                break;
-            case 2:
-                for (size_t x = 0; x < n; ++x) {
-                    cur[x] = (uint8_t)(cur[x] + prev[x]);
-                }
-                break;
-            case 3:
-                for (size_t x = 0; x < bpp; ++x) {
-                    cur[x] = (uint8_t)(cur[x] + (prev[x] >> 1));
-                }
-                for (size_t x = bpp; x < n; ++x) {
-                    cur[x] = (uint8_t)(cur[x] + ((cur[x - bpp] + prev[x]) >> 1));
-                }
-                break;
-            case 4:
-                for (size_t x = 0; x < bpp; ++x) {
-                    cur[x] = (uint8_t)(cur[x] + prev[x]);  // (a = c = 0: the predictor is b)
-                }
-                for (size_t x = bpp; x < n; ++x) {
-                    const int a = cur[x - bpp], b = prev[x], c = prev[x - bpp];
-                    const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
-                    cur[x] = (uint8_t)(cur[x] + ((pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c)));
-                }
-                break;
-            default: throw std::runtime_error("corrupt PNG filter: " + path);
-            }
-            prev = cur;
-            if (rows_in_place) {
-                continue;
-            }
-            uint8_t *dst_row = &samples[(size_t)(ps.y0 + y * ps.dy) * width * ch * sample_bytes];
-            for (int x = 0; x < ps.w; ++x) {
-                uint8_t *dst = dst_row + (size_t)(ps.x0 + x * ps.dx) * ch * sample_bytes;
-                if (bit_depth >= 8) {
-                    std::memcpy(dst, &cur[(size_t)x * ch * sample_bytes], (size_t)ch * sample_bytes);
-                } else {  // one channel, several samples per byte, the leftmost in the high bits
-                    const int per_byte = 8 / bit_depth, shift = (per_byte - 1 - x % per_byte) * bit_depth;
-                    dst[0] = (uint8_t)((cur[(size_t)x / per_byte] >> shift) & ((1 << bit_depth) - 1));
-                }
-            }
-        }
-    }
-    const size_t sample_stride = rows_in_place ? passes[0].row_bytes + 1 : (size_t)width * ch * sample_bytes;
-    const uint8_t *sample_base = rows_in_place ? raw.data() + 1 : samples.data();
-    // ---- to RGBA as stbi_load(..., 4) does; flip: rows bottom-up (stbi_set_flip_vertically_on_load(1), util/material.cpp:8) ----
-    static const int depth_scale[9] = {0, 0xff, 0x55, 0, 0x11, 0, 0, 0, 0x01};
-    const int scale = color_type == 0 && bit_depth < 8 ? depth_scale[bit_depth] : 1;
-    const auto sample16 = [](const uint8_t *p) { return (uint32_t)((p[0] << 8) | p[1]); };
-    uint32_t key[3] = {0, 0, 0};  // the transparent colour of a grey / RGB image, at the sample width the comparison uses
-    const bool has_key = (color_type == 0 && trns.size() >= 2) || (color_type == 2 && trns.size() >= 6);
-    for (int k = 0; has_key && k < (color_type == 0 ? 1 : 3); ++k) {
-        const uint32_t v = sample16(&trns[2 * (size_t)k]);
-        key[k] = bit_depth == 16 ? v : (uint32_t)(uint8_t)((v & 255) * (uint32_t)scale);
-    }
-    out.resize((size_t)width * height * 4);
-    for (int y = 0; y < height; ++y) {
-        const uint8_t *src = sample_base + (size_t)(flip ? height - 1 - y : y) * sample_stride;
-        uint8_t *dst = &out[(size_t)width * 4 * y];
-        if (bit_depth == 8 && !has_key && color_type == 6) {  // the common cases without per-pixel decisions
-            std::memcpy(dst, src, (size_t)width * 4);
-            continue;
-        }
-        if (bit_depth == 8 && !has_key && color_type == 2) {
-            for (int x = 0; x < width; ++x) {
-                dst[4 * x] = src[3 * x], dst[4 * x + 1] = src[3 * x + 1], dst[4 * x + 2] = src[3 * x + 2], dst[4 * x + 3] = 255;
-            }
-            continue;
-        }
-        for (int x = 0; x < width; ++x) {
-            const uint8_t *px = src + (size_t)x * ch * sample_bytes;
-            uint8_t r, g, b, a = 255;
-            if (color_type == 3) {
-                const size_t i = px[0];
-                if (3 * i + 2 >= palette.size()) {
-                    throw std::runtime_error("corrupt PNG palette: " + path);
-                }
-                r = palette[3 * i], g = palette[3 * i + 1], b = palette[3 * i + 2];
-                a = i < trns.size() ? trns[i] : 255;
-            } else if (bit_depth == 16) {
-                uint32_t v[4] = {0, 0, 0, 0xffff};
-                for (int k = 0; k < ch; ++k) {
-                    v[k] = sample16(px + 2 * k);
-                }
-                switch (color_type) {
-                case 0: r = g = b = (uint8_t)(v[0] >> 8), a = (has_key && v[0] == key[0]) ? 0 : 255; break;
-                case 2:
-                    r = (uint8_t)(v[0] >> 8), g = (uint8_t)(v[1] >> 8), b = (uint8_t)(v[2] >> 8);
-                    a = (has_key && v[0] == key[0] && v[1] == key[1] && v[2] == key[2]) ? 0 : 255;
-                    break;
-                case 4: r = g = b = (uint8_t)(v[0] >> 8), a = (uint8_t)(v[1] >> 8); break;
-                default: r = (uint8_t)(v[0] >> 8), g = (uint8_t)(v[1] >> 8), b = (uint8_t)(v[2] >> 8), a = (uint8_t)(v[3] >> 8); break;
-                }
-            } else {
-                switch (color_type) {
-                case 0:
-                    r = g = b = (uint8_t)(px[0] * scale);
-                    a = (has_key && r == key[0]) ? 0 : 255;
-                    break;
-                case 2:
-                    r = px[0], g = px[1], b = px[2];
-                    a = (has_key && r == key[0] && g == key[1] && b == key[2]) ? 0 : 255;
-                    break;
-                case 4: r = g = b = px[0], a = px[1]; break;
-                default: r = px[0], g = px[1], b = px[2], a = px[3]; break;
-                }
-            }
-            dst[4 * x] = r, dst[4 * x + 1] = g, dst[4 * x + 2] = b, dst[4 * x + 3] = a;
-        }
-    }
-}
-
-// ---- TGA (stb_image.h: stbi__tga_test, stbi__tga_load): true-colour, grey and colour-mapped images, raw or run-length
-// encoded, 8 / 15 / 16 / 24 / 32 bits; stb_image's reading of the format: 15- and 16-bit pixels are 5-5-5 RGB without alpha
-// ((c * 255) / 31), a 16-bit grey image is grey + alpha, the colour map starts `first entry index` BYTES into its data, an
-// index past the map reads entry 0, bytes missing at the end read as 0. `path`: its name for messages.
-bool looks_like_tga(const uint8_t *d, size_t n)
-{
-    if (n < 18 || d[1] > 1) {
-        return false;
-    }
-    const int type = d[2], bpp = d[16];
-    if (d[1] == 1) {
-        const int pal_bits = d[7];
-        if ((type != 1 && type != 9) || (pal_bits != 8 && pal_bits != 15 && pal_bits != 16 && pal_bits != 24 && pal_bits != 32) ||
-            (bpp != 8 && bpp != 16)) {
-            return false;
-        }
-    } else if (type != 2 && type != 3 && type != 10 && type != 11) {
-        return false;
-    }
-    const int w = d[12] | (d[13] << 8), h = d[14] | (d[15] << 8);
-    return w >= 1 && h >= 1 && (bpp == 8 || bpp == 15 || bpp == 16 || bpp == 24 || bpp == 32);
-}
-
-void decode_tga_rgba(const uint8_t *data, size_t size, const std::string &path, std::vector<uint8_t> &out, int &width, int &height, bool flip)
-{
-    if (!looks_like_tga(data, size)) {
-        throw std::runtime_error("not a PNG, JPEG or TGA file (the formats this loader reads): " + path);
-    }
-    size_t pos = 0;
-    const auto get8 = [&]() -> int { return pos < size ? data[pos++] : (++pos, 0); };
-    const auto get16 = [&]() {
-        const int lo = get8();
-        return lo | (get8() << 8);
-    };
-    const int id_length = get8(), indexed = get8();
-    int type = get8();
-    const bool rle = type >= 8;
-    type -= rle ? 8 : 0;
-    const int pal_start = get16(), pal_len = get16(), pal_bits = get8();
-    get16();
-    get16();
-    width = get16();
-    height = get16();
-    const int bpp = get8(), descriptor = get8();
-    const bool bottom_up = ((descriptor >> 5) & 1) == 0;
-    bool rgb16 = false;
-    const auto components = [&](int bits, bool grey) {
-        switch (bits) {
-        case 8: return 1;
-        case 16:
-            if (grey) {
-                return 2;
-            }
-            rgb16 = true;
-            return 3;
-        case 15: rgb16 = true; return 3;
-        case 24: return 3;
-        case 32: return 4;
-        default: return 0;
-        }
-    };
-    const int comp = indexed ? components(pal_bits, false) : components(bpp, type == 3);
-    if (!comp) {
-        throw std::runtime_error("unsupported TGA pixel format: " + path);
-    }
-    const auto read_rgb16 = [&](uint8_t *o) {
-        const int px = get16();
-        o[0] = (uint8_t)((((px >> 10) & 31) * 255) / 31);
-        o[1] = (uint8_t)((((px >> 5) & 31) * 255) / 31);
-        o[2] = (uint8_t)(((px & 31) * 255) / 31);
-    };
-    pos += (size_t)id_length;
-    std::vector<uint8_t> map;
-    if (indexed) {
-        pos += (size_t)pal_start;
-        map.resize((size_t)pal_len * comp);
-        for (int i = 0; i < pal_len; ++i) {
-            if (rgb16) {
-                read_rgb16(&map[(size_t)i * comp]);
-            } else {
-                for (int j = 0; j < comp; ++j) {
-                    map[(size_t)i * comp + j] = (uint8_t)get8();
-                }
-            }
-        }
-    }
-    const size_t count = (size_t)width * height;
-    std::vector<uint8_t> px(count * comp);
-    uint8_t current[4] = {0, 0, 0, 0};
-    int run = 0;
-    bool repeating = false;
-    for (size_t i = 0; i < count; ++i) {
-        bool read = true;
-        if (rle) {
-            if (run == 0) {
-                const int cmd = get8();
-                run = 1 + (cmd & 127);
-                repeating = (cmd >> 7) != 0;
-            } else {
-                read = !repeating;
-            }
-        }
-        if (read) {
-            if (indexed) {
-                int idx = bpp == 8 ? get8() : get16();
-                idx = idx >= pal_len ? 0 : idx;
-                for (int j = 0; j < comp; ++j) {
-                    current[j] = (size_t)idx * comp + j < map.size() ? map[(size_t)idx * comp + j] : 0;
-                }
-            } else if (rgb16) {
-                read_rgb16(current);
-            } else {
-                for (int j = 0; j < comp; ++j) {
-                    current[j] = (uint8_t)get8();
-                }
-            }
-        }
-        std::memcpy(&px[i * comp], current, (size_t)comp);
-        --run;
-    }
-    out.resize(count * 4);
-    for (int y = 0; y < height; ++y) {
-        // the file's rows are bottom-up unless the descriptor says otherwise; stbi returns top-down rows, `flip` turns them again
-        const bool reverse = bottom_up != flip;
-        const uint8_t *src = &px[(size_t)(reverse ? height - 1 - y : y) * width * comp];
-        uint8_t *dst = &out[(size_t)y * width * 4];
-        for (int x = 0; x < width; ++x, src += comp, dst += 4) {
-            switch (comp) {
-            case 1: dst[0] = dst[1] = dst[2] = src[0], dst[3] = 255; break;
-            case 2: dst[0] = dst[1] = dst[2] = src[0], dst[3] = src[1]; break;
-            case 3:
-                if (rgb16) {
-                    dst[0] = src[0], dst[1] = src[1], dst[2] = src[2];
-                } else {
-                    dst[0] = src[2], dst[1] = src[1], dst[2] = src[0];  // stored blue first
-                }
-                dst[3] = 255;
-                break;
-            default: dst[0] = src[2], dst[1] = src[1], dst[2] = src[0], dst[3] = src[3]; break;
-            }
-        }
-    }
-}
-
-// stbi_load_from_memory(..., 4) for the formats textures come in: PNG and TGA (above), JPEG (jpeg_decode.h)
-void decode_image_rgba(const uint8_t *data, size_t size, const std::string &name, std::vector<uint8_t> &out, int &width, int &height,
-                       bool flip)
-{
-    static const uint8_t png_sig[4] = {0x89, 'P', 'N', 'G'};
-    if (crt_jpeg::is_jpeg(data, size)) {
-        crt_jpeg::decode_rgba(data, size, name, out, width, height, flip);
-    } else if (size >= 4 && std::memcmp(data, png_sig, 4) == 0) {
-        decode_png_rgba(data, size, name, out, width, height, flip);
-    } else {  // (TGA has no signature: stb_image tries it last, too)
-        decode_tga_rgba(data, size, name, out, width, height, flip);
-    }
-}
+using crt_image::decode_image_rgba;
 
 void load_image_rgba_flipped(const std::string &path, std::vector<uint8_t> &out, int &width, int &height)
 {
@@ -1566,306 +1171,9 @@ void load_obj_impl(const std::string &file, int threads, crtio_scene &S)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// .crts (util/scene.cpp:417-625). The header is JSON, which the reference reads with nlohmann::json; what matters of that
-// library's behaviour is restated here: numbers without fraction or exponent are integers (unsigned if not negative), the
-// others go through strtod; get<float>() is a static_cast from whichever of the three the number is; a key given twice
-// keeps its last value; operator[] on a missing key yields null, whose size() is 0.
-struct Json {
-    enum Kind { kNull, kBool, kUnsigned, kSigned, kFloat, kString, kArray, kObject };
-    Kind kind = kNull;
-    bool boolean = false;
-    uint64_t u = 0;
-    int64_t i = 0;
-    double d = 0;
-    std::string str;
-    std::vector<Json> items;
-    std::vector<std::pair<std::string, Json>> members;
-
-    const Json *find(const char *key) const
-    {
-        const Json *found = nullptr;
-        for (const auto &m : members) {
-            if (m.first == key) {
-                found = &m.second;
-            }
-        }
-        return found;
-    }
-    const Json &at(const char *key, const std::string &where) const
-    {
-        const Json *j = kind == kObject ? find(key) : nullptr;
-        if (!j) {
-            throw std::runtime_error("scene header: " + where + " has no \"" + key + "\"");
-        }
-        return *j;
-    }
-    const Json &at(size_t index, const std::string &where) const
-    {
-        if (kind != kArray || index >= items.size()) {
-            throw std::runtime_error("scene header: " + where + " has no element " + std::to_string(index));
-        }
-        return items[index];
-    }
-    size_t size() const
-    {
-        return kind == kArray ? items.size() : (kind == kObject ? members.size() : (kind == kNull ? 0 : 1));
-    }
-    template <typename T>
-    T number(const std::string &where) const
-    {
-        switch (kind) {
-        case kUnsigned: return static_cast<T>(u);
-        case kSigned: return static_cast<T>(i);
-        case kFloat: return static_cast<T>(d);
-        case kBool: return static_cast<T>(boolean);
-        default: throw std::runtime_error("scene header: " + where + " is not a number");
-        }
-    }
-    const std::string &string(const std::string &where) const
-    {
-        if (kind != kString) {
-            throw std::runtime_error("scene header: " + where + " is not a string");
-        }
-        return str;
-    }
-    std::vector<float> floats(size_t at_least, const std::string &where) const
-    {
-        if (kind != kArray || items.size() < at_least) {
-            throw std::runtime_error("scene header: " + where + " is not an array of " + std::to_string(at_least) + " numbers");
-        }
-        std::vector<float> out(items.size());
-        for (size_t k = 0; k < items.size(); ++k) {
-            out[k] = items[k].number<float>(where);
-        }
-        return out;
-    }
-};
-
-class JsonParser {
-public:
-    JsonParser(const char *begin, const char *end) : p(begin), end(end) {}
-    Json parse_document()
-    {
-        Json j = value(0);
-        skip_space();
-        if (p != end) {
-            fail("text after the document");
-        }
-        return j;
-    }
-
-private:
-    const char *p, *end;
-    [[noreturn]] void fail(const std::string &what) const
-    {
-        throw std::runtime_error("scene header: malformed JSON (" + what + ")");
-    }
-    void skip_space()
-    {
-        while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) {
-            ++p;
-        }
-    }
-    bool literal(const char *word)
-    {
-        const size_t n = std::strlen(word);
-        if ((size_t)(end - p) >= n && std::memcmp(p, word, n) == 0) {
-            p += n;
-            return true;
-        }
-        return false;
-    }
-    static void append_utf8(std::string &out, uint32_t cp)
-    {
-        if (cp < 0x80) {
-            out += (char)cp;
-        } else if (cp < 0x800) {
-            out += (char)(0xC0 | (cp >> 6));
-            out += (char)(0x80 | (cp & 0x3F));
-        } else if (cp < 0x10000) {
-            out += (char)(0xE0 | (cp >> 12));
-            out += (char)(0x80 | ((cp >> 6) & 0x3F));
-            out += (char)(0x80 | (cp & 0x3F));
-        } else {
-            out += (char)(0xF0 | (cp >> 18));
-            out += (char)(0x80 | ((cp >> 12) & 0x3F));
-            out += (char)(0x80 | ((cp >> 6) & 0x3F));
-            out += (char)(0x80 | (cp & 0x3F));
-        }
-    }
-    uint32_t hex4()
-    {
-        if (end - p < 4) {
-            fail("short \\u escape");
-        }
-        uint32_t v = 0;
-        for (int k = 0; k < 4; ++k, ++p) {
-            const char c = *p;
-            v = v * 16 + (c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : (fail("bad \\u escape"), 0));
-        }
-        return v;
-    }
-    std::string string_body()
-    {
-        std::string out;
-        ++p;  // the opening quote
-        for (;;) {
-            if (p >= end) {
-                fail("unterminated string");
-            }
-            const char c = *p++;
-            if (c == '"') {
-                return out;
-            }
-            if (c != '\\') {
-                out += c;
-                continue;
-            }
-            if (p >= end) {
-                fail("unterminated escape");
-            }
-            const char e = *p++;
-            switch (e) {
-            case '"': out += '"'; break;
-            case '\\': out += '\\'; break;
-            case '/': out += '/'; break;
-            case 'b': out += '\b'; break;
-            case 'f': out += '\f'; break;
-            case 'n': out += '\n'; break;
-            case 'r': out += '\r'; break;
-            case 't': out += '\t'; break;
-            case 'u': {
-                uint32_t cp = hex4();
-                if (cp >= 0xD800 && cp < 0xDC00 && end - p >= 6 && p[0] == '\\' && p[1] == 'u') {
-                    p += 2;
-                    const uint32_t low = hex4();
-                    cp = 0x10000 + ((cp - 0xD800) << 10) + (low - 0xDC00);
-                }
-                append_utf8(out, cp);
-                break;
-            }
-            default: fail("unknown escape");
-            }
-        }
-    }
-    Json number()
-    {
-        const char *start = p;
-        bool integral = true;
-        if (p < end && *p == '-') {
-            ++p;
-        }
-        while (p < end && ((*p >= '0' && *p <= '9') || *p == '.' || *p == 'e' || *p == 'E' || *p == '+' || *p == '-')) {
-            integral = integral && *p >= '0' && *p <= '9';
-            ++p;
-        }
-        const std::string text(start, p);
-        if (text.empty() || text == "-") {
-            fail("a value was expected");
-        }
-        Json j;
-        char *stop = nullptr;
-        errno = 0;
-        if (integral && text[0] != '-') {
-            j.u = std::strtoull(text.c_str(), &stop, 10);
-            j.kind = Json::kUnsigned;
-        } else if (integral) {
-            j.i = std::strtoll(text.c_str(), &stop, 10);
-            j.kind = Json::kSigned;
-        }
-        if (!integral || errno == ERANGE) {  // (an integer too large for 64 bits is read as a float, as nlohmann does)
-            j.d = std::strtod(text.c_str(), &stop);
-            j.kind = Json::kFloat;
-        }
-        if (!stop || *stop != '\0') {
-            fail("bad number " + text);
-        }
-        return j;
-    }
-    Json value(int depth)
-    {
-        if (depth > 64) {
-            fail("nesting too deep");
-        }
-        skip_space();
-        if (p >= end) {
-            fail("unexpected end");
-        }
-        Json j;
-        if (*p == '{') {
-            ++p;
-            j.kind = Json::kObject;
-            skip_space();
-            if (p < end && *p == '}') {
-                ++p;
-                return j;
-            }
-            for (;;) {
-                skip_space();
-                if (p >= end || *p != '"') {
-                    fail("a member name was expected");
-                }
-                std::string key = string_body();
-                skip_space();
-                if (p >= end || *p != ':') {
-                    fail("':' was expected");
-                }
-                ++p;
-                j.members.emplace_back(std::move(key), value(depth + 1));
-                skip_space();
-                if (p < end && *p == ',') {
-                    ++p;
-                    continue;
-                }
-                if (p < end && *p == '}') {
-                    ++p;
-                    return j;
-                }
-                fail("',' or '}' was expected");
-            }
-        }
-        if (*p == '[') {
-            ++p;
-            j.kind = Json::kArray;
-            skip_space();
-            if (p < end && *p == ']') {
-                ++p;
-                return j;
-            }
-            for (;;) {
-                j.items.push_back(value(depth + 1));
-                skip_space();
-                if (p < end && *p == ',') {
-                    ++p;
-                    continue;
-                }
-                if (p < end && *p == ']') {
-                    ++p;
-                    return j;
-                }
-                fail("',' or ']' was expected");
-            }
-        }
-        if (*p == '"') {
-            j.kind = Json::kString;
-            j.str = string_body();
-            return j;
-        }
-        if (literal("true")) {
-            j.kind = Json::kBool;
-            j.boolean = true;
-            return j;
-        }
-        if (literal("false")) {
-            j.kind = Json::kBool;
-            return j;
-        }
-        if (literal("null")) {
-            return j;
-        }
-        return number();
-    }
-};
+// .crts (util/scene.cpp:417-625); its header is JSON (json_reader.h)
+using crt_json::Json;
+using crt_json::JsonParser;
 
 // dtype_stride(parse_dtype(name)) (util/gltf_types.cpp:144-215, :431-505): "<SHAPE>_<COMPONENT>" or a scalar's long name
 size_t crts_dtype_stride(const std::string &name)

@@ -1,5 +1,5 @@
 // fuzz_scene_io.cpp — TEST INFRASTRUCTURE: mutation fuzzing of the native scene loaders and texture decoders
-// (chameleonrt_b200/csrc/scene_io.cpp, jpeg_decode.h) under AddressSanitizer + UndefinedBehaviorSanitizer. Every seed file is
+// (chameleonrt_b200/csrc/scene_io.cpp, image_decode.h, jpeg_decode.h, json_reader.h) under AddressSanitizer + UndefinedBehaviorSanitizer. Every seed file is
 // mutated (random bytes, bit flips, truncation, "interesting" bytes) and loaded; a load may succeed or throw, but must not
 // touch memory it does not own or run into undefined behaviour. Built and driven by tests/test_scene_io_fuzz.py:
 //     fuzz_scene_io <seed dir> <work dir> <iterations per seed>
