@@ -454,24 +454,40 @@ void load_mtl(const std::string &path, std::vector<Material> &materials, std::ma
             continue;
         }
         if (n >= 7 && std::memcmp(tok, "map_Kd", 6) == 0 && is_blank(tok[6])) {
-            // ParseTextureNameAndOption (:906-1011): options start with '-', the texture name is the remaining token
+            // ParseTextureNameAndOption (:906-985): options with their arguments, then the name = the rest of the line (it may
+            // hold blanks)
             tok += 7;
             std::string name;
+            static const struct {
+                const char *flag;
+                int args;
+            } options[] = {{"-blendu", 1}, {"-blendv", 1}, {"-clamp", 1}, {"-boost", 1}, {"-bm", 1}, {"-o", 3}, {"-s", 3}, {"-t", 3},
+                           {"-type", 1}, {"-imfchan", 1}, {"-mm", 2}, {"-colorspace", 1}};
             while (tok < end) {
                 while (tok < end && is_blank(*tok)) {
                     ++tok;
                 }
-                const char *e = tok;
-                while (e < end && !is_blank(*e)) {
-                    ++e;
-                }
-                if (tok < e) {
-                    if (*tok == '-') {
-                        throw std::runtime_error("map_Kd with texture options is not supported by this loader: " + linebuf);
+                bool is_option = false;
+                for (const auto &o : options) {
+                    const size_t len = std::strlen(o.flag);
+                    if ((size_t)(end - tok) > len && std::memcmp(tok, o.flag, len) == 0 && is_blank(tok[len])) {
+                        tok += len;
+                        for (int a = 0; a < o.args; ++a) {  // each argument: blanks, then a run of non-blanks (none at the line end)
+                            while (tok < end && is_blank(*tok)) {
+                                ++tok;
+                            }
+                            while (tok < end && !is_blank(*tok)) {
+                                ++tok;
+                            }
+                        }
+                        is_option = true;
+                        break;
                     }
-                    name = std::string(tok, e);
                 }
-                tok = e;
+                if (!is_option) {
+                    name = std::string(tok, end);
+                    break;
+                }
             }
             material.diffuse_texname = name;
             continue;

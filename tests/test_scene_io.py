@@ -1091,3 +1091,26 @@ def test_native_loader_behind_the_references_scene_type(built, tmp_path):
             shim = _reference_arrays(path, white, lib_path=NATIVE_SHIM_LIB)
             _assert_same(shim, ref)
             assert shim["texture_names"] == ref["texture_names"], path
+
+
+@needs_ref
+def test_native_obj_loader_texture_statements(built, tmp_path):
+    """map_Kd as tinyobjloader's ParseTextureNameAndOption reads it: texture options with their arguments in front of the name, a
+    file name with blanks in it (the name is the rest of the line), the same file named by two materials (one texture), a
+    backslash path (canonicalize_path)."""
+    pytest.importorskip("PIL")
+    from PIL import Image as PILImage
+
+    rng = np.random.default_rng(2)
+    (tmp_path / "sub").mkdir()
+    for name in ("plain.png", "with blank.png", "sub/deep.png"):
+        PILImage.fromarray(rng.integers(0, 256, (6, 9, 3)).astype(np.uint8)).save(str(tmp_path / name))
+    (tmp_path / "m.mtl").write_text("newmtl a\nKd 1 1 1\nmap_Kd -blendu on -s 2 2 1 -o 0.5 0 0 -mm 0 1 -bm 0.3 -clamp off plain.png\n"
+                                    "newmtl b\nmap_Kd with blank.png  \nnewmtl c\nmap_Kd   sub\\deep.png\r\nnewmtl d\nmap_Kd -colorspace sRGB plain.png\n"
+                                    "newmtl e\nmap_Kd -imfchan r -type sphere -boost 2 -t 1 1 1 with blank.png\n")
+    (tmp_path / "m.obj").write_text("mtllib m.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\n" +
+                                    "".join(f"g g{k}\nusemtl {k}\nf 1/1 2/2 3/3\n" for k in "abcde"))
+    ref = _reference_arrays(str(tmp_path / "m.obj"))
+    nat, _ = _native_arrays(str(tmp_path / "m.obj"))
+    _assert_same(nat, ref)
+    assert nat["counts"][4] == 5 and nat["counts"][5] == 3
