@@ -1114,3 +1114,136 @@ def test_native_obj_loader_texture_statements(built, tmp_path):
     nat, _ = _native_arrays(str(tmp_path / "m.obj"))
     _assert_same(nat, ref)
     assert nat["counts"][4] == 5 and nat["counts"][5] == 3
+
+
+def _random_obj_text(rng, nfaces=30):
+    """A random OBJ file in the spelling real exporters and hand-edited files use: blanks and tabs in any amount, CRLF or LF,
+    numbers as fixed / exponent / integer / leading-dot / trailing-dot, positions with 2 to 6 components (w, vertex colours),
+    texture coordinates with 1 to 3, absolute and relative indices, v / v/t / v//n / v/t/n corners, faces of 3 to 5 corners,
+    g (several names) / o / s / usemtl / mtllib statements anywhere, statements the loaders ignore, comments, empty lines."""
+    lines=[]
+    nv=nvt=nvn=0
+    def ws(): return rng.choice([" ", "  ", "\t", " \t "])
+    def num():
+        k=rng.integers(0,8)
+        x=rng.normal()*10.0**int(rng.integers(-3,4))
+        if k==0: return f"{x:.6f}"
+        if k==1: return f"{x:.3e}"
+        if k==2: return f"{int(x)}"
+        if k==3: return f"{x:+.4f}"
+        if k==4: return f"{x:.10g}"
+        if k==5: return f"{x:.2E}"
+        if k==6: return f".{rng.integers(0,1000)}"
+        return f"{int(x)}."
+    if rng.integers(0,2): lines.append("mtllib"+ws()+"fz.mtl")
+    mats=["red","green","blue shade","nomat"]
+    file_vt=rng.integers(0,2)
+    for f in range(nfaces):
+        r=rng.integers(0,20)
+        if r==0: lines.append("# comment "+num())
+        if r==1: lines.append("")
+        if r==2: lines.append("g"+ws()+" ".join(rng.choice(["a","b","c_d","e1"], rng.integers(1,3))))
+        if r==3: lines.append("o"+ws()+"obj"+str(f))
+        if r==4: lines.append("usemtl"+ws()+str(rng.choice(mats)))
+        if r==5: lines.append("s"+ws()+str(rng.choice(["off","1","0","3"])))
+        if r==6: lines.append(rng.choice(["vp 0.1 0.2","l 1 2","p 1","mg 1 0.5","cstype bezier","g"]))
+        if r==7: lines.append("usemtl"+ws()+str(rng.choice(mats))+("  " if rng.integers(0,2) else ""))
+        n=int(rng.integers(3,6)) if rng.integers(0,4)==0 else 3
+        for k in range(n):
+            comps=[num() for _ in range(int(rng.choice([3,3,3,4,6,2])))]
+            lines.append((ws() if rng.integers(0,6)==0 else "")+"v"+ws()+ws().join(comps)); nv+=1
+        has_vt=file_vt; has_vn=rng.integers(0,2)
+        if has_vt:
+            for k in range(n):
+                lines.append("vt"+ws()+ws().join(num() for _ in range(int(rng.choice([2,2,3,1]))))); nvt+=1
+        if has_vn:
+            for k in range(n):
+                lines.append("vn"+ws()+ws().join(num() for _ in range(3))); nvn+=1
+        corners=[]
+        rel=rng.integers(0,2)
+        for k in range(n):
+            v = (k-n) if rel else nv-n+k+1
+            vt= (k-n) if rel else nvt-n+k+1
+            vn= (k-n) if rel else nvn-n+k+1
+            if has_vt and has_vn: c=f"{v}/{vt}/{vn}"
+            elif has_vt: c=f"{v}/{vt}"
+            elif has_vn: c=f"{v}//{vn}"
+            else: c=f"{v}"
+            corners.append(c)
+        lines.append("f"+ws()+ws().join(corners)+(ws() if rng.integers(0,4)==0 else ""))
+    eol = "\r\n" if rng.integers(0,3)==0 else "\n"
+    text=eol.join(lines)+(eol if rng.integers(0,4) else "")
+    return text
+
+
+@needs_ref
+def test_native_obj_loader_differential_fuzz(built, tmp_path):
+    """Random OBJ files through both loaders: the same Scene, array for array, or an error from both. (One spelling is left
+    out: a `g` statement followed only by blanks — the reference's loader crashes on it, this one reads an unnamed group.)"""
+    (tmp_path / "fz.mtl").write_text("newmtl red\nKd 0.8 0.1 0.1\nNs 200\nnewmtl green\n  Kd 0.1 .8 1e-1\nNs 5e2\n\nnewmtl blue shade\nKd 0 0 1\nd 0.5\n"
+                                     "illum 2\nKa 1 1 1\n")
+    lib = _ref()
+    path = str(tmp_path / "f.obj")
+    loaded_ok = 0
+    for seed in range(int(os.environ.get("CRT_OBJ_FUZZ_FILES", "60"))):
+        rng = np.random.default_rng(seed)
+        with open(path, "w", newline="") as f:
+            f.write(_random_obj_text(rng, int(rng.integers(1, 40))))
+        h = lib.refscene_load_mode(path.encode(), 0, None)
+        if h:
+            lib.refscene_free(h)
+        try:
+            nat, _ = _native_arrays(path, threads=1 + seed % 3)
+        except RuntimeError:
+            nat = None
+        assert (nat is None) == (not h), f"seed {seed}: one loader accepts the file, the other does not"
+        if nat is not None:
+            _assert_same(nat, _reference_arrays(path))
+            loaded_ok += 1
+    assert loaded_ok >= 40
+
+
+@needs_ref
+def test_native_mtl_reader_differential_fuzz(built, tmp_path):
+    """Random material files through both loaders: statements in any spelling (Kd with 1 to 4 numbers, Ns, map_Kd with and
+    without options and with blanks in the name, indented statements, comments, statements that do not matter, look-alikes such
+    as Kdx / map_Kdx), material names with blanks and trailing blanks, names defined twice (the first definition is the one a
+    usemtl finds), a usemtl of a name no file defines. (`Tr` next to `d` is left out: the reference's reader crashes on it.)"""
+    pytest.importorskip("PIL")
+    from PIL import Image as PILImage
+
+    for n in ("a.png", "b c.png"):
+        PILImage.fromarray(np.random.default_rng(1).integers(0, 256, (4, 4, 3)).astype(np.uint8)).save(str(tmp_path / n))
+
+    def ws(rng):
+        return str(rng.choice([" ", "  ", "\t", " \t "]))
+
+    def num(rng):
+        x = rng.normal() * 10.0 ** int(rng.integers(-2, 4))
+        return [f"{x:.4f}", f"{x:.2e}", f"{int(x)}", f"{abs(x):.3f}", f".{rng.integers(0, 99)}"][rng.integers(0, 5)]
+
+    ignored = ["Ka 1 1 1", "Ks 0.5 0.5 0.5", "d 0.5", "illum 2", "Ni 1.5", "map_Bump a.png", "Ke 1 1 1", "Pr 0.5", "Kdx 1 1 1", "map_Kdx a.png", "Nsx 1"]
+    path = str(tmp_path / "f.obj")
+    for seed in range(int(os.environ.get("CRT_MTL_FUZZ_FILES", "80"))):
+        rng = np.random.default_rng(seed)
+        lines, names = [], []
+        for _ in range(int(rng.integers(1, 6))):
+            names.append(str(rng.choice(["red", "green", "blue shade", "x", "red"])))
+            lines.append((ws(rng) if rng.integers(0, 4) == 0 else "") + "newmtl" + ws(rng) + names[-1] + ("  " if rng.integers(0, 3) == 0 else ""))
+            for _ in range(int(rng.integers(0, 7))):
+                r = rng.integers(0, 12)
+                if r == 0:
+                    lines.append("Kd" + ws(rng) + ws(rng).join(num(rng) for _ in range(int(rng.choice([3, 3, 1, 2, 4])))))
+                elif r == 1:
+                    lines.append("Ns" + ws(rng) + num(rng))
+                elif r == 2:
+                    lines.append("map_Kd" + ws(rng) + str(rng.choice(["a.png", "b c.png", "-s 1 1 1 a.png", "-clamp on b c.png"])))
+                elif r == 3:
+                    lines.append(str(rng.choice(["# c", "", "\tKd 0.5 0.25 0.125"])))
+                elif r == 4:
+                    lines.append(str(rng.choice(ignored)))
+        (tmp_path / "f.mtl").write_text("\n".join(lines) + ("\n" if rng.integers(0, 3) else ""))
+        (tmp_path / "f.obj").write_text("mtllib f.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\n" +
+                                        "".join(f"g g{i}\nusemtl {n}\nf 1/1 2/2 3/3\n" for i, n in enumerate(names + ["zzz"])))
+        nat, _ = _native_arrays(path)
+        _assert_same(nat, _reference_arrays(path))
