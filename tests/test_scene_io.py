@@ -1247,3 +1247,112 @@ def test_native_mtl_reader_differential_fuzz(built, tmp_path):
                                         "".join(f"g g{i}\nusemtl {n}\nf 1/1 2/2 3/3\n" for i, n in enumerate(names + ["zzz"])))
         nat, _ = _native_arrays(path)
         _assert_same(nat, _reference_arrays(path))
+
+
+def _random_gltf(rng, d):
+    """A random glTF 2.0 scene: 1-3 meshes of 1-3 primitives (interleaved / packed / offset accessors, 16- or 32-bit indices whose
+    count need not be a multiple of three, with and without uvs and materials), up to 8 nodes in a random forest with matrix,
+    T / R / S (any subset; quaternions not always normalised, negative scales) or both, camera nodes, one or two scenes, written
+    as .gltf + .bin, as .gltf with a data: URI, or as .glb."""
+    import base64
+    import json
+    import struct
+
+    blob=bytearray(); views=[]; accessors=[]
+    def add_view(raw, stride=None, align=4):
+        while len(blob)%align: blob.append(0)
+        v={"buffer":0,"byteOffset":len(blob),"byteLength":len(raw)}
+        if stride: v["byteStride"]=stride
+        if rng.integers(0,3)==0: v["target"]=34962
+        views.append(v); blob.extend(raw); return len(views)-1
+    def acc(view,comp,typ,count,offset=0):
+        a={"bufferView":view,"componentType":comp,"count":count,"type":typ}
+        if offset or rng.integers(0,4)==0: a["byteOffset"]=offset
+        accessors.append(a); return len(accessors)-1
+    meshes=[]
+    for m in range(int(rng.integers(1,4))):
+        prims=[]
+        for p in range(int(rng.integers(1,4))):
+            n=int(rng.integers(3,12)); ntri=int(rng.integers(1,8))
+            pos=rng.normal(size=(n,3)).astype(np.float32); uv=rng.uniform(size=(n,2)).astype(np.float32)
+            idx=rng.integers(0,n,ntri*3+int(rng.integers(0,3)))
+            layout=int(rng.integers(0,3)); attrs={}
+            has_uv=bool(rng.integers(0,2))
+            if layout==0:  # interleaved
+                stride=int(rng.choice([20,24,32]))
+                inter=np.zeros((n,stride//4),np.float32); inter[:,0:3]=pos; inter[:,3:5]=uv
+                v=add_view(inter.tobytes(),stride)
+                attrs["POSITION"]=acc(v,5126,"VEC3",n)
+                if has_uv: attrs["TEXCOORD_0"]=acc(v,5126,"VEC2",n,12)
+            elif layout==1:  # packed separate
+                attrs["POSITION"]=acc(add_view(pos.tobytes()),5126,"VEC3",n)
+                if has_uv: attrs["TEXCOORD_0"]=acc(add_view(uv.tobytes()),5126,"VEC2",n)
+            else:  # one view, accessor offsets, possibly misaligned start (2 mod 4 is not allowed by gltf but tinygltf reads it)
+                pad=int(rng.choice([0,4,8]))
+                v=add_view(bytes(pad)+pos.tobytes()+uv.tobytes())
+                attrs["POSITION"]=acc(v,5126,"VEC3",n,pad)
+                if has_uv: attrs["TEXCOORD_0"]=acc(v,5126,"VEC2",n,pad+12*n)
+            if rng.integers(0,2):
+                ia=acc(add_view(idx.astype(np.uint16).tobytes(),align=2),5123,"SCALAR",len(idx))
+            else:
+                ia=acc(add_view(idx.astype(np.uint32).tobytes()),5125,"SCALAR",len(idx))
+            prim={"attributes":attrs,"indices":ia}
+            if rng.integers(0,3): prim["material"]=int(rng.integers(0,3))
+            if rng.integers(0,3)==0: prim["mode"]=4
+            prims.append(prim)
+        meshes.append({"primitives":prims})
+    def quat():
+        q=rng.normal(size=4)
+        if rng.integers(0,3): q=q/np.linalg.norm(q)
+        return [float(x) for x in q]
+    nn=int(rng.integers(1,9)); nodes=[]
+    for i in range(nn):
+        node={}
+        if rng.integers(0,4): node["mesh"]=int(rng.integers(0,len(meshes)))
+        k=rng.integers(0,5)
+        if k==0: node["matrix"]=_rotated(int(rng.integers(0,1000)))
+        if k in (1,2):
+            if rng.integers(0,2): node["translation"]=[float(x) for x in rng.normal(size=3)]
+            if rng.integers(0,2): node["rotation"]=quat()
+            if rng.integers(0,2): node["scale"]=[float(x) for x in rng.uniform(-2,2,3)]
+        if k==3: node["matrix"]=_rotated(int(rng.integers(0,1000))); node["translation"]=[1.0,2.0,3.0]
+        if rng.integers(0,5)==0: node["camera"]=0
+        nodes.append(node)
+    # children: node i may have children among later nodes (tree)
+    parent={}
+    roots=[]
+    for i in range(nn):
+        if i>0 and rng.integers(0,2):
+            par=int(rng.integers(0,i)); nodes[par].setdefault("children",[]).append(i); parent[i]=par
+        else: roots.append(i)
+    scenes=[{"nodes":roots}]
+    doc={"asset":{"version":"2.0"},"scenes":scenes,"nodes":nodes,"meshes":meshes,"accessors":accessors,"bufferViews":views,
+         "cameras":[{"type":"perspective","perspective":{"yfov":0.8,"znear":0.1}}],
+         "materials":[{"pbrMetallicRoughness":{"baseColorFactor":[float(x) for x in rng.uniform(size=4)],"metallicFactor":float(rng.uniform())}},
+                      {"pbrMetallicRoughness":{"roughnessFactor":float(rng.uniform())}}, {}]}
+    if rng.integers(0,2): doc["scene"]=0
+    if rng.integers(0,3)==0:
+        doc["scenes"].insert(0,{"nodes":[roots[0]]}); doc["scene"]=1
+    kind=int(rng.integers(0,3))
+    if kind==0:
+        open(f'{d}/s.bin','wb').write(bytes(blob)); doc["buffers"]=[{"uri":"s.bin","byteLength":len(blob)}]
+        p=f'{d}/s.gltf'; open(p,'w').write(json.dumps(doc)); return p
+    if kind==1:
+        doc["buffers"]=[{"uri":"data:application/octet-stream;base64,"+base64.b64encode(bytes(blob)).decode(),"byteLength":len(blob)}]
+        p=f'{d}/s.gltf'; open(p,'w').write(json.dumps(doc, indent=int(rng.integers(0,3)) or None)); return p
+    doc["buffers"]=[{"byteLength":len(blob)}]
+    js=json.dumps(doc).encode(); js+=b" "*(-len(js)%4)
+    while len(blob)%4: blob.append(0)
+    p=f'{d}/s.glb'
+    open(p,'wb').write(struct.pack("<4sII",b"glTF",2,12+8+len(js)+8+len(blob))+struct.pack("<II",len(js),0x4E4F534A)+js+struct.pack("<II",len(blob),0x004E4942)+bytes(blob))
+    return p
+
+
+@needs_ref
+def test_native_gltf_loader_differential_fuzz(built, tmp_path):
+    """Random glTF scenes through both loaders: the same Scene — geometry arrays, parameterized meshes, materials and, above
+    all, the instance transforms the flattening of the node hierarchy computes in float."""
+    for seed in range(int(os.environ.get("CRT_GLTF_FUZZ_FILES", "60"))):
+        path = _random_gltf(np.random.default_rng(seed), str(tmp_path))
+        nat, _ = _native_arrays(path, threads=1 + seed % 2)
+        _assert_same(nat, _reference_arrays(path))
