@@ -1,0 +1,71 @@
+"""The kernels and the renderer under AddressSanitizer + UndefinedBehaviorSanitizer (or ThreadSanitizer), on the CPU SIMT emulation
+(tests/simt_emu: every CUDA thread an OS thread, shared memory and atomics real): a sanitized build of the emulated core renders a
+few small frames through the C ABI with every option that changes the kernel chain. An out-of-bounds access to a queue, a
+shared-memory array or a scene buffer, a signed overflow or a misaligned access in kernel code stops the run with a report.
+What compute-sanitizer would check on the device, checked where no GPU is available.
+
+    python scripts/simt_sanitize.py [--tsan]
+"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def build(tsan: bool) -> str:
+    from simt_emu import build as simt_build
+
+    simt_build.build()  # (generates the translated sources under tests/simt_emu/_build)
+    out = os.path.join(simt_build.OUT, "libcrt_cuda_core_simt_tsan.so" if tsan else "libcrt_cuda_core_simt_asan.so")
+    csrc = simt_build.CSRC
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"))), "include")
+    san = ["-fsanitize=thread"] if tsan else ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"]
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-pthread", "-march=x86-64-v3", "-ffp-contract=off", "-Wno-attributes",
+                           "-fno-omit-frame-pointer"] + san + ["-I" + csrc, "-I" + cuda_inc, "-I" + os.path.join(ROOT, "include"), "-shared",
+                           "-Wl,-Bsymbolic", "-o", out, os.path.join(simt_build.OUT, "crt_cuda_core_simt.cpp"),
+                           os.path.join(simt_build.HERE, "cuda_emu.cpp"), os.path.join(csrc, "host_scene.cpp"), os.path.join(csrc, "bvh8_build.cpp")])
+    return out
+
+
+def render_all(lib: str):
+    import numpy as np
+
+    from chameleonrt_b200 import ArcballCamera, backend
+    from chameleonrt_b200.scenes import cornell_box, sponza_like
+    from helpers import synthetic_material_scene
+
+    backend._LIB_PATH, backend._lib = lib, None
+    cases = [("cornell", cornell_box(spp=1), {}), ("materials", synthetic_material_scene(spp=1), {}),
+             ("sponza, device PLOC build, shade_sort", sponza_like(spp=1, detail=0.15, tex_size=16), {"bvh_builder": 1, "shade_sort": 2}),
+             ("sponza, LBVH, far-first, no defer, top-of-tree in shared memory", sponza_like(spp=1, detail=0.15, tex_size=16),
+              {"bvh_builder": 2, "any_far_first": 1, "tri_pass_defer": 0, "bvh_top_smem": 1}),
+             ("cornell, tile shard 1 of 2 (130 x 70: six tiles)", cornell_box(spp=1), {"world_size": 2, "rank": 1, "size": (130, 70)})]
+    for name, (scene, cam), options in cases:
+        r = backend.RenderCUDA(0, max_depth=4)
+        size = options.pop("size", (40, 24))
+        for k, v in options.items():
+            r.set_option(k, v)
+        r.initialize(*size)
+        r.set_scene(scene)
+        c = ArcballCamera(cam["eye"], cam["center"], cam["up"])
+        for f in range(2):
+            st = r.render(c.eye(), c.dir(), c.up(), cam["fov_y"], f == 0, True)
+        a = r.read_accum()
+        assert np.isfinite(a).all() and st.num_rays > 0  # (the materials scene has one pixel at -1.7e9: the reference's own value)
+        print(f"{name}: {st.num_rays} rays, mean {float(a.mean()):.4f}", flush=True)
+        del r
+
+
+if __name__ == "__main__":
+    tsan = "--tsan" in sys.argv
+    if os.environ.get("CRT_SANITIZED_CHILD") != "1":
+        lib = build(tsan)
+        runtime = subprocess.check_output(["g++", "-print-file-name=" + ("libtsan.so" if tsan else "libasan.so")], text=True).strip()
+        env = dict(os.environ, CRT_SANITIZED_CHILD="1", CRT_SANITIZED_LIB=lib, LD_PRELOAD=runtime,
+                   ASAN_OPTIONS="detect_leaks=0:abort_on_error=0:halt_on_error=1", TSAN_OPTIONS="halt_on_error=0:report_signal_unsafe=0")
+        sys.exit(subprocess.call([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env))
+    render_all(os.environ["CRT_SANITIZED_LIB"])
+    print("sanitized run finished")
