@@ -57,6 +57,41 @@ def render_all(lib: str):
         assert np.isfinite(a).all() and st.num_rays > 0  # (the materials scene has one pixel at -1.7e9: the reference's own value)
         print(f"{name}: {st.num_rays} rays, mean {float(a.mean()):.4f}", flush=True)
         del r
+    # frames in flight, the instrumented traversal kernels, stage events off, a resize, the traversal API
+    scene, cam = cornell_box(spp=2)
+    c = ArcballCamera(cam["eye"], cam["center"], cam["up"])
+    args = (c.eye(), c.dir(), c.up(), cam["fov_y"])
+    r = backend.RenderCUDA(0, max_depth=3)
+    r.set_option("count_traversal", 1)
+    r.set_option("stage_events", 0)
+    r.initialize(33, 17)
+    r.set_scene(scene)
+    r.render_async(*args, True, 3)
+    r.sync()
+    r.initialize(70, 66)
+    r.set_scene(scene)
+    r.render(*args, True, True)
+    from oracle.oracle import primary_rays
+
+    rays = primary_rays(16, 12, c.eye(), c.dir(), c.up(), cam["fov_y"])
+    hits = r.trace_closest(rays)
+    occluded = r.trace_any(rays)
+    print(f"async + counting + resize + traversal API: {r.counters()['closest_nodes_visited']} nodes visited, "
+          f"{int(np.isfinite(hits[:, 0]).sum())} of {len(rays)} primary rays hit, {int(occluded.sum())} occluded", flush=True)
+    # two renderers of one process sharing rank 0's frame (peer stores + completion flags)
+    ranks = [backend.RenderCUDA(0, max_depth=3, rank=k, world_size=2) for k in range(2)]
+    for rr in ranks:
+        rr.initialize(130, 70)
+        rr.set_scene(scene)
+    ranks[1].import_frame(ranks[0].export_frame())
+    for rr in ranks:  # (kernels run synchronously here: the order tests/test_simt_renderer.py uses)
+        rr.render_async(*args, True, 2)
+        rr.render_async(*args, False, 1)
+        rr.sync()
+    full = ranks[0].read_accum()
+    lit = (full.reshape(-1, 3).sum(axis=1) > 0).reshape(full.shape[0], full.shape[1])
+    assert np.isfinite(full).all() and lit[:, :64].mean() > 0.5 and lit[:, 64:128].mean() > 0.5  # tiles of both ranks arrived
+    print(f"shared frame of two renderers: mean {float(full.mean()):.4f}, lit {lit.mean():.2f}", flush=True)
 
 
 if __name__ == "__main__":
