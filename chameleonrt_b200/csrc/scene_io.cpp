@@ -1948,6 +1948,10 @@ void load_gltf_impl(const std::string &file, int threads, crtio_scene &S)
     crt::parallel_blocks((uint32_t)num_images, nthreads, [&](uint32_t i) {
         try {
             int w = 0, h = 0;
+            // (tinygltf keeps the 16 bits of a 16-bit PNG, and Scene::load_gltf refuses such an image: scene.cpp:335-338)
+            if (encoded[i].size > 24 && std::memcmp(encoded[i].data, "\x89PNG", 4) == 0 && encoded[i].data[24] == 16) {
+                throw std::runtime_error("Unsupported image pixel type");
+            }
             decode_image_rgba(encoded[i].data, encoded[i].size, image_names[i], S.texture_data[i], w, h, false);
             S.textures[i].data = S.texture_data[i].data();
             S.textures[i].width = w;

@@ -721,6 +721,9 @@ def test_native_gltf_loader_errors(built, tmp_path):
         scene_io.load_gltf(write("jpeg.gltf", broken(images=[{"uri": "data:image/jpeg;base64,/9j/4AAQSkZJRgABAQAAAQABAAD/2wBDAAgGBgcGBQgHBwcJCQgKDBQNDAsLDBkSEw8UHRofHh0a"}])))
     with pytest.raises(RuntimeError, match="exactly one of"):
         scene_io.load_gltf(write("img.gltf", broken(images=[{"name": "nothing"}])))
+    _write_png(str(tmp_path / "deep.png"), np.random.default_rng(0).integers(0, 65536, (4, 4, 3)), 2, 16)
+    with pytest.raises(RuntimeError, match="Unsupported image pixel type"):  # (as Scene::load_gltf, scene.cpp:335-338)
+        scene_io.load_gltf(write("deep.gltf", broken(images=[{"uri": "deep.png"}])))
 
 
 def test_native_gltf_loader_round_trip_and_oracle_frame(built, tmp_path):
