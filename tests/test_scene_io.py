@@ -1359,3 +1359,67 @@ def test_native_gltf_loader_differential_fuzz(built, tmp_path):
         path = _random_gltf(np.random.default_rng(seed), str(tmp_path))
         nat, _ = _native_arrays(path, threads=1 + seed % 2)
         _assert_same(nat, _reference_arrays(path))
+
+
+_CRTS_PARAMS = ["metallic","specular","roughness","specular_tint","anisotropic","sheen","sheen_tint","clearcoat","clearcoat_roughness","ior","transmission"]
+def _crts_number_text(rng):
+    k=rng.integers(0,9); x=rng.normal()*10.0**int(rng.integers(-3,4))
+    return [f"{x:.6f}",f"{x:.3e}",f"{int(x)}",f"{x:.17g}",f"{abs(int(x))}",f"{x:.2E}","0","-0.0","1e-40"][k]
+def _random_crts(rng, d):
+    """A random .crts file: 1-3 meshes (indices typed VEC3_U32 or UINT_32, with and without texcoords), 0-2 embedded PNG images,
+    0-3 materials with numbers in every JSON spelling (fixed, exponent, integer, 17 digits, -0.0, a float32 denormal) and random
+    texture handles, 1-7 MESH / LIGHT / CAMERA objects with arbitrary matrices, a padded or unpadded header."""
+    import json
+    import re
+    import struct
+
+    blob=bytearray(); views=[]
+    def view(raw,typ,align=8):
+        while len(blob)%align: blob.append(0)
+        views.append({"byte_offset":len(blob),"byte_length":len(raw),"type":typ}); blob.extend(raw); return len(views)-1
+    meshes=[]
+    for m in range(int(rng.integers(1,4))):
+        n=int(rng.integers(3,10)); nt=int(rng.integers(1,6))
+        e={"positions":view(rng.normal(size=(n,3)).astype(np.float32).tobytes(),"VEC3_F32"),
+           "indices":view(rng.integers(0,n,(nt,3)).astype(np.uint32).tobytes(), str(rng.choice(["VEC3_U32","UINT_32"])))}
+        if rng.integers(0,2): e["texcoords"]=view(rng.uniform(size=(n,2)).astype(np.float32).tobytes(),"VEC2_F32")
+        meshes.append(e)
+    images=[]
+    for i in range(int(rng.integers(0,3))):
+        png=_png_bytes(rng.integers(0,256,(int(rng.integers(1,6)),int(rng.integers(1,6)),int(rng.choice([1,3,4])))).astype(np.uint8))
+        images.append({"name":f"img {i}","view":view(png,"UINT_8",align=1),"color_space":str(rng.choice(["SRGB","LINEAR","srgb"]))})
+    nmat=int(rng.integers(0,4)); mats=[]
+    for i in range(nmat):
+        jm={"base_color":"@[%s, %s, %s]"%(_crts_number_text(rng),_crts_number_text(rng),_crts_number_text(rng))}
+        if images and rng.integers(0,2): jm["base_color_texture"]=int(rng.integers(0,len(images)))
+        for pn in _CRTS_PARAMS:
+            jm[pn]="@"+_crts_number_text(rng)
+            if images and rng.integers(0,5)==0: jm[pn+"_texture"]={"texture":int(rng.integers(0,len(images))),"channel":int(rng.integers(0,4))}
+        mats.append(jm)
+    objs=[]
+    for i in range(int(rng.integers(1,8))):
+        k=rng.integers(0,6)
+        mat="@["+", ".join(_crts_number_text(rng) for _ in range(16))+"]"
+        if k<4: objs.append({"type":"MESH","mesh":int(rng.integers(0,len(meshes))),"material":int(rng.integers(0,nmat)) if nmat and rng.integers(0,4) else 4294967295,"matrix":mat})
+        elif k==4: objs.append({"type":"LIGHT","color":"@[%s, %s, %s]"%(_crts_number_text(rng),_crts_number_text(rng),_crts_number_text(rng)),"energy":"@"+_crts_number_text(rng),"size":"@[%s, %s]"%(_crts_number_text(rng),_crts_number_text(rng)),"matrix":mat})
+        else: objs.append({"type":"CAMERA","fov_y":"@"+_crts_number_text(rng),"matrix":mat})
+    hdr={"meshes":meshes,"images":images,"materials":mats,"objects":objs,"buffer_views":views}
+    js=json.dumps(hdr, indent=int(rng.integers(0,3)) or None)
+    # "@..." strings become raw number text
+    js = re.sub(r'"@([^"]*)"', lambda m: m.group(1), js)
+    js=js.encode()
+    if rng.integers(0,2): js+=b" "*((-(len(js)+8))%8)
+    p=f'{d}/s.crts'
+    open(p,'wb').write(struct.pack("<Q",len(js))+js+bytes(blob))
+    return p
+
+
+@needs_ref
+def test_native_crts_loader_differential_fuzz(built, tmp_path):
+    """Random .crts files through both loaders: the same Scene (numbers through the JSON reader and the float casts, material
+    handles, (mesh, material) pairs, light and camera frames)."""
+    pytest.importorskip("PIL")
+    for seed in range(int(os.environ.get("CRT_CRTS_FUZZ_FILES", "60"))):
+        path = _random_crts(np.random.default_rng(seed), str(tmp_path))
+        nat, _ = _native_arrays(path)
+        _assert_same(nat, _reference_arrays(path))
