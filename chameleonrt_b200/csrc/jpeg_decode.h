@@ -19,6 +19,10 @@
 // samples and arithmetic coding are errors (the latter two are errors in stb_image as well).
 #pragma once
 
+#ifdef __AVX2__
+#include <immintrin.h>
+#endif
+
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
@@ -174,6 +178,26 @@ inline void idct_dc_only(uint8_t *out, size_t out_stride, short dc)
 // arithmetic shifts lane by lane — the values are the scalar version's (the all-zero-column shortcut of the scalar code
 // computes the same numbers as the full pass: (d0 * 4096 + 512) >> 10 == d0 * 4).
 
+#ifdef __AVX2__
+inline void transpose8(v8i r[8])  // (written with intrinsics: the compiler turns the generic shuffles below into ~5x as many instructions)
+{
+    __m256i t[8], u[8];
+    for (int k = 0; k < 4; ++k) {
+        t[2 * k] = _mm256_unpacklo_epi32((__m256i)r[2 * k], (__m256i)r[2 * k + 1]);
+        t[2 * k + 1] = _mm256_unpackhi_epi32((__m256i)r[2 * k], (__m256i)r[2 * k + 1]);
+    }
+    for (int k = 0; k < 2; ++k) {
+        u[4 * k] = _mm256_unpacklo_epi64(t[4 * k], t[4 * k + 2]);
+        u[4 * k + 1] = _mm256_unpackhi_epi64(t[4 * k], t[4 * k + 2]);
+        u[4 * k + 2] = _mm256_unpacklo_epi64(t[4 * k + 1], t[4 * k + 3]);
+        u[4 * k + 3] = _mm256_unpackhi_epi64(t[4 * k + 1], t[4 * k + 3]);
+    }
+    for (int k = 0; k < 4; ++k) {
+        r[k] = (v8i)_mm256_permute2x128_si256(u[k], u[k + 4], 0x20);
+        r[k + 4] = (v8i)_mm256_permute2x128_si256(u[k], u[k + 4], 0x31);
+    }
+}
+#else
 inline void transpose8(v8i r[8])
 {
     const v8i lo32 = {0, 8, 1, 9, 4, 12, 5, 13}, hi32 = {2, 10, 3, 11, 6, 14, 7, 15};
@@ -195,6 +219,7 @@ inline void transpose8(v8i r[8])
         r[k + 4] = __builtin_shuffle(u[k], u[k + 4], hi128);
     }
 }
+#endif
 
 inline void idct_block(uint8_t *out, size_t out_stride, const short d[64])
 {
@@ -208,14 +233,20 @@ inline void idct_block(uint8_t *out, size_t out_stride, const short d[64])
     transpose8(v);  // v[c]: column c of the intermediate, one lane per row
     Idct1d<v8i>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]).finish(v, 65536 + (128 << 17), 17);
     transpose8(v);  // back to rows
-    for (int r = 0; r < 8; ++r) {
-        v8i x = v[r];
-        x &= ~(x < 0);
-        const v8i over = x > 255;
-        x = (x & ~over) | (over & 255);
-        const v8b bytes = __builtin_convertvector(x, v8b);
-        std::memcpy(out + out_stride * r, &bytes, 8);
+#ifdef __AVX2__
+    for (int r = 0; r < 8; r += 2) {  // two rows at a time; the saturating packs are the clamp (|x| < 2^14 after the shift by 17)
+        const __m256i words = _mm256_permute4x64_epi64(_mm256_packs_epi32((__m256i)v[r], (__m256i)v[r + 1]), 0xD8);  // a0-7 | b0-7
+        const __m256i bytes = _mm256_packus_epi16(words, words);                                                     // a0-7 a0-7 | b0-7 b0-7
+        _mm_storel_epi64(reinterpret_cast<__m128i *>(out + out_stride * r), _mm256_castsi256_si128(bytes));
+        _mm_storel_epi64(reinterpret_cast<__m128i *>(out + out_stride * (r + 1)), _mm256_extracti128_si256(bytes, 1));
     }
+#else
+    for (int r = 0; r < 8; ++r) {
+        for (int c = 0; c < 8; ++c) {
+            out[out_stride * r + c] = clamp_u8(v[r][c]);
+        }
+    }
+#endif
 }
 #else
 inline void idct_block(uint8_t *out, size_t out_stride, const short d[64])
@@ -258,14 +289,21 @@ inline const uint8_t *resample_row(uint8_t *out, const uint8_t *near, const uint
             out[0] = out[1] = (uint8_t)((3 * near[0] + far[0] + 2) >> 2);
             return out;
         }
-        int t1 = 3 * near[0] + far[0];
-        out[0] = (uint8_t)((t1 + 2) >> 2);
-        for (int i = 1; i < w; ++i) {
-            const int t0 = t1;
-            t1 = 3 * near[i] + far[i];
-            out[i * 2 - 1] = (uint8_t)((3 * t0 + t1 + 8) >> 4);
-            out[i * 2] = (uint8_t)((3 * t1 + t0 + 8) >> 4);
+        // t[i] = 3 * near[i] + far[i]; out[2i - 1] and out[2i] blend t[i - 1] and t[i] 3:1 / 1:3. In chunks, so that both loops are
+        // free of loop-carried values (the compiler vectorises them)
+        out[0] = (uint8_t)((3 * near[0] + far[0] + 2) >> 2);
+        for (int base = 1; base < w; base += 256) {
+            const int n = std::min(256, w - base);
+            uint16_t t[257];
+            for (int k = 0; k <= n; ++k) {
+                t[k] = (uint16_t)(3 * near[base - 1 + k] + far[base - 1 + k]);
+            }
+            for (int k = 0; k < n; ++k) {
+                out[(base + k) * 2 - 1] = (uint8_t)((3 * t[k] + t[k + 1] + 8) >> 4);
+                out[(base + k) * 2] = (uint8_t)((3 * t[k + 1] + t[k] + 8) >> 4);
+            }
         }
+        const int t1 = 3 * near[w - 1] + far[w - 1];
         out[w * 2 - 1] = (uint8_t)((t1 + 2) >> 2);
         return out;
     }
@@ -284,27 +322,30 @@ constexpr int float2fixed(float x)
 inline void ycbcr_to_rgba_row(uint8_t *out, const uint8_t *y, const uint8_t *pcb, const uint8_t *pcr, int count)
 {
     int i = 0;
-#if defined(__GNUC__) && !defined(CRT_JPEG_NO_VECTOR)
-    for (; i + 8 <= count; i += 8) {  // the arithmetic below on eight pixels; wrap-around sums as in the unsigned scalar expression
-        v8b yb, cbb, crb;
-        std::memcpy(&yb, y + i, 8);
-        std::memcpy(&cbb, pcb + i, 8);
-        std::memcpy(&crb, pcr + i, 8);
-        const v8i y_fixed = (__builtin_convertvector(yb, v8i) << 20) + (1 << 19);
-        const v8i cr = __builtin_convertvector(crb, v8i) - 128, cb = __builtin_convertvector(cbb, v8i) - 128;
-        v8i r = y_fixed + cr * float2fixed(1.40200f);
-        v8i g = (v8i)((v8u)(y_fixed + cr * -float2fixed(0.71414f)) + ((v8u)(cb * -float2fixed(0.34414f)) & 0xffff0000u));
-        v8i b = y_fixed + cb * float2fixed(1.77200f);
-        r >>= 20;
-        g >>= 20;
-        b >>= 20;
-        const auto clamp = [](v8i x) {
-            x &= ~(x < 0);
-            const v8i over = x > 255;
-            return (x & ~over) | (over & 255);
-        };
-        const v8u px = (v8u)clamp(r) | ((v8u)clamp(g) << 8) | ((v8u)clamp(b) << 16) | 0xff000000u;
-        std::memcpy(out + 4 * i, &px, 32);
+#if defined(__AVX2__) && !defined(CRT_JPEG_NO_VECTOR)
+    // the arithmetic below on eight pixels (32-bit lanes wrap like the unsigned scalar expression; the saturating packs are the
+    // clamp: after the shift by 20 the values lie within +-2048)
+    const __m256i c_r = _mm256_set1_epi32(float2fixed(1.40200f)), c_g1 = _mm256_set1_epi32(-float2fixed(0.71414f));
+    const __m256i c_g2 = _mm256_set1_epi32(-float2fixed(0.34414f)), c_b = _mm256_set1_epi32(float2fixed(1.77200f));
+    const __m256i half = _mm256_set1_epi32(1 << 19), mid = _mm256_set1_epi32(128), mask = _mm256_set1_epi32((int)0xffff0000u);
+    const __m128i opaque = _mm_set1_epi8((char)0xff);
+    for (; i + 8 <= count; i += 8) {
+        const __m256i yy = _mm256_cvtepu8_epi32(_mm_loadl_epi64(reinterpret_cast<const __m128i *>(y + i)));
+        const __m256i cb = _mm256_sub_epi32(_mm256_cvtepu8_epi32(_mm_loadl_epi64(reinterpret_cast<const __m128i *>(pcb + i))), mid);
+        const __m256i cr = _mm256_sub_epi32(_mm256_cvtepu8_epi32(_mm_loadl_epi64(reinterpret_cast<const __m128i *>(pcr + i))), mid);
+        const __m256i y_fixed = _mm256_add_epi32(_mm256_slli_epi32(yy, 20), half);
+        const __m256i r = _mm256_srai_epi32(_mm256_add_epi32(y_fixed, _mm256_mullo_epi32(cr, c_r)), 20);
+        const __m256i g = _mm256_srai_epi32(_mm256_add_epi32(_mm256_add_epi32(y_fixed, _mm256_mullo_epi32(cr, c_g1)),
+                                                             _mm256_and_si256(_mm256_mullo_epi32(cb, c_g2), mask)), 20);
+        const __m256i b = _mm256_srai_epi32(_mm256_add_epi32(y_fixed, _mm256_mullo_epi32(cb, c_b)), 20);
+        const __m256i rg16 = _mm256_permute4x64_epi64(_mm256_packs_epi32(r, g), 0xD8);  // r0-7 | g0-7 as 16-bit
+        const __m256i b16 = _mm256_permute4x64_epi64(_mm256_packs_epi32(b, b), 0xD8);   // b0-7 | b0-7
+        const __m128i r8 = _mm_packus_epi16(_mm256_castsi256_si128(rg16), _mm256_castsi256_si128(rg16));
+        const __m128i g8 = _mm_packus_epi16(_mm256_extracti128_si256(rg16, 1), _mm256_extracti128_si256(rg16, 1));
+        const __m128i b8 = _mm_packus_epi16(_mm256_castsi256_si128(b16), _mm256_castsi256_si128(b16));
+        const __m128i rg = _mm_unpacklo_epi8(r8, g8), ba = _mm_unpacklo_epi8(b8, opaque);
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(out + 4 * i), _mm_unpacklo_epi16(rg, ba));
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(out + 4 * i + 16), _mm_unpackhi_epi16(rg, ba));
     }
 #endif
     for (; i < count; ++i) {
