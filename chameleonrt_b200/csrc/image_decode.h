@@ -15,6 +15,10 @@
 
 #include "jpeg_decode.h"
 
+#if defined(__SSE4_1__)
+#include <smmintrin.h>
+#endif
+
 namespace crt_image {
 
 inline uint32_t be32(const uint8_t *p)
@@ -100,7 +104,7 @@ inline void decode_png_rgba(const uint8_t *file_data, size_t file_size, const st
     for (const Pass &ps : passes) {
         raw_size += (ps.row_bytes + 1) * (size_t)ps.h;
     }
-    std::vector<uint8_t> raw(raw_size);
+    std::vector<uint8_t> raw(raw_size + 16);  // (+ room for the 4-byte loads of the last 3-byte pixel of the last row)
     {
         z_stream zs;
         std::memset(&zs, 0, sizeof(zs));
@@ -110,11 +114,11 @@ inline void decode_png_rgba(const uint8_t *file_data, size_t file_size, const st
         zs.next_in = idat.data();
         zs.avail_in = (uInt)idat.size();
         zs.next_out = raw.data();
-        zs.avail_out = (uInt)raw.size();
+        zs.avail_out = (uInt)raw_size;
         const int rc = inflate(&zs, Z_FINISH);
-        const size_t got = raw.size() - zs.avail_out;
+        const size_t got = raw_size - zs.avail_out;
         inflateEnd(&zs);
-        if ((rc != Z_STREAM_END && rc != Z_OK && rc != Z_BUF_ERROR) || got != raw.size()) {  // (more data than the image needs is ignored)
+        if ((rc != Z_STREAM_END && rc != Z_OK && rc != Z_BUF_ERROR) || got != raw_size) {  // (more data than the image needs is ignored)
             throw std::runtime_error("corrupt PNG data: " + path);
         }
     }
@@ -131,7 +135,7 @@ inline void decode_png_rgba(const uint8_t *file_data, size_t file_size, const st
     for (const Pass &ps : passes) {
         longest_row = std::max(longest_row, ps.row_bytes);
     }
-    const std::vector<uint8_t> zero_row(longest_row, 0);  // the row "above" the first one of a pass
+    const std::vector<uint8_t> zero_row(longest_row + 16, 0);  // the row "above" the first one of a pass (+ room as above)
     for (const Pass &ps : passes) {
         const size_t n = ps.row_bytes, bpp = std::min(filter_bpp, ps.row_bytes);
         const uint8_t *prev = zero_row.data();
@@ -163,10 +167,36 @@ inline void decode_png_rgba(const uint8_t *file_data, size_t file_size, const st
                 for (size_t x = 0; x < bpp; ++x) {
                     cur[x] = (uint8_t)(cur[x] + prev[x]);  // (a = c = 0: the predictor is b)
                 }
-                for (size_t x = bpp; x < n; ++x) {
-                    const int a = cur[x - bpp], b = prev[x], c = prev[x - bpp];
-                    const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
-                    cur[x] = (uint8_t)(cur[x] + ((pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c)));
+                {
+                    size_t x = bpp;
+#if defined(__SSE4_1__)
+                    if ((bpp == 3 || bpp == 4) && n >= 2 * bpp) {
+                        // one pixel per step, its channels in 16-bit lanes: pa = |b - c|, pb = |a - c|, pc = |a + b - 2c|; the
+                        // predictor is a, b or c by the smallest of them, ties in that order (the scalar rule below)
+                        const auto load = [](const uint8_t *p) {
+                            int32_t v;
+                            std::memcpy(&v, p, 4);  // (4 bytes also for 3-byte pixels: the buffer is padded)
+                            return _mm_cvtepu8_epi16(_mm_cvtsi32_si128(v));
+                        };
+                        __m128i a = load(cur), c = load(prev);  // the first pixel is done: it is the left neighbour of the next
+                        for (; x + bpp <= n; x += bpp) {
+                            const __m128i b = load(prev + x);
+                            const __m128i d_bc = _mm_sub_epi16(b, c), d_ac = _mm_sub_epi16(a, c);
+                            const __m128i pa = _mm_abs_epi16(d_bc), pb = _mm_abs_epi16(d_ac), pc = _mm_abs_epi16(_mm_add_epi16(d_bc, d_ac));
+                            const __m128i smallest = _mm_min_epi16(pc, _mm_min_epi16(pa, pb));
+                            const __m128i nearest = _mm_blendv_epi8(_mm_blendv_epi8(c, b, _mm_cmpeq_epi16(smallest, pb)), a, _mm_cmpeq_epi16(smallest, pa));
+                            a = _mm_and_si128(_mm_add_epi16(load(cur + x), nearest), _mm_set1_epi16(0xff));
+                            c = b;
+                            const int32_t px = _mm_cvtsi128_si32(_mm_packus_epi16(a, a));
+                            std::memcpy(cur + x, &px, bpp);
+                        }
+                    }
+#endif
+                    for (; x < n; ++x) {
+                        const int a = cur[x - bpp], b = prev[x], c = prev[x - bpp];
+                        const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+                        cur[x] = (uint8_t)(cur[x] + ((pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c)));
+                    }
                 }
                 break;
             default: throw std::runtime_error("corrupt PNG filter: " + path);
@@ -208,7 +238,15 @@ inline void decode_png_rgba(const uint8_t *file_data, size_t file_size, const st
             continue;
         }
         if (bit_depth == 8 && !has_key && color_type == 2) {
-            for (int x = 0; x < width; ++x) {
+            int x = 0;
+#if defined(__SSE4_1__)
+            const __m128i spread = _mm_setr_epi8(0, 1, 2, -1, 3, 4, 5, -1, 6, 7, 8, -1, 9, 10, 11, -1), alpha = _mm_set1_epi32((int)0xff000000u);
+            for (; x + 6 <= width; x += 4) {  // four pixels per step; the 16-byte load reads into the fifth and sixth
+                const __m128i rgb = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + 3 * x));
+                _mm_storeu_si128(reinterpret_cast<__m128i *>(dst + 4 * x), _mm_or_si128(_mm_shuffle_epi8(rgb, spread), alpha));
+            }
+#endif
+            for (; x < width; ++x) {
                 dst[4 * x] = src[3 * x], dst[4 * x + 1] = src[3 * x + 1], dst[4 * x + 2] = src[3 * x + 2], dst[4 * x + 3] = 255;
             }
             continue;

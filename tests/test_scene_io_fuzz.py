@@ -43,7 +43,9 @@ def test_mutated_files_never_break_the_loaders(built, tmp_path):
     os.rename(t._crts_file(seed)[1], str(seed / "s.crts"))
     shutil.copy(str(seed / "poly.mtl"), str(work / "poly.mtl"))  # (what the mutated OBJ's mtllib line usually still names)
     exe = str(tmp_path / "fuzz_scene_io")
-    build = subprocess.run([cxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+    # -march=x86-64-v3: the product's flags, i.e. the AVX2 / SSE4.1 paths of the decoders (the portable ones run in
+    # oracle/_ref/libcrt_refscene_native.so, which tests/test_scene_io.py compares with the reference)
+    build = subprocess.run([cxx, "-std=c++17", "-O1", "-g", "-march=x86-64-v3", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
                             "-fno-omit-frame-pointer", "-I" + os.path.join(ROOT, "include"), "-o", exe,
                             os.path.join(ROOT, "tests", "fuzz", "fuzz_scene_io.cpp"), "-lz", "-pthread"], capture_output=True, text=True, timeout=600)
     if build.returncode != 0 and "sanitize" in build.stderr and "cannot find" in build.stderr:
