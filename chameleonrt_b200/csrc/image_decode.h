@@ -38,33 +38,69 @@ inline void decode_png_rgba(const uint8_t *file_data, size_t file_size, const st
     if (file_size < 8 + 25 || std::memcmp(file_data, sig, 8) != 0) {
         throw std::runtime_error("not a PNG, JPEG or TGA file (the formats this loader reads): " + path);
     }
+    // the chunks, with the structural checks stb_image makes (stbi__parse_png_file: a file it refuses is refused here)
     size_t pos = 8;
     int bit_depth = 0, color_type = 0, interlace = 0;
     std::vector<uint8_t> idat, palette, trns;
+    bool have_header = false, have_idat = false, ended = false;
     width = height = 0;
-    while (pos + 12 <= file_size) {
+    const auto corrupt = [&](const char *what) { return std::runtime_error(std::string("corrupt PNG (") + what + "): " + path); };
+    while (!ended && pos + 8 <= file_size) {
         const uint32_t len = be32(file_data + pos);
         const char *type = reinterpret_cast<const char *>(file_data + pos + 4);
         const uint8_t *body = file_data + pos + 8;
-        if (pos + 12 + (size_t)len > file_size) {
+        if ((size_t)len > file_size - (pos + 8)) {
             throw std::runtime_error("truncated PNG: " + path);
         }
-        if (std::memcmp(type, "IHDR", 4) == 0 && len >= 13) {
+        const auto is = [&](const char *name) { return std::memcmp(type, name, 4) == 0; };
+        if (!have_header && !is("IHDR") && !is("CgBI")) {
+            throw corrupt("first not IHDR");
+        }
+        if (is("IHDR")) {
+            if (have_header || len != 13) {
+                throw corrupt("IHDR");
+            }
+            have_header = true;
             width = (int)be32(body);
             height = (int)be32(body + 4);
             bit_depth = body[8];
             color_type = body[9];
             interlace = body[12];
-        } else if (std::memcmp(type, "PLTE", 4) == 0) {
+            if (be32(body) > (1u << 24) || be32(body + 4) > (1u << 24) || body[10] != 0 || body[11] != 0) {
+                throw corrupt("size, compression or filter method");
+            }
+        } else if (is("PLTE")) {
+            if (len > 256 * 3 || len % 3 != 0) {
+                throw corrupt("invalid PLTE");
+            }
             palette.assign(body, body + len);
-        } else if (std::memcmp(type, "tRNS", 4) == 0) {
+        } else if (is("tRNS")) {
+            if (have_idat) {
+                throw corrupt("tRNS after IDAT");
+            }
+            if (color_type == 3) {
+                if (palette.empty() || len > palette.size() / 3) {
+                    throw corrupt("tRNS and PLTE");
+                }
+            } else if ((color_type & 4) || len != (uint32_t)((color_type & 2) ? 6 : 2)) {
+                throw corrupt("tRNS of an image with alpha, or of the wrong length");
+            }
             trns.assign(body, body + len);
-        } else if (std::memcmp(type, "IDAT", 4) == 0) {
+        } else if (is("IDAT")) {
+            if (color_type == 3 && palette.empty()) {
+                throw corrupt("no PLTE");
+            }
+            have_idat = true;
             idat.insert(idat.end(), body, body + len);
-        } else if (std::memcmp(type, "IEND", 4) == 0) {
-            break;
+        } else if (is("IEND")) {
+            ended = true;
+        } else if ((type[0] & 0x20) == 0 && !is("CgBI")) {
+            throw std::runtime_error("PNG not supported: unknown critical chunk: " + path);
         }
-        pos += 12 + (size_t)len;
+        pos += 8 + (size_t)len + 4;  // (the CRC is not checked, as in stb_image)
+    }
+    if (!have_header || !have_idat) {
+        throw corrupt("no IHDR or no IDAT");
     }
     int ch;
     switch (color_type) {

@@ -1423,3 +1423,66 @@ def test_native_crts_loader_differential_fuzz(built, tmp_path):
         path = _random_crts(np.random.default_rng(seed), str(tmp_path))
         nat, _ = _native_arrays(path)
         _assert_same(nat, _reference_arrays(path))
+
+
+@needs_ref
+def test_native_png_decoder_refuses_what_stb_image_refuses(built, tmp_path):
+    """Structurally wrong PNG files (stbi__parse_png_file's checks): a tRNS chunk in an image with alpha, of the wrong length,
+    longer than the palette, before the palette or after the data; a palette image without palette; a palette of a length that
+    is no multiple of three; an unknown critical chunk; a second header; no data — each refused by both loaders, while the
+    untouched file and harmless variations (an unknown ancillary chunk, a wrong CRC) load to the same pixels."""
+    import struct
+    import zlib
+
+    rng = np.random.default_rng(5)
+
+    def chunk(kind, body, crc_ok=True):
+        return struct.pack(">I", len(body)) + kind + body + struct.pack(">I", (zlib.crc32(kind + body) & 0xFFFFFFFF) ^ (0 if crc_ok else 0x5a5a))
+
+    def png(color_type, depth, chunks_before_idat=(), chunks_after_idat=(), palette=None, idat=True, header_twice=False, ihdr_tail=(0, 0, 0)):
+        ch = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[color_type]
+        w, h = 5, 4
+        raw = b"".join(b"\0" + bytes(rng.integers(0, 2 ** min(depth, 8) if color_type != 3 else 4, (w * ch * depth + 7) // 8, dtype=np.uint8)) for _ in range(h))
+        out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, color_type, *ihdr_tail))
+        if header_twice:
+            out += chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, color_type, 0, 0, 0))
+        if palette is not None:
+            out += chunk(b"PLTE", bytes(palette))
+        for c in chunks_before_idat:
+            out += c
+        if idat:
+            out += chunk(b"IDAT", zlib.compress(raw))
+        for c in chunks_after_idat:
+            out += c
+        return out + chunk(b"IEND", b"")
+
+    pal = list(rng.integers(0, 256, 12))
+    cases = {
+        "ok_rgb": (png(2, 8), True), "ok_pal": (png(3, 8, palette=pal), True), "ok_pal_trns": (png(3, 8, [chunk(b"tRNS", bytes([1, 2, 3]))], palette=pal), True),
+        "ok_ancillary": (png(2, 8, [chunk(b"teSt", b"hello")]), True), "ok_bad_crc": (png(2, 8, [chunk(b"teXt", b"hello", crc_ok=False)]), True),
+        "trns_with_alpha": (png(6, 8, [chunk(b"tRNS", bytes(6))]), False), "trns_short": (png(2, 8, [chunk(b"tRNS", bytes(2))]), False),
+        "trns_long_grey": (png(0, 8, [chunk(b"tRNS", bytes(6))]), False), "trns_longer_than_palette": (png(3, 8, [chunk(b"tRNS", bytes(5))], palette=pal), False),
+        "trns_after_idat": (png(2, 8, (), [chunk(b"tRNS", bytes(6))]), False), "no_palette": (png(3, 8), False),
+        "palette_length": (png(3, 8, palette=pal[:11]), False), "critical_chunk": (png(2, 8, [chunk(b"TEST", b"x")]), False),
+        "two_headers": (png(2, 8, header_twice=True), False), "no_idat": (png(2, 8, idat=False), False),
+        "compression_method": (png(2, 8, ihdr_tail=(1, 0, 0)), False), "filter_method": (png(2, 8, ihdr_tail=(0, 1, 0)), False),
+        "interlace_method": (png(2, 8, ihdr_tail=(0, 0, 2)), False), "palette_16_bit": (png(3, 16, palette=pal), False), "colour_type_5": (png(5, 8) if False else None, False),
+    }
+    from chameleonrt_b200 import scene_io
+
+    lib = _ref()
+    for name, (data, should_load) in cases.items():
+        if data is None:
+            continue
+        (tmp_path / f"{name}.png").write_bytes(data)
+        path = _texture_scene(tmp_path, [f"{name}.png"])
+        h = lib.refscene_load_mode(path.encode(), 0, None)
+        if h:
+            lib.refscene_free(h)
+        assert bool(h) == should_load, f"{name}: the reference {'loads' if h else 'refuses'} it"
+        if should_load:
+            nat, _ = _native_arrays(path)
+            assert np.array_equal(nat["textures"][0][0], _reference_arrays(path)["textures"][0][0]), name
+        else:
+            with pytest.raises(RuntimeError):
+                scene_io.load_scene(path)
