@@ -5,7 +5,8 @@
 //
 //     Scene scene = crt_cuda::load_scene_native(scene_file, material_mode);
 //
-// and adds scene_native_load.cpp + chameleonrt_b200/csrc/scene_io.cpp (-lz) to the `util` target. The Scene that comes back
+// and links the static library crt_scene_native of this directory's CMakeLists.txt (scene_native_load.cpp +
+// chameleonrt_b200/csrc/scene_io.cpp, zlib) into the application. The Scene that comes back
 // is, array for array, the one the constructor builds (oracle/ref_build builds both and tests/test_scene_io.py compares them).
 #pragma once
 
