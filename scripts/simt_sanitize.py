@@ -94,6 +94,42 @@ def render_all(lib: str):
     print(f"shared frame of two renderers: mean {float(full.mean()):.4f}, lit {lit.mean():.2f}", flush=True)
 
 
+def adversarial_geometry():
+    """NaN / infinite / huge / tiny coordinates, degenerate, identical, duplicated and collinear triangles, a single triangle:
+    through set_scene (host builder, PLOC, LBVH) and a frame. Every builder must cope, and cast the same number of rays."""
+    import numpy as np
+
+    from chameleonrt_b200 import ArcballCamera, backend
+    from chameleonrt_b200.scene import DisneyMaterial, Geometry, Instance, Mesh, ParameterizedMesh, Scene, default_obj_light
+
+    rng = np.random.default_rng(0)
+
+    def scene_of(verts, idx):
+        g = Geometry(np.asarray(verts, np.float32), np.asarray(idx, np.uint32), None)
+        return Scene(meshes=[Mesh([g])], parameterized_meshes=[ParameterizedMesh(0, [0])], instances=[Instance(np.eye(4, dtype=np.float32), 0)],
+                     materials=[DisneyMaterial(base_color=(0.8, 0.8, 0.8))], textures=[], lights=[default_obj_light()], samples_per_pixel=1)
+
+    v0, i0 = rng.normal(size=(60, 3)), rng.integers(0, 60, (100, 3))
+    with_nan, with_inf = v0.copy(), v0.copy()
+    with_nan[3] = np.nan
+    with_inf[5], with_inf[6] = np.inf, -np.inf
+    cases = {"nan vertex": (with_nan, i0), "infinite vertices": (with_inf, i0), "coordinates x 1e30": (v0 * 1e30, i0), "coordinates x 1e-30": (v0 * 1e-30, i0),
+             "degenerate triangles": (v0, np.repeat(rng.integers(0, 60, (100, 1)), 3, axis=1)), "identical vertices": (np.zeros((60, 3)), i0),
+             "single triangle": (v0[:3], [[0, 1, 2]]), "50 copies of two triangles": (v0, np.tile(i0[:2], (50, 1))),
+             "collinear vertices": (np.outer(np.linspace(0, 1, 60), [1, 2, 3]), i0)}
+    c = ArcballCamera((0, 0, 5), (0, 0, 0), (0, 1, 0))
+    for name, (v, i) in cases.items():
+        rays = []
+        for builder in (0, 1, 2):
+            r = backend.RenderCUDA(0, max_depth=3)
+            r.set_option("bvh_builder", builder)
+            r.initialize(24, 16)
+            r.set_scene(scene_of(v, i))
+            rays.append(r.render(c.eye(), c.dir(), c.up(), 45.0, True, True).num_rays)
+        assert rays[0] == rays[1] == rays[2], (name, rays)
+        print(f"adversarial geometry, {name}: {rays[0]} rays with every builder", flush=True)
+
+
 if __name__ == "__main__":
     tsan = "--tsan" in sys.argv
     if os.environ.get("CRT_SANITIZED_CHILD") != "1":
@@ -103,4 +139,5 @@ if __name__ == "__main__":
                    ASAN_OPTIONS="detect_leaks=0:abort_on_error=0:halt_on_error=1", TSAN_OPTIONS="halt_on_error=0:report_signal_unsafe=0")
         sys.exit(subprocess.call([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env))
     render_all(os.environ["CRT_SANITIZED_LIB"])
+    adversarial_geometry()
     print("sanitized run finished")
