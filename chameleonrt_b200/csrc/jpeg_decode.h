@@ -19,6 +19,10 @@
 // samples and arithmetic coding are errors (the latter two are errors in stb_image as well).
 #pragma once
 
+#if defined(__GNUC__) && !defined(__clang__)
+#pragma GCC diagnostic ignored "-Wpsabi"  // (256-bit vector values through inline helpers when the build has no -mavx: no ABI crosses a library boundary)
+#endif
+
 #ifdef __AVX2__
 #include <immintrin.h>
 #endif

@@ -173,3 +173,24 @@ def test_cuda_plugin_drop_in_crts_all_lobes(built, tmp_path):
     a_cpu, v2, _ = run_headless("oracle", crts, cam, 192, 128, 2, 2, tmp_path, depth=6)
     assert v1 == v2 and "CUDA wavefront" in out
     assert_parity(a_gpu, a_cpu, min_frac=0.99, max_rel_l1=1e-2)
+
+
+@needs_ref
+def test_backends_cuda_cmake_builds_in_a_chameleonrt_like_project(built, tmp_path):
+    """backends/cuda/CMakeLists.txt — what ChameleonRT's backends/CMakeLists.txt picks up — configured and built by CMake inside a
+    stand-in for the reference's top-level project (oracle/ref_build/cmake_check: the reference's target names and headers; SDL2 /
+    OpenGL / GLM headers from third_party/): the CUDA language is enabled, crt_cuda_core.cu compiles for sm_100a, libcrt_cuda.so
+    comes out as a MODULE in its interactive (GLDisplay + CUDA-GL interop) form exporting populate_plugin_functions, and the
+    optional crt_scene_native library builds."""
+    import shutil
+
+    if shutil.which("cmake") is None or not os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+        pytest.skip("needs cmake and nvcc")
+    build = tmp_path / "cmake_check"
+    r = subprocess.run([os.path.join(ROOT, "oracle", "ref_build", "cmake_check", "run.sh"), str(build)], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    flags = open(build / "backends" / "cuda" / "CMakeFiles" / "crt_cuda.dir" / "flags.make").read()
+    assert "arch=compute_100a" in flags and "-fmad=false" in flags
+    symbols = subprocess.run(["nm", "-D", str(build / "libcrt_cuda.so")], capture_output=True, text=True).stdout
+    assert " T populate_plugin_functions" in symbols
+    assert os.path.getsize(build / "backends" / "cuda" / "libcrt_scene_native.a") > 100000
