@@ -36,7 +36,7 @@ inline void decode_png_rgba(const uint8_t *file_data, size_t file_size, const st
 {
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
     if (file_size < 8 + 25 || std::memcmp(file_data, sig, 8) != 0) {
-        throw std::runtime_error("not a PNG, JPEG or TGA file (the formats this loader reads): " + path);
+        throw std::runtime_error("not a PNG, JPEG, TGA or BMP file (the formats this loader reads): " + path);
     }
     // the chunks, with the structural checks stb_image makes (stbi__parse_png_file: a file it refuses is refused here)
     size_t pos = 8;
@@ -356,7 +356,7 @@ inline bool looks_like_tga(const uint8_t *d, size_t n)
 inline void decode_tga_rgba(const uint8_t *data, size_t size, const std::string &path, std::vector<uint8_t> &out, int &width, int &height, bool flip)
 {
     if (!looks_like_tga(data, size)) {
-        throw std::runtime_error("not a PNG, JPEG or TGA file (the formats this loader reads): " + path);
+        throw std::runtime_error("not a PNG, JPEG, TGA or BMP file (the formats this loader reads): " + path);
     }
     size_t pos = 0;
     const auto get8 = [&]() -> int { return pos < size ? data[pos++] : (++pos, 0); };
@@ -474,7 +474,223 @@ inline void decode_tga_rgba(const uint8_t *data, size_t size, const std::string 
     }
 }
 
-// stbi_load_from_memory(..., 4) for the formats textures come in: PNG and TGA (above), JPEG (jpeg_decode.h)
+// ---- BMP (stb_image.h: stbi__bmp_parse_header, stbi__bmp_load): core (12-byte), info (40 / 56-byte) and V4 / V5 headers;
+// 1 / 4 / 8-bit palette images, 16-bit (5-5-5 or bit fields), 24-bit, 32-bit (BGRA or bit fields); either row order; no RLE.
+// stb_image's reading of the format: a 32-bit BI_RGB image whose alpha bytes are all 0 is opaque; channel masks of any width
+// are expanded to 8 bits by bit replication (stbi__shiftsigned); the palette of a core-header file is counted from offset - 38.
+inline bool looks_like_bmp(const uint8_t *d, size_t n)
+{
+    if (n < 18 || d[0] != 'B' || d[1] != 'M') {
+        return false;
+    }
+    const uint32_t hsz = (uint32_t)d[14] | ((uint32_t)d[15] << 8) | ((uint32_t)d[16] << 16) | ((uint32_t)d[17] << 24);
+    return hsz == 12 || hsz == 40 || hsz == 56 || hsz == 108 || hsz == 124;
+}
+
+inline void decode_bmp_rgba(const uint8_t *data, size_t size, const std::string &path, std::vector<uint8_t> &out, int &width, int &height, bool flip)
+{
+    size_t pos = 2;
+    const auto get8 = [&]() -> uint32_t { return pos < size ? data[pos++] : (++pos, 0u); };  // (bytes past the end read as 0)
+    const auto get16 = [&]() {
+        const uint32_t lo = get8();
+        return lo | (get8() << 8);
+    };
+    const auto get32 = [&]() {
+        const uint32_t lo = get16();
+        return lo | (get16() << 16);
+    };
+    const auto bad = [&](const char *what) { return std::runtime_error(std::string("unsupported or corrupt BMP (") + what + "): " + path); };
+    get32();
+    get16();
+    get16();
+    const int64_t offset = (int32_t)get32();
+    const uint32_t hsz = get32();
+    int32_t img_x, img_y;
+    if (hsz == 12) {
+        img_x = (int32_t)get16();
+        img_y = (int32_t)get16();
+    } else {
+        img_x = (int32_t)get32();
+        img_y = (int32_t)get32();
+    }
+    if (get16() != 1) {
+        throw bad("planes");
+    }
+    const int bpp = (int)get16();
+    uint32_t mr = 0, mg = 0, mb = 0, ma = 0, all_a = 255;
+    if (hsz != 12) {
+        const uint32_t compress = get32();
+        if (compress == 1 || compress == 2) {
+            throw bad("run-length encoded");
+        }
+        for (int k = 0; k < 5; ++k) {
+            get32();  // image size, resolutions, colours used / important
+        }
+        if (hsz == 40 || hsz == 56) {
+            for (int k = 0; hsz == 56 && k < 4; ++k) {
+                get32();
+            }
+            if (bpp == 16 || bpp == 32) {
+                if (compress == 0) {
+                    if (bpp == 32) {
+                        mr = 0xffu << 16, mg = 0xffu << 8, mb = 0xffu, ma = 0xffu << 24;
+                        all_a = 0;  // an alpha channel that turns out to be all 0 is replaced by 255
+                    } else {
+                        mr = 31u << 10, mg = 31u << 5, mb = 31u;
+                    }
+                } else if (compress == 3) {
+                    mr = get32(), mg = get32(), mb = get32();
+                    if (mr == mg && mg == mb) {
+                        throw bad("masks");
+                    }
+                } else {
+                    throw bad("compression");
+                }
+            }
+        } else {
+            mr = get32(), mg = get32(), mb = get32(), ma = get32();
+            for (int k = 0; k < 13 + (hsz == 124 ? 4 : 0); ++k) {
+                get32();  // colour space, its parameters, (V5) intent and profile
+            }
+        }
+    }
+    const bool bottom_up = img_y > 0;
+    if (img_y < 0) {
+        img_y = img_y == INT32_MIN ? 0 : -img_y;
+    }
+    if (img_x <= 0 || img_y <= 0 || (uint64_t)img_x * (uint64_t)img_y > ((uint64_t)1 << 28)) {
+        throw bad("size");
+    }
+    width = img_x;
+    height = img_y;
+    int64_t psize = 0;
+    if (hsz == 12) {
+        psize = bpp < 24 ? (offset - 14 - 24) / 3 : 0;
+    } else if (bpp < 16) {
+        psize = (offset - 14 - (int64_t)hsz) >> 2;
+    }
+    std::vector<uint8_t> px((size_t)img_x * img_y * 4);  // rows in file order
+    size_t z = 0;
+    const auto skip = [&](int64_t n) {
+        pos = n < 0 ? std::max(pos, size) : pos + (size_t)n;  // (stbi__skip: a negative count goes to the end of the data)
+    };
+    if (bpp < 16) {
+        if (psize <= 0 || psize > 256) {
+            throw bad("palette size");
+        }
+        uint8_t pal[256][3] = {};
+        for (int64_t i = 0; i < psize; ++i) {
+            pal[i][2] = (uint8_t)get8();
+            pal[i][1] = (uint8_t)get8();
+            pal[i][0] = (uint8_t)get8();
+            if (hsz != 12) {
+                get8();
+            }
+        }
+        skip(offset - 14 - (int64_t)hsz - psize * (hsz == 12 ? 3 : 4));
+        int row_bytes;
+        if (bpp == 1) {
+            row_bytes = (img_x + 7) >> 3;
+        } else if (bpp == 4) {
+            row_bytes = (img_x + 1) >> 1;
+        } else if (bpp == 8) {
+            row_bytes = img_x;
+        } else {
+            throw bad("bits per pixel");
+        }
+        const int pad = (-row_bytes) & 3;
+        for (int j = 0; j < img_y; ++j) {
+            uint32_t v = 0;
+            for (int i = 0; i < img_x; ++i) {
+                uint32_t index;
+                if (bpp == 1) {
+                    v = (i & 7) == 0 ? get8() : v;
+                    index = (v >> (7 - (i & 7))) & 1u;
+                } else if (bpp == 4) {
+                    v = (i & 1) == 0 ? get8() : v;
+                    index = (i & 1) == 0 ? (v >> 4) : (v & 15u);
+                } else {
+                    index = get8();
+                }
+                px[z++] = pal[index][0], px[z++] = pal[index][1], px[z++] = pal[index][2], px[z++] = 255;
+            }
+            skip(pad);
+        }
+    } else {
+        skip(offset - 14 - (int64_t)hsz);
+        const int pad = bpp == 24 ? (-(3 * img_x)) & 3 : (bpp == 16 ? (-(2 * img_x)) & 3 : 0);
+        const int easy = bpp == 24 ? 1 : ((bpp == 32 && mb == 0xffu && mg == 0xff00u && mr == 0x00ff0000u && ma == 0xff000000u) ? 2 : 0);
+        const auto high_bit = [](uint32_t v) {
+            int n = -1;
+            for (; v; v >>= 1) {
+                ++n;
+            }
+            return n;
+        };
+        const auto bit_count = [](uint32_t v) {
+            int n = 0;
+            for (; v; v &= v - 1) {
+                ++n;
+            }
+            return n;
+        };
+        // an arbitrarily placed field of `bits` bits -> 8 bits, the pattern repeated to fill them (stbi__shiftsigned)
+        const auto expand = [](uint32_t v, int shift, int bits) -> uint8_t {
+            static const uint32_t mul_table[9] = {0, 0xff, 0x55, 0x49, 0x11, 0x21, 0x41, 0x81, 0x01};
+            static const uint32_t shift_table[9] = {0, 0, 0, 1, 0, 2, 4, 6, 0};
+            v = shift < 0 ? v << -shift : v >> shift;
+            v >>= (8 - bits);
+            return (uint8_t)((int)(v * mul_table[bits]) >> shift_table[bits]);
+        };
+        int rshift = 0, gshift = 0, bshift = 0, ashift = 0, rcount = 0, gcount = 0, bcount = 0, acount = 0;
+        if (!easy) {
+            if (!mr || !mg || !mb) {
+                throw bad("masks");
+            }
+            rshift = high_bit(mr) - 7, rcount = bit_count(mr);
+            gshift = high_bit(mg) - 7, gcount = bit_count(mg);
+            bshift = high_bit(mb) - 7, bcount = bit_count(mb);
+            ashift = high_bit(ma) - 7, acount = bit_count(ma);
+            if (rcount > 8 || gcount > 8 || bcount > 8 || acount > 8) {
+                throw bad("masks wider than 8 bits");  // (stb_image indexes past its tables here)
+            }
+        }
+        for (int j = 0; j < img_y; ++j) {
+            for (int i = 0; i < img_x; ++i) {
+                uint32_t a;
+                if (easy) {
+                    px[z + 2] = (uint8_t)get8();
+                    px[z + 1] = (uint8_t)get8();
+                    px[z + 0] = (uint8_t)get8();
+                    a = easy == 2 ? get8() : 255u;
+                    z += 3;
+                } else {
+                    const uint32_t v = bpp == 16 ? get16() : get32();
+                    px[z++] = expand(v & mr, rshift, rcount);
+                    px[z++] = expand(v & mg, gshift, gcount);
+                    px[z++] = expand(v & mb, bshift, bcount);
+                    a = ma ? expand(v & ma, ashift, acount) : 255u;
+                }
+                all_a |= a;
+                px[z++] = (uint8_t)a;
+            }
+            skip(pad);
+        }
+    }
+    if (all_a == 0) {
+        for (size_t i = 3; i < px.size(); i += 4) {
+            px[i] = 255;
+        }
+    }
+    out.resize(px.size());
+    const size_t row = (size_t)img_x * 4;
+    for (int y = 0; y < img_y; ++y) {  // stbi returns top-down rows; `flip` turns them again
+        const bool reverse = bottom_up != flip;
+        std::memcpy(&out[row * (size_t)y], &px[row * (size_t)(reverse ? img_y - 1 - y : y)], row);
+    }
+}
+
+// stbi_load_from_memory(..., 4) for the formats textures come in: PNG, TGA and BMP (above), JPEG (jpeg_decode.h)
 inline void decode_image_rgba(const uint8_t *data, size_t size, const std::string &name, std::vector<uint8_t> &out, int &width, int &height,
                        bool flip)
 {
@@ -483,6 +699,8 @@ inline void decode_image_rgba(const uint8_t *data, size_t size, const std::strin
         crt_jpeg::decode_rgba(data, size, name, out, width, height, flip);
     } else if (size >= 4 && std::memcmp(data, png_sig, 4) == 0) {
         decode_png_rgba(data, size, name, out, width, height, flip);
+    } else if (looks_like_bmp(data, size)) {
+        decode_bmp_rgba(data, size, name, out, width, height, flip);
     } else {  // (TGA has no signature: stb_image tries it last, too)
         decode_tga_rgba(data, size, name, out, width, height, flip);
     }

@@ -21,7 +21,7 @@
  * Textures — the reference decodes them with stb_image to four components (flipped vertically for OBJ and .crts,
  * util/material.cpp:5-17; not for glTF) — are decoded concurrently, to the bytes stb_image returns: PNG of every colour type
  * and bit depth, Adam7 interlacing and tRNS transparency included; TGA true-colour / grey / colour-mapped, raw or run-length
- * encoded, with stb_image's reading of 15/16-bit pixels; JPEG (chameleonrt_b200/csrc/jpeg_decode.h) baseline and progressive,
+ * encoded, with stb_image's reading of 15/16-bit pixels; BMP with palettes, 16 / 24 / 32 bits and bit-field masks; JPEG (chameleonrt_b200/csrc/jpeg_decode.h) baseline and progressive,
  * grey or three components, any sampling factors, restart intervals, with stb_image's integer inverse DCT, chroma upsampling
  * and YCbCr -> RGB conversion.
  *
@@ -52,7 +52,7 @@ int crtio_load_obj(const char *path, int threads, crtio_scene **out);
 /* Scene::load_crts (util/scene.cpp:417-625): the reference's own binary format (a uint64 header size, a JSON header, a data
  * block of buffer views) — one geometry per mesh, MESH objects that instance a (mesh, material) pair under a matrix, LIGHT
  * objects (quad lights, frame = the object's matrix), CAMERA objects, every DisneyMaterial parameter with optional texture
- * handles, images as embedded PNG / JPEG / TGA files. The geometry arrays are NOT copied: the file stays mapped for the
+ * handles, images as embedded PNG / JPEG / TGA / BMP files. The geometry arrays are NOT copied: the file stays mapped for the
  * lifetime of the handle and crt_geometry_t points into it (arrays that are not 4-byte aligned in the file are copied). */
 int crtio_load_crts(const char *path, int threads, crtio_scene **out);
 /* Scene::load_gltf (util/scene.cpp:230-415, which reads the file through tinygltf and flattens the scene graph with

@@ -19,7 +19,7 @@ int main(int argc, char **argv)
     }
     const std::string seed_dir = argv[1], work_dir = argv[2];
     const int iters = atoi(argv[3]);
-    const char *names[] = {"a.jpg", "b.jpg", "c.jpg", "a.png", "b.png", "c.png", "a.tga", "b.tga", "poly.obj", "h.glb", "h.gltf", "s.crts"};
+    const char *names[] = {"a.jpg", "b.jpg", "c.jpg", "a.png", "b.png", "c.png", "a.tga", "b.tga", "a.bmp", "b.bmp", "poly.obj", "h.glb", "h.gltf", "s.crts"};
     std::mt19937 rng(12345);
     int ok = 0, failed = 0;
     for (const char *name : names) {
@@ -37,7 +37,7 @@ int main(int argc, char **argv)
                 else { const uint8_t special[] = {0, 0xff, 0x7f, 0x80, 1, '0', '-', '/', ' ', '\n', '{', '[', '"'}; m[pos] = special[rng() % sizeof(special)]; }
             }
             try {
-                if (ext == ".jpg" || ext == ".png" || ext == ".tga") {
+                if (ext == ".jpg" || ext == ".png" || ext == ".tga" || ext == ".bmp") {
                     std::vector<uint8_t> out;
                     int w, h;
                     decode_image_rgba(m.data(), m.size(), name, out, w, h, it & 1);

@@ -1486,3 +1486,101 @@ def test_native_png_decoder_refuses_what_stb_image_refuses(built, tmp_path):
         else:
             with pytest.raises(RuntimeError):
                 scene_io.load_scene(path)
+
+
+def _write_bmp(path, rows, bpp, header=40, top_down=False, masks=None, palette=None, compression=None, gap=0):
+    """A BMP writer for the variants of the format: `rows` (h, w) of pixel values (palette indices, or packed 16 / 32-bit pixels)
+    or (h, w, 3 / 4) of B, G, R[, A] bytes; header = 12 (OS/2 core), 40 (info), 56, 108 (V4) or 124 (V5); bit-field masks;
+    `gap` unused bytes between the headers and the pixel data."""
+    import struct
+
+    rows = np.asarray(rows)
+    h, w = rows.shape[:2]
+    if rows.ndim == 3:
+        raw_rows = [bytes(rows[y].astype(np.uint8).tobytes()) for y in range(h)]
+    elif bpp in (16, 32):
+        raw_rows = [rows[y].astype("<u2" if bpp == 16 else "<u4").tobytes() for y in range(h)]
+    elif bpp == 8:
+        raw_rows = [rows[y].astype(np.uint8).tobytes() for y in range(h)]
+    else:
+        per = 8 // bpp
+        raw_rows = []
+        for y in range(h):
+            r = np.concatenate([rows[y], np.zeros((-w) % per, rows.dtype)]).reshape(-1, per)
+            raw_rows.append(bytes((r << (np.arange(per)[::-1] * bpp)).sum(1).astype(np.uint8)))
+    raw_rows = [r + bytes((-len(r)) % 4) for r in raw_rows]
+    if not top_down:
+        raw_rows = raw_rows[::-1]
+    pal = b""
+    if palette is not None:
+        pal = b"".join(bytes([c[2], c[1], c[0]] + ([] if header == 12 else [0])) for c in palette)
+    compression = (3 if masks and header == 40 else 0) if compression is None else compression
+    if header == 12:
+        info = struct.pack("<IHHHH", 12, w, h, 1, bpp)
+    else:
+        info = struct.pack("<IiiHHIIiiII", header, w, -h if top_down else h, 1, bpp, compression, 0, 2835, 2835, 0, 0)
+        if header == 40 and masks:
+            info += struct.pack("<III", *masks[:3])
+        elif header >= 56:
+            m = list(masks) + [0] * (4 - len(masks)) if masks else [0, 0, 0, 0]
+            info += struct.pack("<IIII", *m)
+            info += bytes(header - 56)
+            if header == 56 and compression == 3:
+                info += struct.pack("<III", *m[:3])  # (stb_image skips the mask fields of a 56-byte header and reads three masks behind it)
+    offset = 14 + len(info) + len(pal) + gap
+    data = b"".join(raw_rows)
+    with open(path, "wb") as f:
+        f.write(b"BM" + struct.pack("<IHHI", offset + len(data), 0, 0, offset) + info + pal + bytes(gap) + data)
+
+
+@needs_ref
+def test_native_bmp_textures_are_stb_images_bytes(built, tmp_path):
+    """BMP as stb_image reads it: 24-bit, 32-bit BGRA (with alpha, and with an all-zero alpha channel, which counts as opaque),
+    32- and 16-bit with bit-field masks of 1 to 8 bits per channel in info / V4 / V5 headers, 16-bit 5-5-5, 8 / 4 / 1-bit palettes,
+    the OS/2 core header, bottom-up and top-down rows, widths that need row padding, a gap before the pixel data — plus PIL's files."""
+    rng = np.random.default_rng(6)
+    names = []
+
+    def add(*args, **kw):
+        names.append(f"b{len(names)}.bmp")
+        _write_bmp(str(tmp_path / names[-1]), *args, **kw)
+
+    for (w, h) in [(1, 1), (5, 3), (14, 9), (33, 4)]:
+        for top_down in (False, True):
+            add(rng.integers(0, 256, (h, w, 3)), 24, top_down=top_down)
+            add(rng.integers(0, 256, (h, w, 4)), 32, top_down=top_down)
+            add(np.concatenate([rng.integers(0, 256, (h, w, 3)), np.zeros((h, w, 1), int)], 2), 32, top_down=top_down)  # alpha all 0
+            add(rng.integers(0, 2 ** 32, (h, w), dtype=np.uint64), 32, masks=(0x00FF0000, 0x0000FF00, 0x000000FF), top_down=top_down)
+            add(rng.integers(0, 2 ** 32, (h, w), dtype=np.uint64), 32, header=108, masks=(0x000000FF, 0x0000FF00, 0x00FF0000, 0xFF000000), top_down=top_down)
+            add(rng.integers(0, 2 ** 32, (h, w), dtype=np.uint64), 32, header=124, masks=(0xF8000000, 0x07E00000, 0x001F0000, 0x0000000F), top_down=top_down)
+            add(rng.integers(0, 2 ** 16, (h, w)), 16, top_down=top_down)
+            add(rng.integers(0, 2 ** 16, (h, w)), 16, masks=(0xF800, 0x07E0, 0x001F), top_down=top_down)
+            add(rng.integers(0, 2 ** 16, (h, w)), 16, header=56, masks=(0x0F00, 0x00F0, 0x000F, 0xF000), compression=3, top_down=top_down)
+            add(rng.integers(0, 2 ** 16, (h, w)), 16, header=108, masks=(0x7000, 0x0380, 0x0003, 0x8000), compression=3, top_down=top_down)
+            add(rng.integers(0, 256, (h, w)), 8, palette=rng.integers(0, 256, (256, 3)), top_down=top_down)
+            add(rng.integers(0, 16, (h, w)), 4, palette=rng.integers(0, 256, (16, 3)), top_down=top_down, gap=0)
+            add(rng.integers(0, 2, (h, w)), 1, palette=rng.integers(0, 256, (2, 3)), top_down=top_down)
+            add(rng.integers(0, 7, (h, w)), 8, palette=rng.integers(0, 256, (7, 3)), header=108, top_down=top_down, gap=8)
+        add(rng.integers(0, 256, (h, w, 3)), 24, header=12)
+        # (stb_image counts the palette of a core-header file from offset - 38: of 256 entries it reads 252; the rest is uninitialised there)
+        add(rng.integers(0, 252, (h, w)), 8, header=12, palette=rng.integers(0, 256, (256, 3)))
+    names = [n for n in names if os.path.exists(tmp_path / n)]
+    try:
+        from PIL import Image as PILImage
+
+        y, x = np.mgrid[0:13, 0:22]
+        rgb = np.stack([x * 11, y * 19, x + y], 2).astype(np.uint8)
+        PILImage.fromarray(rgb, "RGB").save(str(tmp_path / "pil_rgb.bmp"))
+        PILImage.fromarray(rgb[:, :, 0], "L").save(str(tmp_path / "pil_l.bmp"))
+        PILImage.fromarray(rgb, "RGB").quantize(16).save(str(tmp_path / "pil_p.bmp"))
+        PILImage.fromarray(((x + y) % 2).astype(bool)).save(str(tmp_path / "pil_1.bmp"))
+        PILImage.fromarray(np.dstack([rgb, (x * 9).astype(np.uint8)]), "RGBA").save(str(tmp_path / "pil_rgba.bmp"))
+        names += ["pil_rgb.bmp", "pil_l.bmp", "pil_p.bmp", "pil_1.bmp", "pil_rgba.bmp"]
+    except ImportError:
+        pass
+    path = _texture_scene(tmp_path, names)
+    ref = _reference_arrays(path)
+    nat, _ = _native_arrays(path)
+    assert len(nat["textures"]) == len(names) >= 120
+    for name, (a, _), (b, _) in zip(names, nat["textures"], ref["textures"]):
+        assert a.shape == b.shape and np.array_equal(a, b), name

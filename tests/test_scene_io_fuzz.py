@@ -1,6 +1,6 @@
 """Mutation fuzzing of the native scene loaders and texture decoders under ASan + UBSan (tests/fuzz/fuzz_scene_io.cpp): seeds of
 every format the loaders read (OBJ with polygons, glTF with data: URIs, GLB, .crts, baseline / progressive / restart-marker JPEG,
-8-bit / palette-interlaced / 16-bit-interlaced PNG, RLE and colour-mapped TGA) are mutated and loaded; whatever the bytes, a load
+8-bit / palette-interlaced / 16-bit-interlaced PNG, RLE and colour-mapped TGA, bit-field and palette BMP) are mutated and loaded; whatever the bytes, a load
 ends in a scene or in an exception — never in a sanitizer report. A short run here (CRT_FUZZ_ITERS per seed, default 25); the same
 binary with 1500 iterations per seed (18 000 inputs) ran clean when the loaders were written."""
 import os
@@ -37,6 +37,8 @@ def test_mutated_files_never_break_the_loaders(built, tmp_path):
     t._write_png(str(seed / "c.png"), rng.integers(0, 65536, (9, 13, 3)), 2, 16, True, None, [0, 1, 0, 2, 0, 3], seed=2)
     t._write_tga(str(seed / "a.tga"), rng.integers(0, 256, (9, 13, 3)), 2, 24, rle=True)
     t._write_tga(str(seed / "b.tga"), rng.integers(0, 8, (9, 13, 1)), 1, 8, cmap=rng.integers(0, 256, (8, 3)), cmap_bits=24)
+    t._write_bmp(str(seed / "a.bmp"), rng.integers(0, 2 ** 16, (9, 13)), 16, header=108, masks=(0x7000, 0x0380, 0x0003, 0x8000), compression=3)
+    t._write_bmp(str(seed / "b.bmp"), rng.integers(0, 16, (9, 13)), 4, palette=rng.integers(0, 256, (16, 3)))
     t._polygon_obj(str(seed / "poly.obj"), 1, faces=40)
     os.rename(t._gltf_hierarchy(seed, "glb"), str(seed / "h.glb"))
     os.rename(t._gltf_hierarchy(seed, "datauri"), str(seed / "h.gltf"))
